@@ -1,0 +1,126 @@
+"""ctypes bindings for the CPU oracle (oracle/liboracle.so) and, when present, the reference's own
+CPU code compiled in place (oracle/_ref/libgpujpeg_refcpu.so).  Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_i16p = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
+
+
+def _build():
+    so = os.path.join(ORACLE_DIR, "liboracle.so")
+    src = os.path.join(ORACLE_DIR, "oracle.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "all"], stdout=subprocess.DEVNULL)
+    return so
+
+
+class StreamInfo(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("comp_count", C.c_int), ("restart_interval", C.c_int),
+                ("interleaved", C.c_int), ("scan_count", C.c_int), ("segment_count", C.c_int),
+                ("quality_guess", C.c_int), ("header_size", C.c_size_t), ("scan_bytes", C.c_size_t * 4)]
+
+
+lib = C.CDLL(_build())
+lib.orc_gen_random.argtypes = [_u8p, C.c_size_t, C.c_int]
+lib.orc_gen_gradient.argtypes = [_u8p, C.c_int, C.c_int, C.c_int]
+lib.orc_gen_photo.argtypes = [_u8p, C.c_int, C.c_int, C.c_int]
+lib.orc_quant_tables.argtypes = [C.c_int, _u8p, np.ctypeslib.ndpointer(np.float32), np.ctypeslib.ndpointer(np.uint16)]
+lib.orc_huff_encoder_table.argtypes = [C.c_int, C.c_int, np.ctypeslib.ndpointer(np.uint16), _u8p]
+lib.orc_preprocess_rgb444.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p, C.c_int, C.c_int]
+lib.orc_postprocess_rgb444.argtypes = [_u8p, C.c_int, C.c_int, _u8p, C.c_int, C.c_int, C.c_int]
+lib.orc_fdct_quant_plane.argtypes = [_u8p, C.c_int, C.c_int, np.ctypeslib.ndpointer(np.float32), _i16p]
+lib.orc_idct_plane.argtypes = [_i16p, C.c_int, C.c_int, np.ctypeslib.ndpointer(np.uint16), C.c_int, _u8p]
+lib.orc_idct_int_block.argtypes = [_i16p, np.ctypeslib.ndpointer(np.uint16)]
+lib.orc_huff_encode_segment.argtypes = [_i16p, C.c_int, C.c_int, _u8p]
+lib.orc_huff_encode_segment.restype = C.c_size_t
+lib.orc_write_header.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+lib.orc_write_header.restype = C.c_size_t
+lib.orc_encode_rgb.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_void_p]
+lib.orc_encode_rgb.restype = C.c_size_t
+lib.orc_decode_rgb.argtypes = [_u8p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int),
+                               C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
+lib.orc_probe.argtypes = [_u8p, C.c_size_t, C.POINTER(StreamInfo)]
+
+IDCT_INT, IDCT_FLOAT_GPUREF = 0, 1
+ZIGZAG = np.ctypeslib.as_array((C.c_uint8 * 64).in_dll(lib, "orc_zigzag_to_natural")).copy()
+
+
+def gen_image(kind, w, h, seed=12345):
+    """Synthetic RGB frames of SURVEY.md section 8d: 'random' (reference LCG), 'gradient', 'photo'."""
+    img = np.empty((h, w, 3), np.uint8)
+    if kind == "random":
+        lib.orc_gen_random(img.reshape(-1), img.size, seed)
+    elif kind == "gradient":
+        lib.orc_gen_gradient(img.reshape(-1), w, h, 3)
+    elif kind == "photo":
+        lib.orc_gen_photo(img.reshape(-1), w, h, seed)
+    elif kind == "zero":
+        img[:] = 0
+    else:
+        raise ValueError(kind)
+    return img
+
+
+def quant_tables(quality):
+    raw = np.zeros((2, 64), np.uint8)
+    fwd = np.zeros((2, 64), np.float32)
+    inv = np.zeros((2, 64), np.uint16)
+    lib.orc_quant_tables(quality, raw, fwd, inv)
+    return raw, fwd, inv
+
+
+def encode(rgb, quality=75, rst=24, interleaved=0, threads=1, want_coef=False, pad=0):
+    h, w = rgb.shape[:2]
+    rgb = np.ascontiguousarray(rgb)
+    out = np.empty(1000 + w * h * 6 + 4096, np.uint8)
+    dw, dh = (w + 7) // 8 * 8, (h + 7) // 8 * 8
+    coef = np.zeros((3, dw * dh), np.int16) if want_coef else None
+    n = lib.orc_encode_rgb(rgb.reshape(-1), w, h, pad, quality, rst, interleaved, threads, out,
+                           coef.ctypes.data if want_coef else None)
+    assert n > 0
+    jpeg = out[:n].copy()
+    return (jpeg, coef) if want_coef else jpeg
+
+
+def decode(jpeg, flavour=IDCT_INT, threads=1, want_coef=False):
+    jpeg = np.ascontiguousarray(jpeg, np.uint8)
+    w, h, c = C.c_int(), C.c_int(), C.c_int()
+    rc = lib.orc_decode_rgb(jpeg, jpeg.size, flavour, threads, None, C.byref(w), C.byref(h), C.byref(c), None)
+    assert rc == 0, "oracle could not parse stream"
+    img = np.empty((h.value, w.value, c.value), np.uint8)
+    dw, dh = (w.value + 7) // 8 * 8, (h.value + 7) // 8 * 8
+    coef = np.zeros((c.value, dw * dh), np.int16) if want_coef else None
+    rc = lib.orc_decode_rgb(jpeg, jpeg.size, flavour, threads, img.ctypes.data, C.byref(w), C.byref(h), C.byref(c),
+                            coef.ctypes.data if want_coef else None)
+    assert rc == 0, "oracle decode failed"
+    return (img, coef) if want_coef else img
+
+
+def probe(jpeg):
+    jpeg = np.ascontiguousarray(jpeg, np.uint8)
+    info = StreamInfo()
+    assert lib.orc_probe(jpeg, jpeg.size, C.byref(info)) == 0
+    return info
+
+
+# ---- the reference's own CPU code, compiled in place (optional: present when oracle/_ref was built) ----
+_REF_SO = os.path.join(ORACLE_DIR, "_ref", "libgpujpeg_refcpu.so")
+ref = None
+if os.path.exists(_REF_SO):
+    ref = C.CDLL(_REF_SO)
+    ref.ref_quant_tables.argtypes = [C.c_int, _u8p, np.ctypeslib.ndpointer(np.float32),
+                                     np.ctypeslib.ndpointer(np.uint16)]
+    ref.ref_huff_encoder_table.argtypes = [C.c_int, C.c_int, np.ctypeslib.ndpointer(np.uint32), _u8p]
+    ref.ref_encode_from_coef.argtypes = [_i16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_size_t]
+    ref.ref_encode_from_coef.restype = C.c_size_t
+    ref.ref_huff_decode.argtypes = [_u8p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    np.ctypeslib.ndpointer(np.int32), np.ctypeslib.ndpointer(np.int32),
+                                    np.ctypeslib.ndpointer(np.uint64), np.ctypeslib.ndpointer(np.uint64),
+                                    _u8p, _u8p, _i16p]
+    ref.ref_idct_block.argtypes = [_i16p, np.ctypeslib.ndpointer(np.uint16)]

@@ -1,0 +1,77 @@
+"""Differential tests: oracle restatement vs the reference's own CPU sources compiled in place
+(oracle/_ref/libgpujpeg_refcpu.so).  Skipped when that library has not been built (it needs
+/root/reference at build time; the prebuilt .so travels to the GPU box).  CPU only."""
+import numpy as np
+import pytest
+
+import _oracle as o
+from _refcpu import ref_decode_coef, ref_encode_coef, ref_idct_planes
+
+pytestmark = pytest.mark.skipif(o.ref is None, reason="oracle/_ref/libgpujpeg_refcpu.so not built")
+
+
+@pytest.mark.parametrize("q", [1, 10, 25, 50, 75, 90, 95, 100])
+def test_quant_tables(q):
+    raw, fwd, inv = o.quant_tables(q)
+    r2, f2, i2 = np.zeros_like(raw), np.zeros_like(fwd), np.zeros_like(inv)
+    assert o.ref.ref_quant_tables(q, r2, f2, i2) == 0
+    assert np.array_equal(raw, r2) and np.array_equal(inv, i2)
+    assert np.array_equal(fwd.view(np.uint32), f2.view(np.uint32)), "forward float table must be bit-identical"
+
+
+@pytest.mark.parametrize("cls,kind", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_huffman_tables(cls, kind):
+    code, size = np.zeros(256, np.uint16), np.zeros(256, np.uint8)
+    o.lib.orc_huff_encoder_table(cls, kind, code, size)
+    c2, s2 = np.zeros(256, np.uint32), np.zeros(256, np.uint8)
+    o.ref.ref_huff_encoder_table(cls, kind, c2, s2)
+    assert np.array_equal(code.astype(np.uint32), c2) and np.array_equal(size, s2)
+
+
+CASES = [("random", 1920, 1080, 75, 24, 0), ("photo", 1920, 1080, 75, 24, 0), ("random", 1119, 561, 75, 8, 0),
+         ("gradient", 640, 480, 75, 12, 0), ("zero", 256, 256, 75, 36, 0), ("random", 200, 120, 100, 36, 0),
+         ("photo", 640, 360, 30, 7, 1), ("random", 64, 64, 75, 0, 0), ("photo", 16, 8, 75, 1, 0),
+         ("random", 8, 8, 95, 24, 1)]
+
+
+@pytest.mark.parametrize("kind,w,h,q,rst,il", CASES)
+def test_encode_bytes_and_decode_coefficients(kind, w, h, q, rst, il):
+    img = o.gen_image(kind, w, h)
+    jpeg, coef = o.encode(img, q, rst, il, want_coef=True)
+    ref_jpeg = ref_encode_coef(coef, w, h, q, rst, il)
+    assert np.array_equal(jpeg, ref_jpeg), "oracle bytes != reference header writer + CPU Huffman encoder"
+    ref_coef = ref_decode_coef(jpeg, w, h, rst, il)
+    assert np.array_equal(ref_coef, coef), "reference CPU Huffman decoder must recover the encoder's coefficients"
+    _, coef_dec = o.decode(jpeg, want_coef=True)
+    assert np.array_equal(coef_dec, coef)
+
+
+@pytest.mark.parametrize("kind,q", [("random", 75), ("photo", 75), ("random", 100), ("gradient", 20)])
+def test_integer_idct_matches_gpujpeg_idct_cpu(kind, q):
+    w, h = 256, 128
+    img = o.gen_image(kind, w, h)
+    _, coef = o.encode(img, q, 8, want_coef=True)
+    planes = ref_idct_planes(coef, w, h, q)
+    _, _, inv = o.quant_tables(q)
+    for c in range(3):
+        plane = np.zeros(w * h, np.uint8)
+        o.lib.orc_idct_plane(np.ascontiguousarray(coef[c]), w, h, inv[0 if c == 0 else 1], o.IDCT_INT, plane)
+        assert np.array_equal(plane.reshape(h, w), planes[c])
+
+
+def test_idct_saturating_blocks():
+    """sparse blocks whose reconstruction overshoots [-256,255] but stays inside the reference's
+    1024-entry clip table (outside it the reference reads out of bounds, src/gpujpeg_dct_cpu.c:42-43)."""
+    rng = np.random.default_rng(7)
+    _, _, inv = o.quant_tables(50)
+    for _ in range(3000):
+        blk = np.zeros(64, np.int16)
+        idx = rng.choice(64, 6, replace=False)
+        blk[idx] = rng.integers(-10, 11, 6)
+        blk[0] = rng.integers(-24, 25)
+        if np.abs(blk.astype(np.int64) * inv[0]).sum() > 4000:
+            continue
+        a, b = blk.copy(), blk.copy()
+        o.lib.orc_idct_int_block(a, inv[0])
+        o.ref.ref_idct_block(b, inv[0])
+        assert np.array_equal(a, b)
