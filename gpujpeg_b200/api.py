@@ -1,0 +1,248 @@
+"""ctypes mirror of the libgpujpeg C API (include/gpujpeg_b200.h).
+
+Names, argument meaning and error behaviour follow the reference interface
+(libgpujpeg/gpujpeg_{common,encoder,decoder}.h): functions return 0 / -1, constructors return NULL,
+diagnostics go to stderr.  The small ``Encoder`` / ``Decoder`` classes only manage lifetimes and
+numpy <-> pointer conversion around ``gpujpeg_encoder_encode`` / ``gpujpeg_decoder_decode``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+GPUJPEG_NOERR, GPUJPEG_ERROR = 0, -1
+# enum gpujpeg_color_space
+GPUJPEG_NONE, GPUJPEG_RGB, GPUJPEG_YCBCR_BT601, GPUJPEG_YCBCR_BT601_256LVLS, GPUJPEG_YCBCR_BT709, GPUJPEG_YUV = 0, 1, 2, 3, 4, 5
+GPUJPEG_YCBCR_JPEG = GPUJPEG_YCBCR_BT601_256LVLS
+# enum gpujpeg_pixel_format
+GPUJPEG_PIXFMT_NONE, GPUJPEG_U8, GPUJPEG_444_U8_P012, GPUJPEG_444_U8_P0P1P2 = -1, 0, 1, 2
+GPUJPEG_422_U8_P1020, GPUJPEG_422_U8_P0P1P2, GPUJPEG_420_U8_P0P1P2, GPUJPEG_4444_U8_P0123 = 3, 4, 5, 6
+# enum gpujpeg_encoder_input_type / gpujpeg_decoder_output_type
+GPUJPEG_ENCODER_INPUT_IMAGE, GPUJPEG_ENCODER_INPUT_OPENGL_TEXTURE, GPUJPEG_ENCODER_INPUT_GPU_IMAGE = 0, 1, 2
+(GPUJPEG_DECODER_OUTPUT_INTERNAL_BUFFER, GPUJPEG_DECODER_OUTPUT_CUSTOM_BUFFER, GPUJPEG_DECODER_OUTPUT_OPENGL_TEXTURE,
+ GPUJPEG_DECODER_OUTPUT_CUDA_BUFFER, GPUJPEG_DECODER_OUTPUT_CUSTOM_CUDA_BUFFER) = range(5)
+RESTART_AUTO, RESTART_NONE = -1, 0
+
+
+class SamplingFactor(C.Structure):
+    _fields_ = [("horizontal", C.c_uint8), ("vertical", C.c_uint8)]
+
+
+class Parameters(C.Structure):
+    """struct gpujpeg_parameters"""
+    _fields_ = [("verbose", C.c_int), ("perf_stats", C.c_int), ("quality", C.c_int), ("restart_interval", C.c_int),
+                ("interleaved", C.c_int), ("segment_info", C.c_int), ("comp_count", C.c_int),
+                ("sampling_factor", SamplingFactor * 4), ("color_space_internal", C.c_int)]
+
+
+class ImageParameters(C.Structure):
+    """struct gpujpeg_image_parameters"""
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("color_space", C.c_int), ("pixel_format", C.c_int),
+                ("width_padding", C.c_int)]
+
+
+class EncoderInput(C.Structure):
+    _fields_ = [("type", C.c_int), ("image", C.c_void_p), ("texture", C.c_void_p)]
+
+
+class DecoderOutput(C.Structure):
+    _fields_ = [("type", C.c_int), ("data", C.c_void_p), ("data_size", C.c_size_t), ("param_image", ImageParameters),
+                ("texture", C.c_void_p), ("metadata", C.c_void_p)]
+
+
+class DurationStats(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("duration_memory_to", "duration_memory_from", "duration_memory_map",
+                                          "duration_memory_unmap", "duration_preprocessor", "duration_dct_quantization",
+                                          "duration_huffman_coder", "duration_stream", "duration_in_gpu")]
+
+
+class GpuJpegError(RuntimeError):
+    pass
+
+
+def library_path():
+    return _build.build_library()
+
+
+def _load():
+    path = library_path()
+    lib_ = C.CDLL(path)
+    vp, ci, cs = C.c_void_p, C.c_int, C.c_size_t
+    sigs = {
+        "gpujpeg_version": (ci, []),
+        "gpujpeg_version_to_string": (C.c_char_p, [ci]),
+        "gpujpeg_init_device": (ci, [ci, ci]),
+        "gpujpeg_set_default_parameters": (None, [C.POINTER(Parameters)]),
+        "gpujpeg_image_set_default_parameters": (None, [C.POINTER(ImageParameters)]),
+        "gpujpeg_image_calculate_size": (cs, [C.POINTER(ImageParameters)]),
+        "gpujpeg_image_load_from_file": (ci, [C.c_char_p, C.POINTER(vp), C.POINTER(cs)]),
+        "gpujpeg_image_destroy": (ci, [vp]),
+        "gpujpeg_encoder_create": (vp, [vp]),
+        "gpujpeg_encoder_destroy": (ci, [vp]),
+        "gpujpeg_encoder_encode": (ci, [vp, C.POINTER(Parameters), C.POINTER(ImageParameters), C.POINTER(EncoderInput),
+                                        C.POINTER(vp), C.POINTER(cs)]),
+        "gpujpeg_encoder_set_option": (ci, [vp, C.c_char_p, C.c_char_p]),
+        "gpujpeg_encoder_get_stats": (ci, [vp, C.POINTER(DurationStats)]),
+        "gpujpeg_encoder_suggest_restart_interval": (ci, [C.POINTER(ImageParameters), C.c_uint32, C.c_bool, ci]),
+        "gpujpeg_decoder_create": (vp, [vp]),
+        "gpujpeg_decoder_destroy": (ci, [vp]),
+        "gpujpeg_decoder_decode": (ci, [vp, vp, cs, C.POINTER(DecoderOutput)]),
+        "gpujpeg_decoder_set_option": (ci, [vp, C.c_char_p, C.c_char_p]),
+        "gpujpeg_decoder_set_output_format": (None, [vp, ci, ci]),
+        "gpujpeg_decoder_get_stats": (ci, [vp, C.POINTER(DurationStats)]),
+        "gpujpeg_decoder_get_image_info": (ci, [vp, cs, C.POINTER(ImageParameters), C.POINTER(Parameters), C.POINTER(ci)]),
+        "gpujpegx_encoder_get_coefficients": (ci, [vp, vp, cs]),
+        "gpujpegx_decoder_get_coefficients": (ci, [vp, vp, cs]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib_, name)
+        fn.restype, fn.argtypes = res, args
+    return lib_
+
+
+lib = _load()
+
+
+def version():
+    return lib.gpujpeg_version_to_string(lib.gpujpeg_version()).decode()
+
+
+def default_parameters(quality=75, restart_interval=RESTART_AUTO, interleaved=0):
+    p = Parameters()
+    lib.gpujpeg_set_default_parameters(C.byref(p))
+    p.quality, p.restart_interval, p.interleaved = quality, restart_interval, interleaved
+    return p
+
+
+def image_parameters(width, height, width_padding=0):
+    pi = ImageParameters()
+    lib.gpujpeg_image_set_default_parameters(C.byref(pi))
+    pi.width, pi.height, pi.width_padding = width, height, width_padding
+    return pi
+
+
+def _ptr(x):
+    """host numpy array, torch tensor (host or device) or raw integer address -> (address, is_device)"""
+    if isinstance(x, int):
+        return x, None
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        return x.ctypes.data, False
+    if hasattr(x, "data_ptr"):
+        assert x.is_contiguous()
+        return x.data_ptr(), bool(x.is_cuda)
+    raise TypeError(type(x))
+
+
+class Encoder:
+    """gpujpeg_encoder_create / gpujpeg_encoder_encode / gpujpeg_encoder_destroy"""
+
+    def __init__(self, stream=0, pinned_output=False):
+        self._h = lib.gpujpeg_encoder_create(C.c_void_p(stream))
+        if not self._h:
+            raise GpuJpegError("gpujpeg_encoder_create failed (no CUDA device?)")
+        if pinned_output:
+            self.set_option("enc_opt_out", "enc_out_val_pinned")
+
+    def set_option(self, key, val):
+        if lib.gpujpeg_encoder_set_option(self._h, key.encode(), val.encode()) != 0:
+            raise GpuJpegError("gpujpeg_encoder_set_option(%s, %s) failed" % (key, val))
+
+    def encode_raw(self, image, param, param_image, device=None):
+        """returns (address, size) of the encoder-owned JPEG buffer (valid until the next call)"""
+        addr, is_dev = _ptr(image)
+        if device is not None:
+            is_dev = device
+        inp = EncoderInput(GPUJPEG_ENCODER_INPUT_GPU_IMAGE if is_dev else GPUJPEG_ENCODER_INPUT_IMAGE, addr, None)
+        out, size = C.c_void_p(), C.c_size_t()
+        rc = lib.gpujpeg_encoder_encode(self._h, C.byref(param), C.byref(param_image), C.byref(inp), C.byref(out),
+                                        C.byref(size))
+        if rc != 0:
+            raise GpuJpegError("gpujpeg_encoder_encode failed (%d)" % rc)
+        return out.value, size.value
+
+    def encode(self, image, quality=75, restart_interval=RESTART_AUTO, interleaved=0, width=None, height=None,
+               width_padding=0, verbose=0):
+        """image: HxWx3 uint8 numpy array / torch tensor (host or cuda).  Returns the JPEG as numpy uint8 (a copy)."""
+        if width is None:
+            height, width = image.shape[0], image.shape[1]
+        p = default_parameters(quality, restart_interval, interleaved)
+        p.verbose = verbose
+        addr, size = self.encode_raw(image, p, image_parameters(width, height, width_padding))
+        return np.ctypeslib.as_array((C.c_uint8 * size).from_address(addr)).copy()
+
+    def coefficients(self, width, height):
+        """quantised coefficients of the last frame: (3, blocks*64) int16, natural order (parity tests)"""
+        dw, dh = (width + 7) // 8 * 8, (height + 7) // 8 * 8
+        out = np.empty((3, dw * dh), np.int16)
+        if lib.gpujpegx_encoder_get_coefficients(self._h, out.ctypes.data, out.size) != 0:
+            raise GpuJpegError("gpujpegx_encoder_get_coefficients failed")
+        return out
+
+    def stats(self):
+        s = DurationStats()
+        return s if lib.gpujpeg_encoder_get_stats(self._h, C.byref(s)) == 0 else None
+
+    def close(self):
+        if self._h:
+            lib.gpujpeg_encoder_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+class Decoder:
+    """gpujpeg_decoder_create / gpujpeg_decoder_decode / gpujpeg_decoder_destroy"""
+
+    def __init__(self, stream=0, idct="int"):
+        self._h = lib.gpujpeg_decoder_create(C.c_void_p(stream))
+        if not self._h:
+            raise GpuJpegError("gpujpeg_decoder_create failed (no CUDA device?)")
+        if idct != "int":
+            self.set_option("dec_opt_idct", idct)
+
+    def set_option(self, key, val):
+        if lib.gpujpeg_decoder_set_option(self._h, key.encode(), val.encode()) != 0:
+            raise GpuJpegError("gpujpeg_decoder_set_option(%s, %s) failed" % (key, val))
+
+    def decode_raw(self, jpeg_addr, jpeg_size, out_type=GPUJPEG_DECODER_OUTPUT_INTERNAL_BUFFER, out_addr=None):
+        out = DecoderOutput()
+        out.type = out_type
+        out.data = out_addr
+        rc = lib.gpujpeg_decoder_decode(self._h, C.c_void_p(jpeg_addr), jpeg_size, C.byref(out))
+        if rc != 0:
+            raise GpuJpegError("gpujpeg_decoder_decode failed (%d)" % rc)
+        return out
+
+    def decode(self, jpeg, out=None):
+        """jpeg: uint8 numpy array.  out: optional HxWx3 destination (numpy = custom host buffer, cuda tensor =
+        custom CUDA buffer).  Returns an HxWx3 uint8 numpy array (a copy) or `out`."""
+        jpeg = np.ascontiguousarray(jpeg, np.uint8)
+        if out is None:
+            o = self.decode_raw(jpeg.ctypes.data, jpeg.size)
+            w, h = o.param_image.width, o.param_image.height
+            return np.ctypeslib.as_array((C.c_uint8 * o.data_size).from_address(o.data)).reshape(h, w, 3).copy()
+        addr, is_dev = _ptr(out)
+        self.decode_raw(jpeg.ctypes.data, jpeg.size,
+                        GPUJPEG_DECODER_OUTPUT_CUSTOM_CUDA_BUFFER if is_dev else GPUJPEG_DECODER_OUTPUT_CUSTOM_BUFFER, addr)
+        return out
+
+    def coefficients(self, width, height):
+        dw, dh = (width + 7) // 8 * 8, (height + 7) // 8 * 8
+        out = np.empty((3, dw * dh), np.int16)
+        if lib.gpujpegx_decoder_get_coefficients(self._h, out.ctypes.data, out.size) != 0:
+            raise GpuJpegError("gpujpegx_decoder_get_coefficients failed")
+        return out
+
+    def stats(self):
+        s = DurationStats()
+        return s if lib.gpujpeg_decoder_get_stats(self._h, C.byref(s)) == 0 else None
+
+    def close(self):
+        if self._h:
+            lib.gpujpeg_decoder_destroy(self._h)
+            self._h = None
+
+    __del__ = close

@@ -1,0 +1,428 @@
+/*
+ * gj_codestream.c -- frame geometry, codestream writer and codestream reader.  Host C; these stay
+ * on the host by design (north_star), only the entropy-coded payload is produced/consumed on the GPU.
+ *
+ *   geometry : restates what the kernels index by        [ref: src/gpujpeg_common.c:676-865]
+ *   writer   : SOI/APP0/DQT/SOF0/DHT/DRI/COM and SOS     [ref: src/gpujpeg_writer.c:120-156, 282-518, 600-658]
+ *   reader   : marker walk + RST split                   [ref: src/gpujpeg_reader.c:681-1155, 1256-1382, 1619-1736]
+ */
+#include <stdlib.h>
+#include <string.h>
+
+#include "gj_internal.h"
+
+/* ------------------------------------------------------------------------------------------- */
+/* geometry                                                                                      */
+
+int gj_geometry_init(struct gj_geometry* g, const struct gpujpeg_parameters* param,
+                     const struct gpujpeg_image_parameters* pi)
+{
+    memset(g, 0, sizeof *g);
+    g->width = pi->width;
+    g->height = pi->height;
+    g->comp_count = param->comp_count;
+    g->pitch = 3 * pi->width + pi->width_padding;
+    g->data_width = (pi->width + 7) / 8 * 8;
+    g->data_height = (pi->height + 7) / 8 * 8;
+    g->bcx = g->data_width / 8;
+    g->bcy = g->data_height / 8;
+    g->nblk = g->bcx * g->bcy;
+    g->interleaved = param->interleaved && param->comp_count > 1;
+    g->restart_interval = param->restart_interval;
+    g->seg_mcu = param->restart_interval > 0 ? param->restart_interval : g->nblk;
+    g->scan_count = g->interleaved ? 1 : g->comp_count;
+    g->comps_per_scan = g->interleaved ? g->comp_count : 1;
+    g->seg_per_scan = (g->nblk + g->seg_mcu - 1) / g->seg_mcu;
+    g->seg_count = g->scan_count * g->seg_per_scan;
+    g->raw_size = (size_t)g->pitch * pi->height;
+    g->coef_count = (size_t)g->comp_count * g->nblk * 64;
+    /* worst case per 8x8 block: 64 x (16-bit code + 11 value bits) < 208 bytes, doubled by stuffing */
+    g->slot_stride = ((size_t)g->seg_mcu * g->comps_per_scan * 416 + 2 + 127) / 128 * 128;
+    /* same budget as the reference's output buffer [ref: src/gpujpeg_writer.c:63-89] */
+    g->stream_cap = 4096 + (size_t)pi->width * pi->height * g->comp_count * 2;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* writer                                                                                        */
+
+static uint8_t* w8(uint8_t* p, int v) { *p++ = (uint8_t)v; return p; }
+static uint8_t* w16(uint8_t* p, int v) { *p++ = (uint8_t)(v >> 8); *p++ = (uint8_t)v; return p; }
+static uint8_t* wmark(uint8_t* p, int m) { *p++ = 0xFF; *p++ = (uint8_t)m; return p; }
+
+static int comp_is_luma(const struct gpujpeg_parameters* param, int c)
+{
+    /* [ref: src/gpujpeg_common.c:689-692] */
+    return param->color_space_internal == GPUJPEG_RGB || c == 0 || c == 3;
+}
+static int comp_id(const struct gpujpeg_parameters* param, int c)
+{
+    /* [ref: src/gpujpeg_writer.c:305-313] */
+    static const char rgb_ids[4] = {'R', 'G', 'B', 'A'};
+    return param->color_space_internal == GPUJPEG_RGB ? rgb_ids[c] : c + 1;
+}
+
+/* Everything before the first SOS.  Only the JFIF flavour (YCbCr-JPEG internal colour space, no
+ * orientation metadata) and the Adobe flavour (RGB internal) are produced; SPIFF/Exif are outside
+ * the hot path.  [ref: src/gpujpeg_writer.c:456-518] */
+size_t gj_write_header(uint8_t* out, const struct gpujpeg_parameters* param,
+                       const struct gpujpeg_image_parameters* pi, const uint8_t raw_q[2][64],
+                       const struct gj_huff_spec spec[2][2])
+{
+    uint8_t* p = out;
+    p = wmark(p, 0xD8);
+    if ( param->color_space_internal == GPUJPEG_RGB ) {
+        /* Adobe APP14, transform 0 [ref: src/gpujpeg_writer.c:258-276] */
+        p = wmark(p, 0xEE);
+        p = w16(p, 14);
+        memcpy(p, "Adobe", 5);
+        p += 5;
+        p = w16(p, 100);
+        p = w16(p, 0);
+        p = w16(p, 0);
+        p = w8(p, 0);
+    }
+    else {
+        /* JFIF 1.01, 300x300 dpi, no thumbnail [ref: src/gpujpeg_writer.c:120-156] */
+        p = wmark(p, 0xE0);
+        p = w16(p, 16);
+        memcpy(p, "JFIF", 5);
+        p += 5;
+        p = w8(p, 1);
+        p = w8(p, 1);
+        p = w8(p, 1);
+        p = w16(p, 300);
+        p = w16(p, 300);
+        p = w8(p, 0);
+        p = w8(p, 0);
+    }
+    unsigned emitted = 0;
+    for ( int c = 0; c < param->comp_count; c++ ) {
+        const int t = comp_is_luma(param, c) ? 0 : 1;
+        if ( emitted & (1u << t) ) continue;
+        emitted |= 1u << t;
+        p = wmark(p, 0xDB);
+        p = w16(p, 67);
+        p = w8(p, t);
+        memcpy(p, raw_q[t], 64);
+        p += 64;
+    }
+    p = wmark(p, 0xC0);
+    p = w16(p, 8 + 3 * param->comp_count);
+    p = w8(p, 8);
+    p = w16(p, pi->height);
+    p = w16(p, pi->width);
+    p = w8(p, param->comp_count);
+    for ( int c = 0; c < param->comp_count; c++ ) {
+        p = w8(p, comp_id(param, c));
+        p = w8(p, (param->sampling_factor[c].horizontal << 4) + param->sampling_factor[c].vertical);
+        p = w8(p, comp_is_luma(param, c) ? 0 : 1);
+    }
+    emitted = 0;
+    for ( int c = 0; c < param->comp_count; c++ ) {
+        const int t = comp_is_luma(param, c) ? 0 : 1;
+        if ( emitted & (1u << t) ) continue;
+        emitted |= 1u << t;
+        for ( int kind = 0; kind < 2; kind++ ) {
+            const struct gj_huff_spec* s = &spec[t][kind];
+            p = wmark(p, 0xC4);
+            p = w16(p, s->nvals + 2 + 1 + 16);
+            p = w8(p, (kind << 4) | t);
+            memcpy(p, s->bits + 1, 16);
+            p += 16;
+            memcpy(p, s->vals, s->nvals);
+            p += s->nvals;
+        }
+    }
+    p = wmark(p, 0xDD);
+    p = w16(p, 4);
+    p = w16(p, param->restart_interval);
+    char com[48];
+    const int q = param->quality < 1 ? 1 : param->quality > 100 ? 100 : param->quality;
+    const int n = snprintf(com, sizeof com, "CREATOR: GPUJPEG, quality = %d", q);
+    p = wmark(p, 0xFE);
+    p = w16(p, 2 + n + 1);
+    memcpy(p, com, (size_t)n + 1);
+    p += n + 1;
+    return (size_t)(p - out);
+}
+
+/* [ref: src/gpujpeg_writer.c:600-658] */
+size_t gj_write_sos(uint8_t* out, const struct gpujpeg_parameters* param, int scan_index)
+{
+    uint8_t* p = out;
+    p = wmark(p, 0xDA);
+    if ( param->interleaved && param->comp_count > 1 ) {
+        p = w16(p, 6 + 2 * param->comp_count);
+        p = w8(p, param->comp_count);
+        for ( int c = 0; c < param->comp_count; c++ ) {
+            p = w8(p, comp_id(param, c));
+            p = w8(p, comp_is_luma(param, c) ? 0x00 : 0x11);
+        }
+    }
+    else {
+        p = w16(p, 8);
+        p = w8(p, 1);
+        p = w8(p, comp_id(param, scan_index));
+        p = w8(p, comp_is_luma(param, scan_index) ? 0x00 : 0x11);
+    }
+    p = w8(p, 0);
+    p = w8(p, 0x3F);
+    p = w8(p, 0);
+    return (size_t)(p - out);
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* reader                                                                                        */
+
+static int r16(const uint8_t* p) { return (p[0] << 8) | p[1]; }
+
+/* find the end of a scan's entropy-coded data: first 0xFF followed by something that is neither a
+ * stuffed zero nor RSTn nor a fill byte.  memchr-driven like the reference
+ * [ref: src/gpujpeg_reader.c:1060-1066]. */
+static size_t scan_end(const uint8_t* d, size_t b, size_t size)
+{
+    size_t i = b;
+    while ( i < size ) {
+        const uint8_t* f = (const uint8_t*)memchr(d + i, 0xFF, size - i);
+        if ( !f || (size_t)(f - d) + 1 >= size ) return size;
+        i = (size_t)(f - d);
+        const int m = d[i + 1];
+        if ( m == 0 || (m >= 0xD0 && m <= 0xD7) ) {
+            i += 2;
+            continue;
+        }
+        if ( m == 0xFF ) {
+            i += 1;
+            continue;
+        }
+        return i;
+    }
+    return size;
+}
+
+int gj_reader_parse(const uint8_t* d, size_t size, struct gj_stream* s, int verbose)
+{
+    memset(s, 0, sizeof *s);
+    s->color_space = GPUJPEG_YCBCR_BT601_256LVLS; /* JFIF default */
+    s->header_type = GPUJPEG_HEADER_DEFAULT;
+    if ( size < 4 || d[0] != 0xFF || d[1] != 0xD8 ) {
+        GJ_ERR("JPEG data should begin with SOI marker!\n");
+        return -1;
+    }
+    size_t i = 2;
+    int seen_eoi = 0, adobe_transform = -1;
+    while ( i + 2 <= size ) {
+        if ( d[i] != 0xFF ) {
+            GJ_ERR("Failed to read marker from JPEG data at offset %zu!\n", i);
+            return -1;
+        }
+        const int m = d[i + 1];
+        if ( m == 0xFF ) {
+            i++;
+            continue;
+        }
+        if ( m == 0xD9 ) {
+            seen_eoi = 1;
+            break;
+        }
+        if ( m == 0xD8 || m == 0x01 || (m >= 0xD0 && m <= 0xD7) ) { /* standalone markers */
+            i += 2;
+            continue;
+        }
+        if ( i + 4 > size ) break;
+        const int len = r16(d + i + 2);
+        if ( len < 2 || i + 2 + (size_t)len > size ) {
+            GJ_ERR("JPEG marker 0x%X has invalid length %d!\n", m, len);
+            return -1;
+        }
+        const uint8_t* b = d + i + 4;
+        const int n = len - 2;
+        switch ( m ) {
+            case 0xE0:
+                if ( n >= 5 && memcmp(b, "JFIF", 5) == 0 ) s->header_type = GPUJPEG_HEADER_JFIF;
+                break;
+            case 0xEE:
+                if ( n >= 12 && memcmp(b, "Adobe", 5) == 0 ) {
+                    s->header_type = GPUJPEG_HEADER_ADOBE;
+                    adobe_transform = b[11];
+                }
+                break;
+            case 0xFE:
+                s->comment = (const char*)b;
+                break;
+            case 0xDB: { /* [ref: src/gpujpeg_reader.c:681-730] 8-bit tables only */
+                int off = 0;
+                while ( off < n ) {
+                    const int pq = b[off] >> 4, tq = b[off] & 15;
+                    if ( pq != 0 ) {
+                        GJ_ERR("16-bit quantization tables are not supported!\n");
+                        return -1;
+                    }
+                    if ( tq > 3 || off + 65 > n ) {
+                        GJ_ERR("Invalid DQT marker!\n");
+                        return -1;
+                    }
+                    memcpy(s->qt[tq], b + off + 1, 64);
+                    s->have_qt[tq] = 1;
+                    off += 65;
+                }
+                break;
+            }
+            case 0xC0: /* [ref: src/gpujpeg_reader.c:806-886] */
+                if ( n < 6 || b[0] != 8 ) {
+                    GJ_ERR("SOF0 marker precision should be 8 but %d was presented!\n", n >= 1 ? b[0] : -1);
+                    return -1;
+                }
+                s->height = r16(b + 1);
+                s->width = r16(b + 3);
+                s->comp_count = b[5];
+                if ( s->comp_count < 1 || s->comp_count > GJ_MAX_COMP || n < 6 + 3 * s->comp_count ) {
+                    GJ_ERR("SOF0 marker component count %d is not supported!\n", s->comp_count);
+                    return -1;
+                }
+                for ( int c = 0; c < s->comp_count; c++ ) {
+                    s->comp_id[c] = b[6 + 3 * c];
+                    s->comp_hv[c] = b[7 + 3 * c];
+                    s->comp_tq[c] = b[8 + 3 * c];
+                    if ( s->comp_tq[c] > 3 ) return -1;
+                }
+                break;
+            case 0xC1: case 0xC2: case 0xC3: case 0xC5: case 0xC6: case 0xC7:
+            case 0xC9: case 0xCA: case 0xCB: case 0xCD: case 0xCE: case 0xCF:
+                GJ_ERR("Unsupported JPEG process (SOF marker 0x%X): only baseline is supported!\n", m);
+                return -1;
+            case 0xC4: { /* [ref: src/gpujpeg_reader.c:920-986] */
+                int off = 0;
+                while ( off < n ) {
+                    if ( off + 17 > n ) return -1;
+                    const int tc = b[off] >> 4, th = b[off] & 15;
+                    if ( tc > 1 || th > 3 ) {
+                        GJ_ERR("DHT marker index should be 0-3 and class 0-1!\n");
+                        return -1;
+                    }
+                    struct gj_huff_spec* h = &s->huff[tc][th];
+                    memset(h, 0, sizeof *h);
+                    int cnt = 0;
+                    for ( int k = 1; k <= 16; k++ ) {
+                        h->bits[k] = b[off + k];
+                        cnt += b[off + k];
+                    }
+                    if ( cnt > 256 || off + 17 + cnt > n ) {
+                        GJ_ERR("DHT marker has invalid symbol count %d!\n", cnt);
+                        return -1;
+                    }
+                    memcpy(h->vals, b + off + 17, (size_t)cnt);
+                    h->nvals = cnt;
+                    s->have_huff[tc][th] = 1;
+                    off += 17 + cnt;
+                }
+                break;
+            }
+            case 0xDD: /* [ref: src/gpujpeg_reader.c:996-1027] */
+                if ( n < 2 ) return -1;
+                s->restart_interval = r16(b);
+                break;
+            case 0xDA: { /* [ref: src/gpujpeg_reader.c:1256-1382] */
+                if ( s->comp_count == 0 ) {
+                    GJ_ERR("SOS marker before SOF0!\n");
+                    return -1;
+                }
+                if ( s->scan_count >= GJ_MAX_COMP ) {
+                    GJ_ERR("Too many scans!\n");
+                    return -1;
+                }
+                if ( s->scan_count == 0 ) s->header_size = i;
+                struct gj_scan_info* sc = &s->scan[s->scan_count++];
+                sc->ncomp = b[0];
+                if ( sc->ncomp < 1 || sc->ncomp > s->comp_count || n < 1 + 2 * sc->ncomp + 3 ) return -1;
+                for ( int k = 0; k < sc->ncomp; k++ ) {
+                    int idx = -1;
+                    for ( int c = 0; c < s->comp_count; c++ )
+                        if ( s->comp_id[c] == b[1 + 2 * k] ) idx = c;
+                    if ( idx < 0 ) {
+                        GJ_ERR("SOS marker refers to unknown component id %d!\n", b[1 + 2 * k]);
+                        return -1;
+                    }
+                    sc->comp[k] = idx;
+                    sc->td[k] = b[2 + 2 * k] >> 4;
+                    sc->ta[k] = b[2 + 2 * k] & 15;
+                    if ( sc->td[k] > 3 || sc->ta[k] > 3 ) return -1;
+                }
+                sc->begin = i + 2 + (size_t)len;
+                sc->end = scan_end(d, sc->begin, size);
+                i = sc->end;
+                continue;
+            }
+            default:
+                break; /* APPn and anything else with a length: skipped */
+        }
+        i += 2 + (size_t)len;
+    }
+    (void)seen_eoi;
+    if ( s->scan_count == 0 || s->width == 0 || s->height == 0 ) {
+        GJ_ERR("JPEG data contains no image!\n");
+        return -1;
+    }
+    /* colour space detection subset [ref: src/gpujpeg_reader.c:264-640]: Adobe transform 0 or
+     * component ids 'R','G','B' => RGB; everything else => YCbCr JPEG (full range BT.601) */
+    if ( s->comp_count == 3 &&
+         (adobe_transform == 0 || (s->comp_id[0] == 'R' && s->comp_id[1] == 'G' && s->comp_id[2] == 'B')) )
+        s->color_space = GPUJPEG_RGB;
+    s->interleaved = s->scan_count == 1 && s->comp_count > 1;
+    GJ_DEBUG(verbose, "parsed %dx%d, %d comps, %d scans, rst %d\n", s->width, s->height, s->comp_count,
+             s->scan_count, s->restart_interval);
+    return 0;
+}
+
+/* Split every scan at its RSTn markers.  Offsets/lengths describe the stuffed entropy bytes inside
+ * the original file, so the payload is uploaded once, untouched -- no per-segment host memcpy as in
+ * [ref: src/gpujpeg_reader.c:1107-1112].  Returns total segment count or -1. */
+int gj_reader_split(const uint8_t* d, struct gj_stream* s, uint32_t* seg_off, uint32_t* seg_len, int max_segments)
+{
+    int n = 0;
+    for ( int k = 0; k < s->scan_count; k++ ) {
+        struct gj_scan_info* sc = &s->scan[k];
+        sc->first_segment = n;
+        size_t start = sc->begin, i = sc->begin;
+        const size_t e = sc->end;
+        int expected = 0;
+        while ( i < e ) {
+            const uint8_t* f = (const uint8_t*)memchr(d + i, 0xFF, e - i);
+            if ( !f || (size_t)(f - d) + 1 >= e ) break;
+            i = (size_t)(f - d);
+            const int m = d[i + 1];
+            if ( m >= 0xD0 && m <= 0xD7 ) {
+                if ( m != 0xD0 + expected ) {
+                    /* the reference tries to resynchronise [ref: src/gpujpeg_reader.c:1071-1105];
+                     * here a broken restart sequence is reported, not repaired */
+                    GJ_ERR("Expected marker 0x%X but 0x%X was presented!\n", 0xD0 + expected, m);
+                    return -1;
+                }
+                expected = (expected + 1) & 7;
+                if ( n >= max_segments ) return -1;
+                seg_off[n] = (uint32_t)start;
+                seg_len[n] = (uint32_t)(i - start);
+                n++;
+                start = i + 2;
+                i += 2;
+            }
+            else if ( m == 0xFF ) {
+                i += 1;
+            }
+            else {
+                i += 2;
+            }
+        }
+        if ( e > start || n == sc->first_segment ) {
+            if ( n >= max_segments ) return -1;
+            seg_off[n] = (uint32_t)start;
+            seg_len[n] = (uint32_t)(e - start);
+            n++;
+        }
+        /* FFmpeg writes an empty segment after the last RST [ref: src/gpujpeg_reader.c:1131-1134]:
+         * the `e > start` test above already drops it */
+        sc->segment_count = n - sc->first_segment;
+    }
+    return n;
+}

@@ -1,0 +1,534 @@
+/*
+ * gj_decoder.c -- the public decoder API on top of the sm_100a stage launchers.  Host C.
+ *
+ * Contract of the reference orchestrator (src/gpujpeg_decoder.c:94-469): lazily (re)initialises
+ * from the stream, one CUDA stream, blocks until the pixels are where the output descriptor says.
+ * Pipeline of this build:
+ *
+ *     host reader: marker walk + RST split (offsets only; the file is uploaded ONCE, untouched,
+ *                  instead of being re-packed segment by segment, src/gpujpeg_reader.c:1107-1112)
+ *     H2D file bytes + segment table
+ *       -> K3 Huffman decode (always on the GPU: no "fewer than 32 segments => CPU" fallback,
+ *          src/gpujpeg_decoder.c:254-286)
+ *       -> K4 dequant + IDCT + colour transform + interleave (one launch)
+ *     D2H pixels (unless a device output was requested)
+ *
+ * Supported: baseline 8-bit, 3 components 4:4:4, YCbCr-JPEG -> GPUJPEG_RGB / GPUJPEG_444_U8_P012,
+ * interleaved or not, any restart interval, any DHT/DQT tables with ids 0..3.
+ */
+#include <stdlib.h>
+#include <string.h>
+
+#include "gj_internal.h"
+
+struct gpujpeg_decoder {
+    gj_stream_t stream;
+    int device;
+    int verbose, perf_stats;
+    struct gpujpeg_parameters param;
+    struct gpujpeg_image_parameters param_image;
+    struct gj_geometry geo;
+    int initialised;
+    enum gpujpeg_pixel_format req_pixel_format;
+    enum gpujpeg_color_space req_color_space;
+    int idct_flavour;
+    struct gpujpeg_image_metadata metadata;
+
+    struct gj_dev_dec_tables h_tab, h_tab_prev;
+    struct gj_dev_dec_tables* d_tab;
+    int tab_valid;
+
+    uint8_t* d_file; size_t d_file_size;
+    uint32_t* d_seg; size_t d_seg_size;      /* offsets then lengths */
+    uint32_t* h_seg; size_t h_seg_size;      /* pinned; offsets then lengths */
+    int16_t* d_coef; size_t d_coef_size;
+    uint8_t* d_raw; size_t d_raw_size;
+    uint8_t* h_raw; size_t h_raw_size;       /* pinned, INTERNAL_BUFFER output */
+
+    struct gj_timer t_to, t_from, t_huff, t_dct, t_gpu;
+    int timers_ok;
+    struct gpujpeg_duration_stats stats;
+    int stats_valid;
+};
+
+/* ---- output descriptor helpers [ref: src/gpujpeg_decoder.c:44-92] ---- */
+void gpujpeg_decoder_output_set_default(struct gpujpeg_decoder_output* output)
+{
+    memset(output, 0, sizeof *output);
+    output->type = GPUJPEG_DECODER_OUTPUT_INTERNAL_BUFFER;
+}
+void gpujpeg_decoder_output_set_custom(struct gpujpeg_decoder_output* output, uint8_t* custom_buffer)
+{
+    memset(output, 0, sizeof *output);
+    output->type = GPUJPEG_DECODER_OUTPUT_CUSTOM_BUFFER;
+    output->data = custom_buffer;
+}
+void gpujpeg_decoder_output_set_texture(struct gpujpeg_decoder_output* output, struct gpujpeg_opengl_texture* texture)
+{
+    memset(output, 0, sizeof *output);
+    output->type = GPUJPEG_DECODER_OUTPUT_OPENGL_TEXTURE;
+    output->texture = texture;
+}
+void gpujpeg_decoder_output_set_cuda_buffer(struct gpujpeg_decoder_output* output)
+{
+    memset(output, 0, sizeof *output);
+    output->type = GPUJPEG_DECODER_OUTPUT_CUDA_BUFFER;
+}
+void gpujpeg_decoder_output_set_custom_cuda(struct gpujpeg_decoder_output* output, uint8_t* d_custom_buffer)
+{
+    memset(output, 0, sizeof *output);
+    output->type = GPUJPEG_DECODER_OUTPUT_CUSTOM_CUDA_BUFFER;
+    output->data = d_custom_buffer;
+}
+
+struct gpujpeg_decoder_init_parameters gpujpeg_decoder_default_init_parameters(void)
+{
+    struct gpujpeg_decoder_init_parameters p;
+    memset(&p, 0, sizeof p);
+    return p;
+}
+
+/* [ref: src/gpujpeg_decoder.c:94-181] */
+struct gpujpeg_decoder* gpujpeg_decoder_create_with_params(const struct gpujpeg_decoder_init_parameters* params)
+{
+    struct gpujpeg_decoder* d = (struct gpujpeg_decoder*)calloc(1, sizeof *d);
+    if ( !d ) return NULL;
+    d->stream = (gj_stream_t)params->stream;
+    d->verbose = params->verbose;
+    d->perf_stats = params->perf_stats;
+    d->device = gj_cuda_get_device();
+    d->req_pixel_format = GPUJPEG_PIXFMT_AUTODETECT;
+    d->req_color_space = GPUJPEG_CS_DEFAULT;
+    if ( d->device < 0 || gj_cuda_malloc((void**)&d->d_tab, sizeof *d->d_tab) ) {
+        GJ_ERR("Decoder allocation failed: %s\n", gj_cuda_last_error());
+        free(d);
+        return NULL;
+    }
+    d->timers_ok = !(gj_timer_create(&d->t_to) || gj_timer_create(&d->t_from) || gj_timer_create(&d->t_huff) ||
+                     gj_timer_create(&d->t_dct) || gj_timer_create(&d->t_gpu));
+    return d;
+}
+
+struct gpujpeg_decoder* gpujpeg_decoder_create(cudaStream_t stream)
+{
+    struct gpujpeg_decoder_init_parameters p = gpujpeg_decoder_default_init_parameters();
+    p.stream = stream;
+    return gpujpeg_decoder_create_with_params(&p);
+}
+
+int gpujpeg_decoder_destroy(struct gpujpeg_decoder* d)
+{
+    if ( !d ) return -1;
+    gj_cuda_free(d->d_tab);
+    gj_cuda_free(d->d_file);
+    gj_cuda_free(d->d_seg);
+    gj_cuda_free_host(d->h_seg);
+    gj_cuda_free(d->d_coef);
+    gj_cuda_free(d->d_raw);
+    gj_cuda_free_host(d->h_raw);
+    gj_timer_destroy(&d->t_to);
+    gj_timer_destroy(&d->t_from);
+    gj_timer_destroy(&d->t_huff);
+    gj_timer_destroy(&d->t_dct);
+    gj_timer_destroy(&d->t_gpu);
+    free(d);
+    return 0;
+}
+
+static int grow_dev(void** p, size_t* have, size_t want)
+{
+    if ( *have >= want ) return 0;
+    gj_cuda_free(*p);
+    *p = NULL;
+    *have = 0;
+    if ( gj_cuda_malloc(p, want) ) return -1;
+    *have = want;
+    return 0;
+}
+static int grow_host(void** p, size_t* have, size_t want)
+{
+    if ( *have >= want ) return 0;
+    gj_cuda_free_host(*p);
+    *p = NULL;
+    *have = 0;
+    if ( gj_cuda_malloc_host(p, want) ) return -1;
+    *have = want;
+    return 0;
+}
+
+/* [ref: src/gpujpeg_decoder.c:184-231] pre-allocation for a known geometry */
+int gpujpeg_decoder_init(struct gpujpeg_decoder* d, const struct gpujpeg_parameters* param,
+                         const struct gpujpeg_image_parameters* param_image)
+{
+    d->verbose = param->verbose;
+    d->perf_stats = param->perf_stats || param->verbose >= GPUJPEG_LL_STATUS;
+    if ( param_image->width * param_image->height * param->comp_count == 0 ) return 0;
+    struct gpujpeg_parameters p = *param;
+    struct gpujpeg_image_parameters pi = *param_image;
+    if ( p.comp_count != 3 ) {
+        GJ_ERR("This build decodes 3-component images only.\n");
+        return -1;
+    }
+    gj_geometry_init(&d->geo, &p, &pi);
+    const struct gj_geometry* g = &d->geo;
+    if ( grow_dev((void**)&d->d_coef, &d->d_coef_size, g->coef_count * 2) ||
+         grow_dev((void**)&d->d_raw, &d->d_raw_size, g->raw_size) ||
+         grow_dev((void**)&d->d_seg, &d->d_seg_size, (size_t)g->seg_count * 8) ) {
+        GJ_ERR("Decoder device allocation failed: %s\n", gj_cuda_last_error());
+        return -1;
+    }
+    if ( grow_host((void**)&d->h_seg, &d->h_seg_size, (size_t)g->seg_count * 8) ) return -1;
+    d->param = p;
+    d->param_image = pi;
+    d->initialised = 1;
+    return 0;
+}
+
+/* [ref: src/gpujpeg_decoder.c:471-483] */
+void gpujpeg_decoder_set_output_format(struct gpujpeg_decoder* decoder, enum gpujpeg_color_space color_space,
+                                       enum gpujpeg_pixel_format pixel_format)
+{
+    decoder->req_color_space = color_space;
+    decoder->req_pixel_format = pixel_format;
+}
+
+static int output_format_supported(const struct gpujpeg_decoder* d)
+{
+    const enum gpujpeg_pixel_format pf = d->req_pixel_format;
+    const enum gpujpeg_color_space cs = d->req_color_space;
+    const int pf_ok = pf == GPUJPEG_444_U8_P012 || pf == GPUJPEG_PIXFMT_AUTODETECT || pf == GPUJPEG_PIXFMT_NO_ALPHA ||
+                      pf == GPUJPEG_PIXFMT_STD || pf == GPUJPEG_PIXFMT_NATIVE || pf == GPUJPEG_PIXFMT_NONE;
+    const int cs_ok = cs == GPUJPEG_RGB || cs == GPUJPEG_CS_DEFAULT || cs == GPUJPEG_NONE;
+    if ( !pf_ok || !cs_ok ) {
+        GJ_ERR("This build decodes to GPUJPEG_RGB / GPUJPEG_444_U8_P012 only.\n");
+        return 0;
+    }
+    return 1;
+}
+
+/* [ref: src/gpujpeg_decoder.c:234-469] */
+int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t image_size,
+                           struct gpujpeg_decoder_output* output)
+{
+    if ( !d || !image || !output ) return GPUJPEG_ERROR;
+    const int stats = d->perf_stats || d->verbose >= GPUJPEG_LL_STATUS;
+    const double t_begin = gpujpeg_get_time();
+
+    /* ---- host reader ---- */
+    struct gj_stream st;
+    if ( gj_reader_parse(image, image_size, &st, d->verbose) ) {
+        GJ_ERR("Decoder failed when decoding image data!\n");
+        return GPUJPEG_ERROR;
+    }
+    if ( st.comp_count != 3 ) {
+        GJ_ERR("This build decodes 3-component JPEGs only (stream has %d).\n", st.comp_count);
+        return GPUJPEG_ERROR;
+    }
+    for ( int c = 0; c < 3; c++ ) {
+        if ( st.comp_hv[c] != 0x11 ) {
+            GJ_ERR("This build decodes 4:4:4 only (chroma subsampling is not implemented yet).\n");
+            return GPUJPEG_ERROR;
+        }
+        if ( !st.have_qt[st.comp_tq[c]] ) {
+            GJ_ERR("Quantization table %d is missing!\n", st.comp_tq[c]);
+            return GPUJPEG_ERROR;
+        }
+    }
+    if ( st.color_space != GPUJPEG_YCBCR_BT601_256LVLS ) {
+        GJ_ERR("This build decodes YCbCr JPEG streams only (stream is %s).\n", gpujpeg_color_space_get_name(st.color_space));
+        return GPUJPEG_ERROR;
+    }
+    if ( !output_format_supported(d) ) return GPUJPEG_ERROR;
+    if ( !((st.scan_count == 1 && st.scan[0].ncomp == 3) || st.scan_count == 3) ) {
+        GJ_ERR("Unsupported scan structure (%d scans).\n", st.scan_count);
+        return GPUJPEG_ERROR;
+    }
+    if ( image_size >= 0xFFFFFFFFull ) {
+        GJ_ERR("JPEG streams of 4 GiB or more are not supported.\n");
+        return GPUJPEG_ERROR;
+    }
+
+    struct gpujpeg_parameters p;
+    gpujpeg_set_default_parameters(&p);
+    p.verbose = d->verbose;
+    p.perf_stats = d->perf_stats;
+    p.restart_interval = st.restart_interval;
+    p.interleaved = st.interleaved;
+    p.comp_count = 3;
+    for ( int c = 0; c < 3; c++ ) {
+        p.sampling_factor[c].horizontal = 1;
+        p.sampling_factor[c].vertical = 1;
+    }
+    p.color_space_internal = st.color_space;
+    struct gpujpeg_image_parameters pi;
+    gpujpeg_image_set_default_parameters(&pi);
+    pi.width = st.width;
+    pi.height = st.height;
+    pi.color_space = GPUJPEG_RGB;
+    pi.pixel_format = GPUJPEG_444_U8_P012;
+
+    if ( !d->initialised || d->param_image.width != pi.width || d->param_image.height != pi.height ||
+         d->param.restart_interval != p.restart_interval || d->param.interleaved != p.interleaved ) {
+        if ( d->initialised ) GJ_VERBOSE(d->verbose, "Reinitializing decoder.\n");
+        if ( gpujpeg_decoder_init(d, &p, &pi) ) return GPUJPEG_ERROR;
+    }
+    const struct gj_geometry* g = &d->geo;
+
+    uint32_t* seg_off = d->h_seg;
+    uint32_t* seg_len = d->h_seg + g->seg_count;
+    const int nseg = gj_reader_split(image, &st, seg_off, seg_len, g->seg_count);
+    if ( nseg != g->seg_count ) {
+        GJ_ERR("JPEG stream has %d restart segments, expected %d for a %dx%d image with restart interval %d!\n", nseg,
+               g->seg_count, st.width, st.height, st.restart_interval);
+        return GPUJPEG_ERROR;
+    }
+    for ( int s = 0; s < st.scan_count; s++ ) {
+        if ( st.scan[s].segment_count != g->seg_per_scan ) {
+            GJ_ERR("Scan %d has %d restart segments, expected %d!\n", s, st.scan[s].segment_count, g->seg_per_scan);
+            return GPUJPEG_ERROR;
+        }
+    }
+
+    /* tables: dequantisation (zig-zag order, by table id) and Huffman LUTs (by class and id) */
+    memset(&d->h_tab, 0, sizeof d->h_tab);
+    for ( int t = 0; t < 4; t++ )
+        if ( st.have_qt[t] )
+            for ( int k = 0; k < 64; k++ )
+                d->h_tab.qinv_zz[t][k] = st.qt[t][k];
+    struct gj_huff_dec_args ha;
+    memset(&ha, 0, sizeof ha);
+    for ( int s = 0; s < st.scan_count; s++ ) {
+        for ( int k = 0; k < st.scan[s].ncomp; k++ ) {
+            const int td = st.scan[s].td[k], ta = st.scan[s].ta[k];
+            if ( !st.have_huff[0][td] || !st.have_huff[1][ta] ) {
+                GJ_ERR("Huffman table (DC %d / AC %d) used by scan %d is missing!\n", td, ta, s);
+                return GPUJPEG_ERROR;
+            }
+            ha.scan_comp[s][k] = st.scan[s].comp[k];
+            ha.scan_td[s][k] = td;
+            ha.scan_ta[s][k] = ta;
+        }
+    }
+    for ( int cls = 0; cls < 2; cls++ )
+        for ( int id = 0; id < 4; id++ )
+            if ( st.have_huff[cls][id] && gj_dec_lut_build(&st.huff[cls][id], &d->h_tab.lut[cls][id]) ) {
+                GJ_ERR("Invalid Huffman table (class %d id %d)!\n", cls, id);
+                return GPUJPEG_ERROR;
+            }
+    const double t_reader_ms = (gpujpeg_get_time() - t_begin) * 1000.0;
+
+    /* ---- upload ---- */
+    if ( grow_dev((void**)&d->d_file, &d->d_file_size, image_size + 64) ) {
+        GJ_ERR("Decoder device allocation failed: %s\n", gj_cuda_last_error());
+        return GPUJPEG_ERROR;
+    }
+    if ( stats && d->timers_ok ) gj_timer_start(&d->t_to, d->stream);
+    int rc = 0;
+    if ( !d->tab_valid || memcmp(&d->h_tab, &d->h_tab_prev, sizeof d->h_tab) != 0 ) {
+        /* h_tab_prev is what the in-flight copy reads from: never modified while a frame is running */
+        d->h_tab_prev = d->h_tab;
+        rc |= gj_cuda_memcpy_h2d_async(d->d_tab, &d->h_tab_prev, sizeof d->h_tab, d->stream);
+        d->tab_valid = 1;
+    }
+    rc |= gj_cuda_memcpy_h2d_async(d->d_file, image, image_size, d->stream);
+    rc |= gj_cuda_memcpy_h2d_async(d->d_seg, d->h_seg, (size_t)g->seg_count * 8, d->stream);
+    if ( rc ) {
+        GJ_ERR("Decoder copy of compressed data failed: %s\n", gj_cuda_last_error());
+        return GPUJPEG_ERROR;
+    }
+    if ( stats && d->timers_ok ) {
+        gj_timer_stop(&d->t_to, d->stream);
+        gj_timer_start(&d->t_gpu, d->stream);
+        gj_timer_start(&d->t_huff, d->stream);
+    }
+
+    /* ---- K3 ---- */
+    ha.d_file = d->d_file;
+    ha.d_seg_off = d->d_seg;
+    ha.d_seg_len = d->d_seg + g->seg_count;
+    ha.seg_count = g->seg_count;
+    ha.seg_per_scan = g->seg_per_scan;
+    ha.scan_count = g->scan_count;
+    ha.comps_per_scan = g->comps_per_scan;
+    ha.seg_mcu = g->seg_mcu;
+    ha.nblk = g->nblk;
+    ha.d_coef = d->d_coef;
+    ha.d_tables = d->d_tab;
+    if ( gj_launch_huffman_decode(&ha, d->stream) ) {
+        GJ_ERR("Huffman decoder launch failed: %s\n", gj_cuda_last_error());
+        return GPUJPEG_ERROR;
+    }
+    if ( stats && d->timers_ok ) {
+        gj_timer_stop(&d->t_huff, d->stream);
+        gj_timer_start(&d->t_dct, d->stream);
+    }
+
+    /* ---- K4, straight into the buffer the caller asked for ---- */
+    uint8_t* d_out = d->d_raw;
+    if ( output->type == GPUJPEG_DECODER_OUTPUT_CUSTOM_CUDA_BUFFER ) {
+        if ( !output->data ) return GPUJPEG_ERROR;
+        d_out = output->data;
+    }
+    else if ( output->type == GPUJPEG_DECODER_OUTPUT_OPENGL_TEXTURE ) {
+        GJ_ERR("OpenGL texture output is not supported in this build.\n");
+        return GPUJPEG_ERROR;
+    }
+    if ( gj_launch_idct_rgb444(d->d_coef, g->bcx, g->bcy, st.comp_tq, d_out, g->width, g->height, g->pitch,
+                               d->idct_flavour, &d->h_tab, d->stream) ) {
+        GJ_ERR("Inverse DCT launch failed: %s\n", gj_cuda_last_error());
+        return GPUJPEG_ERROR;
+    }
+    if ( stats && d->timers_ok ) {
+        gj_timer_stop(&d->t_dct, d->stream);
+        gj_timer_stop(&d->t_gpu, d->stream);
+    }
+
+    output->data_size = g->raw_size;
+    output->param_image = pi;
+    if ( output->type == GPUJPEG_DECODER_OUTPUT_INTERNAL_BUFFER || output->type == GPUJPEG_DECODER_OUTPUT_CUSTOM_BUFFER ) {
+        uint8_t* h_dst = output->data;
+        if ( output->type == GPUJPEG_DECODER_OUTPUT_INTERNAL_BUFFER ) {
+            if ( grow_host((void**)&d->h_raw, &d->h_raw_size, g->raw_size) ) return GPUJPEG_ERROR;
+            h_dst = d->h_raw;
+        }
+        else if ( !h_dst ) {
+            return GPUJPEG_ERROR;
+        }
+        if ( stats && d->timers_ok ) gj_timer_start(&d->t_from, d->stream);
+        if ( gj_cuda_memcpy_d2h_async(h_dst, d_out, g->raw_size, d->stream) ) {
+            GJ_ERR("Decoder copy of raw data failed: %s\n", gj_cuda_last_error());
+            return GPUJPEG_ERROR;
+        }
+        if ( stats && d->timers_ok ) gj_timer_stop(&d->t_from, d->stream);
+        output->data = h_dst;
+    }
+    else {
+        output->data = d_out;
+    }
+    if ( gj_cuda_stream_sync(d->stream) ) {
+        GJ_ERR("Decoder failed: %s\n", gj_cuda_last_error());
+        return GPUJPEG_ERROR;
+    }
+    output->metadata = &d->metadata;
+
+    d->stats_valid = 0;
+    if ( stats && d->timers_ok ) {
+        memset(&d->stats, 0, sizeof d->stats);
+        d->stats.duration_stream = t_reader_ms;
+        d->stats.duration_memory_to = gj_timer_ms(&d->t_to);
+        d->stats.duration_huffman_coder = gj_timer_ms(&d->t_huff);
+        d->stats.duration_dct_quantization = gj_timer_ms(&d->t_dct);
+        d->stats.duration_in_gpu = gj_timer_ms(&d->t_gpu);
+        if ( output->type == GPUJPEG_DECODER_OUTPUT_INTERNAL_BUFFER || output->type == GPUJPEG_DECODER_OUTPUT_CUSTOM_BUFFER )
+            d->stats.duration_memory_from = gj_timer_ms(&d->t_from);
+        d->stats_valid = 1;
+        if ( d->verbose >= GPUJPEG_LL_STATUS ) {
+            fprintf(stderr, " -Stream Reader:     %10.3f ms\n", d->stats.duration_stream);
+            fprintf(stderr, " -Copy To Device:    %10.3f ms\n", d->stats.duration_memory_to);
+            fprintf(stderr, " -Huffman Decoder:   %10.3f ms\n", d->stats.duration_huffman_coder);
+            fprintf(stderr, " -DeQuant+IDCT+Post: %10.3f ms\n", d->stats.duration_dct_quantization);
+            fprintf(stderr, " -Copy From Device:  %10.3f ms\n", d->stats.duration_memory_from);
+            fprintf(stderr, "Decode Image GPU:    %10.3f ms (only in-GPU processing)\n", d->stats.duration_in_gpu);
+            fprintf(stderr, "Decode Image:        %10.3f ms\n", (gpujpeg_get_time() - t_begin) * 1000.0);
+            fprintf(stderr, "Decompressed Size:%13zu bytes %dx%d %s %s\n", output->data_size, pi.width, pi.height,
+                    gpujpeg_pixel_format_get_name(pi.pixel_format), gpujpeg_color_space_get_name(pi.color_space));
+        }
+    }
+    return GPUJPEG_NOERR;
+}
+
+int gpujpeg_decoder_get_stats(struct gpujpeg_decoder* decoder, struct gpujpeg_duration_stats* stats)
+{
+    if ( !decoder || !stats || !decoder->stats_valid ) return -1;
+    *stats = decoder->stats;
+    return 0;
+}
+
+/* [ref: src/gpujpeg_reader.c:1738-1872] */
+int gpujpeg_decoder_get_image_info2(uint8_t* image, size_t image_size, struct gpujpeg_image_info* info, int verbose,
+                                    unsigned flags)
+{
+    struct gj_stream st;
+    if ( gj_reader_parse(image, image_size, &st, verbose) ) return -1;
+    memset(info, 0, sizeof *info);
+    gpujpeg_image_set_default_parameters(&info->param_image);
+    gpujpeg_set_default_parameters(&info->param);
+    info->param_image.width = st.width;
+    info->param_image.height = st.height;
+    info->param_image.color_space = st.color_space;
+    info->param_image.pixel_format = st.comp_count == 1 ? GPUJPEG_U8 : GPUJPEG_444_U8_P012;
+    info->param.comp_count = st.comp_count;
+    info->param.restart_interval = st.restart_interval;
+    info->param.interleaved = st.interleaved;
+    info->param.color_space_internal = st.color_space;
+    for ( int c = 0; c < st.comp_count; c++ ) {
+        info->param.sampling_factor[c].horizontal = (uint8_t)(st.comp_hv[c] >> 4);
+        info->param.sampling_factor[c].vertical = (uint8_t)(st.comp_hv[c] & 15);
+    }
+    info->header_type = st.header_type;
+    info->comment = st.comment;
+    info->segment_count = 0;
+    if ( flags & GPUJPEG_COUNT_SEG_COUNT_REQ ) {
+        int n = 0;
+        for ( int s = 0; s < st.scan_count; s++ ) {
+            n++;
+            for ( size_t i = st.scan[s].begin; i + 1 < st.scan[s].end; i++ )
+                if ( image[i] == 0xFF && image[i + 1] >= 0xD0 && image[i + 1] <= 0xD7 ) n++;
+        }
+        info->segment_count = n;
+    }
+    return 0;
+}
+
+int gpujpeg_decoder_get_image_info(uint8_t* image, size_t image_size, struct gpujpeg_image_parameters* param_image,
+                                   struct gpujpeg_parameters* param, int* segment_count)
+{
+    struct gpujpeg_image_info info;
+    if ( gpujpeg_decoder_get_image_info2(image, image_size, &info, param ? param->verbose : 0,
+                                         segment_count ? GPUJPEG_COUNT_SEG_COUNT_REQ : 0) )
+        return -1;
+    if ( param_image ) *param_image = info.param_image;
+    if ( param ) {
+        const int verbose = param->verbose, perf = param->perf_stats;
+        *param = info.param;
+        param->verbose = verbose;
+        param->perf_stats = perf;
+    }
+    if ( segment_count ) *segment_count = info.segment_count;
+    return 0;
+}
+
+/* [ref: src/gpujpeg_decoder.c:485-531] */
+int gpujpeg_decoder_set_option(struct gpujpeg_decoder* decoder, const char* opt, const char* val)
+{
+    if ( !decoder || !opt || !val ) return GPUJPEG_ERROR;
+    if ( strcmp(opt, GPUJPEG_DEC_OPT_IDCT) == 0 ) {
+        if ( strcmp(val, GPUJPEG_DEC_IDCT_VAL_INT) == 0 ) decoder->idct_flavour = 0;
+        else if ( strcmp(val, GPUJPEG_DEC_IDCT_VAL_FLOAT_GPUREF) == 0 ) decoder->idct_flavour = 1;
+        else {
+            GJ_ERR("Unknown IDCT flavour: %s\n", val);
+            return GPUJPEG_ERROR;
+        }
+        return GPUJPEG_NOERR;
+    }
+    if ( strcmp(opt, GPUJPEG_DEC_OPT_TGA_RLE_BOOL) == 0 || strcmp(opt, GPUJPEG_DEC_OPT_FLIPPED_BOOL) == 0 ||
+         strcmp(opt, GPUJPEG_DEC_OPT_CHANNEL_REMAP) == 0 || strcmp(opt, GPUJPEG_DEC_OPT_ALIGNMENT_BYTES_INT) == 0 ) {
+        GJ_ERR("Decoder option %s is not implemented in this build.\n", opt);
+        return GPUJPEG_ERROR;
+    }
+    GJ_ERR("Invalid decoder option: %s!\n", opt);
+    return GPUJPEG_ERROR;
+}
+
+void gpujpeg_decoder_print_options(void)
+{
+    printf("\t" GPUJPEG_DEC_OPT_IDCT "=[" GPUJPEG_DEC_IDCT_VAL_INT "|" GPUJPEG_DEC_IDCT_VAL_FLOAT_GPUREF
+           "] - inverse DCT flavour (default: int = gpujpeg_idct_cpu)\n");
+}
+
+/* ---- extension used by the parity tests: coefficients of the last decoded frame, natural order ---- */
+GPUJPEG_API int gpujpegx_decoder_get_coefficients(struct gpujpeg_decoder* d, int16_t* out, size_t count)
+{
+    if ( !d || !d->initialised || count != d->geo.coef_count ) return -1;
+    return gj_coef_to_host_natural(d->d_coef, count, out, d->stream);
+}

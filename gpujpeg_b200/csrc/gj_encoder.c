@@ -1,0 +1,600 @@
+/*
+ * gj_encoder.c -- the public encoder API on top of the sm_100a stage launchers.  Host C.
+ *
+ * Mirrors the reference orchestrator's contract (src/gpujpeg_encoder.c:351-646): same parameter
+ * handling (comp_count 0 => from pixel format, RESTART_AUTO heuristic), same re-initialisation
+ * rules, one stream, blocks until the JPEG is complete in an encoder-owned host buffer.
+ * What differs is the pipeline behind it:
+ *
+ *     H2D raw  ->  K1 (colour+FDCT+quant, one launch for all components)
+ *              ->  K2 (Huffman encode -> scan -> finished byte stream on the device)
+ *              ->  D2H 32-byte info, D2H payload (one copy; the reference copies 43 200 segments
+ *                  one by one on the host, src/gpujpeg_encoder.c:567-623)
+ *
+ * Supported on this path (anything else fails loudly with GPUJPEG_ERROR, never a CPU fallback):
+ *   pixel format GPUJPEG_444_U8_P012, colour space GPUJPEG_RGB -> internal YCbCr JPEG (BT.601 full
+ *   range), 3 components 4:4:4, interleaved or not, any restart interval, JFIF header.
+ */
+#include <assert.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "gj_internal.h"
+
+struct gpujpeg_encoder {
+    gj_stream_t stream;
+    int device;
+    struct gpujpeg_parameters param;           /* as adjusted */
+    struct gpujpeg_image_parameters param_image;
+    int initialised;
+    struct gj_geometry geo;
+    int quality;                               /* quality the tables were built for (-1 = none) */
+    enum gpujpeg_header_type header_type;
+    int out_pinned;
+
+    uint8_t raw_q[2][64];
+    struct gj_huff_spec spec[2][2];
+    struct gj_dev_enc_tables h_tab;            /* host copy (K1 takes it by value) */
+    struct gj_dev_enc_tables* d_tab;           /* device copy (K2 LUTs) */
+
+    /* device buffers */
+    uint8_t* d_raw; size_t d_raw_size;
+    int16_t* d_coef; size_t d_coef_size;
+    uint8_t* d_tmp; size_t d_tmp_size;
+    uint32_t* d_seg_bytes; uint64_t* d_seg_off; int seg_alloc;
+    uint8_t* d_stream; size_t d_stream_size;
+    uint8_t* d_sos;
+    uint64_t* d_info;
+    uint64_t* h_info;                          /* pinned */
+
+    /* host output */
+    uint8_t* out; size_t out_size; int out_is_pinned;
+    uint8_t header[1024]; size_t header_size;
+    uint8_t sos[GJ_MAX_COMP][16]; int sos_len;
+
+    /* timers [ref: src/gpujpeg_common_internal.h:414-422] */
+    struct gj_timer t_to, t_from, t_pre, t_huff, t_gpu;
+    int timers_ok;
+    double t_stream_ms;
+    struct gpujpeg_duration_stats stats;
+    int stats_valid;
+};
+
+/* ---- small public helpers [ref: src/gpujpeg_encoder.c:47-110] ---- */
+void gpujpeg_encoder_input_set_image(struct gpujpeg_encoder_input* input, uint8_t* image)
+{
+    input->type = GPUJPEG_ENCODER_INPUT_IMAGE;
+    input->image = image;
+    input->texture = NULL;
+}
+void gpujpeg_encoder_input_set_gpu_image(struct gpujpeg_encoder_input* input, uint8_t* image)
+{
+    input->type = GPUJPEG_ENCODER_INPUT_GPU_IMAGE;
+    input->image = image;
+    input->texture = NULL;
+}
+void gpujpeg_encoder_input_set_texture(struct gpujpeg_encoder_input* input, struct gpujpeg_opengl_texture* texture)
+{
+    input->type = GPUJPEG_ENCODER_INPUT_OPENGL_TEXTURE;
+    input->image = NULL;
+    input->texture = texture;
+}
+struct gpujpeg_encoder_input gpujpeg_encoder_input_image(uint8_t* image)
+{
+    struct gpujpeg_encoder_input r;
+    gpujpeg_encoder_input_set_image(&r, image);
+    return r;
+}
+struct gpujpeg_encoder_input gpujpeg_encoder_input_gpu_image(uint8_t* image)
+{
+    struct gpujpeg_encoder_input r;
+    gpujpeg_encoder_input_set_gpu_image(&r, image);
+    return r;
+}
+struct gpujpeg_encoder_input gpujpeg_encoder_input_texture(struct gpujpeg_opengl_texture* texture)
+{
+    struct gpujpeg_encoder_input r;
+    gpujpeg_encoder_input_set_texture(&r, texture);
+    return r;
+}
+
+/* [ref: src/gpujpeg_encoder.c:113-181] */
+struct gpujpeg_encoder* gpujpeg_encoder_create(cudaStream_t stream)
+{
+    struct gpujpeg_encoder* e = (struct gpujpeg_encoder*)calloc(1, sizeof *e);
+    if ( !e ) return NULL;
+    e->stream = (gj_stream_t)stream;
+    e->device = gj_cuda_get_device();
+    e->quality = -1;
+    e->header_type = GPUJPEG_HEADER_DEFAULT;
+    if ( e->device < 0 ) {
+        GJ_ERR("Cannot get CUDA device: %s\n", gj_cuda_last_error());
+        free(e);
+        return NULL;
+    }
+    for ( int t = 0; t < 2; t++ )
+        for ( int k = 0; k < 2; k++ )
+            gj_huff_spec_default(t, k, &e->spec[t][k]);
+    for ( int t = 0; t < 2; t++ )
+        gj_enc_lut_build(&e->spec[t][0], &e->spec[t][1], &e->h_tab.lut[t]);
+    if ( gj_cuda_malloc((void**)&e->d_tab, sizeof *e->d_tab) || gj_cuda_malloc((void**)&e->d_info, 64) ||
+         gj_cuda_malloc((void**)&e->d_sos, 64) || gj_cuda_malloc_host((void**)&e->h_info, 64) ) {
+        GJ_ERR("Encoder allocation failed: %s\n", gj_cuda_last_error());
+        gpujpeg_encoder_destroy(e);
+        return NULL;
+    }
+    e->timers_ok = !(gj_timer_create(&e->t_to) || gj_timer_create(&e->t_from) || gj_timer_create(&e->t_pre) ||
+                     gj_timer_create(&e->t_huff) || gj_timer_create(&e->t_gpu));
+    return e;
+}
+
+int gpujpeg_encoder_destroy(struct gpujpeg_encoder* e)
+{
+    if ( !e ) return -1;
+    gj_cuda_free(e->d_tab);
+    gj_cuda_free(e->d_info);
+    gj_cuda_free(e->d_sos);
+    gj_cuda_free_host(e->h_info);
+    gj_cuda_free(e->d_raw);
+    gj_cuda_free(e->d_coef);
+    gj_cuda_free(e->d_tmp);
+    gj_cuda_free(e->d_seg_bytes);
+    gj_cuda_free(e->d_seg_off);
+    gj_cuda_free(e->d_stream);
+    if ( e->out ) {
+        if ( e->out_is_pinned ) gj_cuda_free_host(e->out);
+        else free(e->out);
+    }
+    gj_timer_destroy(&e->t_to);
+    gj_timer_destroy(&e->t_from);
+    gj_timer_destroy(&e->t_pre);
+    gj_timer_destroy(&e->t_huff);
+    gj_timer_destroy(&e->t_gpu);
+    free(e);
+    return 0;
+}
+
+/* [ref: src/gpujpeg_encoder.c:290-317] */
+int gpujpeg_encoder_suggest_restart_interval(const struct gpujpeg_image_parameters* param_image,
+                                             gpujpeg_sampling_factor_t subsampling, bool interleaved, int verbose)
+{
+    const int comp_count = gpujpeg_pixel_format_get_comp_count(param_image->pixel_format);
+    const double mpix = ((double)param_image->width * param_image->height * comp_count) / (1000000.0 * 3.0);
+    int rst = mpix < 1.0 ? 4 : mpix < 3.0 ? 8 : mpix < 9.0 ? 10 : 12;
+    if ( subsampling != GPUJPEG_SUBSAMPLING_444 && interleaved ) rst /= 2;
+    if ( !interleaved ) rst *= comp_count;
+    GJ_VERBOSE(verbose, "Auto-adjusting restart interval to %d for better performance.\n", rst);
+    return rst;
+}
+
+static int grow(void** p, size_t* have, size_t want)
+{
+    if ( *have >= want ) return 0;
+    gj_cuda_free(*p);
+    *p = NULL;
+    *have = 0;
+    if ( gj_cuda_malloc(p, want) ) return -1;
+    *have = want;
+    return 0;
+}
+
+static int params_supported(const struct gpujpeg_parameters* p, const struct gpujpeg_image_parameters* pi)
+{
+    if ( pi->pixel_format != GPUJPEG_444_U8_P012 || pi->color_space != GPUJPEG_RGB ) {
+        GJ_ERR("This build encodes GPUJPEG_RGB / GPUJPEG_444_U8_P012 input only (got %s / %s).\n",
+               gpujpeg_color_space_get_name(pi->color_space), gpujpeg_pixel_format_get_name(pi->pixel_format));
+        return 0;
+    }
+    if ( p->color_space_internal != GPUJPEG_YCBCR_BT601_256LVLS ) {
+        GJ_ERR("This build encodes to internal color space %s only.\n",
+               gpujpeg_color_space_get_name(GPUJPEG_YCBCR_BT601_256LVLS));
+        return 0;
+    }
+    if ( p->comp_count != 3 ) {
+        GJ_ERR("This build encodes 3-component images only (comp_count = %d).\n", p->comp_count);
+        return 0;
+    }
+    for ( int c = 0; c < 3; c++ ) {
+        if ( p->sampling_factor[c].horizontal != 1 || p->sampling_factor[c].vertical != 1 ) {
+            GJ_ERR("This build encodes 4:4:4 only (chroma subsampling is not implemented yet).\n");
+            return 0;
+        }
+    }
+    if ( p->segment_info ) {
+        GJ_ERR("segment_info headers are not implemented in this build.\n");
+        return 0;
+    }
+    if ( pi->width < 1 || pi->height < 1 || pi->width > 65535 || pi->height > 65535 || pi->width_padding < 0 ) {
+        GJ_ERR("Unsupported image size %dx%d.\n", pi->width, pi->height);
+        return 0;
+    }
+    if ( p->restart_interval < 0 || p->restart_interval > 65535 ) {
+        GJ_ERR("Restart interval %d cannot be stored in a DRI marker.\n", p->restart_interval);
+        return 0;
+    }
+    return 1;
+}
+
+/* (re)build everything that depends on geometry [ref: src/gpujpeg_common.c:628-1106] */
+static int encoder_init_image(struct gpujpeg_encoder* e, const struct gpujpeg_parameters* p,
+                              const struct gpujpeg_image_parameters* pi)
+{
+    gj_geometry_init(&e->geo, p, pi);
+    const struct gj_geometry* g = &e->geo;
+    size_t coef_bytes = g->coef_count * sizeof(int16_t);
+    size_t tmp_bytes = (size_t)g->seg_count * g->slot_stride + 256;
+    if ( grow((void**)&e->d_coef, &e->d_coef_size, coef_bytes) || grow((void**)&e->d_tmp, &e->d_tmp_size, tmp_bytes) ||
+         grow((void**)&e->d_stream, &e->d_stream_size, g->stream_cap + 64) ) {
+        GJ_ERR("Encoder device allocation failed (%zu + %zu + %zu bytes): %s\n", coef_bytes, tmp_bytes, g->stream_cap,
+               gj_cuda_last_error());
+        return -1;
+    }
+    if ( g->seg_count > e->seg_alloc ) {
+        gj_cuda_free(e->d_seg_bytes);
+        gj_cuda_free(e->d_seg_off);
+        e->d_seg_bytes = NULL;
+        e->d_seg_off = NULL;
+        e->seg_alloc = 0;
+        if ( gj_cuda_malloc((void**)&e->d_seg_bytes, (size_t)g->seg_count * 4) ||
+             gj_cuda_malloc((void**)&e->d_seg_off, (size_t)g->seg_count * 8) )
+            return -1;
+        e->seg_alloc = g->seg_count;
+    }
+    if ( e->out_size < g->stream_cap || e->out_is_pinned != e->out_pinned ) {
+        if ( e->out ) {
+            if ( e->out_is_pinned ) gj_cuda_free_host(e->out);
+            else free(e->out);
+        }
+        e->out = NULL;
+        e->out_size = 0;
+        e->out_is_pinned = e->out_pinned;
+        if ( e->out_pinned ) {
+            if ( gj_cuda_malloc_host((void**)&e->out, g->stream_cap) ) return -1;
+        }
+        else if ( !(e->out = (uint8_t*)malloc(g->stream_cap)) ) {
+            return -1;
+        }
+        e->out_size = g->stream_cap;
+    }
+    e->param = *p;
+    e->param_image = *pi;
+    e->initialised = 1;
+    return 0;
+}
+
+static int same_image(const struct gpujpeg_image_parameters* a, const struct gpujpeg_image_parameters* b)
+{
+    return a->width == b->width && a->height == b->height && a->color_space == b->color_space &&
+           a->pixel_format == b->pixel_format && a->width_padding == b->width_padding;
+}
+static int same_param(const struct gpujpeg_parameters* a, const struct gpujpeg_parameters* b)
+{
+    /* everything but verbose / perf_stats / quality [ref: src/gpujpeg_common.c:348-367] */
+    if ( a->restart_interval != b->restart_interval || a->interleaved != b->interleaved ||
+         a->segment_info != b->segment_info || a->comp_count != b->comp_count ||
+         a->color_space_internal != b->color_space_internal )
+        return 0;
+    for ( int c = 0; c < a->comp_count; c++ )
+        if ( a->sampling_factor[c].horizontal != b->sampling_factor[c].horizontal ||
+             a->sampling_factor[c].vertical != b->sampling_factor[c].vertical )
+            return 0;
+    return 1;
+}
+
+/* [ref: src/gpujpeg_encoder.c:319-348] */
+static struct gpujpeg_parameters adjust_params(struct gpujpeg_encoder* e, const struct gpujpeg_parameters* param,
+                                               const struct gpujpeg_image_parameters* pi, int img_changed)
+{
+    struct gpujpeg_parameters a = *param;
+    if ( param->comp_count == 0 ) {
+        if ( img_changed || !e->initialised ) {
+            const int n = gpujpeg_pixel_format_get_comp_count(pi->pixel_format);
+            a.comp_count = n > 3 ? 3 : n;
+            memset(a.sampling_factor, 0, sizeof a.sampling_factor);
+            for ( int c = 0; c < a.comp_count; c++ ) {
+                a.sampling_factor[c].horizontal = 1;
+                a.sampling_factor[c].vertical = 1;
+            }
+        }
+        else {
+            a.comp_count = e->param.comp_count;
+            memcpy(a.sampling_factor, e->param.sampling_factor, sizeof a.sampling_factor);
+        }
+    }
+    if ( param->restart_interval == RESTART_AUTO ) {
+        if ( img_changed || !e->initialised || a.interleaved != e->param.interleaved )
+            a.restart_interval =
+                gpujpeg_encoder_suggest_restart_interval(pi, GPUJPEG_SUBSAMPLING_444, a.interleaved, a.verbose);
+        else
+            a.restart_interval = e->param.restart_interval;
+    }
+    return a;
+}
+
+int gpujpeg_encoder_allocate(struct gpujpeg_encoder* encoder, const struct gpujpeg_parameters* param,
+                             const struct gpujpeg_image_parameters* param_image,
+                             enum gpujpeg_encoder_input_type image_input_type)
+{
+    struct gpujpeg_parameters a = adjust_params(encoder, param, param_image, 1);
+    if ( !params_supported(&a, param_image) ) return -1;
+    if ( encoder_init_image(encoder, &a, param_image) ) return -1;
+    if ( image_input_type == GPUJPEG_ENCODER_INPUT_IMAGE &&
+         grow((void**)&encoder->d_raw, &encoder->d_raw_size, encoder->geo.raw_size) )
+        return -1;
+    return 0;
+}
+
+/* [ref: src/gpujpeg_encoder.c:183-288] memory model of this build: raw + coefficients + scan tmp + stream */
+size_t gpujpeg_encoder_max_memory(struct gpujpeg_parameters* param, struct gpujpeg_image_parameters* param_image,
+                                  enum gpujpeg_encoder_input_type image_input_type, int max_pixels)
+{
+    struct gpujpeg_image_parameters pi = *param_image;
+    struct gpujpeg_parameters p = *param;
+    if ( p.comp_count == 0 ) p.comp_count = 3;
+    pi.width = 8 * (int)((max_pixels > 0 ? (size_t)max_pixels : 0) / 8 / 8 + 1);
+    pi.height = 8 * 8;
+    if ( pi.width < 8 ) pi.width = 8;
+    /* use a squarish estimate: memory is linear in pixel count */
+    struct gj_geometry g;
+    pi.width = 4096;
+    pi.height = (max_pixels + 4095) / 4096;
+    if ( pi.height < 1 ) pi.height = 1;
+    if ( p.restart_interval == RESTART_AUTO ) p.restart_interval = 36;
+    gj_geometry_init(&g, &p, &pi);
+    size_t total = g.coef_count * 2 + (size_t)g.seg_count * g.slot_stride + g.stream_cap + (size_t)g.seg_count * 12;
+    if ( image_input_type == GPUJPEG_ENCODER_INPUT_IMAGE ) total += g.raw_size;
+    return total;
+}
+
+size_t gpujpeg_encoder_max_pixels(struct gpujpeg_parameters* param, struct gpujpeg_image_parameters* param_image,
+                                  enum gpujpeg_encoder_input_type image_input_type, size_t memory_size, int* max_pixels)
+{
+    /* bisection over the linear model above [ref: src/gpujpeg_encoder.c:183-262] */
+    int lo = 0, hi = 1 << 30;
+    while ( hi - lo > 4096 ) {
+        const int mid = lo + (hi - lo) / 2;
+        if ( gpujpeg_encoder_max_memory(param, param_image, image_input_type, mid) <= memory_size ) lo = mid;
+        else hi = mid;
+    }
+    if ( max_pixels ) *max_pixels = lo;
+    return lo ? gpujpeg_encoder_max_memory(param, param_image, image_input_type, lo) : 0;
+}
+
+/* [ref: src/gpujpeg_encoder.c:351-646] */
+int gpujpeg_encoder_encode(struct gpujpeg_encoder* e, const struct gpujpeg_parameters* param,
+                           const struct gpujpeg_image_parameters* param_image, const struct gpujpeg_encoder_input* input,
+                           uint8_t** image_compressed, size_t* image_compressed_size)
+{
+    assert(param->comp_count <= GPUJPEG_MAX_COMPONENT_COUNT);
+    assert(param->quality >= 0 && param->quality <= 100);
+    assert(param->restart_interval >= RESTART_AUTO);
+    assert(param->interleaved == 0 || param->interleaved == 1);
+    if ( !e || !input || !image_compressed || !image_compressed_size ) return GPUJPEG_ERROR;
+
+    const int img_changed = !e->initialised || !same_image(&e->param_image, param_image);
+    struct gpujpeg_parameters a = adjust_params(e, param, param_image, img_changed);
+    const int stats = a.perf_stats || a.verbose >= GPUJPEG_LL_STATUS;
+    const double t_begin = stats ? gpujpeg_get_time() : 0.0;
+    if ( !params_supported(&a, param_image) ) return GPUJPEG_ERROR;
+
+    /* quantisation tables follow the quality [ref: src/gpujpeg_encoder.c:372-380] */
+    int tables_dirty = 0;
+    if ( e->quality != a.quality ) {
+        for ( int t = 0; t < 2; t++ ) {
+            gj_quant_raw(t, a.quality, e->raw_q[t]);
+            gj_quant_forward_zz(e->raw_q[t], e->h_tab.fwd_zz[t]);
+        }
+        e->quality = a.quality;
+        tables_dirty = 1;
+    }
+    int geometry_dirty = 0;
+    if ( img_changed || !same_param(&e->param, &a) || e->out_is_pinned != e->out_pinned || !e->out ) {
+        if ( encoder_init_image(e, &a, param_image) ) return GPUJPEG_ERROR;
+        geometry_dirty = 1;
+    }
+    e->param.quality = a.quality;
+    e->param.verbose = a.verbose;
+    e->param.perf_stats = a.perf_stats;
+    const struct gj_geometry* g = &e->geo;
+
+    if ( tables_dirty || geometry_dirty ) {
+        /* host codestream writer: file header + SOS headers, composed once per parameter change */
+        e->header_size = gj_write_header(e->header, &e->param, &e->param_image, e->raw_q, e->spec);
+        uint8_t sos_flat[GJ_MAX_COMP * 16];
+        e->sos_len = 0;
+        for ( int s = 0; s < g->scan_count; s++ ) {
+            e->sos_len = (int)gj_write_sos(e->sos[s], &e->param, s);
+            memcpy(sos_flat + s * e->sos_len, e->sos[s], (size_t)e->sos_len);
+        }
+        if ( gj_cuda_memcpy_h2d_async(e->d_tab, &e->h_tab, sizeof e->h_tab, e->stream) ||
+             gj_cuda_memcpy_h2d_async(e->d_sos, sos_flat, (size_t)g->scan_count * e->sos_len, e->stream) ||
+             gj_cuda_stream_sync(e->stream) ) {
+            GJ_ERR("Encoder table upload failed: %s\n", gj_cuda_last_error());
+            return GPUJPEG_ERROR;
+        }
+    }
+
+    /* input [ref: src/gpujpeg_encoder.c:402-476] */
+    const uint8_t* d_raw;
+    if ( input->type == GPUJPEG_ENCODER_INPUT_IMAGE ) {
+        /* the reference's unit test passes a device pointer as a host image and expects it to work
+         * [ref: test/unit/run_tests.c:40-79]; cudaMemcpyDefault semantics give the same result */
+        if ( grow((void**)&e->d_raw, &e->d_raw_size, g->raw_size) ) {
+            GJ_ERR("Encoder raw data allocation failed: %s\n", gj_cuda_last_error());
+            return GPUJPEG_ERROR;
+        }
+        if ( stats && e->timers_ok ) gj_timer_start(&e->t_to, e->stream);
+        int rc = gj_cuda_pointer_is_device(input->image)
+                     ? gj_cuda_memcpy_d2d_async(e->d_raw, input->image, g->raw_size, e->stream)
+                     : gj_cuda_memcpy_h2d_async(e->d_raw, input->image, g->raw_size, e->stream);
+        if ( rc ) {
+            GJ_ERR("Encoder raw data copy failed: %s\n", gj_cuda_last_error());
+            return GPUJPEG_ERROR;
+        }
+        if ( stats && e->timers_ok ) gj_timer_stop(&e->t_to, e->stream);
+        d_raw = e->d_raw;
+    }
+    else if ( input->type == GPUJPEG_ENCODER_INPUT_GPU_IMAGE ) {
+        d_raw = input->image;
+    }
+    else {
+        GJ_ERR("OpenGL texture input is not supported in this build.\n");
+        return GPUJPEG_ERROR;
+    }
+
+    if ( stats && e->timers_ok ) {
+        gj_timer_start(&e->t_gpu, e->stream);
+        gj_timer_start(&e->t_pre, e->stream);
+    }
+    if ( gj_launch_fdct_rgb444(d_raw, g->width, g->height, g->pitch, e->d_coef, g->bcx, g->bcy, &e->h_tab, e->stream) ) {
+        GJ_ERR("Forward DCT launch failed: %s\n", gj_cuda_last_error());
+        return GPUJPEG_ERROR;
+    }
+    if ( stats && e->timers_ok ) {
+        gj_timer_stop(&e->t_pre, e->stream);
+        gj_timer_start(&e->t_huff, e->stream);
+    }
+    struct gj_huff_enc_args ha;
+    memset(&ha, 0, sizeof ha);
+    ha.d_coef = e->d_coef;
+    ha.nblk = g->nblk;
+    ha.comp_count = g->comp_count;
+    ha.comps_per_scan = g->comps_per_scan;
+    ha.seg_mcu = g->seg_mcu;
+    ha.seg_per_scan = g->seg_per_scan;
+    ha.scan_count = g->scan_count;
+    ha.d_tmp = e->d_tmp;
+    ha.slot_stride = g->slot_stride;
+    ha.d_seg_bytes = e->d_seg_bytes;
+    ha.d_seg_off = e->d_seg_off;
+    ha.d_stream = e->d_stream;
+    ha.stream_cap = g->stream_cap;
+    ha.header_size = (uint32_t)e->header_size;
+    ha.d_sos = e->d_sos;
+    ha.sos_len = e->sos_len;
+    ha.d_info = e->d_info;
+    ha.d_tables = e->d_tab;
+    if ( gj_launch_huffman_encode(&ha, e->stream) ) {
+        GJ_ERR("Huffman encoder launch failed: %s\n", gj_cuda_last_error());
+        return GPUJPEG_ERROR;
+    }
+    if ( stats && e->timers_ok ) {
+        gj_timer_stop(&e->t_huff, e->stream);
+        gj_timer_stop(&e->t_gpu, e->stream);
+        gj_timer_start(&e->t_from, e->stream);
+    }
+    /* the only two synchronisation points of a frame: size, then payload */
+    if ( gj_cuda_memcpy_d2h_async(e->h_info, e->d_info, 32, e->stream) || gj_cuda_stream_sync(e->stream) ) {
+        GJ_ERR("Encoder failed: %s\n", gj_cuda_last_error());
+        return GPUJPEG_ERROR;
+    }
+    const size_t total = (size_t)e->h_info[0];
+    if ( e->h_info[1] || total > e->out_size || total < e->header_size + 2 ) {
+        GJ_ERR("Compressed image (%zu bytes) does not fit the output buffer (%zu bytes)!\n", total, e->out_size);
+        return GPUJPEG_ERROR;
+    }
+    if ( gj_cuda_memcpy_d2h_async(e->out + e->header_size, e->d_stream + e->header_size, total - e->header_size,
+                                  e->stream) ) {
+        GJ_ERR("Encoder copy of compressed data failed: %s\n", gj_cuda_last_error());
+        return GPUJPEG_ERROR;
+    }
+    if ( stats && e->timers_ok ) gj_timer_stop(&e->t_from, e->stream);
+    const double t_fmt = stats ? gpujpeg_get_time() : 0.0;
+    memcpy(e->out, e->header, e->header_size); /* host writer output, overlaps the copy */
+    e->t_stream_ms = stats ? (gpujpeg_get_time() - t_fmt) * 1000.0 : 0.0;
+    if ( gj_cuda_stream_sync(e->stream) ) {
+        GJ_ERR("Encoder copy of compressed data failed: %s\n", gj_cuda_last_error());
+        return GPUJPEG_ERROR;
+    }
+    *image_compressed = e->out;
+    *image_compressed_size = total;
+
+    e->stats_valid = 0;
+    if ( stats && e->timers_ok ) {
+        memset(&e->stats, 0, sizeof e->stats);
+        e->stats.duration_memory_to = input->type == GPUJPEG_ENCODER_INPUT_IMAGE ? gj_timer_ms(&e->t_to) : 0.0;
+        e->stats.duration_memory_from = gj_timer_ms(&e->t_from);
+        e->stats.duration_preprocessor = 0.0; /* fused into the DCT kernel */
+        e->stats.duration_dct_quantization = gj_timer_ms(&e->t_pre);
+        e->stats.duration_huffman_coder = gj_timer_ms(&e->t_huff);
+        e->stats.duration_stream = e->t_stream_ms;
+        e->stats.duration_in_gpu = gj_timer_ms(&e->t_gpu);
+        e->stats_valid = 1;
+        if ( a.verbose >= GPUJPEG_LL_STATUS ) {
+            /* [ref: src/gpujpeg_common.c:2169-2253] */
+            fprintf(stderr, " -Copy To Device:    %10.3f ms\n", e->stats.duration_memory_to);
+            fprintf(stderr, " -Preproc+DCT+Quant: %10.3f ms\n", e->stats.duration_dct_quantization);
+            fprintf(stderr, " -Huffman Encoder:   %10.3f ms\n", e->stats.duration_huffman_coder);
+            fprintf(stderr, " -Copy From Device:  %10.3f ms\n", e->stats.duration_memory_from);
+            fprintf(stderr, " -Stream Formatter:  %10.3f ms\n", e->stats.duration_stream);
+            fprintf(stderr, "Encode Image GPU:    %10.3f ms (only in-GPU processing)\n", e->stats.duration_in_gpu);
+            fprintf(stderr, "Encode Image Bare:   %10.3f ms (without copy to/from GPU memory)\n",
+                    (gpujpeg_get_time() - t_begin) * 1000.0 - e->stats.duration_memory_to - e->stats.duration_memory_from);
+            fprintf(stderr, "Encode Image:        %10.3f ms\n", (gpujpeg_get_time() - t_begin) * 1000.0);
+            fprintf(stderr, "Compressed Size:%15zu bytes %dx%d %s %s%s\n", total, e->param_image.width,
+                    e->param_image.height, gpujpeg_color_space_get_name(e->param.color_space_internal),
+                    gpujpeg_subsampling_get_name(e->param.comp_count, e->param.sampling_factor),
+                    e->param.interleaved ? " interleaved" : " non-interleaved");
+        }
+    }
+    return GPUJPEG_NOERR;
+}
+
+int gpujpeg_encoder_get_stats(struct gpujpeg_encoder* encoder, struct gpujpeg_duration_stats* stats)
+{
+    if ( !encoder || !stats || !encoder->stats_valid ) return -1;
+    *stats = encoder->stats;
+    return 0;
+}
+
+void gpujpeg_encoder_set_jpeg_header(struct gpujpeg_encoder* encoder, enum gpujpeg_header_type header_type)
+{
+    if ( header_type != GPUJPEG_HEADER_DEFAULT && header_type != GPUJPEG_HEADER_JFIF )
+        GJ_WARN("Only the JFIF header is implemented in this build; request ignored.\n");
+    encoder->header_type = GPUJPEG_HEADER_DEFAULT;
+}
+
+/* [ref: src/gpujpeg_encoder.c:736-800] */
+int gpujpeg_encoder_set_option(struct gpujpeg_encoder* encoder, const char* opt, const char* val)
+{
+    if ( !encoder || !opt || !val ) return GPUJPEG_ERROR;
+    if ( strcmp(opt, GPUJPEG_ENC_OPT_OUT) == 0 ) {
+        if ( strcmp(val, GPUJPEG_ENC_OUT_VAL_PINNED) == 0 ) encoder->out_pinned = 1;
+        else if ( strcmp(val, GPUJPEG_ENC_OUT_VAL_PAGEABLE) == 0 ) encoder->out_pinned = 0;
+        else {
+            GJ_ERR("Unknown encoder output type: %s\n", val);
+            return GPUJPEG_ERROR;
+        }
+        return GPUJPEG_NOERR;
+    }
+    if ( strcmp(opt, GPUJPEG_ENCODER_OPT_OUT_PINNED) == 0 ) {
+        encoder->out_pinned = strcmp(val, GPUJPEG_VAL_TRUE) == 0;
+        return GPUJPEG_NOERR;
+    }
+    if ( strcmp(opt, GPUJPEG_ENC_OPT_HDR) == 0 ) {
+        if ( strcmp(val, GPUJPEG_ENC_HDR_VAL_JFIF) == 0 ) return GPUJPEG_NOERR;
+        GJ_ERR("Header type %s is not implemented in this build (JFIF only).\n", val);
+        return GPUJPEG_ERROR;
+    }
+    if ( strcmp(opt, GPUJPEG_ENC_OPT_FLIPPED_BOOL) == 0 || strcmp(opt, GPUJPEG_ENC_OPT_CHANNEL_REMAP) == 0 ||
+         strcmp(opt, GPUJPEG_ENC_OPT_EXIF_TAG) == 0 || strcmp(opt, GPUJPEG_ENC_OPT_METADATA) == 0 ) {
+        GJ_ERR("Encoder option %s is not implemented in this build.\n", opt);
+        return GPUJPEG_ERROR;
+    }
+    GJ_ERR("Invalid encoder option: %s!\n", opt);
+    return GPUJPEG_ERROR;
+}
+
+void gpujpeg_encoder_print_options(void)
+{
+    printf("\t" GPUJPEG_ENC_OPT_OUT "=[" GPUJPEG_ENC_OUT_VAL_PAGEABLE "|" GPUJPEG_ENC_OUT_VAL_PINNED
+           "] - output buffer in pageable or pinned host memory\n");
+    printf("\t" GPUJPEG_ENC_OPT_HDR "=[" GPUJPEG_ENC_HDR_VAL_JFIF "] - JPEG header type (JFIF only in this build)\n");
+}
+
+/* ---- extension used by the parity tests: quantised coefficients of the last frame, natural order ---- */
+GPUJPEG_API int gpujpegx_encoder_get_coefficients(struct gpujpeg_encoder* e, int16_t* out, size_t count)
+{
+    if ( !e || !e->initialised || count != e->geo.coef_count ) return -1;
+    return gj_coef_to_host_natural(e->d_coef, count, out, e->stream);
+}

@@ -1,0 +1,557 @@
+/*
+ * gj_huffman.cu -- restart-interval-parallel Huffman encoder and decoder (sm_100a).
+ *
+ * ENCODER (replaces the reference's three kernels src/gpujpeg_huffman_gpu_encoder.cu:299-404,
+ * 416-502, 562-615 and the host re-ordering loop src/gpujpeg_encoder.c:567-626):
+ *
+ *   k_huff_encode   one WARP per restart segment, one LANE per 8x8 block.  Each lane turns its
+ *                   block into a bit string (sparse walk over the 64-bit non-zero mask of the
+ *                   zig-zag ordered coefficients), a warp prefix sum over the bit lengths places
+ *                   the strings, lanes OR them into a per-warp shared-memory bit buffer, and the
+ *                   warp then byte-stuffs the buffer into the segment's slot.  The buffer is
+ *                   flushed in rounds, so segments of any length (even restart_interval = 0)
+ *                   stream through 2 KB of shared memory.
+ *   k_huff_offsets  exclusive scan of the segment sizes -> final byte offsets (deterministic,
+ *                   unlike the reference's atomicAdd compaction).
+ *   k_huff_compact  copies every segment to its final place and writes RSTn markers, the SOS
+ *                   headers prepared by the host writer and EOI: the device buffer then holds the
+ *                   finished scan data and the host does a single D2H copy.
+ *
+ * DECODER (replaces src/gpujpeg_huffman_gpu_decoder.cu:390-537, 596-610):
+ *   k_huff_decode   one THREAD per restart segment (sequential by nature); lanes advance block
+ *                   by block in lock step, each decoding into a private shared-memory block that
+ *                   the warp then writes out as whole 128-byte lines (no memset of the coefficient
+ *                   buffer, no scattered 2-byte stores).  Tables: 9-bit lookahead + canonical
+ *                   bounds (1.4 KB per table) instead of the reference's 4 x 64 Ki-entry tables.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gj_device.cuh"
+#include "gj_internal.h"
+
+namespace {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane)
+{
+#pragma unroll
+    for ( int d = 1; d < 32; d <<= 1 ) {
+        const int t = __shfl_up_sync(FULL, v, d);
+        if ( lane >= d ) v += t;
+    }
+    return v;
+}
+
+/* =========================================================================================== */
+/* encoder                                                                                       */
+
+constexpr int HE_WARPS = 8;
+constexpr int HE_WORDS = 512;                    // per-warp bit buffer, 32-bit words (2 KB)
+constexpr int HE_CAP_BITS = (HE_WORDS - 2) * 32; // keep slack for the trailing partial word
+
+struct BitSink {
+    uint32_t* buf;   // warp's bit buffer: word i holds stream bits [32i, 32i+32), MSB first
+    int word;        // current word index
+    uint64_t acc;    // pending bits, right aligned (upper bits are stale and ignored)
+    int n;           // number of pending bits, < 32 between calls
+    bool first;      // next flushed word is shared with the preceding lane
+};
+
+__device__ __forceinline__ void sink_put(BitSink& s, uint32_t bits, int len)
+{
+    s.acc = (s.acc << len) | bits;
+    s.n += len;
+    if ( s.n >= 32 ) {
+        const uint32_t w = (uint32_t)(s.acc >> (s.n - 32));
+        if ( s.first ) {
+            atomicOr(&s.buf[s.word], w);
+            s.first = false;
+        }
+        else {
+            s.buf[s.word] = w;
+        }
+        s.word++;
+        s.n -= 32;
+    }
+}
+__device__ __forceinline__ void sink_finish(BitSink& s)
+{
+    if ( s.n > 0 ) {
+        const uint32_t w = (uint32_t)(s.acc << (32 - s.n));  // left-align the tail
+        atomicOr(&s.buf[s.word], w);
+    }
+}
+
+/* stuff + store `nw` complete words of the bit buffer to out[pos...]; returns new pos (uniform) */
+__device__ __forceinline__ uint32_t flush_words(const uint32_t* buf, int nw, uint8_t* out, uint32_t pos, int lane)
+{
+    for ( int base = 0; base < nw; base += 32 ) {
+        const int i = base + lane;
+        const uint32_t w = i < nw ? buf[i] : 0u;
+        int cnt = 0;
+        if ( i < nw ) {
+            // bytes equal to 0xFF need a stuffed zero after them
+            const uint32_t t = w & (w >> 4) & 0x0F0F0F0Fu;               // low nibble = hi&lo nibble
+            const uint32_t ff = t & (t >> 2) & 0x03030303u;
+            const uint32_t m = ff & (ff >> 1) & 0x01010101u;             // 1 per byte that is 0xFF
+            cnt = 4 + __popc(m);
+        }
+        const int incl = warp_incl_scan(cnt, lane);
+        uint8_t* o = out + pos + (incl - cnt);
+        if ( i < nw ) {
+#pragma unroll
+            for ( int j = 3; j >= 0; j-- ) {
+                const uint8_t b = (uint8_t)(w >> (8 * j));
+                *o++ = b;
+                if ( b == 0xFF ) *o++ = 0;
+            }
+        }
+        pos += (uint32_t)__shfl_sync(FULL, incl, 31);
+    }
+    return pos;
+}
+
+__global__ void __launch_bounds__(HE_WARPS * 32)
+k_huff_encode(const int16_t* __restrict__ coef, int nblk, int cps /*components per scan*/, int seg_mcu, int seg_per_scan,
+              int seg_count, uint8_t* __restrict__ tmp, size_t slot_stride, uint32_t* __restrict__ seg_bytes,
+              const gj_dev_enc_tables* __restrict__ tables)
+{
+    __shared__ uint32_t s_ac[2][256];
+    __shared__ uint32_t s_dc[2][16];
+    __shared__ uint32_t s_buf[HE_WARPS][HE_WORDS];
+
+    for ( int i = threadIdx.x; i < 512; i += blockDim.x )
+        s_ac[i >> 8][i & 255] = tables->lut[i >> 8].ac[i & 255];
+    if ( threadIdx.x < 32 ) s_dc[threadIdx.x >> 4][threadIdx.x & 15] = tables->lut[threadIdx.x >> 4].dc[threadIdx.x & 15];
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * HE_WARPS + warp;
+    if ( g >= seg_count ) return;
+    const int scan = g / seg_per_scan, s = g - scan * seg_per_scan;
+    const int first_mcu = s * seg_mcu;
+    const int mcus = min(seg_mcu, nblk - first_mcu);
+    const int nblocks = mcus * cps;
+    uint32_t* buf = s_buf[warp];
+    uint8_t* out = tmp + (size_t)g * slot_stride;
+    uint32_t out_pos = 0;
+    int carry = 0;  // bits already sitting in buf[0] (always < 32 between rounds)
+
+    for ( int i = lane; i < HE_WORDS; i += 32 )
+        buf[i] = 0;
+    __syncwarp();
+
+    int prev_dc = 0;  // DC of the same component's previous block, valid in lanes < cps at round start
+    for ( int base = 0; base < nblocks; base += 32 ) {
+        const int j = base + lane;
+        const bool active = j < nblocks;
+        int mcu = 0, ci = 0;
+        if ( cps == 1 ) mcu = j;
+        else { mcu = j / cps; ci = j - mcu * cps; }
+        const int comp = cps == 1 ? scan : ci;
+        const int tbl = comp == 0 ? 0 : 1;
+        const int16_t* blk = coef + ((size_t)comp * nblk + first_mcu + mcu) * 64;
+
+        /* ---- pass 1: non-zero mask, DC, exact bit length ---- */
+        uint64_t nz = 0;
+        int dc = 0;
+        if ( active ) {
+            const uint4* p = reinterpret_cast<const uint4*>(blk);
+#pragma unroll
+            for ( int i = 0; i < 8; i++ ) {
+                const uint4 t = __ldg(p + i);
+                const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for ( int q = 0; q < 4; q++ ) {
+                    const uint64_t lo = (w[q] & 0xFFFFu) ? 1ull : 0ull;
+                    const uint64_t hi = (w[q] >> 16) ? 1ull : 0ull;
+                    nz |= (lo | (hi << 1)) << (8 * i + 2 * q);
+                }
+                if ( i == 0 ) dc = (int)(short)(t.x & 0xFFFFu);
+            }
+        }
+        /* DC predictor: previous block of the same component inside the segment, 0 at its start
+         * [ref: src/gpujpeg_huffman_cpu_encoder.c:147-148, 361-364] */
+        int pred = __shfl_up_sync(FULL, dc, cps);
+        if ( lane < cps ) pred = prev_dc;
+        if ( j < cps ) pred = 0;
+        prev_dc = __shfl_sync(FULL, dc, (32 - cps + lane) & 31);
+        const int diff = dc - pred;
+        const int dcat = gj_category(diff);
+        int len = 0;
+        if ( active ) {
+            len = (int)(s_dc[tbl][dcat] & 31u) + dcat;
+            uint64_t m = nz & ~1ull;
+            int last = 0;
+            while ( m ) {
+                const int k = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                const int run = k - last - 1;
+                last = k;
+                const int v = blk[k];
+                const int size = gj_category(v);
+                len += (run >> 4) * (int)(s_ac[tbl][0xF0] & 31u) + (int)(s_ac[tbl][((run & 15) << 4) | size] & 31u) + size;
+            }
+            if ( last < 63 ) len += (int)(s_ac[tbl][0] & 31u);
+        }
+        const int incl = warp_incl_scan(len, lane);
+        const int excl = incl - len;
+
+        /* ---- pass 2: emit, in as many sub-rounds as the buffer needs (normally one) ---- */
+        int lane0 = 0;
+        while ( lane0 < 32 ) {
+            const int rel0 = __shfl_sync(FULL, excl, lane0);
+            const int mypos = carry + (excl - rel0);
+            const bool fits = lane >= lane0 && mypos + len <= HE_CAP_BITS;
+            const int nfit = __popc(__ballot_sync(FULL, fits));   // fits is monotone in lane
+            if ( nfit == 0 ) break;  // cannot happen (a block is < 2 Kbit, the buffer 16 Kbit); never spin
+            const bool mine = lane >= lane0 && lane < lane0 + nfit;
+            if ( mine && active ) {
+                BitSink sk;
+                sk.buf = buf;
+                sk.word = mypos >> 5;
+                sk.acc = 0;
+                sk.n = mypos & 31;
+                sk.first = true;
+                const uint32_t de = s_dc[tbl][dcat];
+                sink_put(sk, ((de >> 5) << dcat) | (dcat ? gj_value_bits(diff, dcat) : 0u), (int)(de & 31u) + dcat);
+                uint64_t m = nz & ~1ull;
+                int last = 0;
+                const uint32_t zrl = s_ac[tbl][0xF0];
+                while ( m ) {
+                    const int k = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    int run = k - last - 1;
+                    last = k;
+                    const int v = blk[k];
+                    const int size = gj_category(v);
+                    while ( run > 15 ) {
+                        sink_put(sk, zrl >> 5, (int)(zrl & 31u));
+                        run -= 16;
+                    }
+                    const uint32_t e = s_ac[tbl][(run << 4) | size];
+                    sink_put(sk, ((e >> 5) << size) | gj_value_bits(v, size), (int)(e & 31u) + size);
+                }
+                if ( last < 63 ) {
+                    const uint32_t e = s_ac[tbl][0];
+                    sink_put(sk, e >> 5, (int)(e & 31u));
+                }
+                sink_finish(sk);
+            }
+            __syncwarp();
+            const int lastl = lane0 + nfit - 1;
+            const int newbits = carry + (__shfl_sync(FULL, incl, lastl) - rel0);
+            const int nw = newbits >> 5;
+            out_pos = flush_words(buf, nw, out, out_pos, lane);
+            __syncwarp();
+            /* keep the trailing partial word as the new word 0, clear what was used */
+            const uint32_t tail = buf[nw];
+            __syncwarp();
+            for ( int i = lane; i <= nw; i += 32 )
+                buf[i] = 0;
+            __syncwarp();
+            if ( lane == 0 ) buf[0] = tail;
+            __syncwarp();
+            carry = newbits & 31;
+            lane0 += nfit;
+        }
+    }
+
+    /* segment end: pad with 1-bits to a byte boundary, emit the remaining <= 4 bytes
+     * [ref: src/gpujpeg_huffman_cpu_encoder.c:115-128] */
+    if ( lane == 0 ) {
+        uint32_t w = buf[0];
+        const int nbytes = (carry + 7) >> 3;
+        if ( carry & 7 ) w |= ((1u << (8 - (carry & 7))) - 1u) << (32 - nbytes * 8);
+        uint8_t* o = out + out_pos;
+        for ( int j = 0; j < nbytes; j++ ) {
+            const uint8_t b = (uint8_t)(w >> (24 - 8 * j));
+            *o++ = b;
+            if ( b == 0xFF ) *o++ = 0;
+        }
+        seg_bytes[g] = (uint32_t)(o - out);
+    }
+}
+
+/* exclusive scan over segment sizes -> byte offsets in the finished stream.  One CTA. */
+constexpr int OFF_THREADS = 1024;
+__global__ void __launch_bounds__(OFF_THREADS)
+k_huff_offsets(const uint32_t* __restrict__ seg_bytes, int seg_count, int seg_per_scan, uint32_t header_size, int sos_len,
+               uint64_t stream_cap, uint64_t* __restrict__ seg_off, uint64_t* __restrict__ info)
+{
+    __shared__ uint64_t s_part[OFF_THREADS];
+    const int per = (seg_count + OFF_THREADS - 1) / OFF_THREADS;
+    const int a = threadIdx.x * per, b = min(seg_count, a + per);
+    uint64_t sum = 0;
+    for ( int g = a; g < b; g++ ) {
+        const int s = g % seg_per_scan;
+        // every segment but the last of its scan is followed by a 2-byte RSTn marker;
+        // the first segment of a scan is preceded by the SOS header
+        sum += seg_bytes[g] + (s + 1 < seg_per_scan ? 2u : 0u) + (s == 0 ? (uint32_t)sos_len : 0u);
+    }
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for ( int d = 1; d < OFF_THREADS; d <<= 1 ) {
+        uint64_t t = 0;
+        if ( (int)threadIdx.x >= d ) t = s_part[threadIdx.x - d];
+        __syncthreads();
+        s_part[threadIdx.x] += t;
+        __syncthreads();
+    }
+    uint64_t off = header_size + (threadIdx.x ? s_part[threadIdx.x - 1] : 0);
+    for ( int g = a; g < b; g++ ) {
+        const int s = g % seg_per_scan;
+        if ( s == 0 ) off += (uint32_t)sos_len;
+        seg_off[g] = off;
+        off += seg_bytes[g] + (s + 1 < seg_per_scan ? 2u : 0u);
+    }
+    if ( threadIdx.x == OFF_THREADS - 1 ) {
+        const uint64_t total = header_size + s_part[OFF_THREADS - 1] + 2;  // + EOI
+        info[0] = total;
+        info[1] = total > stream_cap ? 1 : 0;
+    }
+}
+
+/* move every segment to its final offset; add RSTn / SOS / EOI.  One warp per segment. */
+__global__ void __launch_bounds__(256)
+k_huff_compact(const uint8_t* __restrict__ tmp, size_t slot_stride, const uint32_t* __restrict__ seg_bytes,
+               const uint64_t* __restrict__ seg_off, int seg_count, int seg_per_scan, const uint8_t* __restrict__ sos,
+               int sos_len, uint8_t* __restrict__ stream, const uint64_t* __restrict__ info)
+{
+    if ( info[1] ) return;  // would overflow the stream buffer: host reports the error
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * 8 + warp;
+    if ( g >= seg_count ) return;
+    const int scan = g / seg_per_scan, s = g - scan * seg_per_scan;
+    const uint8_t* src = tmp + (size_t)g * slot_stride;
+    const uint32_t n = seg_bytes[g];
+    uint8_t* dst = stream + seg_off[g];
+    /* head bytes up to 16-byte alignment of dst, then 16 B stores assembled from 4 B loads */
+    uint32_t i = 0;
+    const uint32_t head = min(n, (uint32_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15));
+    if ( lane < head ) dst[lane] = src[lane];
+    i = head;
+    const uint32_t sh = (i & 3) * 8;
+    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src + (i & ~3u));
+    const uint32_t nvec = (n - i) >> 4;
+    for ( uint32_t v = lane; v < nvec; v += 32 ) {
+        const uint32_t* p = s32 + v * 4;
+        uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3];
+        if ( sh ) {
+            const uint32_t w4 = p[4];
+            w0 = __funnelshift_r(w0, w1, sh);
+            w1 = __funnelshift_r(w1, w2, sh);
+            w2 = __funnelshift_r(w2, w3, sh);
+            w3 = __funnelshift_r(w3, w4, sh);
+        }
+        reinterpret_cast<uint4*>(dst + i)[v] = make_uint4(w0, w1, w2, w3);
+    }
+    i += nvec << 4;
+    if ( i + lane < n ) dst[i + lane] = src[i + lane];   // tail < 16 bytes
+    if ( lane == 0 ) {
+        if ( s + 1 < seg_per_scan ) {
+            /* RSTn, n = index in scan mod 8 [ref: src/gpujpeg_huffman_cpu_encoder.c:366-367] */
+            dst[n] = 0xFF;
+            dst[n + 1] = (uint8_t)(0xD0 + (s & 7));
+        }
+        else if ( g + 1 == seg_count ) {
+            dst[n] = 0xFF;
+            dst[n + 1] = 0xD9;
+        }
+    }
+    if ( s == 0 && lane < sos_len ) (dst - sos_len)[lane] = sos[scan * sos_len + lane];
+}
+
+/* =========================================================================================== */
+/* decoder                                                                                       */
+
+constexpr int HD_THREADS = 128;
+constexpr int HD_STRIDE = 33;  // words per private block (32 + 1 pad: bank = (tid + word) % 32)
+
+struct DecTabs {
+    gj_dec_lut t[2][4];
+};
+
+struct BitSource {
+    const uint8_t* p;
+    const uint8_t* end;
+    uint64_t acc;
+    int n;
+};
+
+__device__ __forceinline__ void src_fill(BitSource& r)
+{
+    while ( r.n <= 56 ) {
+        uint32_t b = 0;  // past the end of the segment: zeros (only corrupt streams get here)
+        if ( r.p < r.end ) {
+            b = *r.p++;
+            if ( b == 0xFF && r.p < r.end && *r.p == 0 ) r.p++;  // drop the stuffed zero
+        }
+        r.acc = (r.acc << 8) | b;
+        r.n += 8;
+    }
+}
+__device__ __forceinline__ uint32_t src_peek16(const BitSource& r) { return (uint32_t)(r.acc >> (r.n - 16)) & 0xFFFFu; }
+__device__ __forceinline__ uint32_t src_get(BitSource& r, int len)
+{
+    r.n -= len;
+    return (uint32_t)(r.acc >> r.n) & ((1u << len) - 1u);
+}
+
+__device__ __forceinline__ int decode_symbol(BitSource& r, const gj_dec_lut& t)
+{
+    const uint32_t peek = src_peek16(r);
+    const uint32_t e = t.look[peek >> (16 - GJ_DEC_LOOK_BITS)];
+    if ( e & 15u ) {
+        r.n -= (int)(e & 15u);
+        return (int)(e >> 4);
+    }
+    int l = GJ_DEC_LOOK_BITS + 1;
+    while ( l <= 16 && peek >= t.maxcode[l] ) l++;
+    if ( l > 16 ) {  // garbage: consume and return 0 like [ref: src/gpujpeg_huffman_cpu_decoder.c:155-159]
+        r.n -= 16;
+        return 0;
+    }
+    r.n -= l;
+    return t.vals[((int)(peek >> (16 - l)) + t.valoff[l]) & 255];
+}
+
+__global__ void __launch_bounds__(HD_THREADS)
+k_huff_decode(const uint8_t* __restrict__ file, const uint32_t* __restrict__ seg_off, const uint32_t* __restrict__ seg_len,
+              int seg_count, int seg_per_scan, int cps, int seg_mcu, int nblk, const __grid_constant__ gj_huff_dec_args a,
+              int16_t* __restrict__ coef, const gj_dev_dec_tables* __restrict__ tables)
+{
+    __shared__ DecTabs s_tab;
+    __shared__ uint32_t s_blk[HD_THREADS * HD_STRIDE];
+
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&tables->lut[0][0]);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
+        for ( int i = threadIdx.x; i < (int)(sizeof(DecTabs) / 4); i += HD_THREADS )
+            dst[i] = src[i];
+        for ( int i = threadIdx.x; i < HD_THREADS * HD_STRIDE; i += HD_THREADS )
+            s_blk[i] = 0;
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int g0 = (blockIdx.x * HD_THREADS + threadIdx.x) & ~31;  // first segment of this warp
+    if ( g0 >= seg_count ) return;
+    const int g = g0 + lane;
+    const bool live = g < seg_count;
+    int scan = 0, s = 0, nblocks = 0;
+    BitSource r = {nullptr, nullptr, 0, 0};
+    if ( live ) {
+        scan = g / seg_per_scan;
+        s = g - scan * seg_per_scan;
+        nblocks = min(seg_mcu, nblk - s * seg_mcu) * cps;
+        r.p = file + seg_off[g];
+        r.end = r.p + seg_len[g];
+    }
+    const int max_blocks = seg_mcu * cps;
+    int16_t* mine = reinterpret_cast<int16_t*>(s_blk + threadIdx.x * HD_STRIDE);
+    uint32_t* wbase = s_blk + (threadIdx.x & ~31) * HD_STRIDE;
+    int pred[GJ_MAX_COMP] = {0, 0, 0, 0};
+
+    for ( int b = 0; b < max_blocks; b++ ) {
+        int mcu = b, ci = 0;
+        if ( cps != 1 ) { mcu = b / cps; ci = b - mcu * cps; }
+        if ( live && b < nblocks ) {
+            const gj_dec_lut& tdc = s_tab.t[0][a.scan_td[scan][ci]];
+            const gj_dec_lut& tac = s_tab.t[1][a.scan_ta[scan][ci]];
+            src_fill(r);
+            int sz = decode_symbol(r, tdc) & 15;
+            int diff = 0;
+            if ( sz ) diff = gj_extend((int)src_get(r, sz), sz);
+            /* per-component predictor, reset at segment start [ref: src/gpujpeg_huffman_cpu_decoder.c:407-411] */
+            int pr;
+            if ( ci == 0 ) pr = (pred[0] += diff);
+            else if ( ci == 1 ) pr = (pred[1] += diff);
+            else if ( ci == 2 ) pr = (pred[2] += diff);
+            else pr = (pred[3] += diff);
+            mine[0] = (int16_t)pr;
+            for ( int k = 1; k < 64; ) {
+                src_fill(r);
+                const int rs = decode_symbol(r, tac);
+                const int run = rs >> 4;
+                sz = rs & 15;
+                if ( sz ) {
+                    k += run;
+                    const int v = gj_extend((int)src_get(r, sz), sz);
+                    if ( k < 64 ) mine[k] = (int16_t)v;
+                    k++;
+                }
+                else {
+                    if ( run != 15 ) break;  // EOB
+                    k += 16;                 // ZRL
+                }
+            }
+        }
+        __syncwarp();
+        /* write the 32 private blocks of this warp out as 128-byte lines and clear them */
+        int gs = g0 / seg_per_scan, ss = g0 - gs * seg_per_scan;
+        for ( int i = 0; i < 32; i++ ) {
+            const bool ok = g0 + i < seg_count && b < min(seg_mcu, nblk - ss * seg_mcu) * cps;
+            const uint32_t w = wbase[i * HD_STRIDE + lane];
+            wbase[i * HD_STRIDE + lane] = 0;
+            if ( ok ) {
+                const int comp = a.scan_comp[gs][ci];
+                uint32_t* dst = reinterpret_cast<uint32_t*>(coef + ((size_t)comp * nblk + (size_t)ss * seg_mcu + mcu) * 64);
+                dst[lane] = w;
+            }
+            if ( ++ss == seg_per_scan ) { ss = 0; gs++; }
+        }
+        __syncwarp();
+    }
+}
+
+/* zig-zag device coefficients -> natural order (debug / parity-test path only) */
+__constant__ uint8_t c_zz2nat[64] = {
+    0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+    41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+    30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+__global__ void k_coef_to_natural(const int16_t* __restrict__ in, int16_t* __restrict__ out, size_t nblocks)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ( i >= nblocks * 64 ) return;
+    const int k = (int)(i & 63);
+    out[(i & ~(size_t)63) + c_zz2nat[k]] = in[i];
+}
+
+}  // namespace
+
+extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_stream_t stream)
+{
+    const int seg_count = a->seg_per_scan * a->scan_count;
+    k_huff_encode<<<(seg_count + HE_WARPS - 1) / HE_WARPS, HE_WARPS * 32, 0, stream>>>(
+        a->d_coef, a->nblk, a->comps_per_scan, a->seg_mcu, a->seg_per_scan, seg_count, a->d_tmp, a->slot_stride,
+        a->d_seg_bytes, a->d_tables);
+    k_huff_offsets<<<1, OFF_THREADS, 0, stream>>>(a->d_seg_bytes, seg_count, a->seg_per_scan, a->header_size, a->sos_len,
+                                                  (uint64_t)a->stream_cap, a->d_seg_off, a->d_info);
+    k_huff_compact<<<(seg_count + 7) / 8, 256, 0, stream>>>(a->d_tmp, a->slot_stride, a->d_seg_bytes, a->d_seg_off,
+                                                            seg_count, a->seg_per_scan, a->d_sos, a->sos_len,
+                                                            a->d_stream, a->d_info);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+extern "C" int gj_launch_huffman_decode(const struct gj_huff_dec_args* a, gj_stream_t stream)
+{
+    k_huff_decode<<<(a->seg_count + HD_THREADS - 1) / HD_THREADS, HD_THREADS, 0, stream>>>(
+        a->d_file, a->d_seg_off, a->d_seg_len, a->seg_count, a->seg_per_scan, a->comps_per_scan, a->seg_mcu, a->nblk, *a,
+        a->d_coef, a->d_tables);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+extern "C" int gj_coef_to_host_natural(const int16_t* d_coef, size_t count, int16_t* h_out, gj_stream_t stream)
+{
+    int16_t* d_tmp = nullptr;
+    if ( cudaMalloc(&d_tmp, count * sizeof(int16_t)) != cudaSuccess ) return -1;
+    const size_t nblocks = count / 64;
+    k_coef_to_natural<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(d_coef, d_tmp, nblocks);
+    cudaMemcpyAsync(h_out, d_tmp, count * sizeof(int16_t), cudaMemcpyDeviceToHost, stream);
+    const cudaError_t e = cudaStreamSynchronize(stream);
+    cudaFree(d_tmp);
+    return e == cudaSuccess ? 0 : -1;
+}

@@ -1,0 +1,225 @@
+/*
+ * gj_internal.h -- internal structures of the B200-native libgpujpeg replacement.
+ *
+ * Host code is plain C (north_star: "host code stays C calling into a thin C-ABI layer of
+ * hand-written sm_100a CUDA kernels").  The stage launchers at the bottom are that thin layer:
+ * extern "C", plain pointers and sizes, implemented in the .cu files.
+ *
+ * Data layout in HBM:
+ *   raw      u8   RGB interleaved, row pitch 3*W+padding                      (3 B/pixel)
+ *   coef     i16  [comp][block][64], blocks in raster order, coefficients in ZIG-ZAG order
+ *                 (the reference keeps natural order, src/gpujpeg_dct_gpu.cu:286-293; zig-zag is
+ *                 free for the producer here and removes the gather from both Huffman kernels)
+ *   scan tmp u8   one fixed-stride slot per restart segment (encoder only)
+ *   stream   u8   the finished JPEG byte stream (encoder) / the input file bytes (decoder)
+ */
+#ifndef GJ_INTERNAL_H
+#define GJ_INTERNAL_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gpujpeg_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GJ_MAX_COMP 4
+#define GJ_SOS_LEN_1 10 /* bytes of an SOS header with one component */
+
+/* ---- logging [ref: src/gpujpeg_common_internal.h:125-150] ---- */
+#define GJ_ERR(...) (void)(fprintf(stderr, "[GPUJPEG] [Error] " __VA_ARGS__))
+#define GJ_WARN(...) (void)(fprintf(stderr, "[GPUJPEG] [Warning] " __VA_ARGS__))
+#define GJ_VERBOSE(v, ...) do { if ( (v) >= GPUJPEG_LL_VERBOSE ) (void)fprintf(stderr, "[GPUJPEG] [Verbose] " __VA_ARGS__); } while ( 0 )
+#define GJ_DEBUG(v, ...) do { if ( (v) >= GPUJPEG_LL_DEBUG ) (void)fprintf(stderr, "[GPUJPEG] [Debug] " __VA_ARGS__); } while ( 0 )
+
+/* ---- tables (gj_tables.c) ---- */
+extern const uint8_t gj_zigzag_to_natural[64];
+extern const uint8_t gj_natural_to_zigzag[64];
+
+/* Huffman specification as carried by a DHT marker */
+struct gj_huff_spec {
+    uint8_t bits[17]; /* bits[1..16] */
+    uint8_t vals[256];
+    int nvals;
+};
+void gj_huff_spec_default(int cls /*0 lum,1 chroma*/, int kind /*0 DC,1 AC*/, struct gj_huff_spec* spec);
+
+/* quantisation: raw zig-zag u8 table for a quality [ref: src/gpujpeg_table.c:83-99] */
+void gj_quant_raw(int cls, int quality, uint8_t raw_zz[64]);
+/* forward table in ZIG-ZAG coefficient order: fwd_zz[k] = 1/(raw[k]*aan[x]*aan[y]*8) as float
+ * (same values as the reference's transposed table, src/gpujpeg_table.c:112-120, re-indexed) */
+void gj_quant_forward_zz(const uint8_t raw_zz[64], float fwd_zz[64]);
+
+/* Encoder LUTs for the device: per table set (0 = luminance, 1 = chrominance)
+ *   ac[sym]  = (code << 5) | len   (len 0 = symbol has no code)
+ *   dc[cat]  = (code << 5) | len */
+struct gj_enc_lut {
+    uint32_t ac[256];
+    uint32_t dc[16];
+};
+void gj_enc_lut_build(const struct gj_huff_spec* dc, const struct gj_huff_spec* ac, struct gj_enc_lut* lut);
+
+/* Decoder LUT for the device, one per (class, id):
+ *   look[peek9] = (symbol << 4) | len for codes of length <= 9, 0 if longer
+ *   maxcode[l]  = largest code of length l left-justified to 16 bits + 1 (exclusive bound), l = 1..16
+ *   valoff[l]   = valptr[l] - mincode[l]
+ *   vals[]      = HUFFVAL */
+#define GJ_DEC_LOOK_BITS 9
+struct gj_dec_lut {
+    uint16_t look[1 << GJ_DEC_LOOK_BITS];
+    uint32_t maxcode[18];
+    int32_t valoff[18];
+    uint8_t vals[256];
+};
+int gj_dec_lut_build(const struct gj_huff_spec* spec, struct gj_dec_lut* lut);
+
+/* ---- geometry (gj_geometry.c)  [ref: src/gpujpeg_common.c:628-1106] ---- */
+struct gj_geometry {
+    int width, height, comp_count;
+    int pitch;            /* bytes per raw row */
+    int data_width, data_height;
+    int bcx, bcy, nblk;   /* 8x8 blocks per component */
+    int interleaved;
+    int restart_interval; /* as given (0 = none) */
+    int seg_mcu;          /* MCUs per segment (restart_interval or all) */
+    int scan_count;
+    int comps_per_scan;   /* 1 (non-interleaved) or comp_count */
+    int seg_per_scan;
+    int seg_count;        /* scan_count * seg_per_scan */
+    size_t raw_size;      /* bytes of the raw image */
+    size_t coef_count;    /* int16 coefficients, all components */
+    size_t slot_stride;   /* bytes reserved per segment in the encoder's scan tmp buffer */
+    size_t stream_cap;    /* capacity of the finished stream buffer */
+};
+int gj_geometry_init(struct gj_geometry* g, const struct gpujpeg_parameters* param,
+                     const struct gpujpeg_image_parameters* param_image);
+
+/* ---- codestream writer (gj_writer.c)  [ref: src/gpujpeg_writer.c] ---- */
+size_t gj_write_header(uint8_t* out, const struct gpujpeg_parameters* param,
+                       const struct gpujpeg_image_parameters* param_image, const uint8_t raw_q[2][64],
+                       const struct gj_huff_spec spec[2][2]);
+size_t gj_write_sos(uint8_t* out, const struct gpujpeg_parameters* param, int scan_index);
+
+/* ---- codestream reader (gj_reader.c)  [ref: src/gpujpeg_reader.c] ---- */
+struct gj_scan_info {
+    int ncomp;
+    int comp[GJ_MAX_COMP];
+    int td[GJ_MAX_COMP], ta[GJ_MAX_COMP];
+    size_t begin, end; /* entropy-coded bytes [begin,end) in the file */
+    int first_segment, segment_count;
+};
+struct gj_stream {
+    int width, height, comp_count;
+    int restart_interval;
+    int comp_id[GJ_MAX_COMP], comp_hv[GJ_MAX_COMP], comp_tq[GJ_MAX_COMP];
+    uint8_t qt[4][64];
+    int have_qt[4];
+    struct gj_huff_spec huff[2][4]; /* [class][id] */
+    int have_huff[2][4];
+    int scan_count;
+    struct gj_scan_info scan[GJ_MAX_COMP];
+    enum gpujpeg_color_space color_space;
+    enum gpujpeg_header_type header_type;
+    const char* comment;
+    size_t header_size;
+    int interleaved;
+};
+/* parse all markers; does not split scans into segments */
+int gj_reader_parse(const uint8_t* data, size_t size, struct gj_stream* s, int verbose);
+/* split scan data at RSTn markers: fills seg_off/seg_len (file offsets of stuffed entropy bytes) */
+int gj_reader_split(const uint8_t* data, struct gj_stream* s, uint32_t* seg_off, uint32_t* seg_len, int max_segments);
+
+/* ---- device side: the C-ABI stage launchers (implemented in *.cu) ---- */
+typedef struct CUstream_st* gj_stream_t;
+
+/* constant tables a coder instance keeps on the device */
+struct gj_dev_enc_tables {
+    float fwd_zz[2][64];      /* forward quant tables, zig-zag order */
+    struct gj_enc_lut lut[2]; /* Huffman encoder LUTs */
+};
+struct gj_dev_dec_tables {
+    uint16_t qinv_zz[4][64];  /* dequantisation tables by table id, zig-zag order */
+    struct gj_dec_lut lut[2][4];
+};
+
+/* K1: RGB u8 interleaved -> quantised zig-zag coefficients (fused colour transform + FDCT + quant)
+ * [replaces ref: src/gpujpeg_preprocessor.cu:562-586 + src/gpujpeg_dct_gpu.cu:621-678] */
+int gj_launch_fdct_rgb444(const uint8_t* d_raw, int width, int height, int pitch, int16_t* d_coef, int bcx,
+                          int bcy, const struct gj_dev_enc_tables* d_tables, gj_stream_t stream);
+
+/* K2: Huffman-encode every restart segment and assemble the finished scan data
+ * [replaces ref: src/gpujpeg_huffman_gpu_encoder.cu:1071-1167 + host loop src/gpujpeg_encoder.c:567-626]
+ * d_stream receives [header gap][SOS][scan 0]...[EOI]; d_info[0] = total bytes, d_info[1] = error flag */
+struct gj_huff_enc_args {
+    const int16_t* d_coef;
+    int nblk, comp_count, comps_per_scan, seg_mcu, seg_per_scan, scan_count;
+    uint8_t* d_tmp;
+    size_t slot_stride;
+    uint32_t* d_seg_bytes;  /* [seg_count] */
+    uint64_t* d_seg_off;    /* [seg_count] */
+    uint8_t* d_stream;
+    size_t stream_cap;
+    uint32_t header_size;
+    const uint8_t* d_sos;   /* scan_count SOS headers, sos_len bytes each */
+    int sos_len;
+    uint64_t* d_info;       /* [4]: total, error, reserved */
+    const struct gj_dev_enc_tables* d_tables;
+};
+int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_stream_t stream);
+
+/* K3: Huffman-decode every restart segment into zig-zag coefficients
+ * [replaces ref: src/gpujpeg_huffman_gpu_decoder.cu:663-746] */
+struct gj_huff_dec_args {
+    const uint8_t* d_file;      /* the JPEG bytes */
+    const uint32_t* d_seg_off;  /* [seg_count] file offset of each segment's entropy bytes */
+    const uint32_t* d_seg_len;
+    int seg_count, seg_per_scan, scan_count, comps_per_scan, seg_mcu, nblk;
+    int scan_comp[GJ_MAX_COMP][GJ_MAX_COMP]; /* component index of the i-th component of scan s */
+    int scan_td[GJ_MAX_COMP][GJ_MAX_COMP], scan_ta[GJ_MAX_COMP][GJ_MAX_COMP];
+    int16_t* d_coef;
+    const struct gj_dev_dec_tables* d_tables;
+};
+int gj_launch_huffman_decode(const struct gj_huff_dec_args* a, gj_stream_t stream);
+
+/* K4: zig-zag coefficients -> RGB u8 interleaved (fused dequant + IDCT + colour transform)
+ * idct_flavour: 0 = integer (gpujpeg_idct_cpu), 1 = float GPU-reference
+ * [replaces ref: src/gpujpeg_dct_gpu.cu:681-727 + src/gpujpeg_postprocessor.cu:444-496] */
+int gj_launch_idct_rgb444(const int16_t* d_coef, int bcx, int bcy, const int comp_tq[3], uint8_t* d_raw, int width,
+                          int height, int pitch, int idct_flavour, const struct gj_dev_dec_tables* d_tables,
+                          gj_stream_t stream);
+
+/* debug/test helper: device coefficient buffer (zig-zag) -> host natural order, block-major */
+int gj_coef_to_host_natural(const int16_t* d_coef, size_t count, int16_t* h_out, gj_stream_t stream);
+
+/* thin wrappers over the CUDA runtime so the host files stay plain C without cuda headers */
+int gj_cuda_malloc(void** p, size_t size);
+int gj_cuda_free(void* p);
+int gj_cuda_malloc_host(void** p, size_t size);
+int gj_cuda_free_host(void* p);
+int gj_cuda_memcpy_h2d_async(void* dst, const void* src, size_t size, gj_stream_t s);
+int gj_cuda_memcpy_d2h_async(void* dst, const void* src, size_t size, gj_stream_t s);
+int gj_cuda_memcpy_d2d_async(void* dst, const void* src, size_t size, gj_stream_t s);
+int gj_cuda_memset_async(void* dst, int v, size_t size, gj_stream_t s);
+int gj_cuda_stream_sync(gj_stream_t s);
+int gj_cuda_pointer_is_device(const void* p);
+const char* gj_cuda_last_error(void);
+/* event timers [ref: src/gpujpeg_common_internal.h:156-205] */
+struct gj_timer { void* start; void* stop; int armed; };
+int gj_timer_create(struct gj_timer* t);
+void gj_timer_destroy(struct gj_timer* t);
+void gj_timer_start(struct gj_timer* t, gj_stream_t s);
+void gj_timer_stop(struct gj_timer* t, gj_stream_t s);
+double gj_timer_ms(struct gj_timer* t);
+int gj_cuda_device_count(void);
+int gj_cuda_device_props(int dev, struct gpujpeg_device_info* info);
+int gj_cuda_set_device(int dev);
+int gj_cuda_get_device(void);
+void gj_cuda_device_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,107 @@
+/* Exposes a few internal host functions of the product (tables, writer, reader) to the CPU tests.
+ * Compiled by tests/_shims.py together with gj_tables.c and gj_codestream.c (no CUDA involved). */
+#include <string.h>
+
+#include "../../gpujpeg_b200/csrc/gj_internal.h"
+
+int shim_header(int width, int height, int quality, int rst, int interleaved, unsigned char* out)
+{
+    struct gpujpeg_parameters p;
+    struct gpujpeg_image_parameters pi;
+    memset(&p, 0, sizeof p);
+    memset(&pi, 0, sizeof pi);
+    p.quality = quality;
+    p.restart_interval = rst;
+    p.interleaved = interleaved;
+    p.comp_count = 3;
+    for ( int c = 0; c < 4; c++ )
+        p.sampling_factor[c].horizontal = p.sampling_factor[c].vertical = 1;
+    p.color_space_internal = GPUJPEG_YCBCR_BT601_256LVLS;
+    pi.width = width;
+    pi.height = height;
+    pi.color_space = GPUJPEG_RGB;
+    pi.pixel_format = GPUJPEG_444_U8_P012;
+    uint8_t raw[2][64];
+    struct gj_huff_spec spec[2][2];
+    for ( int t = 0; t < 2; t++ ) {
+        gj_quant_raw(t, quality, raw[t]);
+        for ( int k = 0; k < 2; k++ )
+            gj_huff_spec_default(t, k, &spec[t][k]);
+    }
+    size_t n = gj_write_header(out, &p, &pi, raw, spec);
+    n += gj_write_sos(out + n, &p, 0);
+    return (int)n;
+}
+
+void shim_forward_table_zz(int cls, int quality, float* fwd_zz, unsigned char* raw_zz)
+{
+    gj_quant_raw(cls, quality, raw_zz);
+    gj_quant_forward_zz(raw_zz, fwd_zz);
+}
+
+void shim_enc_lut(int cls, unsigned* ac256, unsigned* dc16)
+{
+    struct gj_huff_spec dc, ac;
+    struct gj_enc_lut lut;
+    gj_huff_spec_default(cls, 0, &dc);
+    gj_huff_spec_default(cls, 1, &ac);
+    gj_enc_lut_build(&dc, &ac, &lut);
+    memcpy(ac256, lut.ac, sizeof lut.ac);
+    memcpy(dc16, lut.dc, sizeof lut.dc);
+}
+
+/* decode one symbol from a 16-bit peek with the device LUT logic (mirrors decode_symbol in gj_huffman.cu) */
+int shim_dec_lut_symbol(int cls, int kind, unsigned peek16, int* len)
+{
+    struct gj_huff_spec spec;
+    struct gj_dec_lut t;
+    gj_huff_spec_default(cls, kind, &spec);
+    if ( gj_dec_lut_build(&spec, &t) ) return -1;
+    const unsigned e = t.look[peek16 >> (16 - GJ_DEC_LOOK_BITS)];
+    if ( e & 15u ) {
+        *len = (int)(e & 15u);
+        return (int)(e >> 4);
+    }
+    int l = GJ_DEC_LOOK_BITS + 1;
+    while ( l <= 16 && peek16 >= t.maxcode[l] ) l++;
+    if ( l > 16 ) {
+        *len = 16;
+        return -2;
+    }
+    *len = l;
+    return t.vals[((int)(peek16 >> (16 - l)) + t.valoff[l]) & 255];
+}
+
+/* parse + split; returns number of segments, fills a few fields */
+int shim_parse(const unsigned char* data, size_t size, int* info /*[8]*/, unsigned* seg_off, unsigned* seg_len, int max_seg)
+{
+    struct gj_stream s;
+    if ( gj_reader_parse(data, size, &s, 0) ) return -1;
+    info[0] = s.width;
+    info[1] = s.height;
+    info[2] = s.comp_count;
+    info[3] = s.restart_interval;
+    info[4] = s.scan_count;
+    info[5] = s.interleaved;
+    info[6] = (int)s.header_size;
+    info[7] = (int)s.color_space;
+    return gj_reader_split(data, &s, seg_off, seg_len, max_seg);
+}
+
+int shim_geometry(int width, int height, int rst, int interleaved, long* out /*[8]*/)
+{
+    struct gpujpeg_parameters p;
+    struct gpujpeg_image_parameters pi;
+    memset(&p, 0, sizeof p);
+    memset(&pi, 0, sizeof pi);
+    p.restart_interval = rst;
+    p.interleaved = interleaved;
+    p.comp_count = 3;
+    pi.width = width;
+    pi.height = height;
+    struct gj_geometry g;
+    gj_geometry_init(&g, &p, &pi);
+    out[0] = g.bcx; out[1] = g.bcy; out[2] = g.nblk; out[3] = g.seg_per_scan; out[4] = g.seg_count;
+    out[5] = g.scan_count; out[6] = (long)g.slot_stride; out[7] = (long)g.coef_count;
+    return 0;
+}

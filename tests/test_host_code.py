@@ -1,0 +1,99 @@
+"""Host-side code of the product (tables, codestream writer/reader, geometry) against the oracle.
+No GPU involved: the C sources are compiled into a shim next to the tests.  CPU only."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import _oracle as o
+from _shims import hs
+
+
+@pytest.mark.parametrize("w,h,q,rst,il", [(1920, 1080, 75, 24, 0), (7680, 4320, 75, 36, 0), (33, 17, 90, 2, 0),
+                                          (640, 480, 1, 0, 0), (64, 64, 100, 65535, 1)])
+def test_header_bytes_match_oracle(w, h, q, rst, il):
+    mine = np.zeros(2048, np.uint8)
+    n = hs.shim_header(w, h, q, rst, il, mine)
+    want = np.zeros(2048, np.uint8)
+    m = o.lib.orc_write_header(want, w, h, q, rst, 3)
+    assert np.array_equal(mine[:m], want[:m])
+    # followed by the first SOS header: compare against a real oracle stream
+    jpeg = o.encode(o.gen_image("zero", 16, 16), q, 1, il)
+    info = o.probe(jpeg)
+    sos_len = n - m
+    assert np.array_equal(mine[m:n], jpeg[info.header_size:info.header_size + sos_len])
+
+
+@pytest.mark.parametrize("cls", [0, 1])
+def test_encoder_lut_matches_oracle_tables(cls):
+    ac, dc = np.zeros(256, np.uint32), np.zeros(16, np.uint32)
+    hs.shim_enc_lut(cls, ac, dc)
+    for kind, lut, n in ((0, dc, 12), (1, ac, 256)):
+        code, size = np.zeros(256, np.uint16), np.zeros(256, np.uint8)
+        o.lib.orc_huff_encoder_table(cls, kind, code, size)
+        assert np.array_equal(lut[:n] & 31, size[:n])
+        assert np.array_equal((lut[:n] >> 5)[size[:n] > 0], code[:n][size[:n] > 0])
+
+
+@pytest.mark.parametrize("cls,kind", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_decoder_lut_decodes_every_code(cls, kind):
+    code, size = np.zeros(256, np.uint16), np.zeros(256, np.uint8)
+    o.lib.orc_huff_encoder_table(cls, kind, code, size)
+    rng = np.random.default_rng(3)
+    for sym in range(256):
+        if size[sym] == 0:
+            continue
+        for _ in range(4):
+            sz = int(size[sym])
+            tail = int(rng.integers(0, 1 << (16 - sz))) if sz < 16 else 0
+            peek = (int(code[sym]) << (16 - sz)) | tail
+            ln = C.c_int()
+            assert hs.shim_dec_lut_symbol(cls, kind, peek, C.byref(ln)) == sym
+            assert ln.value == size[sym]
+
+
+@pytest.mark.parametrize("kind,w,h,rst,il", [("random", 1920, 1080, 24, 0), ("photo", 640, 360, 7, 1),
+                                             ("random", 100, 50, 0, 0), ("gradient", 64, 64, 1, 0)])
+def test_reader_finds_every_segment(kind, w, h, rst, il):
+    jpeg = o.encode(o.gen_image(kind, w, h), 75, rst, il)
+    info = np.zeros(8, np.int32)
+    cap = 100000
+    off, ln = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+    n = hs.shim_parse(jpeg, jpeg.size, info, off, ln, cap)
+    p = o.probe(jpeg)
+    assert n == p.segment_count
+    assert tuple(info[:6]) == (w, h, 3, rst, p.scan_count, il)
+    assert info[6] == p.header_size
+    # every segment decodes (with the oracle's segment decoder) to the coefficients of the frame
+    _, coef = o.decode(jpeg, want_coef=True)
+    if not il:
+        dw, dh = (w + 7) // 8 * 8, (h + 7) // 8 * 8
+        nblk = dw * dh // 64
+        seg_mcu = rst if rst else nblk
+        per = (nblk + seg_mcu - 1) // seg_mcu
+        bits = [[None, None], [None, None]]
+        for g in (0, per, 2 * per, n - 1):
+            c, s = divmod(g, per)
+            cnt = min(seg_mcu, nblk - s * seg_mcu)
+            out = np.zeros(cnt * 64, np.int16)
+            specs = []
+            for k in (0, 1):
+                b, v, nv = C.POINTER(C.c_uint8)(), C.POINTER(C.c_uint8)(), C.c_int()
+                o.lib.orc_huff_spec(0 if c == 0 else 1, k, C.byref(b), C.byref(v), C.byref(nv))
+                specs += [b, v]
+            o.lib.orc_huff_decode_segment.argtypes = None
+            seg = np.ascontiguousarray(jpeg[off[g]:off[g] + ln[g]])
+            rc = o.lib.orc_huff_decode_segment(seg.ctypes.data_as(C.c_void_p), C.c_size_t(seg.size), cnt, specs[0],
+                                               specs[1], specs[2], specs[3], out.ctypes.data_as(C.c_void_p))
+            assert rc == 0
+            assert np.array_equal(out, coef[c][s * seg_mcu * 64:(s * seg_mcu + cnt) * 64])
+
+
+def test_geometry_matches_survey_table():
+    out = np.zeros(8, np.int64)
+    hs.shim_geometry(7680, 4320, 36, 0, out)
+    assert tuple(out[:6]) == (960, 540, 518400, 14400, 43200, 3)
+    hs.shim_geometry(1920, 1080, 24, 0, out)
+    assert tuple(out[:6]) == (240, 135, 32400, 1350, 4050, 3)
+    hs.shim_geometry(1119, 561, 8, 1, out)
+    assert tuple(out[:6]) == (140, 71, 9940, 1243, 1243, 1)

@@ -1,0 +1,53 @@
+"""Level-2 cross-check on the GPU box: the REFERENCE GPU library itself (compiled in place by
+`make -C oracle refgpu`, shipped as oracle/_ref/libgpujpeg_refgpu.so) against the oracle restatement and
+against the product.  This is what validates the restated float FDCT (FMA placement) and colour
+transforms on real hardware.  Skipped when the .so was not built."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import _oracle as o
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libgpujpeg_refgpu.so")
+
+
+def run_ref(*args):
+    subprocess.check_call([sys.executable, os.path.join(HERE, "_refgpu.py")] + [str(a) for a in args], timeout=600)
+
+
+@pytest.mark.skipif(not os.path.exists(SO), reason="oracle/_ref/libgpujpeg_refgpu.so not built")
+@pytest.mark.parametrize("kind,w,h,q,rst,il", [("random", 1920, 1080, 75, 24, 0), ("photo", 1920, 1080, 75, 24, 0),
+                                               ("random", 1119, 561, 75, 8, 0), ("photo", 640, 360, 90, 7, 1),
+                                               ("random", 512, 512, 100, 12, 0), ("photo", 3840, 2160, 75, 24, 0)])
+def test_reference_gpu_encoder_bytes_equal_oracle_and_product(tmp_path, kind, w, h, q, rst, il):
+    path = tmp_path / "ref.jpg"
+    run_ref("encode", kind, w, h, q, rst, il, path)
+    ref = np.fromfile(path, np.uint8)
+    img = o.gen_image(kind, w, h)
+    want = o.encode(img, q, rst, il, threads=4)
+    assert ref.size == want.size and np.array_equal(ref, want), "oracle restatement != reference GPU library output"
+    import gpujpeg_b200 as g
+    e = g.Encoder()
+    assert np.array_equal(e.encode(img, q, rst, il), ref), "product != reference GPU library output"
+    e.close()
+
+
+@pytest.mark.skipif(not os.path.exists(SO), reason="oracle/_ref/libgpujpeg_refgpu.so not built")
+@pytest.mark.parametrize("kind,w,h,q", [("random", 1920, 1080, 75), ("photo", 1920, 1080, 75), ("random", 333, 77, 95)])
+def test_reference_gpu_decoder_pixels_equal_float_flavour(tmp_path, kind, w, h, q):
+    jpeg = o.encode(o.gen_image(kind, w, h), q, 24)
+    src, dst = tmp_path / "in.jpg", tmp_path / "out.rgb"
+    jpeg.tofile(src)
+    run_ref("decode", src, dst)
+    ref = np.fromfile(dst, np.uint8).reshape(h, w, 3)
+    want = o.decode(jpeg, o.IDCT_FLOAT_GPUREF)
+    assert np.array_equal(ref, want), "float-GPU-reference IDCT restatement != reference GPU library output"
+    import gpujpeg_b200 as g
+    d = g.Decoder(idct="float_gpuref")
+    assert np.array_equal(d.decode(jpeg), ref)
+    d.close()
