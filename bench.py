@@ -1,0 +1,266 @@
+#!/usr/bin/env python
+"""bench.py -- the measurement contract of this repository.
+
+    python bench.py --gpus N --steps K --warmup W              (N = 1: plain python; N > 1: torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json `metric`: "Mpix/s encode+decode 8K RGB q75"):  one STEP = encode one 7680x4320
+RGB 4:4:4 frame at q75, restart interval 36, non-interleaved, then decode the JPEG just produced.
+Frames are synthetic "S-photo" images, one distinct frame per rank.
+
+  value   : Mpix/s with every input already resident in HBM (raw frame for the encoder; JPEG bytes and
+            segment table for the decoder).  Timed with CUDA events on the coder's stream around exactly K
+            steps of the four GPU stages; max over ranks; aggregate over ranks (weak scaling).
+  e2e     : the same metric through the reference-facing C API (gpujpeg_encoder_encode /
+            gpujpeg_decoder_decode) with HOST buffers: pinned host RGB in, host JPEG out, host JPEG in,
+            host RGB out -- H2D/D2H and the host codestream writer/reader inside the timed region.
+  roofline: for the slowest GPU stage: algorithmic bytes of SURVEY.md section 8d (9 B/pixel for the
+            transform kernels, 6+c for the Huffman kernels) / its CUDA-event time / measured HBM peak.
+  cpu_baseline / --impl reference : the CPU oracle (oracle/liboracle.so, a port of the reference's CPU
+            path, byte-identical to the reference's own gpujpeg_huffman_cpu_* code) on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+W, H, QUALITY, RST = 7680, 4320, 75, 36
+WORKLOADS = {"8k": (7680, 4320, 36), "4k": (3840, 2160, 24), "hd": (1920, 1080, 24), "16k": (15360, 8640, 36)}
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples if len(s) >= 6 for i in range(4) if s[2 + i] == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_baseline(width, height, rst, frames, threads):
+    """Times the oracle port (encode + decode) on the host cores; returns Mpix/s and the sample description."""
+    import _oracle as o
+    img = o.gen_image("photo", width, height)
+    jpeg = o.encode(img, QUALITY, rst, threads=threads)  # warm (page faults, tables)
+    t0 = time.perf_counter()
+    for _ in range(frames):
+        jpeg = o.encode(img, QUALITY, rst, threads=threads)
+        o.decode(jpeg, threads=threads)
+    dt = time.perf_counter() - t0
+    return frames * width * height / dt / 1e6, dt
+
+
+def run_reference(args):
+    """--impl reference: the CPU path on this box's host cores.  Under torchrun only rank 0 works."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    width, height, rst = WORKLOADS[args.size]
+    cores = os.cpu_count() or 1
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_baseline(width, height, rst, 1, cores)
+    t0 = time.perf_counter()
+    mpix, dt = cpu_baseline(width, height, rst, args.steps, cores)
+    line = {
+        "impl": "reference", "metric": "Mpix/s encode+decode %s RGB q75" % args.size, "value": round(mpix, 2), "unit": "Mpix/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
+        "config": {"workload": "%dx%d RGB 4:4:4 q%d rst%d non-interleaved, encode+decode per step (S-photo)" % (width, height, QUALITY, rst)},
+        "cpu_baseline": {"value": round(mpix, 2), "unit": "Mpix/s", "cores": cores, "kind": "port",
+                         "sample": "%d full frames, oracle port (bit-identical to the reference's gpujpeg_huffman_cpu_* + "
+                                   "gpujpeg_idct_cpu; restated colour/FDCT), OpenMP over segments/blocks" % args.steps},
+        "e2e": {"value": round(mpix, 2), "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", default="8k", choices=sorted(WORKLOADS))
+    ap.add_argument("--kind", default="photo", choices=["photo", "random", "gradient"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import gpujpeg_b200 as g
+    import _oracle as o  # synthetic frame generator only (the checker is never timed here)
+
+    width, height, rst = WORKLOADS[args.size]
+    npix = width * height
+    frame = o.gen_image(args.kind, width, height, seed=12345 + rank)
+    h_raw = torch.from_numpy(frame).pin_memory()
+    d_raw = h_raw.to(dev, non_blocking=True)
+    stream = torch.cuda.current_stream().cuda_stream
+    enc = g.Encoder(stream=stream, pinned_output=True)
+    dec = g.Decoder(stream=stream)
+
+    # one reference-facing call each: sets up geometry/tables and leaves the decoder's inputs on the device
+    jpeg = enc.encode(d_raw, QUALITY, rst)
+    c_bpp = (jpeg.size - 700) / npix
+    h_jpeg = torch.from_numpy(jpeg).pin_memory()
+    d_out = torch.empty((height, width, 3), dtype=torch.uint8, device=dev)
+    h_out = torch.empty((height, width, 3), dtype=torch.uint8).pin_memory()
+    dec.decode(h_jpeg.numpy(), out=d_out)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        enc.run_resident(d_raw, 3)
+        dec.run_resident(d_out, 3)
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident throughput (headline `value`) ----
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_resident, args.steps)
+    ms_step = ms_total / args.steps
+    value = world * npix / (ms_step * 1e-3) / 1e6
+
+    # ---- per-stage times for the roofline (same stream, CUDA events, inputs > L2) ----
+    stages = {}
+    for name, fn in (("k1_fdct", lambda: enc.run_resident(d_raw, 1)), ("k2_huffman_encode", lambda: enc.run_resident(d_raw, 2)),
+                     ("k3_huffman_decode", lambda: dec.run_resident(d_out, 1)), ("k4_idct", lambda: dec.run_resident(d_out, 2))):
+        for _ in range(2):
+            fn()
+        stages[name] = timed(fn, max(5, args.steps // 2)) / max(5, args.steps // 2)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the C API with host buffers ----
+    host_img = h_raw.numpy()
+
+    def step_e2e():
+        p = g.api.default_parameters(QUALITY, rst)
+        addr, size = enc.encode_raw(host_img, p, g.api.image_parameters(width, height), device=False)
+        dec.decode_raw(addr, size, g.api.GPUJPEG_DECODER_OUTPUT_CUSTOM_BUFFER, h_out.data_ptr())
+        return size
+
+    for _ in range(args.warmup):
+        jpeg_size = step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        jpeg_size = step_e2e()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_ms = float(dt.item()) / args.steps * 1e3
+    e2e_value = world * npix / (e2e_ms * 1e-3) / 1e6
+    assert np.array_equal(h_out.numpy(), d_out.cpu().numpy()), "e2e and resident paths disagree"
+
+    if rank == 0:
+        peak, peak_kind = hbm_peak()
+        alg = {"k1_fdct": 9.0, "k2_huffman_encode": 6.0 + c_bpp, "k3_huffman_decode": 6.0 + c_bpp, "k4_idct": 9.0}
+        worst = max(stages, key=lambda k: stages[k])
+        roof = {k: alg[k] * npix / (stages[k] * 1e-3) / 1e9 for k in stages}
+        path_gbs = (30.0 + 2 * c_bpp) * npix / (ms_step * 1e-3) / 1e9
+        line = {
+            "metric": "Mpix/s encode+decode %s RGB q75" % args.size, "value": round(value, 1), "unit": "Mpix/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32+i32 (u8 in, i16 coefficients)", "data": "synthetic",
+            "config": {"workload": "%dx%d RGB 4:4:4 q%d rst%d non-interleaved, encode+decode per step, S-%s frame per rank, "
+                                   "c=%.3f B/pixel" % (width, height, QUALITY, rst, args.kind, c_bpp),
+                       "l2": "inputs larger than L2 (99.5 MB raw + 199 MB coefficients per direction)",
+                       "sharding": "one coder instance per GPU, independent frames, no data-path collective"},
+            "stage_ms": {k: round(v, 4) for k, v in stages.items()},
+            "roofline": {"bound": "hbm", "kernel": worst, "achieved": round(roof[worst], 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(roof[worst] / peak, 4), "traffic": None, "peak_source": peak_kind,
+                         "all_stages_gbs": {k: round(v, 1) for k, v in roof.items()},
+                         "path_achieved_gbs": round(path_gbs, 1), "path_frac": round(path_gbs / peak, 4)},
+            "e2e": {"value": round(e2e_value, 1), "unit": "Mpix/s", "ms_per_step": round(e2e_ms, 3),
+                    "h2d_bytes_per_step": int(npix * 3 + jpeg_size + 8 * 43200), "d2h_bytes_per_step": int(jpeg_size + npix * 3)},
+            "gpu_launches": 6 * args.steps,
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            mpix, sec = cpu_baseline(width, height, rst, 2, cores)
+            line["cpu_baseline"] = {"value": round(mpix, 2), "unit": "Mpix/s", "cores": cores, "kind": "port",
+                                    "sample": "2 full %dx%d frames encode+decode, %.1f s, OpenMP %d threads" % (width, height, sec, cores)}
+        print(json.dumps(line))
+    enc.close()
+    dec.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -94,6 +94,8 @@ def _load():
         "gpujpeg_decoder_get_stats": (ci, [vp, C.POINTER(DurationStats)]),
         "gpujpeg_decoder_get_image_info": (ci, [vp, cs, C.POINTER(ImageParameters), C.POINTER(Parameters), C.POINTER(ci)]),
         "gpujpegx_encoder_get_coefficients": (ci, [vp, vp, cs]),
+        "gpujpegx_encoder_run_resident": (ci, [vp, vp, ci]),
+        "gpujpegx_decoder_run_resident": (ci, [vp, vp, ci]),
         "gpujpegx_decoder_get_coefficients": (ci, [vp, vp, cs]),
     }
     for name, (res, args) in sigs.items():
@@ -173,6 +175,12 @@ class Encoder:
         addr, size = self.encode_raw(image, p, image_parameters(width, height, width_padding))
         return np.ctypeslib.as_array((C.c_uint8 * size).from_address(addr)).copy()
 
+    def run_resident(self, d_raw=None, stage_mask=3):
+        """enqueue the GPU stages only (bit0 K1, bit1 K2) on device-resident data; no copies, no sync"""
+        addr = _ptr(d_raw)[0] if d_raw is not None else None
+        if lib.gpujpegx_encoder_run_resident(self._h, addr, stage_mask) != 0:
+            raise GpuJpegError("gpujpegx_encoder_run_resident failed")
+
     def coefficients(self, width, height):
         """quantised coefficients of the last frame: (3, blocks*64) int16, natural order (parity tests)"""
         dw, dh = (width + 7) // 8 * 8, (height + 7) // 8 * 8
@@ -228,6 +236,12 @@ class Decoder:
         self.decode_raw(jpeg.ctypes.data, jpeg.size,
                         GPUJPEG_DECODER_OUTPUT_CUSTOM_CUDA_BUFFER if is_dev else GPUJPEG_DECODER_OUTPUT_CUSTOM_BUFFER, addr)
         return out
+
+    def run_resident(self, d_out=None, stage_mask=3):
+        """enqueue the GPU stages only (bit0 K3, bit1 K4) of the last decoded frame; no copies, no sync"""
+        addr = _ptr(d_out)[0] if d_out is not None else None
+        if lib.gpujpegx_decoder_run_resident(self._h, addr, stage_mask) != 0:
+            raise GpuJpegError("gpujpegx_decoder_run_resident failed")
 
     def coefficients(self, width, height):
         dw, dh = (width + 7) // 8 * 8, (height + 7) // 8 * 8

@@ -49,6 +49,10 @@ struct gpujpeg_decoder {
     int timers_ok;
     struct gpujpeg_duration_stats stats;
     int stats_valid;
+
+    struct gj_huff_dec_args last_args;  /* launch arguments of the last frame (resident re-runs) */
+    int last_tq[3];
+    int last_valid;
 };
 
 /* ---- output descriptor helpers [ref: src/gpujpeg_decoder.c:44-92] ---- */
@@ -354,6 +358,9 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     ha.nblk = g->nblk;
     ha.d_coef = d->d_coef;
     ha.d_tables = d->d_tab;
+    d->last_args = ha;
+    memcpy(d->last_tq, st.comp_tq, sizeof d->last_tq);
+    d->last_valid = 1;
     if ( gj_launch_huffman_decode(&ha, d->stream) ) {
         GJ_ERR("Huffman decoder launch failed: %s\n", gj_cuda_last_error());
         return GPUJPEG_ERROR;
@@ -524,6 +531,20 @@ void gpujpeg_decoder_print_options(void)
 {
     printf("\t" GPUJPEG_DEC_OPT_IDCT "=[" GPUJPEG_DEC_IDCT_VAL_INT "|" GPUJPEG_DEC_IDCT_VAL_FLOAT_GPUREF
            "] - inverse DCT flavour (default: int = gpujpeg_idct_cpu)\n");
+}
+
+/* ---- extension: re-run the GPU stages of the last decoded frame on the data already on the device ----
+ * stage_mask bit 0 = K3 (Huffman decode), bit 1 = K4 (dequant+IDCT+colour).  No copies, no sync. */
+GPUJPEG_API int gpujpegx_decoder_run_resident(struct gpujpeg_decoder* d, uint8_t* d_out, int stage_mask)
+{
+    if ( !d || !d->last_valid ) return -1;
+    const struct gj_geometry* g = &d->geo;
+    if ( (stage_mask & 1) && gj_launch_huffman_decode(&d->last_args, d->stream) ) return -1;
+    if ( (stage_mask & 2) &&
+         gj_launch_idct_rgb444(d->d_coef, g->bcx, g->bcy, d->last_tq, d_out ? d_out : d->d_raw, g->width, g->height,
+                               g->pitch, d->idct_flavour, &d->h_tab, d->stream) )
+        return -1;
+    return 0;
 }
 
 /* ---- extension used by the parity tests: coefficients of the last decoded frame, natural order ---- */
