@@ -244,11 +244,14 @@ class Decoder:
             raise GpuJpegError("gpujpegx_decoder_run_resident failed")
 
     def coefficients(self, width, height):
+        """coefficients of the last frame, natural order: (array, dequantized) -- with the integer IDCT flavour
+        the Huffman decoder already stores coefficient*quantiser wrapped to int16 (dequantized = True)"""
         dw, dh = (width + 7) // 8 * 8, (height + 7) // 8 * 8
         out = np.empty((3, dw * dh), np.int16)
-        if lib.gpujpegx_decoder_get_coefficients(self._h, out.ctypes.data, out.size) != 0:
+        rc = lib.gpujpegx_decoder_get_coefficients(self._h, out.ctypes.data, out.size)
+        if rc < 0:
             raise GpuJpegError("gpujpegx_decoder_get_coefficients failed")
-        return out
+        return out, bool(rc)
 
     def stats(self):
         s = DurationStats()

@@ -478,7 +478,8 @@ static int tst_load(const char* filename, uint8_t** image, size_t* image_size)
             break;
         }
         case PAT_BLANK: memset(data, arg, size); break;
-        case PAT_NOISE: arg = (int)(gpujpeg_get_time() * 1e6); /* fall through: non-deterministic seed */
+        case PAT_NOISE: arg = (int)(gpujpeg_get_time() * 1e6); /* non-deterministic seed */
+        /* fall through */
         case PAT_RANDOM: {
             uint32_t s = (uint32_t)arg;
             for ( size_t i = 0; i < size; i++ ) {

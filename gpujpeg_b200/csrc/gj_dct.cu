@@ -8,19 +8,23 @@
  *       Algorithmic traffic: 3 B read + 6 B written per pixel.
  *
  *   K4  k_idct_rgb444 : int16 zig-zag coefficients -> RGB u8 interleaved
- *       = dequantisation + inverse DCT + level shift + colour transform + interleave in one pass
+ *       = (dequantisation +) inverse DCT + level shift + colour transform + interleave in one pass
  *       (reference: three IDCT launches + a postprocessor kernel, src/gpujpeg_dct_gpu.cu:472-618,
  *        src/gpujpeg_postprocessor.cu:183-216).  6 B read + 3 B written per pixel.
  *
  * Work decomposition (both kernels): one CTA owns a strip of TB = 64 horizontally adjacent 8x8
- * blocks (512 x 8 pixels).  192 threads; during the transform phase thread t owns block (t % 64) of
- * component (t / 64) entirely in registers -- both 1-D passes run without any transpose or shuffle,
- * which matters because the arithmetic must follow the reference's rounding sequence exactly and
- * the kernels are issue-bound, not bandwidth-bound, near the roofline.  Pixels move through shared
- * memory twice: raw interleaved bytes (coalesced 16 B global accesses) and a planar staging area.
+ * blocks (512 x 8 pixels), 192 threads.  In the transform phase thread t owns block (t % 64) of
+ * component (t / 64) entirely in registers: both 1-D passes run without any transpose or shuffle,
+ * which matters because the arithmetic has to follow the reference's rounding sequence exactly and
+ * these kernels are instruction-issue bound, not bandwidth bound (ncu, profiles/r1_a).  In the colour
+ * phase every thread handles 4 pixels = 12 interleaved bytes = three 32-bit words, read from / written
+ * to global memory directly (a warp touches 384 contiguous bytes); the only shared-memory traffic is
+ * the planar staging area between the two phases.  No conversion-pipe (XU) instruction is used for
+ * the colour transform (see gj_device.cuh); clamping + byte packing use cvt.pack.sat (I2IP).
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "gj_device.cuh"
 #include "gj_internal.h"
@@ -30,13 +34,12 @@ namespace {
 constexpr int TB = 64;                 // blocks per strip
 constexpr int NT = 192;                // threads per CTA = 3 components x TB
 constexpr int STRIP_PX = TB * 8;       // 512 pixels
-constexpr int ROW_BYTES = STRIP_PX * 3;  // 1536 raw bytes per strip row
-constexpr int BLK_F = 68;              // floats per block in the planar staging area (64 + 4 pad:
-                                       // block stride 272 B makes the 16 B row reads of consecutive
-                                       // blocks hit distinct bank groups)
-constexpr int K1_SMEM = 8 * ROW_BYTES + 3 * TB * BLK_F * 4;   // 12288 + 52224 = 64512 B
-constexpr int K4_PLANE = 8 * STRIP_PX;                        // bytes per component plane of a strip
-constexpr int K4_SMEM = 8 * ROW_BYTES + 3 * K4_PLANE;         // 12288 + 12288 = 24576 B
+constexpr int GROUPS = 8 * (STRIP_PX / 4);   // 4-pixel groups per strip
+constexpr int BLK_F = 68;              // floats per block in K1's planar staging area (64 + 4 pad: block
+                                       // stride 272 B puts the 16 B row reads of consecutive blocks on
+                                       // distinct bank groups)
+constexpr int K1_SMEM = 3 * TB * BLK_F * 4;   // 52224 B
+constexpr int K4_PLANE = 8 * STRIP_PX;        // bytes per component plane of a strip
 
 struct FdctParams {
     float fwd_zz[2][64];
@@ -45,126 +48,66 @@ struct IdctParams {
     uint16_t q_zz[3][64];
 };
 
-/* ---- raw strip <-> global memory, with whatever alignment the caller's image has ---- */
-
-// copy `nbytes` of each of `rows` image rows into smem rows of ROW_BYTES; VEC = 16, 4 or 1
-template <int VEC>
-__device__ __forceinline__ void load_strip(uint8_t* s_raw, const uint8_t* g, size_t pitch, int rows, int nbytes)
+/* clamp four ints to [0,255] and pack them, p0 in the lowest byte: two I2IP instructions */
+__device__ __forceinline__ uint32_t pack4_sat_u8(int p0, int p1, int p2, int p3)
 {
-    if ( VEC == 16 ) {
-        const int nvec = nbytes >> 4;
-        for ( int i = threadIdx.x; i < rows * (ROW_BYTES / 16); i += NT ) {
-            const int r = i / (ROW_BYTES / 16), c = i % (ROW_BYTES / 16);
-            if ( c < nvec ) {
-                const int4 v = __ldg(reinterpret_cast<const int4*>(g + (size_t)r * pitch) + c);
-                reinterpret_cast<int4*>(s_raw + r * ROW_BYTES)[c] = v;
-            }
-        }
-        const int tail0 = nvec << 4;
-        for ( int i = threadIdx.x; i < rows * 16; i += NT ) {
-            const int r = i >> 4, c = tail0 + (i & 15);
-            if ( c < nbytes ) s_raw[r * ROW_BYTES + c] = __ldg(g + (size_t)r * pitch + c);
-        }
-    }
-    else if ( VEC == 4 ) {
-        const int nvec = nbytes >> 2;
-        for ( int i = threadIdx.x; i < rows * (ROW_BYTES / 4); i += NT ) {
-            const int r = i / (ROW_BYTES / 4), c = i % (ROW_BYTES / 4);
-            if ( c < nvec )
-                reinterpret_cast<uint32_t*>(s_raw + r * ROW_BYTES)[c] =
-                    __ldg(reinterpret_cast<const uint32_t*>(g + (size_t)r * pitch) + c);
-        }
-        const int tail0 = nvec << 2;
-        for ( int i = threadIdx.x; i < rows * 4; i += NT ) {
-            const int r = i >> 2, c = tail0 + (i & 3);
-            if ( c < nbytes ) s_raw[r * ROW_BYTES + c] = __ldg(g + (size_t)r * pitch + c);
-        }
-    }
-    else {
-        for ( int i = threadIdx.x; i < rows * ROW_BYTES; i += NT ) {
-            const int r = i / ROW_BYTES, c = i % ROW_BYTES;
-            if ( c < nbytes ) s_raw[r * ROW_BYTES + c] = __ldg(g + (size_t)r * pitch + c);
-        }
-    }
+    uint32_t hi, d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(p3), "r"(p2), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(p1), "r"(p0), "r"(hi));
+    return d;
 }
-
-template <int VEC>
-__device__ __forceinline__ void store_strip(const uint8_t* s_raw, uint8_t* g, size_t pitch, int rows, int nbytes)
-{
-    if ( VEC == 16 ) {
-        const int nvec = nbytes >> 4;
-        for ( int i = threadIdx.x; i < rows * (ROW_BYTES / 16); i += NT ) {
-            const int r = i / (ROW_BYTES / 16), c = i % (ROW_BYTES / 16);
-            if ( c < nvec )
-                reinterpret_cast<int4*>(g + (size_t)r * pitch)[c] = reinterpret_cast<const int4*>(s_raw + r * ROW_BYTES)[c];
-        }
-        const int tail0 = nvec << 4;
-        for ( int i = threadIdx.x; i < rows * 16; i += NT ) {
-            const int r = i >> 4, c = tail0 + (i & 15);
-            if ( c < nbytes ) g[(size_t)r * pitch + c] = s_raw[r * ROW_BYTES + c];
-        }
-    }
-    else if ( VEC == 4 ) {
-        const int nvec = nbytes >> 2;
-        for ( int i = threadIdx.x; i < rows * (ROW_BYTES / 4); i += NT ) {
-            const int r = i / (ROW_BYTES / 4), c = i % (ROW_BYTES / 4);
-            if ( c < nvec )
-                reinterpret_cast<uint32_t*>(g + (size_t)r * pitch)[c] =
-                    reinterpret_cast<const uint32_t*>(s_raw + r * ROW_BYTES)[c];
-        }
-        const int tail0 = nvec << 2;
-        for ( int i = threadIdx.x; i < rows * 4; i += NT ) {
-            const int r = i >> 2, c = tail0 + (i & 3);
-            if ( c < nbytes ) g[(size_t)r * pitch + c] = s_raw[r * ROW_BYTES + c];
-        }
-    }
-    else {
-        for ( int i = threadIdx.x; i < rows * ROW_BYTES; i += NT ) {
-            const int r = i / ROW_BYTES, c = i % ROW_BYTES;
-            if ( c < nbytes ) g[(size_t)r * pitch + c] = s_raw[r * ROW_BYTES + c];
-        }
-    }
-}
-
-__device__ __forceinline__ float byte_f(uint32_t w, int i) { return (float)((w >> (8 * i)) & 0xFFu); }
 
 /* =========================================================================================== */
 /* K1                                                                                            */
 
+// VEC = 4: base pointer and pitch are 4-byte aligned -> 32-bit global loads; VEC = 1: byte loads
 template <int VEC>
 __global__ void __launch_bounds__(NT)
 k_fdct_rgb444(const uint8_t* __restrict__ raw, int width, int height, size_t pitch, int16_t* __restrict__ coef,
               int bcx, int nblk, const __grid_constant__ FdctParams prm)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t* s_raw = smem;
-    float* s_pl = reinterpret_cast<float*>(smem + 8 * ROW_BYTES);
+    float* s_pl = reinterpret_cast<float*>(smem);
 
     const int bx0 = blockIdx.x * TB;
     const int by = blockIdx.y;
     const int x0 = bx0 * 8;
     const int vw = min(STRIP_PX, width - x0);        // valid pixels in this strip (>= 1)
     const int vh = min(8, height - by * 8);          // valid rows (>= 1)
+    const uint8_t* src = raw + (size_t)by * 8 * pitch + (size_t)x0 * 3;
 
-    /* phase A: raw rows -> smem */
-    load_strip<VEC>(s_raw, raw + (size_t)by * 8 * pitch + (size_t)x0 * 3, pitch, vh, vw * 3);
-    __syncthreads();
-
-    /* phase B: colour transform, 4 pixels (12 bytes = 3 words) per step, planar float staging.
+    /* phase A: colour transform, 4 pixels (12 bytes = 3 words) per step, planar float staging.
      * Pixels outside the image are 0 in every component, as in the reference whose planes are
      * zero-initialised and only written inside the image [ref: src/gpujpeg_common.c:941-944]. */
-    for ( int g = threadIdx.x; g < 8 * (STRIP_PX / 4); g += NT ) {
+#pragma unroll 2
+    for ( int g = threadIdx.x; g < GROUPS; g += NT ) {
         const int row = g >> 7, gx = g & 127;
         const int px0 = gx * 4;
         float4 y4 = make_float4(0.f, 0.f, 0.f, 0.f), cb4 = y4, cr4 = y4;
         if ( row < vh && px0 < vw ) {
-            const uint32_t* w = reinterpret_cast<const uint32_t*>(s_raw + row * ROW_BYTES + gx * 12);
-            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-            gj_rgb_to_ycbcr(byte_f(w0, 0), byte_f(w0, 1), byte_f(w0, 2), y4.x, cb4.x, cr4.x);
-            gj_rgb_to_ycbcr(byte_f(w0, 3), byte_f(w1, 0), byte_f(w1, 1), y4.y, cb4.y, cr4.y);
-            gj_rgb_to_ycbcr(byte_f(w1, 2), byte_f(w1, 3), byte_f(w2, 0), y4.z, cb4.z, cr4.z);
-            gj_rgb_to_ycbcr(byte_f(w2, 1), byte_f(w2, 2), byte_f(w2, 3), y4.w, cb4.w, cr4.w);
-            if ( px0 + 4 > vw ) {  // strip ends inside this group (width not a multiple of 4)
+            const uint8_t* p = src + (size_t)row * pitch + gx * 12;
+            uint32_t w0, w1, w2;
+            if ( VEC == 4 && px0 + 4 <= vw ) {
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
+                w0 = __ldg(w);
+                w1 = __ldg(w + 1);
+                w2 = __ldg(w + 2);
+            }
+            else {
+                const int nb = min(12, (vw - px0) * 3);   // never read past the end of the row
+                uint32_t b[12];
+#pragma unroll
+                for ( int i = 0; i < 12; i++ )
+                    b[i] = i < nb ? (uint32_t)__ldg(p + i) : 0u;
+                w0 = b[0] | b[1] << 8 | b[2] << 16 | b[3] << 24;
+                w1 = b[4] | b[5] << 8 | b[6] << 16 | b[7] << 24;
+                w2 = b[8] | b[9] << 8 | b[10] << 16 | b[11] << 24;
+            }
+            gj_rgb_to_ycbcr_m(gj_byte_as_magic(w0, 0), gj_byte_as_magic(w0, 1), gj_byte_as_magic(w0, 2), y4.x, cb4.x, cr4.x);
+            gj_rgb_to_ycbcr_m(gj_byte_as_magic(w0, 3), gj_byte_as_magic(w1, 0), gj_byte_as_magic(w1, 1), y4.y, cb4.y, cr4.y);
+            gj_rgb_to_ycbcr_m(gj_byte_as_magic(w1, 2), gj_byte_as_magic(w1, 3), gj_byte_as_magic(w2, 0), y4.z, cb4.z, cr4.z);
+            gj_rgb_to_ycbcr_m(gj_byte_as_magic(w2, 1), gj_byte_as_magic(w2, 2), gj_byte_as_magic(w2, 3), y4.w, cb4.w, cr4.w);
+            if ( px0 + 4 > vw ) {  // the image ends inside this group
                 if ( px0 + 1 >= vw ) { y4.y = cb4.y = cr4.y = 0.f; }
                 if ( px0 + 2 >= vw ) { y4.z = cb4.z = cr4.z = 0.f; }
                 if ( px0 + 3 >= vw ) { y4.w = cb4.w = cr4.w = 0.f; }
@@ -177,16 +120,16 @@ k_fdct_rgb444(const uint8_t* __restrict__ raw, int width, int height, size_t pit
     }
     __syncthreads();
 
-    /* phase C: one thread = one 8x8 block of one component, everything in registers */
+    /* phase B: one thread = one 8x8 block of one component, everything in registers */
     const int comp = threadIdx.x >> 6;
     const int b = threadIdx.x & 63;
     if ( bx0 + b >= bcx ) return;
     float v[64];
     {
-        const float4* src = reinterpret_cast<const float4*>(s_pl + (comp * TB + b) * BLK_F);
+        const float4* in = reinterpret_cast<const float4*>(s_pl + (comp * TB + b) * BLK_F);
 #pragma unroll
         for ( int i = 0; i < 16; i++ ) {
-            const float4 t = src[i];
+            const float4 t = in[i];
             v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
         }
     }
@@ -198,7 +141,7 @@ k_fdct_rgb444(const uint8_t* __restrict__ raw, int width, int height, size_t pit
     for ( int k = 0; k < 64; k += 2 ) {
         const int q0 = GJ_RINT(GJ_FMUL(v[gj_zz2nat(k)], tab[k]));
         const int q1 = GJ_RINT(GJ_FMUL(v[gj_zz2nat(k + 1)], tab[k + 1]));
-        packed[k >> 1] = ((uint32_t)q0 & 0xFFFFu) | ((uint32_t)q1 << 16);
+        packed[k >> 1] = __byte_perm((uint32_t)q0, (uint32_t)q1, 0x5410);
     }
     uint4* dst = reinterpret_cast<uint4*>(coef + ((size_t)comp * nblk + (size_t)by * bcx + bx0 + b) * 64);
 #pragma unroll
@@ -209,14 +152,15 @@ k_fdct_rgb444(const uint8_t* __restrict__ raw, int width, int height, size_t pit
 /* =========================================================================================== */
 /* K4                                                                                            */
 
-template <int VEC, int FLAVOUR>
+// FLAVOUR 0 = integer IDCT (gpujpeg_idct_cpu), 1 = float GPU-reference IDCT
+// DEQ     true  = coefficients are raw quantised values: multiply by the table here
+//         false = K3 already stored coefficient*quantiser wrapped to int16 (FLAVOUR 0 only)
+template <int VEC, int FLAVOUR, bool DEQ>
 __global__ void __launch_bounds__(NT)
 k_idct_rgb444(const int16_t* __restrict__ coef, int bcx, int nblk, uint8_t* __restrict__ raw, int width, int height,
               size_t pitch, const __grid_constant__ IdctParams prm)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t* s_raw = smem;
-    uint8_t* s_pl = smem + 8 * ROW_BYTES;
+    __shared__ __align__(16) uint8_t s_pl[3 * K4_PLANE];
 
     const int bx0 = blockIdx.x * TB;
     const int by = blockIdx.y;
@@ -239,43 +183,32 @@ k_idct_rgb444(const int16_t* __restrict__ coef, int bcx, int nblk, uint8_t* __re
             const uint16_t* q = prm.q_zz[comp];
             uint32_t px[16];  // 64 output bytes, row-major
             if ( FLAVOUR == 0 ) {
-                /* integer path == gpujpeg_idct_cpu: dequantise with int16 wrap, rows, columns,
+                /* integer path == gpujpeg_idct_cpu: dequantised int16 coefficients, rows, columns,
                  * +128, clamp [ref: src/gpujpeg_dct_cpu.c:178-189, 239-251] */
                 int v[64];
 #pragma unroll
                 for ( int k = 0; k < 64; k++ ) {
-                    const int c = (int)(short)(k & 1 ? packed[k >> 1] >> 16 : packed[k >> 1] & 0xFFFFu);
-                    v[gj_zz2nat(k)] = gj_s16(c * (int)(short)q[k]);
+                    const int c = (k & 1) ? (int)packed[k >> 1] >> 16 : (int)(short)(packed[k >> 1] & 0xFFFFu);
+                    v[gj_zz2nat(k)] = DEQ ? gj_s16(c * (int)(short)q[k]) : c;
                 }
-                gj_idct_int_block(v);
+                gj_idct_int_block_px(v);
 #pragma unroll
-                for ( int i = 0; i < 16; i++ ) {
-                    uint32_t w = 0;
-#pragma unroll
-                    for ( int j = 0; j < 4; j++ ) {
-                        const int s = gj_s16(v[4 * i + j] + 128);
-                        w |= (uint32_t)gj_clamp8(s) << (8 * j);
-                    }
-                    px[i] = w;
-                }
+                for ( int i = 0; i < 16; i++ )
+                    px[i] = pack4_sat_u8(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
             else {
                 /* float path == the reference CUDA kernel [ref: src/gpujpeg_dct_gpu.cu:497-501, 597-617] */
                 float f[64];
 #pragma unroll
                 for ( int k = 0; k < 64; k++ ) {
-                    const int c = (int)(short)(k & 1 ? packed[k >> 1] >> 16 : packed[k >> 1] & 0xFFFFu);
+                    const int c = (k & 1) ? (int)packed[k >> 1] >> 16 : (int)(short)(packed[k >> 1] & 0xFFFFu);
                     f[gj_zz2nat(k)] = (float)(c * (int)q[k]);
                 }
                 gj_idct_float_block(f);
 #pragma unroll
-                for ( int i = 0; i < 16; i++ ) {
-                    uint32_t w = 0;
-#pragma unroll
-                    for ( int j = 0; j < 4; j++ )
-                        w |= (uint32_t)gj_clamp8(GJ_RINT(GJ_FADD(f[4 * i + j], 128.0f))) << (8 * j);
-                    px[i] = w;
-                }
+                for ( int i = 0; i < 16; i++ )
+                    px[i] = pack4_sat_u8(GJ_RINT(GJ_FADD(f[4 * i], 128.0f)), GJ_RINT(GJ_FADD(f[4 * i + 1], 128.0f)),
+                                         GJ_RINT(GJ_FADD(f[4 * i + 2], 128.0f)), GJ_RINT(GJ_FADD(f[4 * i + 3], 128.0f)));
             }
             uint8_t* dst = s_pl + comp * K4_PLANE + b * 8;
 #pragma unroll
@@ -285,38 +218,43 @@ k_idct_rgb444(const int16_t* __restrict__ coef, int bcx, int nblk, uint8_t* __re
     }
     __syncthreads();
 
-    /* phase B: 4 pixels per step: 3 plane words -> 3 interleaved words */
-    for ( int g = threadIdx.x; g < 8 * (STRIP_PX / 4); g += NT ) {
+    /* phase B: 4 pixels per step: 3 plane words -> 3 interleaved words, straight to global memory */
+    uint8_t* out = raw + (size_t)by * 8 * pitch + (size_t)x0 * 3;
+    for ( int g = threadIdx.x; g < GROUPS; g += NT ) {
         const int row = g >> 7, gx = g & 127;
-        if ( row >= vh || gx * 4 >= vw ) continue;
-        const uint32_t yw = *reinterpret_cast<const uint32_t*>(s_pl + row * STRIP_PX + gx * 4);
-        const uint32_t bw = *reinterpret_cast<const uint32_t*>(s_pl + K4_PLANE + row * STRIP_PX + gx * 4);
-        const uint32_t rw = *reinterpret_cast<const uint32_t*>(s_pl + 2 * K4_PLANE + row * STRIP_PX + gx * 4);
+        const int px0 = gx * 4;
+        if ( row >= vh || px0 >= vw ) continue;
+        const uint32_t yw = *reinterpret_cast<const uint32_t*>(s_pl + row * STRIP_PX + px0);
+        const uint32_t bw = *reinterpret_cast<const uint32_t*>(s_pl + K4_PLANE + row * STRIP_PX + px0);
+        const uint32_t rw = *reinterpret_cast<const uint32_t*>(s_pl + 2 * K4_PLANE + row * STRIP_PX + px0);
         int r[4], gg[4], bb[4];
 #pragma unroll
         for ( int j = 0; j < 4; j++ )
-            gj_ycbcr_to_rgb((yw >> (8 * j)) & 0xFF, (bw >> (8 * j)) & 0xFF, (rw >> (8 * j)) & 0xFF, r[j], gg[j], bb[j]);
-        uint32_t* o = reinterpret_cast<uint32_t*>(s_raw + row * ROW_BYTES + gx * 12);
-        o[0] = (uint32_t)r[0] | ((uint32_t)gg[0] << 8) | ((uint32_t)bb[0] << 16) | ((uint32_t)r[1] << 24);
-        o[1] = (uint32_t)gg[1] | ((uint32_t)bb[1] << 8) | ((uint32_t)r[2] << 16) | ((uint32_t)gg[2] << 24);
-        o[2] = (uint32_t)bb[2] | ((uint32_t)r[3] << 8) | ((uint32_t)gg[3] << 16) | ((uint32_t)bb[3] << 24);
+            gj_ycbcr_to_rgb_raw((yw >> (8 * j)) & 0xFF, (bw >> (8 * j)) & 0xFF, (rw >> (8 * j)) & 0xFF, r[j], gg[j], bb[j]);
+        const uint32_t o0 = pack4_sat_u8(r[0], gg[0], bb[0], r[1]);
+        const uint32_t o1 = pack4_sat_u8(gg[1], bb[1], r[2], gg[2]);
+        const uint32_t o2 = pack4_sat_u8(bb[2], r[3], gg[3], bb[3]);
+        uint8_t* p = out + (size_t)row * pitch + gx * 12;
+        if ( VEC == 4 && px0 + 4 <= vw ) {
+            uint32_t* w = reinterpret_cast<uint32_t*>(p);
+            w[0] = o0;
+            w[1] = o1;
+            w[2] = o2;
+        }
+        else {
+            const int nb = min(12, (vw - px0) * 3);
+            const uint32_t o[3] = {o0, o1, o2};
+#pragma unroll
+            for ( int i = 0; i < 12; i++ )
+                if ( i < nb ) p[i] = (uint8_t)(o[i >> 2] >> (8 * (i & 3)));
+        }
     }
-    __syncthreads();
-
-    /* phase C: interleaved rows -> global */
-    store_strip<VEC>(s_raw, raw + (size_t)by * 8 * pitch + (size_t)x0 * 3, pitch, vh, vw * 3);
 }
 
 int pick_vec(const void* p, size_t pitch)
 {
     const uintptr_t a = reinterpret_cast<uintptr_t>(p) | pitch;
-    return (a & 15) == 0 ? 16 : (a & 3) == 0 ? 4 : 1;
-}
-
-template <typename K>
-int set_smem(K kernel, int bytes)
-{
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess ? 0 : -1;
+    return (a & 3) == 0 ? 4 : 1;
 }
 
 }  // namespace
@@ -328,17 +266,17 @@ extern "C" int gj_launch_fdct_rgb444(const uint8_t* d_raw, int width, int height
     memcpy(prm.fwd_zz, h_tables->fwd_zz, sizeof prm.fwd_zz);
     const dim3 grid((bcx + TB - 1) / TB, bcy);
     const int nblk = bcx * bcy;
-    const int vec = pick_vec(d_raw, (size_t)pitch);
-    static bool attr_done = false;
-    if ( !attr_done ) {
-        if ( set_smem(k_fdct_rgb444<16>, K1_SMEM) || set_smem(k_fdct_rgb444<4>, K1_SMEM) ||
-             set_smem(k_fdct_rgb444<1>, K1_SMEM) )
+    /* > 48 KB of dynamic shared memory needs an opt-in, once per device */
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    if ( cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 ) return -1;
+    if ( !attr_done[dev] ) {
+        if ( cudaFuncSetAttribute(k_fdct_rgb444<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM) != cudaSuccess ||
+             cudaFuncSetAttribute(k_fdct_rgb444<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM) != cudaSuccess )
             return -1;
-        attr_done = true;
+        attr_done[dev] = true;
     }
-    if ( vec == 16 )
-        k_fdct_rgb444<16><<<grid, NT, K1_SMEM, stream>>>(d_raw, width, height, (size_t)pitch, d_coef, bcx, nblk, prm);
-    else if ( vec == 4 )
+    if ( pick_vec(d_raw, (size_t)pitch) == 4 )
         k_fdct_rgb444<4><<<grid, NT, K1_SMEM, stream>>>(d_raw, width, height, (size_t)pitch, d_coef, bcx, nblk, prm);
     else
         k_fdct_rgb444<1><<<grid, NT, K1_SMEM, stream>>>(d_raw, width, height, (size_t)pitch, d_coef, bcx, nblk, prm);
@@ -346,7 +284,7 @@ extern "C" int gj_launch_fdct_rgb444(const uint8_t* d_raw, int width, int height
 }
 
 extern "C" int gj_launch_idct_rgb444(const int16_t* d_coef, int bcx, int bcy, const int comp_tq[3], uint8_t* d_raw,
-                                     int width, int height, int pitch, int idct_flavour,
+                                     int width, int height, int pitch, int idct_flavour, int coef_dequantized,
                                      const struct gj_dev_dec_tables* h_tables, gj_stream_t stream)
 {
     IdctParams prm;
@@ -355,12 +293,16 @@ extern "C" int gj_launch_idct_rgb444(const int16_t* d_coef, int bcx, int bcy, co
     const dim3 grid((bcx + TB - 1) / TB, bcy);
     const int nblk = bcx * bcy;
     const int vec = pick_vec(d_raw, (size_t)pitch);
-#define GJ_K4(V, F) k_idct_rgb444<V, F><<<grid, NT, K4_SMEM, stream>>>(d_coef, bcx, nblk, d_raw, width, height, (size_t)pitch, prm)
-    if ( idct_flavour == 0 ) {
-        if ( vec == 16 ) GJ_K4(16, 0); else if ( vec == 4 ) GJ_K4(4, 0); else GJ_K4(1, 0);
+    if ( idct_flavour != 0 && coef_dequantized ) return -1;   // the float flavour needs raw coefficients
+#define GJ_K4(V, F, D) k_idct_rgb444<V, F, D><<<grid, NT, 0, stream>>>(d_coef, bcx, nblk, d_raw, width, height, (size_t)pitch, prm)
+    if ( idct_flavour == 0 && coef_dequantized ) {
+        if ( vec == 4 ) GJ_K4(4, 0, false); else GJ_K4(1, 0, false);
+    }
+    else if ( idct_flavour == 0 ) {
+        if ( vec == 4 ) GJ_K4(4, 0, true); else GJ_K4(1, 0, true);
     }
     else {
-        if ( vec == 16 ) GJ_K4(16, 1); else if ( vec == 4 ) GJ_K4(4, 1); else GJ_K4(1, 1);
+        if ( vec == 4 ) GJ_K4(4, 1, true); else GJ_K4(1, 1, true);
     }
 #undef GJ_K4
     return cudaGetLastError() == cudaSuccess ? 0 : -1;

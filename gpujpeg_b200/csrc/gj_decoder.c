@@ -310,6 +310,7 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
             }
             ha.scan_comp[s][k] = st.scan[s].comp[k];
             ha.scan_td[s][k] = td;
+            ha.scan_tq[s][k] = st.comp_tq[st.scan[s].comp[k]];
             ha.scan_ta[s][k] = ta;
         }
     }
@@ -348,6 +349,8 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
 
     /* ---- K3 ---- */
     ha.d_file = d->d_file;
+    ha.file_size = image_size;
+    ha.dequantize = d->idct_flavour == 0;
     ha.d_seg_off = d->d_seg;
     ha.d_seg_len = d->d_seg + g->seg_count;
     ha.seg_count = g->seg_count;
@@ -381,7 +384,7 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
         return GPUJPEG_ERROR;
     }
     if ( gj_launch_idct_rgb444(d->d_coef, g->bcx, g->bcy, st.comp_tq, d_out, g->width, g->height, g->pitch,
-                               d->idct_flavour, &d->h_tab, d->stream) ) {
+                               d->idct_flavour, ha.dequantize, &d->h_tab, d->stream) ) {
         GJ_ERR("Inverse DCT launch failed: %s\n", gj_cuda_last_error());
         return GPUJPEG_ERROR;
     }
@@ -542,14 +545,17 @@ GPUJPEG_API int gpujpegx_decoder_run_resident(struct gpujpeg_decoder* d, uint8_t
     if ( (stage_mask & 1) && gj_launch_huffman_decode(&d->last_args, d->stream) ) return -1;
     if ( (stage_mask & 2) &&
          gj_launch_idct_rgb444(d->d_coef, g->bcx, g->bcy, d->last_tq, d_out ? d_out : d->d_raw, g->width, g->height,
-                               g->pitch, d->idct_flavour, &d->h_tab, d->stream) )
+                               g->pitch, d->idct_flavour, d->last_args.dequantize, &d->h_tab, d->stream) )
         return -1;
     return 0;
 }
 
 /* ---- extension used by the parity tests: coefficients of the last decoded frame, natural order ---- */
+/* Returns 0 when the values are raw quantised coefficients, 1 when they are already multiplied by the
+ * quantiser and wrapped to int16 (integer IDCT flavour: the multiply is fused into the Huffman decoder). */
 GPUJPEG_API int gpujpegx_decoder_get_coefficients(struct gpujpeg_decoder* d, int16_t* out, size_t count)
 {
-    if ( !d || !d->initialised || count != d->geo.coef_count ) return -1;
-    return gj_coef_to_host_natural(d->d_coef, count, out, d->stream);
+    if ( !d || !d->initialised || !d->last_valid || count != d->geo.coef_count ) return -1;
+    if ( gj_coef_to_host_natural(d->d_coef, count, out, d->stream) ) return -1;
+    return d->last_args.dequantize ? 1 : 0;
 }

@@ -62,30 +62,60 @@ GJ_HD constexpr int gj_nat2zz(int n)
 
 /* RGB -> YCbCr (JPEG full range).  Integer definition [ref: src/gpujpeg_colorspace.h:64-79, 251-266]:
  *     s = c*256/255 (== c + (c==255));  Y = clamp8((77 sR + 150 sG + 29 sB + 128) >> 8) ...
- * evaluated here in float: every intermediate is a multiple of 2^-8 below 2^9, so each product
- * and sum is exact in binary32 and floor() reproduces the arithmetic shift; the result is the
- * integer-valued float the DCT wants.  (tests/test_kernel_math.py checks all 2^24 inputs.) */
-GJ_HD float gj_scale255(float c) { return fmaxf(c, fmaf(c, 2.0f, -254.0f)); }
+ * evaluated here in float WITHOUT any conversion instruction (the XU pipe is 1/8 rate):
+ *   - a byte enters as the float 2^23 + c (the byte PRMT-ed into the mantissa of 0x4B000000);
+ *   - every intermediate is a multiple of 2^-9 below 2^9, so products and sums are exact in binary32;
+ *   - floor((S+128)/256) is obtained by adding 1.5*2^23 to S/256 + 2^-9: the add rounds to the nearest
+ *     integer, and S/256 + 2^-9 is never a tie and never crosses the next integer (fractions are
+ *     k/256 - 127.5/256), so the rounded value IS the arithmetic shift of the reference.
+ * tests/test_kernel_math.py checks all 2^24 RGB inputs against the integer definition. */
+#define GJ_MAGIC23 8388608.0f   /* 2^23     : integer <-> float mantissa trick for bytes   */
+#define GJ_MAGIC15 12582912.0f  /* 1.5*2^23 : round-to-nearest-integer by addition         */
+GJ_HD float gj_byte_as_magic(uint32_t word, int i)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7440 + i));   /* {0x4B,0x00,0x00,byte i} */
+#else
+    union { uint32_t u; float f; } c;
+    c.u = 0x4B000000u | ((word >> (8 * i)) & 0xFFu);
+    return c.f;
+#endif
+}
+/* magic-domain byte (2^23 + c) -> c + (c == 255) as an ordinary float */
+GJ_HD float gj_scale255_m(float cm) { return fmaxf(cm, fmaf(cm, 2.0f, -(GJ_MAGIC23 + 254.0f))) - GJ_MAGIC23; }
+GJ_HD float gj_round_clamp255(float acc) { return fminf(acc + GJ_MAGIC15, GJ_MAGIC15 + 255.0f) - GJ_MAGIC15; }
+GJ_HD void gj_rgb_to_ycbcr_m(float rm, float gm, float bm, float& y, float& cb, float& cr)
+{
+    const float r = gj_scale255_m(rm), g = gj_scale255_m(gm), b = gj_scale255_m(bm);
+    const float e = 1.0f / 512.0f;
+    y = gj_round_clamp255(fmaf(77.0f / 256.0f, r, fmaf(150.0f / 256.0f, g, fmaf(29.0f / 256.0f, b, e))));
+    cb = gj_round_clamp255(fmaf(-43.0f / 256.0f, r, fmaf(-85.0f / 256.0f, g, fmaf(128.0f / 256.0f, b, 128.0f + e))));
+    cr = gj_round_clamp255(fmaf(128.0f / 256.0f, r, fmaf(-107.0f / 256.0f, g, fmaf(-21.0f / 256.0f, b, 128.0f + e))));
+}
+/* convenience form on plain 0..255 values (host tests) */
 GJ_HD void gj_rgb_to_ycbcr(float r, float g, float b, float& y, float& cb, float& cr)
 {
-    r = gj_scale255(r);
-    g = gj_scale255(g);
-    b = gj_scale255(b);
-    y = fminf(floorf(fmaf(77.0f / 256.0f, r, fmaf(150.0f / 256.0f, g, fmaf(29.0f / 256.0f, b, 0.5f)))), 255.0f);
-    cb = fminf(floorf(fmaf(-43.0f / 256.0f, r, fmaf(-85.0f / 256.0f, g, fmaf(128.0f / 256.0f, b, 128.5f)))), 255.0f);
-    cr = fminf(floorf(fmaf(128.0f / 256.0f, r, fmaf(-107.0f / 256.0f, g, fmaf(-21.0f / 256.0f, b, 128.5f)))), 255.0f);
+    gj_rgb_to_ycbcr_m(r + GJ_MAGIC23, g + GJ_MAGIC23, b + GJ_MAGIC23, y, cb, cr);
 }
 
 /* YCbCr (JPEG full range) -> RGB, integer [ref: src/gpujpeg_colorspace.h:86-101, 268-283]:
  *   y = Y*256/255 (== Y + (Y==255)); cb = (Cb-128)*256/255 (== Cb-128, C truncation); likewise cr */
 GJ_HD int gj_clamp8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+/* values BEFORE the final clamp to [0,255] (the kernel clamps while packing bytes) */
+GJ_HD void gj_ycbcr_to_rgb_raw(int Y, int Cb, int Cr, int& r, int& g, int& b)
+{
+    const int y = Y * 256 + ((Y + 1) & 0x100) + 128;   /* (Y + (Y==255)) * 256 + 128 */
+    const int cb = Cb - 128, cr = Cr - 128;
+    r = (y + 359 * cr) >> 8;
+    g = (y - 88 * cb - 183 * cr) >> 8;
+    b = (y + 454 * cb) >> 8;
+}
 GJ_HD void gj_ycbcr_to_rgb(int Y, int Cb, int Cr, int& r, int& g, int& b)
 {
-    const int y = (Y + (Y == 255 ? 1 : 0)) * 256 + 128;
-    const int cb = Cb - 128, cr = Cr - 128;
-    r = gj_clamp8((y + 359 * cr) >> 8);
-    g = gj_clamp8((y - 88 * cb - 183 * cr) >> 8);
-    b = gj_clamp8((y + 454 * cb) >> 8);
+    gj_ycbcr_to_rgb_raw(Y, Cb, Cr, r, g, b);
+    r = gj_clamp8(r);
+    g = gj_clamp8(g);
+    b = gj_clamp8(b);
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -209,6 +239,57 @@ GJ_HD void gj_idct_col(int& b0, int& b1, int& b2, int& b3, int& b4, int& b5, int
     b5 = gj_iclip((x0 - x4) >> 14);
     b6 = gj_iclip((x3 - x2) >> 14);
     b7 = gj_iclip((x7 - x1) >> 14);
+}
+
+/* Column pass producing PIXEL values before the final clamp: the reference computes
+ *     clamp8( int16( iclip(t) + 128 ) ),  t = (..) >> 14,  iclip = clamp to [-256,255]
+ * (src/gpujpeg_dct_cpu.c:163-170, 243-248).  iclip(t)+128 lies in [-128,383] so the int16 cast is the
+ * identity and the two clamps collapse into clamp(t + 128, 0, 255); t + 128 == (x + (128 << 14)) >> 14
+ * exactly, so the level shift rides on the rounding constant of x0.  Returns t + 128 (unclamped). */
+GJ_HD void gj_idct_col_px(int& b0, int& b1, int& b2, int& b3, int& b4, int& b5, int& b6, int& b7)
+{
+    int x0 = (b0 << 8) + 8192 + (128 << 14), x1 = b4 << 8, x2 = b6, x3 = b2, x4 = b1, x5 = b7, x6 = b5, x7 = b3, x8;
+    x8 = GJ_W7 * (x4 + x5) + 4;
+    x4 = (x8 + (GJ_W1 - GJ_W7) * x4) >> 3;
+    x5 = (x8 - (GJ_W1 + GJ_W7) * x5) >> 3;
+    x8 = GJ_W3 * (x6 + x7) + 4;
+    x6 = (x8 - (GJ_W3 - GJ_W5) * x6) >> 3;
+    x7 = (x8 - (GJ_W3 + GJ_W5) * x7) >> 3;
+    x8 = x0 + x1;
+    x0 -= x1;
+    x1 = GJ_W6 * (x3 + x2) + 4;
+    x2 = (x1 - (GJ_W2 + GJ_W6) * x2) >> 3;
+    x3 = (x1 + (GJ_W2 - GJ_W6) * x3) >> 3;
+    x1 = x4 + x6;
+    x4 -= x6;
+    x6 = x5 + x7;
+    x5 -= x7;
+    x7 = x8 + x3;
+    x8 -= x3;
+    x3 = x0 + x2;
+    x0 -= x2;
+    x2 = (181 * (x4 + x5) + 128) >> 8;
+    x4 = (181 * (x4 - x5) + 128) >> 8;
+    b0 = (x7 + x1) >> 14;
+    b1 = (x3 + x2) >> 14;
+    b2 = (x0 + x4) >> 14;
+    b3 = (x8 + x6) >> 14;
+    b4 = (x8 - x6) >> 14;
+    b5 = (x0 - x4) >> 14;
+    b6 = (x3 - x2) >> 14;
+    b7 = (x7 - x1) >> 14;
+}
+/* rows as the reference, columns with gj_idct_col_px: v[] in = dequantised int16 coefficients,
+ * v[] out = pixel values before the clamp to [0,255] */
+GJ_HD void gj_idct_int_block_px(int (&v)[64])
+{
+#pragma unroll
+    for ( int y = 0; y < 8; y++ )
+        gj_idct_row(v[8 * y], v[8 * y + 1], v[8 * y + 2], v[8 * y + 3], v[8 * y + 4], v[8 * y + 5], v[8 * y + 6],
+                    v[8 * y + 7]);
+#pragma unroll
+    for ( int x = 0; x < 8; x++ )
+        gj_idct_col_px(v[x], v[8 + x], v[16 + x], v[24 + x], v[32 + x], v[40 + x], v[48 + x], v[56 + x]);
 }
 
 /* v[] holds DEQUANTISED coefficients already wrapped to int16 (natural order); result: samples

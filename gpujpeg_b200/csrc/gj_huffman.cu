@@ -275,40 +275,78 @@ k_huff_encode(const int16_t* __restrict__ coef, int nblk, int cps /*components p
     }
 }
 
-/* exclusive scan over segment sizes -> byte offsets in the finished stream.  One CTA. */
+/* exclusive scan over segment sizes -> byte offsets in the finished stream.  One CTA walks the array in
+ * tiles of 8192 segments: coalesced 32-byte loads per thread, shuffle scans, one smem hop per tile. */
 constexpr int OFF_THREADS = 1024;
+constexpr int OFF_PER = 8;
 __global__ void __launch_bounds__(OFF_THREADS)
 k_huff_offsets(const uint32_t* __restrict__ seg_bytes, int seg_count, int seg_per_scan, uint32_t header_size, int sos_len,
                uint64_t stream_cap, uint64_t* __restrict__ seg_off, uint64_t* __restrict__ info)
 {
-    __shared__ uint64_t s_part[OFF_THREADS];
-    const int per = (seg_count + OFF_THREADS - 1) / OFF_THREADS;
-    const int a = threadIdx.x * per, b = min(seg_count, a + per);
-    uint64_t sum = 0;
-    for ( int g = a; g < b; g++ ) {
-        const int s = g % seg_per_scan;
-        // every segment but the last of its scan is followed by a 2-byte RSTn marker;
-        // the first segment of a scan is preceded by the SOS header
-        sum += seg_bytes[g] + (s + 1 < seg_per_scan ? 2u : 0u) + (s == 0 ? (uint32_t)sos_len : 0u);
-    }
-    s_part[threadIdx.x] = sum;
-    __syncthreads();
-    for ( int d = 1; d < OFF_THREADS; d <<= 1 ) {
-        uint64_t t = 0;
-        if ( (int)threadIdx.x >= d ) t = s_part[threadIdx.x - d];
+    __shared__ uint64_t s_warp[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t carry = header_size;   // stream offset where the current tile starts (uniform)
+    for ( int tile0 = 0; tile0 < seg_count; tile0 += OFF_THREADS * OFF_PER ) {
+        const int g0 = tile0 + threadIdx.x * OFF_PER;
+        uint32_t v[OFF_PER];
+        if ( g0 + OFF_PER <= seg_count ) {
+            const uint4 a = reinterpret_cast<const uint4*>(seg_bytes + g0)[0];
+            const uint4 b = reinterpret_cast<const uint4*>(seg_bytes + g0)[1];
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        }
+        else {
+#pragma unroll
+            for ( int i = 0; i < OFF_PER; i++ )
+                v[i] = g0 + i < seg_count ? seg_bytes[g0 + i] : 0u;
+        }
+        /* size of every segment as it appears in the stream: [SOS header] bytes [RSTn] */
+        int s = g0 < seg_count ? g0 % seg_per_scan : 0;
+        uint32_t pre[OFF_PER];   // SOS bytes in front of the segment
+        uint32_t sum = 0;
+        uint32_t excl[OFF_PER];
+#pragma unroll
+        for ( int i = 0; i < OFF_PER; i++ ) {
+            const bool valid = g0 + i < seg_count;
+            pre[i] = valid && s == 0 ? (uint32_t)sos_len : 0u;
+            excl[i] = sum + pre[i];
+            sum += pre[i] + v[i] + (valid && s + 1 < seg_per_scan ? 2u : 0u);
+            if ( ++s == seg_per_scan ) s = 0;
+        }
+        uint64_t incl = sum;
+#pragma unroll
+        for ( int d = 1; d < 32; d <<= 1 ) {
+            const uint64_t t = __shfl_up_sync(FULL, incl, d);
+            if ( lane >= d ) incl += t;
+        }
+        if ( lane == 31 ) s_warp[warp] = incl;
         __syncthreads();
-        s_part[threadIdx.x] += t;
+        if ( warp == 0 ) {
+            uint64_t w = s_warp[lane];
+#pragma unroll
+            for ( int d = 1; d < 32; d <<= 1 ) {
+                const uint64_t t = __shfl_up_sync(FULL, w, d);
+                if ( lane >= d ) w += t;
+            }
+            s_warp[lane] = w;   // inclusive prefix over warps
+        }
+        __syncthreads();
+        const uint64_t base = carry + (warp ? s_warp[warp - 1] : 0) + (incl - sum);
+        if ( g0 + OFF_PER <= seg_count ) {
+            ulonglong2* o = reinterpret_cast<ulonglong2*>(seg_off + g0);
+#pragma unroll
+            for ( int i = 0; i < OFF_PER; i += 2 )
+                o[i >> 1] = make_ulonglong2(base + excl[i], base + excl[i + 1]);
+        }
+        else {
+#pragma unroll
+            for ( int i = 0; i < OFF_PER; i++ )
+                if ( g0 + i < seg_count ) seg_off[g0 + i] = base + excl[i];
+        }
+        carry += s_warp[31];
         __syncthreads();
     }
-    uint64_t off = header_size + (threadIdx.x ? s_part[threadIdx.x - 1] : 0);
-    for ( int g = a; g < b; g++ ) {
-        const int s = g % seg_per_scan;
-        if ( s == 0 ) off += (uint32_t)sos_len;
-        seg_off[g] = off;
-        off += seg_bytes[g] + (s + 1 < seg_per_scan ? 2u : 0u);
-    }
-    if ( threadIdx.x == OFF_THREADS - 1 ) {
-        const uint64_t total = header_size + s_part[OFF_THREADS - 1] + 2;  // + EOI
+    if ( threadIdx.x == 0 ) {
+        const uint64_t total = carry + 2;  // + EOI
         info[0] = total;
         info[1] = total > stream_cap ? 1 : 0;
     }
@@ -368,29 +406,70 @@ k_huff_compact(const uint8_t* __restrict__ tmp, size_t slot_stride, const uint32
 /* decoder                                                                                       */
 
 constexpr int HD_THREADS = 128;
-constexpr int HD_STRIDE = 33;  // words per private block (32 + 1 pad: bank = (tid + word) % 32)
 
 struct DecTabs {
     gj_dec_lut t[2][4];
 };
 
+/* Bit source of one lane.  The segment's bytes are pulled as aligned 32-bit words, one word ahead of
+ * use so the load latency hides behind the decoding of the previous word; byte stuffing (FF 00) is
+ * removed word-wise on the fast path (no 0xFF in the word) and byte-wise otherwise. */
 struct BitSource {
-    const uint8_t* p;
-    const uint8_t* end;
-    uint64_t acc;
-    int n;
+    const uint32_t* wp;   // next word to fetch
+    const uint32_t* wend; // first word that must not be read
+    uint32_t nextw;       // word already loaded from wp[-1]... see src_init
+    uint64_t acc;         // bit buffer, newest bits at the bottom
+    int n;                // valid bits in acc
+    bool skip_zero;       // previous byte was 0xFF: a following 0x00 is stuffing
 };
 
-__device__ __forceinline__ void src_fill(BitSource& r)
+__device__ __forceinline__ uint32_t src_load(BitSource& r)
 {
-    while ( r.n <= 56 ) {
-        uint32_t b = 0;  // past the end of the segment: zeros (only corrupt streams get here)
-        if ( r.p < r.end ) {
-            b = *r.p++;
-            if ( b == 0xFF && r.p < r.end && *r.p == 0 ) r.p++;  // drop the stuffed zero
+    const uint32_t w = r.nextw;
+    r.nextw = r.wp < r.wend ? __ldg(r.wp) : 0u;
+    r.wp++;
+    return w;
+}
+__device__ __forceinline__ void src_bytes(BitSource& r, uint32_t w, int first)
+{
+#pragma unroll
+    for ( int i = 0; i < 4; i++ ) {
+        if ( i < first ) continue;
+        const uint32_t b = (w >> (8 * i)) & 0xFFu;
+        if ( r.skip_zero ) {
+            r.skip_zero = false;
+            if ( b == 0 ) continue;
         }
         r.acc = (r.acc << 8) | b;
         r.n += 8;
+        r.skip_zero = b == 0xFFu;
+    }
+}
+__device__ __forceinline__ void src_init(BitSource& r, const uint8_t* p, const uint8_t* file_end)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    r.wp = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
+    r.wend = reinterpret_cast<const uint32_t*>((reinterpret_cast<uintptr_t>(file_end) + 3) & ~static_cast<uintptr_t>(3));
+    r.acc = 0;
+    r.n = 0;
+    r.skip_zero = false;
+    r.nextw = r.wp < r.wend ? __ldg(r.wp) : 0u;
+    r.wp++;
+    src_bytes(r, src_load(r), (int)(a & 3));   // the segment may start inside a word
+}
+/* make at least 33 bits available (a Huffman code + its value bits need at most 16 + 15) */
+__device__ __forceinline__ void src_fill(BitSource& r)
+{
+    while ( r.n <= 32 ) {   // one word is enough unless it held stuffed bytes
+        const uint32_t w = src_load(r);
+        const uint32_t ff = ((w & 0x7F7F7F7Fu) + 0x01010101u) & w & 0x80808080u;   // != 0 iff some byte is 0xFF
+        if ( ff == 0 && !r.skip_zero ) {
+            r.acc = (r.acc << 32) | __byte_perm(w, 0, 0x0123);
+            r.n += 32;
+        }
+        else {
+            src_bytes(r, w, 0);
+        }
     }
 }
 __device__ __forceinline__ uint32_t src_peek16(const BitSource& r) { return (uint32_t)(r.acc >> (r.n - 16)) & 0xFFFFu; }
@@ -418,20 +497,27 @@ __device__ __forceinline__ int decode_symbol(BitSource& r, const gj_dec_lut& t)
     return t.vals[((int)(peek >> (16 - l)) + t.valoff[l]) & 255];
 }
 
+/* DEQ: store coefficient * quantiser wrapped to int16 -- exactly what the reference's integer IDCT
+ * starts from (src/gpujpeg_dct_cpu.c:180-182) -- so the multiply is paid per NON-ZERO coefficient here
+ * instead of 64 times per block in K4.  DEQ = false keeps raw quantised values (float IDCT flavour). */
+template <bool DEQ>
 __global__ void __launch_bounds__(HD_THREADS)
-k_huff_decode(const uint8_t* __restrict__ file, const uint32_t* __restrict__ seg_off, const uint32_t* __restrict__ seg_len,
+k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file_end, const uint32_t* __restrict__ seg_off,
               int seg_count, int seg_per_scan, int cps, int seg_mcu, int nblk, const __grid_constant__ gj_huff_dec_args a,
               int16_t* __restrict__ coef, const gj_dev_dec_tables* __restrict__ tables)
 {
     __shared__ DecTabs s_tab;
-    __shared__ uint32_t s_blk[HD_THREADS * HD_STRIDE];
+    __shared__ uint16_t s_q[4][64];
+    __shared__ __align__(16) uint32_t s_blk[HD_THREADS * 32];   // one private 8x8 block (128 B) per thread
 
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(&tables->lut[0][0]);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
         for ( int i = threadIdx.x; i < (int)(sizeof(DecTabs) / 4); i += HD_THREADS )
             dst[i] = src[i];
-        for ( int i = threadIdx.x; i < HD_THREADS * HD_STRIDE; i += HD_THREADS )
+        for ( int i = threadIdx.x; i < 256; i += HD_THREADS )
+            s_q[i >> 6][i & 63] = tables->qinv_zz[i >> 6][i & 63];
+        for ( int i = threadIdx.x; i < HD_THREADS * 32; i += HD_THREADS )
             s_blk[i] = 0;
     }
     __syncthreads();
@@ -441,18 +527,24 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint32_t* __restrict__ seg
     if ( g0 >= seg_count ) return;
     const int g = g0 + lane;
     const bool live = g < seg_count;
-    int scan = 0, s = 0, nblocks = 0;
-    BitSource r = {nullptr, nullptr, 0, 0};
+    int scan = 0, nblocks = 0, mybase = 0;
+    BitSource r;
+    r.n = 0;
     if ( live ) {
         scan = g / seg_per_scan;
-        s = g - scan * seg_per_scan;
+        const int s = g - scan * seg_per_scan;
         nblocks = min(seg_mcu, nblk - s * seg_mcu) * cps;
-        r.p = file + seg_off[g];
-        r.end = r.p + seg_len[g];
+        // block index (in units of 64 coefficients) of the segment's first MCU; for single-component
+        // scans the component plane is folded in here, for interleaved scans it is added per block
+        mybase = s * seg_mcu + (cps == 1 ? a.scan_comp[scan][0] * nblk : 0);
+        src_init(r, file + seg_off[g], file_end);
     }
     const int max_blocks = seg_mcu * cps;
-    int16_t* mine = reinterpret_cast<int16_t*>(s_blk + threadIdx.x * HD_STRIDE);
-    uint32_t* wbase = s_blk + (threadIdx.x & ~31) * HD_STRIDE;
+    /* private block: 16-byte chunk c of lane L lives at chunk (c ^ (L & 7)) so that the warp-wide
+     * 16-byte reads of the flush below are bank-conflict free */
+    const int sw = lane & 7;
+    int16_t* mine = reinterpret_cast<int16_t*>(s_blk + threadIdx.x * 32);
+    uint4* wbase = reinterpret_cast<uint4*>(s_blk + (threadIdx.x & ~31) * 32);
     int pred[GJ_MAX_COMP] = {0, 0, 0, 0};
 
     for ( int b = 0; b < max_blocks; b++ ) {
@@ -461,6 +553,7 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint32_t* __restrict__ seg
         if ( live && b < nblocks ) {
             const gj_dec_lut& tdc = s_tab.t[0][a.scan_td[scan][ci]];
             const gj_dec_lut& tac = s_tab.t[1][a.scan_ta[scan][ci]];
+            const uint16_t* q = s_q[a.scan_tq[scan][ci]];
             src_fill(r);
             int sz = decode_symbol(r, tdc) & 15;
             int diff = 0;
@@ -471,7 +564,7 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint32_t* __restrict__ seg
             else if ( ci == 1 ) pr = (pred[1] += diff);
             else if ( ci == 2 ) pr = (pred[2] += diff);
             else pr = (pred[3] += diff);
-            mine[0] = (int16_t)pr;
+            mine[(0 ^ sw) << 3] = (int16_t)(DEQ ? pr * (int)q[0] : pr);
             for ( int k = 1; k < 64; ) {
                 src_fill(r);
                 const int rs = decode_symbol(r, tac);
@@ -480,7 +573,7 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint32_t* __restrict__ seg
                 if ( sz ) {
                     k += run;
                     const int v = gj_extend((int)src_get(r, sz), sz);
-                    if ( k < 64 ) mine[k] = (int16_t)v;
+                    if ( k < 64 ) mine[(((k >> 3) ^ sw) << 3) | (k & 7)] = (int16_t)(DEQ ? v * (int)q[k] : v);
                     k++;
                 }
                 else {
@@ -490,18 +583,18 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint32_t* __restrict__ seg
             }
         }
         __syncwarp();
-        /* write the 32 private blocks of this warp out as 128-byte lines and clear them */
-        int gs = g0 / seg_per_scan, ss = g0 - gs * seg_per_scan;
-        for ( int i = 0; i < 32; i++ ) {
-            const bool ok = g0 + i < seg_count && b < min(seg_mcu, nblk - ss * seg_mcu) * cps;
-            const uint32_t w = wbase[i * HD_STRIDE + lane];
-            wbase[i * HD_STRIDE + lane] = 0;
-            if ( ok ) {
-                const int comp = a.scan_comp[gs][ci];
-                uint32_t* dst = reinterpret_cast<uint32_t*>(coef + ((size_t)comp * nblk + (size_t)ss * seg_mcu + mcu) * 64);
-                dst[lane] = w;
-            }
-            if ( ++ss == seg_per_scan ) { ss = 0; gs++; }
+        /* write the warp's 32 private blocks out as 128-byte lines, four blocks per step, and clear them */
+        const int extra = (cps == 1 ? 0 : a.scan_comp[0][ci] * nblk) + mcu;
+#pragma unroll
+        for ( int j = 0; j < 8; j++ ) {
+            const int i = 4 * j + (lane >> 3);   // owner lane of the block this lane helps to move
+            const int c = lane & 7;              // its 16-byte chunk
+            const int ob = __shfl_sync(FULL, mybase, i);
+            const int on = __shfl_sync(FULL, nblocks, i);
+            uint4* src = wbase + i * 8 + (c ^ (i & 7));
+            const uint4 v = *src;
+            *src = make_uint4(0u, 0u, 0u, 0u);
+            if ( b < on ) reinterpret_cast<uint4*>(coef + (size_t)(ob + extra) * 64)[c] = v;
         }
         __syncwarp();
     }
@@ -538,9 +631,15 @@ extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_str
 
 extern "C" int gj_launch_huffman_decode(const struct gj_huff_dec_args* a, gj_stream_t stream)
 {
-    k_huff_decode<<<(a->seg_count + HD_THREADS - 1) / HD_THREADS, HD_THREADS, 0, stream>>>(
-        a->d_file, a->d_seg_off, a->d_seg_len, a->seg_count, a->seg_per_scan, a->comps_per_scan, a->seg_mcu, a->nblk, *a,
-        a->d_coef, a->d_tables);
+    const dim3 grid((a->seg_count + HD_THREADS - 1) / HD_THREADS);
+    if ( a->dequantize )
+        k_huff_decode<true><<<grid, HD_THREADS, 0, stream>>>(a->d_file, a->d_file + a->file_size, a->d_seg_off, a->seg_count,
+                                                             a->seg_per_scan, a->comps_per_scan, a->seg_mcu, a->nblk, *a,
+                                                             a->d_coef, a->d_tables);
+    else
+        k_huff_decode<false><<<grid, HD_THREADS, 0, stream>>>(a->d_file, a->d_file + a->file_size, a->d_seg_off, a->seg_count,
+                                                              a->seg_per_scan, a->comps_per_scan, a->seg_mcu, a->nblk, *a,
+                                                              a->d_coef, a->d_tables);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -174,11 +174,14 @@ int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_stream_t strea
  * [replaces ref: src/gpujpeg_huffman_gpu_decoder.cu:663-746] */
 struct gj_huff_dec_args {
     const uint8_t* d_file;      /* the JPEG bytes */
+    size_t file_size;
     const uint32_t* d_seg_off;  /* [seg_count] file offset of each segment's entropy bytes */
-    const uint32_t* d_seg_len;
+    const uint32_t* d_seg_len;  /* informative: the decoder stops after the segment's block count */
+    int dequantize;             /* 1: store coefficient*quantiser wrapped to int16 (integer IDCT flavour) */
     int seg_count, seg_per_scan, scan_count, comps_per_scan, seg_mcu, nblk;
     int scan_comp[GJ_MAX_COMP][GJ_MAX_COMP]; /* component index of the i-th component of scan s */
     int scan_td[GJ_MAX_COMP][GJ_MAX_COMP], scan_ta[GJ_MAX_COMP][GJ_MAX_COMP];
+    int scan_tq[GJ_MAX_COMP][GJ_MAX_COMP]; /* quantisation table id of that component */
     int16_t* d_coef;
     const struct gj_dev_dec_tables* d_tables;
 };
@@ -188,8 +191,8 @@ int gj_launch_huffman_decode(const struct gj_huff_dec_args* a, gj_stream_t strea
  * idct_flavour: 0 = integer (gpujpeg_idct_cpu), 1 = float GPU-reference
  * [replaces ref: src/gpujpeg_dct_gpu.cu:681-727 + src/gpujpeg_postprocessor.cu:444-496] */
 int gj_launch_idct_rgb444(const int16_t* d_coef, int bcx, int bcy, const int comp_tq[3], uint8_t* d_raw, int width,
-                          int height, int pitch, int idct_flavour, const struct gj_dev_dec_tables* d_tables,
-                          gj_stream_t stream);
+                          int height, int pitch, int idct_flavour, int coef_dequantized,
+                          const struct gj_dev_dec_tables* d_tables, gj_stream_t stream);
 
 /* debug/test helper: device coefficient buffer (zig-zag) -> host natural order, block-major */
 int gj_coef_to_host_natural(const int16_t* d_coef, size_t count, int16_t* h_out, gj_stream_t stream);

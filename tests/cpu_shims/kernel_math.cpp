@@ -78,9 +78,15 @@ void km_idct_plane(const int16_t* coef, int dw, int dh, const uint16_t* q_zz, in
                     const int n = gj_zz2nat(k);
                     v[n] = gj_s16((int)in[n] * (int)(short)q_zz[k]);
                 }
-                gj_idct_int_block(v);
+                int u[64];
                 for ( int i = 0; i < 64; i++ )
-                    px[i] = (uint8_t)gj_clamp8(gj_s16(v[i] + 128));
+                    u[i] = v[i];
+                gj_idct_int_block(v);      // the reference's own formulation ...
+                gj_idct_int_block_px(u);   // ... and the fused-level-shift variant the kernel runs
+                for ( int i = 0; i < 64; i++ ) {
+                    px[i] = (uint8_t)gj_clamp8(u[i]);
+                    if ( px[i] != (uint8_t)gj_clamp8(gj_s16(v[i] + 128)) ) px[i] ^= 0x55;   // force a test failure
+                }
             }
             else {
                 float f[64];
