@@ -201,17 +201,12 @@ static size_t scan_end(const uint8_t* d, size_t b, size_t size)
     return size;
 }
 
-int gj_reader_parse(const uint8_t* d, size_t size, struct gj_stream* s, int verbose)
+/* Walks marker segments starting at *pos.  Returns 1 when an SOS header was parsed (a new entry in
+ * s->scan with .begin = first entropy-coded byte, *pos = .begin), 0 at EOI or end of data, -1 on error.
+ * Never looks at entropy-coded data. */
+int gj_reader_walk(const uint8_t* d, size_t size, size_t* pos, struct gj_stream* s, int* adobe_transform)
 {
-    memset(s, 0, sizeof *s);
-    s->color_space = GPUJPEG_YCBCR_BT601_256LVLS; /* JFIF default */
-    s->header_type = GPUJPEG_HEADER_DEFAULT;
-    if ( size < 4 || d[0] != 0xFF || d[1] != 0xD8 ) {
-        GJ_ERR("JPEG data should begin with SOI marker!\n");
-        return -1;
-    }
-    size_t i = 2;
-    int seen_eoi = 0, adobe_transform = -1;
+    size_t i = *pos;
     while ( i + 2 <= size ) {
         if ( d[i] != 0xFF ) {
             GJ_ERR("Failed to read marker from JPEG data at offset %zu!\n", i);
@@ -223,8 +218,8 @@ int gj_reader_parse(const uint8_t* d, size_t size, struct gj_stream* s, int verb
             continue;
         }
         if ( m == 0xD9 ) {
-            seen_eoi = 1;
-            break;
+            *pos = i;
+            return 0;
         }
         if ( m == 0xD8 || m == 0x01 || (m >= 0xD0 && m <= 0xD7) ) { /* standalone markers */
             i += 2;
@@ -245,7 +240,7 @@ int gj_reader_parse(const uint8_t* d, size_t size, struct gj_stream* s, int verb
             case 0xEE:
                 if ( n >= 12 && memcmp(b, "Adobe", 5) == 0 ) {
                     s->header_type = GPUJPEG_HEADER_ADOBE;
-                    adobe_transform = b[11];
+                    *adobe_transform = b[11];
                 }
                 break;
             case 0xFE:
@@ -334,6 +329,7 @@ int gj_reader_parse(const uint8_t* d, size_t size, struct gj_stream* s, int verb
                 }
                 if ( s->scan_count == 0 ) s->header_size = i;
                 struct gj_scan_info* sc = &s->scan[s->scan_count++];
+                memset(sc, 0, sizeof *sc);
                 sc->ncomp = b[0];
                 if ( sc->ncomp < 1 || sc->ncomp > s->comp_count || n < 1 + 2 * sc->ncomp + 3 ) return -1;
                 for ( int k = 0; k < sc->ncomp; k++ ) {
@@ -350,29 +346,63 @@ int gj_reader_parse(const uint8_t* d, size_t size, struct gj_stream* s, int verb
                     if ( sc->td[k] > 3 || sc->ta[k] > 3 ) return -1;
                 }
                 sc->begin = i + 2 + (size_t)len;
-                sc->end = scan_end(d, sc->begin, size);
-                i = sc->end;
-                continue;
+                sc->end = sc->begin;
+                *pos = sc->begin;
+                return 1;
             }
             default:
                 break; /* APPn and anything else with a length: skipped */
         }
         i += 2 + (size_t)len;
     }
-    (void)seen_eoi;
+    *pos = i;
+    return 0;
+}
+
+void gj_reader_begin(struct gj_stream* s)
+{
+    memset(s, 0, sizeof *s);
+    s->color_space = GPUJPEG_YCBCR_BT601_256LVLS; /* JFIF default */
+    s->header_type = GPUJPEG_HEADER_DEFAULT;
+}
+
+/* colour space detection subset [ref: src/gpujpeg_reader.c:264-640]: Adobe transform 0 or component ids
+ * 'R','G','B' => RGB; everything else => YCbCr JPEG (full range BT.601) */
+int gj_reader_finish(struct gj_stream* s, int adobe_transform, int verbose)
+{
     if ( s->scan_count == 0 || s->width == 0 || s->height == 0 ) {
         GJ_ERR("JPEG data contains no image!\n");
         return -1;
     }
-    /* colour space detection subset [ref: src/gpujpeg_reader.c:264-640]: Adobe transform 0 or
-     * component ids 'R','G','B' => RGB; everything else => YCbCr JPEG (full range BT.601) */
     if ( s->comp_count == 3 &&
          (adobe_transform == 0 || (s->comp_id[0] == 'R' && s->comp_id[1] == 'G' && s->comp_id[2] == 'B')) )
         s->color_space = GPUJPEG_RGB;
-    s->interleaved = s->scan_count == 1 && s->comp_count > 1;
+    s->interleaved = s->scan[0].ncomp > 1;
     GJ_DEBUG(verbose, "parsed %dx%d, %d comps, %d scans, rst %d\n", s->width, s->height, s->comp_count,
              s->scan_count, s->restart_interval);
     return 0;
+}
+
+/* full host parse: headers by gj_reader_walk, scan extents by a memchr walk (used by the image-info
+ * functions and the tests; the decoder finds scan extents on the GPU instead, gj_markers.cu) */
+int gj_reader_parse(const uint8_t* d, size_t size, struct gj_stream* s, int verbose)
+{
+    gj_reader_begin(s);
+    if ( size < 4 || d[0] != 0xFF || d[1] != 0xD8 ) {
+        GJ_ERR("JPEG data should begin with SOI marker!\n");
+        return -1;
+    }
+    size_t pos = 2;
+    int adobe = -1;
+    for ( ;; ) {
+        const int r = gj_reader_walk(d, size, &pos, s, &adobe);
+        if ( r < 0 ) return -1;
+        if ( r == 0 ) break;
+        struct gj_scan_info* sc = &s->scan[s->scan_count - 1];
+        sc->end = scan_end(d, sc->begin, size);
+        pos = sc->end;
+    }
+    return gj_reader_finish(s, adobe, verbose);
 }
 
 /* Split every scan at its RSTn markers.  Offsets/lengths describe the stuffed entropy bytes inside

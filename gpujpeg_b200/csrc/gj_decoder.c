@@ -5,9 +5,11 @@
  * from the stream, one CUDA stream, blocks until the pixels are where the output descriptor says.
  * Pipeline of this build:
  *
- *     host reader: marker walk + RST split (offsets only; the file is uploaded ONCE, untouched,
- *                  instead of being re-packed segment by segment, src/gpujpeg_reader.c:1107-1112)
- *     H2D file bytes + segment table
+ *     host reader: marker segments only (headers, SOS); the file is uploaded ONCE, untouched, and the
+ *                  restart markers are found by K0 on the device -- the reference walks the whole stream
+ *                  with memchr and re-packs it segment by segment (src/gpujpeg_reader.c:1038-1155),
+ *                  which alone costs 2.1 ms for an 8K frame on a B200 host (profiles/r1_b)
+ *     H2D file bytes -> K0 marker list -> (tiny D2H, sync) -> host finishes the marker walk
  *       -> K3 Huffman decode (always on the GPU: no "fewer than 32 segments => CPU" fallback,
  *          src/gpujpeg_decoder.c:254-286)
  *       -> K4 dequant + IDCT + colour transform + interleave (one launch)
@@ -20,6 +22,8 @@
 #include <string.h>
 
 #include "gj_internal.h"
+
+#define GJ_MK_OTHER_CAP 64 /* markers other than RSTn the device reports back (SOS, EOI, ...) */
 
 struct gpujpeg_decoder {
     gj_stream_t stream;
@@ -39,8 +43,11 @@ struct gpujpeg_decoder {
     int tab_valid;
 
     uint8_t* d_file; size_t d_file_size;
-    uint32_t* d_seg; size_t d_seg_size;      /* offsets then lengths */
-    uint32_t* h_seg; size_t h_seg_size;      /* pinned; offsets then lengths */
+    uint32_t* d_list_pos; size_t d_list_pos_size;   /* K0 marker list: positions */
+    uint8_t* d_list_code; size_t d_list_code_size;  /*                  codes     */
+    uint32_t* d_cta; size_t d_cta_size;             /* K0 scratch */
+    uint32_t* d_mk;                                 /* K0 results (layout in gpujpeg_decoder_decode) */
+    uint32_t* h_mk;                                 /* pinned mirror */
     int16_t* d_coef; size_t d_coef_size;
     uint8_t* d_raw; size_t d_raw_size;
     uint8_t* h_raw; size_t h_raw_size;       /* pinned, INTERNAL_BUFFER output */
@@ -103,7 +110,9 @@ struct gpujpeg_decoder* gpujpeg_decoder_create_with_params(const struct gpujpeg_
     d->device = gj_cuda_get_device();
     d->req_pixel_format = GPUJPEG_PIXFMT_AUTODETECT;
     d->req_color_space = GPUJPEG_CS_DEFAULT;
-    if ( d->device < 0 || gj_cuda_malloc((void**)&d->d_tab, sizeof *d->d_tab) ) {
+    if ( d->device < 0 || gj_cuda_malloc((void**)&d->d_tab, sizeof *d->d_tab) ||
+         gj_cuda_malloc((void**)&d->d_mk, (8 + 3 * GJ_MK_OTHER_CAP) * 4) ||
+         gj_cuda_malloc_host((void**)&d->h_mk, (8 + 3 * GJ_MK_OTHER_CAP) * 4) ) {
         GJ_ERR("Decoder allocation failed: %s\n", gj_cuda_last_error());
         free(d);
         return NULL;
@@ -125,8 +134,11 @@ int gpujpeg_decoder_destroy(struct gpujpeg_decoder* d)
     if ( !d ) return -1;
     gj_cuda_free(d->d_tab);
     gj_cuda_free(d->d_file);
-    gj_cuda_free(d->d_seg);
-    gj_cuda_free_host(d->h_seg);
+    gj_cuda_free(d->d_list_pos);
+    gj_cuda_free(d->d_list_code);
+    gj_cuda_free(d->d_cta);
+    gj_cuda_free(d->d_mk);
+    gj_cuda_free_host(d->h_mk);
     gj_cuda_free(d->d_coef);
     gj_cuda_free(d->d_raw);
     gj_cuda_free_host(d->h_raw);
@@ -176,12 +188,10 @@ int gpujpeg_decoder_init(struct gpujpeg_decoder* d, const struct gpujpeg_paramet
     gj_geometry_init(&d->geo, &p, &pi);
     const struct gj_geometry* g = &d->geo;
     if ( grow_dev((void**)&d->d_coef, &d->d_coef_size, g->coef_count * 2) ||
-         grow_dev((void**)&d->d_raw, &d->d_raw_size, g->raw_size) ||
-         grow_dev((void**)&d->d_seg, &d->d_seg_size, (size_t)g->seg_count * 8) ) {
+         grow_dev((void**)&d->d_raw, &d->d_raw_size, g->raw_size) ) {
         GJ_ERR("Decoder device allocation failed: %s\n", gj_cuda_last_error());
         return -1;
     }
-    if ( grow_host((void**)&d->h_seg, &d->h_seg_size, (size_t)g->seg_count * 8) ) return -1;
     d->param = p;
     d->param_image = pi;
     d->initialised = 1;
@@ -218,10 +228,21 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     const int stats = d->perf_stats || d->verbose >= GPUJPEG_LL_STATUS;
     const double t_begin = gpujpeg_get_time();
 
-    /* ---- host reader ---- */
+    /* ---- host reader, part 1: marker segments up to the first SOS (never touches entropy-coded data) ---- */
     struct gj_stream st;
-    if ( gj_reader_parse(image, image_size, &st, d->verbose) ) {
-        GJ_ERR("Decoder failed when decoding image data!\n");
+    gj_reader_begin(&st);
+    if ( image_size < 4 || image[0] != 0xFF || image[1] != 0xD8 ) {
+        GJ_ERR("JPEG data should begin with SOI marker!\n");
+        return GPUJPEG_ERROR;
+    }
+    if ( image_size >= 0xFFFFFFFFull ) {
+        GJ_ERR("JPEG streams of 4 GiB or more are not supported.\n");
+        return GPUJPEG_ERROR;
+    }
+    size_t pos = 2;
+    int adobe = -1;
+    if ( gj_reader_walk(image, image_size, &pos, &st, &adobe) != 1 ) {
+        GJ_ERR("Decoder failed when decoding image data (no scan found)!\n");
         return GPUJPEG_ERROR;
     }
     if ( st.comp_count != 3 ) {
@@ -233,22 +254,11 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
             GJ_ERR("This build decodes 4:4:4 only (chroma subsampling is not implemented yet).\n");
             return GPUJPEG_ERROR;
         }
-        if ( !st.have_qt[st.comp_tq[c]] ) {
-            GJ_ERR("Quantization table %d is missing!\n", st.comp_tq[c]);
-            return GPUJPEG_ERROR;
-        }
-    }
-    if ( st.color_space != GPUJPEG_YCBCR_BT601_256LVLS ) {
-        GJ_ERR("This build decodes YCbCr JPEG streams only (stream is %s).\n", gpujpeg_color_space_get_name(st.color_space));
-        return GPUJPEG_ERROR;
     }
     if ( !output_format_supported(d) ) return GPUJPEG_ERROR;
-    if ( !((st.scan_count == 1 && st.scan[0].ncomp == 3) || st.scan_count == 3) ) {
-        GJ_ERR("Unsupported scan structure (%d scans).\n", st.scan_count);
-        return GPUJPEG_ERROR;
-    }
-    if ( image_size >= 0xFFFFFFFFull ) {
-        GJ_ERR("JPEG streams of 4 GiB or more are not supported.\n");
+    st.interleaved = st.scan[0].ncomp > 1;
+    if ( st.interleaved && st.scan[0].ncomp != 3 ) {
+        GJ_ERR("Unsupported scan structure (%d components in first scan).\n", st.scan[0].ncomp);
         return GPUJPEG_ERROR;
     }
 
@@ -263,7 +273,7 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
         p.sampling_factor[c].horizontal = 1;
         p.sampling_factor[c].vertical = 1;
     }
-    p.color_space_internal = st.color_space;
+    p.color_space_internal = GPUJPEG_YCBCR_BT601_256LVLS;
     struct gpujpeg_image_parameters pi;
     gpujpeg_image_set_default_parameters(&pi);
     pi.width = st.width;
@@ -278,17 +288,82 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     }
     const struct gj_geometry* g = &d->geo;
 
-    uint32_t* seg_off = d->h_seg;
-    uint32_t* seg_len = d->h_seg + g->seg_count;
-    const int nseg = gj_reader_split(image, &st, seg_off, seg_len, g->seg_count);
-    if ( nseg != g->seg_count ) {
-        GJ_ERR("JPEG stream has %d restart segments, expected %d for a %dx%d image with restart interval %d!\n", nseg,
-               g->seg_count, st.width, st.height, st.restart_interval);
+    /* ---- upload the file once, untouched; K0 builds the marker list on the device ---- */
+    const size_t ecs_begin = st.scan[0].begin;
+    const uint32_t list_cap = (uint32_t)g->seg_count + GJ_MK_OTHER_CAP;
+    const size_t n_cta = (image_size - ecs_begin + 16) / 4096 + 2;
+    if ( grow_dev((void**)&d->d_file, &d->d_file_size, image_size + 64) ||
+         grow_dev((void**)&d->d_list_pos, &d->d_list_pos_size, (size_t)list_cap * 4) ||
+         grow_dev((void**)&d->d_list_code, &d->d_list_code_size, (size_t)list_cap) ||
+         grow_dev((void**)&d->d_cta, &d->d_cta_size, n_cta * 4) ) {
+        GJ_ERR("Decoder device allocation failed: %s\n", gj_cuda_last_error());
         return GPUJPEG_ERROR;
     }
-    for ( int s = 0; s < st.scan_count; s++ ) {
-        if ( st.scan[s].segment_count != g->seg_per_scan ) {
-            GJ_ERR("Scan %d has %d restart segments, expected %d!\n", s, st.scan[s].segment_count, g->seg_per_scan);
+    if ( stats && d->timers_ok ) gj_timer_start(&d->t_to, d->stream);
+    if ( gj_cuda_memcpy_h2d_async(d->d_file, image, image_size, d->stream) ) {
+        GJ_ERR("Decoder copy of compressed data failed: %s\n", gj_cuda_last_error());
+        return GPUJPEG_ERROR;
+    }
+    if ( stats && d->timers_ok ) gj_timer_stop(&d->t_to, d->stream);
+    /* d_mk: [0] total markers, [1] non-RST markers, [2] list overflow, [3] restart structure error,
+     *       [4..7] first marker rank per scan, [8..] {rank, position, code} of the non-RST markers */
+    if ( gj_launch_marker_scan(d->d_file, ecs_begin, image_size, d->d_cta, d->d_list_pos, d->d_list_code, list_cap, d->d_mk,
+                               d->d_mk + 8, GJ_MK_OTHER_CAP, d->stream) ||
+         gj_cuda_memcpy_d2h_async(d->h_mk, d->d_mk, (8 + 3 * GJ_MK_OTHER_CAP) * 4, d->stream) ||
+         gj_cuda_stream_sync(d->stream) ) {
+        GJ_ERR("Marker scan failed: %s\n", gj_cuda_last_error());
+        return GPUJPEG_ERROR;
+    }
+
+    /* ---- host reader, part 2: scan extents from the marker list, marker segments between scans by length ---- */
+    const uint32_t n_other = d->h_mk[1];
+    if ( d->h_mk[2] || n_other == 0 || n_other > GJ_MK_OTHER_CAP ) {
+        GJ_ERR("JPEG stream has %u restart markers / %u other markers in its scan data, expected %d restart segments "
+               "for a %dx%d image with restart interval %d!\n", d->h_mk[0], n_other, g->seg_count, st.width, st.height,
+               st.restart_interval);
+        return GPUJPEG_ERROR;
+    }
+    uint32_t* other = d->h_mk + 8; /* insertion sort by position: a handful of entries */
+    for ( uint32_t i = 1; i < n_other; i++ ) {
+        uint32_t t[3] = {other[3 * i], other[3 * i + 1], other[3 * i + 2]};
+        uint32_t j = i;
+        while ( j > 0 && other[3 * (j - 1) + 1] > t[1] ) {
+            memcpy(other + 3 * j, other + 3 * (j - 1), 12);
+            j--;
+        }
+        memcpy(other + 3 * j, t, 12);
+    }
+    for ( int k = 0; k < st.scan_count; k++ ) {
+        /* a scan ends at the first marker that is not RSTn: inside entropy-coded data that test is exact */
+        size_t e1 = 0;
+        for ( uint32_t i = 0; i < n_other; i++ ) {
+            if ( other[3 * i + 1] >= st.scan[k].begin ) {
+                e1 = other[3 * i + 1];
+                break;
+            }
+        }
+        if ( e1 == 0 ) {
+            GJ_ERR("JPEG data unexpected ended while reading SOS marker!\n");
+            return GPUJPEG_ERROR;
+        }
+        st.scan[k].end = e1;
+        pos = e1;
+        const int r = gj_reader_walk(image, image_size, &pos, &st, &adobe);
+        if ( r < 0 ) return GPUJPEG_ERROR;
+        if ( r == 0 ) break; /* EOI (or end of data) */
+    }
+    if ( gj_reader_finish(&st, adobe, d->verbose) ) return GPUJPEG_ERROR;
+    if ( st.color_space != GPUJPEG_YCBCR_BT601_256LVLS ) {
+        GJ_ERR("This build decodes YCbCr JPEG streams only (stream is %s).\n", gpujpeg_color_space_get_name(st.color_space));
+        return GPUJPEG_ERROR;
+    }
+    if ( st.scan_count != g->scan_count ) {
+        GJ_ERR("Unsupported scan structure (%d scans, expected %d).\n", st.scan_count, g->scan_count);
+        return GPUJPEG_ERROR;
+    }
+    for ( int c = 0; c < 3; c++ ) {
+        if ( !st.have_qt[st.comp_tq[c]] ) {
+            GJ_ERR("Quantization table %d is missing!\n", st.comp_tq[c]);
             return GPUJPEG_ERROR;
         }
     }
@@ -301,7 +376,12 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
                 d->h_tab.qinv_zz[t][k] = st.qt[t][k];
     struct gj_huff_dec_args ha;
     memset(&ha, 0, sizeof ha);
+    uint32_t scan_begin[4] = {0, 0, 0, 0}, scan_end[4] = {0, 0, 0, 0};
     for ( int s = 0; s < st.scan_count; s++ ) {
+        if ( st.scan[s].ncomp != g->comps_per_scan ) {
+            GJ_ERR("Unsupported scan structure (scan %d has %d components).\n", s, st.scan[s].ncomp);
+            return GPUJPEG_ERROR;
+        }
         for ( int k = 0; k < st.scan[s].ncomp; k++ ) {
             const int td = st.scan[s].td[k], ta = st.scan[s].ta[k];
             if ( !st.have_huff[0][td] || !st.have_huff[1][ta] ) {
@@ -313,6 +393,9 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
             ha.scan_tq[s][k] = st.comp_tq[st.scan[s].comp[k]];
             ha.scan_ta[s][k] = ta;
         }
+        scan_begin[s] = (uint32_t)st.scan[s].begin;
+        scan_end[s] = (uint32_t)st.scan[s].end;
+        ha.scan_begin[s] = scan_begin[s];
     }
     for ( int cls = 0; cls < 2; cls++ )
         for ( int id = 0; id < 4; id++ )
@@ -322,37 +405,32 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
             }
     const double t_reader_ms = (gpujpeg_get_time() - t_begin) * 1000.0;
 
-    /* ---- upload ---- */
-    if ( grow_dev((void**)&d->d_file, &d->d_file_size, image_size + 64) ) {
-        GJ_ERR("Decoder device allocation failed: %s\n", gj_cuda_last_error());
-        return GPUJPEG_ERROR;
-    }
-    if ( stats && d->timers_ok ) gj_timer_start(&d->t_to, d->stream);
-    int rc = 0;
     if ( !d->tab_valid || memcmp(&d->h_tab, &d->h_tab_prev, sizeof d->h_tab) != 0 ) {
         /* h_tab_prev is what the in-flight copy reads from: never modified while a frame is running */
         d->h_tab_prev = d->h_tab;
-        rc |= gj_cuda_memcpy_h2d_async(d->d_tab, &d->h_tab_prev, sizeof d->h_tab, d->stream);
+        if ( gj_cuda_memcpy_h2d_async(d->d_tab, &d->h_tab_prev, sizeof d->h_tab, d->stream) ) return GPUJPEG_ERROR;
         d->tab_valid = 1;
     }
-    rc |= gj_cuda_memcpy_h2d_async(d->d_file, image, image_size, d->stream);
-    rc |= gj_cuda_memcpy_h2d_async(d->d_seg, d->h_seg, (size_t)g->seg_count * 8, d->stream);
-    if ( rc ) {
-        GJ_ERR("Decoder copy of compressed data failed: %s\n", gj_cuda_last_error());
-        return GPUJPEG_ERROR;
-    }
     if ( stats && d->timers_ok ) {
-        gj_timer_stop(&d->t_to, d->stream);
         gj_timer_start(&d->t_gpu, d->stream);
         gj_timer_start(&d->t_huff, d->stream);
+    }
+    if ( gj_launch_scan_ranks(d->d_list_pos, d->d_mk, st.scan_count, scan_begin, scan_end, g->seg_per_scan, d->d_mk + 4,
+                              d->stream) ) {
+        GJ_ERR("Scan rank launch failed: %s\n", gj_cuda_last_error());
+        return GPUJPEG_ERROR;
     }
 
     /* ---- K3 ---- */
     ha.d_file = d->d_file;
     ha.file_size = image_size;
     ha.dequantize = d->idct_flavour == 0;
-    ha.d_seg_off = d->d_seg;
-    ha.d_seg_len = d->d_seg + g->seg_count;
+    ha.d_seg_off = NULL; /* segment starts come from the device-built marker list */
+    ha.d_seg_len = NULL;
+    ha.d_list_pos = d->d_list_pos;
+    ha.d_list_code = d->d_list_code;
+    ha.d_first_rank = d->d_mk + 4;
+    ha.d_error = d->d_mk + 3;
     ha.seg_count = g->seg_count;
     ha.seg_per_scan = g->seg_per_scan;
     ha.scan_count = g->scan_count;
@@ -415,8 +493,15 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     else {
         output->data = d_out;
     }
-    if ( gj_cuda_stream_sync(d->stream) ) {
+    if ( gj_cuda_memcpy_d2h_async(d->h_mk, d->d_mk, 16, d->stream) || gj_cuda_stream_sync(d->stream) ) {
         GJ_ERR("Decoder failed: %s\n", gj_cuda_last_error());
+        return GPUJPEG_ERROR;
+    }
+    if ( d->h_mk[3] ) {
+        /* the reference tries to resynchronise on a broken restart sequence
+         * [ref: src/gpujpeg_reader.c:1071-1105]; here it is reported, not repaired */
+        GJ_ERR("JPEG stream has a broken restart-marker structure (expected %d restart segments per scan for a %dx%d "
+               "image with restart interval %d)!\n", g->seg_per_scan, st.width, st.height, st.restart_interval);
         return GPUJPEG_ERROR;
     }
     output->metadata = &d->metadata;

@@ -525,6 +525,7 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file
     const int lane = threadIdx.x & 31;
     const int g0 = (blockIdx.x * HD_THREADS + threadIdx.x) & ~31;  // first segment of this warp
     if ( g0 >= seg_count ) return;
+    if ( !seg_off && *a.d_error ) return;   // restart structure does not match the geometry: list ranks are meaningless
     const int g = g0 + lane;
     const bool live = g < seg_count;
     int scan = 0, nblocks = 0, mybase = 0;
@@ -537,7 +538,21 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file
         // block index (in units of 64 coefficients) of the segment's first MCU; for single-component
         // scans the component plane is folded in here, for interleaved scans it is added per block
         mybase = s * seg_mcu + (cps == 1 ? a.scan_comp[scan][0] * nblk : 0);
-        src_init(r, file + seg_off[g], file_end);
+        uint32_t start;
+        if ( seg_off ) {
+            start = seg_off[g];
+        }
+        else if ( s == 0 ) {
+            start = a.scan_begin[scan];
+        }
+        else {
+            const uint32_t m = a.d_first_rank[scan] + (uint32_t)s - 1u;
+            start = a.d_list_pos[m] + 2u;
+            /* restart markers must count D0..D7 cyclically [ref: src/gpujpeg_reader.c:1068-1071] */
+            if ( a.d_list_code[m] != (uint8_t)(0xD0 + ((s - 1) & 7)) ) atomicExch(a.d_error, 1u);
+        }
+        if ( start >= (uint32_t)(file_end - file) ) start = 0;   // corrupt table: stay inside the buffer
+        src_init(r, file + start, file_end);
     }
     const int max_blocks = seg_mcu * cps;
     /* private block: 16-byte chunk c of lane L lives at chunk (c ^ (L & 7)) so that the warp-wide

@@ -127,6 +127,10 @@ struct gj_stream {
     size_t header_size;
     int interleaved;
 };
+/* incremental pieces: begin, walk marker segments up to the next SOS, finish */
+void gj_reader_begin(struct gj_stream* s);
+int gj_reader_walk(const uint8_t* data, size_t size, size_t* pos, struct gj_stream* s, int* adobe_transform);
+int gj_reader_finish(struct gj_stream* s, int adobe_transform, int verbose);
 /* parse all markers; does not split scans into segments */
 int gj_reader_parse(const uint8_t* data, size_t size, struct gj_stream* s, int verbose);
 /* split scan data at RSTn markers: fills seg_off/seg_len (file offsets of stuffed entropy bytes) */
@@ -175,8 +179,15 @@ int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_stream_t strea
 struct gj_huff_dec_args {
     const uint8_t* d_file;      /* the JPEG bytes */
     size_t file_size;
-    const uint32_t* d_seg_off;  /* [seg_count] file offset of each segment's entropy bytes */
+    const uint32_t* d_seg_off;  /* host-built table: [seg_count] file offset of each segment (or NULL) */
     const uint32_t* d_seg_len;  /* informative: the decoder stops after the segment's block count */
+    /* device-built marker list (K0): segment j of scan s starts at scan_begin[s] (j = 0) or two bytes
+     * after marker number d_first_rank[s] + j - 1 */
+    const uint32_t* d_list_pos;
+    const uint8_t* d_list_code;
+    const uint32_t* d_first_rank; /* [scan_count], written by gj_launch_scan_ranks */
+    uint32_t scan_begin[GJ_MAX_COMP];
+    uint32_t* d_error;            /* set to non-zero by K3 when the RSTn sequence is broken */
     int dequantize;             /* 1: store coefficient*quantiser wrapped to int16 (integer IDCT flavour) */
     int seg_count, seg_per_scan, scan_count, comps_per_scan, seg_mcu, nblk;
     int scan_comp[GJ_MAX_COMP][GJ_MAX_COMP]; /* component index of the i-th component of scan s */
@@ -186,6 +197,15 @@ struct gj_huff_dec_args {
     const struct gj_dev_dec_tables* d_tables;
 };
 int gj_launch_huffman_decode(const struct gj_huff_dec_args* a, gj_stream_t stream);
+
+/* K0: marker list of the entropy-coded part of the file, built on the device (gj_markers.cu)
+ * [replaces ref: src/gpujpeg_reader.c:1038-1155] */
+int gj_launch_marker_scan(const uint8_t* d_file, size_t begin, size_t end, uint32_t* d_cta, uint32_t* d_list_pos,
+                          uint8_t* d_list_code, uint32_t list_cap, uint32_t* d_result, uint32_t* d_other, uint32_t other_cap,
+                          gj_stream_t stream);
+/* rank of the first marker of every scan + restart-count validation (error -> d_result[3]) */
+int gj_launch_scan_ranks(const uint32_t* d_list_pos, const uint32_t* d_result, int scan_count, const uint32_t scan_begin[4],
+                         const uint32_t scan_end[4], int seg_per_scan, uint32_t* d_first_rank, gj_stream_t stream);
 
 /* K4: zig-zag coefficients -> RGB u8 interleaved (fused dequant + IDCT + colour transform)
  * idct_flavour: 0 = integer (gpujpeg_idct_cpu), 1 = float GPU-reference
