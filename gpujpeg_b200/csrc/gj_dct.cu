@@ -78,20 +78,23 @@ k_fdct_rgb444(const uint8_t* __restrict__ raw, int width, int height, size_t pit
 
     /* phase A: colour transform, 4 pixels (12 bytes = 3 words) per step, planar float staging.
      * Pixels outside the image are 0 in every component, as in the reference whose planes are
-     * zero-initialised and only written inside the image [ref: src/gpujpeg_common.c:941-944]. */
-#pragma unroll 2
-    for ( int g = threadIdx.x; g < GROUPS; g += NT ) {
-        const int row = g >> 7, gx = g & 127;
-        const int px0 = gx * 4;
-        float4 y4 = make_float4(0.f, 0.f, 0.f, 0.f), cb4 = y4, cr4 = y4;
-        if ( row < vh && px0 < vw ) {
+     * zero-initialised and only written inside the image [ref: src/gpujpeg_common.c:941-944].
+     * All of a thread's loads are issued before the first use (18 words in flight per thread): the
+     * phase is otherwise bound by global-load latency (ncu r1_c: 33 % of stall samples). */
+    constexpr int ITERS = (GROUPS + NT - 1) / NT;   // 6
+    uint32_t w0[ITERS], w1[ITERS], w2[ITERS];
+#pragma unroll
+    for ( int it = 0; it < ITERS; it++ ) {
+        const int g = threadIdx.x + it * NT;
+        const int row = g >> 7, gx = g & 127, px0 = gx * 4;
+        w0[it] = w1[it] = w2[it] = 0u;
+        if ( g < GROUPS && row < vh && px0 < vw ) {
             const uint8_t* p = src + (size_t)row * pitch + gx * 12;
-            uint32_t w0, w1, w2;
             if ( VEC == 4 && px0 + 4 <= vw ) {
                 const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
-                w0 = __ldg(w);
-                w1 = __ldg(w + 1);
-                w2 = __ldg(w + 2);
+                w0[it] = __ldg(w);
+                w1[it] = __ldg(w + 1);
+                w2[it] = __ldg(w + 2);
             }
             else {
                 const int nb = min(12, (vw - px0) * 3);   // never read past the end of the row
@@ -99,14 +102,24 @@ k_fdct_rgb444(const uint8_t* __restrict__ raw, int width, int height, size_t pit
 #pragma unroll
                 for ( int i = 0; i < 12; i++ )
                     b[i] = i < nb ? (uint32_t)__ldg(p + i) : 0u;
-                w0 = b[0] | b[1] << 8 | b[2] << 16 | b[3] << 24;
-                w1 = b[4] | b[5] << 8 | b[6] << 16 | b[7] << 24;
-                w2 = b[8] | b[9] << 8 | b[10] << 16 | b[11] << 24;
+                w0[it] = b[0] | b[1] << 8 | b[2] << 16 | b[3] << 24;
+                w1[it] = b[4] | b[5] << 8 | b[6] << 16 | b[7] << 24;
+                w2[it] = b[8] | b[9] << 8 | b[10] << 16 | b[11] << 24;
             }
-            gj_rgb_to_ycbcr_m(gj_byte_as_magic(w0, 0), gj_byte_as_magic(w0, 1), gj_byte_as_magic(w0, 2), y4.x, cb4.x, cr4.x);
-            gj_rgb_to_ycbcr_m(gj_byte_as_magic(w0, 3), gj_byte_as_magic(w1, 0), gj_byte_as_magic(w1, 1), y4.y, cb4.y, cr4.y);
-            gj_rgb_to_ycbcr_m(gj_byte_as_magic(w1, 2), gj_byte_as_magic(w1, 3), gj_byte_as_magic(w2, 0), y4.z, cb4.z, cr4.z);
-            gj_rgb_to_ycbcr_m(gj_byte_as_magic(w2, 1), gj_byte_as_magic(w2, 2), gj_byte_as_magic(w2, 3), y4.w, cb4.w, cr4.w);
+        }
+    }
+#pragma unroll
+    for ( int it = 0; it < ITERS; it++ ) {
+        const int g = threadIdx.x + it * NT;
+        if ( g >= GROUPS ) break;
+        const int row = g >> 7, gx = g & 127, px0 = gx * 4;
+        float4 y4 = make_float4(0.f, 0.f, 0.f, 0.f), cb4 = y4, cr4 = y4;
+        if ( row < vh && px0 < vw ) {
+            const uint32_t a0 = w0[it], a1 = w1[it], a2 = w2[it];
+            gj_rgb_to_ycbcr_m(gj_byte_as_magic(a0, 0), gj_byte_as_magic(a0, 1), gj_byte_as_magic(a0, 2), y4.x, cb4.x, cr4.x);
+            gj_rgb_to_ycbcr_m(gj_byte_as_magic(a0, 3), gj_byte_as_magic(a1, 0), gj_byte_as_magic(a1, 1), y4.y, cb4.y, cr4.y);
+            gj_rgb_to_ycbcr_m(gj_byte_as_magic(a1, 2), gj_byte_as_magic(a1, 3), gj_byte_as_magic(a2, 0), y4.z, cb4.z, cr4.z);
+            gj_rgb_to_ycbcr_m(gj_byte_as_magic(a2, 1), gj_byte_as_magic(a2, 2), gj_byte_as_magic(a2, 3), y4.w, cb4.w, cr4.w);
             if ( px0 + 4 > vw ) {  // the image ends inside this group
                 if ( px0 + 1 >= vw ) { y4.y = cb4.y = cr4.y = 0.f; }
                 if ( px0 + 2 >= vw ) { y4.z = cb4.z = cr4.z = 0.f; }

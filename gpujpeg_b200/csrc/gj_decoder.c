@@ -437,6 +437,7 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     ha.comps_per_scan = g->comps_per_scan;
     ha.seg_mcu = g->seg_mcu;
     ha.nblk = g->nblk;
+    ha.comp_count = g->comp_count;
     ha.d_coef = d->d_coef;
     ha.d_tables = d->d_tab;
     d->last_args = ha;

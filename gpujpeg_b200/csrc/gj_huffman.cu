@@ -412,14 +412,14 @@ struct DecTabs {
 };
 
 /* Bit source of one lane.  The segment's bytes are pulled as aligned 32-bit words, one word ahead of
- * use so the load latency hides behind the decoding of the previous word; byte stuffing (FF 00) is
- * removed word-wise on the fast path (no 0xFF in the word) and byte-wise otherwise. */
+ * use; byte stuffing (FF 00) is removed word-wise on the fast path (no 0xFF in the word) and byte-wise
+ * otherwise.  The 64-bit bit buffer is LEFT-aligned: peeking is a plain shift of its upper word. */
 struct BitSource {
     const uint32_t* wp;   // next word to fetch
     const uint32_t* wend; // first word that must not be read
-    uint32_t nextw;       // word already loaded from wp[-1]... see src_init
-    uint64_t acc;         // bit buffer, newest bits at the bottom
-    int n;                // valid bits in acc
+    uint32_t nextw;       // word fetched ahead
+    uint64_t acc;         // valid bits at the top, zeros below
+    int n;                // number of valid bits
     bool skip_zero;       // previous byte was 0xFF: a following 0x00 is stuffing
 };
 
@@ -440,7 +440,7 @@ __device__ __forceinline__ void src_bytes(BitSource& r, uint32_t w, int first)
             r.skip_zero = false;
             if ( b == 0 ) continue;
         }
-        r.acc = (r.acc << 8) | b;
+        r.acc |= (uint64_t)b << (56 - r.n);
         r.n += 8;
         r.skip_zero = b == 0xFFu;
     }
@@ -457,14 +457,14 @@ __device__ __forceinline__ void src_init(BitSource& r, const uint8_t* p, const u
     r.wp++;
     src_bytes(r, src_load(r), (int)(a & 3));   // the segment may start inside a word
 }
-/* make at least 33 bits available (a Huffman code + its value bits need at most 16 + 15) */
+/* make at least 32 bits available (a Huffman code + its value bits need at most 16 + 15) */
 __device__ __forceinline__ void src_fill(BitSource& r)
 {
-    while ( r.n <= 32 ) {   // one word is enough unless it held stuffed bytes
+    while ( r.n < 32 ) {   // one word is enough unless it held stuffed bytes
         const uint32_t w = src_load(r);
         const uint32_t ff = ((w & 0x7F7F7F7Fu) + 0x01010101u) & w & 0x80808080u;   // != 0 iff some byte is 0xFF
         if ( ff == 0 && !r.skip_zero ) {
-            r.acc = (r.acc << 32) | __byte_perm(w, 0, 0x0123);
+            r.acc |= (uint64_t)__byte_perm(w, 0, 0x0123) << (32 - r.n);
             r.n += 32;
         }
         else {
@@ -472,34 +472,16 @@ __device__ __forceinline__ void src_fill(BitSource& r)
         }
     }
 }
-__device__ __forceinline__ uint32_t src_peek16(const BitSource& r) { return (uint32_t)(r.acc >> (r.n - 16)) & 0xFFFFu; }
-__device__ __forceinline__ uint32_t src_get(BitSource& r, int len)
-{
-    r.n -= len;
-    return (uint32_t)(r.acc >> r.n) & ((1u << len) - 1u);
-}
-
-__device__ __forceinline__ int decode_symbol(BitSource& r, const gj_dec_lut& t)
-{
-    const uint32_t peek = src_peek16(r);
-    const uint32_t e = t.look[peek >> (16 - GJ_DEC_LOOK_BITS)];
-    if ( e & 15u ) {
-        r.n -= (int)(e & 15u);
-        return (int)(e >> 4);
-    }
-    int l = GJ_DEC_LOOK_BITS + 1;
-    while ( l <= 16 && peek >= t.maxcode[l] ) l++;
-    if ( l > 16 ) {  // garbage: consume and return 0 like [ref: src/gpujpeg_huffman_cpu_decoder.c:155-159]
-        r.n -= 16;
-        return 0;
-    }
-    r.n -= l;
-    return t.vals[((int)(peek >> (16 - l)) + t.valoff[l]) & 255];
-}
 
 /* DEQ: store coefficient * quantiser wrapped to int16 -- exactly what the reference's integer IDCT
  * starts from (src/gpujpeg_dct_cpu.c:180-182) -- so the multiply is paid per NON-ZERO coefficient here
- * instead of 64 times per block in K4.  DEQ = false keeps raw quantised values (float IDCT flavour). */
+ * instead of 64 times per block in K4.  DEQ = false keeps raw quantised values (float IDCT flavour).
+ *
+ * One thread decodes one restart segment.  The loop below handles ONE SYMBOL per iteration, DC and AC
+ * alike (table, predictor and target index are selected, not branched on), so the 32 lanes of a warp
+ * run through their segments independently: a lane that meets an early end-of-block simply starts its
+ * next block while the others are still inside theirs.  Coefficients go straight to global memory with
+ * 2-byte stores; the coefficient buffer is zeroed beforehand (launcher), so zeros are never touched. */
 template <bool DEQ>
 __global__ void __launch_bounds__(HD_THREADS)
 k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file_end, const uint32_t* __restrict__ seg_off,
@@ -508,8 +490,6 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file
 {
     __shared__ DecTabs s_tab;
     __shared__ uint16_t s_q[4][64];
-    __shared__ __align__(16) uint32_t s_blk[HD_THREADS * 32];   // one private 8x8 block (128 B) per thread
-
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(&tables->lut[0][0]);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
@@ -517,101 +497,95 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file
             dst[i] = src[i];
         for ( int i = threadIdx.x; i < 256; i += HD_THREADS )
             s_q[i >> 6][i & 63] = tables->qinv_zz[i >> 6][i & 63];
-        for ( int i = threadIdx.x; i < HD_THREADS * 32; i += HD_THREADS )
-            s_blk[i] = 0;
     }
     __syncthreads();
 
-    const int lane = threadIdx.x & 31;
-    const int g0 = (blockIdx.x * HD_THREADS + threadIdx.x) & ~31;  // first segment of this warp
-    if ( g0 >= seg_count ) return;
+    const int g = blockIdx.x * HD_THREADS + threadIdx.x;
+    if ( g >= seg_count ) return;
     if ( !seg_off && *a.d_error ) return;   // restart structure does not match the geometry: list ranks are meaningless
-    const int g = g0 + lane;
-    const bool live = g < seg_count;
-    int scan = 0, nblocks = 0, mybase = 0;
-    BitSource r;
-    r.n = 0;
-    if ( live ) {
-        scan = g / seg_per_scan;
-        const int s = g - scan * seg_per_scan;
-        nblocks = min(seg_mcu, nblk - s * seg_mcu) * cps;
-        // block index (in units of 64 coefficients) of the segment's first MCU; for single-component
-        // scans the component plane is folded in here, for interleaved scans it is added per block
-        mybase = s * seg_mcu + (cps == 1 ? a.scan_comp[scan][0] * nblk : 0);
-        uint32_t start;
-        if ( seg_off ) {
-            start = seg_off[g];
-        }
-        else if ( s == 0 ) {
-            start = a.scan_begin[scan];
-        }
-        else {
-            const uint32_t m = a.d_first_rank[scan] + (uint32_t)s - 1u;
-            start = a.d_list_pos[m] + 2u;
-            /* restart markers must count D0..D7 cyclically [ref: src/gpujpeg_reader.c:1068-1071] */
-            if ( a.d_list_code[m] != (uint8_t)(0xD0 + ((s - 1) & 7)) ) atomicExch(a.d_error, 1u);
-        }
-        if ( start >= (uint32_t)(file_end - file) ) start = 0;   // corrupt table: stay inside the buffer
-        src_init(r, file + start, file_end);
-    }
-    const int max_blocks = seg_mcu * cps;
-    /* private block: 16-byte chunk c of lane L lives at chunk (c ^ (L & 7)) so that the warp-wide
-     * 16-byte reads of the flush below are bank-conflict free */
-    const int sw = lane & 7;
-    int16_t* mine = reinterpret_cast<int16_t*>(s_blk + threadIdx.x * 32);
-    uint4* wbase = reinterpret_cast<uint4*>(s_blk + (threadIdx.x & ~31) * 32);
-    int pred[GJ_MAX_COMP] = {0, 0, 0, 0};
+    const int scan = g / seg_per_scan;
+    const int s = g - scan * seg_per_scan;
+    const int first_mcu = s * seg_mcu;
+    const int nblocks = min(seg_mcu, nblk - first_mcu) * cps;
 
-    for ( int b = 0; b < max_blocks; b++ ) {
-        int mcu = b, ci = 0;
-        if ( cps != 1 ) { mcu = b / cps; ci = b - mcu * cps; }
-        if ( live && b < nblocks ) {
-            const gj_dec_lut& tdc = s_tab.t[0][a.scan_td[scan][ci]];
-            const gj_dec_lut& tac = s_tab.t[1][a.scan_ta[scan][ci]];
-            const uint16_t* q = s_q[a.scan_tq[scan][ci]];
-            src_fill(r);
-            int sz = decode_symbol(r, tdc) & 15;
-            int diff = 0;
-            if ( sz ) diff = gj_extend((int)src_get(r, sz), sz);
-            /* per-component predictor, reset at segment start [ref: src/gpujpeg_huffman_cpu_decoder.c:407-411] */
-            int pr;
-            if ( ci == 0 ) pr = (pred[0] += diff);
-            else if ( ci == 1 ) pr = (pred[1] += diff);
-            else if ( ci == 2 ) pr = (pred[2] += diff);
-            else pr = (pred[3] += diff);
-            mine[(0 ^ sw) << 3] = (int16_t)(DEQ ? pr * (int)q[0] : pr);
-            for ( int k = 1; k < 64; ) {
-                src_fill(r);
-                const int rs = decode_symbol(r, tac);
-                const int run = rs >> 4;
-                sz = rs & 15;
-                if ( sz ) {
-                    k += run;
-                    const int v = gj_extend((int)src_get(r, sz), sz);
-                    if ( k < 64 ) mine[(((k >> 3) ^ sw) << 3) | (k & 7)] = (int16_t)(DEQ ? v * (int)q[k] : v);
-                    k++;
-                }
-                else {
-                    if ( run != 15 ) break;  // EOB
-                    k += 16;                 // ZRL
-                }
+    uint32_t start;
+    if ( seg_off ) {
+        start = seg_off[g];
+    }
+    else if ( s == 0 ) {
+        start = a.scan_begin[scan];
+    }
+    else {
+        const uint32_t m = a.d_first_rank[scan] + (uint32_t)s - 1u;
+        start = a.d_list_pos[m] + 2u;
+        /* restart markers must count D0..D7 cyclically [ref: src/gpujpeg_reader.c:1068-1071] */
+        if ( a.d_list_code[m] != (uint8_t)(0xD0 + ((s - 1) & 7)) ) atomicExch(a.d_error, 1u);
+    }
+    if ( start >= (uint32_t)(file_end - file) ) start = 0;   // corrupt table: stay inside the buffer
+    BitSource r;
+    src_init(r, file + start, file_end);
+
+    int ci = 0, mcu = 0;       // position inside the segment: component index within the MCU, MCU index
+    int b = 0, k = 0;          // block counter, zig-zag index of the next coefficient (0 = DC comes next)
+    int pred0 = 0, pred1 = 0, pred2 = 0, pred3 = 0;
+    const gj_dec_lut* tdc = &s_tab.t[0][a.scan_td[scan][0]];
+    const gj_dec_lut* tac = &s_tab.t[1][a.scan_ta[scan][0]];
+    const uint16_t* q = s_q[a.scan_tq[scan][0]];
+    int16_t* dst = coef + ((size_t)a.scan_comp[scan][0] * nblk + first_mcu) * 64;
+
+    while ( b < nblocks ) {
+        src_fill(r);
+        const bool isdc = k == 0;
+        const gj_dec_lut* t = isdc ? tdc : tac;
+        const uint32_t hi = (uint32_t)(r.acc >> 32);
+        const uint32_t peek = hi >> 16;
+        uint32_t e = t->look[peek >> (16 - GJ_DEC_LOOK_BITS)];
+        int len = (int)(e & 15u), sym = (int)(e >> 4);
+        if ( len == 0 ) {   // code longer than the lookahead: canonical search (rare)
+            len = GJ_DEC_LOOK_BITS + 1;
+            while ( len <= 16 && peek >= t->maxcode[len] ) len++;
+            if ( len > 16 ) {   // garbage: consume and decode as 0 [ref: src/gpujpeg_huffman_cpu_decoder.c:155-159]
+                len = 16;
+                sym = 0;
+            }
+            else {
+                sym = t->vals[((int)(peek >> (16 - len)) + t->valoff[len]) & 255];
             }
         }
-        __syncwarp();
-        /* write the warp's 32 private blocks out as 128-byte lines, four blocks per step, and clear them */
-        const int extra = (cps == 1 ? 0 : a.scan_comp[0][ci] * nblk) + mcu;
-#pragma unroll
-        for ( int j = 0; j < 8; j++ ) {
-            const int i = 4 * j + (lane >> 3);   // owner lane of the block this lane helps to move
-            const int c = lane & 7;              // its 16-byte chunk
-            const int ob = __shfl_sync(FULL, mybase, i);
-            const int on = __shfl_sync(FULL, nblocks, i);
-            uint4* src = wbase + i * 8 + (c ^ (i & 7));
-            const uint4 v = *src;
-            *src = make_uint4(0u, 0u, 0u, 0u);
-            if ( b < on ) reinterpret_cast<uint4*>(coef + (size_t)(ob + extra) * 64)[c] = v;
+        const int sz = sym & 15;
+        const int run = isdc ? 0 : sym >> 4;
+        /* the sz value bits follow the code; gj_extend() turns them into the signed coefficient */
+        int v = 0;
+        if ( sz ) v = gj_extend((int)((hi << len) >> (32 - sz)), sz);
+        r.acc <<= len + sz;
+        r.n -= len + sz;
+        if ( isdc ) {
+            /* per-component predictor, reset at segment start [ref: src/gpujpeg_huffman_cpu_decoder.c:407-411] */
+            if ( ci == 0 ) v = (pred0 += v);
+            else if ( ci == 1 ) v = (pred1 += v);
+            else if ( ci == 2 ) v = (pred2 += v);
+            else v = (pred3 += v);
         }
-        __syncwarp();
+        const int kk = k + run;
+        if ( (isdc || sz) && kk < 64 ) dst[kk] = (int16_t)(DEQ ? v * (int)q[kk] : v);
+        k = (!isdc && sz == 0 && run != 15) ? 64 : kk + 1;   // EOB ends the block, ZRL skips 16
+        if ( k >= 64 ) {   // next block
+            k = 0;
+            b++;
+            if ( cps == 1 ) {
+                dst += 64;
+            }
+            else {
+                if ( ++ci == cps ) {
+                    ci = 0;
+                    mcu++;
+                }
+                tdc = &s_tab.t[0][a.scan_td[scan][ci]];
+                tac = &s_tab.t[1][a.scan_ta[scan][ci]];
+                q = s_q[a.scan_tq[scan][ci]];
+                dst = coef + ((size_t)a.scan_comp[scan][ci] * nblk + first_mcu + mcu) * 64;
+            }
+        }
     }
 }
 
@@ -647,6 +621,9 @@ extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_str
 extern "C" int gj_launch_huffman_decode(const struct gj_huff_dec_args* a, gj_stream_t stream)
 {
     const dim3 grid((a->seg_count + HD_THREADS - 1) / HD_THREADS);
+    /* K3 only writes non-zero coefficients: start from an all-zero buffer (the reference does the same,
+     * src/gpujpeg_decoder.c:301) */
+    if ( cudaMemsetAsync(a->d_coef, 0, (size_t)a->comp_count * a->nblk * 64 * sizeof(int16_t), stream) != cudaSuccess ) return -1;
     if ( a->dequantize )
         k_huff_decode<true><<<grid, HD_THREADS, 0, stream>>>(a->d_file, a->d_file + a->file_size, a->d_seg_off, a->seg_count,
                                                              a->seg_per_scan, a->comps_per_scan, a->seg_mcu, a->nblk, *a,

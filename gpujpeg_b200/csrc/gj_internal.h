@@ -189,7 +189,7 @@ struct gj_huff_dec_args {
     uint32_t scan_begin[GJ_MAX_COMP];
     uint32_t* d_error;            /* set to non-zero by K3 when the RSTn sequence is broken */
     int dequantize;             /* 1: store coefficient*quantiser wrapped to int16 (integer IDCT flavour) */
-    int seg_count, seg_per_scan, scan_count, comps_per_scan, seg_mcu, nblk;
+    int seg_count, seg_per_scan, scan_count, comps_per_scan, seg_mcu, nblk, comp_count;
     int scan_comp[GJ_MAX_COMP][GJ_MAX_COMP]; /* component index of the i-th component of scan s */
     int scan_td[GJ_MAX_COMP][GJ_MAX_COMP], scan_ta[GJ_MAX_COMP][GJ_MAX_COMP];
     int scan_tq[GJ_MAX_COMP][GJ_MAX_COMP]; /* quantisation table id of that component */
