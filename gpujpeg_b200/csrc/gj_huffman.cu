@@ -406,47 +406,28 @@ k_huff_compact(const uint8_t* __restrict__ tmp, size_t slot_stride, const uint32
 /* decoder                                                                                       */
 
 constexpr int HD_THREADS = 128;
-constexpr int HD_RING = 4;   // 16-byte chunks of compressed data in flight per lane (cp.async ring)
 
 struct DecTabs {
     gj_dec_lut t[2][4];
 };
 
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-/* Bit source of one lane.  The segment's bytes stream through a private ring of HD_RING 16-byte chunks
- * in shared memory filled by cp.async (LDGSTS): the global-memory latency of the compressed data is
- * paid 48..64 bytes ahead of use and never sits on the decoder's dependency chain (with plain loads it
- * was the largest stall, ncu r1_a/r1_c).  Byte stuffing (FF 00) is removed word-wise on the fast path
- * (no 0xFF in the word) and byte-wise otherwise.  The 64-bit bit buffer is LEFT-aligned: peeking is a
- * shift of its upper word, consuming is one 64-bit shift. */
+/* Bit source of one lane.  The segment's bytes are pulled as aligned 32-bit words, one word ahead of
+ * use so the load latency hides behind the decoding of the previous word; byte stuffing (FF 00) is
+ * removed word-wise on the fast path (no 0xFF in the word) and byte-wise otherwise. */
 struct BitSource {
-    uint32_t ring;         // shared-space address of this lane's ring
-    const uint8_t* gnext;  // next 16-byte chunk to request
-    const uint8_t* gend;   // end of the readable buffer (16-byte aligned)
-    uint32_t widx;         // index of the next word to take from the ring
-    uint64_t acc;          // valid bits at the top, zeros below
-    int n;                 // number of valid bits
-    bool skip_zero;        // previous byte was 0xFF: a following 0x00 is stuffing
+    const uint32_t* wp;   // next word to fetch
+    const uint32_t* wend; // first word that must not be read
+    uint32_t nextw;       // word already loaded from wp[-1]... see src_init
+    uint64_t acc;         // bit buffer, newest bits at the bottom
+    int n;                // valid bits in acc
+    bool skip_zero;       // previous byte was 0xFF: a following 0x00 is stuffing
 };
 
-__device__ __forceinline__ uint32_t src_word(BitSource& r)
+__device__ __forceinline__ uint32_t src_load(BitSource& r)
 {
-    if ( (r.widx & 3u) == 0 ) cp_async_wait<HD_RING - 1>();   // entering a chunk: the oldest request has landed
-    uint32_t w;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(r.ring + ((r.widx & (4u * HD_RING - 1u)) << 2)) : "memory");
-    r.widx++;
-    if ( (r.widx & 3u) == 0 ) {   // left a chunk: its slot takes the next request
-        if ( r.gnext < r.gend ) cp_async16(r.ring + (((r.widx - 4u) & (4u * HD_RING - 1u)) << 2), r.gnext);
-        cp_async_commit();
-        r.gnext += 16;
-    }
+    const uint32_t w = r.nextw;
+    r.nextw = r.wp < r.wend ? __ldg(r.wp) : 0u;
+    r.wp++;
     return w;
 }
 __device__ __forceinline__ void src_bytes(BitSource& r, uint32_t w, int first)
@@ -459,38 +440,31 @@ __device__ __forceinline__ void src_bytes(BitSource& r, uint32_t w, int first)
             r.skip_zero = false;
             if ( b == 0 ) continue;
         }
-        r.acc |= (uint64_t)b << (56 - r.n);
+        r.acc = (r.acc << 8) | b;
         r.n += 8;
         r.skip_zero = b == 0xFFu;
     }
 }
-__device__ __forceinline__ void src_init(BitSource& r, uint32_t ring, const uint8_t* p, const uint8_t* buf_end)
+__device__ __forceinline__ void src_init(BitSource& r, const uint8_t* p, const uint8_t* file_end)
 {
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const uint8_t* g0 = reinterpret_cast<const uint8_t*>(a & ~static_cast<uintptr_t>(15));
-    r.ring = ring;
-    r.gend = buf_end;
-#pragma unroll
-    for ( int c = 0; c < HD_RING; c++ ) {
-        if ( g0 + 16 * c < buf_end ) cp_async16(ring + 16 * c, g0 + 16 * c);
-        cp_async_commit();
-    }
-    r.gnext = g0 + 16 * HD_RING;
-    r.widx = (uint32_t)(a & 15) >> 2;
+    r.wp = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
+    r.wend = reinterpret_cast<const uint32_t*>((reinterpret_cast<uintptr_t>(file_end) + 3) & ~static_cast<uintptr_t>(3));
     r.acc = 0;
     r.n = 0;
     r.skip_zero = false;
-    cp_async_wait<HD_RING - 1>();
-    src_bytes(r, src_word(r), (int)(a & 3));   // the segment may start inside a word
+    r.nextw = r.wp < r.wend ? __ldg(r.wp) : 0u;
+    r.wp++;
+    src_bytes(r, src_load(r), (int)(a & 3));   // the segment may start inside a word
 }
-/* make at least 32 bits available (a Huffman code + its value bits need at most 16 + 15) */
+/* make at least 33 bits available (a Huffman code + its value bits need at most 16 + 15) */
 __device__ __forceinline__ void src_fill(BitSource& r)
 {
-    while ( r.n < 32 ) {   // one word is enough unless it held stuffed bytes
-        const uint32_t w = src_word(r);
+    while ( r.n <= 32 ) {   // one word is enough unless it held stuffed bytes
+        const uint32_t w = src_load(r);
         const uint32_t ff = ((w & 0x7F7F7F7Fu) + 0x01010101u) & w & 0x80808080u;   // != 0 iff some byte is 0xFF
         if ( ff == 0 && !r.skip_zero ) {
-            r.acc |= (uint64_t)__byte_perm(w, 0, 0x0123) << (32 - r.n);
+            r.acc = (r.acc << 32) | __byte_perm(w, 0, 0x0123);
             r.n += 32;
         }
         else {
@@ -498,31 +472,29 @@ __device__ __forceinline__ void src_fill(BitSource& r)
         }
     }
 }
-
-/* one Huffman symbol + its value bits; returns the symbol, v = the signed value (0 if the size is 0) */
-__device__ __forceinline__ int decode_symbol(BitSource& r, const gj_dec_lut& t, int& v)
+__device__ __forceinline__ uint32_t src_peek16(const BitSource& r) { return (uint32_t)(r.acc >> (r.n - 16)) & 0xFFFFu; }
+__device__ __forceinline__ uint32_t src_get(BitSource& r, int len)
 {
-    src_fill(r);
-    const uint32_t hi = (uint32_t)(r.acc >> 32);
-    const uint32_t peek = hi >> 16;
-    uint32_t e = t.look[peek >> (16 - GJ_DEC_LOOK_BITS)];
-    if ( (e & 255u) == 0 ) {   // longer than the first level
-        const uint32_t pre = peek >> 7;
-        if ( t.l2_ok && pre >= t.l2_base ) e = t.look2[(pre - t.l2_base) * 128u + (peek & 127u)];
-        if ( (e & 255u) == 0 ) {   // table too wide for the second level, or garbage: canonical search
-            int l = GJ_DEC_LOOK_BITS + 1;
-            while ( l <= 16 && peek >= t.maxcode[l] ) l++;
-            /* garbage decodes as symbol 0 [ref: src/gpujpeg_huffman_cpu_decoder.c:155-159] */
-            e = l > 16 ? 16u : ((uint32_t)t.vals[((int)(peek >> (16 - l)) + t.valoff[l]) & 255] << 8) | (uint32_t)l;
-        }
+    r.n -= len;
+    return (uint32_t)(r.acc >> r.n) & ((1u << len) - 1u);
+}
+
+__device__ __forceinline__ int decode_symbol(BitSource& r, const gj_dec_lut& t)
+{
+    const uint32_t peek = src_peek16(r);
+    const uint32_t e = t.look[peek >> (16 - GJ_DEC_LOOK_BITS)];
+    if ( e & 15u ) {
+        r.n -= (int)(e & 15u);
+        return (int)(e >> 4);
     }
-    const int len = (int)(e & 255u), sym = (int)(e >> 8);
-    const int sz = sym & 15;
-    v = 0;
-    if ( sz ) v = gj_extend((int)((hi << len) >> (32 - sz)), sz);
-    r.acc <<= len + sz;
-    r.n -= len + sz;
-    return sym;
+    int l = GJ_DEC_LOOK_BITS + 1;
+    while ( l <= 16 && peek >= t.maxcode[l] ) l++;
+    if ( l > 16 ) {  // garbage: consume and return 0 like [ref: src/gpujpeg_huffman_cpu_decoder.c:155-159]
+        r.n -= 16;
+        return 0;
+    }
+    r.n -= l;
+    return t.vals[((int)(peek >> (16 - l)) + t.valoff[l]) & 255];
 }
 
 /* DEQ: store coefficient * quantiser wrapped to int16 -- exactly what the reference's integer IDCT
@@ -530,16 +502,14 @@ __device__ __forceinline__ int decode_symbol(BitSource& r, const gj_dec_lut& t, 
  * instead of 64 times per block in K4.  DEQ = false keeps raw quantised values (float IDCT flavour). */
 template <bool DEQ>
 __global__ void __launch_bounds__(HD_THREADS)
-k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ buf_end, uint32_t file_size,
-              const uint32_t* __restrict__ seg_off, int seg_count, int seg_per_scan, int cps, int seg_mcu, int nblk,
-              const __grid_constant__ gj_huff_dec_args a, int16_t* __restrict__ coef,
-              const gj_dev_dec_tables* __restrict__ tables)
+k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file_end, const uint32_t* __restrict__ seg_off,
+              int seg_count, int seg_per_scan, int cps, int seg_mcu, int nblk, const __grid_constant__ gj_huff_dec_args a,
+              int16_t* __restrict__ coef, const gj_dev_dec_tables* __restrict__ tables)
 {
-    extern __shared__ __align__(16) uint8_t hd_smem[];
-    DecTabs& s_tab = *reinterpret_cast<DecTabs*>(hd_smem);
-    uint16_t (*s_q)[64] = reinterpret_cast<uint16_t (*)[64]>(hd_smem + sizeof(DecTabs));
-    uint32_t* s_blk = reinterpret_cast<uint32_t*>(hd_smem + sizeof(DecTabs) + 512);          // one private 8x8 block per thread
-    uint8_t* s_ring = hd_smem + sizeof(DecTabs) + 512 + HD_THREADS * 128;                    // HD_RING x 16 B per thread
+    __shared__ DecTabs s_tab;
+    __shared__ uint16_t s_q[4][64];
+    __shared__ __align__(16) uint32_t s_blk[HD_THREADS * 32];   // one private 8x8 block (128 B) per thread
+
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(&tables->lut[0][0]);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
@@ -581,8 +551,8 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ buf_
             /* restart markers must count D0..D7 cyclically [ref: src/gpujpeg_reader.c:1068-1071] */
             if ( a.d_list_code[m] != (uint8_t)(0xD0 + ((s - 1) & 7)) ) atomicExch(a.d_error, 1u);
         }
-        if ( start >= file_size ) start = 0;   // corrupt table: stay inside the buffer
-        src_init(r, (uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x * (16 * HD_RING)), file + start, buf_end);
+        if ( start >= (uint32_t)(file_end - file) ) start = 0;   // corrupt table: stay inside the buffer
+        src_init(r, file + start, file_end);
     }
     const int max_blocks = seg_mcu * cps;
     /* private block: 16-byte chunk c of lane L lives at chunk (c ^ (L & 7)) so that the warp-wide
@@ -591,12 +561,6 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ buf_
     int16_t* mine = reinterpret_cast<int16_t*>(s_blk + threadIdx.x * 32);
     uint4* wbase = reinterpret_cast<uint4*>(s_blk + (threadIdx.x & ~31) * 32);
     int pred[GJ_MAX_COMP] = {0, 0, 0, 0};
-    /* when the whole warp lies inside one scan the owners' base/length follow from lane 0's by
-     * arithmetic; only a warp straddling two scans needs shuffles in the flush */
-    const int gl = min(g0 + 31, seg_count - 1);
-    const bool one_scan = g0 / seg_per_scan == gl / seg_per_scan;
-    const int base0 = __shfl_sync(FULL, mybase, 0);
-    const int s0 = g0 % seg_per_scan;
 
     for ( int b = 0; b < max_blocks; b++ ) {
         int mcu = b, ci = 0;
@@ -605,25 +569,31 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ buf_
             const gj_dec_lut& tdc = s_tab.t[0][a.scan_td[scan][ci]];
             const gj_dec_lut& tac = s_tab.t[1][a.scan_ta[scan][ci]];
             const uint16_t* q = s_q[a.scan_tq[scan][ci]];
-            int v;
-            decode_symbol(r, tdc, v);
+            src_fill(r);
+            int sz = decode_symbol(r, tdc) & 15;
+            int diff = 0;
+            if ( sz ) diff = gj_extend((int)src_get(r, sz), sz);
             /* per-component predictor, reset at segment start [ref: src/gpujpeg_huffman_cpu_decoder.c:407-411] */
             int pr;
-            if ( ci == 0 ) pr = (pred[0] += v);
-            else if ( ci == 1 ) pr = (pred[1] += v);
-            else if ( ci == 2 ) pr = (pred[2] += v);
-            else pr = (pred[3] += v);
+            if ( ci == 0 ) pr = (pred[0] += diff);
+            else if ( ci == 1 ) pr = (pred[1] += diff);
+            else if ( ci == 2 ) pr = (pred[2] += diff);
+            else pr = (pred[3] += diff);
             mine[(0 ^ sw) << 3] = (int16_t)(DEQ ? pr * (int)q[0] : pr);
             for ( int k = 1; k < 64; ) {
-                const int rs = decode_symbol(r, tac, v);
-                if ( rs & 15 ) {
-                    k += rs >> 4;
+                src_fill(r);
+                const int rs = decode_symbol(r, tac);
+                const int run = rs >> 4;
+                sz = rs & 15;
+                if ( sz ) {
+                    k += run;
+                    const int v = gj_extend((int)src_get(r, sz), sz);
                     if ( k < 64 ) mine[(((k >> 3) ^ sw) << 3) | (k & 7)] = (int16_t)(DEQ ? v * (int)q[k] : v);
                     k++;
                 }
                 else {
-                    if ( rs != 0xF0 ) break;  // EOB (any run other than 15 with size 0 ends the block)
-                    k += 16;                  // ZRL
+                    if ( run != 15 ) break;  // EOB
+                    k += 16;                 // ZRL
                 }
             }
         }
@@ -634,26 +604,16 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ buf_
         for ( int j = 0; j < 8; j++ ) {
             const int i = 4 * j + (lane >> 3);   // owner lane of the block this lane helps to move
             const int c = lane & 7;              // its 16-byte chunk
-            int ob, on;
-            if ( one_scan ) {
-                ob = base0 + i * seg_mcu;
-                on = g0 + i < seg_count ? min(seg_mcu, nblk - (s0 + i) * seg_mcu) * cps : 0;
-            }
-            else {
-                ob = __shfl_sync(FULL, mybase, i);
-                on = __shfl_sync(FULL, nblocks, i);
-            }
+            const int ob = __shfl_sync(FULL, mybase, i);
+            const int on = __shfl_sync(FULL, nblocks, i);
             uint4* src = wbase + i * 8 + (c ^ (i & 7));
-            const uint4 val = *src;
+            const uint4 v = *src;
             *src = make_uint4(0u, 0u, 0u, 0u);
-            if ( b < on ) reinterpret_cast<uint4*>(coef + (size_t)(ob + extra) * 64)[c] = val;
+            if ( b < on ) reinterpret_cast<uint4*>(coef + (size_t)(ob + extra) * 64)[c] = v;
         }
         __syncwarp();
     }
-    cp_async_wait<0>();   // do not leave requests in flight when the CTA's shared memory is released
 }
-
-constexpr int HD_SMEM = (int)sizeof(DecTabs) + 512 + HD_THREADS * 128 + HD_THREADS * 16 * HD_RING;
 
 /* zig-zag device coefficients -> natural order (debug / parity-test path only) */
 __constant__ uint8_t c_zz2nat[64] = {
@@ -687,25 +647,14 @@ extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_str
 extern "C" int gj_launch_huffman_decode(const struct gj_huff_dec_args* a, gj_stream_t stream)
 {
     const dim3 grid((a->seg_count + HD_THREADS - 1) / HD_THREADS);
-    static bool attr_done[64] = {false};
-    int dev = 0;
-    if ( cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 ) return -1;
-    if ( !attr_done[dev] ) {
-        if ( cudaFuncSetAttribute(k_huff_decode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HD_SMEM) != cudaSuccess ||
-             cudaFuncSetAttribute(k_huff_decode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HD_SMEM) != cudaSuccess )
-            return -1;
-        attr_done[dev] = true;
-    }
-    /* the device copy of the file is allocated with 64 bytes of slack: whole 16-byte chunks may be read */
-    const uint8_t* buf_end = a->d_file + ((a->file_size + 15) & ~(size_t)15);
     if ( a->dequantize )
-        k_huff_decode<true><<<grid, HD_THREADS, HD_SMEM, stream>>>(a->d_file, buf_end, (uint32_t)a->file_size, a->d_seg_off,
-                                                                   a->seg_count, a->seg_per_scan, a->comps_per_scan,
-                                                                   a->seg_mcu, a->nblk, *a, a->d_coef, a->d_tables);
+        k_huff_decode<true><<<grid, HD_THREADS, 0, stream>>>(a->d_file, a->d_file + a->file_size, a->d_seg_off, a->seg_count,
+                                                             a->seg_per_scan, a->comps_per_scan, a->seg_mcu, a->nblk, *a,
+                                                             a->d_coef, a->d_tables);
     else
-        k_huff_decode<false><<<grid, HD_THREADS, HD_SMEM, stream>>>(a->d_file, buf_end, (uint32_t)a->file_size, a->d_seg_off,
-                                                                    a->seg_count, a->seg_per_scan, a->comps_per_scan,
-                                                                    a->seg_mcu, a->nblk, *a, a->d_coef, a->d_tables);
+        k_huff_decode<false><<<grid, HD_THREADS, 0, stream>>>(a->d_file, a->d_file + a->file_size, a->d_seg_off, a->seg_count,
+                                                              a->seg_per_scan, a->comps_per_scan, a->seg_mcu, a->nblk, *a,
+                                                              a->d_coef, a->d_tables);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

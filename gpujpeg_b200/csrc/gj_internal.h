@@ -62,21 +62,16 @@ struct gj_enc_lut {
 };
 void gj_enc_lut_build(const struct gj_huff_spec* dc, const struct gj_huff_spec* ac, struct gj_enc_lut* lut);
 
-/* Decoder LUT for the device, one per (class, id), indexed by the next 16 bits of the stream (peek16):
- *   look[peek16 >> 7]  = (symbol << 8) | len for codes of length <= 9, 0 if the code is longer
- *   look2[((peek16 >> 7) - l2_base) * 128 + (peek16 & 127)] = (symbol << 8) | len for the longer codes.
- *       Canonical codes are sorted, so all long codes share the numerically largest 9-bit prefixes; the
- *       second level covers GJ_DEC_L2_PREFIXES of them (the Annex K tables need 5).  l2_ok = 0 when a
- *       table needs more: the kernel then falls back to the canonical search below.
- *   maxcode[l] = exclusive upper bound of all codes of length <= l, left-justified to 16 bits
- *   valoff[l]  = valptr[l] - mincode[l];  vals[] = HUFFVAL */
+/* Decoder LUT for the device, one per (class, id):
+ *   look[peek9] = (symbol << 4) | len for codes of length <= 9, 0 if longer
+ *   maxcode[l]  = exclusive upper bound of all codes of length <= l, left-justified to 16 bits
+ *   valoff[l]   = valptr[l] - mincode[l]
+ *   vals[]      = HUFFVAL
+ * (a two-level table and a cp.async staging ring were measured as well, profiles/r1_e: both lengthen the
+ * per-warp instruction stream, which is what bounds the decoder, and lost against this variant) */
 #define GJ_DEC_LOOK_BITS 9
-#define GJ_DEC_L2_PREFIXES 16
 struct gj_dec_lut {
     uint16_t look[1 << GJ_DEC_LOOK_BITS];
-    uint16_t look2[GJ_DEC_L2_PREFIXES * 128];
-    uint32_t l2_base;
-    uint32_t l2_ok;
     uint32_t maxcode[18];
     int32_t valoff[18];
     uint8_t vals[256];

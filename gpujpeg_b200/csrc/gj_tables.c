@@ -129,11 +129,8 @@ int gj_dec_lut_build(const struct gj_huff_spec* spec, struct gj_dec_lut* lut)
 {
     memset(lut, 0, sizeof *lut);
     memcpy(lut->vals, spec->vals, 256);
-    lut->l2_base = 1u << GJ_DEC_LOOK_BITS;
-    lut->l2_ok = 1;
     uint32_t code = 0;
     int p = 0;
-    /* pass 1: first level, canonical bounds, and the smallest 9-bit prefix owning a long code */
     for ( int l = 1; l <= 16; l++ ) {
         /* valoff: symbol index = code + valoff[l] for a code of length l */
         lut->valoff[l] = p - (int32_t)code;
@@ -143,11 +140,7 @@ int gj_dec_lut_build(const struct gj_huff_spec* spec, struct gj_dec_lut* lut)
                 const uint32_t first = code << (GJ_DEC_LOOK_BITS - l);
                 const uint32_t count = 1u << (GJ_DEC_LOOK_BITS - l);
                 for ( uint32_t j = 0; j < count; j++ )
-                    lut->look[first + j] = (uint16_t)((spec->vals[p] << 8) | l);
-            }
-            else {
-                const uint32_t prefix = code >> (l - GJ_DEC_LOOK_BITS);
-                if ( prefix < lut->l2_base ) lut->l2_base = prefix;
+                    lut->look[first + j] = (uint16_t)((spec->vals[p] << 4) | l);
             }
             code++;
         }
@@ -156,27 +149,5 @@ int gj_dec_lut_build(const struct gj_huff_spec* spec, struct gj_dec_lut* lut)
         code <<= 1;
     }
     lut->maxcode[17] = 0xFFFFFFFFu;
-    /* pass 2: second level */
-    code = 0;
-    p = 0;
-    for ( int l = 1; l <= 16; l++ ) {
-        for ( int i = 0; i < spec->bits[l]; i++, p++ ) {
-            if ( l > GJ_DEC_LOOK_BITS ) {
-                const uint32_t first = code << (16 - l); /* as peek16 */
-                const uint32_t count = 1u << (16 - l);
-                for ( uint32_t j = 0; j < count; j++ ) {
-                    const uint32_t pk = first + j;
-                    const uint32_t idx = ((pk >> 7) - lut->l2_base) * 128 + (pk & 127);
-                    if ( idx >= GJ_DEC_L2_PREFIXES * 128 ) {
-                        lut->l2_ok = 0;
-                        continue;
-                    }
-                    lut->look2[idx] = (uint16_t)((spec->vals[p] << 8) | l);
-                }
-            }
-            code++;
-        }
-        code <<= 1;
-    }
     return 0;
 }

@@ -57,12 +57,10 @@ int shim_dec_lut_symbol(int cls, int kind, unsigned peek16, int* len)
     struct gj_dec_lut t;
     gj_huff_spec_default(cls, kind, &spec);
     if ( gj_dec_lut_build(&spec, &t) ) return -1;
-    unsigned e = t.look[peek16 >> (16 - GJ_DEC_LOOK_BITS)];
-    if ( (e & 255u) == 0 && t.l2_ok && (peek16 >> 7) >= t.l2_base )
-        e = t.look2[((peek16 >> 7) - t.l2_base) * 128 + (peek16 & 127)];
-    if ( e & 255u ) {
-        *len = (int)(e & 255u);
-        return (int)(e >> 8);
+    const unsigned e = t.look[peek16 >> (16 - GJ_DEC_LOOK_BITS)];
+    if ( e & 15u ) {
+        *len = (int)(e & 15u);
+        return (int)(e >> 4);
     }
     int l = GJ_DEC_LOOK_BITS + 1;
     while ( l <= 16 && peek16 >= t.maxcode[l] ) l++;
