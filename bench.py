@@ -75,6 +75,18 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def host_cores():
+    """cores this process may actually use: min(affinity mask, cgroup CPU quota)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(quota) // int(period)))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_baseline(width, height, rst, frames, threads):
     """Times the oracle port (encode + decode) on the host cores; returns Mpix/s and the sample description."""
     import _oracle as o
@@ -94,7 +106,7 @@ def run_reference(args):
     if rank != 0:
         return
     width, height, rst = WORKLOADS[args.size]
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_baseline(width, height, rst, 1, cores)
     t0 = time.perf_counter()
@@ -251,10 +263,10 @@ def main():
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
-            cores = os.cpu_count() or 1
-            mpix, sec = cpu_baseline(width, height, rst, 2, cores)
+            cores = host_cores()
+            mpix, sec = cpu_baseline(width, height, rst, 4, cores)
             line["cpu_baseline"] = {"value": round(mpix, 2), "unit": "Mpix/s", "cores": cores, "kind": "port",
-                                    "sample": "2 full %dx%d frames encode+decode, %.1f s, OpenMP %d threads" % (width, height, sec, cores)}
+                                    "sample": "4 full %dx%d frames encode+decode, %.1f s, OpenMP %d threads (= cgroup CPU quota of the box)" % (width, height, sec, cores)}
         print(json.dumps(line))
     enc.close()
     dec.close()

@@ -20,6 +20,22 @@
 #endif
 
 /* ------------------------------------------------------------------------------------------- */
+/* scratch buffers are kept between calls (grow-only, not thread-safe across concurrent callers): a
+ * fresh malloc of ~0.5 GB per 8K frame spends more time in page faults than in the codec once the
+ * loops run on 16+ threads */
+static void* scratch(int slot, size_t size)
+{
+    static void* buf[8];
+    static size_t cap[8];
+    if ( cap[slot] < size ) {
+        free(buf[slot]);
+        buf[slot] = malloc(size);
+        cap[slot] = buf[slot] ? size : 0;
+    }
+    return buf[slot];
+}
+
+/* ------------------------------------------------------------------------------------------- */
 /* constant tables                                                                              */
 
 /* zig-zag index -> natural (row-major) index.  [ref: src/gpujpeg_table.h:73-84] */
@@ -196,7 +212,7 @@ static inline uint8_t clamp8(int v) { return (uint8_t)(v < 0 ? 0 : v > 255 ? 255
 void orc_preprocess_rgb444(const uint8_t* rgb, int w, int h, int pad, uint8_t* planes, int dw, int dh)
 {
     size_t psz = (size_t)dw * dh;
-    memset(planes, 0, 3 * psz);
+    if ( dw != w || dh != h ) memset(planes, 0, 3 * psz); /* padding is 0; skip the pass when there is none */
     size_t pitch = (size_t)3 * w + pad;
 #pragma omp parallel for schedule(static)
     for ( int y = 0; y < h; y++ ) {
@@ -722,12 +738,11 @@ size_t orc_encode_rgb(const uint8_t* rgb, int w, int h, int pad, int quality, in
     float fwd[2][64];
     orc_quant_tables(quality, raw, fwd, NULL);
 
-    uint8_t* planes = (uint8_t*)malloc(3 * psz);
-    int16_t* coef = coef_out ? coef_out : (int16_t*)malloc(3 * psz * sizeof(int16_t));
+    uint8_t* planes = (uint8_t*)scratch(0, 3 * psz);
+    int16_t* coef = coef_out ? coef_out : (int16_t*)scratch(1, 3 * psz * sizeof(int16_t));
     orc_preprocess_rgb444(rgb, w, h, pad, planes, dw, dh);
     for ( int c = 0; c < comps; c++ )
         orc_fdct_quant_plane(planes + c * psz, dw, dh, fwd[c == 0 ? 0 : 1], coef + c * psz);
-    free(planes);
 
     uint8_t* p = out + orc_write_header(out, w, h, quality, rst, comps);
 
@@ -739,9 +754,9 @@ size_t orc_encode_rgb(const uint8_t* rgb, int w, int h, int pad, int quality, in
     /* encode every segment of every scan independently (legal: segments share no state), then
      * concatenate in order with RSTn between segments of a scan */
     size_t total_seg = (size_t)nscan * nseg;
-    size_t* seg_len = (size_t*)malloc(total_seg * sizeof(size_t));
-    /* to bound memory for rst==0 (one huge segment) encode straight into a big buffer */
-    uint8_t* tmp = (uint8_t*)malloc(total_seg * slot);
+    size_t* seg_len = (size_t*)scratch(2, total_seg * sizeof(size_t));
+    /* one worst-case slot per segment; only the used prefix of each slot is ever touched */
+    uint8_t* tmp = (uint8_t*)scratch(3, total_seg * slot);
     if ( !seg_len || !tmp ) return 0;
 #pragma omp parallel for schedule(dynamic, 16)
     for ( long long si = 0; si < (long long)total_seg; si++ ) {
@@ -773,9 +788,6 @@ size_t orc_encode_rgb(const uint8_t* rgb, int w, int h, int pad, int quality, in
         }
     }
     p = putm(p, 0xD9);
-    free(tmp);
-    free(seg_len);
-    if ( !coef_out ) free(coef);
 #ifdef _OPENMP
     omp_set_num_threads(saved_threads);
 #endif
@@ -987,13 +999,13 @@ static int parse_stream(const uint8_t* j, size_t size, struct parsed* P)
             /* entropy-coded data runs until a marker that is neither RSTn nor a stuffed zero
              * [ref: src/gpujpeg_reader.c:1038-1155] */
             while ( e + 1 < size ) {
-                if ( j[e] == 0xFF ) {
-                    int mm = j[e + 1];
-                    if ( mm == 0 || (mm >= 0xD0 && mm <= 0xD7) ) { e += 2; continue; }
-                    if ( mm == 0xFF ) { e++; continue; }
-                    break;
-                }
-                e++;
+                const uint8_t* f = (const uint8_t*)memchr(j + e, 0xFF, size - 1 - e);
+                if ( !f ) { e = size; break; }
+                e = (size_t)(f - j);
+                int mm = j[e + 1];
+                if ( mm == 0 || (mm >= 0xD0 && mm <= 0xD7) ) { e += 2; continue; }
+                if ( mm == 0xFF ) { e++; continue; }
+                break;
             }
             P->scan[s].begin = b;
             P->scan[s].end = e;
@@ -1011,20 +1023,18 @@ static int split_scan(const uint8_t* j, size_t b, size_t e, size_t* seg_off, siz
     int n = 0;
     size_t start = b;
     for ( size_t i = b; i + 1 < e; ) {
-        if ( j[i] == 0xFF ) {
-            int m = j[i + 1];
-            if ( m >= 0xD0 && m <= 0xD7 ) {
-                if ( n >= max_seg ) return -1;
-                seg_off[n] = start;
-                seg_len[n] = i - start;
-                n++;
-                start = i + 2;
-            }
-            i += 2;
+        const uint8_t* f = (const uint8_t*)memchr(j + i, 0xFF, e - 1 - i);
+        if ( !f ) break;
+        i = (size_t)(f - j);
+        int m = j[i + 1];
+        if ( m >= 0xD0 && m <= 0xD7 ) {
+            if ( n >= max_seg ) return -1;
+            seg_off[n] = start;
+            seg_len[n] = i - start;
+            n++;
+            start = i + 2;
         }
-        else {
-            i++;
-        }
+        i += 2;
     }
     if ( n >= max_seg ) return -1;
     seg_off[n] = start;
@@ -1076,11 +1086,11 @@ int orc_decode_rgb(const uint8_t* jpeg, size_t size, int idct_flavour, int threa
     int dw = (P.w + 7) / 8 * 8, dh = (P.h + 7) / 8 * 8;
     size_t psz = (size_t)dw * dh;
     int nblk = (dw / 8) * (dh / 8);
-    int16_t* coef = coef_out ? coef_out : (int16_t*)malloc(P.comps * psz * sizeof(int16_t));
+    int16_t* coef = coef_out ? coef_out : (int16_t*)scratch(4, P.comps * psz * sizeof(int16_t));
     int seg_mcu = P.rst > 0 ? P.rst : nblk;
     int nseg = (nblk + seg_mcu - 1) / seg_mcu;
-    size_t* so = (size_t*)malloc(sizeof(size_t) * (nseg + 1));
-    size_t* sl = (size_t*)malloc(sizeof(size_t) * (nseg + 1));
+    size_t* so = (size_t*)scratch(5, sizeof(size_t) * (nseg + 1));
+    size_t* sl = (size_t*)scratch(6, sizeof(size_t) * (nseg + 1));
     int rc = 0;
     for ( int s = 0; s < P.nscan && rc == 0; s++ ) {
         int n = split_scan(jpeg, P.scan[s].begin, P.scan[s].end, so, sl, nseg + 1);
@@ -1137,10 +1147,8 @@ int orc_decode_rgb(const uint8_t* jpeg, size_t size, int idct_flavour, int threa
             }
         }
     }
-    free(so);
-    free(sl);
     if ( rc == 0 && rgb ) {
-        uint8_t* planes = (uint8_t*)malloc(P.comps * psz);
+        uint8_t* planes = (uint8_t*)scratch(7, P.comps * psz);
         for ( int c = 0; c < P.comps; c++ ) {
             uint16_t inv[64];
             for ( int i = 0; i < 64; i++ )
@@ -1154,9 +1162,7 @@ int orc_decode_rgb(const uint8_t* jpeg, size_t size, int idct_flavour, int threa
             for ( int y = 0; y < P.h; y++ )
                 memcpy(rgb + (size_t)y * P.w, planes + (size_t)y * dw, P.w);
         }
-        free(planes);
     }
-    if ( !coef_out ) free(coef);
 #ifdef _OPENMP
     omp_set_num_threads(saved_threads);
 #endif
