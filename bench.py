@@ -242,6 +242,18 @@ def main():
         peak, peak_kind = hbm_peak()
         alg = {"k1_fdct": 9.0, "k2_huffman_encode": 6.0 + c_bpp, "k3_huffman_decode": 6.0 + c_bpp, "k4_idct": 9.0}
         worst = max(stages, key=lambda k: stages[k])
+        # DRAM traffic of that kernel from the committed ncu --set full capture of the same workload (per launch)
+        traffic = None
+        try:
+            if args.size == "8k" and args.kind == "photo":
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_8k_photo.json")))["kernels"]
+                name = {"k1_fdct": "k_fdct_rgb444", "k2_huffman_encode": "k_huff_encode", "k3_huffman_decode": "k_huff_decode",
+                        "k4_idct": "k_idct_rgb444"}[worst]
+                for k, v in tj.items():
+                    if k.startswith(name):
+                        traffic = int(v["dram_bytes_read"] + v["dram_bytes_write"])
+        except Exception:
+            traffic = None
         roof = {k: alg[k] * npix / (stages[k] * 1e-3) / 1e9 for k in stages}
         path_gbs = (30.0 + 2 * c_bpp) * npix / (ms_step * 1e-3) / 1e9
         line = {
@@ -254,7 +266,7 @@ def main():
                        "sharding": "one coder instance per GPU, independent frames, no data-path collective"},
             "stage_ms": {k: round(v, 4) for k, v in stages.items()},
             "roofline": {"bound": "hbm", "kernel": worst, "achieved": round(roof[worst], 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(roof[worst] / peak, 4), "traffic": None, "peak_source": peak_kind,
+                         "frac": round(roof[worst] / peak, 4), "traffic": traffic, "peak_source": peak_kind,
                          "all_stages_gbs": {k: round(v, 1) for k, v in roof.items()},
                          "path_achieved_gbs": round(path_gbs, 1), "path_frac": round(path_gbs / peak, 4)},
             "e2e": {"value": round(e2e_value, 1), "unit": "Mpix/s", "ms_per_step": round(e2e_ms, 3),
