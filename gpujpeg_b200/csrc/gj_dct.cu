@@ -64,7 +64,7 @@ __device__ __forceinline__ uint32_t pack4_sat_u8(int p0, int p1, int p2, int p3)
 template <int VEC>
 __global__ void __launch_bounds__(NT)
 k_fdct_rgb444(const uint8_t* __restrict__ raw, int width, int height, size_t pitch, int16_t* __restrict__ coef,
-              int bcx, int nblk, const __grid_constant__ FdctParams prm)
+              uint64_t* __restrict__ nzmask, int bcx, int nblk, const __grid_constant__ FdctParams prm)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     float* s_pl = reinterpret_cast<float*>(smem);
@@ -150,13 +150,24 @@ k_fdct_rgb444(const uint8_t* __restrict__ raw, int width, int height, size_t pit
     /* quantise: q = rint(c * table) [ref: src/gpujpeg_dct_gpu.cu:276-283], emit in zig-zag order */
     const float* tab = prm.fwd_zz[comp == 0 ? 0 : 1];
     uint32_t packed[32];
+    uint32_t mlo = 0, mhi = 0;   // bit k <=> zig-zag coefficient k is non-zero: saves K2 a pass over the block
 #pragma unroll
     for ( int k = 0; k < 64; k += 2 ) {
         const int q0 = GJ_RINT(GJ_FMUL(v[gj_zz2nat(k)], tab[k]));
         const int q1 = GJ_RINT(GJ_FMUL(v[gj_zz2nat(k + 1)], tab[k + 1]));
         packed[k >> 1] = __byte_perm((uint32_t)q0, (uint32_t)q1, 0x5410);
+        if ( k < 32 ) {
+            if ( q0 ) mlo |= 1u << (k & 31);
+            if ( q1 ) mlo |= 1u << ((k + 1) & 31);
+        }
+        else {
+            if ( q0 ) mhi |= 1u << (k & 31);
+            if ( q1 ) mhi |= 1u << ((k + 1) & 31);
+        }
     }
-    uint4* dst = reinterpret_cast<uint4*>(coef + ((size_t)comp * nblk + (size_t)by * bcx + bx0 + b) * 64);
+    const size_t bi = (size_t)comp * nblk + (size_t)by * bcx + bx0 + b;
+    nzmask[bi] = (uint64_t)mhi << 32 | mlo;
+    uint4* dst = reinterpret_cast<uint4*>(coef + bi * 64);
 #pragma unroll
     for ( int i = 0; i < 8; i++ )
         dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
@@ -272,8 +283,9 @@ int pick_vec(const void* p, size_t pitch)
 
 }  // namespace
 
-extern "C" int gj_launch_fdct_rgb444(const uint8_t* d_raw, int width, int height, int pitch, int16_t* d_coef, int bcx,
-                                     int bcy, const struct gj_dev_enc_tables* h_tables, gj_stream_t stream)
+extern "C" int gj_launch_fdct_rgb444(const uint8_t* d_raw, int width, int height, int pitch, int16_t* d_coef,
+                                     uint64_t* d_nzmask, int bcx, int bcy, const struct gj_dev_enc_tables* h_tables,
+                                     gj_stream_t stream)
 {
     FdctParams prm;
     memcpy(prm.fwd_zz, h_tables->fwd_zz, sizeof prm.fwd_zz);
@@ -290,9 +302,9 @@ extern "C" int gj_launch_fdct_rgb444(const uint8_t* d_raw, int width, int height
         attr_done[dev] = true;
     }
     if ( pick_vec(d_raw, (size_t)pitch) == 4 )
-        k_fdct_rgb444<4><<<grid, NT, K1_SMEM, stream>>>(d_raw, width, height, (size_t)pitch, d_coef, bcx, nblk, prm);
+        k_fdct_rgb444<4><<<grid, NT, K1_SMEM, stream>>>(d_raw, width, height, (size_t)pitch, d_coef, d_nzmask, bcx, nblk, prm);
     else
-        k_fdct_rgb444<1><<<grid, NT, K1_SMEM, stream>>>(d_raw, width, height, (size_t)pitch, d_coef, bcx, nblk, prm);
+        k_fdct_rgb444<1><<<grid, NT, K1_SMEM, stream>>>(d_raw, width, height, (size_t)pitch, d_coef, d_nzmask, bcx, nblk, prm);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

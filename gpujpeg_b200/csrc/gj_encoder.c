@@ -40,6 +40,7 @@ struct gpujpeg_encoder {
     /* device buffers */
     uint8_t* d_raw; size_t d_raw_size;
     int16_t* d_coef; size_t d_coef_size;
+    uint64_t* d_nzmask; size_t d_nzmask_size;
     uint8_t* d_tmp; size_t d_tmp_size;
     uint32_t* d_seg_bytes; uint64_t* d_seg_off; int seg_alloc;
     uint8_t* d_stream; size_t d_stream_size;
@@ -137,6 +138,7 @@ int gpujpeg_encoder_destroy(struct gpujpeg_encoder* e)
     gj_cuda_free_host(e->h_info);
     gj_cuda_free(e->d_raw);
     gj_cuda_free(e->d_coef);
+    gj_cuda_free(e->d_nzmask);
     gj_cuda_free(e->d_tmp);
     gj_cuda_free(e->d_seg_bytes);
     gj_cuda_free(e->d_seg_off);
@@ -223,7 +225,9 @@ static int encoder_init_image(struct gpujpeg_encoder* e, const struct gpujpeg_pa
     const struct gj_geometry* g = &e->geo;
     size_t coef_bytes = g->coef_count * sizeof(int16_t);
     size_t tmp_bytes = (size_t)g->seg_count * g->slot_stride + 256;
-    if ( grow((void**)&e->d_coef, &e->d_coef_size, coef_bytes) || grow((void**)&e->d_tmp, &e->d_tmp_size, tmp_bytes) ||
+    if ( grow((void**)&e->d_coef, &e->d_coef_size, coef_bytes) ||
+         grow((void**)&e->d_nzmask, &e->d_nzmask_size, g->coef_count / 64 * sizeof(uint64_t)) ||
+         grow((void**)&e->d_tmp, &e->d_tmp_size, tmp_bytes) ||
          grow((void**)&e->d_stream, &e->d_stream_size, g->stream_cap + 64) ) {
         GJ_ERR("Encoder device allocation failed (%zu + %zu + %zu bytes): %s\n", coef_bytes, tmp_bytes, g->stream_cap,
                gj_cuda_last_error());
@@ -446,7 +450,7 @@ int gpujpeg_encoder_encode(struct gpujpeg_encoder* e, const struct gpujpeg_param
         gj_timer_start(&e->t_gpu, e->stream);
         gj_timer_start(&e->t_pre, e->stream);
     }
-    if ( gj_launch_fdct_rgb444(d_raw, g->width, g->height, g->pitch, e->d_coef, g->bcx, g->bcy, &e->h_tab, e->stream) ) {
+    if ( gj_launch_fdct_rgb444(d_raw, g->width, g->height, g->pitch, e->d_coef, e->d_nzmask, g->bcx, g->bcy, &e->h_tab, e->stream) ) {
         GJ_ERR("Forward DCT launch failed: %s\n", gj_cuda_last_error());
         return GPUJPEG_ERROR;
     }
@@ -457,6 +461,7 @@ int gpujpeg_encoder_encode(struct gpujpeg_encoder* e, const struct gpujpeg_param
     struct gj_huff_enc_args ha;
     memset(&ha, 0, sizeof ha);
     ha.d_coef = e->d_coef;
+    ha.d_nzmask = e->d_nzmask;
     ha.nblk = g->nblk;
     ha.comp_count = g->comp_count;
     ha.comps_per_scan = g->comps_per_scan;
@@ -604,12 +609,13 @@ GPUJPEG_API int gpujpegx_encoder_run_resident(struct gpujpeg_encoder* e, const u
     if ( !d_raw ) d_raw = e->d_raw;
     if ( !d_raw ) return -1;
     if ( (stage_mask & 1) &&
-         gj_launch_fdct_rgb444(d_raw, g->width, g->height, g->pitch, e->d_coef, g->bcx, g->bcy, &e->h_tab, e->stream) )
+         gj_launch_fdct_rgb444(d_raw, g->width, g->height, g->pitch, e->d_coef, e->d_nzmask, g->bcx, g->bcy, &e->h_tab, e->stream) )
         return -1;
     if ( stage_mask & 2 ) {
         struct gj_huff_enc_args ha;
         memset(&ha, 0, sizeof ha);
         ha.d_coef = e->d_coef;
+        ha.d_nzmask = e->d_nzmask;
         ha.nblk = g->nblk;
         ha.comp_count = g->comp_count;
         ha.comps_per_scan = g->comps_per_scan;

@@ -4,13 +4,13 @@
  * ENCODER (replaces the reference's three kernels src/gpujpeg_huffman_gpu_encoder.cu:299-404,
  * 416-502, 562-615 and the host re-ordering loop src/gpujpeg_encoder.c:567-626):
  *
- *   k_huff_encode   one WARP per restart segment, one LANE per 8x8 block.  Each lane turns its
- *                   block into a bit string (sparse walk over the 64-bit non-zero mask of the
- *                   zig-zag ordered coefficients), a warp prefix sum over the bit lengths places
- *                   the strings, lanes OR them into a per-warp shared-memory bit buffer, and the
- *                   warp then byte-stuffs the buffer into the segment's slot.  The buffer is
- *                   flushed in rounds, so segments of any length (even restart_interval = 0)
- *                   stream through 2 KB of shared memory.
+ *   k_huff_encode   one WARP per restart segment, one LANE per 8x8 block, one pass per block: each
+ *                   lane turns its block into a private bit string (sparse walk over the 64-bit
+ *                   non-zero mask K1 wrote next to the zig-zag ordered coefficients), a warp prefix
+ *                   sum over the lengths places the strings, lanes funnel-shift them into a per-warp
+ *                   shared-memory stream buffer, and the warp byte-stuffs the buffer into the
+ *                   segment's slot.  The buffer is flushed in rounds, so segments of any length
+ *                   (even restart_interval = 0) stream through 2 KB of shared memory.
  *   k_huff_offsets  exclusive scan of the segment sizes -> final byte offsets (deterministic,
  *                   unlike the reference's atomicAdd compaction).
  *   k_huff_compact  copies every segment to its final place and writes RSTn markers, the SOS
@@ -113,14 +113,29 @@ __device__ __forceinline__ uint32_t flush_words(const uint32_t* buf, int nw, uin
     return pos;
 }
 
+constexpr int HE_PRIV = 57;   // words of private bit string per lane: an 8x8 block never needs more than 54
+                              // (64 x (16-bit code + 11 value bits)); odd stride = conflict-free columns
+constexpr int HE_SMEM = (2 * 256 + 2 * 16 + HE_WARPS * HE_WORDS + HE_WARPS * 32 * HE_PRIV) * 4;
+
+/* One WARP per restart segment, one LANE per 8x8 block, ONE pass per block:
+ *   1. the lane walks the set bits of the block's non-zero mask (written by K1 next to the coefficients),
+ *      looks code and length up in shared memory and appends code+value bits to a private bit string in
+ *      shared memory (a 64-bit accumulator flushes whole words);
+ *   2. a warp prefix sum over the string lengths gives every block its bit offset in the segment;
+ *   3. the lane funnel-shifts its words into the warp's stream buffer: words lying completely inside its
+ *      own bit range are plain stores, only the first and last one are shared with the neighbours (atomicOr);
+ *   4. the warp byte-stuffs the completed words of the stream buffer into the segment's slot.
+ * The stream buffer is flushed in rounds, so segments of any length stream through it. */
 __global__ void __launch_bounds__(HE_WARPS * 32)
-k_huff_encode(const int16_t* __restrict__ coef, int nblk, int cps /*components per scan*/, int seg_mcu, int seg_per_scan,
-              int seg_count, uint8_t* __restrict__ tmp, size_t slot_stride, uint32_t* __restrict__ seg_bytes,
-              const gj_dev_enc_tables* __restrict__ tables)
+k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzmask, int nblk, int cps /*components per scan*/,
+              int seg_mcu, int seg_per_scan, int seg_count, uint8_t* __restrict__ tmp, size_t slot_stride,
+              uint32_t* __restrict__ seg_bytes, const gj_dev_enc_tables* __restrict__ tables)
 {
-    __shared__ uint32_t s_ac[2][256];
-    __shared__ uint32_t s_dc[2][16];
-    __shared__ uint32_t s_buf[HE_WARPS][HE_WORDS];
+    extern __shared__ __align__(16) uint32_t he_smem[];
+    uint32_t (*s_ac)[256] = reinterpret_cast<uint32_t (*)[256]>(he_smem);
+    uint32_t (*s_dc)[16] = reinterpret_cast<uint32_t (*)[16]>(he_smem + 512);
+    uint32_t* s_buf = he_smem + 512 + 32;
+    uint32_t* s_priv = s_buf + HE_WARPS * HE_WORDS;
 
     for ( int i = threadIdx.x; i < 512; i += blockDim.x )
         s_ac[i >> 8][i & 255] = tables->lut[i >> 8].ac[i & 255];
@@ -134,7 +149,8 @@ k_huff_encode(const int16_t* __restrict__ coef, int nblk, int cps /*components p
     const int first_mcu = s * seg_mcu;
     const int mcus = min(seg_mcu, nblk - first_mcu);
     const int nblocks = mcus * cps;
-    uint32_t* buf = s_buf[warp];
+    uint32_t* buf = s_buf + warp * HE_WORDS;
+    uint32_t* priv = s_priv + (warp * 32 + lane) * HE_PRIV;
     uint8_t* out = tmp + (size_t)g * slot_stride;
     uint32_t out_pos = 0;
     int carry = 0;  // bits already sitting in buf[0] (always < 32 between rounds)
@@ -152,25 +168,14 @@ k_huff_encode(const int16_t* __restrict__ coef, int nblk, int cps /*components p
         else { mcu = j / cps; ci = j - mcu * cps; }
         const int comp = cps == 1 ? scan : ci;
         const int tbl = comp == 0 ? 0 : 1;
-        const int16_t* blk = coef + ((size_t)comp * nblk + first_mcu + mcu) * 64;
+        const size_t bi = (size_t)comp * nblk + first_mcu + mcu;
+        const int16_t* blk = coef + bi * 64;
 
-        /* ---- pass 1: non-zero mask, DC, exact bit length ---- */
         uint64_t nz = 0;
         int dc = 0;
         if ( active ) {
-            const uint4* p = reinterpret_cast<const uint4*>(blk);
-#pragma unroll
-            for ( int i = 0; i < 8; i++ ) {
-                const uint4 t = __ldg(p + i);
-                const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-                for ( int q = 0; q < 4; q++ ) {
-                    const uint64_t lo = (w[q] & 0xFFFFu) ? 1ull : 0ull;
-                    const uint64_t hi = (w[q] >> 16) ? 1ull : 0ull;
-                    nz |= (lo | (hi << 1)) << (8 * i + 2 * q);
-                }
-                if ( i == 0 ) dc = (int)(short)(t.x & 0xFFFFu);
-            }
+            nz = __ldg(nzmask + bi);
+            dc = __ldg(blk);
         }
         /* DC predictor: previous block of the same component inside the segment, 0 at its start
          * [ref: src/gpujpeg_huffman_cpu_encoder.c:147-148, 361-364] */
@@ -178,28 +183,55 @@ k_huff_encode(const int16_t* __restrict__ coef, int nblk, int cps /*components p
         if ( lane < cps ) pred = prev_dc;
         if ( j < cps ) pred = 0;
         prev_dc = __shfl_sync(FULL, dc, (32 - cps + lane) & 31);
-        const int diff = dc - pred;
-        const int dcat = gj_category(diff);
-        int len = 0;
+
+        /* ---- 1. the block's bit string, into the lane's private words ---- */
+        int len = 0;   // total bits of this block
         if ( active ) {
-            len = (int)(s_dc[tbl][dcat] & 31u) + dcat;
-            uint64_t m = nz & ~1ull;
+            uint64_t acc = 0;
+            int nb = 0, wi = 0;
+#define GJ_PUT(bits_, len_)                                        \
+    do {                                                           \
+        acc = (acc << (len_)) | (uint64_t)(bits_);                 \
+        nb += (len_);                                              \
+        if ( nb >= 32 ) {                                          \
+            priv[wi++] = (uint32_t)(acc >> (nb - 32));             \
+            nb -= 32;                                              \
+        }                                                          \
+    } while ( 0 )
+            const int diff = dc - pred;
+            const int dcat = gj_category(diff);
+            const uint32_t de = s_dc[tbl][dcat];
+            GJ_PUT(((de >> 5) << dcat) | (dcat ? gj_value_bits(diff, dcat) : 0u), (int)(de & 31u) + dcat);
+            uint32_t mlo = (uint32_t)nz & ~1u, mhi = (uint32_t)(nz >> 32);
             int last = 0;
-            while ( m ) {
-                const int k = __ffsll((long long)m) - 1;
-                m &= m - 1;
-                const int run = k - last - 1;
+            const uint32_t zrl = s_ac[tbl][0xF0];
+            while ( mlo | mhi ) {
+                int k;
+                if ( mlo ) { k = __ffs((int)mlo) - 1; mlo &= mlo - 1; }
+                else { k = 32 + __ffs((int)mhi) - 1; mhi &= mhi - 1; }
+                int run = k - last - 1;
                 last = k;
-                const int v = blk[k];
+                const int v = __ldg(blk + k);
                 const int size = gj_category(v);
-                len += (run >> 4) * (int)(s_ac[tbl][0xF0] & 31u) + (int)(s_ac[tbl][((run & 15) << 4) | size] & 31u) + size;
+                while ( run > 15 ) {
+                    GJ_PUT(zrl >> 5, (int)(zrl & 31u));
+                    run -= 16;
+                }
+                const uint32_t e = s_ac[tbl][(run << 4) | size];
+                GJ_PUT(((e >> 5) << size) | gj_value_bits(v, size), (int)(e & 31u) + size);
             }
-            if ( last < 63 ) len += (int)(s_ac[tbl][0] & 31u);
+            if ( last < 63 ) {
+                const uint32_t e = s_ac[tbl][0];
+                GJ_PUT(e >> 5, (int)(e & 31u));
+            }
+#undef GJ_PUT
+            if ( nb ) priv[wi] = (uint32_t)(acc << (32 - nb));   // left-aligned tail, low bits zero
+            len = 32 * wi + nb;
         }
         const int incl = warp_incl_scan(len, lane);
         const int excl = incl - len;
 
-        /* ---- pass 2: emit, in as many sub-rounds as the buffer needs (normally one) ---- */
+        /* ---- 2.+3. place the strings, in as many sub-rounds as the buffer needs (normally one) ---- */
         int lane0 = 0;
         while ( lane0 < 32 ) {
             const int rel0 = __shfl_sync(FULL, excl, lane0);
@@ -208,48 +240,31 @@ k_huff_encode(const int16_t* __restrict__ coef, int nblk, int cps /*components p
             const int nfit = __popc(__ballot_sync(FULL, fits));   // fits is monotone in lane
             if ( nfit == 0 ) break;  // cannot happen (a block is < 2 Kbit, the buffer 16 Kbit); never spin
             const bool mine = lane >= lane0 && lane < lane0 + nfit;
-            if ( mine && active ) {
-                BitSink sk;
-                sk.buf = buf;
-                sk.word = mypos >> 5;
-                sk.acc = 0;
-                sk.n = mypos & 31;
-                sk.first = true;
-                const uint32_t de = s_dc[tbl][dcat];
-                sink_put(sk, ((de >> 5) << dcat) | (dcat ? gj_value_bits(diff, dcat) : 0u), (int)(de & 31u) + dcat);
-                uint64_t m = nz & ~1ull;
-                int last = 0;
-                const uint32_t zrl = s_ac[tbl][0xF0];
-                while ( m ) {
-                    const int k = __ffsll((long long)m) - 1;
-                    m &= m - 1;
-                    int run = k - last - 1;
-                    last = k;
-                    const int v = blk[k];
-                    const int size = gj_category(v);
-                    while ( run > 15 ) {
-                        sink_put(sk, zrl >> 5, (int)(zrl & 31u));
-                        run -= 16;
-                    }
-                    const uint32_t e = s_ac[tbl][(run << 4) | size];
-                    sink_put(sk, ((e >> 5) << size) | gj_value_bits(v, size), (int)(e & 31u) + size);
+            if ( mine && len > 0 ) {
+                const int nw = (len + 31) >> 5;
+                const int d0 = mypos >> 5, sh = mypos & 31;
+                const int endbit = mypos + len;
+                uint32_t prev = 0;
+                for ( int q = 0; q <= nw; q++ ) {
+                    const uint32_t w = q < nw ? priv[q] : 0u;
+                    const uint32_t o = sh ? (prev | (w >> sh)) : w;
+                    prev = sh ? (w << (32 - sh)) : 0u;
+                    const int d = d0 + q;
+                    if ( 32 * d >= endbit ) break;              // nothing of this block reaches word d
+                    if ( 32 * d >= mypos && 32 * d + 32 <= endbit ) buf[d] = o;   // word lies inside this block
+                    else atomicOr(&buf[d], o);                                    // shared with a neighbour
                 }
-                if ( last < 63 ) {
-                    const uint32_t e = s_ac[tbl][0];
-                    sink_put(sk, e >> 5, (int)(e & 31u));
-                }
-                sink_finish(sk);
             }
             __syncwarp();
             const int lastl = lane0 + nfit - 1;
             const int newbits = carry + (__shfl_sync(FULL, incl, lastl) - rel0);
-            const int nw = newbits >> 5;
-            out_pos = flush_words(buf, nw, out, out_pos, lane);
+            const int nwords = newbits >> 5;
+            out_pos = flush_words(buf, nwords, out, out_pos, lane);
             __syncwarp();
             /* keep the trailing partial word as the new word 0, clear what was used */
-            const uint32_t tail = buf[nw];
+            const uint32_t tail = buf[nwords];
             __syncwarp();
-            for ( int i = lane; i <= nw; i += 32 )
+            for ( int i = lane; i <= nwords; i += 32 )
                 buf[i] = 0;
             __syncwarp();
             if ( lane == 0 ) buf[0] = tail;
@@ -266,8 +281,8 @@ k_huff_encode(const int16_t* __restrict__ coef, int nblk, int cps /*components p
         const int nbytes = (carry + 7) >> 3;
         if ( carry & 7 ) w |= ((1u << (8 - (carry & 7))) - 1u) << (32 - nbytes * 8);
         uint8_t* o = out + out_pos;
-        for ( int j = 0; j < nbytes; j++ ) {
-            const uint8_t b = (uint8_t)(w >> (24 - 8 * j));
+        for ( int q = 0; q < nbytes; q++ ) {
+            const uint8_t b = (uint8_t)(w >> (24 - 8 * q));
             *o++ = b;
             if ( b == 0xFF ) *o++ = 0;
         }
@@ -633,8 +648,15 @@ __global__ void k_coef_to_natural(const int16_t* __restrict__ in, int16_t* __res
 extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_stream_t stream)
 {
     const int seg_count = a->seg_per_scan * a->scan_count;
-    k_huff_encode<<<(seg_count + HE_WARPS - 1) / HE_WARPS, HE_WARPS * 32, 0, stream>>>(
-        a->d_coef, a->nblk, a->comps_per_scan, a->seg_mcu, a->seg_per_scan, seg_count, a->d_tmp, a->slot_stride,
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    if ( cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 ) return -1;
+    if ( !attr_done[dev] ) {
+        if ( cudaFuncSetAttribute(k_huff_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, HE_SMEM) != cudaSuccess ) return -1;
+        attr_done[dev] = true;
+    }
+    k_huff_encode<<<(seg_count + HE_WARPS - 1) / HE_WARPS, HE_WARPS * 32, HE_SMEM, stream>>>(
+        a->d_coef, a->d_nzmask, a->nblk, a->comps_per_scan, a->seg_mcu, a->seg_per_scan, seg_count, a->d_tmp, a->slot_stride,
         a->d_seg_bytes, a->d_tables);
     k_huff_offsets<<<1, OFF_THREADS, 0, stream>>>(a->d_seg_bytes, seg_count, a->seg_per_scan, a->header_size, a->sos_len,
                                                   (uint64_t)a->stream_cap, a->d_seg_off, a->d_info);

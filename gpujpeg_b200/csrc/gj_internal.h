@@ -153,14 +153,15 @@ struct gj_dev_dec_tables {
 
 /* K1: RGB u8 interleaved -> quantised zig-zag coefficients (fused colour transform + FDCT + quant)
  * [replaces ref: src/gpujpeg_preprocessor.cu:562-586 + src/gpujpeg_dct_gpu.cu:621-678] */
-int gj_launch_fdct_rgb444(const uint8_t* d_raw, int width, int height, int pitch, int16_t* d_coef, int bcx,
-                          int bcy, const struct gj_dev_enc_tables* d_tables, gj_stream_t stream);
+int gj_launch_fdct_rgb444(const uint8_t* d_raw, int width, int height, int pitch, int16_t* d_coef, uint64_t* d_nzmask,
+                          int bcx, int bcy, const struct gj_dev_enc_tables* d_tables, gj_stream_t stream);
 
 /* K2: Huffman-encode every restart segment and assemble the finished scan data
  * [replaces ref: src/gpujpeg_huffman_gpu_encoder.cu:1071-1167 + host loop src/gpujpeg_encoder.c:567-626]
  * d_stream receives [header gap][SOS][scan 0]...[EOI]; d_info[0] = total bytes, d_info[1] = error flag */
 struct gj_huff_enc_args {
     const int16_t* d_coef;
+    const uint64_t* d_nzmask; /* [comp][block]: bit k set <=> zig-zag coefficient k is non-zero (written by K1) */
     int nblk, comp_count, comps_per_scan, seg_mcu, seg_per_scan, scan_count;
     uint8_t* d_tmp;
     size_t slot_stride;
