@@ -42,6 +42,7 @@ struct gpujpeg_encoder {
     int16_t* d_coef; size_t d_coef_size;
     uint64_t* d_nzmask; size_t d_nzmask_size;
     uint8_t* d_tmp; size_t d_tmp_size;
+    uint32_t* d_spill; size_t d_spill_size;
     uint32_t* d_seg_bytes; uint64_t* d_seg_off; int seg_alloc;
     uint8_t* d_stream; size_t d_stream_size;
     uint8_t* d_sos;
@@ -140,6 +141,7 @@ int gpujpeg_encoder_destroy(struct gpujpeg_encoder* e)
     gj_cuda_free(e->d_coef);
     gj_cuda_free(e->d_nzmask);
     gj_cuda_free(e->d_tmp);
+    gj_cuda_free(e->d_spill);
     gj_cuda_free(e->d_seg_bytes);
     gj_cuda_free(e->d_seg_off);
     gj_cuda_free(e->d_stream);
@@ -228,6 +230,7 @@ static int encoder_init_image(struct gpujpeg_encoder* e, const struct gpujpeg_pa
     if ( grow((void**)&e->d_coef, &e->d_coef_size, coef_bytes) ||
          grow((void**)&e->d_nzmask, &e->d_nzmask_size, g->coef_count / 64 * sizeof(uint64_t)) ||
          grow((void**)&e->d_tmp, &e->d_tmp_size, tmp_bytes) ||
+         grow((void**)&e->d_spill, &e->d_spill_size, (size_t)g->seg_count * 32 * 32 * sizeof(uint32_t)) ||
          grow((void**)&e->d_stream, &e->d_stream_size, g->stream_cap + 64) ) {
         GJ_ERR("Encoder device allocation failed (%zu + %zu + %zu bytes): %s\n", coef_bytes, tmp_bytes, g->stream_cap,
                gj_cuda_last_error());
@@ -469,6 +472,7 @@ int gpujpeg_encoder_encode(struct gpujpeg_encoder* e, const struct gpujpeg_param
     ha.seg_per_scan = g->seg_per_scan;
     ha.scan_count = g->scan_count;
     ha.d_tmp = e->d_tmp;
+    ha.d_spill = e->d_spill;
     ha.slot_stride = g->slot_stride;
     ha.d_seg_bytes = e->d_seg_bytes;
     ha.d_seg_off = e->d_seg_off;
@@ -623,6 +627,7 @@ GPUJPEG_API int gpujpegx_encoder_run_resident(struct gpujpeg_encoder* e, const u
         ha.seg_per_scan = g->seg_per_scan;
         ha.scan_count = g->scan_count;
         ha.d_tmp = e->d_tmp;
+        ha.d_spill = e->d_spill;
         ha.slot_stride = g->slot_stride;
         ha.d_seg_bytes = e->d_seg_bytes;
         ha.d_seg_off = e->d_seg_off;

@@ -113,8 +113,10 @@ __device__ __forceinline__ uint32_t flush_words(const uint32_t* buf, int nw, uin
     return pos;
 }
 
-constexpr int HE_PRIV = 57;   // words of private bit string per lane: an 8x8 block never needs more than 54
-                              // (64 x (16-bit code + 11 value bits)); odd stride = conflict-free columns
+constexpr int HE_PRIV = 25;    // words of private bit string per lane kept in shared memory (odd stride =
+                               // conflict-free columns); 800 bits cover every block of ordinary content
+constexpr int HE_SPILL = 32;   // further words per lane in global memory: an 8x8 block never needs more than
+                               // 54 words in total (64 x (16-bit code + 11 value bits))
 constexpr int HE_SMEM = (2 * 256 + 2 * 16 + HE_WARPS * HE_WORDS + HE_WARPS * 32 * HE_PRIV) * 4;
 
 /* One WARP per restart segment, one LANE per 8x8 block, ONE pass per block:
@@ -129,7 +131,7 @@ constexpr int HE_SMEM = (2 * 256 + 2 * 16 + HE_WARPS * HE_WORDS + HE_WARPS * 32 
 __global__ void __launch_bounds__(HE_WARPS * 32)
 k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzmask, int nblk, int cps /*components per scan*/,
               int seg_mcu, int seg_per_scan, int seg_count, uint8_t* __restrict__ tmp, size_t slot_stride,
-              uint32_t* __restrict__ seg_bytes, const gj_dev_enc_tables* __restrict__ tables)
+              uint32_t* __restrict__ seg_bytes, uint32_t* __restrict__ spill_all, const gj_dev_enc_tables* __restrict__ tables)
 {
     extern __shared__ __align__(16) uint32_t he_smem[];
     uint32_t (*s_ac)[256] = reinterpret_cast<uint32_t (*)[256]>(he_smem);
@@ -151,6 +153,7 @@ k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzm
     const int nblocks = mcus * cps;
     uint32_t* buf = s_buf + warp * HE_WORDS;
     uint32_t* priv = s_priv + (warp * 32 + lane) * HE_PRIV;
+    uint32_t* spill = spill_all + ((size_t)g * 32 + lane) * HE_SPILL;   // touched only by blocks longer than HE_PRIV words
     uint8_t* out = tmp + (size_t)g * slot_stride;
     uint32_t out_pos = 0;
     int carry = 0;  // bits already sitting in buf[0] (always < 32 between rounds)
@@ -160,6 +163,19 @@ k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzm
     __syncwarp();
 
     int prev_dc = 0;  // DC of the same component's previous block, valid in lanes < cps at round start
+    /* mask and DC of a round are fetched one round ahead: their latency hides behind the previous round */
+    uint64_t nz_next = 0;
+    int dc_next = 0;
+    {
+        const int j = lane;
+        if ( j < nblocks ) {
+            const int mcu = cps == 1 ? j : j / cps;
+            const int comp = cps == 1 ? scan : j - mcu * cps;
+            const size_t bi = (size_t)comp * nblk + first_mcu + mcu;
+            nz_next = __ldg(nzmask + bi);
+            dc_next = __ldg(coef + bi * 64);
+        }
+    }
     for ( int base = 0; base < nblocks; base += 32 ) {
         const int j = base + lane;
         const bool active = j < nblocks;
@@ -171,11 +187,19 @@ k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzm
         const size_t bi = (size_t)comp * nblk + first_mcu + mcu;
         const int16_t* blk = coef + bi * 64;
 
-        uint64_t nz = 0;
-        int dc = 0;
-        if ( active ) {
-            nz = __ldg(nzmask + bi);
-            dc = __ldg(blk);
+        const uint64_t nz = nz_next;
+        const int dc = dc_next;
+        nz_next = 0;
+        dc_next = 0;
+        {
+            const int jn = j + 32;
+            if ( jn < nblocks ) {
+                const int mcun = cps == 1 ? jn : jn / cps;
+                const int compn = cps == 1 ? scan : jn - mcun * cps;
+                const size_t bn = (size_t)compn * nblk + first_mcu + mcun;
+                nz_next = __ldg(nzmask + bn);
+                dc_next = __ldg(coef + bn * 64);
+            }
         }
         /* DC predictor: previous block of the same component inside the segment, 0 at its start
          * [ref: src/gpujpeg_huffman_cpu_encoder.c:147-148, 361-364] */
@@ -194,7 +218,10 @@ k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzm
         acc = (acc << (len_)) | (uint64_t)(bits_);                 \
         nb += (len_);                                              \
         if ( nb >= 32 ) {                                          \
-            priv[wi++] = (uint32_t)(acc >> (nb - 32));             \
+            const uint32_t w_ = (uint32_t)(acc >> (nb - 32));      \
+            if ( wi < HE_PRIV ) priv[wi] = w_;                     \
+            else spill[wi - HE_PRIV] = w_;                         \
+            wi++;                                                  \
             nb -= 32;                                              \
         }                                                          \
     } while ( 0 )
@@ -225,7 +252,11 @@ k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzm
                 GJ_PUT(e >> 5, (int)(e & 31u));
             }
 #undef GJ_PUT
-            if ( nb ) priv[wi] = (uint32_t)(acc << (32 - nb));   // left-aligned tail, low bits zero
+            if ( nb ) {   // left-aligned tail, low bits zero
+                const uint32_t w_ = (uint32_t)(acc << (32 - nb));
+                if ( wi < HE_PRIV ) priv[wi] = w_;
+                else spill[wi - HE_PRIV] = w_;
+            }
             len = 32 * wi + nb;
         }
         const int incl = warp_incl_scan(len, lane);
@@ -246,7 +277,7 @@ k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzm
                 const int endbit = mypos + len;
                 uint32_t prev = 0;
                 for ( int q = 0; q <= nw; q++ ) {
-                    const uint32_t w = q < nw ? priv[q] : 0u;
+                    const uint32_t w = q < nw ? (q < HE_PRIV ? priv[q] : spill[q - HE_PRIV]) : 0u;
                     const uint32_t o = sh ? (prev | (w >> sh)) : w;
                     prev = sh ? (w << (32 - sh)) : 0u;
                     const int d = d0 + q;
@@ -657,7 +688,7 @@ extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_str
     }
     k_huff_encode<<<(seg_count + HE_WARPS - 1) / HE_WARPS, HE_WARPS * 32, HE_SMEM, stream>>>(
         a->d_coef, a->d_nzmask, a->nblk, a->comps_per_scan, a->seg_mcu, a->seg_per_scan, seg_count, a->d_tmp, a->slot_stride,
-        a->d_seg_bytes, a->d_tables);
+        a->d_seg_bytes, a->d_spill, a->d_tables);
     k_huff_offsets<<<1, OFF_THREADS, 0, stream>>>(a->d_seg_bytes, seg_count, a->seg_per_scan, a->header_size, a->sos_len,
                                                   (uint64_t)a->stream_cap, a->d_seg_off, a->d_info);
     k_huff_compact<<<(seg_count + 7) / 8, 256, 0, stream>>>(a->d_tmp, a->slot_stride, a->d_seg_bytes, a->d_seg_off,

@@ -165,6 +165,7 @@ struct gj_huff_enc_args {
     int nblk, comp_count, comps_per_scan, seg_mcu, seg_per_scan, scan_count;
     uint8_t* d_tmp;
     size_t slot_stride;
+    uint32_t* d_spill;      /* [seg_count][32 lanes][32 words]: overflow of the per-lane bit strings (rarely touched) */
     uint32_t* d_seg_bytes;  /* [seg_count] */
     uint64_t* d_seg_off;    /* [seg_count] */
     uint8_t* d_stream;
