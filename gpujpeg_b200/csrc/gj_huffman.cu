@@ -51,39 +51,6 @@ constexpr int HE_WARPS = 8;
 constexpr int HE_WORDS = 512;                    // per-warp bit buffer, 32-bit words (2 KB)
 constexpr int HE_CAP_BITS = (HE_WORDS - 2) * 32; // keep slack for the trailing partial word
 
-struct BitSink {
-    uint32_t* buf;   // warp's bit buffer: word i holds stream bits [32i, 32i+32), MSB first
-    int word;        // current word index
-    uint64_t acc;    // pending bits, right aligned (upper bits are stale and ignored)
-    int n;           // number of pending bits, < 32 between calls
-    bool first;      // next flushed word is shared with the preceding lane
-};
-
-__device__ __forceinline__ void sink_put(BitSink& s, uint32_t bits, int len)
-{
-    s.acc = (s.acc << len) | bits;
-    s.n += len;
-    if ( s.n >= 32 ) {
-        const uint32_t w = (uint32_t)(s.acc >> (s.n - 32));
-        if ( s.first ) {
-            atomicOr(&s.buf[s.word], w);
-            s.first = false;
-        }
-        else {
-            s.buf[s.word] = w;
-        }
-        s.word++;
-        s.n -= 32;
-    }
-}
-__device__ __forceinline__ void sink_finish(BitSink& s)
-{
-    if ( s.n > 0 ) {
-        const uint32_t w = (uint32_t)(s.acc << (32 - s.n));  // left-align the tail
-        atomicOr(&s.buf[s.word], w);
-    }
-}
-
 /* stuff + store `nw` complete words of the bit buffer to out[pos...]; returns new pos (uniform) */
 __device__ __forceinline__ uint32_t flush_words(const uint32_t* buf, int nw, uint8_t* out, uint32_t pos, int lane)
 {
@@ -117,7 +84,9 @@ constexpr int HE_PRIV = 25;    // words of private bit string per lane kept in s
                                // conflict-free columns); 800 bits cover every block of ordinary content
 constexpr int HE_SPILL = 32;   // further words per lane in global memory: an 8x8 block never needs more than
                                // 54 words in total (64 x (16-bit code + 11 value bits))
-constexpr int HE_SMEM = (2 * 256 + 2 * 16 + HE_WARPS * HE_WORDS + HE_WARPS * 32 * HE_PRIV) * 4;
+constexpr int HE_HEAD = 12;    // words per lane holding the first 16 coefficients of its block (8 used; the 48-byte
+                               // stride keeps the lanes' 16-byte stores on distinct bank groups)
+constexpr int HE_SMEM = (2 * 256 + 2 * 16 + HE_WARPS * HE_WORDS + HE_WARPS * 32 * HE_PRIV + HE_WARPS * 32 * HE_HEAD) * 4;
 
 /* One WARP per restart segment, one LANE per 8x8 block, ONE pass per block:
  *   1. the lane walks the set bits of the block's non-zero mask (written by K1 next to the coefficients),
@@ -138,6 +107,7 @@ k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzm
     uint32_t (*s_dc)[16] = reinterpret_cast<uint32_t (*)[16]>(he_smem + 512);
     uint32_t* s_buf = he_smem + 512 + 32;
     uint32_t* s_priv = s_buf + HE_WARPS * HE_WORDS;
+    uint32_t* s_head = s_priv + HE_WARPS * 32 * HE_PRIV;   // 16-byte aligned: all region sizes are multiples of 4 words
 
     for ( int i = threadIdx.x; i < 512; i += blockDim.x )
         s_ac[i >> 8][i & 255] = tables->lut[i >> 8].ac[i & 255];
@@ -154,6 +124,8 @@ k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzm
     uint32_t* buf = s_buf + warp * HE_WORDS;
     uint32_t* priv = s_priv + (warp * 32 + lane) * HE_PRIV;
     uint32_t* spill = spill_all + ((size_t)g * 32 + lane) * HE_SPILL;   // touched only by blocks longer than HE_PRIV words
+    uint32_t* head = s_head + (warp * 32 + lane) * HE_HEAD;
+    const int16_t* head16 = reinterpret_cast<const int16_t*>(head);
     uint8_t* out = tmp + (size_t)g * slot_stride;
     uint32_t out_pos = 0;
     int carry = 0;  // bits already sitting in buf[0] (always < 32 between rounds)
@@ -163,9 +135,11 @@ k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzm
     __syncwarp();
 
     int prev_dc = 0;  // DC of the same component's previous block, valid in lanes < cps at round start
-    /* mask and DC of a round are fetched one round ahead: their latency hides behind the previous round */
+    /* mask and the first 16 coefficients (one 32-byte sector: DC + the low frequencies, where nearly all
+     * non-zeros of photographic content live) are fetched one round ahead: their latency hides behind the
+     * previous round; the value loads were the largest stall of the single-pass kernel (ncu r1_h: 18 %) */
     uint64_t nz_next = 0;
-    int dc_next = 0;
+    uint4 ha_next = make_uint4(0u, 0u, 0u, 0u), hb_next = ha_next;
     {
         const int j = lane;
         if ( j < nblocks ) {
@@ -173,7 +147,8 @@ k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzm
             const int comp = cps == 1 ? scan : j - mcu * cps;
             const size_t bi = (size_t)comp * nblk + first_mcu + mcu;
             nz_next = __ldg(nzmask + bi);
-            dc_next = __ldg(coef + bi * 64);
+            ha_next = __ldg(reinterpret_cast<const uint4*>(coef + bi * 64));
+            hb_next = __ldg(reinterpret_cast<const uint4*>(coef + bi * 64) + 1);
         }
     }
     for ( int base = 0; base < nblocks; base += 32 ) {
@@ -188,9 +163,11 @@ k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzm
         const int16_t* blk = coef + bi * 64;
 
         const uint64_t nz = nz_next;
-        const int dc = dc_next;
+        const int dc = (int)(short)(ha_next.x & 0xFFFFu);
+        reinterpret_cast<uint4*>(head)[0] = ha_next;   // only this lane reads its head: no barrier needed
+        reinterpret_cast<uint4*>(head)[1] = hb_next;
         nz_next = 0;
-        dc_next = 0;
+        ha_next = hb_next = make_uint4(0u, 0u, 0u, 0u);
         {
             const int jn = j + 32;
             if ( jn < nblocks ) {
@@ -198,7 +175,8 @@ k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzm
                 const int compn = cps == 1 ? scan : jn - mcun * cps;
                 const size_t bn = (size_t)compn * nblk + first_mcu + mcun;
                 nz_next = __ldg(nzmask + bn);
-                dc_next = __ldg(coef + bn * 64);
+                ha_next = __ldg(reinterpret_cast<const uint4*>(coef + bn * 64));
+                hb_next = __ldg(reinterpret_cast<const uint4*>(coef + bn * 64) + 1);
             }
         }
         /* DC predictor: previous block of the same component inside the segment, 0 at its start
@@ -238,7 +216,7 @@ k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzm
                 else { k = 32 + __ffs((int)mhi) - 1; mhi &= mhi - 1; }
                 int run = k - last - 1;
                 last = k;
-                const int v = __ldg(blk + k);
+                const int v = k < 16 ? (int)head16[k] : (int)__ldg(blk + k);
                 const int size = gj_category(v);
                 while ( run > 15 ) {
                     GJ_PUT(zrl >> 5, (int)(zrl & 31u));
@@ -321,78 +299,75 @@ k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzm
     }
 }
 
-/* exclusive scan over segment sizes -> byte offsets in the finished stream.  One CTA walks the array in
- * tiles of 8192 segments: coalesced 32-byte loads per thread, shuffle scans, one smem hop per tile. */
+/* exclusive scan over segment sizes -> byte offsets in the finished stream.  A single CTA walking the
+ * array is a chain of dependent memory latencies (measured 23-30 us for the 43 200 segments of an 8K frame),
+ * so the array is cut into one chunk per CTA; a CTA first adds up everything in front of its chunk
+ * (independent coalesced loads of an array that sits in L2 -- redundant between CTAs, but only
+ * grid * n / 2 four-byte reads) and then scans its own chunk in tiles of 1024.  The grid is capped at the SM
+ * count, so the redundant part stays O(148 n).  Deterministic order (the reference's atomicAdd compaction
+ * is not). */
 constexpr int OFF_THREADS = 1024;
-constexpr int OFF_PER = 8;
+__device__ __forceinline__ uint32_t seg_stream_size(uint32_t bytes, int s, int seg_per_scan, int sos_len)
+{
+    /* a segment as it appears in the stream: [SOS header] bytes [RSTn] */
+    return bytes + (s == 0 ? (uint32_t)sos_len : 0u) + (s + 1 < seg_per_scan ? 2u : 0u);
+}
 __global__ void __launch_bounds__(OFF_THREADS)
-k_huff_offsets(const uint32_t* __restrict__ seg_bytes, int seg_count, int seg_per_scan, uint32_t header_size, int sos_len,
-               uint64_t stream_cap, uint64_t* __restrict__ seg_off, uint64_t* __restrict__ info)
+k_huff_offsets(const uint32_t* __restrict__ seg_bytes, int seg_count, int seg_per_scan, int chunk, uint32_t header_size,
+               int sos_len, uint64_t stream_cap, uint64_t* __restrict__ seg_off, uint64_t* __restrict__ info)
 {
     __shared__ uint64_t s_warp[32];
+    __shared__ uint32_t s_tile[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint64_t carry = header_size;   // stream offset where the current tile starts (uniform)
-    for ( int tile0 = 0; tile0 < seg_count; tile0 += OFF_THREADS * OFF_PER ) {
-        const int g0 = tile0 + threadIdx.x * OFF_PER;
-        uint32_t v[OFF_PER];
-        if ( g0 + OFF_PER <= seg_count ) {
-            const uint4 a = reinterpret_cast<const uint4*>(seg_bytes + g0)[0];
-            const uint4 b = reinterpret_cast<const uint4*>(seg_bytes + g0)[1];
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        }
-        else {
+    const int begin = blockIdx.x * chunk, end = min(seg_count, begin + chunk);
+
+    /* everything in front of the chunk: entropy bytes summed with 16-byte loads (begin is a multiple of 1024,
+     * cudaMalloc aligns the array), the SOS headers and RSTn markers in closed form */
+    uint64_t sum = 0;
+    const uint4* v4 = reinterpret_cast<const uint4*>(seg_bytes);
+#pragma unroll 4
+    for ( int q = threadIdx.x; q < begin / 4; q += OFF_THREADS ) {
+        const uint4 t = __ldg(v4 + q);
+        sum += (uint64_t)t.x + t.y + t.z + t.w;
+    }
 #pragma unroll
-            for ( int i = 0; i < OFF_PER; i++ )
-                v[i] = g0 + i < seg_count ? seg_bytes[g0 + i] : 0u;
-        }
-        /* size of every segment as it appears in the stream: [SOS header] bytes [RSTn] */
-        int s = g0 < seg_count ? g0 % seg_per_scan : 0;
-        uint32_t pre[OFF_PER];   // SOS bytes in front of the segment
-        uint32_t sum = 0;
-        uint32_t excl[OFF_PER];
+    for ( int d = 16; d > 0; d >>= 1 )
+        sum += __shfl_down_sync(FULL, sum, d);
+    if ( lane == 0 ) s_warp[warp] = sum;
+    __syncthreads();
+    const int full_scans = begin / seg_per_scan, rem = begin - full_scans * seg_per_scan;
+    uint64_t base = header_size + (uint64_t)(full_scans + (rem > 0)) * (uint64_t)sos_len +
+                    2ull * ((uint64_t)full_scans * (uint64_t)(seg_per_scan - 1) + (uint64_t)rem);
 #pragma unroll
-        for ( int i = 0; i < OFF_PER; i++ ) {
-            const bool valid = g0 + i < seg_count;
-            pre[i] = valid && s == 0 ? (uint32_t)sos_len : 0u;
-            excl[i] = sum + pre[i];
-            sum += pre[i] + v[i] + (valid && s + 1 < seg_per_scan ? 2u : 0u);
-            if ( ++s == seg_per_scan ) s = 0;
-        }
-        uint64_t incl = sum;
+    for ( int w = 0; w < 32; w++ )
+        base += s_warp[w];
+
+    for ( int t0 = begin; t0 < end; t0 += OFF_THREADS ) {
+        const int g = t0 + threadIdx.x;
+        const int s = g % seg_per_scan;
+        const uint32_t v = g < end ? seg_stream_size(__ldg(seg_bytes + g), s, seg_per_scan, sos_len) : 0u;
+        uint32_t incl = v;
 #pragma unroll
         for ( int d = 1; d < 32; d <<= 1 ) {
-            const uint64_t t = __shfl_up_sync(FULL, incl, d);
+            const uint32_t t = __shfl_up_sync(FULL, incl, d);
             if ( lane >= d ) incl += t;
         }
-        if ( lane == 31 ) s_warp[warp] = incl;
+        __syncthreads();   // s_tile of the previous tile fully consumed
+        if ( lane == 31 ) s_tile[warp] = incl;
         __syncthreads();
-        if ( warp == 0 ) {
-            uint64_t w = s_warp[lane];
+        uint32_t before = 0, tile_total = 0;
 #pragma unroll
-            for ( int d = 1; d < 32; d <<= 1 ) {
-                const uint64_t t = __shfl_up_sync(FULL, w, d);
-                if ( lane >= d ) w += t;
-            }
-            s_warp[lane] = w;   // inclusive prefix over warps
+        for ( int w = 0; w < 32; w++ ) {
+            const uint32_t t = s_tile[w];
+            if ( w < warp ) before += t;
+            tile_total += t;
         }
-        __syncthreads();
-        const uint64_t base = carry + (warp ? s_warp[warp - 1] : 0) + (incl - sum);
-        if ( g0 + OFF_PER <= seg_count ) {
-            ulonglong2* o = reinterpret_cast<ulonglong2*>(seg_off + g0);
-#pragma unroll
-            for ( int i = 0; i < OFF_PER; i += 2 )
-                o[i >> 1] = make_ulonglong2(base + excl[i], base + excl[i + 1]);
-        }
-        else {
-#pragma unroll
-            for ( int i = 0; i < OFF_PER; i++ )
-                if ( g0 + i < seg_count ) seg_off[g0 + i] = base + excl[i];
-        }
-        carry += s_warp[31];
-        __syncthreads();
+        /* the segment's bytes start after its SOS header (if any) */
+        if ( g < end ) seg_off[g] = base + before + (incl - v) + (s == 0 ? (uint32_t)sos_len : 0u);
+        base += tile_total;
     }
-    if ( threadIdx.x == 0 ) {
-        const uint64_t total = carry + 2;  // + EOI
+    if ( end == seg_count && threadIdx.x == 0 ) {
+        const uint64_t total = base + 2;  // + EOI
         info[0] = total;
         info[1] = total > stream_cap ? 1 : 0;
     }
@@ -689,7 +664,11 @@ extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_str
     k_huff_encode<<<(seg_count + HE_WARPS - 1) / HE_WARPS, HE_WARPS * 32, HE_SMEM, stream>>>(
         a->d_coef, a->d_nzmask, a->nblk, a->comps_per_scan, a->seg_mcu, a->seg_per_scan, seg_count, a->d_tmp, a->slot_stride,
         a->d_seg_bytes, a->d_spill, a->d_tables);
-    k_huff_offsets<<<1, OFF_THREADS, 0, stream>>>(a->d_seg_bytes, seg_count, a->seg_per_scan, a->header_size, a->sos_len,
+    /* one chunk (a multiple of the 1024-segment tile) per CTA, at most one CTA per SM */
+    int off_chunk = (seg_count + 147) / 148;
+    off_chunk = ((off_chunk + OFF_THREADS - 1) / OFF_THREADS) * OFF_THREADS;
+    const int off_grid = (seg_count + off_chunk - 1) / off_chunk;
+    k_huff_offsets<<<off_grid, OFF_THREADS, 0, stream>>>(a->d_seg_bytes, seg_count, a->seg_per_scan, off_chunk, a->header_size, a->sos_len,
                                                   (uint64_t)a->stream_cap, a->d_seg_off, a->d_info);
     k_huff_compact<<<(seg_count + 7) / 8, 256, 0, stream>>>(a->d_tmp, a->slot_stride, a->d_seg_bytes, a->d_seg_off,
                                                             seg_count, a->seg_per_scan, a->d_sos, a->sos_len,
