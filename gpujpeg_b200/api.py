@@ -76,6 +76,7 @@ def _load():
         "gpujpeg_init_device": (ci, [ci, ci]),
         "gpujpeg_set_default_parameters": (None, [C.POINTER(Parameters)]),
         "gpujpeg_image_set_default_parameters": (None, [C.POINTER(ImageParameters)]),
+        "gpujpeg_parameters_chroma_subsampling": (None, [C.POINTER(Parameters), C.c_uint32]),
         "gpujpeg_image_calculate_size": (cs, [C.POINTER(ImageParameters)]),
         "gpujpeg_image_load_from_file": (ci, [C.c_char_p, C.POINTER(vp), C.POINTER(cs)]),
         "gpujpeg_image_destroy": (ci, [vp]),
@@ -111,11 +112,33 @@ def version():
     return lib.gpujpeg_version_to_string(lib.gpujpeg_version()).decode()
 
 
-def default_parameters(quality=75, restart_interval=RESTART_AUTO, interleaved=0):
+SUBSAMPLING = {"4:4:4": (1, 1), "4:2:2": (2, 1), "4:2:0": (2, 2), "4:4:0": (1, 2)}
+
+
+def default_parameters(quality=75, restart_interval=RESTART_AUTO, interleaved=0, subsampling="4:4:4"):
+    """subsampling: a J:a:b name or the luminance sampling factors (h, v); chrominance is 1x1
+    (what gpujpeg_parameters_chroma_subsampling(param, GPUJPEG_SUBSAMPLING_xxx) sets)."""
     p = Parameters()
     lib.gpujpeg_set_default_parameters(C.byref(p))
     p.quality, p.restart_interval, p.interleaved = quality, restart_interval, interleaved
+    lh, lv = SUBSAMPLING[subsampling] if isinstance(subsampling, str) else subsampling
+    if (lh, lv) != (1, 1):   # GPUJPEG_SUBSAMPLING_xxx packing: one nibble pair per component, first component on top
+        lib.gpujpeg_parameters_chroma_subsampling(C.byref(p), lh << 28 | lv << 24 | 0x111100)
     return p
+
+
+def coefficient_count(width, height, sampling=(1, 1), interleaved=0):
+    """int16 coefficients the coder keeps for a 3-component frame [ref: src/gpujpeg_common.c:671-736]"""
+    mh, mv = sampling
+    n = 0
+    for c in range(3):
+        hs, vs = (mh, mv) if c == 0 else (1, 1)
+        dh_, dv_ = mh // hs, mv // vs
+        cw = (width + dh_ - 1) // dh_ * dh_ * hs // mh
+        ch = (height + dv_ - 1) // dv_ * dv_ * vs // mv
+        mx, my = (8 * hs, 8 * vs) if interleaved else (8, 8)
+        n += ((cw + mx - 1) // mx * mx) * ((ch + my - 1) // my * my)
+    return n
 
 
 def image_parameters(width, height, width_padding=0):
@@ -166,11 +189,11 @@ class Encoder:
         return out.value, size.value
 
     def encode(self, image, quality=75, restart_interval=RESTART_AUTO, interleaved=0, width=None, height=None,
-               width_padding=0, verbose=0):
+               width_padding=0, verbose=0, subsampling="4:4:4"):
         """image: HxWx3 uint8 numpy array / torch tensor (host or cuda).  Returns the JPEG as numpy uint8 (a copy)."""
         if width is None:
             height, width = image.shape[0], image.shape[1]
-        p = default_parameters(quality, restart_interval, interleaved)
+        p = default_parameters(quality, restart_interval, interleaved, subsampling)
         p.verbose = verbose
         addr, size = self.encode_raw(image, p, image_parameters(width, height, width_padding))
         return np.ctypeslib.as_array((C.c_uint8 * size).from_address(addr)).copy()
@@ -181,10 +204,14 @@ class Encoder:
         if lib.gpujpegx_encoder_run_resident(self._h, addr, stage_mask) != 0:
             raise GpuJpegError("gpujpegx_encoder_run_resident failed")
 
-    def coefficients(self, width, height):
-        """quantised coefficients of the last frame: (3, blocks*64) int16, natural order (parity tests)"""
-        dw, dh = (width + 7) // 8 * 8, (height + 7) // 8 * 8
-        out = np.empty((3, dw * dh), np.int16)
+    def coefficients(self, width, height, sampling=(1, 1), interleaved=0):
+        """quantised coefficients of the last frame, natural order (parity tests): (3, blocks*64) int16 for 4:4:4,
+        one flat array, component after component, for the subsampled modes"""
+        if tuple(sampling) == (1, 1):
+            dw, dh = (width + 7) // 8 * 8, (height + 7) // 8 * 8
+            out = np.empty((3, dw * dh), np.int16)
+        else:
+            out = np.empty(coefficient_count(width, height, sampling, interleaved), np.int16)
         if lib.gpujpegx_encoder_get_coefficients(self._h, out.ctypes.data, out.size) != 0:
             raise GpuJpegError("gpujpegx_encoder_get_coefficients failed")
         return out
@@ -243,11 +270,14 @@ class Decoder:
         if lib.gpujpegx_decoder_run_resident(self._h, addr, stage_mask) != 0:
             raise GpuJpegError("gpujpegx_decoder_run_resident failed")
 
-    def coefficients(self, width, height):
+    def coefficients(self, width, height, sampling=(1, 1), interleaved=0):
         """coefficients of the last frame, natural order: (array, dequantized) -- with the integer IDCT flavour
         the Huffman decoder already stores coefficient*quantiser wrapped to int16 (dequantized = True)"""
-        dw, dh = (width + 7) // 8 * 8, (height + 7) // 8 * 8
-        out = np.empty((3, dw * dh), np.int16)
+        if tuple(sampling) == (1, 1):
+            dw, dh = (width + 7) // 8 * 8, (height + 7) // 8 * 8
+            out = np.empty((3, dw * dh), np.int16)
+        else:
+            out = np.empty(coefficient_count(width, height, sampling, interleaved), np.int16)
         rc = lib.gpujpegx_decoder_get_coefficients(self._h, out.ctypes.data, out.size)
         if rc < 0:
             raise GpuJpegError("gpujpegx_decoder_get_coefficients failed")

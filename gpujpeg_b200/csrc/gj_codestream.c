@@ -24,20 +24,98 @@ int gj_geometry_init(struct gj_geometry* g, const struct gpujpeg_parameters* par
     g->pitch = 3 * pi->width + pi->width_padding;
     g->data_width = (pi->width + 7) / 8 * 8;
     g->data_height = (pi->height + 7) / 8 * 8;
-    g->bcx = g->data_width / 8;
-    g->bcy = g->data_height / 8;
-    g->nblk = g->bcx * g->bcy;
     g->interleaved = param->interleaved && param->comp_count > 1;
     g->restart_interval = param->restart_interval;
-    g->seg_mcu = param->restart_interval > 0 ? param->restart_interval : g->nblk;
     g->scan_count = g->interleaved ? 1 : g->comp_count;
     g->comps_per_scan = g->interleaved ? g->comp_count : 1;
-    g->seg_per_scan = (g->nblk + g->seg_mcu - 1) / g->seg_mcu;
-    g->seg_count = g->scan_count * g->seg_per_scan;
+
+    /* component planes [ref: src/gpujpeg_common.c:671-736]: a component with sampling factor h of maximum H has
+     * ceil(W / (H/h)) samples per row; its block grid is padded to 8 samples, in an interleaved scan to whole MCUs */
+    struct gj_scan_layout* l = &g->lay;
+    g->max_hs = g->max_vs = 1;
+    for ( int c = 0; c < g->comp_count; c++ ) {
+        int hs = param->sampling_factor[c].horizontal, vs = param->sampling_factor[c].vertical;
+        if ( hs < 1 ) hs = 1;
+        if ( vs < 1 ) vs = 1;
+        g->comp[c].hs = hs;
+        g->comp[c].vs = vs;
+        if ( hs > g->max_hs ) g->max_hs = hs;
+        if ( vs > g->max_vs ) g->max_vs = vs;
+    }
+    int off = 0;
+    l->simple = 1;
+    for ( int c = 0; c < g->comp_count; c++ ) {
+        struct gj_comp_geo* k = &g->comp[c];
+        const int div_h = g->max_hs / k->hs, div_v = g->max_vs / k->vs;
+        k->width = ((pi->width + div_h - 1) / div_h * div_h) * k->hs / g->max_hs;
+        k->height = ((pi->height + div_v - 1) / div_v * div_v) * k->vs / g->max_vs;
+        const int mx = g->interleaved ? 8 * k->hs : 8, my = g->interleaved ? 8 * k->vs : 8;
+        k->bcx = (k->width + mx - 1) / mx * (mx / 8);
+        k->bcy = (k->height + my - 1) / my * (my / 8);
+        k->nblk = k->bcx * k->bcy;
+        k->blk_off = off;
+        off += k->nblk;
+        if ( k->hs != 1 || k->vs != 1 ) l->simple = 0;
+        if ( div_h != 1 || div_v != 1 ) g->subsampled = 1;
+        l->blk_off[c] = k->blk_off;
+        l->bcx[c] = k->bcx;
+        l->comp_hs[c] = (uint8_t)k->hs;
+        l->comp_vs[c] = (uint8_t)k->vs;
+    }
+    g->bcx = g->comp[0].bcx;
+    g->bcy = g->comp[0].bcy;
+    g->nblk = g->comp[0].nblk;
+    g->coef_count = (size_t)off * 64;
+
+    /* scans, MCUs and restart segments [ref: src/gpujpeg_common.c:738-866] */
+    l->interleaved = g->interleaved;
+    l->comp_count = g->comp_count;
+    l->scan_count = g->scan_count;
+    l->bpm = 1;
+    int max_mcus = 0;
+    if ( g->interleaved ) {
+        l->mcu_x = g->comp[0].bcx / g->comp[0].hs;
+        l->scan_mcus[0] = l->mcu_x * (g->comp[0].bcy / g->comp[0].vs);
+        int n = 0;
+        for ( int c = 0; c < g->comp_count; c++ ) {
+            const int per = g->comp[c].hs * g->comp[c].vs;
+            for ( int y = 0; y < g->comp[c].vs; y++ )
+                for ( int x = 0; x < g->comp[c].hs; x++, n++ ) {
+                    if ( n >= GJ_MAX_MCU_BLOCKS ) return -1;
+                    l->idx_comp[n] = (uint8_t)c;
+                    l->idx_dx[n] = (uint8_t)x;
+                    l->idx_dy[n] = (uint8_t)y;
+                    /* previous block of the same component: the neighbour inside the MCU, or the last
+                     * block of this component in the previous MCU */
+                    l->idx_pred[n] = (uint8_t)((x | y) ? 1 : 0);
+                }
+            (void)per;
+        }
+        l->bpm = n;
+        for ( int i = 0; i < n; i++ )
+            if ( l->idx_pred[i] == 0 ) {
+                const int c = l->idx_comp[i];
+                l->idx_pred[i] = (uint8_t)(n - (g->comp[c].hs * g->comp[c].vs - 1));
+            }
+        max_mcus = l->scan_mcus[0];
+    }
+    else {
+        for ( int c = 0; c < g->comp_count; c++ ) {
+            l->scan_mcus[c] = g->comp[c].nblk;
+            if ( g->comp[c].nblk > max_mcus ) max_mcus = g->comp[c].nblk;
+        }
+    }
+    g->seg_mcu = param->restart_interval > 0 ? param->restart_interval : max_mcus;
+    int segs = 0;
+    for ( int k = 0; k <= GJ_MAX_COMP; k++ ) {
+        l->scan_seg_begin[k] = segs;
+        if ( k < g->scan_count ) segs += (l->scan_mcus[k] + g->seg_mcu - 1) / g->seg_mcu;
+    }
+    g->seg_count = segs;
+    g->seg_per_scan = l->scan_seg_begin[1];
     g->raw_size = (size_t)g->pitch * pi->height;
-    g->coef_count = (size_t)g->comp_count * g->nblk * 64;
     /* worst case per 8x8 block: 64 x (16-bit code + 11 value bits) < 208 bytes, doubled by stuffing */
-    g->slot_stride = ((size_t)g->seg_mcu * g->comps_per_scan * 416 + 2 + 127) / 128 * 128;
+    g->slot_stride = ((size_t)g->seg_mcu * (g->interleaved ? l->bpm : 1) * 416 + 2 + 127) / 128 * 128;
     /* same budget as the reference's output buffer [ref: src/gpujpeg_writer.c:63-89] */
     g->stream_cap = 4096 + (size_t)pi->width * pi->height * g->comp_count * 2;
     return 0;

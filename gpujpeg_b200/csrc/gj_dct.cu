@@ -173,6 +173,153 @@ k_fdct_rgb444(const uint8_t* __restrict__ raw, int width, int height, size_t pit
         dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
 }
 
+/* ------------------------------------------------------------------------------------------- */
+/* K1 with chroma subsampling: luminance sampling factors HS x VS in {1,2}, chrominance 1x1.
+ * A CTA owns one MCU row of a 512-pixel strip: 8*VS pixel rows = 64*VS luminance blocks plus 64/HS blocks of
+ * each chrominance component, one thread per block in the transform phase (4:2:0: 128 + 32 + 32 = 192 threads,
+ * the same shape as the 4:4:4 kernel).  Chrominance keeps the sample of every HS-th pixel of every VS-th row,
+ * unfiltered, exactly as the reference's preprocessor [ref: src/gpujpeg_preprocessor.cu:50-64]; samples and
+ * blocks outside the image are 0 [ref: src/gpujpeg_common.c:941-944]. */
+struct SsGrid {
+    int bcx[3], bcy[3], blk_off[3];
+};
+
+template <int HS, int VS, int VEC>
+__global__ void __launch_bounds__(TB * VS + 2 * TB / HS)
+k_fdct_rgb_ss(const uint8_t* __restrict__ raw, int width, int height, size_t pitch, int16_t* __restrict__ coef,
+              uint64_t* __restrict__ nzmask, const __grid_constant__ SsGrid grid, const __grid_constant__ FdctParams prm)
+{
+    constexpr int NTS = TB * VS + 2 * TB / HS;      // threads = blocks per strip
+    constexpr int CB = TB / HS;                      // chrominance blocks per component per strip
+    constexpr int ITERS = (GROUPS + NTS - 1) / NTS;
+    extern __shared__ __align__(16) uint8_t smem[];
+    float* s_y = reinterpret_cast<float*>(smem);                 // [VS][TB] blocks
+    float* s_c = s_y + VS * TB * BLK_F;                          // [2][CB] blocks
+
+    const int bx0 = blockIdx.x * TB;
+    const int x0 = bx0 * 8;
+    const int y0 = blockIdx.y * 8 * VS;
+    const int vw = min(STRIP_PX, width - x0);   // may be <= 0 for strips that only hold padding blocks
+    const uint8_t* src = raw + (size_t)y0 * pitch + (size_t)x0 * 3;
+
+#pragma unroll
+    for ( int half = 0; half < VS; half++ ) {
+        const int vh = min(8, height - y0 - half * 8);   // valid rows of this half (may be <= 0)
+        uint32_t w0[ITERS], w1[ITERS], w2[ITERS];
+#pragma unroll
+        for ( int it = 0; it < ITERS; it++ ) {
+            const int g = threadIdx.x + it * NTS;
+            const int row = g >> 7, gx = g & 127, px0 = gx * 4;
+            w0[it] = w1[it] = w2[it] = 0u;
+            if ( g < GROUPS && row < vh && px0 < vw ) {
+                const uint8_t* p = src + (size_t)(half * 8 + row) * pitch + gx * 12;
+                if ( VEC == 4 && px0 + 4 <= vw ) {
+                    const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
+                    w0[it] = __ldg(w);
+                    w1[it] = __ldg(w + 1);
+                    w2[it] = __ldg(w + 2);
+                }
+                else {
+                    const int nb = min(12, (vw - px0) * 3);
+                    uint32_t b[12];
+#pragma unroll
+                    for ( int i = 0; i < 12; i++ )
+                        b[i] = i < nb ? (uint32_t)__ldg(p + i) : 0u;
+                    w0[it] = b[0] | b[1] << 8 | b[2] << 16 | b[3] << 24;
+                    w1[it] = b[4] | b[5] << 8 | b[6] << 16 | b[7] << 24;
+                    w2[it] = b[8] | b[9] << 8 | b[10] << 16 | b[11] << 24;
+                }
+            }
+        }
+#pragma unroll
+        for ( int it = 0; it < ITERS; it++ ) {
+            const int g = threadIdx.x + it * NTS;
+            if ( g >= GROUPS ) break;
+            const int row = g >> 7, gx = g & 127, px0 = gx * 4;
+            float4 y4 = make_float4(0.f, 0.f, 0.f, 0.f), cb4 = y4, cr4 = y4;
+            if ( row < vh && px0 < vw ) {
+                const uint32_t a0 = w0[it], a1 = w1[it], a2 = w2[it];
+                gj_rgb_to_ycbcr_m(gj_byte_as_magic(a0, 0), gj_byte_as_magic(a0, 1), gj_byte_as_magic(a0, 2), y4.x, cb4.x, cr4.x);
+                gj_rgb_to_ycbcr_m(gj_byte_as_magic(a0, 3), gj_byte_as_magic(a1, 0), gj_byte_as_magic(a1, 1), y4.y, cb4.y, cr4.y);
+                gj_rgb_to_ycbcr_m(gj_byte_as_magic(a1, 2), gj_byte_as_magic(a1, 3), gj_byte_as_magic(a2, 0), y4.z, cb4.z, cr4.z);
+                gj_rgb_to_ycbcr_m(gj_byte_as_magic(a2, 1), gj_byte_as_magic(a2, 2), gj_byte_as_magic(a2, 3), y4.w, cb4.w, cr4.w);
+                if ( px0 + 4 > vw ) {
+                    if ( px0 + 1 >= vw ) { y4.y = cb4.y = cr4.y = 0.f; }
+                    if ( px0 + 2 >= vw ) { y4.z = cb4.z = cr4.z = 0.f; }
+                    if ( px0 + 3 >= vw ) { y4.w = cb4.w = cr4.w = 0.f; }
+                }
+            }
+            *reinterpret_cast<float4*>(s_y + (half * TB + (gx >> 1)) * BLK_F + row * 8 + (gx & 1) * 4) = y4;
+            const int srow = half * 8 + row;           // row inside the strip
+            if ( VS == 1 || (srow & 1) == 0 ) {
+                const int crow = srow / VS;
+                if ( HS == 1 ) {
+                    const int off = (gx >> 1) * BLK_F + crow * 8 + (gx & 1) * 4;
+                    *reinterpret_cast<float4*>(s_c + off) = cb4;
+                    *reinterpret_cast<float4*>(s_c + CB * BLK_F + off) = cr4;
+                }
+                else {
+                    const int off = (gx >> 2) * BLK_F + crow * 8 + (gx & 3) * 2;
+                    *reinterpret_cast<float2*>(s_c + off) = make_float2(cb4.x, cb4.z);
+                    *reinterpret_cast<float2*>(s_c + CB * BLK_F + off) = make_float2(cr4.x, cr4.z);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    /* phase B: one thread = one block */
+    int comp, bx, by, sblk;
+    if ( threadIdx.x < TB * VS ) {
+        comp = 0;
+        const int b = threadIdx.x & (TB - 1), byl = threadIdx.x / TB;
+        bx = bx0 + b;
+        by = blockIdx.y * VS + byl;
+        sblk = threadIdx.x;
+    }
+    else {
+        const int u = threadIdx.x - TB * VS;
+        comp = 1 + u / CB;
+        bx = bx0 / HS + u % CB;
+        by = blockIdx.y;
+        sblk = TB * VS + u;
+    }
+    if ( bx >= grid.bcx[comp] || by >= grid.bcy[comp] ) return;
+    float v[64];
+    {
+        const float4* in = reinterpret_cast<const float4*>(s_y + sblk * BLK_F);
+#pragma unroll
+        for ( int i = 0; i < 16; i++ ) {
+            const float4 t = in[i];
+            v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        }
+    }
+    gj_fdct_block(v);
+    const float* tab = prm.fwd_zz[comp == 0 ? 0 : 1];
+    uint32_t packed[32];
+    uint32_t mlo = 0, mhi = 0;
+#pragma unroll
+    for ( int k = 0; k < 64; k += 2 ) {
+        const int q0 = GJ_RINT(GJ_FMUL(v[gj_zz2nat(k)], tab[k]));
+        const int q1 = GJ_RINT(GJ_FMUL(v[gj_zz2nat(k + 1)], tab[k + 1]));
+        packed[k >> 1] = __byte_perm((uint32_t)q0, (uint32_t)q1, 0x5410);
+        if ( k < 32 ) {
+            if ( q0 ) mlo |= 1u << (k & 31);
+            if ( q1 ) mlo |= 1u << ((k + 1) & 31);
+        }
+        else {
+            if ( q0 ) mhi |= 1u << (k & 31);
+            if ( q1 ) mhi |= 1u << ((k + 1) & 31);
+        }
+    }
+    const size_t bi = (size_t)grid.blk_off[comp] + (size_t)by * grid.bcx[comp] + bx;
+    nzmask[bi] = (uint64_t)mhi << 32 | mlo;
+    uint4* dst = reinterpret_cast<uint4*>(coef + bi * 64);
+#pragma unroll
+    for ( int i = 0; i < 8; i++ )
+        dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+}
+
 /* =========================================================================================== */
 /* K4                                                                                            */
 
@@ -275,6 +422,129 @@ k_idct_rgb444(const int16_t* __restrict__ coef, int bcx, int nblk, uint8_t* __re
     }
 }
 
+/* K4 with chroma subsampling: the mirror image of k_fdct_rgb_ss.  Every pixel takes the chrominance sample at
+ * (x / HS, y / VS) -- sample replication, as the reference's postprocessor [ref: src/gpujpeg_postprocessor.cu:55-76]. */
+template <int HS, int VS, int VEC, int FLAVOUR, bool DEQ>
+__global__ void __launch_bounds__(TB * VS + 2 * TB / HS)
+k_idct_rgb_ss(const int16_t* __restrict__ coef, const __grid_constant__ SsGrid grid, uint8_t* __restrict__ raw, int width,
+              int height, size_t pitch, const __grid_constant__ IdctParams prm)
+{
+    constexpr int NTS = TB * VS + 2 * TB / HS;
+    constexpr int CB = TB / HS;
+    constexpr int CW = STRIP_PX / HS;                 // chrominance samples per strip row
+    __shared__ __align__(16) uint8_t s_y[8 * VS * STRIP_PX];
+    __shared__ __align__(16) uint8_t s_c[2][8 * CW];
+
+    const int bx0 = blockIdx.x * TB;
+    const int x0 = bx0 * 8;
+    const int y0 = blockIdx.y * 8 * VS;
+    const int vw = min(STRIP_PX, width - x0);
+    const int vh = min(8 * VS, height - y0);
+
+    {
+        int comp, bx, by;
+        uint8_t* dst;
+        int dpitch;
+        if ( threadIdx.x < TB * VS ) {
+            comp = 0;
+            const int b = threadIdx.x & (TB - 1), byl = threadIdx.x / TB;
+            bx = bx0 + b;
+            by = blockIdx.y * VS + byl;
+            dst = s_y + byl * 8 * STRIP_PX + b * 8;
+            dpitch = STRIP_PX;
+        }
+        else {
+            const int u = threadIdx.x - TB * VS;
+            comp = 1 + u / CB;
+            bx = bx0 / HS + u % CB;
+            by = blockIdx.y;
+            dst = s_c[comp - 1] + (u % CB) * 8;
+            dpitch = CW;
+        }
+        if ( bx < grid.bcx[comp] && by < grid.bcy[comp] ) {
+            const uint4* src =
+                reinterpret_cast<const uint4*>(coef + ((size_t)grid.blk_off[comp] + (size_t)by * grid.bcx[comp] + bx) * 64);
+            uint32_t packed[32];
+#pragma unroll
+            for ( int i = 0; i < 8; i++ ) {
+                const uint4 t = __ldg(src + i);
+                packed[4 * i] = t.x; packed[4 * i + 1] = t.y; packed[4 * i + 2] = t.z; packed[4 * i + 3] = t.w;
+            }
+            const uint16_t* q = prm.q_zz[comp];
+            uint32_t px[16];
+            if ( FLAVOUR == 0 ) {
+                int v[64];
+#pragma unroll
+                for ( int k = 0; k < 64; k++ ) {
+                    const int c = (k & 1) ? (int)packed[k >> 1] >> 16 : (int)(short)(packed[k >> 1] & 0xFFFFu);
+                    v[gj_zz2nat(k)] = DEQ ? gj_s16(c * (int)(short)q[k]) : c;
+                }
+                gj_idct_int_block_px(v);
+#pragma unroll
+                for ( int i = 0; i < 16; i++ )
+                    px[i] = pack4_sat_u8(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+            else {
+                float f[64];
+#pragma unroll
+                for ( int k = 0; k < 64; k++ ) {
+                    const int c = (k & 1) ? (int)packed[k >> 1] >> 16 : (int)(short)(packed[k >> 1] & 0xFFFFu);
+                    f[gj_zz2nat(k)] = (float)(c * (int)q[k]);
+                }
+                gj_idct_float_block(f);
+#pragma unroll
+                for ( int i = 0; i < 16; i++ )
+                    px[i] = pack4_sat_u8(GJ_RINT(GJ_FADD(f[4 * i], 128.0f)), GJ_RINT(GJ_FADD(f[4 * i + 1], 128.0f)),
+                                         GJ_RINT(GJ_FADD(f[4 * i + 2], 128.0f)), GJ_RINT(GJ_FADD(f[4 * i + 3], 128.0f)));
+            }
+#pragma unroll
+            for ( int r = 0; r < 8; r++ )
+                *reinterpret_cast<uint2*>(dst + r * dpitch) = make_uint2(px[2 * r], px[2 * r + 1]);
+        }
+    }
+    __syncthreads();
+
+    uint8_t* out = raw + (size_t)y0 * pitch + (size_t)x0 * 3;
+    for ( int g = threadIdx.x; g < GROUPS * VS; g += NTS ) {
+        const int row = g >> 7, gx = g & 127;
+        const int px0 = gx * 4;
+        if ( row >= vh || px0 >= vw ) continue;
+        const uint32_t yw = *reinterpret_cast<const uint32_t*>(s_y + row * STRIP_PX + px0);
+        uint32_t bw, rw;
+        if ( HS == 1 ) {
+            bw = *reinterpret_cast<const uint32_t*>(s_c[0] + (row / VS) * CW + px0);
+            rw = *reinterpret_cast<const uint32_t*>(s_c[1] + (row / VS) * CW + px0);
+        }
+        else {
+            const uint32_t b2 = *reinterpret_cast<const uint16_t*>(s_c[0] + (row / VS) * CW + px0 / 2);
+            const uint32_t r2 = *reinterpret_cast<const uint16_t*>(s_c[1] + (row / VS) * CW + px0 / 2);
+            bw = __byte_perm(b2, 0u, 0x1100);   // c0 c0 c1 c1
+            rw = __byte_perm(r2, 0u, 0x1100);
+        }
+        int r[4], gg[4], bb[4];
+#pragma unroll
+        for ( int j = 0; j < 4; j++ )
+            gj_ycbcr_to_rgb_raw((yw >> (8 * j)) & 0xFF, (bw >> (8 * j)) & 0xFF, (rw >> (8 * j)) & 0xFF, r[j], gg[j], bb[j]);
+        const uint32_t o0 = pack4_sat_u8(r[0], gg[0], bb[0], r[1]);
+        const uint32_t o1 = pack4_sat_u8(gg[1], bb[1], r[2], gg[2]);
+        const uint32_t o2 = pack4_sat_u8(bb[2], r[3], gg[3], bb[3]);
+        uint8_t* p = out + (size_t)row * pitch + gx * 12;
+        if ( VEC == 4 && px0 + 4 <= vw ) {
+            uint32_t* w = reinterpret_cast<uint32_t*>(p);
+            w[0] = o0;
+            w[1] = o1;
+            w[2] = o2;
+        }
+        else {
+            const int nb = min(12, (vw - px0) * 3);
+            const uint32_t o[3] = {o0, o1, o2};
+#pragma unroll
+            for ( int i = 0; i < 12; i++ )
+                if ( i < nb ) p[i] = (uint8_t)(o[i >> 2] >> (8 * (i & 3)));
+        }
+    }
+}
+
 int pick_vec(const void* p, size_t pitch)
 {
     const uintptr_t a = reinterpret_cast<uintptr_t>(p) | pitch;
@@ -330,5 +600,83 @@ extern "C" int gj_launch_idct_rgb444(const int16_t* d_coef, int bcx, int bcy, co
         if ( vec == 4 ) GJ_K4(4, 1, true); else GJ_K4(1, 1, true);
     }
 #undef GJ_K4
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+/* ---- subsampled variants: luminance hs x vs in {2x1, 2x2, 1x2}, chrominance 1x1 ---- */
+extern "C" int gj_launch_fdct_rgb_ss(const uint8_t* d_raw, int width, int height, int pitch, int16_t* d_coef,
+                                     uint64_t* d_nzmask, const struct gj_comp_geo comp[3],
+                                     const struct gj_dev_enc_tables* h_tables, gj_stream_t stream)
+{
+    FdctParams prm;
+    memcpy(prm.fwd_zz, h_tables->fwd_zz, sizeof prm.fwd_zz);
+    SsGrid sg;
+    for ( int c = 0; c < 3; c++ ) {
+        sg.bcx[c] = comp[c].bcx;
+        sg.bcy[c] = comp[c].bcy;
+        sg.blk_off[c] = comp[c].blk_off;
+    }
+    const int hs = comp[0].hs, vs = comp[0].vs;
+    if ( comp[1].hs != 1 || comp[1].vs != 1 || comp[2].hs != 1 || comp[2].vs != 1 ) return -1;
+    const dim3 grid((comp[0].bcx + TB - 1) / TB, (comp[0].bcy + vs - 1) / vs);
+    const int vec = pick_vec(d_raw, (size_t)pitch);
+#define GJ_K1SS(H, V)                                                                                                        \
+    do {                                                                                                                     \
+        constexpr int nt = TB * V + 2 * TB / H;                                                                              \
+        constexpr int sm = nt * BLK_F * 4;                                                                                   \
+        if ( cudaFuncSetAttribute(k_fdct_rgb_ss<H, V, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm) != cudaSuccess || \
+             cudaFuncSetAttribute(k_fdct_rgb_ss<H, V, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm) != cudaSuccess )  \
+            return -1;                                                                                                       \
+        if ( vec == 4 )                                                                                                      \
+            k_fdct_rgb_ss<H, V, 4><<<grid, nt, sm, stream>>>(d_raw, width, height, (size_t)pitch, d_coef, d_nzmask, sg, prm); \
+        else                                                                                                                 \
+            k_fdct_rgb_ss<H, V, 1><<<grid, nt, sm, stream>>>(d_raw, width, height, (size_t)pitch, d_coef, d_nzmask, sg, prm); \
+    } while ( 0 )
+    if ( hs == 2 && vs == 2 ) GJ_K1SS(2, 2);
+    else if ( hs == 2 && vs == 1 ) GJ_K1SS(2, 1);
+    else if ( hs == 1 && vs == 2 ) GJ_K1SS(1, 2);
+    else return -1;
+#undef GJ_K1SS
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+extern "C" int gj_launch_idct_rgb_ss(const int16_t* d_coef, const struct gj_comp_geo comp[3], const int comp_tq[3],
+                                     uint8_t* d_raw, int width, int height, int pitch, int idct_flavour,
+                                     int coef_dequantized, const struct gj_dev_dec_tables* h_tables, gj_stream_t stream)
+{
+    IdctParams prm;
+    for ( int c = 0; c < 3; c++ )
+        memcpy(prm.q_zz[c], h_tables->qinv_zz[comp_tq[c]], sizeof prm.q_zz[c]);
+    SsGrid sg;
+    for ( int c = 0; c < 3; c++ ) {
+        sg.bcx[c] = comp[c].bcx;
+        sg.bcy[c] = comp[c].bcy;
+        sg.blk_off[c] = comp[c].blk_off;
+    }
+    const int hs = comp[0].hs, vs = comp[0].vs;
+    if ( comp[1].hs != 1 || comp[1].vs != 1 || comp[2].hs != 1 || comp[2].vs != 1 ) return -1;
+    if ( idct_flavour != 0 && coef_dequantized ) return -1;
+    const dim3 grid((comp[0].bcx + TB - 1) / TB, (comp[0].bcy + vs - 1) / vs);
+    const int vec = pick_vec(d_raw, (size_t)pitch);
+#define GJ_K4SS2(H, V, VE, F, D) \
+    k_idct_rgb_ss<H, V, VE, F, D><<<grid, TB * V + 2 * TB / H, 0, stream>>>(d_coef, sg, d_raw, width, height, (size_t)pitch, prm)
+#define GJ_K4SS(H, V)                                                                  \
+    do {                                                                               \
+        if ( idct_flavour == 0 && coef_dequantized ) {                                 \
+            if ( vec == 4 ) GJ_K4SS2(H, V, 4, 0, false); else GJ_K4SS2(H, V, 1, 0, false); \
+        }                                                                              \
+        else if ( idct_flavour == 0 ) {                                                \
+            if ( vec == 4 ) GJ_K4SS2(H, V, 4, 0, true); else GJ_K4SS2(H, V, 1, 0, true);   \
+        }                                                                              \
+        else {                                                                         \
+            if ( vec == 4 ) GJ_K4SS2(H, V, 4, 1, true); else GJ_K4SS2(H, V, 1, 1, true);   \
+        }                                                                              \
+    } while ( 0 )
+    if ( hs == 2 && vs == 2 ) GJ_K4SS(2, 2);
+    else if ( hs == 2 && vs == 1 ) GJ_K4SS(2, 1);
+    else if ( hs == 1 && vs == 2 ) GJ_K4SS(1, 2);
+    else return -1;
+#undef GJ_K4SS
+#undef GJ_K4SS2
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

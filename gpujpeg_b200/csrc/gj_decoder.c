@@ -220,6 +220,17 @@ static int output_format_supported(const struct gpujpeg_decoder* d)
     return 1;
 }
 
+/* K4 for the coder's geometry: the 4:4:4 kernel or the chroma-subsampling template instance */
+static int launch_k4(struct gpujpeg_decoder* d, const int comp_tq[3], uint8_t* d_out, int coef_dequantized)
+{
+    const struct gj_geometry* g = &d->geo;
+    if ( g->lay.simple )
+        return gj_launch_idct_rgb444(d->d_coef, g->bcx, g->bcy, comp_tq, d_out, g->width, g->height, g->pitch, d->idct_flavour,
+                                     coef_dequantized, &d->h_tab, d->stream);
+    return gj_launch_idct_rgb_ss(d->d_coef, g->comp, comp_tq, d_out, g->width, g->height, g->pitch, d->idct_flavour,
+                                 coef_dequantized, &d->h_tab, d->stream);
+}
+
 /* [ref: src/gpujpeg_decoder.c:234-469] */
 int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t image_size,
                            struct gpujpeg_decoder_output* output)
@@ -249,9 +260,12 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
         GJ_ERR("This build decodes 3-component JPEGs only (stream has %d).\n", st.comp_count);
         return GPUJPEG_ERROR;
     }
-    for ( int c = 0; c < 3; c++ ) {
-        if ( st.comp_hv[c] != 0x11 ) {
-            GJ_ERR("This build decodes 4:4:4 only (chroma subsampling is not implemented yet).\n");
+    /* luminance 1x1, 2x1, 1x2 or 2x2 with 1x1 chrominance (4:4:4, 4:2:2, 4:4:0, 4:2:0) */
+    {
+        const int lh = st.comp_hv[0] >> 4, lv = st.comp_hv[0] & 15;
+        if ( lh < 1 || lh > 2 || lv < 1 || lv > 2 || st.comp_hv[1] != 0x11 || st.comp_hv[2] != 0x11 ) {
+            GJ_ERR("This build decodes 4:4:4, 4:2:2, 4:2:0 and 4:4:0 only (sampling factors %dx%d %dx%d %dx%d).\n", lh, lv,
+                   st.comp_hv[1] >> 4, st.comp_hv[1] & 15, st.comp_hv[2] >> 4, st.comp_hv[2] & 15);
             return GPUJPEG_ERROR;
         }
     }
@@ -270,8 +284,8 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     p.interleaved = st.interleaved;
     p.comp_count = 3;
     for ( int c = 0; c < 3; c++ ) {
-        p.sampling_factor[c].horizontal = 1;
-        p.sampling_factor[c].vertical = 1;
+        p.sampling_factor[c].horizontal = (uint8_t)(st.comp_hv[c] >> 4);
+        p.sampling_factor[c].vertical = (uint8_t)(st.comp_hv[c] & 15);
     }
     p.color_space_internal = GPUJPEG_YCBCR_BT601_256LVLS;
     struct gpujpeg_image_parameters pi;
@@ -282,7 +296,8 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     pi.pixel_format = GPUJPEG_444_U8_P012;
 
     if ( !d->initialised || d->param_image.width != pi.width || d->param_image.height != pi.height ||
-         d->param.restart_interval != p.restart_interval || d->param.interleaved != p.interleaved ) {
+         d->param.restart_interval != p.restart_interval || d->param.interleaved != p.interleaved ||
+         memcmp(d->param.sampling_factor, p.sampling_factor, sizeof p.sampling_factor) != 0 ) {
         if ( d->initialised ) GJ_VERBOSE(d->verbose, "Reinitializing decoder.\n");
         if ( gpujpeg_decoder_init(d, &p, &pi) ) return GPUJPEG_ERROR;
     }
@@ -383,6 +398,13 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
             return GPUJPEG_ERROR;
         }
         for ( int k = 0; k < st.scan[s].ncomp; k++ ) {
+            /* the block order inside an MCU follows the frame's component order (T.81 A.2.3) */
+            if ( g->interleaved && st.scan[s].comp[k] != k ) {
+                GJ_ERR("Unsupported scan structure (components of the interleaved scan are not in frame order).\n");
+                return GPUJPEG_ERROR;
+            }
+        }
+        for ( int k = 0; k < st.scan[s].ncomp; k++ ) {
             const int td = st.scan[s].td[k], ta = st.scan[s].ta[k];
             if ( !st.have_huff[0][td] || !st.have_huff[1][ta] ) {
                 GJ_ERR("Huffman table (DC %d / AC %d) used by scan %d is missing!\n", td, ta, s);
@@ -415,7 +437,10 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
         gj_timer_start(&d->t_gpu, d->stream);
         gj_timer_start(&d->t_huff, d->stream);
     }
-    if ( gj_launch_scan_ranks(d->d_list_pos, d->d_mk, st.scan_count, scan_begin, scan_end, g->seg_per_scan, d->d_mk + 4,
+    int scan_segments[4] = {0, 0, 0, 0};
+    for ( int s = 0; s < g->scan_count; s++ )
+        scan_segments[s] = g->lay.scan_seg_begin[s + 1] - g->lay.scan_seg_begin[s];
+    if ( gj_launch_scan_ranks(d->d_list_pos, d->d_mk, st.scan_count, scan_begin, scan_end, scan_segments, d->d_mk + 4,
                               d->stream) ) {
         GJ_ERR("Scan rank launch failed: %s\n", gj_cuda_last_error());
         return GPUJPEG_ERROR;
@@ -432,12 +457,8 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     ha.d_first_rank = d->d_mk + 4;
     ha.d_error = d->d_mk + 3;
     ha.seg_count = g->seg_count;
-    ha.seg_per_scan = g->seg_per_scan;
-    ha.scan_count = g->scan_count;
-    ha.comps_per_scan = g->comps_per_scan;
+    ha.lay = g->lay;
     ha.seg_mcu = g->seg_mcu;
-    ha.nblk = g->nblk;
-    ha.comp_count = g->comp_count;
     ha.d_coef = d->d_coef;
     ha.d_tables = d->d_tab;
     d->last_args = ha;
@@ -462,8 +483,7 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
         GJ_ERR("OpenGL texture output is not supported in this build.\n");
         return GPUJPEG_ERROR;
     }
-    if ( gj_launch_idct_rgb444(d->d_coef, g->bcx, g->bcy, st.comp_tq, d_out, g->width, g->height, g->pitch,
-                               d->idct_flavour, ha.dequantize, &d->h_tab, d->stream) ) {
+    if ( launch_k4(d, st.comp_tq, d_out, ha.dequantize) ) {
         GJ_ERR("Inverse DCT launch failed: %s\n", gj_cuda_last_error());
         return GPUJPEG_ERROR;
     }
@@ -627,12 +647,8 @@ void gpujpeg_decoder_print_options(void)
 GPUJPEG_API int gpujpegx_decoder_run_resident(struct gpujpeg_decoder* d, uint8_t* d_out, int stage_mask)
 {
     if ( !d || !d->last_valid ) return -1;
-    const struct gj_geometry* g = &d->geo;
     if ( (stage_mask & 1) && gj_launch_huffman_decode(&d->last_args, d->stream) ) return -1;
-    if ( (stage_mask & 2) &&
-         gj_launch_idct_rgb444(d->d_coef, g->bcx, g->bcy, d->last_tq, d_out ? d_out : d->d_raw, g->width, g->height,
-                               g->pitch, d->idct_flavour, d->last_args.dequantize, &d->h_tab, d->stream) )
-        return -1;
+    if ( (stage_mask & 2) && launch_k4(d, d->last_tq, d_out ? d_out : d->d_raw, d->last_args.dequantize) ) return -1;
     return 0;
 }
 

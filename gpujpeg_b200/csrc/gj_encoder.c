@@ -198,11 +198,14 @@ static int params_supported(const struct gpujpeg_parameters* p, const struct gpu
         GJ_ERR("This build encodes 3-component images only (comp_count = %d).\n", p->comp_count);
         return 0;
     }
-    for ( int c = 0; c < 3; c++ ) {
-        if ( p->sampling_factor[c].horizontal != 1 || p->sampling_factor[c].vertical != 1 ) {
-            GJ_ERR("This build encodes 4:4:4 only (chroma subsampling is not implemented yet).\n");
-            return 0;
-        }
+    /* luminance 1x1, 2x1, 1x2 or 2x2 with 1x1 chrominance: the sampling modes the reference has precompiled
+     * preprocessor kernels for [ref: src/gpujpeg_preprocessor.cu:241-253] */
+    const int lh = p->sampling_factor[0].horizontal, lv = p->sampling_factor[0].vertical;
+    if ( lh < 1 || lh > 2 || lv < 1 || lv > 2 || p->sampling_factor[1].horizontal != 1 || p->sampling_factor[1].vertical != 1 ||
+         p->sampling_factor[2].horizontal != 1 || p->sampling_factor[2].vertical != 1 ) {
+        GJ_ERR("This build encodes 4:4:4, 4:2:2, 4:2:0 and 4:4:0 only (got %s).\n",
+               gpujpeg_subsampling_get_name(3, p->sampling_factor));
+        return 0;
     }
     if ( p->segment_info ) {
         GJ_ERR("segment_info headers are not implemented in this build.\n");
@@ -217,6 +220,38 @@ static int params_supported(const struct gpujpeg_parameters* p, const struct gpu
         return 0;
     }
     return 1;
+}
+
+/* K1 for the coder's geometry: the 4:4:4 kernel or the chroma-subsampling template instance */
+static int launch_k1(struct gpujpeg_encoder* e, const uint8_t* d_raw)
+{
+    const struct gj_geometry* g = &e->geo;
+    if ( g->lay.simple )
+        return gj_launch_fdct_rgb444(d_raw, g->width, g->height, g->pitch, e->d_coef, e->d_nzmask, g->bcx, g->bcy, &e->h_tab,
+                                     e->stream);
+    return gj_launch_fdct_rgb_ss(d_raw, g->width, g->height, g->pitch, e->d_coef, e->d_nzmask, g->comp, &e->h_tab, e->stream);
+}
+
+static void fill_huff_args(const struct gpujpeg_encoder* e, struct gj_huff_enc_args* ha)
+{
+    const struct gj_geometry* g = &e->geo;
+    memset(ha, 0, sizeof *ha);
+    ha->d_coef = e->d_coef;
+    ha->d_nzmask = e->d_nzmask;
+    ha->lay = g->lay;
+    ha->seg_mcu = g->seg_mcu;
+    ha->d_tmp = e->d_tmp;
+    ha->d_spill = e->d_spill;
+    ha->slot_stride = g->slot_stride;
+    ha->d_seg_bytes = e->d_seg_bytes;
+    ha->d_seg_off = e->d_seg_off;
+    ha->d_stream = e->d_stream;
+    ha->stream_cap = g->stream_cap;
+    ha->header_size = (uint32_t)e->header_size;
+    ha->d_sos = e->d_sos;
+    ha->sos_len = e->sos_len;
+    ha->d_info = e->d_info;
+    ha->d_tables = e->d_tab;
 }
 
 /* (re)build everything that depends on geometry [ref: src/gpujpeg_common.c:628-1106] */
@@ -274,6 +309,16 @@ static int same_image(const struct gpujpeg_image_parameters* a, const struct gpu
     return a->width == b->width && a->height == b->height && a->color_space == b->color_space &&
            a->pixel_format == b->pixel_format && a->width_padding == b->width_padding;
 }
+/* sampling factors in the packed form of GPUJPEG_SUBSAMPLING_* (one nibble pair per component) */
+static gpujpeg_sampling_factor_t packed_sampling(const struct gpujpeg_parameters* p)
+{
+    gpujpeg_sampling_factor_t r = 0;
+    for ( int c = 0; c < p->comp_count && c < 4; c++ )
+        r |= (gpujpeg_sampling_factor_t)p->sampling_factor[c].horizontal << (28 - 8 * c) |
+             (gpujpeg_sampling_factor_t)p->sampling_factor[c].vertical << (24 - 8 * c);
+    return r;
+}
+
 static int same_param(const struct gpujpeg_parameters* a, const struct gpujpeg_parameters* b)
 {
     /* everything but verbose / perf_stats / quality [ref: src/gpujpeg_common.c:348-367] */
@@ -311,7 +356,7 @@ static struct gpujpeg_parameters adjust_params(struct gpujpeg_encoder* e, const 
     if ( param->restart_interval == RESTART_AUTO ) {
         if ( img_changed || !e->initialised || a.interleaved != e->param.interleaved )
             a.restart_interval =
-                gpujpeg_encoder_suggest_restart_interval(pi, GPUJPEG_SUBSAMPLING_444, a.interleaved, a.verbose);
+                gpujpeg_encoder_suggest_restart_interval(pi, packed_sampling(&a), a.interleaved, a.verbose);
         else
             a.restart_interval = e->param.restart_interval;
     }
@@ -453,7 +498,7 @@ int gpujpeg_encoder_encode(struct gpujpeg_encoder* e, const struct gpujpeg_param
         gj_timer_start(&e->t_gpu, e->stream);
         gj_timer_start(&e->t_pre, e->stream);
     }
-    if ( gj_launch_fdct_rgb444(d_raw, g->width, g->height, g->pitch, e->d_coef, e->d_nzmask, g->bcx, g->bcy, &e->h_tab, e->stream) ) {
+    if ( launch_k1(e, d_raw) ) {
         GJ_ERR("Forward DCT launch failed: %s\n", gj_cuda_last_error());
         return GPUJPEG_ERROR;
     }
@@ -462,27 +507,7 @@ int gpujpeg_encoder_encode(struct gpujpeg_encoder* e, const struct gpujpeg_param
         gj_timer_start(&e->t_huff, e->stream);
     }
     struct gj_huff_enc_args ha;
-    memset(&ha, 0, sizeof ha);
-    ha.d_coef = e->d_coef;
-    ha.d_nzmask = e->d_nzmask;
-    ha.nblk = g->nblk;
-    ha.comp_count = g->comp_count;
-    ha.comps_per_scan = g->comps_per_scan;
-    ha.seg_mcu = g->seg_mcu;
-    ha.seg_per_scan = g->seg_per_scan;
-    ha.scan_count = g->scan_count;
-    ha.d_tmp = e->d_tmp;
-    ha.d_spill = e->d_spill;
-    ha.slot_stride = g->slot_stride;
-    ha.d_seg_bytes = e->d_seg_bytes;
-    ha.d_seg_off = e->d_seg_off;
-    ha.d_stream = e->d_stream;
-    ha.stream_cap = g->stream_cap;
-    ha.header_size = (uint32_t)e->header_size;
-    ha.d_sos = e->d_sos;
-    ha.sos_len = e->sos_len;
-    ha.d_info = e->d_info;
-    ha.d_tables = e->d_tab;
+    fill_huff_args(e, &ha);
     if ( gj_launch_huffman_encode(&ha, e->stream) ) {
         GJ_ERR("Huffman encoder launch failed: %s\n", gj_cuda_last_error());
         return GPUJPEG_ERROR;
@@ -609,35 +634,12 @@ void gpujpeg_encoder_print_options(void)
 GPUJPEG_API int gpujpegx_encoder_run_resident(struct gpujpeg_encoder* e, const uint8_t* d_raw, int stage_mask)
 {
     if ( !e || !e->initialised ) return -1;
-    const struct gj_geometry* g = &e->geo;
     if ( !d_raw ) d_raw = e->d_raw;
     if ( !d_raw ) return -1;
-    if ( (stage_mask & 1) &&
-         gj_launch_fdct_rgb444(d_raw, g->width, g->height, g->pitch, e->d_coef, e->d_nzmask, g->bcx, g->bcy, &e->h_tab, e->stream) )
-        return -1;
+    if ( (stage_mask & 1) && launch_k1(e, d_raw) ) return -1;
     if ( stage_mask & 2 ) {
         struct gj_huff_enc_args ha;
-        memset(&ha, 0, sizeof ha);
-        ha.d_coef = e->d_coef;
-        ha.d_nzmask = e->d_nzmask;
-        ha.nblk = g->nblk;
-        ha.comp_count = g->comp_count;
-        ha.comps_per_scan = g->comps_per_scan;
-        ha.seg_mcu = g->seg_mcu;
-        ha.seg_per_scan = g->seg_per_scan;
-        ha.scan_count = g->scan_count;
-        ha.d_tmp = e->d_tmp;
-        ha.d_spill = e->d_spill;
-        ha.slot_stride = g->slot_stride;
-        ha.d_seg_bytes = e->d_seg_bytes;
-        ha.d_seg_off = e->d_seg_off;
-        ha.d_stream = e->d_stream;
-        ha.stream_cap = g->stream_cap;
-        ha.header_size = (uint32_t)e->header_size;
-        ha.d_sos = e->d_sos;
-        ha.sos_len = e->sos_len;
-        ha.d_info = e->d_info;
-        ha.d_tables = e->d_tab;
+        fill_huff_args(e, &ha);
         if ( gj_launch_huffman_encode(&ha, e->stream) ) return -1;
     }
     return 0;

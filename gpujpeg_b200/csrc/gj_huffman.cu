@@ -44,6 +44,48 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane)
     return v;
 }
 
+/* scan of global segment g: scan_seg_begin[k] holds seg_count for every k >= scan_count */
+__device__ __forceinline__ int scan_of_segment(const gj_scan_layout& L, int g)
+{
+    return (g >= L.scan_seg_begin[1]) + (g >= L.scan_seg_begin[2]) + (g >= L.scan_seg_begin[3]);
+}
+
+/* block number j (coding order) of the segment that starts at MCU first_mcu of scan `scan`:
+ * -> index of the block in the coefficient / mask buffers, its component, and the distance (in blocks of the
+ * segment) to the previous block of the same component (the DC predictor) */
+__device__ __forceinline__ void segment_block(const gj_scan_layout& L, int scan, int first_mcu, int j, size_t& bi, int& comp,
+                                              int& pd)
+{
+    if ( L.simple ) {
+        if ( !L.interleaved ) {
+            comp = scan;
+            bi = (size_t)L.blk_off[scan] + first_mcu + j;
+            pd = 1;
+        }
+        else {
+            const int cps = L.comp_count;
+            const int mcu = j / cps;
+            comp = j - mcu * cps;
+            bi = (size_t)L.blk_off[comp] + first_mcu + mcu;
+            pd = cps;
+        }
+    }
+    else if ( !L.interleaved ) {
+        comp = scan;
+        bi = (size_t)L.blk_off[scan] + first_mcu + j;
+        pd = 1;
+    }
+    else {
+        const int mcu = j / L.bpm, i = j - mcu * L.bpm;
+        const int m = first_mcu + mcu;
+        const int my = m / L.mcu_x, mx = m - my * L.mcu_x;
+        comp = L.idx_comp[i];
+        bi = (size_t)L.blk_off[comp] + (size_t)(my * L.comp_vs[comp] + L.idx_dy[i]) * L.bcx[comp] + mx * L.comp_hs[comp] +
+             L.idx_dx[i];
+        pd = L.idx_pred[i];
+    }
+}
+
 /* =========================================================================================== */
 /* encoder                                                                                       */
 
@@ -98,8 +140,8 @@ constexpr int HE_SMEM = (2 * 256 + 2 * 16 + HE_WARPS * HE_WORDS + HE_WARPS * 32 
  *   4. the warp byte-stuffs the completed words of the stream buffer into the segment's slot.
  * The stream buffer is flushed in rounds, so segments of any length stream through it. */
 __global__ void __launch_bounds__(HE_WARPS * 32)
-k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzmask, int nblk, int cps /*components per scan*/,
-              int seg_mcu, int seg_per_scan, int seg_count, uint8_t* __restrict__ tmp, size_t slot_stride,
+k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzmask, const __grid_constant__ gj_scan_layout lay,
+              int seg_mcu, int seg_count, uint8_t* __restrict__ tmp, size_t slot_stride,
               uint32_t* __restrict__ seg_bytes, uint32_t* __restrict__ spill_all, const gj_dev_enc_tables* __restrict__ tables)
 {
     extern __shared__ __align__(16) uint32_t he_smem[];
@@ -117,10 +159,10 @@ k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzm
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.x * HE_WARPS + warp;
     if ( g >= seg_count ) return;
-    const int scan = g / seg_per_scan, s = g - scan * seg_per_scan;
+    const int scan = scan_of_segment(lay, g), s = g - lay.scan_seg_begin[scan];
     const int first_mcu = s * seg_mcu;
-    const int mcus = min(seg_mcu, nblk - first_mcu);
-    const int nblocks = mcus * cps;
+    const int mcus = min(seg_mcu, lay.scan_mcus[scan] - first_mcu);
+    const int nblocks = mcus * lay.bpm;
     uint32_t* buf = s_buf + warp * HE_WORDS;
     uint32_t* priv = s_priv + (warp * 32 + lane) * HE_PRIV;
     uint32_t* spill = spill_all + ((size_t)g * 32 + lane) * HE_SPILL;   // touched only by blocks longer than HE_PRIV words
@@ -134,33 +176,29 @@ k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzm
         buf[i] = 0;
     __syncwarp();
 
-    int prev_dc = 0;  // DC of the same component's previous block, valid in lanes < cps at round start
+    int dc_before = 0;  // this lane's DC of the previous round (predictor source for the first blocks of a round)
     /* mask and the first 16 coefficients (one 32-byte sector: DC + the low frequencies, where nearly all
      * non-zeros of photographic content live) are fetched one round ahead: their latency hides behind the
      * previous round; the value loads were the largest stall of the single-pass kernel (ncu r1_h: 18 %) */
     uint64_t nz_next = 0;
     uint4 ha_next = make_uint4(0u, 0u, 0u, 0u), hb_next = ha_next;
+    size_t bi_next = 0;
+    int comp_next = 0, pd_next = 1;
     {
         const int j = lane;
         if ( j < nblocks ) {
-            const int mcu = cps == 1 ? j : j / cps;
-            const int comp = cps == 1 ? scan : j - mcu * cps;
-            const size_t bi = (size_t)comp * nblk + first_mcu + mcu;
-            nz_next = __ldg(nzmask + bi);
-            ha_next = __ldg(reinterpret_cast<const uint4*>(coef + bi * 64));
-            hb_next = __ldg(reinterpret_cast<const uint4*>(coef + bi * 64) + 1);
+            segment_block(lay, scan, first_mcu, j, bi_next, comp_next, pd_next);
+            nz_next = __ldg(nzmask + bi_next);
+            ha_next = __ldg(reinterpret_cast<const uint4*>(coef + bi_next * 64));
+            hb_next = __ldg(reinterpret_cast<const uint4*>(coef + bi_next * 64) + 1);
         }
     }
     for ( int base = 0; base < nblocks; base += 32 ) {
         const int j = base + lane;
         const bool active = j < nblocks;
-        int mcu = 0, ci = 0;
-        if ( cps == 1 ) mcu = j;
-        else { mcu = j / cps; ci = j - mcu * cps; }
-        const int comp = cps == 1 ? scan : ci;
+        const int comp = comp_next, pd = pd_next;
         const int tbl = comp == 0 ? 0 : 1;
-        const size_t bi = (size_t)comp * nblk + first_mcu + mcu;
-        const int16_t* blk = coef + bi * 64;
+        const int16_t* blk = coef + bi_next * 64;
 
         const uint64_t nz = nz_next;
         const int dc = (int)(short)(ha_next.x & 0xFFFFu);
@@ -171,20 +209,20 @@ k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzm
         {
             const int jn = j + 32;
             if ( jn < nblocks ) {
-                const int mcun = cps == 1 ? jn : jn / cps;
-                const int compn = cps == 1 ? scan : jn - mcun * cps;
-                const size_t bn = (size_t)compn * nblk + first_mcu + mcun;
-                nz_next = __ldg(nzmask + bn);
-                ha_next = __ldg(reinterpret_cast<const uint4*>(coef + bn * 64));
-                hb_next = __ldg(reinterpret_cast<const uint4*>(coef + bn * 64) + 1);
+                segment_block(lay, scan, first_mcu, jn, bi_next, comp_next, pd_next);
+                nz_next = __ldg(nzmask + bi_next);
+                ha_next = __ldg(reinterpret_cast<const uint4*>(coef + bi_next * 64));
+                hb_next = __ldg(reinterpret_cast<const uint4*>(coef + bi_next * 64) + 1);
             }
         }
         /* DC predictor: previous block of the same component inside the segment, 0 at its start
          * [ref: src/gpujpeg_huffman_cpu_encoder.c:147-148, 361-364] */
-        int pred = __shfl_up_sync(FULL, dc, cps);
-        if ( lane < cps ) pred = prev_dc;
-        if ( j < cps ) pred = 0;
-        prev_dc = __shfl_sync(FULL, dc, (32 - cps + lane) & 31);
+        const int from = (lane - pd) & 31;
+        int pred = __shfl_sync(FULL, dc, from);
+        const int pred_before = __shfl_sync(FULL, dc_before, from);
+        if ( lane < pd ) pred = pred_before;
+        if ( j < pd ) pred = 0;
+        dc_before = dc;
 
         /* ---- 1. the block's bit string, into the lane's private words ---- */
         int len = 0;   // total bits of this block
@@ -307,14 +345,18 @@ k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzm
  * count, so the redundant part stays O(148 n).  Deterministic order (the reference's atomicAdd compaction
  * is not). */
 constexpr int OFF_THREADS = 1024;
-__device__ __forceinline__ uint32_t seg_stream_size(uint32_t bytes, int s, int seg_per_scan, int sos_len)
+/* first global segment of every scan; entries past the last scan hold seg_count */
+struct ScanSegs {
+    int begin[GJ_MAX_COMP + 1];
+};
+__device__ __forceinline__ int scan_of_segment(const ScanSegs& S, int g)
 {
-    /* a segment as it appears in the stream: [SOS header] bytes [RSTn] */
-    return bytes + (s == 0 ? (uint32_t)sos_len : 0u) + (s + 1 < seg_per_scan ? 2u : 0u);
+    return (g >= S.begin[1]) + (g >= S.begin[2]) + (g >= S.begin[3]);
 }
 __global__ void __launch_bounds__(OFF_THREADS)
-k_huff_offsets(const uint32_t* __restrict__ seg_bytes, int seg_count, int seg_per_scan, int chunk, uint32_t header_size,
-               int sos_len, uint64_t stream_cap, uint64_t* __restrict__ seg_off, uint64_t* __restrict__ info)
+k_huff_offsets(const uint32_t* __restrict__ seg_bytes, int seg_count, const __grid_constant__ ScanSegs segs, int chunk,
+               uint32_t header_size, int sos_len, uint64_t stream_cap, uint64_t* __restrict__ seg_off,
+               uint64_t* __restrict__ info)
 {
     __shared__ uint64_t s_warp[32];
     __shared__ uint32_t s_tile[32];
@@ -335,17 +377,23 @@ k_huff_offsets(const uint32_t* __restrict__ seg_bytes, int seg_count, int seg_pe
         sum += __shfl_down_sync(FULL, sum, d);
     if ( lane == 0 ) s_warp[warp] = sum;
     __syncthreads();
-    const int full_scans = begin / seg_per_scan, rem = begin - full_scans * seg_per_scan;
-    uint64_t base = header_size + (uint64_t)(full_scans + (rem > 0)) * (uint64_t)sos_len +
-                    2ull * ((uint64_t)full_scans * (uint64_t)(seg_per_scan - 1) + (uint64_t)rem);
+    /* a segment as it appears in the stream: [SOS header if first of its scan] bytes [RSTn unless last of its scan] */
+    int started = 0, finished = 0;   // scans with a segment in front of the chunk / lying completely in front of it
+#pragma unroll
+    for ( int k = 0; k < GJ_MAX_COMP; k++ ) {
+        if ( segs.begin[k] < begin && segs.begin[k] < seg_count ) started++;
+        if ( segs.begin[k + 1] <= begin && segs.begin[k] < seg_count ) finished++;
+    }
+    uint64_t base = header_size + (uint64_t)started * (uint64_t)sos_len + 2ull * (uint64_t)(begin - finished);
 #pragma unroll
     for ( int w = 0; w < 32; w++ )
         base += s_warp[w];
 
     for ( int t0 = begin; t0 < end; t0 += OFF_THREADS ) {
         const int g = t0 + threadIdx.x;
-        const int s = g % seg_per_scan;
-        const uint32_t v = g < end ? seg_stream_size(__ldg(seg_bytes + g), s, seg_per_scan, sos_len) : 0u;
+        const int scan = scan_of_segment(segs, g);
+        const bool first = g == segs.begin[scan], last = g + 1 == segs.begin[scan + 1];
+        const uint32_t v = g < end ? __ldg(seg_bytes + g) + (first ? (uint32_t)sos_len : 0u) + (last ? 0u : 2u) : 0u;
         uint32_t incl = v;
 #pragma unroll
         for ( int d = 1; d < 32; d <<= 1 ) {
@@ -363,7 +411,7 @@ k_huff_offsets(const uint32_t* __restrict__ seg_bytes, int seg_count, int seg_pe
             tile_total += t;
         }
         /* the segment's bytes start after its SOS header (if any) */
-        if ( g < end ) seg_off[g] = base + before + (incl - v) + (s == 0 ? (uint32_t)sos_len : 0u);
+        if ( g < end ) seg_off[g] = base + before + (incl - v) + (first ? (uint32_t)sos_len : 0u);
         base += tile_total;
     }
     if ( end == seg_count && threadIdx.x == 0 ) {
@@ -376,14 +424,15 @@ k_huff_offsets(const uint32_t* __restrict__ seg_bytes, int seg_count, int seg_pe
 /* move every segment to its final offset; add RSTn / SOS / EOI.  One warp per segment. */
 __global__ void __launch_bounds__(256)
 k_huff_compact(const uint8_t* __restrict__ tmp, size_t slot_stride, const uint32_t* __restrict__ seg_bytes,
-               const uint64_t* __restrict__ seg_off, int seg_count, int seg_per_scan, const uint8_t* __restrict__ sos,
-               int sos_len, uint8_t* __restrict__ stream, const uint64_t* __restrict__ info)
+               const uint64_t* __restrict__ seg_off, int seg_count, const __grid_constant__ ScanSegs segs,
+               const uint8_t* __restrict__ sos, int sos_len, uint8_t* __restrict__ stream, const uint64_t* __restrict__ info)
 {
     if ( info[1] ) return;  // would overflow the stream buffer: host reports the error
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.x * 8 + warp;
     if ( g >= seg_count ) return;
-    const int scan = g / seg_per_scan, s = g - scan * seg_per_scan;
+    const int scan = scan_of_segment(segs, g), s = g - segs.begin[scan];
+    const bool last_of_scan = g + 1 == segs.begin[scan + 1];
     const uint8_t* src = tmp + (size_t)g * slot_stride;
     const uint32_t n = seg_bytes[g];
     uint8_t* dst = stream + seg_off[g];
@@ -410,7 +459,7 @@ k_huff_compact(const uint8_t* __restrict__ tmp, size_t slot_stride, const uint32
     i += nvec << 4;
     if ( i + lane < n ) dst[i + lane] = src[i + lane];   // tail < 16 bytes
     if ( lane == 0 ) {
-        if ( s + 1 < seg_per_scan ) {
+        if ( !last_of_scan ) {
             /* RSTn, n = index in scan mod 8 [ref: src/gpujpeg_huffman_cpu_encoder.c:366-367] */
             dst[n] = 0xFF;
             dst[n + 1] = (uint8_t)(0xD0 + (s & 7));
@@ -524,7 +573,7 @@ __device__ __forceinline__ int decode_symbol(BitSource& r, const gj_dec_lut& t)
 template <bool DEQ>
 __global__ void __launch_bounds__(HD_THREADS)
 k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file_end, const uint32_t* __restrict__ seg_off,
-              int seg_count, int seg_per_scan, int cps, int seg_mcu, int nblk, const __grid_constant__ gj_huff_dec_args a,
+              int seg_count, int seg_mcu, const __grid_constant__ gj_huff_dec_args a,
               int16_t* __restrict__ coef, const gj_dev_dec_tables* __restrict__ tables)
 {
     __shared__ DecTabs s_tab;
@@ -549,16 +598,24 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file
     if ( !seg_off && *a.d_error ) return;   // restart structure does not match the geometry: list ranks are meaningless
     const int g = g0 + lane;
     const bool live = g < seg_count;
+    const gj_scan_layout& L = a.lay;
+    const int bpm = L.bpm;
+    const bool general = !L.simple && L.interleaved;   // MCUs of several blocks per component
     int scan = 0, nblocks = 0, mybase = 0;
+    int mx = 0, my = 0;   // general layout: position of the lane's current MCU
     BitSource r;
     r.n = 0;
     if ( live ) {
-        scan = g / seg_per_scan;
-        const int s = g - scan * seg_per_scan;
-        nblocks = min(seg_mcu, nblk - s * seg_mcu) * cps;
+        scan = scan_of_segment(L, g);
+        const int s = g - L.scan_seg_begin[scan];
+        nblocks = min(seg_mcu, L.scan_mcus[scan] - s * seg_mcu) * bpm;
         // block index (in units of 64 coefficients) of the segment's first MCU; for single-component
         // scans the component plane is folded in here, for interleaved scans it is added per block
-        mybase = s * seg_mcu + (cps == 1 ? a.scan_comp[scan][0] * nblk : 0);
+        mybase = s * seg_mcu + (L.interleaved ? 0 : L.blk_off[a.scan_comp[scan][0]]);
+        if ( general ) {
+            my = (s * seg_mcu) / L.mcu_x;
+            mx = s * seg_mcu - my * L.mcu_x;
+        }
         uint32_t start;
         if ( seg_off ) {
             start = seg_off[g];
@@ -575,7 +632,7 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file
         if ( start >= (uint32_t)(file_end - file) ) start = 0;   // corrupt table: stay inside the buffer
         src_init(r, file + start, file_end);
     }
-    const int max_blocks = seg_mcu * cps;
+    const int max_blocks = seg_mcu * bpm;
     /* private block: 16-byte chunk c of lane L lives at chunk (c ^ (L & 7)) so that the warp-wide
      * 16-byte reads of the flush below are bank-conflict free */
     const int sw = lane & 7;
@@ -583,9 +640,10 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file
     uint4* wbase = reinterpret_cast<uint4*>(s_blk + (threadIdx.x & ~31) * 32);
     int pred[GJ_MAX_COMP] = {0, 0, 0, 0};
 
+    int mcu = 0, bi_in_mcu = 0;   // block b = mcu * bpm + bi_in_mcu, the same in every lane
     for ( int b = 0; b < max_blocks; b++ ) {
-        int mcu = b, ci = 0;
-        if ( cps != 1 ) { mcu = b / cps; ci = b - mcu * cps; }
+        /* ci: position of the block's component in the scan header (tables, predictor) */
+        const int ci = general ? L.idx_comp[bi_in_mcu] : bi_in_mcu;
         if ( live && b < nblocks ) {
             const gj_dec_lut& tdc = s_tab.t[0][a.scan_td[scan][ci]];
             const gj_dec_lut& tac = s_tab.t[1][a.scan_ta[scan][ci]];
@@ -619,20 +677,37 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file
             }
         }
         __syncwarp();
+        /* where this lane's block goes (index in units of 64 coefficients) */
+        int target;
+        if ( general ) {
+            const int comp = a.scan_comp[0][ci];
+            target = L.blk_off[comp] + (my * L.comp_vs[comp] + L.idx_dy[bi_in_mcu]) * L.bcx[comp] + mx * L.comp_hs[comp] +
+                     L.idx_dx[bi_in_mcu];
+        }
+        else {
+            target = mybase + (L.interleaved ? L.blk_off[a.scan_comp[0][ci]] : 0) + mcu;
+        }
         /* write the warp's 32 private blocks out as 128-byte lines, four blocks per step, and clear them */
-        const int extra = (cps == 1 ? 0 : a.scan_comp[0][ci] * nblk) + mcu;
 #pragma unroll
         for ( int j = 0; j < 8; j++ ) {
             const int i = 4 * j + (lane >> 3);   // owner lane of the block this lane helps to move
             const int c = lane & 7;              // its 16-byte chunk
-            const int ob = __shfl_sync(FULL, mybase, i);
+            const int ob = __shfl_sync(FULL, target, i);
             const int on = __shfl_sync(FULL, nblocks, i);
             uint4* src = wbase + i * 8 + (c ^ (i & 7));
             const uint4 v = *src;
             *src = make_uint4(0u, 0u, 0u, 0u);
-            if ( b < on ) reinterpret_cast<uint4*>(coef + (size_t)(ob + extra) * 64)[c] = v;
+            if ( b < on ) reinterpret_cast<uint4*>(coef + (size_t)ob * 64)[c] = v;
         }
         __syncwarp();
+        if ( ++bi_in_mcu == bpm ) {
+            bi_in_mcu = 0;
+            mcu++;
+            if ( general && ++mx == L.mcu_x ) {
+                mx = 0;
+                my++;
+            }
+        }
     }
 }
 
@@ -653,7 +728,10 @@ __global__ void k_coef_to_natural(const int16_t* __restrict__ in, int16_t* __res
 
 extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_stream_t stream)
 {
-    const int seg_count = a->seg_per_scan * a->scan_count;
+    const int seg_count = a->lay.scan_seg_begin[GJ_MAX_COMP];
+    ScanSegs segs;
+    for ( int k = 0; k <= GJ_MAX_COMP; k++ )
+        segs.begin[k] = a->lay.scan_seg_begin[k];
     static bool attr_done[64] = {false};
     int dev = 0;
     if ( cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 ) return -1;
@@ -662,17 +740,16 @@ extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_str
         attr_done[dev] = true;
     }
     k_huff_encode<<<(seg_count + HE_WARPS - 1) / HE_WARPS, HE_WARPS * 32, HE_SMEM, stream>>>(
-        a->d_coef, a->d_nzmask, a->nblk, a->comps_per_scan, a->seg_mcu, a->seg_per_scan, seg_count, a->d_tmp, a->slot_stride,
-        a->d_seg_bytes, a->d_spill, a->d_tables);
+        a->d_coef, a->d_nzmask, a->lay, a->seg_mcu, seg_count, a->d_tmp, a->slot_stride, a->d_seg_bytes, a->d_spill,
+        a->d_tables);
     /* one chunk (a multiple of the 1024-segment tile) per CTA, at most one CTA per SM */
     int off_chunk = (seg_count + 147) / 148;
     off_chunk = ((off_chunk + OFF_THREADS - 1) / OFF_THREADS) * OFF_THREADS;
     const int off_grid = (seg_count + off_chunk - 1) / off_chunk;
-    k_huff_offsets<<<off_grid, OFF_THREADS, 0, stream>>>(a->d_seg_bytes, seg_count, a->seg_per_scan, off_chunk, a->header_size, a->sos_len,
-                                                  (uint64_t)a->stream_cap, a->d_seg_off, a->d_info);
-    k_huff_compact<<<(seg_count + 7) / 8, 256, 0, stream>>>(a->d_tmp, a->slot_stride, a->d_seg_bytes, a->d_seg_off,
-                                                            seg_count, a->seg_per_scan, a->d_sos, a->sos_len,
-                                                            a->d_stream, a->d_info);
+    k_huff_offsets<<<off_grid, OFF_THREADS, 0, stream>>>(a->d_seg_bytes, seg_count, segs, off_chunk, a->header_size, a->sos_len,
+                                                         (uint64_t)a->stream_cap, a->d_seg_off, a->d_info);
+    k_huff_compact<<<(seg_count + 7) / 8, 256, 0, stream>>>(a->d_tmp, a->slot_stride, a->d_seg_bytes, a->d_seg_off, seg_count,
+                                                            segs, a->d_sos, a->sos_len, a->d_stream, a->d_info);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -681,12 +758,10 @@ extern "C" int gj_launch_huffman_decode(const struct gj_huff_dec_args* a, gj_str
     const dim3 grid((a->seg_count + HD_THREADS - 1) / HD_THREADS);
     if ( a->dequantize )
         k_huff_decode<true><<<grid, HD_THREADS, 0, stream>>>(a->d_file, a->d_file + a->file_size, a->d_seg_off, a->seg_count,
-                                                             a->seg_per_scan, a->comps_per_scan, a->seg_mcu, a->nblk, *a,
-                                                             a->d_coef, a->d_tables);
+                                                             a->seg_mcu, *a, a->d_coef, a->d_tables);
     else
         k_huff_decode<false><<<grid, HD_THREADS, 0, stream>>>(a->d_file, a->d_file + a->file_size, a->d_seg_off, a->seg_count,
-                                                              a->seg_per_scan, a->comps_per_scan, a->seg_mcu, a->nblk, *a,
-                                                              a->d_coef, a->d_tables);
+                                                              a->seg_mcu, *a, a->d_coef, a->d_tables);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

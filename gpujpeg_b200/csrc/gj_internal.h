@@ -78,19 +78,54 @@ struct gj_dec_lut {
 };
 int gj_dec_lut_build(const struct gj_huff_spec* spec, struct gj_dec_lut* lut);
 
-/* ---- geometry (gj_geometry.c)  [ref: src/gpujpeg_common.c:628-1106] ---- */
+/* ---- geometry (gj_codestream.c)  [ref: src/gpujpeg_common.c:628-1106] ---- */
+#define GJ_MAX_MCU_BLOCKS 10  /* T.81 B.2.3: at most 10 data units per MCU */
+
+/* one component's plane of 8x8 blocks [ref: src/gpujpeg_common.c:671-736] */
+struct gj_comp_geo {
+    int hs, vs;         /* sampling factors as in SOF0 */
+    int width, height;  /* samples that carry image data */
+    int bcx, bcy;       /* block grid (interleaved: padded to whole MCUs) */
+    int nblk;           /* bcx * bcy */
+    int blk_off;        /* index of the component's first block in the coefficient / mask buffers */
+};
+
+/* What the entropy kernels need to turn "block number j of segment s of scan k" into a block index; passed to
+ * K2/K3 by value.  For the 4:4:4 case (`simple`) they keep the closed form comp * nblk + first_mcu + mcu. */
+struct gj_scan_layout {
+    int simple;               /* every component 1x1: MCU index == block index in every plane */
+    int interleaved;
+    int comp_count;
+    int scan_count;
+    int bpm;                  /* blocks per MCU of an interleaved scan (1 otherwise) */
+    int mcu_x;                /* MCUs per MCU row (interleaved) */
+    int blk_off[GJ_MAX_COMP];
+    int bcx[GJ_MAX_COMP];
+    int scan_seg_begin[GJ_MAX_COMP + 1];  /* first global segment of scan k; entries >= scan_count hold seg_count */
+    int scan_mcus[GJ_MAX_COMP];           /* MCUs of scan k */
+    /* interleaved MCU, block i in coding order [ref: src/gpujpeg_common.c:1062-1084]:
+     * component, block offset inside the MCU, distance (in blocks of the scan) to the previous block of the
+     * same component = the DC predictor */
+    uint8_t idx_comp[GJ_MAX_MCU_BLOCKS], idx_dx[GJ_MAX_MCU_BLOCKS], idx_dy[GJ_MAX_MCU_BLOCKS], idx_pred[GJ_MAX_MCU_BLOCKS];
+    uint8_t comp_hs[GJ_MAX_COMP], comp_vs[GJ_MAX_COMP];
+};
+
 struct gj_geometry {
     int width, height, comp_count;
     int pitch;            /* bytes per raw row */
     int data_width, data_height;
-    int bcx, bcy, nblk;   /* 8x8 blocks per component */
+    int bcx, bcy, nblk;   /* 8x8 blocks of component 0 */
     int interleaved;
     int restart_interval; /* as given (0 = none) */
     int seg_mcu;          /* MCUs per segment (restart_interval or all) */
     int scan_count;
     int comps_per_scan;   /* 1 (non-interleaved) or comp_count */
-    int seg_per_scan;
-    int seg_count;        /* scan_count * seg_per_scan */
+    int seg_per_scan;     /* segments of scan 0 (all scans when `lay.simple`) */
+    int seg_count;        /* all scans */
+    int max_hs, max_vs;   /* MCU size in blocks of the full-resolution plane */
+    int subsampled;       /* some component has fewer samples than the image */
+    struct gj_comp_geo comp[GJ_MAX_COMP];
+    struct gj_scan_layout lay;
     size_t raw_size;      /* bytes of the raw image */
     size_t coef_count;    /* int16 coefficients, all components */
     size_t slot_stride;   /* bytes reserved per segment in the encoder's scan tmp buffer */
@@ -162,7 +197,8 @@ int gj_launch_fdct_rgb444(const uint8_t* d_raw, int width, int height, int pitch
 struct gj_huff_enc_args {
     const int16_t* d_coef;
     const uint64_t* d_nzmask; /* [comp][block]: bit k set <=> zig-zag coefficient k is non-zero (written by K1) */
-    int nblk, comp_count, comps_per_scan, seg_mcu, seg_per_scan, scan_count;
+    struct gj_scan_layout lay; /* scans, segments and the block order inside them */
+    int seg_mcu;
     uint8_t* d_tmp;
     size_t slot_stride;
     uint32_t* d_spill;      /* [seg_count][32 lanes][32 words]: overflow of the per-lane bit strings (rarely touched) */
@@ -193,7 +229,8 @@ struct gj_huff_dec_args {
     uint32_t scan_begin[GJ_MAX_COMP];
     uint32_t* d_error;            /* set to non-zero by K3 when the RSTn sequence is broken */
     int dequantize;             /* 1: store coefficient*quantiser wrapped to int16 (integer IDCT flavour) */
-    int seg_count, seg_per_scan, scan_count, comps_per_scan, seg_mcu, nblk, comp_count;
+    struct gj_scan_layout lay;  /* scans, segments and the block order inside them */
+    int seg_count, seg_mcu;
     int scan_comp[GJ_MAX_COMP][GJ_MAX_COMP]; /* component index of the i-th component of scan s */
     int scan_td[GJ_MAX_COMP][GJ_MAX_COMP], scan_ta[GJ_MAX_COMP][GJ_MAX_COMP];
     int scan_tq[GJ_MAX_COMP][GJ_MAX_COMP]; /* quantisation table id of that component */
@@ -209,7 +246,7 @@ int gj_launch_marker_scan(const uint8_t* d_file, size_t begin, size_t end, uint3
                           gj_stream_t stream);
 /* rank of the first marker of every scan + restart-count validation (error -> d_result[3]) */
 int gj_launch_scan_ranks(const uint32_t* d_list_pos, const uint32_t* d_result, int scan_count, const uint32_t scan_begin[4],
-                         const uint32_t scan_end[4], int seg_per_scan, uint32_t* d_first_rank, gj_stream_t stream);
+                         const uint32_t scan_end[4], const int scan_segments[4], uint32_t* d_first_rank, gj_stream_t stream);
 
 /* K4: zig-zag coefficients -> RGB u8 interleaved (fused dequant + IDCT + colour transform)
  * idct_flavour: 0 = integer (gpujpeg_idct_cpu), 1 = float GPU-reference
@@ -217,6 +254,15 @@ int gj_launch_scan_ranks(const uint32_t* d_list_pos, const uint32_t* d_result, i
 int gj_launch_idct_rgb444(const int16_t* d_coef, int bcx, int bcy, const int comp_tq[3], uint8_t* d_raw, int width,
                           int height, int pitch, int idct_flavour, int coef_dequantized,
                           const struct gj_dev_dec_tables* d_tables, gj_stream_t stream);
+
+/* K1 / K4 for chroma-subsampled streams: luminance comp[0].hs x comp[0].vs in {2x1, 2x2, 1x2}, chrominance 1x1
+ * [replaces the subsampling template instances of ref: src/gpujpeg_preprocessor.cu:241-253,
+ *  src/gpujpeg_postprocessor.cu:271-282 plus the DCT launches] */
+int gj_launch_fdct_rgb_ss(const uint8_t* d_raw, int width, int height, int pitch, int16_t* d_coef, uint64_t* d_nzmask,
+                          const struct gj_comp_geo comp[3], const struct gj_dev_enc_tables* h_tables, gj_stream_t stream);
+int gj_launch_idct_rgb_ss(const int16_t* d_coef, const struct gj_comp_geo comp[3], const int comp_tq[3], uint8_t* d_raw,
+                          int width, int height, int pitch, int idct_flavour, int coef_dequantized,
+                          const struct gj_dev_dec_tables* h_tables, gj_stream_t stream);
 
 /* debug/test helper: device coefficient buffer (zig-zag) -> host natural order, block-major */
 int gj_coef_to_host_natural(const int16_t* d_coef, size_t count, int16_t* h_out, gj_stream_t stream);

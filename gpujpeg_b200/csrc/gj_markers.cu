@@ -162,10 +162,11 @@ k_marker_write(const uint8_t* __restrict__ file, size_t begin, size_t end, size_
 
 struct ScanBounds {
     uint32_t begin[4], end[4];
+    int segments[4];   // restart segments the geometry expects in each scan
 };
 /* one thread per scan: rank of its first marker in the list and a check of the restart count */
 __global__ void k_scan_ranks(const uint32_t* __restrict__ list_pos, uint32_t* result, int scan_count, ScanBounds sb,
-                             int seg_per_scan, uint32_t* __restrict__ first_rank)
+                             uint32_t* __restrict__ first_rank)
 {
     const int s = threadIdx.x;
     if ( s >= scan_count ) return;
@@ -182,21 +183,22 @@ __global__ void k_scan_ranks(const uint32_t* __restrict__ list_pos, uint32_t* re
         r[q] = lo;
     }
     first_rank[s] = r[0];
-    if ( r[1] - r[0] != (uint32_t)(seg_per_scan - 1) ) atomicExch(&result[3], 1u + (uint32_t)s);
+    if ( r[1] - r[0] != (uint32_t)(sb.segments[s] - 1) ) atomicExch(&result[3], 1u + (uint32_t)s);
 }
 
 }  // namespace
 
 extern "C" int gj_launch_scan_ranks(const uint32_t* d_list_pos, const uint32_t* d_result, int scan_count,
-                                    const uint32_t scan_begin[4], const uint32_t scan_end[4], int seg_per_scan,
+                                    const uint32_t scan_begin[4], const uint32_t scan_end[4], const int scan_segments[4],
                                     uint32_t* d_first_rank, gj_stream_t stream)
 {
     ScanBounds sb;
     for ( int i = 0; i < 4; i++ ) {
         sb.begin[i] = scan_begin[i];
         sb.end[i] = scan_end[i];
+        sb.segments[i] = scan_segments[i];
     }
-    k_scan_ranks<<<1, 32, 0, stream>>>(d_list_pos, const_cast<uint32_t*>(d_result), scan_count, sb, seg_per_scan, d_first_rank);
+    k_scan_ranks<<<1, 32, 0, stream>>>(d_list_pos, const_cast<uint32_t*>(d_result), scan_count, sb, d_first_rank);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

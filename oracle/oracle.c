@@ -795,6 +795,208 @@ size_t orc_encode_rgb(const uint8_t* rgb, int w, int h, int pad, int quality, in
 }
 
 /* ------------------------------------------------------------------------------------------- */
+/* chroma subsampling: component geometry, point-sampling preprocessor, whole-frame encode          */
+
+struct ogeo {
+    int hs, vs;        /* sampling factors */
+    int w, h;          /* samples carrying image data */
+    int dw, dh;        /* allocated plane (multiple of the component's MCU size) */
+    int bcx, bcy, nblk;
+    size_t off;        /* offset of the plane (samples) == offset of its coefficients */
+};
+
+/* [ref: src/gpujpeg_common.c:671-736] */
+static size_t ogeo_init(struct ogeo g[4], int comps, const int hs[4], const int vs[4], int w, int h, int interleaved,
+                        int* max_hs, int* max_vs)
+{
+    int mh = 1, mv = 1;
+    for ( int c = 0; c < comps; c++ ) {
+        if ( hs[c] > mh ) mh = hs[c];
+        if ( vs[c] > mv ) mv = vs[c];
+    }
+    size_t off = 0;
+    for ( int c = 0; c < comps; c++ ) {
+        int div_h = mh / hs[c], div_v = mv / vs[c];
+        g[c].hs = hs[c];
+        g[c].vs = vs[c];
+        g[c].w = ((w + div_h - 1) / div_h * div_h) * hs[c] / mh;
+        g[c].h = ((h + div_v - 1) / div_v * div_v) * vs[c] / mv;
+        int mx = interleaved ? 8 * hs[c] : 8, my = interleaved ? 8 * vs[c] : 8;
+        g[c].dw = (g[c].w + mx - 1) / mx * mx;
+        g[c].dh = (g[c].h + my - 1) / my * my;
+        g[c].bcx = g[c].dw / 8;
+        g[c].bcy = g[c].dh / 8;
+        g[c].nblk = g[c].bcx * g[c].bcy;
+        g[c].off = off;
+        off += (size_t)g[c].dw * g[c].dh;
+    }
+    *max_hs = mh;
+    *max_vs = mv;
+    return off;
+}
+
+/* block `i` (coding order) of MCU `m` of an interleaved scan -> pointer to its 64 coefficients
+ * [ref: src/gpujpeg_common.c:1056-1085] */
+static inline int16_t* mcu_block(int16_t* coef, const struct ogeo* g, int mcu_x, int m, int x, int y)
+{
+    int mx = m % mcu_x, my = m / mcu_x;
+    size_t b = (size_t)(my * g->vs + y) * g->bcx + (size_t)mx * g->hs + x;
+    return coef + g->off + b * 64;
+}
+
+/* RGB -> YCbCr planes; a component with divisor (dh,dv) keeps the sample of pixel (x,y) when x % dh == 0 and
+ * y % dv == 0 -- no filtering [ref: src/gpujpeg_preprocessor.cu:50-64]; everything else stays 0 */
+static void preprocess_rgb_ss(const uint8_t* rgb, int w, int h, int pad, uint8_t* planes, const struct ogeo g[3],
+                              int max_hs, int max_vs, size_t total)
+{
+    memset(planes, 0, total);
+    size_t pitch = (size_t)3 * w + pad;
+#pragma omp parallel for schedule(static)
+    for ( int y = 0; y < h; y++ ) {
+        const uint8_t* s = rgb + (size_t)y * pitch;
+        for ( int x = 0; x < w; x++ ) {
+            int r = (int)s[3 * x + 0] * 256 / 255;
+            int gg = (int)s[3 * x + 1] * 256 / 255;
+            int b = (int)s[3 * x + 2] * 256 / 255;
+            uint8_t v[3];
+            v[0] = clamp8(((77 * r + 150 * gg + 29 * b + 128) >> 8) + 0);
+            v[1] = clamp8(((-43 * r - 85 * gg + 128 * b + 128) >> 8) + 128);
+            v[2] = clamp8(((128 * r - 107 * gg - 21 * b + 128) >> 8) + 128);
+            for ( int c = 0; c < 3; c++ ) {
+                int dh = max_hs / g[c].hs, dv = max_vs / g[c].vs;
+                if ( x % dh || y % dv ) continue;
+                planes[g[c].off + (size_t)(y / dv) * g[c].dw + x / dh] = v[c];
+            }
+        }
+    }
+}
+
+/* planes -> RGB: every pixel takes the sample at (x / dh, y / dv) [ref: src/gpujpeg_postprocessor.cu:55-76] */
+static void postprocess_rgb_ss(const uint8_t* planes, const struct ogeo g[3], int max_hs, int max_vs, uint8_t* rgb, int w,
+                               int h, int pad)
+{
+    size_t pitch = (size_t)3 * w + pad;
+#pragma omp parallel for schedule(static)
+    for ( int y = 0; y < h; y++ ) {
+        uint8_t* d = rgb + (size_t)y * pitch;
+        for ( int x = 0; x < w; x++ ) {
+            int v[3];
+            for ( int c = 0; c < 3; c++ ) {
+                int dh = max_hs / g[c].hs, dv = max_vs / g[c].vs;
+                v[c] = planes[g[c].off + (size_t)(y / dv) * g[c].dw + x / dh];
+            }
+            int yy = (v[0] - 0) * 256 / 255;
+            int cb = (v[1] - 128) * 256 / 255;
+            int cr = (v[2] - 128) * 256 / 255;
+            d[3 * x + 0] = clamp8((256 * yy + 0 * cb + 359 * cr + 128) >> 8);
+            d[3 * x + 1] = clamp8((256 * yy - 88 * cb - 183 * cr + 128) >> 8);
+            d[3 * x + 2] = clamp8((256 * yy + 454 * cb + 0 * cr + 128) >> 8);
+        }
+    }
+}
+
+/* [ref: src/gpujpeg_encoder.c:351-646; block order of interleaved MCUs src/gpujpeg_common.c:1056-1085;
+ *       per-component scans src/gpujpeg_huffman_cpu_encoder.c:296-376] */
+size_t orc_encode_rgb_ss(const uint8_t* rgb, int w, int h, int pad, int quality, int rst, int interleaved, int lhs,
+                         int lvs, int threads, uint8_t* out, int16_t* coef_out)
+{
+    if ( w <= 0 || h <= 0 || w > 65535 || h > 65535 || rst < 0 || rst > 65535 ) return 0;
+    if ( lhs < 1 || lvs < 1 || lhs > 2 || lvs > 2 ) return 0;
+    enc_tables_init();
+#ifdef _OPENMP
+    int saved_threads = omp_get_max_threads();
+    omp_set_num_threads(threads > 1 ? threads : 1);
+#else
+    (void)threads;
+#endif
+    const int comps = 3;
+    const int hs[4] = {lhs, 1, 1, 0}, vs[4] = {lvs, 1, 1, 0};
+    struct ogeo g[4];
+    int max_hs, max_vs;
+    size_t total = ogeo_init(g, comps, hs, vs, w, h, interleaved, &max_hs, &max_vs);
+    uint8_t raw[2][64];
+    float fwd[2][64];
+    orc_quant_tables(quality, raw, fwd, NULL);
+    uint8_t* planes = (uint8_t*)scratch(0, total);
+    int16_t* coef = coef_out ? coef_out : (int16_t*)scratch(1, total * sizeof(int16_t));
+    preprocess_rgb_ss(rgb, w, h, pad, planes, g, max_hs, max_vs, total);
+    for ( int c = 0; c < comps; c++ )
+        orc_fdct_quant_plane(planes + g[c].off, g[c].dw, g[c].dh, fwd[c == 0 ? 0 : 1], coef + g[c].off);
+
+    /* header: as orc_write_header, with the sampling factors patched into SOF0 */
+    size_t hl = orc_write_header(out, w, h, quality, rst, comps);
+    for ( size_t i = 0; i + 9 < hl; i++ )
+        if ( out[i] == 0xFF && out[i + 1] == 0xC0 ) {
+            for ( int c = 0; c < comps; c++ )
+                out[i + 2 + 8 + 3 * c + 1] = (uint8_t)((hs[c] << 4) | vs[c]);
+            break;
+        }
+    uint8_t* p = out + hl;
+
+    int nscan = interleaved ? 1 : comps;
+    int bpm = 0;
+    for ( int c = 0; c < comps; c++ )
+        bpm += hs[c] * vs[c];
+    int mcu_x = g[0].bcx / g[0].hs;
+    int scan_mcus[4], scan_seg[4], seg_begin[5] = {0, 0, 0, 0, 0};
+    int max_mcus = 0;
+    for ( int k = 0; k < nscan; k++ ) {
+        scan_mcus[k] = interleaved ? mcu_x * (g[0].bcy / g[0].vs) : g[k].nblk;
+        if ( scan_mcus[k] > max_mcus ) max_mcus = scan_mcus[k];
+    }
+    int seg_mcu = rst > 0 ? rst : max_mcus;
+    for ( int k = 0; k < nscan; k++ ) {
+        /* rst == 0: one segment per scan [ref: src/gpujpeg_common.c:723-729] */
+        scan_seg[k] = rst > 0 ? (scan_mcus[k] + seg_mcu - 1) / seg_mcu : 1;
+        seg_begin[k + 1] = seg_begin[k] + scan_seg[k];
+    }
+    size_t total_seg = (size_t)seg_begin[nscan];
+    size_t slot = (size_t)seg_mcu * (interleaved ? bpm : 1) * 416 + 16;
+    size_t* seg_len = (size_t*)scratch(2, total_seg * sizeof(size_t));
+    uint8_t* tmp = (uint8_t*)scratch(3, total_seg * slot);
+    if ( !seg_len || !tmp ) return 0;
+#pragma omp parallel for schedule(dynamic, 16)
+    for ( long long si = 0; si < (long long)total_seg; si++ ) {
+        int scan = 0;
+        while ( scan + 1 < nscan && si >= seg_begin[scan + 1] )
+            scan++;
+        int s = (int)(si - seg_begin[scan]);
+        int first = rst > 0 ? s * seg_mcu : 0;
+        int cnt = rst > 0 ? (scan_mcus[scan] - first < seg_mcu ? scan_mcus[scan] - first : seg_mcu) : scan_mcus[scan];
+        uint8_t* o = tmp + (size_t)si * slot;
+        if ( !interleaved ) {
+            seg_len[si] = orc_huff_encode_segment(coef + g[scan].off + (size_t)first * 64, cnt, scan == 0 ? 0 : 1, o);
+        }
+        else {
+            struct bitw bw = {o, 0, 0};
+            int pred[3] = {0, 0, 0};
+            for ( int m = first; m < first + cnt; m++ )
+                for ( int c = 0; c < comps; c++ )
+                    for ( int y = 0; y < g[c].vs; y++ )
+                        for ( int x = 0; x < g[c].hs; x++ )
+                            encode_block(&bw, mcu_block(coef, &g[c], mcu_x, m, x, y), &pred[c], &g_enc[c == 0 ? 0 : 1][0],
+                                         &g_enc[c == 0 ? 0 : 1][1]);
+            flush_bits(&bw);
+            seg_len[si] = (size_t)(bw.p - o);
+        }
+    }
+    for ( int scan = 0; scan < nscan; scan++ ) {
+        p = write_sos(p, interleaved, comps, scan);
+        for ( int s = 0; s < scan_seg[scan]; s++ ) {
+            size_t si = (size_t)seg_begin[scan] + s;
+            memcpy(p, tmp + si * slot, seg_len[si]);
+            p += seg_len[si];
+            if ( s + 1 < scan_seg[scan] ) p = putm(p, 0xD0 + (s & 7));
+        }
+    }
+    p = putm(p, 0xD9);
+#ifdef _OPENMP
+    omp_set_num_threads(saved_threads);
+#endif
+    return (size_t)(p - out);
+}
+
+/* ------------------------------------------------------------------------------------------- */
 /* Huffman decoding of one restart segment (JPEG Annex F.2.2; behaviour on valid streams equals
  * [ref: src/gpujpeg_huffman_cpu_decoder.c:75-303])                                              */
 
@@ -1064,6 +1266,108 @@ int orc_probe(const uint8_t* jpeg, size_t size, struct orc_stream_info* info)
     return 0;
 }
 
+/* decode one block of an interleaved MCU (JPEG F.2.2) */
+static inline void decode_block(struct bitr* r, const struct dec_tab* dct, const struct dec_tab* act, int* pred, int16_t* blk)
+{
+    memset(blk, 0, 128);
+    int sz = decode_symbol(r, dct);
+    int diff = sz ? extend(get_bits(r, sz), sz) : 0;
+    *pred += diff;
+    blk[0] = (int16_t)*pred;
+    for ( int k = 1; k < 64; k++ ) {
+        int rs = decode_symbol(r, act);
+        int run = rs >> 4, z = rs & 15;
+        if ( z ) {
+            k += run;
+            int v = extend(get_bits(r, z), z);
+            if ( k < 64 ) blk[orc_zigzag_to_natural[k]] = (int16_t)v;
+        }
+        else {
+            if ( run != 15 ) break;
+            k += 15;
+        }
+    }
+}
+
+/* 3-component streams with chroma subsampling, interleaved or one scan per component
+ * [ref: src/gpujpeg_huffman_cpu_decoder.c:305-420; src/gpujpeg_postprocessor.cu:55-76] */
+static int decode_subsampled(const struct parsed* P, const uint8_t* jpeg, int idct_flavour, int threads, uint8_t* rgb,
+                             int16_t* coef_out)
+{
+#ifdef _OPENMP
+    int saved_threads = omp_get_max_threads();
+    omp_set_num_threads(threads > 1 ? threads : 1);
+#else
+    (void)threads;
+#endif
+    int hs[4] = {0, 0, 0, 0}, vs[4] = {0, 0, 0, 0};
+    for ( int c = 0; c < 3; c++ ) {
+        hs[c] = P->comp_hv[c] >> 4;
+        vs[c] = P->comp_hv[c] & 15;
+        if ( hs[c] < 1 || vs[c] < 1 || hs[c] > 4 || vs[c] > 4 ) return -1;
+    }
+    const int interleaved = P->nscan == 1;
+    if ( !interleaved && P->nscan != 3 ) return -1;
+    struct ogeo g[4];
+    int max_hs, max_vs;
+    size_t total = ogeo_init(g, 3, hs, vs, P->w, P->h, interleaved, &max_hs, &max_vs);
+    for ( int c = 0; c < 3; c++ )
+        if ( max_hs % hs[c] || max_vs % vs[c] ) return -1;
+    int16_t* coef = coef_out ? coef_out : (int16_t*)scratch(4, total * sizeof(int16_t));
+    int mcu_x = g[0].bcx / g[0].hs;
+    int rc = 0;
+    for ( int s = 0; s < P->nscan && rc == 0; s++ ) {
+        int mcus = interleaved ? mcu_x * (g[0].bcy / g[0].vs) : g[P->scan[s].comp[0]].nblk;
+        int seg_mcu = P->rst > 0 ? P->rst : mcus;
+        int nseg = (mcus + seg_mcu - 1) / seg_mcu;
+        size_t* so = (size_t*)scratch(5, sizeof(size_t) * (nseg + 1));
+        size_t* sl = (size_t*)scratch(6, sizeof(size_t) * (nseg + 1));
+        int n = split_scan(jpeg, P->scan[s].begin, P->scan[s].end, so, sl, nseg + 1);
+        if ( n != nseg ) { rc = -1; break; }
+        if ( (interleaved && P->scan[s].ncomp != 3) || (!interleaved && P->scan[s].ncomp != 1) ) { rc = -1; break; }
+        struct dec_tab dct[4], act[4];
+        for ( int c = 0; c < P->scan[s].ncomp; c++ ) {
+            dec_table_build(&dct[c], P->hbits[0][P->scan[s].td[c]], P->hvals[0][P->scan[s].td[c]]);
+            dec_table_build(&act[c], P->hbits[1][P->scan[s].ta[c]], P->hvals[1][P->scan[s].ta[c]]);
+        }
+#pragma omp parallel for schedule(dynamic, 16)
+        for ( int q = 0; q < nseg; q++ ) {
+            int first = q * seg_mcu;
+            int cnt = mcus - first < seg_mcu ? mcus - first : seg_mcu;
+            struct bitr r = {jpeg + so[q], jpeg + so[q] + sl[q], 0, 0};
+            int pred[4] = {0, 0, 0, 0};
+            if ( !interleaved ) {
+                const struct ogeo* k = &g[P->scan[s].comp[0]];
+                for ( int m = first; m < first + cnt; m++ )
+                    decode_block(&r, &dct[0], &act[0], &pred[0], coef + k->off + (size_t)m * 64);
+            }
+            else {
+                for ( int m = first; m < first + cnt; m++ )
+                    for ( int c = 0; c < 3; c++ ) {
+                        const struct ogeo* k = &g[P->scan[s].comp[c]];
+                        for ( int y = 0; y < k->vs; y++ )
+                            for ( int x = 0; x < k->hs; x++ )
+                                decode_block(&r, &dct[c], &act[c], &pred[c], mcu_block(coef, k, mcu_x, m, x, y));
+                    }
+            }
+        }
+    }
+    if ( rc == 0 && rgb ) {
+        uint8_t* planes = (uint8_t*)scratch(7, total);
+        for ( int c = 0; c < 3; c++ ) {
+            uint16_t inv[64];
+            for ( int i = 0; i < 64; i++ )
+                inv[orc_zigzag_to_natural[i]] = P->qt[P->comp_tq[c]][i];
+            orc_idct_plane(coef + g[c].off, g[c].dw, g[c].dh, inv, idct_flavour, planes + g[c].off);
+        }
+        postprocess_rgb_ss(planes, g, max_hs, max_vs, rgb, P->w, P->h, 0);
+    }
+#ifdef _OPENMP
+    omp_set_num_threads(saved_threads);
+#endif
+    return rc;
+}
+
 /* [ref: src/gpujpeg_decoder.c:234-469 with the CPU Huffman path :275-295 and gpujpeg_idct_cpu] */
 int orc_decode_rgb(const uint8_t* jpeg, size_t size, int idct_flavour, int threads, uint8_t* rgb, int* w,
                    int* h, int* comps, int16_t* coef_out)
@@ -1075,8 +1379,8 @@ int orc_decode_rgb(const uint8_t* jpeg, size_t size, int idct_flavour, int threa
     if ( comps ) *comps = P.comps;
     if ( !rgb && !coef_out ) return 0;
     if ( P.comps != 3 && P.comps != 1 ) return -1;
-    for ( int c = 0; c < P.comps; c++ )
-        if ( P.comp_hv[c] != 0x11 ) return -1; /* 4:4:4 only */
+    if ( P.comps == 3 && (P.comp_hv[0] != 0x11 || P.comp_hv[1] != 0x11 || P.comp_hv[2] != 0x11) )
+        return decode_subsampled(&P, jpeg, idct_flavour, threads, rgb, coef_out);
 #ifdef _OPENMP
     int saved_threads = omp_get_max_threads();
     omp_set_num_threads(threads > 1 ? threads : 1);

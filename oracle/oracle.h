@@ -70,7 +70,12 @@ size_t orc_write_header(uint8_t* out, int w, int h, int quality, int rst, int co
  * If coef_out != NULL it receives all quantised coefficients (3 planes, block-major natural). */
 size_t orc_encode_rgb(const uint8_t* rgb, int w, int h, int pad, int quality, int rst, int interleaved,
                       int threads, uint8_t* out, int16_t* coef_out);
-/* Decode a baseline JPEG produced by this codec family (3 comp 4:4:4 or 1 comp) to RGB/gray u8.
+/* Same with chroma subsampling: luminance sampling factors lhs x lvs in {1,2} (2x2 = 4:2:0, 2x1 = 4:2:2,
+ * 1x2 = 4:4:0), chrominance 1x1; chroma is point-sampled as the reference's preprocessor does.
+ * coef_out layout: component after component, each block-major natural over ITS block grid. */
+size_t orc_encode_rgb_ss(const uint8_t* rgb, int w, int h, int pad, int quality, int rst, int interleaved, int lhs,
+                         int lvs, int threads, uint8_t* out, int16_t* coef_out);
+/* Decode a baseline JPEG produced by this codec family (3 comp, any of the above samplings, or 1 comp) to RGB/gray u8.
  * Returns 0 on success; fills w,h,comps.  rgb may be NULL to probe. coef_out optional. */
 int orc_decode_rgb(const uint8_t* jpeg, size_t size, int idct_flavour, int threads, uint8_t* rgb,
                    int* w, int* h, int* comps, int16_t* coef_out);

@@ -53,42 +53,47 @@ struct geom {
     int seg_count;
 };
 
-static int geom_init(struct geom* g, int w, int h, int comps, int rst, int interleaved, int16_t* coef)
+static int geom_init(struct geom* g, int w, int h, int comps, int rst, int interleaved, int lhs, int lvs, int16_t* coef)
 {
     memset(g, 0, sizeof *g);
-    int dw = (w + 7) / 8 * 8, dh = (h + 7) / 8 * 8;
-    size_t psz = (size_t)dw * dh;
+    const int max_h = lhs, max_v = lvs;   /* luminance carries the maximum, chrominance is 1x1 */
+    size_t off = 0;
     for ( int c = 0; c < comps; c++ ) {
         struct gpujpeg_component* k = &g->comp[c];
+        const int sh = c == 0 ? lhs : 1, sv = c == 0 ? lvs : 1;
+        const int div_h = max_h / sh, div_v = max_v / sv;
         k->type = c == 0 ? GPUJPEG_COMPONENT_LUMINANCE : GPUJPEG_COMPONENT_CHROMINANCE;
-        k->sampling_factor.horizontal = 1;
-        k->sampling_factor.vertical = 1;
-        k->width = w;
-        k->height = h;
-        k->data_width = dw;
-        k->data_height = dh;
-        k->data_size = psz;
-        k->mcu_size_x = k->mcu_size_y = 8;
-        k->mcu_size = 64;
-        k->mcu_count_x = dw / 8;
-        k->mcu_count_y = dh / 8;
+        k->sampling_factor.horizontal = sh;
+        k->sampling_factor.vertical = sv;
+        k->width = ((w + div_h - 1) / div_h * div_h) * sh / max_h;
+        k->height = ((h + div_v - 1) / div_v * div_v) * sv / max_v;
+        k->mcu_size_x = interleaved ? 8 * sh : 8;
+        k->mcu_size_y = interleaved ? 8 * sv : 8;
+        k->mcu_size = k->mcu_size_x * k->mcu_size_y;
+        k->data_width = (k->width + k->mcu_size_x - 1) / k->mcu_size_x * k->mcu_size_x;
+        k->data_height = (k->height + k->mcu_size_y - 1) / k->mcu_size_y * k->mcu_size_y;
+        k->data_size = (size_t)k->data_width * k->data_height;
+        k->mcu_count_x = k->data_width / k->mcu_size_x;
+        k->mcu_count_y = k->data_height / k->mcu_size_y;
         k->mcu_count = k->mcu_count_x * k->mcu_count_y;
         k->segment_mcu_count = rst ? rst : k->mcu_count;
         k->segment_count = (k->mcu_count + k->segment_mcu_count - 1) / k->segment_mcu_count;
-        k->data_quantized = coef + c * psz;
+        k->data_quantized = coef + off;
+        off += k->data_size;
     }
     int nscan = interleaved ? 1 : comps;
-    int per = g->comp[0].segment_count;
-    g->seg_count = nscan * per;
+    g->seg_count = 0;
+    for ( int s = 0; s < nscan; s++ )
+        g->seg_count += g->comp[s].segment_count;
     g->seg = (struct gpujpeg_segment*)calloc(g->seg_count, sizeof(struct gpujpeg_segment));
     if ( !g->seg ) return -1;
     int i = 0;
     for ( int s = 0; s < nscan; s++ ) {
-        for ( int j = 0; j < per; j++, i++ ) {
+        for ( int j = 0; j < g->comp[s].segment_count; j++, i++ ) {
             g->seg[i].scan_index = s;
             g->seg[i].scan_segment_index = j;
-            int left = g->comp[0].mcu_count - j * g->comp[0].segment_mcu_count;
-            g->seg[i].mcu_count = left < g->comp[0].segment_mcu_count ? left : g->comp[0].segment_mcu_count;
+            int left = g->comp[s].mcu_count - j * g->comp[s].segment_mcu_count;
+            g->seg[i].mcu_count = left < g->comp[s].segment_mcu_count ? left : g->comp[s].segment_mcu_count;
         }
     }
     return 0;
@@ -131,22 +136,22 @@ int ref_huff_encoder_table(int cls, int kind, uint32_t code[256], uint8_t size[2
  * writer + reference CPU Huffman encoder + EOI
  * [ref: src/gpujpeg_encoder.c:504-534, 626; src/gpujpeg_writer.c:456-518;
  *       src/gpujpeg_huffman_cpu_encoder.c:296-376] */
-size_t ref_encode_from_coef(int16_t* coef, int w, int h, int comps, int quality, int rst, int interleaved,
-                            uint8_t* out, size_t out_cap)
+size_t ref_encode_from_coef_ss(int16_t* coef, int w, int h, int comps, int quality, int rst, int interleaved, int lhs,
+                               int lvs, uint8_t* out, size_t out_cap)
 {
     struct gpujpeg_encoder* enc = (struct gpujpeg_encoder*)calloc(1, sizeof *enc);
     struct gpujpeg_writer wr;
     struct geom g;
     memset(&wr, 0, sizeof wr);
-    if ( !enc || geom_init(&g, w, h, comps, rst, interleaved, coef) != 0 ) return 0;
+    if ( !enc || geom_init(&g, w, h, comps, rst, interleaved, lhs, lvs, coef) != 0 ) return 0;
     memset(&enc->coder.param, 0, sizeof enc->coder.param); /* same values gpujpeg_set_default_parameters gives */
     enc->coder.param.quality = quality;
     enc->coder.param.restart_interval = rst;
     enc->coder.param.interleaved = interleaved;
     enc->coder.param.comp_count = comps;
     for ( int c = 0; c < comps; c++ ) {
-        enc->coder.param.sampling_factor[c].horizontal = 1;
-        enc->coder.param.sampling_factor[c].vertical = 1;
+        enc->coder.param.sampling_factor[c].horizontal = c == 0 ? lhs : 1;
+        enc->coder.param.sampling_factor[c].vertical = c == 0 ? lvs : 1;
     }
     enc->coder.param.color_space_internal = GPUJPEG_YCBCR_BT601_256LVLS;
     memset(&enc->coder.param_image, 0, sizeof enc->coder.param_image);
@@ -183,18 +188,24 @@ size_t ref_encode_from_coef(int16_t* coef, int w, int h, int comps, int quality,
     return n;
 }
 
+size_t ref_encode_from_coef(int16_t* coef, int w, int h, int comps, int quality, int rst, int interleaved,
+                            uint8_t* out, size_t out_cap)
+{
+    return ref_encode_from_coef_ss(coef, w, h, comps, quality, rst, interleaved, 1, 1, out, out_cap);
+}
+
 /* Decode entropy-coded data with the reference CPU Huffman decoder.  The caller supplies the
  * segment table (scan index, index in scan, byte offset, byte size -- markers stripped, stuffing
  * kept) exactly as the reference reader would build it [ref: src/gpujpeg_reader.c:1038-1155], and
  * the DHT contents per table id.  [ref: src/gpujpeg_huffman_cpu_decoder.c:371-425] */
-int ref_huff_decode(const uint8_t* data, size_t data_size, int w, int h, int comps, int rst, int interleaved,
-                    int nseg, const int* seg_scan, const int* seg_index, const size_t* seg_off,
-                    const size_t* seg_size, const uint8_t dht_bits[2][2][17], const uint8_t dht_vals[2][2][256],
-                    int16_t* coef)
+int ref_huff_decode_ss(const uint8_t* data, size_t data_size, int w, int h, int comps, int rst, int interleaved, int lhs,
+                       int lvs, int nseg, const int* seg_scan, const int* seg_index, const size_t* seg_off,
+                       const size_t* seg_size, const uint8_t dht_bits[2][2][17], const uint8_t dht_vals[2][2][256],
+                       int16_t* coef)
 {
     struct gpujpeg_decoder* dec = (struct gpujpeg_decoder*)calloc(1, sizeof *dec);
     struct geom g;
-    if ( !dec || geom_init(&g, w, h, comps, rst, interleaved, coef) != 0 ) return -1;
+    if ( !dec || geom_init(&g, w, h, comps, rst, interleaved, lhs, lvs, coef) != 0 ) return -1;
     if ( nseg != g.seg_count ) return -2;
     for ( int i = 0; i < nseg; i++ ) {
         g.seg[i].scan_index = seg_scan[i];
@@ -227,6 +238,15 @@ int ref_huff_decode(const uint8_t* data, size_t data_size, int w, int h, int com
     free(g.seg);
     free(dec);
     return rc;
+}
+
+int ref_huff_decode(const uint8_t* data, size_t data_size, int w, int h, int comps, int rst, int interleaved,
+                    int nseg, const int* seg_scan, const int* seg_index, const size_t* seg_off,
+                    const size_t* seg_size, const uint8_t dht_bits[2][2][17], const uint8_t dht_vals[2][2][256],
+                    int16_t* coef)
+{
+    return ref_huff_decode_ss(data, data_size, w, h, comps, rst, interleaved, 1, 1, nseg, seg_scan, seg_index, seg_off,
+                              seg_size, dht_bits, dht_vals, coef);
 }
 
 /* dequantise + integer IDCT of one block, in place, result before the +128 level shift

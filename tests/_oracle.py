@@ -43,6 +43,9 @@ lib.orc_write_header.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_i
 lib.orc_write_header.restype = C.c_size_t
 lib.orc_encode_rgb.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_void_p]
 lib.orc_encode_rgb.restype = C.c_size_t
+lib.orc_encode_rgb_ss.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  _u8p, C.c_void_p]
+lib.orc_encode_rgb_ss.restype = C.c_size_t
 lib.orc_decode_rgb.argtypes = [_u8p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int),
                                C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
 lib.orc_probe.argtypes = [_u8p, C.c_size_t, C.POINTER(StreamInfo)]
@@ -75,17 +78,55 @@ def quant_tables(quality):
     return raw, fwd, inv
 
 
-def encode(rgb, quality=75, rst=24, interleaved=0, threads=1, want_coef=False, pad=0):
+SAMPLINGS = {"444": (1, 1), "422": (2, 1), "420": (2, 2), "440": (1, 2)}
+
+
+def plane_geometry(w, h, sampling=(1, 1), interleaved=0, comps=3):
+    """Per-component (data_width, data_height) as the reference lays the planes out
+    [ref: src/gpujpeg_common.c:671-736]: luminance carries the sampling factors, chrominance is 1x1."""
+    mh, mv = sampling
+    out = []
+    for c in range(comps):
+        hs, vs = (mh, mv) if c == 0 else (1, 1)
+        dh_, dv_ = mh // hs, mv // vs
+        cw = (w + dh_ - 1) // dh_ * dh_ * hs // mh
+        ch = (h + dv_ - 1) // dv_ * dv_ * vs // mv
+        mx, my = (8 * hs, 8 * vs) if interleaved else (8, 8)
+        out.append(((cw + mx - 1) // mx * mx, (ch + my - 1) // my * my))
+    return out
+
+
+def coef_count(w, h, sampling=(1, 1), interleaved=0, comps=3):
+    return sum(a * b for a, b in plane_geometry(w, h, sampling, interleaved, comps))
+
+
+def encode(rgb, quality=75, rst=24, interleaved=0, threads=1, want_coef=False, pad=0, sampling=(1, 1)):
+    """Returns the JPEG bytes (and, with want_coef, the quantised coefficients: (3, dw*dh) for 4:4:4, a flat array
+    component after component for subsampled modes)."""
     h, w = rgb.shape[:2]
     rgb = np.ascontiguousarray(rgb)
     out = np.empty(1000 + w * h * 6 + 4096, np.uint8)
-    dw, dh = (w + 7) // 8 * 8, (h + 7) // 8 * 8
-    coef = np.zeros((3, dw * dh), np.int16) if want_coef else None
-    n = lib.orc_encode_rgb(rgb.reshape(-1), w, h, pad, quality, rst, interleaved, threads, out,
-                           coef.ctypes.data if want_coef else None)
+    if tuple(sampling) == (1, 1):
+        dw, dh = (w + 7) // 8 * 8, (h + 7) // 8 * 8
+        coef = np.zeros((3, dw * dh), np.int16) if want_coef else None
+        n = lib.orc_encode_rgb(rgb.reshape(-1), w, h, pad, quality, rst, interleaved, threads, out,
+                               coef.ctypes.data if want_coef else None)
+    else:
+        coef = np.zeros(coef_count(w, h, sampling, interleaved), np.int16) if want_coef else None
+        n = lib.orc_encode_rgb_ss(rgb.reshape(-1), w, h, pad, quality, rst, interleaved, sampling[0], sampling[1],
+                                  threads, out, coef.ctypes.data if want_coef else None)
     assert n > 0
     jpeg = out[:n].copy()
     return (jpeg, coef) if want_coef else jpeg
+
+
+def stream_sampling(jpeg):
+    """(luma_h, luma_v) and interleaved flag read from SOF0 / the first SOS of a stream of this codec family."""
+    j = bytes(jpeg[:2048])
+    i = j.index(b"\xff\xc0")
+    hv = j[i + 2 + 8 + 1]
+    k = j.index(b"\xff\xda")
+    return (hv >> 4, hv & 15), int(j[k + 4] > 1)
 
 
 def decode(jpeg, flavour=IDCT_INT, threads=1, want_coef=False):
@@ -94,8 +135,12 @@ def decode(jpeg, flavour=IDCT_INT, threads=1, want_coef=False):
     rc = lib.orc_decode_rgb(jpeg, jpeg.size, flavour, threads, None, C.byref(w), C.byref(h), C.byref(c), None)
     assert rc == 0, "oracle could not parse stream"
     img = np.empty((h.value, w.value, c.value), np.uint8)
-    dw, dh = (w.value + 7) // 8 * 8, (h.value + 7) // 8 * 8
-    coef = np.zeros((c.value, dw * dh), np.int16) if want_coef else None
+    sampling, il = stream_sampling(jpeg) if c.value == 3 else ((1, 1), 0)
+    if sampling == (1, 1):
+        dw, dh = (w.value + 7) // 8 * 8, (h.value + 7) // 8 * 8
+        coef = np.zeros((c.value, dw * dh), np.int16) if want_coef else None
+    else:
+        coef = np.zeros(coef_count(w.value, h.value, sampling, il), np.int16) if want_coef else None
     rc = lib.orc_decode_rgb(jpeg, jpeg.size, flavour, threads, img.ctypes.data, C.byref(w), C.byref(h), C.byref(c),
                             coef.ctypes.data if want_coef else None)
     assert rc == 0, "oracle decode failed"
@@ -123,4 +168,11 @@ if os.path.exists(_REF_SO):
                                     np.ctypeslib.ndpointer(np.int32), np.ctypeslib.ndpointer(np.int32),
                                     np.ctypeslib.ndpointer(np.uint64), np.ctypeslib.ndpointer(np.uint64),
                                     _u8p, _u8p, _i16p]
+    ref.ref_encode_from_coef_ss.argtypes = [_i16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            _u8p, C.c_size_t]
+    ref.ref_encode_from_coef_ss.restype = C.c_size_t
+    ref.ref_huff_decode_ss.argtypes = [_u8p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, np.ctypeslib.ndpointer(np.int32), np.ctypeslib.ndpointer(np.int32),
+                                       np.ctypeslib.ndpointer(np.uint64), np.ctypeslib.ndpointer(np.uint64),
+                                       _u8p, _u8p, _i16p]
     ref.ref_idct_block.argtypes = [_i16p, np.ctypeslib.ndpointer(np.uint16)]

@@ -4,10 +4,10 @@ import numpy as np
 import _oracle as o
 
 
-def ref_encode_coef(coef, w, h, quality, rst, interleaved=0, comps=3):
+def ref_encode_coef(coef, w, h, quality, rst, interleaved=0, comps=3, sampling=(1, 1)):
     out = np.empty(4096 + coef.size * 8, np.uint8)
-    n = o.ref.ref_encode_from_coef(np.ascontiguousarray(coef).reshape(-1), w, h, comps, quality, rst, interleaved,
-                                   out, out.size)
+    n = o.ref.ref_encode_from_coef_ss(np.ascontiguousarray(coef).reshape(-1), w, h, comps, quality, rst, interleaved,
+                                      sampling[0], sampling[1], out, out.size)
     assert n > 0
     return out[:n].copy()
 
@@ -59,12 +59,15 @@ def split_segments(jpeg):
     return a, bits, vals
 
 
-def ref_decode_coef(jpeg, w, h, rst, interleaved=0, comps=3):
+def ref_decode_coef(jpeg, w, h, rst, interleaved=0, comps=3, sampling=(1, 1)):
     segs, bits, vals = split_segments(jpeg)
-    dw, dh = (w + 7) // 8 * 8, (h + 7) // 8 * 8
-    coef = np.zeros((comps, dw * dh), np.int16)
+    if tuple(sampling) == (1, 1):
+        dw, dh = (w + 7) // 8 * 8, (h + 7) // 8 * 8
+        coef = np.zeros((comps, dw * dh), np.int16)
+    else:
+        coef = np.zeros(o.coef_count(w, h, sampling, interleaved, comps), np.int16)
     data = np.ascontiguousarray(jpeg, np.uint8)
-    rc = o.ref.ref_huff_decode(data, data.size, w, h, comps, rst, interleaved, len(segs),
+    rc = o.ref.ref_huff_decode_ss(data, data.size, w, h, comps, rst, interleaved, sampling[0], sampling[1], len(segs),
                                segs[:, 0].astype(np.int32).copy(), segs[:, 1].astype(np.int32).copy(),
                                segs[:, 2].astype(np.uint64).copy(), segs[:, 3].astype(np.uint64).copy(),
                                np.ascontiguousarray(bits).reshape(-1), np.ascontiguousarray(vals).reshape(-1),

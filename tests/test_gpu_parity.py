@@ -90,6 +90,78 @@ def test_decode_float_gpuref_flavour(gj, kind, w, h, q):
         d.close()
 
 
+# ---- chroma subsampling: 4:2:0, 4:2:2, 4:4:0, interleaved or one scan per component ----
+SS_MODES = [("4:2:0", (2, 2)), ("4:2:2", (2, 1)), ("4:4:0", (1, 2))]
+SS_CASES = [  # kind, w, h, quality, rst
+    ("photo", 1920, 1080, 75, 12),
+    ("random", 1119, 561, 75, 8),    # W, H odd: chroma planes round up, MCU padding in the interleaved scan
+    ("random", 33, 17, 90, 2),
+    ("photo", 16, 16, 75, 1),
+    ("random", 100, 50, 60, 0),      # no restart markers: one segment per scan
+    ("photo", 2048, 16, 95, 300),    # segments longer than one warp round
+    ("random", 520, 72, 1, 5),
+]
+
+
+def dequantized(want_coef, q, w, h, sampling, il):
+    """oracle coefficients (flat, component after component) times the quantiser, wrapped to int16"""
+    _, _, inv = o.quant_tables(q)
+    out, off = [], 0
+    for c, (dw, dh) in enumerate(o.plane_geometry(w, h, sampling, il)):
+        blk = want_coef[off:off + dw * dh].reshape(-1, 64).astype(np.int32)
+        out.append((blk * inv[0 if c == 0 else 1].astype(np.int32)).astype(np.int16).reshape(-1))
+        off += dw * dh
+    return np.concatenate(out)
+
+
+@pytest.mark.parametrize("il", [0, 1])
+@pytest.mark.parametrize("name,sampling", SS_MODES)
+@pytest.mark.parametrize("kind,w,h,q,rst", SS_CASES)
+def test_subsampled_encode_bit_exact(enc, kind, w, h, q, rst, name, sampling, il):
+    img = o.gen_image(kind, w, h)
+    want, want_coef = o.encode(img, q, rst, il, want_coef=True, threads=4, sampling=sampling)
+    got = enc.encode(img, q, rst, il, subsampling=name)
+    assert np.array_equal(enc.coefficients(w, h, sampling, il), want_coef), "K1 coefficients differ from the oracle"
+    assert got.size == want.size and np.array_equal(got, want), "JPEG bytes differ from the oracle"
+
+
+@pytest.mark.parametrize("il", [0, 1])
+@pytest.mark.parametrize("name,sampling", SS_MODES)
+@pytest.mark.parametrize("kind,w,h,q,rst", SS_CASES)
+def test_subsampled_decode_bit_exact(gj, dec, kind, w, h, q, rst, name, sampling, il):
+    jpeg = o.encode(o.gen_image(kind, w, h), q, rst, il, threads=4, sampling=sampling)
+    want, want_coef = o.decode(jpeg, o.IDCT_INT, want_coef=True, threads=4)
+    got = dec.decode(jpeg)
+    got_coef, deq = dec.coefficients(w, h, sampling, il)
+    assert np.array_equal(got_coef, dequantized(want_coef, q, w, h, sampling, il) if deq else want_coef), "K3 differs"
+    assert got.shape == want.shape and np.array_equal(got, want), "decoded pixels differ from the oracle (int IDCT)"
+
+
+@pytest.mark.parametrize("name,sampling", SS_MODES)
+def test_subsampled_decode_float_flavour(gj, name, sampling):
+    jpeg = o.encode(o.gen_image("photo", 333, 77), 85, 6, 1, sampling=sampling)
+    d = gj.Decoder(idct="float_gpuref")
+    try:
+        assert np.array_equal(d.decode(jpeg), o.decode(jpeg, o.IDCT_FLOAT_GPUREF))
+    finally:
+        d.close()
+
+
+def test_subsampled_8k_round_trip(enc, dec):
+    """full-size 4:2:0 interleaved (what video pipelines feed): bytes and pixels against the threaded oracle,
+    then back to 4:4:4 on the same coder instances (re-initialisation across sampling modes)"""
+    w, h = 7680, 4320
+    img = o.gen_image("photo", w, h)
+    want = o.encode(img, 75, 6, 1, threads=8, sampling=(2, 2))
+    got = enc.encode(img, 75, 6, 1, subsampling="4:2:0")
+    assert got.size == want.size and np.array_equal(got, want)
+    assert np.array_equal(dec.decode(got), o.decode(want, threads=8))
+    small = o.gen_image("random", 64, 64)
+    j = enc.encode(small, 75, 4)
+    assert np.array_equal(j, o.encode(small, 75, 4))
+    assert np.array_equal(dec.decode(j), o.decode(j))
+
+
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
 
 
