@@ -2,7 +2,7 @@
 by oracle/Makefile `refgpu`) in a process of its own, so its gpujpeg_* symbols never meet the product's.
 Test/bench infrastructure only.
 
-    python tests/_refgpu.py encode <kind> <w> <h> <q> <rst> <interleaved> <out.jpg>
+    python tests/_refgpu.py encode <kind> <w> <h> <q> <rst> <interleaved> <out.jpg> [<luma_h> <luma_v>]
     python tests/_refgpu.py decode <in.jpg> <out.rgb>
     python tests/_refgpu.py bench  <kind> <w> <h> <q> <rst> <iters>      -> prints JSON with ms per frame
 """
@@ -96,6 +96,9 @@ def main():
         img = gen(kind, w, h)
         enc = lib.gpujpeg_encoder_create(None)
         p, pi = params(lib, w, h, q, rst, il)
+        if len(sys.argv) > 10:   # chroma subsampling: GPUJPEG_SUBSAMPLING_xxx packing, first component on top
+            lib.gpujpeg_parameters_chroma_subsampling.argtypes = [C.POINTER(Param), C.c_uint32]
+            lib.gpujpeg_parameters_chroma_subsampling(C.byref(p), int(sys.argv[9]) << 28 | int(sys.argv[10]) << 24 | 0x111100)
         encode(lib, enc, img, p, pi).tofile(path)
         lib.gpujpeg_encoder_destroy(enc)
     elif mode == "decode":

@@ -105,3 +105,36 @@ int shim_geometry(int width, int height, int rst, int interleaved, long* out /*[
     out[5] = g.scan_count; out[6] = (long)g.slot_stride; out[7] = (long)g.coef_count;
     return 0;
 }
+
+/* geometry with chroma subsampling: per component {bcx, bcy, blk_off}, then per scan segment counts,
+ * then {seg_count, seg_mcu, bpm, mcu_x, coef_count, slot_stride} */
+int shim_geometry_ss(int width, int height, int rst, int interleaved, int lhs, int lvs, long* out /*[24]*/)
+{
+    struct gpujpeg_parameters p;
+    struct gpujpeg_image_parameters pi;
+    memset(&p, 0, sizeof p);
+    memset(&pi, 0, sizeof pi);
+    p.restart_interval = rst;
+    p.interleaved = interleaved;
+    p.comp_count = 3;
+    for ( int c = 0; c < 3; c++ ) {
+        p.sampling_factor[c].horizontal = (uint8_t)(c == 0 ? lhs : 1);
+        p.sampling_factor[c].vertical = (uint8_t)(c == 0 ? lvs : 1);
+    }
+    pi.width = width;
+    pi.height = height;
+    struct gj_geometry g;
+    if ( gj_geometry_init(&g, &p, &pi) ) return -1;
+    for ( int c = 0; c < 3; c++ ) {
+        out[3 * c] = g.comp[c].bcx;
+        out[3 * c + 1] = g.comp[c].bcy;
+        out[3 * c + 2] = g.comp[c].blk_off;
+    }
+    for ( int k = 0; k < 4; k++ )
+        out[9 + k] = g.lay.scan_seg_begin[k + 1] - g.lay.scan_seg_begin[k];
+    out[13] = g.seg_count; out[14] = g.seg_mcu; out[15] = g.lay.bpm; out[16] = g.lay.mcu_x;
+    out[17] = (long)g.coef_count; out[18] = (long)g.slot_stride; out[19] = g.lay.simple;
+    for ( int i = 0; i < 4; i++ )
+        out[20 + i] = i < g.lay.bpm ? g.lay.idx_pred[i] : 0;
+    return 0;
+}

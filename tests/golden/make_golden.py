@@ -31,8 +31,24 @@ CASES = [  # name, kind, w, h, quality, rst, interleaved
 ]
 
 
+SS_CASES = [  # name, kind, w, h, quality, rst, interleaved, luminance sampling (chrominance 1x1)
+    ("ss420_photo_72x56_q75_r3_il", "photo", 72, 56, 75, 3, 1, (2, 2)),
+    ("ss422_random_33x17_q90_r2", "random", 33, 17, 90, 2, 0, (2, 1)),
+    ("ss440_random_40x24_q60_r0_il", "random", 40, 24, 60, 0, 1, (1, 2)),
+    ("ss420_random_50x30_q85_r4", "random", 50, 30, 85, 4, 0, (2, 2)),
+]
+
+
 def main():
     assert o.ref is not None, "build oracle/_ref first (make -C oracle ref)"
+    for name, kind, w, h, q, rst, il, samp in SS_CASES:
+        img = o.gen_image(kind, w, h)
+        _, coef = o.encode(img, q, rst, il, want_coef=True, sampling=samp)
+        jpeg = ref_encode_coef(coef, w, h, q, rst, il, sampling=samp)
+        coef_dec = ref_decode_coef(jpeg, w, h, rst, il, sampling=samp)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), kind=kind, w=w, h=h, quality=q, rst=rst, interleaved=il,
+                            sampling=np.array(samp), coef=coef, jpeg=jpeg, coef_dec=coef_dec)
+        print(name, "jpeg bytes", jpeg.size)
     for name, kind, w, h, q, rst, il in CASES:
         img = o.gen_image(kind, w, h)
         _, coef = o.encode(img, q, rst, il, want_coef=True)

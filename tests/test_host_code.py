@@ -97,3 +97,34 @@ def test_geometry_matches_survey_table():
     assert tuple(out[:6]) == (240, 135, 32400, 1350, 4050, 3)
     hs.shim_geometry(1119, 561, 8, 1, out)
     assert tuple(out[:6]) == (140, 71, 9940, 1243, 1243, 1)
+
+
+@pytest.mark.parametrize("il", [0, 1])
+@pytest.mark.parametrize("sampling", [(2, 2), (2, 1), (1, 2), (1, 1)])
+@pytest.mark.parametrize("w,h,rst", [(1920, 1080, 12), (1119, 561, 8), (33, 17, 2), (16, 16, 0), (7680, 4320, 6)])
+def test_geometry_with_chroma_subsampling(w, h, rst, sampling, il):
+    """component planes, scans and restart segments of gj_geometry_init against the reference's rules
+    [ref: src/gpujpeg_common.c:671-866], restated independently in tests/_oracle.plane_geometry"""
+    out = np.zeros(24, np.int64)
+    assert hs.shim_geometry_ss(w, h, rst, il, sampling[0], sampling[1], out) == 0
+    planes = o.plane_geometry(w, h, sampling, il)
+    off = 0
+    for c, (dw, dh) in enumerate(planes):
+        assert tuple(out[3 * c:3 * c + 3]) == (dw // 8, dh // 8, off)
+        off += dw * dh // 64
+    assert out[17] == off * 64
+    bpm = sampling[0] * sampling[1] + 2 if il else 1
+    if il:
+        mcus = [(planes[0][0] // (8 * sampling[0])) * (planes[0][1] // (8 * sampling[1]))]
+        assert out[16] == planes[0][0] // (8 * sampling[0])
+        # DC predictor distance: 1 inside a component's run of blocks, to the previous MCU otherwise
+        n_l = sampling[0] * sampling[1]
+        assert out[20] == bpm - (n_l - 1) and all(out[20 + i] == 1 for i in range(1, min(n_l, 4)))
+    else:
+        mcus = [dw * dh // 64 for dw, dh in planes]
+    seg_mcu = rst if rst else max(mcus)
+    segs = [(m + seg_mcu - 1) // seg_mcu for m in mcus]
+    assert list(out[9:9 + len(segs)]) == segs and out[13] == sum(segs)
+    assert out[14] == seg_mcu and out[15] == bpm
+    assert out[19] == (1 if sampling == (1, 1) else 0)
+    assert out[18] >= seg_mcu * bpm * 416 and out[18] % 128 == 0

@@ -46,6 +46,38 @@ def test_encode_bytes_and_decode_coefficients(kind, w, h, q, rst, il):
     assert np.array_equal(coef_dec, coef)
 
 
+SS_CASES = [("photo", 640, 360, 75, 6), ("random", 1119, 561, 75, 8), ("random", 33, 17, 90, 2), ("photo", 16, 16, 75, 1),
+            ("random", 100, 50, 60, 0), ("random", 8, 8, 95, 3)]
+
+
+@pytest.mark.parametrize("il", [0, 1])
+@pytest.mark.parametrize("sampling", [(2, 2), (2, 1), (1, 2)], ids=["420", "422", "440"])
+@pytest.mark.parametrize("kind,w,h,q,rst", SS_CASES)
+def test_subsampled_encode_bytes_and_decode_coefficients(kind, w, h, q, rst, sampling, il):
+    """chroma subsampling: component geometry, MCU block order, per-component scans and SOF0 sampling factors of the
+    oracle against the reference's header writer + CPU Huffman coder [ref: src/gpujpeg_huffman_cpu_encoder.c:234-290]"""
+    img = o.gen_image(kind, w, h)
+    jpeg, coef = o.encode(img, q, rst, il, want_coef=True, sampling=sampling)
+    ref_jpeg = ref_encode_coef(coef, w, h, q, rst, il, sampling=sampling)
+    assert np.array_equal(jpeg, ref_jpeg), "oracle bytes != reference header writer + CPU Huffman encoder"
+    ref_coef = ref_decode_coef(jpeg, w, h, rst, il, sampling=sampling)
+    assert np.array_equal(ref_coef, coef), "reference CPU Huffman decoder must recover the encoder's coefficients"
+    out, coef_dec = o.decode(jpeg, want_coef=True)
+    assert np.array_equal(coef_dec, coef) and out.shape == (h, w, 3)
+
+
+def test_subsampled_chroma_is_point_sampled():
+    """the preprocessor keeps every second chroma sample unfiltered and the postprocessor replicates it
+    [ref: src/gpujpeg_preprocessor.cu:50-64, src/gpujpeg_postprocessor.cu:55-76]: an image whose colour only changes
+    at even pixel positions decodes to the same pixels with 4:2:0 as with 4:4:4 at quality 100 (up to DCT rounding)"""
+    rng = np.random.default_rng(5)
+    base = rng.integers(0, 256, (24, 32, 3), dtype=np.uint8)
+    img = np.repeat(np.repeat(base, 2, axis=0), 2, axis=1)
+    a = o.decode(o.encode(img, 100, 4, 1, sampling=(2, 2))).astype(int)
+    b = o.decode(o.encode(img, 100, 4, 1)).astype(int)
+    assert np.abs(a - img).max() <= 6 and np.abs(b - img).max() <= 6
+
+
 @pytest.mark.parametrize("kind,q", [("random", 75), ("photo", 75), ("random", 100), ("gradient", 20)])
 def test_integer_idct_matches_gpujpeg_idct_cpu(kind, q):
     w, h = 256, 128

@@ -51,3 +51,31 @@ def test_reference_gpu_decoder_pixels_equal_float_flavour(tmp_path, kind, w, h, 
     d = g.Decoder(idct="float_gpuref")
     assert np.array_equal(d.decode(jpeg), ref)
     d.close()
+
+
+SS = [("4:2:0", (2, 2)), ("4:2:2", (2, 1)), ("4:4:0", (1, 2))]
+
+
+@pytest.mark.skipif(not os.path.exists(SO), reason="oracle/_ref/libgpujpeg_refgpu.so not built")
+@pytest.mark.parametrize("il", [0, 1])
+@pytest.mark.parametrize("name,sampling", SS)
+@pytest.mark.parametrize("kind,w,h,q,rst", [("photo", 1920, 1080, 75, 12), ("random", 1119, 561, 90, 8)])
+def test_reference_gpu_subsampled_encode_and_decode(tmp_path, kind, w, h, q, rst, name, sampling, il):
+    """chroma subsampling: reference GPU encoder bytes == oracle == product; reference GPU decoder pixels ==
+    float flavour of oracle and product"""
+    path, dst = tmp_path / "ref.jpg", tmp_path / "out.rgb"
+    run_ref("encode", kind, w, h, q, rst, il, path, sampling[0], sampling[1])
+    ref = np.fromfile(path, np.uint8)
+    img = o.gen_image(kind, w, h)
+    want = o.encode(img, q, rst, il, threads=4, sampling=sampling)
+    assert ref.size == want.size and np.array_equal(ref, want), "oracle restatement != reference GPU library output"
+    import gpujpeg_b200 as g
+    e = g.Encoder()
+    assert np.array_equal(e.encode(img, q, rst, il, subsampling=name), ref), "product != reference GPU library output"
+    e.close()
+    run_ref("decode", path, dst)
+    pix = np.fromfile(dst, np.uint8).reshape(h, w, 3)
+    assert np.array_equal(pix, o.decode(ref, o.IDCT_FLOAT_GPUREF, threads=4)), "oracle decode != reference GPU decoder"
+    d = g.Decoder(idct="float_gpuref")
+    assert np.array_equal(d.decode(ref), pix), "product decode != reference GPU decoder"
+    d.close()
