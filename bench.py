@@ -44,18 +44,48 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock + throttle reasons sampled DURING the timed regions (B200_PROFILING.md clocks line).  NVML in a thread
+    of this process (the counters nvidia-smi prints; ~2 ms period, so even a 10 ms timed region is covered);
+    falls back to an `nvidia-smi -lms` child when the NVML binding is missing."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.samples, self.proc, self.index = [], None, index
+        self.samples, self.proc, self.index, self.run, self.thread, self.src = [], None, index, False, None, None
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            bits = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
+                    nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap]
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while self.run:
+                    try:
+                        r = get_reasons(h)
+                        self.samples.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx)] +
+                                            ["Active" if r & b else "Not Active" for b in bits])
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+
+            self.run, self.src = True, "nvml"
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.run = False
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
                                           "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
+            self.src = "nvidia-smi"
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -65,14 +95,16 @@ class ClockSampler:
             self.samples.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        self.run = False
+        if self.thread:
+            self.thread.join(timeout=1.0)
         if self.proc:
             self.proc.terminate()
         sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
         mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples if len(s) >= 6 for i in range(4) if s[2 + i] == "Active"})
+        reasons = sorted({self.NAMES[i] for s in self.samples if len(s) >= 6 for i in range(4) if s[2 + i] == "Active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": self.src}
 
 
 def host_cores():
