@@ -141,11 +141,23 @@ def coefficient_count(width, height, sampling=(1, 1), interleaved=0):
     return n
 
 
-def image_parameters(width, height, width_padding=0):
+def image_parameters(width, height, width_padding=0, pixel_format=None, color_space=None):
     pi = ImageParameters()
     lib.gpujpeg_image_set_default_parameters(C.byref(pi))
     pi.width, pi.height, pi.width_padding = width, height, width_padding
+    if pixel_format is not None:
+        pi.pixel_format = pixel_format
+    if color_space is not None:
+        pi.color_space = color_space
     return pi
+
+
+# enum gpujpeg_pixel_format / gpujpeg_color_space values used by the helpers below
+(GPUJPEG_U8, GPUJPEG_444_U8_P012, GPUJPEG_444_U8_P0P1P2, GPUJPEG_422_U8_P1020, GPUJPEG_422_U8_P0P1P2,
+ GPUJPEG_420_U8_P0P1P2) = range(6)
+GPUJPEG_PIXFMT_NATIVE, GPUJPEG_PIXFMT_STD = -5, -4
+GPUJPEG_NONE, GPUJPEG_RGB, GPUJPEG_YCBCR_BT601, GPUJPEG_YCBCR_JPEG, GPUJPEG_YCBCR_BT709 = range(5)
+GPUJPEG_CS_DEFAULT = -1
 
 
 def _ptr(x):
@@ -196,6 +208,14 @@ class Encoder:
         p = default_parameters(quality, restart_interval, interleaved, subsampling)
         p.verbose = verbose
         addr, size = self.encode_raw(image, p, image_parameters(width, height, width_padding))
+        return np.ctypeslib.as_array((C.c_uint8 * size).from_address(addr)).copy()
+
+    def encode_samples(self, raw, width, height, pixel_format, quality=75, restart_interval=RESTART_AUTO, interleaved=0,
+                       color_space=GPUJPEG_YCBCR_JPEG):
+        """raw: flat uint8 buffer in `pixel_format` whose samples already are the JPEG's components (grey, or YCbCr in
+        the JPEG colour space): no colour transform, the JPEG takes the format's sampling.  Returns the JPEG bytes."""
+        p = default_parameters(quality, restart_interval, interleaved)   # comp_count 0: derived from the pixel format
+        addr, size = self.encode_raw(raw, p, image_parameters(width, height, 0, pixel_format, color_space))
         return np.ctypeslib.as_array((C.c_uint8 * size).from_address(addr)).copy()
 
     def run_resident(self, d_raw=None, stage_mask=3):
@@ -263,6 +283,15 @@ class Decoder:
         self.decode_raw(jpeg.ctypes.data, jpeg.size,
                         GPUJPEG_DECODER_OUTPUT_CUSTOM_CUDA_BUFFER if is_dev else GPUJPEG_DECODER_OUTPUT_CUSTOM_BUFFER, addr)
         return out
+
+    def set_output_format(self, color_space, pixel_format):
+        lib.gpujpeg_decoder_set_output_format(self._h, color_space, pixel_format)
+
+    def decode_samples(self, jpeg):
+        """decode with the output format set by set_output_format; returns (flat uint8 copy, ImageParameters)"""
+        jpeg = np.ascontiguousarray(jpeg, np.uint8)
+        o = self.decode_raw(jpeg.ctypes.data, jpeg.size)
+        return np.ctypeslib.as_array((C.c_uint8 * o.data_size).from_address(o.data)).copy(), o.param_image
 
     def run_resident(self, d_out=None, stage_mask=3):
         """enqueue the GPU stages only (bit0 K3, bit1 K4) of the last decoded frame; no copies, no sync"""

@@ -14,6 +14,65 @@
 /* ------------------------------------------------------------------------------------------- */
 /* geometry                                                                                      */
 
+int gj_raw_layout_init(struct gj_raw_layout* l, const struct gpujpeg_image_parameters* pi)
+{
+    memset(l, 0, sizeof *l);
+    const size_t w = (size_t)pi->width, h = (size_t)pi->height, pad = (size_t)pi->width_padding;
+    const size_t cw = (w + 1) / 2, ch = (h + 1) / 2;
+    for ( int c = 0; c < 3; c++ )
+        l->sampling[c].horizontal = l->sampling[c].vertical = 1;
+    switch ( pi->pixel_format ) {
+        case GPUJPEG_U8:
+            l->comp_count = 1;
+            l->comp[0] = (struct gj_raw_comp){0, w + pad, 1};
+            l->size = (w + pad) * h;
+            return 0;
+        case GPUJPEG_444_U8_P012:
+            l->comp_count = 3;
+            for ( int c = 0; c < 3; c++ )
+                l->comp[c] = (struct gj_raw_comp){(size_t)c, 3 * w + pad, 3};
+            l->size = (3 * w + pad) * h;
+            return 0;
+        default: break;
+    }
+    /* planar and packed 4:2:2 formats: plane pitches with row padding are not pinned down by the reference's size
+     * function (src/gpujpeg_common.c:1180-1205), so padding is refused rather than guessed */
+    if ( pad != 0 ) return -1;
+    l->comp_count = 3;
+    switch ( pi->pixel_format ) {
+        case GPUJPEG_444_U8_P0P1P2:
+            for ( int c = 0; c < 3; c++ )
+                l->comp[c] = (struct gj_raw_comp){(size_t)c * w * h, w, 1};
+            l->size = 3 * w * h;
+            return 0;
+        case GPUJPEG_422_U8_P0P1P2:
+            l->comp[0] = (struct gj_raw_comp){0, w, 1};
+            l->comp[1] = (struct gj_raw_comp){w * h, cw, 1};
+            l->comp[2] = (struct gj_raw_comp){w * h + cw * h, cw, 1};
+            l->sampling[0].horizontal = 2;
+            l->size = w * h + 2 * cw * h;
+            return 0;
+        case GPUJPEG_420_U8_P0P1P2:
+            l->comp[0] = (struct gj_raw_comp){0, w, 1};
+            l->comp[1] = (struct gj_raw_comp){w * h, cw, 1};
+            l->comp[2] = (struct gj_raw_comp){w * h + cw * ch, cw, 1};
+            l->sampling[0].horizontal = l->sampling[0].vertical = 2;
+            l->size = w * h + 2 * cw * ch;
+            return 0;
+        case GPUJPEG_422_U8_P1020:
+            /* U Y V Y; the reference treats odd widths as the next even one (src/gpujpeg_preprocessor.cu:372-376)
+             * while its size function does not: only even widths are taken here */
+            if ( w & 1 ) return -1;
+            l->comp[0] = (struct gj_raw_comp){1, 2 * w, 2};
+            l->comp[1] = (struct gj_raw_comp){0, 2 * w, 4};
+            l->comp[2] = (struct gj_raw_comp){2, 2 * w, 4};
+            l->sampling[0].horizontal = 2;
+            l->size = 2 * w * h;
+            return 0;
+        default: return -1;
+    }
+}
+
 int gj_geometry_init(struct gj_geometry* g, const struct gpujpeg_parameters* param,
                      const struct gpujpeg_image_parameters* pi)
 {
@@ -113,7 +172,10 @@ int gj_geometry_init(struct gj_geometry* g, const struct gpujpeg_parameters* par
     }
     g->seg_count = segs;
     g->seg_per_scan = l->scan_seg_begin[1];
-    g->raw_size = (size_t)g->pitch * pi->height;
+    {
+        struct gj_raw_layout rl;
+        g->raw_size = gj_raw_layout_init(&rl, pi) == 0 ? rl.size : (size_t)g->pitch * pi->height;
+    }
     /* worst case per 8x8 block: 64 x (16-bit code + 11 value bits) < 208 bytes, doubled by stuffing */
     g->slot_stride = ((size_t)g->seg_mcu * (g->interleaved ? l->bpm : 1) * 416 + 2 + 127) / 128 * 128;
     /* same budget as the reference's output buffer [ref: src/gpujpeg_writer.c:63-89] */

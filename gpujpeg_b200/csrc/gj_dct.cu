@@ -545,6 +545,131 @@ k_idct_rgb_ss(const int16_t* __restrict__ coef, const __grid_constant__ SsGrid g
     }
 }
 
+/* ------------------------------------------------------------------------------------------- */
+/* K1 / K4 without colour transform: the raw image already holds the JPEG's components (grey, planar or packed
+ * YCbCr in the internal colour space).  One thread per 8x8 block; consecutive threads take consecutive blocks of a
+ * block row, so for planar data a warp reads 256 contiguous bytes per image row.  Samples outside the component
+ * are 0 on the way in [ref: src/gpujpeg_common.c:941-944] and not written on the way out. */
+struct SampleGrid {
+    unsigned long long off[3], pitch[3];
+    int xs[3], cw[3], ch[3], bcx[3], blk_off[4], table[3];
+};
+constexpr int SG_THREADS = 128;
+
+__global__ void __launch_bounds__(SG_THREADS)
+k_fdct_samples(const uint8_t* __restrict__ raw, const __grid_constant__ SampleGrid g, int total_blocks,
+               int16_t* __restrict__ coef, uint64_t* __restrict__ nzmask, const __grid_constant__ FdctParams prm)
+{
+    const int bi = blockIdx.x * SG_THREADS + threadIdx.x;
+    if ( bi >= total_blocks ) return;
+    const int comp = (bi >= g.blk_off[1]) + (bi >= g.blk_off[2]);
+    const int local = bi - g.blk_off[comp];
+    const int by = local / g.bcx[comp], bx = local - by * g.bcx[comp];
+    const int vw = min(8, g.cw[comp] - bx * 8), vh = min(8, g.ch[comp] - by * 8);   // may be <= 0 (MCU padding blocks)
+    const uint8_t* src = raw + g.off[comp] + (size_t)by * 8 * g.pitch[comp] + (size_t)bx * 8 * g.xs[comp];
+    float v[64];
+    const bool rows8 = g.xs[comp] == 1 && vw == 8 && ((reinterpret_cast<uintptr_t>(src) | g.pitch[comp]) & 7) == 0;
+#pragma unroll
+    for ( int y = 0; y < 8; y++ ) {
+        if ( y < vh && rows8 ) {
+            const uint2 t = __ldg(reinterpret_cast<const uint2*>(src + (size_t)y * g.pitch[comp]));
+#pragma unroll
+            for ( int x = 0; x < 8; x++ )
+                v[8 * y + x] = (float)(((x < 4 ? t.x : t.y) >> (8 * (x & 3))) & 0xFFu);
+        }
+        else {
+#pragma unroll
+            for ( int x = 0; x < 8; x++ )
+                v[8 * y + x] = (y < vh && x < vw) ? (float)__ldg(src + (size_t)y * g.pitch[comp] + (size_t)x * g.xs[comp]) : 0.f;
+        }
+    }
+    gj_fdct_block(v);
+    const float* tab = prm.fwd_zz[g.table[comp]];
+    uint32_t packed[32];
+    uint32_t mlo = 0, mhi = 0;
+#pragma unroll
+    for ( int k = 0; k < 64; k += 2 ) {
+        const int q0 = GJ_RINT(GJ_FMUL(v[gj_zz2nat(k)], tab[k]));
+        const int q1 = GJ_RINT(GJ_FMUL(v[gj_zz2nat(k + 1)], tab[k + 1]));
+        packed[k >> 1] = __byte_perm((uint32_t)q0, (uint32_t)q1, 0x5410);
+        if ( k < 32 ) {
+            if ( q0 ) mlo |= 1u << (k & 31);
+            if ( q1 ) mlo |= 1u << ((k + 1) & 31);
+        }
+        else {
+            if ( q0 ) mhi |= 1u << (k & 31);
+            if ( q1 ) mhi |= 1u << ((k + 1) & 31);
+        }
+    }
+    nzmask[bi] = (uint64_t)mhi << 32 | mlo;
+    uint4* dst = reinterpret_cast<uint4*>(coef + (size_t)bi * 64);
+#pragma unroll
+    for ( int i = 0; i < 8; i++ )
+        dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+}
+
+template <int FLAVOUR, bool DEQ>
+__global__ void __launch_bounds__(SG_THREADS)
+k_idct_samples(const int16_t* __restrict__ coef, const __grid_constant__ SampleGrid g, int total_blocks,
+               uint8_t* __restrict__ raw, const __grid_constant__ IdctParams prm)
+{
+    const int bi = blockIdx.x * SG_THREADS + threadIdx.x;
+    if ( bi >= total_blocks ) return;
+    const int comp = (bi >= g.blk_off[1]) + (bi >= g.blk_off[2]);
+    const int local = bi - g.blk_off[comp];
+    const int by = local / g.bcx[comp], bx = local - by * g.bcx[comp];
+    const int vw = min(8, g.cw[comp] - bx * 8), vh = min(8, g.ch[comp] - by * 8);
+    if ( vw <= 0 || vh <= 0 ) return;
+    const uint4* src = reinterpret_cast<const uint4*>(coef + (size_t)bi * 64);
+    uint32_t packed[32];
+#pragma unroll
+    for ( int i = 0; i < 8; i++ ) {
+        const uint4 t = __ldg(src + i);
+        packed[4 * i] = t.x; packed[4 * i + 1] = t.y; packed[4 * i + 2] = t.z; packed[4 * i + 3] = t.w;
+    }
+    const uint16_t* q = prm.q_zz[comp];
+    uint32_t px[16];
+    if ( FLAVOUR == 0 ) {
+        int v[64];
+#pragma unroll
+        for ( int k = 0; k < 64; k++ ) {
+            const int c = (k & 1) ? (int)packed[k >> 1] >> 16 : (int)(short)(packed[k >> 1] & 0xFFFFu);
+            v[gj_zz2nat(k)] = DEQ ? gj_s16(c * (int)(short)q[k]) : c;
+        }
+        gj_idct_int_block_px(v);
+#pragma unroll
+        for ( int i = 0; i < 16; i++ )
+            px[i] = pack4_sat_u8(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+    else {
+        float f[64];
+#pragma unroll
+        for ( int k = 0; k < 64; k++ ) {
+            const int c = (k & 1) ? (int)packed[k >> 1] >> 16 : (int)(short)(packed[k >> 1] & 0xFFFFu);
+            f[gj_zz2nat(k)] = (float)(c * (int)q[k]);
+        }
+        gj_idct_float_block(f);
+#pragma unroll
+        for ( int i = 0; i < 16; i++ )
+            px[i] = pack4_sat_u8(GJ_RINT(GJ_FADD(f[4 * i], 128.0f)), GJ_RINT(GJ_FADD(f[4 * i + 1], 128.0f)),
+                                 GJ_RINT(GJ_FADD(f[4 * i + 2], 128.0f)), GJ_RINT(GJ_FADD(f[4 * i + 3], 128.0f)));
+    }
+    uint8_t* dst = raw + g.off[comp] + (size_t)by * 8 * g.pitch[comp] + (size_t)bx * 8 * g.xs[comp];
+    const bool rows8 = g.xs[comp] == 1 && vw == 8 && ((reinterpret_cast<uintptr_t>(dst) | g.pitch[comp]) & 7) == 0;
+#pragma unroll
+    for ( int y = 0; y < 8; y++ ) {
+        if ( y >= vh ) continue;
+        if ( rows8 ) {
+            *reinterpret_cast<uint2*>(dst + (size_t)y * g.pitch[comp]) = make_uint2(px[2 * y], px[2 * y + 1]);
+        }
+        else {
+#pragma unroll
+            for ( int x = 0; x < 8; x++ )
+                if ( x < vw ) dst[(size_t)y * g.pitch[comp] + (size_t)x * g.xs[comp]] = (uint8_t)(px[2 * y + (x >> 2)] >> (8 * (x & 3)));
+        }
+    }
+}
+
 int pick_vec(const void* p, size_t pitch)
 {
     const uintptr_t a = reinterpret_cast<uintptr_t>(p) | pitch;
@@ -678,5 +803,64 @@ extern "C" int gj_launch_idct_rgb_ss(const int16_t* d_coef, const struct gj_comp
     else return -1;
 #undef GJ_K4SS
 #undef GJ_K4SS2
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+/* ---- no colour transform: grey, planar and packed YCbCr formats ---- */
+static int sample_grid(SampleGrid* sg, const struct gj_raw_layout* raw, const struct gj_comp_geo* comp, int comp_count)
+{
+    if ( comp_count < 1 || comp_count > 3 || raw->comp_count != comp_count ) return -1;
+    memset(sg, 0, sizeof *sg);
+    int total = 0;
+    for ( int c = 0; c < 3; c++ ) {
+        const int k = c < comp_count ? c : comp_count - 1;
+        sg->off[c] = raw->comp[k].off;
+        sg->pitch[c] = raw->comp[k].pitch;
+        sg->xs[c] = raw->comp[k].xs;
+        sg->cw[c] = comp[k].width;
+        sg->ch[c] = comp[k].height;
+        sg->bcx[c] = comp[k].bcx;
+        sg->table[c] = c == 0 ? 0 : 1;
+        if ( c < comp_count ) {
+            sg->blk_off[c] = comp[c].blk_off;
+            total = comp[c].blk_off + comp[c].nblk;
+        }
+    }
+    for ( int c = comp_count; c < 4; c++ )
+        sg->blk_off[c] = 0x7FFFFFFF;   // never reached: the component search stops at the last real component
+    return total;
+}
+
+extern "C" int gj_launch_fdct_samples(const uint8_t* d_raw, const struct gj_raw_layout* raw, int16_t* d_coef,
+                                      uint64_t* d_nzmask, const struct gj_comp_geo* comp, int comp_count,
+                                      const struct gj_dev_enc_tables* h_tables, gj_stream_t stream)
+{
+    FdctParams prm;
+    memcpy(prm.fwd_zz, h_tables->fwd_zz, sizeof prm.fwd_zz);
+    SampleGrid sg;
+    const int total = sample_grid(&sg, raw, comp, comp_count);
+    if ( total <= 0 ) return -1;
+    k_fdct_samples<<<(total + SG_THREADS - 1) / SG_THREADS, SG_THREADS, 0, stream>>>(d_raw, sg, total, d_coef, d_nzmask, prm);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+extern "C" int gj_launch_idct_samples(const int16_t* d_coef, const struct gj_comp_geo* comp, int comp_count, const int* comp_tq,
+                                      uint8_t* d_raw, const struct gj_raw_layout* raw, int idct_flavour, int coef_dequantized,
+                                      const struct gj_dev_dec_tables* h_tables, gj_stream_t stream)
+{
+    IdctParams prm;
+    for ( int c = 0; c < 3; c++ )
+        memcpy(prm.q_zz[c], h_tables->qinv_zz[comp_tq[c < comp_count ? c : 0]], sizeof prm.q_zz[c]);
+    SampleGrid sg;
+    const int total = sample_grid(&sg, raw, comp, comp_count);
+    if ( total <= 0 ) return -1;
+    if ( idct_flavour != 0 && coef_dequantized ) return -1;
+    const int grid = (total + SG_THREADS - 1) / SG_THREADS;
+    if ( idct_flavour == 0 && coef_dequantized )
+        k_idct_samples<0, false><<<grid, SG_THREADS, 0, stream>>>(d_coef, sg, total, d_raw, prm);
+    else if ( idct_flavour == 0 )
+        k_idct_samples<0, true><<<grid, SG_THREADS, 0, stream>>>(d_coef, sg, total, d_raw, prm);
+    else
+        k_idct_samples<1, true><<<grid, SG_THREADS, 0, stream>>>(d_coef, sg, total, d_raw, prm);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

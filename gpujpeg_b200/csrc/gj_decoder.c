@@ -36,6 +36,8 @@ struct gpujpeg_decoder {
     enum gpujpeg_pixel_format req_pixel_format;
     enum gpujpeg_color_space req_color_space;
     int idct_flavour;
+    int out_mode;                 /* GJ_OUT_RGB or GJ_OUT_SAMPLES: which K4 runs */
+    struct gj_raw_layout raw;     /* where the samples go (GJ_OUT_SAMPLES) */
     struct gpujpeg_image_metadata metadata;
 
     struct gj_dev_dec_tables h_tab, h_tab_prev;
@@ -181,10 +183,11 @@ int gpujpeg_decoder_init(struct gpujpeg_decoder* d, const struct gpujpeg_paramet
     if ( param_image->width * param_image->height * param->comp_count == 0 ) return 0;
     struct gpujpeg_parameters p = *param;
     struct gpujpeg_image_parameters pi = *param_image;
-    if ( p.comp_count != 3 ) {
-        GJ_ERR("This build decodes 3-component images only.\n");
+    if ( p.comp_count != 3 && p.comp_count != 1 ) {
+        GJ_ERR("This build decodes 1- and 3-component images only.\n");
         return -1;
     }
+    if ( (int)pi.pixel_format < 0 ) pi.pixel_format = p.comp_count == 1 ? GPUJPEG_U8 : GPUJPEG_444_U8_P012;
     gj_geometry_init(&d->geo, &p, &pi);
     const struct gj_geometry* g = &d->geo;
     if ( grow_dev((void**)&d->d_coef, &d->d_coef_size, g->coef_count * 2) ||
@@ -206,24 +209,76 @@ void gpujpeg_decoder_set_output_format(struct gpujpeg_decoder* decoder, enum gpu
     decoder->req_pixel_format = pixel_format;
 }
 
-static int output_format_supported(const struct gpujpeg_decoder* d)
+/* What this build decodes to, and with which K4 (anything else fails loudly):
+ *   GJ_OUT_RGB      3-component YCbCr stream -> GPUJPEG_RGB / 444-u8-p012 (the default request), any supported sampling
+ *   GJ_OUT_SAMPLES  the stream's own components, no colour transform: GPUJPEG_U8 for 1-component streams; for
+ *                   3-component streams colour space GPUJPEG_YCBCR_JPEG (or GPUJPEG_NONE) with a pixel format of the
+ *                   stream's sampling: 444-u8-p012, 444/422/420-u8-p0p1p2, 422-u8-p1020, or the special values
+ *                   GPUJPEG_PIXFMT_NATIVE / _STD resolved as the reference does [ref: src/gpujpeg_reader.c:1507-1581] */
+enum { GJ_OUT_RGB = 1, GJ_OUT_SAMPLES = 2 };
+
+static int choose_output(const struct gpujpeg_decoder* d, const struct gj_stream* st, struct gpujpeg_image_parameters* pi)
 {
-    const enum gpujpeg_pixel_format pf = d->req_pixel_format;
-    const enum gpujpeg_color_space cs = d->req_color_space;
-    const int pf_ok = pf == GPUJPEG_444_U8_P012 || pf == GPUJPEG_PIXFMT_AUTODETECT || pf == GPUJPEG_PIXFMT_NO_ALPHA ||
-                      pf == GPUJPEG_PIXFMT_STD || pf == GPUJPEG_PIXFMT_NATIVE || pf == GPUJPEG_PIXFMT_NONE;
-    const int cs_ok = cs == GPUJPEG_RGB || cs == GPUJPEG_CS_DEFAULT || cs == GPUJPEG_NONE;
-    if ( !pf_ok || !cs_ok ) {
-        GJ_ERR("This build decodes to GPUJPEG_RGB / GPUJPEG_444_U8_P012 only.\n");
+    enum gpujpeg_pixel_format pf = d->req_pixel_format;
+    enum gpujpeg_color_space cs = d->req_color_space;
+    const int special = (int)pf < 0;   /* GPUJPEG_PIXFMT_NONE / _AUTODETECT / _NO_ALPHA / _STD / _NATIVE */
+    if ( st->comp_count == 1 ) {
+        if ( !special && pf != GPUJPEG_U8 ) {
+            GJ_ERR("This build decodes 1-component JPEGs to GPUJPEG_U8 only (%s requested).\n", gpujpeg_pixel_format_get_name(pf));
+            return 0;
+        }
+        pi->pixel_format = GPUJPEG_U8;
+        pi->color_space = (cs == GPUJPEG_CS_DEFAULT || cs == GPUJPEG_NONE) ? GPUJPEG_YCBCR_JPEG : cs;
+        return GJ_OUT_SAMPLES;
+    }
+    const int lh = st->comp_hv[0] >> 4, lv = st->comp_hv[0] & 15;
+    if ( cs == GPUJPEG_CS_DEFAULT ) cs = GPUJPEG_RGB;
+    if ( cs == GPUJPEG_NONE ) cs = st->color_space;
+    if ( special ) {
+        const int planar_by_sampling = pf == GPUJPEG_PIXFMT_STD && cs != GPUJPEG_RGB;
+        if ( pf == GPUJPEG_PIXFMT_NATIVE || planar_by_sampling ) {
+            const int il = pf == GPUJPEG_PIXFMT_NATIVE && st->scan[0].ncomp > 1;
+            if ( lh == 2 && lv == 2 ) pf = GPUJPEG_420_U8_P0P1P2;
+            else if ( lh == 2 && lv == 1 ) pf = il ? GPUJPEG_422_U8_P1020 : GPUJPEG_422_U8_P0P1P2;
+            else pf = il ? GPUJPEG_444_U8_P012 : GPUJPEG_444_U8_P0P1P2;
+        }
+        else {
+            pf = GPUJPEG_444_U8_P012;
+        }
+    }
+    pi->pixel_format = pf;
+    pi->color_space = cs;
+    if ( cs == GPUJPEG_RGB ) {
+        if ( pf == GPUJPEG_444_U8_P012 ) return GJ_OUT_RGB;
+        GJ_ERR("This build decodes to GPUJPEG_RGB as 444-u8-p012 only (%s requested).\n", gpujpeg_pixel_format_get_name(pf));
         return 0;
     }
-    return 1;
+    if ( cs != st->color_space ) {
+        GJ_ERR("This build decodes to GPUJPEG_RGB or to the stream's own colour space (%s); %s would need another colour "
+               "transform.\n", gpujpeg_color_space_get_name(st->color_space), gpujpeg_color_space_get_name(cs));
+        return 0;
+    }
+    struct gj_raw_layout rl;
+    if ( gj_raw_layout_init(&rl, pi) || rl.comp_count != 3 ) {
+        GJ_ERR("Pixel format %s (%dx%d) is not produced by this build.\n", gpujpeg_pixel_format_get_name(pf), pi->width,
+               pi->height);
+        return 0;
+    }
+    if ( rl.sampling[0].horizontal != lh || rl.sampling[0].vertical != lv ) {
+        GJ_ERR("This build keeps the stream's sampling (%dx%d luminance) when no colour transform is asked for; %s has "
+               "another one.\n", lh, lv, gpujpeg_pixel_format_get_name(pf));
+        return 0;
+    }
+    return GJ_OUT_SAMPLES;
 }
 
 /* K4 for the coder's geometry: the 4:4:4 kernel or the chroma-subsampling template instance */
 static int launch_k4(struct gpujpeg_decoder* d, const int comp_tq[3], uint8_t* d_out, int coef_dequantized)
 {
     const struct gj_geometry* g = &d->geo;
+    if ( d->out_mode == GJ_OUT_SAMPLES )
+        return gj_launch_idct_samples(d->d_coef, g->comp, g->comp_count, comp_tq, d_out, &d->raw, d->idct_flavour,
+                                      coef_dequantized, &d->h_tab, d->stream);
     if ( g->lay.simple )
         return gj_launch_idct_rgb444(d->d_coef, g->bcx, g->bcy, comp_tq, d_out, g->width, g->height, g->pitch, d->idct_flavour,
                                      coef_dequantized, &d->h_tab, d->stream);
@@ -256,12 +311,13 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
         GJ_ERR("Decoder failed when decoding image data (no scan found)!\n");
         return GPUJPEG_ERROR;
     }
-    if ( st.comp_count != 3 ) {
-        GJ_ERR("This build decodes 3-component JPEGs only (stream has %d).\n", st.comp_count);
+    if ( st.comp_count != 3 && st.comp_count != 1 ) {
+        GJ_ERR("This build decodes 1- and 3-component JPEGs only (stream has %d).\n", st.comp_count);
         return GPUJPEG_ERROR;
     }
+    if ( st.comp_count == 1 ) st.comp_hv[0] = 0x11;   /* a single component is never subsampled (T.81 A.2.2) */
     /* luminance 1x1, 2x1, 1x2 or 2x2 with 1x1 chrominance (4:4:4, 4:2:2, 4:4:0, 4:2:0) */
-    {
+    if ( st.comp_count == 3 ) {
         const int lh = st.comp_hv[0] >> 4, lv = st.comp_hv[0] & 15;
         if ( lh < 1 || lh > 2 || lv < 1 || lv > 2 || st.comp_hv[1] != 0x11 || st.comp_hv[2] != 0x11 ) {
             GJ_ERR("This build decodes 4:4:4, 4:2:2, 4:2:0 and 4:4:0 only (sampling factors %dx%d %dx%d %dx%d).\n", lh, lv,
@@ -269,7 +325,6 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
             return GPUJPEG_ERROR;
         }
     }
-    if ( !output_format_supported(d) ) return GPUJPEG_ERROR;
     st.interleaved = st.scan[0].ncomp > 1;
     if ( st.interleaved && st.scan[0].ncomp != 3 ) {
         GJ_ERR("Unsupported scan structure (%d components in first scan).\n", st.scan[0].ncomp);
@@ -282,8 +337,9 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     p.perf_stats = d->perf_stats;
     p.restart_interval = st.restart_interval;
     p.interleaved = st.interleaved;
-    p.comp_count = 3;
-    for ( int c = 0; c < 3; c++ ) {
+    p.comp_count = st.comp_count;
+    memset(p.sampling_factor, 0, sizeof p.sampling_factor);
+    for ( int c = 0; c < st.comp_count; c++ ) {
         p.sampling_factor[c].horizontal = (uint8_t)(st.comp_hv[c] >> 4);
         p.sampling_factor[c].vertical = (uint8_t)(st.comp_hv[c] & 15);
     }
@@ -292,15 +348,21 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     gpujpeg_image_set_default_parameters(&pi);
     pi.width = st.width;
     pi.height = st.height;
-    pi.color_space = GPUJPEG_RGB;
-    pi.pixel_format = GPUJPEG_444_U8_P012;
+    /* the stream's colour space is only known for certain after all markers (an Adobe segment may follow); the
+     * streams this build takes are YCbCr-JPEG, which is verified below before anything is launched */
+    const int out_mode = choose_output(d, &st, &pi);
+    if ( !out_mode ) return GPUJPEG_ERROR;
 
     if ( !d->initialised || d->param_image.width != pi.width || d->param_image.height != pi.height ||
+         d->param_image.pixel_format != pi.pixel_format || d->param.comp_count != p.comp_count ||
          d->param.restart_interval != p.restart_interval || d->param.interleaved != p.interleaved ||
          memcmp(d->param.sampling_factor, p.sampling_factor, sizeof p.sampling_factor) != 0 ) {
         if ( d->initialised ) GJ_VERBOSE(d->verbose, "Reinitializing decoder.\n");
         if ( gpujpeg_decoder_init(d, &p, &pi) ) return GPUJPEG_ERROR;
     }
+    d->out_mode = out_mode;
+    d->param_image.color_space = pi.color_space;
+    if ( out_mode == GJ_OUT_SAMPLES && gj_raw_layout_init(&d->raw, &pi) ) return GPUJPEG_ERROR;
     const struct gj_geometry* g = &d->geo;
 
     /* ---- upload the file once, untouched; K0 builds the marker list on the device ---- */
@@ -376,7 +438,7 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
         GJ_ERR("Unsupported scan structure (%d scans, expected %d).\n", st.scan_count, g->scan_count);
         return GPUJPEG_ERROR;
     }
-    for ( int c = 0; c < 3; c++ ) {
+    for ( int c = 0; c < st.comp_count; c++ ) {
         if ( !st.have_qt[st.comp_tq[c]] ) {
             GJ_ERR("Quantization table %d is missing!\n", st.comp_tq[c]);
             return GPUJPEG_ERROR;

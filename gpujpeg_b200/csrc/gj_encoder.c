@@ -28,6 +28,8 @@ struct gpujpeg_encoder {
     struct gpujpeg_image_parameters param_image;
     int initialised;
     struct gj_geometry geo;
+    int input_mode;                  /* GJ_IN_RGB or GJ_IN_SAMPLES: which K1 runs */
+    struct gj_raw_layout raw;        /* where the samples live (GJ_IN_SAMPLES) */
     int quality;                               /* quality the tables were built for (-1 = none) */
     enum gpujpeg_header_type header_type;
     int out_pinned;
@@ -182,50 +184,84 @@ static int grow(void** p, size_t* have, size_t want)
     return 0;
 }
 
+/* What this build encodes, and with which K1 (anything else fails loudly, there is no CPU fallback):
+ *   GJ_IN_RGB      GPUJPEG_444_U8_P012 + GPUJPEG_RGB -> YCbCr (BT.601 full range) JPEG, 4:4:4 / 4:2:2 / 4:2:0 / 4:4:0:
+ *                  the fused colour + FDCT kernels
+ *   GJ_IN_SAMPLES  the image already holds the JPEG's components (colour space == internal colour space, or a single
+ *                  component): GPUJPEG_U8, 444-u8-p012, 444/422/420-u8-p0p1p2, 422-u8-p1020; the JPEG takes the
+ *                  format's own sampling [ref: src/gpujpeg_preprocessor.cu:296-311 "no transform" rule] */
+enum { GJ_IN_UNSUPPORTED = 0, GJ_IN_RGB = 1, GJ_IN_SAMPLES = 2 };
+
 static int params_supported(const struct gpujpeg_parameters* p, const struct gpujpeg_image_parameters* pi)
 {
-    if ( pi->pixel_format != GPUJPEG_444_U8_P012 || pi->color_space != GPUJPEG_RGB ) {
-        GJ_ERR("This build encodes GPUJPEG_RGB / GPUJPEG_444_U8_P012 input only (got %s / %s).\n",
-               gpujpeg_color_space_get_name(pi->color_space), gpujpeg_pixel_format_get_name(pi->pixel_format));
-        return 0;
+    if ( pi->width < 1 || pi->height < 1 || pi->width > 65535 || pi->height > 65535 || pi->width_padding < 0 ) {
+        GJ_ERR("Unsupported image size %dx%d.\n", pi->width, pi->height);
+        return GJ_IN_UNSUPPORTED;
+    }
+    if ( p->restart_interval < 0 || p->restart_interval > 65535 ) {
+        GJ_ERR("Restart interval %d cannot be stored in a DRI marker.\n", p->restart_interval);
+        return GJ_IN_UNSUPPORTED;
+    }
+    if ( p->segment_info ) {
+        GJ_ERR("segment_info headers are not implemented in this build.\n");
+        return GJ_IN_UNSUPPORTED;
     }
     if ( p->color_space_internal != GPUJPEG_YCBCR_BT601_256LVLS ) {
         GJ_ERR("This build encodes to internal color space %s only.\n",
                gpujpeg_color_space_get_name(GPUJPEG_YCBCR_BT601_256LVLS));
-        return 0;
+        return GJ_IN_UNSUPPORTED;
     }
-    if ( p->comp_count != 3 ) {
-        GJ_ERR("This build encodes 3-component images only (comp_count = %d).\n", p->comp_count);
-        return 0;
+    if ( p->comp_count != 3 && p->comp_count != 1 ) {
+        GJ_ERR("This build encodes 1- and 3-component images only (comp_count = %d).\n", p->comp_count);
+        return GJ_IN_UNSUPPORTED;
     }
-    /* luminance 1x1, 2x1, 1x2 or 2x2 with 1x1 chrominance: the sampling modes the reference has precompiled
-     * preprocessor kernels for [ref: src/gpujpeg_preprocessor.cu:241-253] */
-    const int lh = p->sampling_factor[0].horizontal, lv = p->sampling_factor[0].vertical;
-    if ( lh < 1 || lh > 2 || lv < 1 || lv > 2 || p->sampling_factor[1].horizontal != 1 || p->sampling_factor[1].vertical != 1 ||
-         p->sampling_factor[2].horizontal != 1 || p->sampling_factor[2].vertical != 1 ) {
-        GJ_ERR("This build encodes 4:4:4, 4:2:2, 4:2:0 and 4:4:0 only (got %s).\n",
-               gpujpeg_subsampling_get_name(3, p->sampling_factor));
-        return 0;
+    if ( pi->pixel_format == GPUJPEG_444_U8_P012 && pi->color_space == GPUJPEG_RGB && p->comp_count == 3 ) {
+        /* luminance 1x1, 2x1, 1x2 or 2x2 with 1x1 chrominance: the sampling modes the reference has precompiled
+         * preprocessor kernels for [ref: src/gpujpeg_preprocessor.cu:241-253] */
+        const int lh = p->sampling_factor[0].horizontal, lv = p->sampling_factor[0].vertical;
+        if ( lh < 1 || lh > 2 || lv < 1 || lv > 2 || p->sampling_factor[1].horizontal != 1 ||
+             p->sampling_factor[1].vertical != 1 || p->sampling_factor[2].horizontal != 1 || p->sampling_factor[2].vertical != 1 ) {
+            GJ_ERR("This build encodes 4:4:4, 4:2:2, 4:2:0 and 4:4:0 only (got %s).\n",
+                   gpujpeg_subsampling_get_name(3, p->sampling_factor));
+            return GJ_IN_UNSUPPORTED;
+        }
+        return GJ_IN_RGB;
     }
-    if ( p->segment_info ) {
-        GJ_ERR("segment_info headers are not implemented in this build.\n");
-        return 0;
+    struct gj_raw_layout rl;
+    if ( gj_raw_layout_init(&rl, pi) ) {
+        GJ_ERR("Pixel format %s (%dx%d, row padding %d) is not taken by this build.\n",
+               gpujpeg_pixel_format_get_name(pi->pixel_format), pi->width, pi->height, pi->width_padding);
+        return GJ_IN_UNSUPPORTED;
     }
-    if ( pi->width < 1 || pi->height < 1 || pi->width > 65535 || pi->height > 65535 || pi->width_padding < 0 ) {
-        GJ_ERR("Unsupported image size %dx%d.\n", pi->width, pi->height);
-        return 0;
+    if ( rl.comp_count != p->comp_count ) {
+        GJ_ERR("Pixel format %s has %d components, the JPEG parameters ask for %d.\n",
+               gpujpeg_pixel_format_get_name(pi->pixel_format), rl.comp_count, p->comp_count);
+        return GJ_IN_UNSUPPORTED;
     }
-    if ( p->restart_interval < 0 || p->restart_interval > 65535 ) {
-        GJ_ERR("Restart interval %d cannot be stored in a DRI marker.\n", p->restart_interval);
-        return 0;
+    if ( p->comp_count == 3 && pi->color_space != p->color_space_internal && pi->color_space != GPUJPEG_NONE ) {
+        GJ_ERR("This build converts GPUJPEG_RGB / 444-u8-p012 only; %s input in %s would need a colour transform to %s.\n",
+               gpujpeg_pixel_format_get_name(pi->pixel_format), gpujpeg_color_space_get_name(pi->color_space),
+               gpujpeg_color_space_get_name(p->color_space_internal));
+        return GJ_IN_UNSUPPORTED;
     }
-    return 1;
+    for ( int c = 0; c < p->comp_count; c++ ) {
+        if ( p->sampling_factor[c].horizontal != rl.sampling[c].horizontal ||
+             p->sampling_factor[c].vertical != rl.sampling[c].vertical ) {
+            GJ_ERR("This build keeps the sampling of the pixel format (%s is %s, the JPEG parameters ask for %s).\n",
+                   gpujpeg_pixel_format_get_name(pi->pixel_format), gpujpeg_subsampling_get_name(p->comp_count, rl.sampling),
+                   gpujpeg_subsampling_get_name(p->comp_count, p->sampling_factor));
+            return GJ_IN_UNSUPPORTED;
+        }
+    }
+    return GJ_IN_SAMPLES;
 }
 
 /* K1 for the coder's geometry: the 4:4:4 kernel or the chroma-subsampling template instance */
 static int launch_k1(struct gpujpeg_encoder* e, const uint8_t* d_raw)
 {
     const struct gj_geometry* g = &e->geo;
+    if ( e->input_mode == GJ_IN_SAMPLES )
+        return gj_launch_fdct_samples(d_raw, &e->raw, e->d_coef, e->d_nzmask, g->comp, g->comp_count, &e->h_tab, e->stream);
     if ( g->lay.simple )
         return gj_launch_fdct_rgb444(d_raw, g->width, g->height, g->pitch, e->d_coef, e->d_nzmask, g->bcx, g->bcy, &e->h_tab,
                                      e->stream);
@@ -259,6 +295,8 @@ static int encoder_init_image(struct gpujpeg_encoder* e, const struct gpujpeg_pa
                               const struct gpujpeg_image_parameters* pi)
 {
     gj_geometry_init(&e->geo, p, pi);
+    e->input_mode = params_supported(p, pi);
+    if ( e->input_mode == GJ_IN_SAMPLES && gj_raw_layout_init(&e->raw, pi) ) return -1;
     const struct gj_geometry* g = &e->geo;
     size_t coef_bytes = g->coef_count * sizeof(int16_t);
     size_t tmp_bytes = (size_t)g->seg_count * g->slot_stride + 256;
@@ -342,10 +380,13 @@ static struct gpujpeg_parameters adjust_params(struct gpujpeg_encoder* e, const 
         if ( img_changed || !e->initialised ) {
             const int n = gpujpeg_pixel_format_get_comp_count(pi->pixel_format);
             a.comp_count = n > 3 ? 3 : n;
+            /* the pixel format's own sampling [ref: src/gpujpeg_encoder.c:327-330] */
+            struct gj_raw_layout rl;
+            const int known = gj_raw_layout_init(&rl, pi) == 0;
             memset(a.sampling_factor, 0, sizeof a.sampling_factor);
             for ( int c = 0; c < a.comp_count; c++ ) {
-                a.sampling_factor[c].horizontal = 1;
-                a.sampling_factor[c].vertical = 1;
+                a.sampling_factor[c].horizontal = known ? rl.sampling[c].horizontal : 1;
+                a.sampling_factor[c].vertical = known ? rl.sampling[c].vertical : 1;
             }
         }
         else {

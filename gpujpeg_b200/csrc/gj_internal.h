@@ -131,6 +131,22 @@ struct gj_geometry {
     size_t slot_stride;   /* bytes reserved per segment in the encoder's scan tmp buffer */
     size_t stream_cap;    /* capacity of the finished stream buffer */
 };
+/* Where the samples of component c live in a raw image of a given pixel format [ref: src/gpujpeg_preprocessor.cu:78-160
+ * (loads per format), :409-455 (planar copy)]: sample (x, y) is the byte at off + y * pitch + x * xs. */
+struct gj_raw_comp {
+    size_t off;
+    size_t pitch;
+    int xs;
+};
+struct gj_raw_layout {
+    int comp_count;
+    struct gj_raw_comp comp[GJ_MAX_COMP];
+    struct gpujpeg_component_sampling_factor sampling[GJ_MAX_COMP];  /* the format's own sampling */
+    size_t size;   /* bytes of the whole image */
+};
+/* 0 on success, -1 for a format/size combination this build does not take */
+int gj_raw_layout_init(struct gj_raw_layout* l, const struct gpujpeg_image_parameters* pi);
+
 int gj_geometry_init(struct gj_geometry* g, const struct gpujpeg_parameters* param,
                      const struct gpujpeg_image_parameters* param_image);
 
@@ -263,6 +279,17 @@ int gj_launch_fdct_rgb_ss(const uint8_t* d_raw, int width, int height, int pitch
 int gj_launch_idct_rgb_ss(const int16_t* d_coef, const struct gj_comp_geo comp[3], const int comp_tq[3], uint8_t* d_raw,
                           int width, int height, int pitch, int idct_flavour, int coef_dequantized,
                           const struct gj_dev_dec_tables* h_tables, gj_stream_t stream);
+
+/* K1 / K4 without colour transform, any pixel format gj_raw_layout_init describes, any sampling: one thread per 8x8
+ * block reads / writes its samples straight from / to the raw image
+ * [replaces the "matching format" memcpy path + DCT launches, ref: src/gpujpeg_preprocessor.cu:409-455,
+ *  src/gpujpeg_postprocessor.cu:406-433, and the GPUJPEG_NONE colour-transform kernels] */
+int gj_launch_fdct_samples(const uint8_t* d_raw, const struct gj_raw_layout* raw, int16_t* d_coef, uint64_t* d_nzmask,
+                           const struct gj_comp_geo* comp, int comp_count, const struct gj_dev_enc_tables* h_tables,
+                           gj_stream_t stream);
+int gj_launch_idct_samples(const int16_t* d_coef, const struct gj_comp_geo* comp, int comp_count, const int* comp_tq,
+                           uint8_t* d_raw, const struct gj_raw_layout* raw, int idct_flavour, int coef_dequantized,
+                           const struct gj_dev_dec_tables* h_tables, gj_stream_t stream);
 
 /* debug/test helper: device coefficient buffer (zig-zag) -> host natural order, block-major */
 int gj_coef_to_host_natural(const int16_t* d_coef, size_t count, int16_t* h_out, gj_stream_t stream);

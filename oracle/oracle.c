@@ -897,29 +897,15 @@ static void postprocess_rgb_ss(const uint8_t* planes, const struct ogeo g[3], in
 
 /* [ref: src/gpujpeg_encoder.c:351-646; block order of interleaved MCUs src/gpujpeg_common.c:1056-1085;
  *       per-component scans src/gpujpeg_huffman_cpu_encoder.c:296-376] */
-size_t orc_encode_rgb_ss(const uint8_t* rgb, int w, int h, int pad, int quality, int rst, int interleaved, int lhs,
-                         int lvs, int threads, uint8_t* out, int16_t* coef_out)
+/* planes (already in the JPEG's component layout) -> file: FDCT + quantisation, header, scans.
+ * [ref: src/gpujpeg_encoder.c:351-646; block order of interleaved MCUs src/gpujpeg_common.c:1056-1085;
+ *       per-component scans src/gpujpeg_huffman_cpu_encoder.c:296-376] */
+static size_t encode_from_planes(const uint8_t* planes, const struct ogeo g[4], int comps, const int hs[4], const int vs[4],
+                                 int w, int h, int quality, int rst, int interleaved, uint8_t* out, int16_t* coef)
 {
-    if ( w <= 0 || h <= 0 || w > 65535 || h > 65535 || rst < 0 || rst > 65535 ) return 0;
-    if ( lhs < 1 || lvs < 1 || lhs > 2 || lvs > 2 ) return 0;
-    enc_tables_init();
-#ifdef _OPENMP
-    int saved_threads = omp_get_max_threads();
-    omp_set_num_threads(threads > 1 ? threads : 1);
-#else
-    (void)threads;
-#endif
-    const int comps = 3;
-    const int hs[4] = {lhs, 1, 1, 0}, vs[4] = {lvs, 1, 1, 0};
-    struct ogeo g[4];
-    int max_hs, max_vs;
-    size_t total = ogeo_init(g, comps, hs, vs, w, h, interleaved, &max_hs, &max_vs);
     uint8_t raw[2][64];
     float fwd[2][64];
     orc_quant_tables(quality, raw, fwd, NULL);
-    uint8_t* planes = (uint8_t*)scratch(0, total);
-    int16_t* coef = coef_out ? coef_out : (int16_t*)scratch(1, total * sizeof(int16_t));
-    preprocess_rgb_ss(rgb, w, h, pad, planes, g, max_hs, max_vs, total);
     for ( int c = 0; c < comps; c++ )
         orc_fdct_quant_plane(planes + g[c].off, g[c].dw, g[c].dh, fwd[c == 0 ? 0 : 1], coef + g[c].off);
 
@@ -933,6 +919,7 @@ size_t orc_encode_rgb_ss(const uint8_t* rgb, int w, int h, int pad, int quality,
         }
     uint8_t* p = out + hl;
 
+    if ( comps == 1 ) interleaved = 0;
     int nscan = interleaved ? 1 : comps;
     int bpm = 0;
     for ( int c = 0; c < comps; c++ )
@@ -990,10 +977,140 @@ size_t orc_encode_rgb_ss(const uint8_t* rgb, int w, int h, int pad, int quality,
         }
     }
     p = putm(p, 0xD9);
+    return (size_t)(p - out);
+}
+
+size_t orc_encode_rgb_ss(const uint8_t* rgb, int w, int h, int pad, int quality, int rst, int interleaved, int lhs,
+                         int lvs, int threads, uint8_t* out, int16_t* coef_out)
+{
+    if ( w <= 0 || h <= 0 || w > 65535 || h > 65535 || rst < 0 || rst > 65535 ) return 0;
+    if ( lhs < 1 || lvs < 1 || lhs > 2 || lvs > 2 ) return 0;
+    enc_tables_init();
+#ifdef _OPENMP
+    int saved_threads = omp_get_max_threads();
+    omp_set_num_threads(threads > 1 ? threads : 1);
+#else
+    (void)threads;
+#endif
+    const int comps = 3;
+    const int hs[4] = {lhs, 1, 1, 0}, vs[4] = {lvs, 1, 1, 0};
+    struct ogeo g[4];
+    int max_hs, max_vs;
+    size_t total = ogeo_init(g, comps, hs, vs, w, h, interleaved, &max_hs, &max_vs);
+    uint8_t* planes = (uint8_t*)scratch(0, total);
+    int16_t* coef = coef_out ? coef_out : (int16_t*)scratch(1, total * sizeof(int16_t));
+    preprocess_rgb_ss(rgb, w, h, pad, planes, g, max_hs, max_vs, total);
+    size_t n = encode_from_planes(planes, g, comps, hs, vs, w, h, quality, rst, interleaved, out, coef);
 #ifdef _OPENMP
     omp_set_num_threads(saved_threads);
 #endif
-    return (size_t)(p - out);
+    return n;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* raw pixel formats whose samples go into the JPEG without a colour transform (image colour space == internal
+ * colour space): where the samples of each component live [ref: src/gpujpeg_preprocessor.cu:78-160 (loads),
+ * :409-455 (planar copy), src/gpujpeg_common.c:2075-2107 (format descriptions)]                          */
+
+struct rawcomp {
+    size_t off;    /* byte offset of sample (0,0) */
+    int xs;        /* bytes between horizontally adjacent samples */
+    size_t pitch;  /* bytes between rows */
+};
+
+/* fmt: the reference's enum gpujpeg_pixel_format values (0 u8, 1 444-p012, 2 444-p0p1p2, 3 422-p1020, 4 422-p0p1p2,
+ * 5 420-p0p1p2).  Returns the component count, 0 if unsupported. */
+static int raw_layout(int fmt, int w, int h, int pad, struct rawcomp rc[3], int hs[4], int vs[4], size_t* size)
+{
+    int cw = (w + 1) / 2, ch = (h + 1) / 2;
+    for ( int c = 0; c < 4; c++ )
+        hs[c] = vs[c] = c < 3 ? 1 : 0;
+    switch ( fmt ) {
+        case 0:
+            rc[0] = (struct rawcomp){0, 1, (size_t)w + pad};
+            hs[1] = vs[1] = hs[2] = vs[2] = 0;
+            *size = ((size_t)w + pad) * h;
+            return 1;
+        case 1:
+            for ( int c = 0; c < 3; c++ )
+                rc[c] = (struct rawcomp){(size_t)c, 3, (size_t)3 * w + pad};
+            *size = ((size_t)3 * w + pad) * h;
+            return 3;
+        case 2:
+            for ( int c = 0; c < 3; c++ )
+                rc[c] = (struct rawcomp){(size_t)c * ((size_t)w + pad) * h, 1, (size_t)w + pad};
+            *size = 3 * ((size_t)w + pad) * h;
+            return 3;
+        case 3: {
+            int we = (w + 1) & ~1;
+            size_t pitch = (size_t)2 * we + pad;
+            rc[0] = (struct rawcomp){1, 2, pitch};
+            rc[1] = (struct rawcomp){0, 4, pitch};
+            rc[2] = (struct rawcomp){2, 4, pitch};
+            hs[0] = 2;
+            *size = pitch * h;
+            return 3;
+        }
+        case 4:
+            rc[0] = (struct rawcomp){0, 1, (size_t)w + pad};
+            rc[1] = (struct rawcomp){((size_t)w + pad) * h, 1, (size_t)cw + pad};
+            rc[2] = (struct rawcomp){((size_t)w + pad) * h + ((size_t)cw + pad) * h, 1, (size_t)cw + pad};
+            hs[0] = 2;
+            *size = ((size_t)w + pad) * h + 2 * ((size_t)cw + pad) * h;
+            return 3;
+        case 5:
+            rc[0] = (struct rawcomp){0, 1, (size_t)w + pad};
+            rc[1] = (struct rawcomp){((size_t)w + pad) * h, 1, (size_t)cw + pad};
+            rc[2] = (struct rawcomp){((size_t)w + pad) * h + ((size_t)cw + pad) * ch, 1, (size_t)cw + pad};
+            hs[0] = vs[0] = 2;
+            *size = ((size_t)w + pad) * h + 2 * ((size_t)cw + pad) * ch;
+            return 3;
+        default: return 0;
+    }
+}
+
+size_t orc_raw_size(int fmt, int w, int h, int pad)
+{
+    struct rawcomp rc[3];
+    int hs[4], vs[4];
+    size_t size = 0;
+    return raw_layout(fmt, w, h, pad, rc, hs, vs, &size) ? size : 0;
+}
+
+/* Encode an image whose samples already are the JPEG's components (Y or YCbCr in the internal colour space):
+ * sampling follows the pixel format. */
+size_t orc_encode_ycc(const uint8_t* raw, int w, int h, int pad, int fmt, int quality, int rst, int interleaved,
+                      int threads, uint8_t* out, int16_t* coef_out)
+{
+    if ( w <= 0 || h <= 0 || w > 65535 || h > 65535 || rst < 0 || rst > 65535 ) return 0;
+    struct rawcomp rc[3];
+    int hs[4], vs[4];
+    size_t size;
+    const int comps = raw_layout(fmt, w, h, pad, rc, hs, vs, &size);
+    if ( !comps ) return 0;
+    enc_tables_init();
+#ifdef _OPENMP
+    int saved_threads = omp_get_max_threads();
+    omp_set_num_threads(threads > 1 ? threads : 1);
+#else
+    (void)threads;
+#endif
+    if ( comps == 1 ) interleaved = 0;
+    struct ogeo g[4];
+    int max_hs, max_vs;
+    size_t total = ogeo_init(g, comps, hs, vs, w, h, interleaved, &max_hs, &max_vs);
+    uint8_t* planes = (uint8_t*)scratch(0, total);
+    int16_t* coef = coef_out ? coef_out : (int16_t*)scratch(1, total * sizeof(int16_t));
+    memset(planes, 0, total);
+    for ( int c = 0; c < comps; c++ )
+        for ( int y = 0; y < g[c].h; y++ )
+            for ( int x = 0; x < g[c].w; x++ )
+                planes[g[c].off + (size_t)y * g[c].dw + x] = raw[rc[c].off + (size_t)y * rc[c].pitch + (size_t)x * rc[c].xs];
+    size_t n = encode_from_planes(planes, g, comps, hs, vs, w, h, quality, rst, interleaved, out, coef);
+#ifdef _OPENMP
+    omp_set_num_threads(saved_threads);
+#endif
+    return n;
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -1289,30 +1406,23 @@ static inline void decode_block(struct bitr* r, const struct dec_tab* dct, const
     }
 }
 
-/* 3-component streams with chroma subsampling, interleaved or one scan per component
- * [ref: src/gpujpeg_huffman_cpu_decoder.c:305-420; src/gpujpeg_postprocessor.cu:55-76] */
-static int decode_subsampled(const struct parsed* P, const uint8_t* jpeg, int idct_flavour, int threads, uint8_t* rgb,
-                             int16_t* coef_out)
+/* Entropy-decode + IDCT a 1- or 3-component stream of any sampling into its component planes (scratch slot 7).
+ * [ref: src/gpujpeg_huffman_cpu_decoder.c:305-420] */
+static uint8_t* decode_to_planes(const struct parsed* P, const uint8_t* jpeg, int idct_flavour, struct ogeo g[4], int* max_hs,
+                                 int* max_vs, int16_t* coef_out, int want_planes)
 {
-#ifdef _OPENMP
-    int saved_threads = omp_get_max_threads();
-    omp_set_num_threads(threads > 1 ? threads : 1);
-#else
-    (void)threads;
-#endif
+    const int comps = P->comps;
     int hs[4] = {0, 0, 0, 0}, vs[4] = {0, 0, 0, 0};
-    for ( int c = 0; c < 3; c++ ) {
-        hs[c] = P->comp_hv[c] >> 4;
-        vs[c] = P->comp_hv[c] & 15;
-        if ( hs[c] < 1 || vs[c] < 1 || hs[c] > 4 || vs[c] > 4 ) return -1;
+    for ( int c = 0; c < comps; c++ ) {
+        hs[c] = comps == 1 ? 1 : P->comp_hv[c] >> 4;
+        vs[c] = comps == 1 ? 1 : P->comp_hv[c] & 15;
+        if ( hs[c] < 1 || vs[c] < 1 || hs[c] > 4 || vs[c] > 4 ) return NULL;
     }
-    const int interleaved = P->nscan == 1;
-    if ( !interleaved && P->nscan != 3 ) return -1;
-    struct ogeo g[4];
-    int max_hs, max_vs;
-    size_t total = ogeo_init(g, 3, hs, vs, P->w, P->h, interleaved, &max_hs, &max_vs);
-    for ( int c = 0; c < 3; c++ )
-        if ( max_hs % hs[c] || max_vs % vs[c] ) return -1;
+    const int interleaved = comps > 1 && P->nscan == 1;
+    if ( !interleaved && P->nscan != comps ) return NULL;
+    size_t total = ogeo_init(g, comps, hs, vs, P->w, P->h, interleaved, max_hs, max_vs);
+    for ( int c = 0; c < comps; c++ )
+        if ( *max_hs % hs[c] || *max_vs % vs[c] ) return NULL;
     int16_t* coef = coef_out ? coef_out : (int16_t*)scratch(4, total * sizeof(int16_t));
     int mcu_x = g[0].bcx / g[0].hs;
     int rc = 0;
@@ -1324,7 +1434,7 @@ static int decode_subsampled(const struct parsed* P, const uint8_t* jpeg, int id
         size_t* sl = (size_t*)scratch(6, sizeof(size_t) * (nseg + 1));
         int n = split_scan(jpeg, P->scan[s].begin, P->scan[s].end, so, sl, nseg + 1);
         if ( n != nseg ) { rc = -1; break; }
-        if ( (interleaved && P->scan[s].ncomp != 3) || (!interleaved && P->scan[s].ncomp != 1) ) { rc = -1; break; }
+        if ( (interleaved && P->scan[s].ncomp != comps) || (!interleaved && P->scan[s].ncomp != 1) ) { rc = -1; break; }
         struct dec_tab dct[4], act[4];
         for ( int c = 0; c < P->scan[s].ncomp; c++ ) {
             dec_table_build(&dct[c], P->hbits[0][P->scan[s].td[c]], P->hvals[0][P->scan[s].td[c]]);
@@ -1343,7 +1453,7 @@ static int decode_subsampled(const struct parsed* P, const uint8_t* jpeg, int id
             }
             else {
                 for ( int m = first; m < first + cnt; m++ )
-                    for ( int c = 0; c < 3; c++ ) {
+                    for ( int c = 0; c < comps; c++ ) {
                         const struct ogeo* k = &g[P->scan[s].comp[c]];
                         for ( int y = 0; y < k->vs; y++ )
                             for ( int x = 0; x < k->hs; x++ )
@@ -1352,20 +1462,71 @@ static int decode_subsampled(const struct parsed* P, const uint8_t* jpeg, int id
             }
         }
     }
-    if ( rc == 0 && rgb ) {
-        uint8_t* planes = (uint8_t*)scratch(7, total);
-        for ( int c = 0; c < 3; c++ ) {
+    if ( rc ) return NULL;
+    uint8_t* planes = (uint8_t*)scratch(7, total);
+    if ( want_planes ) {
+        for ( int c = 0; c < comps; c++ ) {
             uint16_t inv[64];
             for ( int i = 0; i < 64; i++ )
                 inv[orc_zigzag_to_natural[i]] = P->qt[P->comp_tq[c]][i];
             orc_idct_plane(coef + g[c].off, g[c].dw, g[c].dh, inv, idct_flavour, planes + g[c].off);
         }
-        postprocess_rgb_ss(planes, g, max_hs, max_vs, rgb, P->w, P->h, 0);
+    }
+    return planes;
+}
+
+/* 3-component streams with chroma subsampling -> RGB [ref: src/gpujpeg_postprocessor.cu:55-76] */
+static int decode_subsampled(const struct parsed* P, const uint8_t* jpeg, int idct_flavour, int threads, uint8_t* rgb,
+                             int16_t* coef_out)
+{
+#ifdef _OPENMP
+    int saved_threads = omp_get_max_threads();
+    omp_set_num_threads(threads > 1 ? threads : 1);
+#else
+    (void)threads;
+#endif
+    struct ogeo g[4];
+    int max_hs, max_vs;
+    uint8_t* planes = decode_to_planes(P, jpeg, idct_flavour, g, &max_hs, &max_vs, coef_out, rgb != NULL);
+    if ( planes && rgb ) postprocess_rgb_ss(planes, g, max_hs, max_vs, rgb, P->w, P->h, 0);
+#ifdef _OPENMP
+    omp_set_num_threads(saved_threads);
+#endif
+    return planes ? 0 : -1;
+}
+
+/* Decode to a raw pixel format WITHOUT colour transform (the samples of the JPEG's components as they are):
+ * the format's sampling must be the stream's.  Returns 0 on success. */
+int orc_decode_ycc(const uint8_t* jpeg, size_t size, int idct_flavour, int threads, int fmt, int pad, uint8_t* raw)
+{
+    struct parsed P;
+    if ( parse_stream(jpeg, size, &P) != 0 ) return -1;
+    struct rawcomp rc[3];
+    int hs[4], vs[4];
+    size_t rsize;
+    const int comps = raw_layout(fmt, P.w, P.h, pad, rc, hs, vs, &rsize);
+    if ( !comps || comps != P.comps ) return -1;
+    for ( int c = 0; c < comps && comps > 1; c++ )
+        if ( (P.comp_hv[c] >> 4) != hs[c] || (P.comp_hv[c] & 15) != vs[c] ) return -1;
+#ifdef _OPENMP
+    int saved_threads = omp_get_max_threads();
+    omp_set_num_threads(threads > 1 ? threads : 1);
+#else
+    (void)threads;
+#endif
+    struct ogeo g[4];
+    int max_hs, max_vs;
+    uint8_t* planes = decode_to_planes(&P, jpeg, idct_flavour, g, &max_hs, &max_vs, NULL, 1);
+    if ( planes ) {
+        for ( int c = 0; c < comps; c++ )
+            for ( int y = 0; y < g[c].h; y++ )
+                for ( int x = 0; x < g[c].w; x++ )
+                    raw[rc[c].off + (size_t)y * rc[c].pitch + (size_t)x * rc[c].xs] = planes[g[c].off + (size_t)y * g[c].dw + x];
     }
 #ifdef _OPENMP
     omp_set_num_threads(saved_threads);
 #endif
-    return rc;
+    return planes ? 0 : -1;
 }
 
 /* [ref: src/gpujpeg_decoder.c:234-469 with the CPU Huffman path :275-295 and gpujpeg_idct_cpu] */

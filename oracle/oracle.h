@@ -75,6 +75,13 @@ size_t orc_encode_rgb(const uint8_t* rgb, int w, int h, int pad, int quality, in
  * coef_out layout: component after component, each block-major natural over ITS block grid. */
 size_t orc_encode_rgb_ss(const uint8_t* rgb, int w, int h, int pad, int quality, int rst, int interleaved, int lhs,
                          int lvs, int threads, uint8_t* out, int16_t* coef_out);
+/* Raw formats whose samples enter the JPEG without a colour transform (image colour space == internal colour space):
+ * fmt = the reference's enum gpujpeg_pixel_format value (0 u8, 1 444-u8-p012, 2 444-u8-p0p1p2, 3 422-u8-p1020,
+ * 4 422-u8-p0p1p2, 5 420-u8-p0p1p2); the JPEG's sampling is the format's.  orc_raw_size gives the buffer size. */
+size_t orc_raw_size(int fmt, int w, int h, int pad);
+size_t orc_encode_ycc(const uint8_t* raw, int w, int h, int pad, int fmt, int quality, int rst, int interleaved,
+                      int threads, uint8_t* out, int16_t* coef_out);
+int orc_decode_ycc(const uint8_t* jpeg, size_t size, int idct_flavour, int threads, int fmt, int pad, uint8_t* raw);
 /* Decode a baseline JPEG produced by this codec family (3 comp, any of the above samplings, or 1 comp) to RGB/gray u8.
  * Returns 0 on success; fills w,h,comps.  rgb may be NULL to probe. coef_out optional. */
 int orc_decode_rgb(const uint8_t* jpeg, size_t size, int idct_flavour, int threads, uint8_t* rgb,

@@ -46,6 +46,11 @@ lib.orc_encode_rgb.restype = C.c_size_t
 lib.orc_encode_rgb_ss.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   _u8p, C.c_void_p]
 lib.orc_encode_rgb_ss.restype = C.c_size_t
+lib.orc_raw_size.argtypes = [C.c_int] * 4
+lib.orc_raw_size.restype = C.c_size_t
+lib.orc_encode_ycc.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_void_p]
+lib.orc_encode_ycc.restype = C.c_size_t
+lib.orc_decode_ycc.argtypes = [_u8p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]
 lib.orc_decode_rgb.argtypes = [_u8p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int),
                                C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
 lib.orc_probe.argtypes = [_u8p, C.c_size_t, C.POINTER(StreamInfo)]
@@ -118,6 +123,42 @@ def encode(rgb, quality=75, rst=24, interleaved=0, threads=1, want_coef=False, p
     assert n > 0
     jpeg = out[:n].copy()
     return (jpeg, coef) if want_coef else jpeg
+
+
+# ---- raw formats that enter the JPEG without a colour transform (grey, planar / packed YCbCr) ----
+FMT_U8, FMT_444_P012, FMT_444_P0P1P2, FMT_422_P1020, FMT_422_P0P1P2, FMT_420_P0P1P2 = range(6)
+FMT_SAMPLING = {FMT_U8: (1, 1), FMT_444_P012: (1, 1), FMT_444_P0P1P2: (1, 1), FMT_422_P1020: (2, 1), FMT_422_P0P1P2: (2, 1),
+                FMT_420_P0P1P2: (2, 2)}
+
+
+def gen_raw(fmt, w, h, seed=777, smooth=True):
+    """synthetic raw buffer of a pixel format: smooth ramps + noise (compressible) or pure LCG noise"""
+    n = lib.orc_raw_size(fmt, w, h, 0)
+    if not smooth:
+        buf = np.empty(n, np.uint8)
+        lib.orc_gen_random(buf, n, seed)
+        return buf
+    rng = np.random.default_rng(seed)
+    t = np.arange(n, dtype=np.int64)
+    return ((t * 7 // max(1, w // 16) + rng.integers(0, 24, n)) % 256).astype(np.uint8)
+
+
+def encode_ycc(raw, w, h, fmt, quality=75, rst=8, interleaved=0, threads=1, want_coef=False):
+    comps = 1 if fmt == FMT_U8 else 3
+    il = interleaved if comps == 3 else 0
+    out = np.empty(4096 + w * h * 6 + 4096, np.uint8)
+    coef = np.zeros(coef_count(w, h, FMT_SAMPLING[fmt], il, comps), np.int16) if want_coef else None
+    n = lib.orc_encode_ycc(np.ascontiguousarray(raw), w, h, 0, fmt, quality, rst, il, threads, out,
+                           coef.ctypes.data if want_coef else None)
+    assert n > 0
+    return (out[:n].copy(), coef) if want_coef else out[:n].copy()
+
+
+def decode_ycc(jpeg, fmt, w, h, flavour=IDCT_INT, threads=1):
+    jpeg = np.ascontiguousarray(jpeg, np.uint8)
+    raw = np.zeros(lib.orc_raw_size(fmt, w, h, 0), np.uint8)
+    assert lib.orc_decode_ycc(jpeg, jpeg.size, flavour, threads, fmt, 0, raw) == 0
+    return raw
 
 
 def stream_sampling(jpeg):

@@ -4,6 +4,8 @@ Test/bench infrastructure only.
 
     python tests/_refgpu.py encode <kind> <w> <h> <q> <rst> <interleaved> <out.jpg> [<luma_h> <luma_v>]
     python tests/_refgpu.py decode <in.jpg> <out.rgb>
+    python tests/_refgpu.py encode_raw <in.raw> <pixfmt> <colorspace> <w> <h> <q> <rst> <interleaved> <out.jpg>
+    python tests/_refgpu.py decode_fmt <in.jpg> <colorspace> <pixfmt> <out.raw>
     python tests/_refgpu.py bench  <kind> <w> <h> <q> <rst> <iters>      -> prints JSON with ms per frame
 """
 import ctypes as C
@@ -101,6 +103,25 @@ def main():
             lib.gpujpeg_parameters_chroma_subsampling(C.byref(p), int(sys.argv[9]) << 28 | int(sys.argv[10]) << 24 | 0x111100)
         encode(lib, enc, img, p, pi).tofile(path)
         lib.gpujpeg_encoder_destroy(enc)
+    elif mode == "encode_raw":
+        src, fmt, cs, w, h, q, rst, il, path = sys.argv[2], *map(int, sys.argv[3:10]), sys.argv[10]
+        raw = np.fromfile(src, np.uint8)
+        enc = lib.gpujpeg_encoder_create(None)
+        p, pi = params(lib, w, h, q, rst, il)
+        pi.pixel_format, pi.color_space = fmt, cs   # comp_count stays 0: sampling follows the pixel format
+        encode(lib, enc, raw, p, pi).tofile(path)
+        lib.gpujpeg_encoder_destroy(enc)
+    elif mode == "decode_fmt":
+        data = np.fromfile(sys.argv[2], np.uint8)
+        dec = lib.gpujpeg_decoder_create(None)
+        lib.gpujpeg_decoder_set_output_format(dec, int(sys.argv[3]), int(sys.argv[4]))
+        out = DecOut()
+        out.type = 0
+        assert lib.gpujpeg_decoder_decode(dec, data.ctypes.data, data.size, C.byref(out)) == 0
+        np.ctypeslib.as_array((C.c_uint8 * out.data_size).from_address(out.data)).tofile(sys.argv[5])
+        print(json.dumps({"pixel_format": out.param_image.pixel_format, "color_space": out.param_image.color_space,
+                          "size": out.data_size}))
+        lib.gpujpeg_decoder_destroy(dec)
     elif mode == "decode":
         data = np.fromfile(sys.argv[2], np.uint8)
         dec = lib.gpujpeg_decoder_create(None)

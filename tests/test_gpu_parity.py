@@ -162,6 +162,61 @@ def test_subsampled_8k_round_trip(enc, dec):
     assert np.array_equal(dec.decode(j), o.decode(j))
 
 
+# ---- raw formats without colour transform: grey, planar and packed YCbCr ----
+FMT_NAMES = {o.FMT_U8: "u8", o.FMT_444_P012: "444-u8-p012", o.FMT_444_P0P1P2: "444-u8-p0p1p2", o.FMT_422_P1020: "422-u8-p1020",
+             o.FMT_422_P0P1P2: "422-u8-p0p1p2", o.FMT_420_P0P1P2: "420-u8-p0p1p2"}
+FMT_CASES = [(64, 48, 75, 4), (1920, 1080, 75, 12), (1118, 561, 90, 8), (34, 18, 85, 0), (16, 16, 100, 1)]
+
+
+@pytest.mark.parametrize("il", [0, 1])
+@pytest.mark.parametrize("fmt", sorted(FMT_NAMES), ids=[FMT_NAMES[f] for f in sorted(FMT_NAMES)])
+@pytest.mark.parametrize("w,h,q,rst", FMT_CASES)
+def test_raw_formats_encode_and_decode_bit_exact(gj, enc, w, h, q, rst, fmt, il):
+    """samples already in the JPEG's colour space: product == oracle for the JPEG bytes and for the decoded samples,
+    with the decoder asked for the same pixel format (no colour transform either way)"""
+    raw = o.gen_raw(fmt, w, h, smooth=w > 100)
+    want = o.encode_ycc(raw, w, h, fmt, q, rst, il, threads=4)
+    got = enc.encode_samples(raw, w, h, fmt, q, rst, il)
+    assert got.size == want.size and np.array_equal(got, want), "JPEG bytes differ from the oracle"
+    d = gj.Decoder()
+    try:
+        d.set_output_format(gj.api.GPUJPEG_YCBCR_JPEG, fmt)
+        out, pi = d.decode_samples(want)
+        assert pi.pixel_format == fmt and pi.width == w and pi.height == h
+        assert np.array_equal(out, o.decode_ycc(want, fmt, w, h, threads=4)), "decoded samples differ from the oracle"
+        # the special request values resolve as in the reference [ref: src/gpujpeg_reader.c:1507-1581]
+        if fmt != o.FMT_U8:
+            d.set_output_format(gj.api.GPUJPEG_YCBCR_JPEG, gj.api.GPUJPEG_PIXFMT_NATIVE)
+            _, pi = d.decode_samples(want)
+            lh, lv = o.FMT_SAMPLING[fmt]
+            native = {(1, 1): (o.FMT_444_P0P1P2, o.FMT_444_P012), (2, 1): (o.FMT_422_P0P1P2, o.FMT_422_P1020),
+                      (2, 2): (o.FMT_420_P0P1P2, o.FMT_420_P0P1P2)}[(lh, lv)][il]
+            assert pi.pixel_format == native
+    finally:
+        d.close()
+
+
+def test_grey_default_output_and_rgb_request_is_refused(gj, enc):
+    raw = o.gen_raw(o.FMT_U8, 200, 100)
+    jpeg = enc.encode_samples(raw, 200, 100, o.FMT_U8, 80, 4)
+    d = gj.Decoder()
+    try:
+        out, pi = d.decode_samples(jpeg)            # default request: GPUJPEG_U8 for a 1-component stream
+        assert pi.pixel_format == o.FMT_U8 and np.array_equal(out, o.decode_ycc(jpeg, o.FMT_U8, 200, 100))
+        d.set_output_format(gj.api.GPUJPEG_RGB, o.FMT_444_P012)
+        with pytest.raises(gj.GpuJpegError):
+            d.decode_samples(jpeg)
+    finally:
+        d.close()
+
+
+def test_ycbcr_stream_decodes_to_rgb_by_default(gj, enc, dec):
+    """a 4:2:0 stream made from planar YCbCr input is an ordinary YCbCr JPEG: the default request gives RGB"""
+    raw = o.gen_raw(o.FMT_420_P0P1P2, 320, 200)
+    jpeg = enc.encode_samples(raw, 320, 200, o.FMT_420_P0P1P2, 85, 6, 1)
+    assert np.array_equal(dec.decode(jpeg), o.decode(jpeg))
+
+
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
 
 
@@ -239,7 +294,7 @@ def test_row_padding(enc):
 def test_unsupported_parameters_fail_loudly(gj, enc):
     p = gj.api.default_parameters()
     pi = gj.api.image_parameters(64, 64)
-    pi.pixel_format = gj.api.GPUJPEG_422_U8_P1020
+    pi.pixel_format = gj.api.GPUJPEG_422_U8_P1020   # packed 4:2:2 samples cannot be GPUJPEG_RGB
     img = np.zeros((64, 64, 3), np.uint8)
     with pytest.raises(gj.GpuJpegError):
         enc.encode_raw(img, p, pi)

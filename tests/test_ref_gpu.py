@@ -79,3 +79,34 @@ def test_reference_gpu_subsampled_encode_and_decode(tmp_path, kind, w, h, q, rst
     d = g.Decoder(idct="float_gpuref")
     assert np.array_equal(d.decode(ref), pix), "product decode != reference GPU decoder"
     d.close()
+
+
+FMTS = {0: "u8", 1: "444-u8-p012", 2: "444-u8-p0p1p2", 3: "422-u8-p1020", 4: "422-u8-p0p1p2", 5: "420-u8-p0p1p2"}
+
+
+@pytest.mark.skipif(not os.path.exists(SO), reason="oracle/_ref/libgpujpeg_refgpu.so not built")
+@pytest.mark.parametrize("il", [0, 1])
+@pytest.mark.parametrize("fmt", sorted(FMTS), ids=[FMTS[f] for f in sorted(FMTS)])
+@pytest.mark.parametrize("w,h,q,rst", [(640, 360, 80, 6), (1118, 561, 90, 8)])
+def test_reference_gpu_raw_formats(tmp_path, w, h, q, rst, fmt, il):
+    """grey / planar / packed YCbCr input in the JPEG colour space (no colour transform): reference GPU encoder bytes
+    == oracle == product; reference GPU decoder samples (same format requested) == float flavour of oracle and product"""
+    raw = o.gen_raw(fmt, w, h)
+    src, path, dst = tmp_path / "in.raw", tmp_path / "ref.jpg", tmp_path / "out.raw"
+    raw.tofile(src)
+    run_ref("encode_raw", src, fmt, 3, w, h, q, rst, il, path)     # 3 = GPUJPEG_YCBCR_BT601_256LVLS
+    ref = np.fromfile(path, np.uint8)
+    want = o.encode_ycc(raw, w, h, fmt, q, rst, il, threads=4)
+    assert ref.size == want.size and np.array_equal(ref, want), "oracle restatement != reference GPU library output"
+    import gpujpeg_b200 as g
+    e = g.Encoder()
+    assert np.array_equal(e.encode_samples(raw, w, h, fmt, q, rst, il), ref), "product != reference GPU library output"
+    e.close()
+    run_ref("decode_fmt", path, 3, fmt, dst)
+    pix = np.fromfile(dst, np.uint8)
+    assert np.array_equal(pix, o.decode_ycc(ref, fmt, w, h, o.IDCT_FLOAT_GPUREF, threads=4)), "oracle != reference GPU decoder"
+    d = g.Decoder(idct="float_gpuref")
+    d.set_output_format(g.api.GPUJPEG_YCBCR_JPEG, fmt)
+    out, _ = d.decode_samples(ref)
+    assert np.array_equal(out, pix), "product decode != reference GPU decoder"
+    d.close()
