@@ -1346,6 +1346,7 @@ static int split_scan(const uint8_t* j, size_t b, size_t e, size_t* seg_off, siz
         if ( !f ) break;
         i = (size_t)(f - j);
         int m = j[i + 1];
+        if ( m == 0xFF ) { i++; continue; }   /* fill byte in front of a marker (T.81 B.1.1.2) */
         if ( m >= 0xD0 && m <= 0xD7 ) {
             if ( n >= max_seg ) return -1;
             seg_off[n] = start;

@@ -1,0 +1,176 @@
+"""Foreign-stream robustness of the decoder: streams that carry the same image as one
+of the codec family's own files but are laid out the way other encoders do it -- other table ids, no DRI marker,
+extra marker segments, fill bytes -- must decode to the same pixels; streams outside baseline JPEG or with a broken
+restart structure must be refused with an error, never decoded to garbage or crash.  GPU, through the C ABI."""
+import numpy as np
+import pytest
+
+import _oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gj():
+    import gpujpeg_b200
+    return gpujpeg_b200
+
+
+@pytest.fixture(scope="module")
+def dec(gj):
+    d = gj.Decoder()
+    yield d
+    d.close()
+
+
+def segments(j):
+    """[(marker, start, end)] of the marker segments in front of the first SOS, plus the SOS position"""
+    j = bytes(j)
+    i, out = 2, []
+    while j[i + 1] != 0xDA:
+        ln = (j[i + 2] << 8) | j[i + 3]
+        out.append((j[i + 1], i, i + 2 + ln))
+        i += 2 + ln
+    return out, i
+
+
+def swap_table_ids(jpeg):
+    """quantisation tables 0<->1, DC Huffman tables 0<->1 (AC stay): luminance then uses Tq 1, Td 1, Ta 0"""
+    j = bytearray(jpeg)
+    segs, _ = segments(j)
+    for m, a, b in segs:
+        if m == 0xDB:
+            j[a + 4] ^= 1
+        elif m == 0xC4 and (j[a + 4] >> 4) == 0:
+            j[a + 4] ^= 1
+        elif m == 0xC0:
+            for c in range(j[a + 9]):
+                j[a + 10 + 3 * c + 2] ^= 1
+    i = 0
+    while True:   # every SOS: flip the DC selector of each component
+        i = bytes(j).find(b"\xff\xda", i)
+        if i < 0:
+            break
+        for c in range(j[i + 4]):
+            j[i + 5 + 2 * c + 1] ^= 0x10
+        i += 4
+    return np.frombuffer(bytes(j), np.uint8)
+
+
+CASES = [("photo", 320, 200, 80, 6, 0, (1, 1)), ("random", 161, 97, 90, 4, 1, (2, 2)), ("photo", 128, 64, 75, 0, 1, (2, 1))]
+
+
+@pytest.mark.parametrize("kind,w,h,q,rst,il,samp", CASES)
+def test_other_table_ids(dec, kind, w, h, q, rst, il, samp):
+    jpeg = o.encode(o.gen_image(kind, w, h), q, rst, il, sampling=samp)
+    want = o.decode(jpeg)
+    other = swap_table_ids(jpeg)
+    assert not np.array_equal(other, jpeg)
+    assert np.array_equal(o.decode(other), want), "oracle must read the re-labelled stream as the same image"
+    assert np.array_equal(dec.decode(other), want)
+
+
+@pytest.mark.parametrize("il,samp", [(0, (1, 1)), (1, (2, 2))])
+def test_stream_without_dri_and_with_extra_segments(dec, il, samp):
+    """no DRI marker at all (restart interval 0 by default), an Exif-like APP1, an APP13, two comments"""
+    jpeg = bytes(o.encode(o.gen_image("photo", 200, 120), 85, 0, il, sampling=samp))
+    want = o.decode(np.frombuffer(jpeg, np.uint8))
+    segs, sos = segments(jpeg)
+    dri = [(a, b) for m, a, b in segs if m == 0xDD][0]
+    extra = b"\xff\xe1\x00\x10Exif\x00\x00MM\x00\x2a\x00\x00\x00\x08" + b"\xff\xed\x00\x06abcd" + b"\xff\xfe\x00\x05hi\x00"
+    other = jpeg[:dri[0]] + extra + jpeg[dri[1]:sos] + b"\xff\xfe\x00\x04ok" + jpeg[sos:]
+    other = np.frombuffer(other, np.uint8)
+    assert np.array_equal(o.decode(other), want)
+    assert np.array_equal(dec.decode(other), want)
+
+
+def test_fill_bytes_before_restart_markers(dec):
+    jpeg = bytes(o.encode(o.gen_image("random", 96, 64), 75, 3, 0))
+    want = o.decode(np.frombuffer(jpeg, np.uint8))
+    _, sos = segments(jpeg)
+    body = bytearray()
+    i = sos
+    while i < len(jpeg):
+        if jpeg[i] == 0xFF and 0xD0 <= jpeg[i + 1] <= 0xD7 and (i // 7) % 2 == 0:
+            body += b"\xff\xff"          # one fill byte in front of about half of the RSTn markers
+            body.append(jpeg[i + 1])
+            i += 2
+        else:
+            body.append(jpeg[i])
+            i += 1
+    other = np.frombuffer(jpeg[:sos] + bytes(body), np.uint8)
+    assert other.size > len(jpeg)
+    assert np.array_equal(o.decode(other), want)
+    assert np.array_equal(dec.decode(other), want)
+
+
+def test_tables_merged_into_one_segment_each(dec):
+    """all DQT tables in one DQT segment and all DHT tables in one DHT segment (what libjpeg writes with -optimize off)"""
+    jpeg = bytes(o.encode(o.gen_image("photo", 160, 96), 75, 5, 1))
+    want = o.decode(np.frombuffer(jpeg, np.uint8))
+    segs, sos = segments(jpeg)
+    dqt = b"".join(jpeg[a + 4:b] for m, a, b in segs if m == 0xDB)
+    dht = b"".join(jpeg[a + 4:b] for m, a, b in segs if m == 0xC4)
+    rest = b"".join(jpeg[a:b] for m, a, b in segs if m not in (0xDB, 0xC4))
+    mk = lambda code, payload: bytes([0xFF, code, (len(payload) + 2) >> 8, (len(payload) + 2) & 255]) + payload
+    other = np.frombuffer(jpeg[:2] + mk(0xDB, dqt) + rest + mk(0xC4, dht) + jpeg[sos:], np.uint8)
+    assert np.array_equal(o.decode(other), want)
+    assert np.array_equal(dec.decode(other), want)
+
+
+def expect_error(gj, data):
+    d = gj.Decoder()
+    try:
+        with pytest.raises(gj.GpuJpegError):
+            d.decode(np.frombuffer(bytes(data), np.uint8))
+    finally:
+        d.close()
+
+
+def test_refused_streams(gj):
+    jpeg = bytearray(o.encode(o.gen_image("photo", 128, 96), 75, 4, 0))
+    segs, sos = segments(jpeg)
+    # progressive frame header
+    sof = [a for m, a, b in segs if m == 0xC0][0]
+    prog = bytearray(jpeg)
+    prog[sof + 1] = 0xC2
+    expect_error(gj, prog)
+    # 12-bit samples
+    deep = bytearray(jpeg)
+    deep[sof + 4] = 12
+    expect_error(gj, deep)
+    # 16-bit quantisation table
+    dqt = [a for m, a, b in segs if m == 0xDB][0]
+    wide = bytearray(jpeg)
+    wide[dqt + 4] |= 0x10
+    expect_error(gj, wide)
+    # a restart marker removed: the scan has one segment too few
+    i = bytes(jpeg).find(b"\xff\xd1", sos)
+    expect_error(gj, jpeg[:i] + jpeg[i + 2:])
+    # restart markers out of sequence
+    swapped = bytearray(jpeg)
+    swapped[i + 1] = 0xD5
+    expect_error(gj, swapped)
+    # truncated in the middle of the scan data, and in the middle of the headers
+    expect_error(gj, jpeg[:sos + 40])
+    expect_error(gj, jpeg[:sof + 6])
+    # not a JPEG at all
+    expect_error(gj, b"\x89PNG\r\n\x1a\n" + bytes(64))
+
+
+def test_decoder_survives_garbage_entropy_data(gj, dec):
+    """random bytes in place of the entropy-coded data must not crash or hang the GPU; the call may succeed or fail"""
+    jpeg = bytearray(o.encode(o.gen_image("photo", 256, 128), 75, 8, 0))
+    _, sos = segments(jpeg)
+    rng = np.random.default_rng(9)
+    end = len(jpeg) - 2
+    for i in range(sos + 12, end):
+        if not (jpeg[i] == 0xFF or jpeg[i - 1] == 0xFF):     # keep the marker structure, scramble the rest
+            jpeg[i] = int(rng.integers(0, 255))
+    try:
+        out = dec.decode(np.frombuffer(bytes(jpeg), np.uint8))
+        assert out.shape == (128, 256, 3)
+    except gj.GpuJpegError:
+        pass
+    good = o.encode(o.gen_image("photo", 64, 64), 75, 4)
+    assert np.array_equal(dec.decode(good), o.decode(good)), "the coder must stay usable afterwards"
