@@ -82,8 +82,34 @@ static const uint8_t k_vals_ac_c[162] = {
     0xc2, 0xc3, 0xc4, 0xc5, 0xc6, 0xc7, 0xc8, 0xc9, 0xca, 0xd2, 0xd3, 0xd4, 0xd5, 0xd6, 0xd7, 0xd8, 0xd9, 0xda,
     0xe2, 0xe3, 0xe4, 0xe5, 0xe6, 0xe7, 0xe8, 0xe9, 0xea, 0xf2, 0xf3, 0xf4, 0xf5, 0xf6, 0xf7, 0xf8, 0xf9, 0xfa};
 
+/* test hook: Huffman tables other than Annex K (what an optimising foreign encoder writes).  The override is used
+ * by the header writer and by the encoder until it is cleared again with bits17 == NULL. */
+static uint8_t g_custom_bits[2][2][17], g_custom_vals[2][2][256];
+static int g_custom_n[2][2], g_custom_on = 0;
+static int g_enc_ready;
+void orc_set_huffman_override(int cls, int kind, const uint8_t* bits17, const uint8_t* vals, int nvals)
+{
+    if ( !bits17 ) {
+        g_custom_on = 0;
+        memset(g_custom_n, 0, sizeof g_custom_n);
+    }
+    else {
+        memcpy(g_custom_bits[cls][kind], bits17, 17);
+        memcpy(g_custom_vals[cls][kind], vals, (size_t)nvals);
+        g_custom_n[cls][kind] = nvals;
+        g_custom_on = 1;
+    }
+    g_enc_ready = 0;
+}
+
 void orc_huff_spec(int cls, int kind, const uint8_t** bits17, const uint8_t** vals, int* nvals)
 {
+    if ( g_custom_on && g_custom_n[cls][kind] ) {
+        *bits17 = g_custom_bits[cls][kind];
+        *vals = g_custom_vals[cls][kind];
+        *nvals = g_custom_n[cls][kind];
+        return;
+    }
     if ( kind == 0 ) {
         *bits17 = cls == 0 ? k_bits_dc_y : k_bits_dc_c;
         *vals = k_vals_dc;
@@ -541,7 +567,6 @@ struct enc_tab {
     uint8_t size[256];
 };
 static struct enc_tab g_enc[2][2];
-static int g_enc_ready = 0;
 static void enc_tables_init(void)
 {
 #pragma omp critical(orc_enc_tables)

@@ -36,6 +36,8 @@ void orc_gen_photo(uint8_t* data, int width, int height, int seed);       /* S-p
 void orc_quant_tables(int quality, uint8_t raw[2][64], float fwd[2][64], uint16_t inv[2][64]);
 /* Annex K Huffman spec: cls 0 = luminance, 1 = chrominance; kind 0 = DC, 1 = AC */
 void orc_huff_spec(int cls, int kind, const uint8_t** bits17, const uint8_t** vals, int* nvals);
+/* test hook: replace the table of (cls, kind) in header writer and encoder; bits17 == NULL restores Annex K */
+void orc_set_huffman_override(int cls, int kind, const uint8_t* bits17, const uint8_t* vals, int nvals);
 /* code/size per symbol (encoder view) */
 void orc_huff_encoder_table(int cls, int kind, uint16_t code[256], uint8_t size[256]);
 

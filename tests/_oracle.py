@@ -46,6 +46,7 @@ lib.orc_encode_rgb.restype = C.c_size_t
 lib.orc_encode_rgb_ss.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   _u8p, C.c_void_p]
 lib.orc_encode_rgb_ss.restype = C.c_size_t
+lib.orc_set_huffman_override.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
 lib.orc_raw_size.argtypes = [C.c_int] * 4
 lib.orc_raw_size.restype = C.c_size_t
 lib.orc_encode_ycc.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_void_p]
@@ -159,6 +160,50 @@ def decode_ycc(jpeg, fmt, w, h, flavour=IDCT_INT, threads=1):
     raw = np.zeros(lib.orc_raw_size(fmt, w, h, 0), np.uint8)
     assert lib.orc_decode_ycc(jpeg, jpeg.size, flavour, threads, fmt, 0, raw) == 0
     return raw
+
+
+def random_huffman_spec(symbols, rng, skew=3.0):
+    """a valid JPEG Huffman table (BITS[17], HUFFVAL) for `symbols` with random code lengths <= 16: Huffman's algorithm on
+    random frequencies plus one reserved dummy symbol, so that the all-ones code stays unused (T.81 Annex K.2)"""
+    import heapq
+    while True:
+        freq = np.exp(-skew * rng.random(len(symbols)) * np.arange(len(symbols)) / 8.0) + 1e-9
+        heap = [(float(f), i, [i]) for i, f in enumerate(freq)] + [(1e-12, len(symbols), [len(symbols)])]
+        heapq.heapify(heap)
+        depth = np.zeros(len(symbols) + 1, int)
+        uid = len(symbols) + 1
+        while len(heap) > 1:
+            a, b = heapq.heappop(heap), heapq.heappop(heap)
+            for i in a[2] + b[2]:
+                depth[i] += 1
+            heapq.heappush(heap, (a[0] + b[0], uid, a[2] + b[2]))
+            uid += 1
+        if depth.max() <= 16:
+            break
+        skew *= 0.7
+    bits = np.zeros(17, np.uint8)
+    order = sorted(range(len(symbols)), key=lambda i: (depth[i], rng.random()))
+    for i in order:
+        bits[depth[i]] += 1
+    return bits, np.array([symbols[i] for i in order], np.uint8)
+
+
+class huffman_override:
+    """with huffman_override(rng): ... -- the oracle writes and uses four random Huffman tables inside the block"""
+
+    def __init__(self, rng):
+        self.rng = rng
+
+    def __enter__(self):
+        ac = [0x00, 0xF0] + [(r << 4) | s for r in range(16) for s in range(1, 11)]
+        for cls in range(2):
+            for kind, syms in ((0, list(range(12))), (1, ac)):
+                bits, vals = random_huffman_spec(syms, self.rng)
+                lib.orc_set_huffman_override(cls, kind, bits.ctypes.data, vals.ctypes.data, len(vals))
+        return self
+
+    def __exit__(self, *exc):
+        lib.orc_set_huffman_override(0, 0, None, None, 0)
 
 
 def stream_sampling(jpeg):

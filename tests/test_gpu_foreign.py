@@ -118,6 +118,20 @@ def test_tables_merged_into_one_segment_each(dec):
     assert np.array_equal(dec.decode(other), want)
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("kind,w,h,q,rst,il,samp", [("photo", 320, 200, 80, 6, 0, (1, 1)), ("random", 161, 97, 95, 4, 1, (2, 2))])
+def test_custom_huffman_tables(dec, seed, kind, w, h, q, rst, il, samp):
+    """four random Huffman tables (code lengths up to 16, not Annex K) as an optimising encoder would write them: the
+    decoder's lookup tables are built from the DHT segments of the stream, whatever they hold"""
+    img = o.gen_image(kind, w, h)
+    want = o.decode(o.encode(img, q, rst, il, sampling=samp))
+    with o.huffman_override(np.random.default_rng(seed)):
+        other = o.encode(img, q, rst, il, sampling=samp)
+    assert not np.array_equal(other, o.encode(img, q, rst, il, sampling=samp)), "override must change the stream"
+    assert np.array_equal(o.decode(other), want), "same coefficients, other codes: same pixels"
+    assert np.array_equal(dec.decode(other), want)
+
+
 def expect_error(gj, data):
     d = gj.Decoder()
     try:
