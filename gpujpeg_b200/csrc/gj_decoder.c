@@ -634,7 +634,14 @@ int gpujpeg_decoder_get_image_info2(uint8_t* image, size_t image_size, struct gp
     info->param_image.width = st.width;
     info->param_image.height = st.height;
     info->param_image.color_space = st.color_space;
+    /* the stream's native pixel format [ref: src/gpujpeg_reader.c:1507-1547, 1750] */
     info->param_image.pixel_format = st.comp_count == 1 ? GPUJPEG_U8 : GPUJPEG_444_U8_P012;
+    if ( st.comp_count == 3 && st.comp_hv[1] == 0x11 && st.comp_hv[2] == 0x11 ) {
+        const int il = st.interleaved;
+        if ( st.comp_hv[0] == 0x22 ) info->param_image.pixel_format = GPUJPEG_420_U8_P0P1P2;
+        else if ( st.comp_hv[0] == 0x21 ) info->param_image.pixel_format = il ? GPUJPEG_422_U8_P1020 : GPUJPEG_422_U8_P0P1P2;
+        else info->param_image.pixel_format = il ? GPUJPEG_444_U8_P012 : GPUJPEG_444_U8_P0P1P2;
+    }
     info->param.comp_count = st.comp_count;
     info->param.restart_interval = st.restart_interval;
     info->param.interleaved = st.interleaved;

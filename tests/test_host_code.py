@@ -128,3 +128,23 @@ def test_geometry_with_chroma_subsampling(w, h, rst, sampling, il):
     assert out[14] == seg_mcu and out[15] == bpm
     assert out[19] == (1 if sampling == (1, 1) else 0)
     assert out[18] >= seg_mcu * bpm * 416 and out[18] % 128 == 0
+
+
+@pytest.mark.parametrize("fmt,il,native", [(o.FMT_U8, 0, o.FMT_U8), (o.FMT_444_P012, 1, o.FMT_444_P012),
+                                           (o.FMT_444_P012, 0, o.FMT_444_P0P1P2), (o.FMT_422_P1020, 1, o.FMT_422_P1020),
+                                           (o.FMT_422_P0P1P2, 0, o.FMT_422_P0P1P2), (o.FMT_420_P0P1P2, 1, o.FMT_420_P0P1P2)])
+def test_get_image_info_reports_the_stream_as_the_reference_does(fmt, il, native):
+    """gpujpeg_decoder_get_image_info is pure host code (no GPU): size, components, sampling, restart interval,
+    interleaving, segment count and the stream's native pixel format [ref: src/gpujpeg_reader.c:1507-1547, 1740-1790]"""
+    import ctypes as C
+    import gpujpeg_b200.api as api
+    w, h, rst = 100, 60, 5
+    jpeg = o.encode_ycc(o.gen_raw(fmt, w, h), w, h, fmt, 75, rst, il)
+    pi, p, nseg = api.ImageParameters(), api.Parameters(), C.c_int()
+    assert api.lib.gpujpeg_decoder_get_image_info(jpeg.ctypes.data, jpeg.size, C.byref(pi), C.byref(p), C.byref(nseg)) == 0
+    comps = 1 if fmt == o.FMT_U8 else 3
+    assert (pi.width, pi.height, p.comp_count, p.restart_interval) == (w, h, comps, rst)
+    assert p.interleaved == (il if comps == 3 else 0) and pi.pixel_format == native
+    lh, lv = o.FMT_SAMPLING[fmt]
+    assert (p.sampling_factor[0].horizontal, p.sampling_factor[0].vertical) == (lh, lv)
+    assert nseg.value == o.probe(jpeg).segment_count
