@@ -476,6 +476,12 @@ k_huff_compact(const uint8_t* __restrict__ tmp, size_t slot_stride, const uint32
 /* decoder                                                                                       */
 
 constexpr int HD_THREADS = 128;
+#ifndef GJ_HD_SPW
+#define GJ_HD_SPW 16
+#endif
+/* measured on B200, 8K 4:4:4 frame, photo-like / random content: 32 owners per warp 207 / 538 us, 16: 190 / 526 us,
+ * 8: 189 / 878 us (issue-bound on dense streams), 4: 255 / 1318 us */
+constexpr int HD_SEGMENTS_PER_WARP = GJ_HD_SPW;
 
 struct DecTabs {
     gj_dec_lut t[2][4];
@@ -570,7 +576,11 @@ __device__ __forceinline__ int decode_symbol(BitSource& r, const gj_dec_lut& t)
 /* DEQ: store coefficient * quantiser wrapped to int16 -- exactly what the reference's integer IDCT
  * starts from (src/gpujpeg_dct_cpu.c:180-182) -- so the multiply is paid per NON-ZERO coefficient here
  * instead of 64 times per block in K4.  DEQ = false keeps raw quantised values (float IDCT flavour). */
-template <bool DEQ>
+/* SPW = segments per warp: only the first SPW lanes of a warp own a segment, the others just help to move the finished
+ * blocks out.  Fewer owners per warp make the warp's instruction stream shorter (the lock-step block loop runs as
+ * long as its slowest lane, and every rarely-taken path is executed whenever ANY lane takes it), and that stream,
+ * not the issue rate, is what bounds this kernel: 43 200 segments cannot fill the machine anyway. */
+template <bool DEQ, int SPW>
 __global__ void __launch_bounds__(HD_THREADS)
 k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file_end, const uint32_t* __restrict__ seg_off,
               int seg_count, int seg_mcu, const __grid_constant__ gj_huff_dec_args a,
@@ -578,7 +588,7 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file
 {
     __shared__ DecTabs s_tab;
     __shared__ uint16_t s_q[4][64];
-    __shared__ __align__(16) uint32_t s_blk[HD_THREADS * 32];   // one private 8x8 block (128 B) per thread
+    __shared__ __align__(16) uint32_t s_blk[(HD_THREADS / 32) * SPW * 32];   // one private 8x8 block (128 B) per owner lane
 
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(&tables->lut[0][0]);
@@ -587,17 +597,17 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file
             dst[i] = src[i];
         for ( int i = threadIdx.x; i < 256; i += HD_THREADS )
             s_q[i >> 6][i & 63] = tables->qinv_zz[i >> 6][i & 63];
-        for ( int i = threadIdx.x; i < HD_THREADS * 32; i += HD_THREADS )
+        for ( int i = threadIdx.x; i < (HD_THREADS / 32) * SPW * 32; i += HD_THREADS )
             s_blk[i] = 0;
     }
     __syncthreads();
 
-    const int lane = threadIdx.x & 31;
-    const int g0 = (blockIdx.x * HD_THREADS + threadIdx.x) & ~31;  // first segment of this warp
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g0 = (blockIdx.x * (HD_THREADS / 32) + warp) * SPW;  // first segment of this warp
     if ( g0 >= seg_count ) return;
     if ( !seg_off && *a.d_error ) return;   // restart structure does not match the geometry: list ranks are meaningless
     const int g = g0 + lane;
-    const bool live = g < seg_count;
+    const bool live = lane < SPW && g < seg_count;
     const gj_scan_layout& L = a.lay;
     const int bpm = L.bpm;
     const bool general = !L.simple && L.interleaved;   // MCUs of several blocks per component
@@ -636,8 +646,8 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file
     /* private block: 16-byte chunk c of lane L lives at chunk (c ^ (L & 7)) so that the warp-wide
      * 16-byte reads of the flush below are bank-conflict free */
     const int sw = lane & 7;
-    int16_t* mine = reinterpret_cast<int16_t*>(s_blk + threadIdx.x * 32);
-    uint4* wbase = reinterpret_cast<uint4*>(s_blk + (threadIdx.x & ~31) * 32);
+    int16_t* mine = reinterpret_cast<int16_t*>(s_blk + (warp * SPW + (lane < SPW ? lane : 0)) * 32);
+    uint4* wbase = reinterpret_cast<uint4*>(s_blk + warp * SPW * 32);
     int pred[GJ_MAX_COMP] = {0, 0, 0, 0};
 
     int mcu = 0, bi_in_mcu = 0;   // block b = mcu * bpm + bi_in_mcu, the same in every lane
@@ -687,9 +697,9 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file
         else {
             target = mybase + (L.interleaved ? L.blk_off[a.scan_comp[0][ci]] : 0) + mcu;
         }
-        /* write the warp's 32 private blocks out as 128-byte lines, four blocks per step, and clear them */
+        /* write the warp's SPW private blocks out as 128-byte lines, four blocks per step, and clear them */
 #pragma unroll
-        for ( int j = 0; j < 8; j++ ) {
+        for ( int j = 0; j < SPW / 4; j++ ) {
             const int i = 4 * j + (lane >> 3);   // owner lane of the block this lane helps to move
             const int c = lane & 7;              // its 16-byte chunk
             const int ob = __shfl_sync(FULL, target, i);
@@ -755,13 +765,15 @@ extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_str
 
 extern "C" int gj_launch_huffman_decode(const struct gj_huff_dec_args* a, gj_stream_t stream)
 {
-    const dim3 grid((a->seg_count + HD_THREADS - 1) / HD_THREADS);
+    constexpr int SPW = HD_SEGMENTS_PER_WARP;
+    const int per_cta = (HD_THREADS / 32) * SPW;
+    const dim3 grid((a->seg_count + per_cta - 1) / per_cta);
     if ( a->dequantize )
-        k_huff_decode<true><<<grid, HD_THREADS, 0, stream>>>(a->d_file, a->d_file + a->file_size, a->d_seg_off, a->seg_count,
-                                                             a->seg_mcu, *a, a->d_coef, a->d_tables);
+        k_huff_decode<true, SPW><<<grid, HD_THREADS, 0, stream>>>(a->d_file, a->d_file + a->file_size, a->d_seg_off, a->seg_count,
+                                                                  a->seg_mcu, *a, a->d_coef, a->d_tables);
     else
-        k_huff_decode<false><<<grid, HD_THREADS, 0, stream>>>(a->d_file, a->d_file + a->file_size, a->d_seg_off, a->seg_count,
-                                                              a->seg_mcu, *a, a->d_coef, a->d_tables);
+        k_huff_decode<false, SPW><<<grid, HD_THREADS, 0, stream>>>(a->d_file, a->d_file + a->file_size, a->d_seg_off, a->seg_count,
+                                                                   a->seg_mcu, *a, a->d_coef, a->d_tables);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
