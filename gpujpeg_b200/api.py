@@ -211,10 +211,15 @@ class Encoder:
         return np.ctypeslib.as_array((C.c_uint8 * size).from_address(addr)).copy()
 
     def encode_samples(self, raw, width, height, pixel_format, quality=75, restart_interval=RESTART_AUTO, interleaved=0,
-                       color_space=GPUJPEG_YCBCR_JPEG):
-        """raw: flat uint8 buffer in `pixel_format` whose samples already are the JPEG's components (grey, or YCbCr in
-        the JPEG colour space): no colour transform, the JPEG takes the format's sampling.  Returns the JPEG bytes."""
-        p = default_parameters(quality, restart_interval, interleaved)   # comp_count 0: derived from the pixel format
+                       color_space=GPUJPEG_YCBCR_JPEG, subsampling=None):
+        """raw: flat uint8 buffer in `pixel_format` / `color_space`.  With the JPEG colour space and subsampling=None the
+        samples go into the JPEG as they are (the JPEG takes the format's sampling); other colour spaces are
+        transformed, and `subsampling` ("4:2:0", ...) selects a JPEG sampling other than the format's.  Returns the
+        JPEG bytes."""
+        p = default_parameters(quality, restart_interval, interleaved, subsampling or "4:4:4")
+        if subsampling == "4:4:4":
+            lib.gpujpeg_parameters_chroma_subsampling(C.byref(p), 0x11111100)
+        # subsampling None: comp_count stays 0 and the sampling is derived from the pixel format
         addr, size = self.encode_raw(raw, p, image_parameters(width, height, 0, pixel_format, color_space))
         return np.ctypeslib.as_array((C.c_uint8 * size).from_address(addr)).copy()
 

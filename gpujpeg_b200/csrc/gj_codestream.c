@@ -73,6 +73,23 @@ int gj_raw_layout_init(struct gj_raw_layout* l, const struct gpujpeg_image_param
     }
 }
 
+void gj_planes_layout(struct gj_raw_layout* l, struct gj_comp_geo padded[GJ_MAX_COMP], const struct gj_comp_geo* comp,
+                      int comp_count)
+{
+    memset(l, 0, sizeof *l);
+    l->comp_count = comp_count;
+    for ( int c = 0; c < comp_count; c++ ) {
+        l->comp[c] = (struct gj_raw_comp){(size_t)comp[c].blk_off * 64, (size_t)comp[c].bcx * 8, 1};
+        l->sampling[c].horizontal = (uint8_t)comp[c].hs;
+        l->sampling[c].vertical = (uint8_t)comp[c].vs;
+        l->size = ((size_t)comp[c].blk_off + comp[c].nblk) * 64;
+        /* the planes are padded to whole blocks with zeros: treat the padding as samples, every row is 8-byte aligned */
+        padded[c] = comp[c];
+        padded[c].width = comp[c].bcx * 8;
+        padded[c].height = comp[c].bcy * 8;
+    }
+}
+
 int gj_geometry_init(struct gj_geometry* g, const struct gpujpeg_parameters* param,
                      const struct gpujpeg_image_parameters* pi)
 {

@@ -1,0 +1,159 @@
+/*
+ * gj_convert.cu -- generic pre-/post-processing pass (sm_100a): any supported pixel format in any of the colour spaces
+ * RGB / YCbCr BT.601 / YCbCr BT.601 full range / YCbCr BT.709 to and from the component planes of a YCbCr JPEG with any
+ * supported sampling.
+ *
+ * The two hot configurations never come here: RGB 444-u8-p012 runs the fused colour+DCT kernels of gj_dct.cu, and
+ * images that already hold the JPEG's components run the DCT straight on the raw image (k_fdct_samples).  Everything
+ * else -- a colour transform other than RGB <-> YCbCr-JPEG, or a pixel format whose sampling is not the JPEG's -- takes
+ * this extra pass over HBM, which restates the reference's generic per-pixel kernels:
+ *   encode: load the pixel's sample triple by the format's rule, colour transform, keep the sample of a component when
+ *           the pixel lies on that component's grid          [ref: src/gpujpeg_preprocessor.cu:50-64, 88-201]
+ *   decode: component samples at (x / dh, y / dv), colour transform, store by the format's rule
+ *                                                            [ref: src/gpujpeg_postprocessor.cu:55-76, 183-216;
+ *                                                                  src/gpujpeg_preprocessor_common.cuh:125-203]
+ * Colour transforms are the reference's 8-bit integer matrices [ref: src/gpujpeg_colorspace.h:52-101, 215-413];
+ * every YCbCr <-> YCbCr pair goes through RGB as it does there.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "gj_internal.h"
+
+namespace {
+
+struct ConvertParams {
+    /* raw image: sample (x, y) of component c at off + (y / rdv) * pitch + (x / rdh) * xs */
+    unsigned long long off[3], pitch[3];
+    int xs[3], rdh[3], rdv[3];
+    int raw_comps;          /* 1: grey */
+    int uyvy;               /* 422-u8-p1020: U is stored by even pixels, V by odd pixels */
+    /* component planes of the JPEG: sample (x, y) of component c at poff + y * ppitch + x; a pixel contributes to /
+     * reads from plane c at (x / pdh, y / pdv) */
+    unsigned long long poff[3];
+    int ppitch[3], pdh[3], pdv[3];
+    int jpeg_comps;
+    int width, height;
+    int cs;                 /* colour space of the raw image (enum gpujpeg_color_space) */
+};
+
+__constant__ int c_to_rgb[5][9] = {{0}, {0}, {298, 0, 409, 298, -100, -208, 298, 516, 0},
+                                   {256, 0, 359, 256, -88, -183, 256, 454, 0}, {298, 0, 459, 298, -55, -136, 298, 541, 0}};
+__constant__ int c_from_rgb[5][9] = {{0}, {0}, {66, 129, 25, -38, -74, 112, 112, -94, -18},
+                                     {77, 150, 29, -43, -85, 128, 128, -107, -21}, {47, 157, 16, -26, -87, 112, 112, -102, -10}};
+__constant__ int c_base[5][3] = {{0, 0, 0}, {0, 0, 0}, {16, 128, 128}, {0, 128, 128}, {16, 128, 128}};
+
+__device__ __forceinline__ int clamp8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+
+__device__ __forceinline__ void cs_to_rgb(int cs, int (&c)[3])
+{
+    if ( cs == GPUJPEG_RGB ) return;
+    const int r0 = (c[0] - c_base[cs][0]) * 256 / 255, r1 = (c[1] - c_base[cs][1]) * 256 / 255,
+              r2 = (c[2] - c_base[cs][2]) * 256 / 255;   // C division: truncates toward zero
+#pragma unroll
+    for ( int i = 0; i < 3; i++ )
+        c[i] = clamp8((c_to_rgb[cs][3 * i] * r0 + c_to_rgb[cs][3 * i + 1] * r1 + c_to_rgb[cs][3 * i + 2] * r2 + 128) >> 8);
+}
+__device__ __forceinline__ void cs_from_rgb(int cs, int (&c)[3])
+{
+    if ( cs == GPUJPEG_RGB ) return;
+    const int r0 = c[0] * 256 / 255, r1 = c[1] * 256 / 255, r2 = c[2] * 256 / 255;
+#pragma unroll
+    for ( int i = 0; i < 3; i++ )
+        c[i] = clamp8(((c_from_rgb[cs][3 * i] * r0 + c_from_rgb[cs][3 * i + 1] * r1 + c_from_rgb[cs][3 * i + 2] * r2 + 128) >> 8) +
+                      c_base[cs][i]);
+}
+__device__ __forceinline__ void cs_transform(int from, int to, int (&c)[3])
+{
+    if ( from == to || from == GPUJPEG_NONE || to == GPUJPEG_NONE ) return;
+    cs_to_rgb(from, c);
+    cs_from_rgb(to, c);
+}
+
+__global__ void __launch_bounds__(256)
+k_convert_in(const uint8_t* __restrict__ raw, uint8_t* __restrict__ planes, const __grid_constant__ ConvertParams p)
+{
+    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+    if ( x >= p.width ) return;
+    int c[3] = {0, 128, 128};
+    for ( int k = 0; k < p.raw_comps; k++ )
+        c[k] = raw[p.off[k] + (size_t)(y / p.rdv[k]) * p.pitch[k] + (size_t)(x / p.rdh[k]) * p.xs[k]];
+    if ( p.raw_comps == 3 ) cs_transform(p.cs, GPUJPEG_YCBCR_BT601_256LVLS, c);
+    for ( int k = 0; k < p.jpeg_comps; k++ )
+        if ( x % p.pdh[k] == 0 && y % p.pdv[k] == 0 )
+            planes[p.poff[k] + (size_t)(y / p.pdv[k]) * p.ppitch[k] + x / p.pdh[k]] = (uint8_t)c[k];
+}
+
+__global__ void __launch_bounds__(256)
+k_convert_out(const uint8_t* __restrict__ planes, uint8_t* __restrict__ raw, const __grid_constant__ ConvertParams p)
+{
+    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+    if ( x >= p.width ) return;
+    int c[3] = {0, 128, 128};
+    for ( int k = 0; k < p.jpeg_comps; k++ )
+        c[k] = planes[p.poff[k] + (size_t)(y / p.pdv[k]) * p.ppitch[k] + x / p.pdh[k]];
+    if ( p.jpeg_comps == 3 ) cs_transform(GPUJPEG_YCBCR_BT601_256LVLS, p.cs, c);
+    raw[p.off[0] + (size_t)y * p.pitch[0] + (size_t)x * p.xs[0]] = (uint8_t)c[0];
+    if ( p.raw_comps == 1 ) return;
+    if ( p.uyvy ) {
+        const int k = (x & 1) ? 2 : 1;
+        raw[p.off[k] + (size_t)y * p.pitch[k] + (size_t)(x / 2) * p.xs[k]] = (uint8_t)c[k];
+    }
+    else if ( x % p.rdh[1] == 0 && y % p.rdv[1] == 0 ) {
+        raw[p.off[1] + (size_t)(y / p.rdv[1]) * p.pitch[1] + (size_t)(x / p.rdh[1]) * p.xs[1]] = (uint8_t)c[1];
+        raw[p.off[2] + (size_t)(y / p.rdv[2]) * p.pitch[2] + (size_t)(x / p.rdh[2]) * p.xs[2]] = (uint8_t)c[2];
+    }
+}
+
+int fill_params(ConvertParams* p, const struct gj_raw_layout* raw, enum gpujpeg_pixel_format fmt, int color_space, int width,
+                int height, const struct gj_comp_geo* comp, int comp_count, int max_hs, int max_vs)
+{
+    memset(p, 0, sizeof *p);
+    if ( comp_count < 1 || comp_count > 3 || (raw->comp_count != 1 && raw->comp_count != 3) ) return -1;
+    if ( color_space < GPUJPEG_NONE || color_space > GPUJPEG_YCBCR_BT709 ) return -1;
+    p->raw_comps = raw->comp_count;
+    p->uyvy = fmt == GPUJPEG_422_U8_P1020;
+    for ( int k = 0; k < 3; k++ ) {
+        const int r = k < raw->comp_count ? k : 0;
+        p->off[k] = raw->comp[r].off;
+        p->pitch[k] = raw->comp[r].pitch;
+        p->xs[k] = raw->comp[r].xs;
+        p->rdh[k] = raw->sampling[0].horizontal / (raw->sampling[r].horizontal ? raw->sampling[r].horizontal : 1);
+        p->rdv[k] = raw->sampling[0].vertical / (raw->sampling[r].vertical ? raw->sampling[r].vertical : 1);
+        const int j = k < comp_count ? k : 0;
+        p->poff[k] = (unsigned long long)comp[j].blk_off * 64;
+        p->ppitch[k] = comp[j].bcx * 8;
+        p->pdh[k] = max_hs / comp[j].hs;
+        p->pdv[k] = max_vs / comp[j].vs;
+    }
+    p->jpeg_comps = comp_count;
+    p->width = width;
+    p->height = height;
+    p->cs = color_space;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int gj_launch_convert_in(const uint8_t* d_raw, const struct gj_raw_layout* raw, enum gpujpeg_pixel_format fmt,
+                                    int color_space, int width, int height, uint8_t* d_planes, size_t planes_size,
+                                    const struct gj_comp_geo* comp, int comp_count, int max_hs, int max_vs, gj_stream_t stream)
+{
+    ConvertParams p;
+    if ( fill_params(&p, raw, fmt, color_space, width, height, comp, comp_count, max_hs, max_vs) ) return -1;
+    /* samples outside the image are 0 [ref: src/gpujpeg_common.c:941-944] */
+    if ( cudaMemsetAsync(d_planes, 0, planes_size, stream) != cudaSuccess ) return -1;
+    k_convert_in<<<dim3((width + 255) / 256, height), 256, 0, stream>>>(d_raw, d_planes, p);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+extern "C" int gj_launch_convert_out(const uint8_t* d_planes, uint8_t* d_raw, const struct gj_raw_layout* raw,
+                                     enum gpujpeg_pixel_format fmt, int color_space, int width, int height,
+                                     const struct gj_comp_geo* comp, int comp_count, int max_hs, int max_vs, gj_stream_t stream)
+{
+    ConvertParams p;
+    if ( fill_params(&p, raw, fmt, color_space, width, height, comp, comp_count, max_hs, max_vs) ) return -1;
+    k_convert_out<<<dim3((width + 255) / 256, height), 256, 0, stream>>>(d_planes, d_raw, p);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}

@@ -36,7 +36,8 @@ struct gpujpeg_decoder {
     enum gpujpeg_pixel_format req_pixel_format;
     enum gpujpeg_color_space req_color_space;
     int idct_flavour;
-    int out_mode;                 /* GJ_OUT_RGB or GJ_OUT_SAMPLES: which K4 runs */
+    int out_mode;                 /* GJ_OUT_RGB, GJ_OUT_SAMPLES or GJ_OUT_GENERIC: which K4 runs */
+    uint8_t* d_planes; size_t d_planes_size;   /* component planes between the IDCT and the generic pass */
     struct gj_raw_layout raw;     /* where the samples go (GJ_OUT_SAMPLES) */
     struct gpujpeg_image_metadata metadata;
 
@@ -142,6 +143,7 @@ int gpujpeg_decoder_destroy(struct gpujpeg_decoder* d)
     gj_cuda_free(d->d_mk);
     gj_cuda_free_host(d->h_mk);
     gj_cuda_free(d->d_coef);
+    gj_cuda_free(d->d_planes);
     gj_cuda_free(d->d_raw);
     gj_cuda_free_host(d->h_raw);
     gj_timer_destroy(&d->t_to);
@@ -214,8 +216,10 @@ void gpujpeg_decoder_set_output_format(struct gpujpeg_decoder* decoder, enum gpu
  *   GJ_OUT_SAMPLES  the stream's own components, no colour transform: GPUJPEG_U8 for 1-component streams; for
  *                   3-component streams colour space GPUJPEG_YCBCR_JPEG (or GPUJPEG_NONE) with a pixel format of the
  *                   stream's sampling: 444-u8-p012, 444/422/420-u8-p0p1p2, 422-u8-p1020, or the special values
- *                   GPUJPEG_PIXFMT_NATIVE / _STD resolved as the reference does [ref: src/gpujpeg_reader.c:1507-1581] */
-enum { GJ_OUT_RGB = 1, GJ_OUT_SAMPLES = 2 };
+ *                   GPUJPEG_PIXFMT_NATIVE / _STD resolved as the reference does [ref: src/gpujpeg_reader.c:1507-1581]
+ *   GJ_OUT_GENERIC  any of those pixel formats in GPUJPEG_RGB / _YCBCR_BT601 / _YCBCR_JPEG / _YCBCR_BT709 whatever the stream's
+ *                   sampling: the IDCT writes component planes, one extra pass converts them (gj_convert.cu) */
+enum { GJ_OUT_RGB = 1, GJ_OUT_SAMPLES = 2, GJ_OUT_GENERIC = 3 };
 
 static int choose_output(const struct gpujpeg_decoder* d, const struct gj_stream* st, struct gpujpeg_image_parameters* pi)
 {
@@ -248,14 +252,9 @@ static int choose_output(const struct gpujpeg_decoder* d, const struct gj_stream
     }
     pi->pixel_format = pf;
     pi->color_space = cs;
-    if ( cs == GPUJPEG_RGB ) {
-        if ( pf == GPUJPEG_444_U8_P012 ) return GJ_OUT_RGB;
-        GJ_ERR("This build decodes to GPUJPEG_RGB as 444-u8-p012 only (%s requested).\n", gpujpeg_pixel_format_get_name(pf));
-        return 0;
-    }
-    if ( cs != st->color_space ) {
-        GJ_ERR("This build decodes to GPUJPEG_RGB or to the stream's own colour space (%s); %s would need another colour "
-               "transform.\n", gpujpeg_color_space_get_name(st->color_space), gpujpeg_color_space_get_name(cs));
+    if ( cs == GPUJPEG_RGB && pf == GPUJPEG_444_U8_P012 ) return GJ_OUT_RGB;
+    if ( cs != GPUJPEG_RGB && cs != GPUJPEG_YCBCR_BT601 && cs != GPUJPEG_YCBCR_BT601_256LVLS && cs != GPUJPEG_YCBCR_BT709 ) {
+        GJ_ERR("Colour space %s is not produced by this build.\n", gpujpeg_color_space_get_name(cs));
         return 0;
     }
     struct gj_raw_layout rl;
@@ -264,10 +263,12 @@ static int choose_output(const struct gpujpeg_decoder* d, const struct gj_stream
                pi->height);
         return 0;
     }
-    if ( rl.sampling[0].horizontal != lh || rl.sampling[0].vertical != lv ) {
-        GJ_ERR("This build keeps the stream's sampling (%dx%d luminance) when no colour transform is asked for; %s has "
-               "another one.\n", lh, lv, gpujpeg_pixel_format_get_name(pf));
-        return 0;
+    if ( cs != st->color_space || rl.sampling[0].horizontal != lh || rl.sampling[0].vertical != lv ) {
+        if ( (pi->width & 1) && rl.sampling[0].horizontal == 2 && pf != GPUJPEG_420_U8_P0P1P2 ) {
+            GJ_ERR("Odd widths are only produced without colour / sampling conversion for this pixel format.\n");
+            return 0;
+        }
+        return GJ_OUT_GENERIC;
     }
     return GJ_OUT_SAMPLES;
 }
@@ -279,6 +280,16 @@ static int launch_k4(struct gpujpeg_decoder* d, const int comp_tq[3], uint8_t* d
     if ( d->out_mode == GJ_OUT_SAMPLES )
         return gj_launch_idct_samples(d->d_coef, g->comp, g->comp_count, comp_tq, d_out, &d->raw, d->idct_flavour,
                                       coef_dequantized, &d->h_tab, d->stream);
+    if ( d->out_mode == GJ_OUT_GENERIC ) {
+        struct gj_raw_layout pl;
+        struct gj_comp_geo padded[GJ_MAX_COMP];
+        gj_planes_layout(&pl, padded, g->comp, g->comp_count);
+        if ( gj_launch_idct_samples(d->d_coef, padded, g->comp_count, comp_tq, d->d_planes, &pl, d->idct_flavour,
+                                    coef_dequantized, &d->h_tab, d->stream) )
+            return -1;
+        return gj_launch_convert_out(d->d_planes, d_out, &d->raw, d->param_image.pixel_format, d->param_image.color_space,
+                                     g->width, g->height, g->comp, g->comp_count, g->max_hs, g->max_vs, d->stream);
+    }
     if ( g->lay.simple )
         return gj_launch_idct_rgb444(d->d_coef, g->bcx, g->bcy, comp_tq, d_out, g->width, g->height, g->pitch, d->idct_flavour,
                                      coef_dequantized, &d->h_tab, d->stream);
@@ -362,7 +373,8 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     }
     d->out_mode = out_mode;
     d->param_image.color_space = pi.color_space;
-    if ( out_mode == GJ_OUT_SAMPLES && gj_raw_layout_init(&d->raw, &pi) ) return GPUJPEG_ERROR;
+    if ( out_mode != GJ_OUT_RGB && gj_raw_layout_init(&d->raw, &pi) ) return GPUJPEG_ERROR;
+    if ( out_mode == GJ_OUT_GENERIC && grow_dev((void**)&d->d_planes, &d->d_planes_size, d->geo.coef_count) ) return GPUJPEG_ERROR;
     const struct gj_geometry* g = &d->geo;
 
     /* ---- upload the file once, untouched; K0 builds the marker list on the device ---- */

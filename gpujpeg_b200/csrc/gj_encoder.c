@@ -28,7 +28,8 @@ struct gpujpeg_encoder {
     struct gpujpeg_image_parameters param_image;
     int initialised;
     struct gj_geometry geo;
-    int input_mode;                  /* GJ_IN_RGB or GJ_IN_SAMPLES: which K1 runs */
+    int input_mode;                  /* GJ_IN_RGB, GJ_IN_SAMPLES or GJ_IN_GENERIC: which K1 runs */
+    uint8_t* d_planes; size_t d_planes_size;   /* component planes between the generic pass and the DCT */
     struct gj_raw_layout raw;        /* where the samples live (GJ_IN_SAMPLES) */
     int quality;                               /* quality the tables were built for (-1 = none) */
     enum gpujpeg_header_type header_type;
@@ -141,6 +142,7 @@ int gpujpeg_encoder_destroy(struct gpujpeg_encoder* e)
     gj_cuda_free_host(e->h_info);
     gj_cuda_free(e->d_raw);
     gj_cuda_free(e->d_coef);
+    gj_cuda_free(e->d_planes);
     gj_cuda_free(e->d_nzmask);
     gj_cuda_free(e->d_tmp);
     gj_cuda_free(e->d_spill);
@@ -189,8 +191,11 @@ static int grow(void** p, size_t* have, size_t want)
  *                  the fused colour + FDCT kernels
  *   GJ_IN_SAMPLES  the image already holds the JPEG's components (colour space == internal colour space, or a single
  *                  component): GPUJPEG_U8, 444-u8-p012, 444/422/420-u8-p0p1p2, 422-u8-p1020; the JPEG takes the
- *                  format's own sampling [ref: src/gpujpeg_preprocessor.cu:296-311 "no transform" rule] */
-enum { GJ_IN_UNSUPPORTED = 0, GJ_IN_RGB = 1, GJ_IN_SAMPLES = 2 };
+ *                  format's own sampling [ref: src/gpujpeg_preprocessor.cu:296-311 "no transform" rule]
+ *   GJ_IN_GENERIC  any of those pixel formats in GPUJPEG_RGB / _YCBCR_BT601 / _YCBCR_BT601_256LVLS / _YCBCR_BT709 with any of
+ *                  the four samplings: one extra pass converts to the JPEG's component planes (gj_convert.cu), then
+ *                  the sample kernel runs on the planes */
+enum { GJ_IN_UNSUPPORTED = 0, GJ_IN_RGB = 1, GJ_IN_SAMPLES = 2, GJ_IN_GENERIC = 3 };
 
 static int params_supported(const struct gpujpeg_parameters* p, const struct gpujpeg_image_parameters* pi)
 {
@@ -238,20 +243,30 @@ static int params_supported(const struct gpujpeg_parameters* p, const struct gpu
                gpujpeg_pixel_format_get_name(pi->pixel_format), rl.comp_count, p->comp_count);
         return GJ_IN_UNSUPPORTED;
     }
-    if ( p->comp_count == 3 && pi->color_space != p->color_space_internal && pi->color_space != GPUJPEG_NONE ) {
-        GJ_ERR("This build converts GPUJPEG_RGB / 444-u8-p012 only; %s input in %s would need a colour transform to %s.\n",
-               gpujpeg_pixel_format_get_name(pi->pixel_format), gpujpeg_color_space_get_name(pi->color_space),
-               gpujpeg_color_space_get_name(p->color_space_internal));
-        return GJ_IN_UNSUPPORTED;
-    }
-    for ( int c = 0; c < p->comp_count; c++ ) {
+    int needs_pass = p->comp_count == 3 && pi->color_space != p->color_space_internal && pi->color_space != GPUJPEG_NONE;
+    for ( int c = 0; c < p->comp_count; c++ )
         if ( p->sampling_factor[c].horizontal != rl.sampling[c].horizontal ||
-             p->sampling_factor[c].vertical != rl.sampling[c].vertical ) {
-            GJ_ERR("This build keeps the sampling of the pixel format (%s is %s, the JPEG parameters ask for %s).\n",
-                   gpujpeg_pixel_format_get_name(pi->pixel_format), gpujpeg_subsampling_get_name(p->comp_count, rl.sampling),
+             p->sampling_factor[c].vertical != rl.sampling[c].vertical )
+            needs_pass = 1;
+    if ( needs_pass ) {
+        const int lh = p->sampling_factor[0].horizontal, lv = p->sampling_factor[0].vertical;
+        if ( p->comp_count != 3 || lh < 1 || lh > 2 || lv < 1 || lv > 2 || p->sampling_factor[1].horizontal != 1 ||
+             p->sampling_factor[1].vertical != 1 || p->sampling_factor[2].horizontal != 1 || p->sampling_factor[2].vertical != 1 ) {
+            GJ_ERR("This build encodes 4:4:4, 4:2:2, 4:2:0 and 4:4:0 only (got %s).\n",
                    gpujpeg_subsampling_get_name(p->comp_count, p->sampling_factor));
             return GJ_IN_UNSUPPORTED;
         }
+        if ( pi->color_space != GPUJPEG_NONE && pi->color_space != GPUJPEG_RGB && pi->color_space != GPUJPEG_YCBCR_BT601 &&
+             pi->color_space != GPUJPEG_YCBCR_BT601_256LVLS && pi->color_space != GPUJPEG_YCBCR_BT709 ) {
+            GJ_ERR("Colour space %s is not taken by this build.\n", gpujpeg_color_space_get_name(pi->color_space));
+            return GJ_IN_UNSUPPORTED;
+        }
+        if ( (pi->width & 1) && rl.sampling[0].horizontal == 2 && pi->pixel_format != GPUJPEG_420_U8_P0P1P2 ) {
+            /* the reference's generic kernel and its planar copy disagree on odd widths of 4:2:2 data */
+            GJ_ERR("Odd widths are only taken without colour / sampling conversion for this pixel format.\n");
+            return GJ_IN_UNSUPPORTED;
+        }
+        return GJ_IN_GENERIC;
     }
     return GJ_IN_SAMPLES;
 }
@@ -262,6 +277,15 @@ static int launch_k1(struct gpujpeg_encoder* e, const uint8_t* d_raw)
     const struct gj_geometry* g = &e->geo;
     if ( e->input_mode == GJ_IN_SAMPLES )
         return gj_launch_fdct_samples(d_raw, &e->raw, e->d_coef, e->d_nzmask, g->comp, g->comp_count, &e->h_tab, e->stream);
+    if ( e->input_mode == GJ_IN_GENERIC ) {
+        struct gj_raw_layout pl;
+        struct gj_comp_geo padded[GJ_MAX_COMP];
+        gj_planes_layout(&pl, padded, g->comp, g->comp_count);
+        if ( gj_launch_convert_in(d_raw, &e->raw, e->param_image.pixel_format, e->param_image.color_space, g->width, g->height,
+                                  e->d_planes, pl.size, g->comp, g->comp_count, g->max_hs, g->max_vs, e->stream) )
+            return -1;
+        return gj_launch_fdct_samples(e->d_planes, &pl, e->d_coef, e->d_nzmask, padded, g->comp_count, &e->h_tab, e->stream);
+    }
     if ( g->lay.simple )
         return gj_launch_fdct_rgb444(d_raw, g->width, g->height, g->pitch, e->d_coef, e->d_nzmask, g->bcx, g->bcy, &e->h_tab,
                                      e->stream);
@@ -296,7 +320,8 @@ static int encoder_init_image(struct gpujpeg_encoder* e, const struct gpujpeg_pa
 {
     gj_geometry_init(&e->geo, p, pi);
     e->input_mode = params_supported(p, pi);
-    if ( e->input_mode == GJ_IN_SAMPLES && gj_raw_layout_init(&e->raw, pi) ) return -1;
+    if ( e->input_mode != GJ_IN_RGB && gj_raw_layout_init(&e->raw, pi) ) return -1;
+    if ( e->input_mode == GJ_IN_GENERIC && grow((void**)&e->d_planes, &e->d_planes_size, e->geo.coef_count) ) return -1;
     const struct gj_geometry* g = &e->geo;
     size_t coef_bytes = g->coef_count * sizeof(int16_t);
     size_t tmp_bytes = (size_t)g->seg_count * g->slot_stride + 256;

@@ -291,6 +291,19 @@ int gj_launch_idct_samples(const int16_t* d_coef, const struct gj_comp_geo* comp
                            uint8_t* d_raw, const struct gj_raw_layout* raw, int idct_flavour, int coef_dequantized,
                            const struct gj_dev_dec_tables* h_tables, gj_stream_t stream);
 
+/* Generic pre-/post-processing pass (gj_convert.cu): raw image in any supported pixel format and colour space <-> the
+ * component planes of the YCbCr JPEG (plane c at byte comp[c].blk_off * 64, pitch comp[c].bcx * 8)
+ * [replaces the generic kernels of ref: src/gpujpeg_preprocessor.cu:163-201, src/gpujpeg_postprocessor.cu:183-216] */
+int gj_launch_convert_in(const uint8_t* d_raw, const struct gj_raw_layout* raw, enum gpujpeg_pixel_format fmt, int color_space,
+                         int width, int height, uint8_t* d_planes, size_t planes_size, const struct gj_comp_geo* comp,
+                         int comp_count, int max_hs, int max_vs, gj_stream_t stream);
+int gj_launch_convert_out(const uint8_t* d_planes, uint8_t* d_raw, const struct gj_raw_layout* raw, enum gpujpeg_pixel_format fmt,
+                          int color_space, int width, int height, const struct gj_comp_geo* comp, int comp_count, int max_hs,
+                          int max_vs, gj_stream_t stream);
+/* the planes above described as a raw layout, so that the sample kernels can run on them */
+void gj_planes_layout(struct gj_raw_layout* l, struct gj_comp_geo padded[GJ_MAX_COMP], const struct gj_comp_geo* comp,
+                      int comp_count);
+
 /* debug/test helper: device coefficient buffer (zig-zag) -> host natural order, block-major */
 int gj_coef_to_host_natural(const int16_t* d_coef, size_t count, int16_t* h_out, gj_stream_t stream);
 

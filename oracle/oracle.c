@@ -1139,6 +1139,106 @@ size_t orc_encode_ycc(const uint8_t* raw, int w, int h, int pad, int fmt, int qu
 }
 
 /* ------------------------------------------------------------------------------------------- */
+/* generic pre-/post-processing: any of the pixel formats above in any of the colour spaces RGB, YCbCr BT.601,
+ * YCbCr BT.601 full range ("JPEG"), YCbCr BT.709, with any JPEG sampling -- the reference's per-pixel kernels
+ * [ref: src/gpujpeg_preprocessor.cu:163-201, src/gpujpeg_postprocessor.cu:183-216, src/gpujpeg_colorspace.h:52-427] */
+
+enum { CS_NONE = 0, CS_RGB = 1, CS_601 = 2, CS_601_256 = 3, CS_709 = 4 };
+
+static const int k_to_rgb[5][9] = {{0}, {0}, {298, 0, 409, 298, -100, -208, 298, 516, 0},
+                                   {256, 0, 359, 256, -88, -183, 256, 454, 0}, {298, 0, 459, 298, -55, -136, 298, 541, 0}};
+static const int k_from_rgb[5][9] = {{0}, {0}, {66, 129, 25, -38, -74, 112, 112, -94, -18},
+                                     {77, 150, 29, -43, -85, 128, 128, -107, -21}, {47, 157, 16, -26, -87, 112, 112, -102, -10}};
+static const int k_base[5][3] = {{0, 0, 0}, {0, 0, 0}, {16, 128, 128}, {0, 128, 128}, {16, 128, 128}};
+
+/* [ref: src/gpujpeg_colorspace.h:86-101] */
+static void cs_to_rgb(int cs, int c[3])
+{
+    if ( cs == CS_RGB ) return;
+    const int* m = k_to_rgb[cs];
+    int r[3];
+    for ( int i = 0; i < 3; i++ )
+        r[i] = (c[i] - k_base[cs][i]) * 256 / 255;   /* C division: truncates toward zero */
+    for ( int i = 0; i < 3; i++ )
+        c[i] = clamp8((m[3 * i] * r[0] + m[3 * i + 1] * r[1] + m[3 * i + 2] * r[2] + 128) >> 8);
+}
+/* [ref: src/gpujpeg_colorspace.h:64-79] */
+static void cs_from_rgb(int cs, int c[3])
+{
+    if ( cs == CS_RGB ) return;
+    const int* m = k_from_rgb[cs];
+    int r[3];
+    for ( int i = 0; i < 3; i++ )
+        r[i] = c[i] * 256 / 255;
+    for ( int i = 0; i < 3; i++ )
+        c[i] = clamp8(((m[3 * i] * r[0] + m[3 * i + 1] * r[1] + m[3 * i + 2] * r[2] + 128) >> 8) + k_base[cs][i]);
+}
+/* every YCbCr <-> YCbCr pair goes through RGB [ref: src/gpujpeg_colorspace.h:340-413] */
+static void cs_transform(int from, int to, int c[3])
+{
+    if ( from == to || from == CS_NONE || to == CS_NONE ) return;
+    cs_to_rgb(from, c);
+    cs_from_rgb(to, c);
+}
+
+/* the sample triple the reference loads for pixel (x, y) [ref: src/gpujpeg_preprocessor.cu:88-160] */
+static void raw_load_pixel(const uint8_t* raw, int fmt, const struct rawcomp rc[3], const int fhs[4], const int fvs[4], int x,
+                           int y, int c[3])
+{
+    if ( fmt == 0 ) {
+        c[0] = raw[rc[0].off + (size_t)y * rc[0].pitch + x];
+        c[1] = c[2] = 128;
+        return;
+    }
+    for ( int k = 0; k < 3; k++ ) {
+        int dh = fhs[0] / fhs[k], dv = fvs[0] / fvs[k];   /* luminance carries the format's maximum */
+        c[k] = raw[rc[k].off + (size_t)(y / dv) * rc[k].pitch + (size_t)(x / dh) * rc[k].xs];
+    }
+}
+
+size_t orc_encode_any(const uint8_t* raw, int w, int h, int fmt, int cs, int quality, int rst, int interleaved, int lhs,
+                      int lvs, int threads, uint8_t* out)
+{
+    if ( w <= 0 || h <= 0 || w > 65535 || h > 65535 || rst < 0 || rst > 65535 ) return 0;
+    struct rawcomp rc[3];
+    int fhs[4], fvs[4];
+    size_t size;
+    const int fcomps = raw_layout(fmt, w, h, 0, rc, fhs, fvs, &size);
+    if ( !fcomps || lhs < 1 || lhs > 2 || lvs < 1 || lvs > 2 ) return 0;
+    enc_tables_init();
+#ifdef _OPENMP
+    int saved_threads = omp_get_max_threads();
+    omp_set_num_threads(threads > 1 ? threads : 1);
+#else
+    (void)threads;
+#endif
+    const int comps = 3;
+    const int hs[4] = {lhs, 1, 1, 0}, vs[4] = {lvs, 1, 1, 0};
+    struct ogeo g[4];
+    int max_hs, max_vs;
+    size_t total = ogeo_init(g, comps, hs, vs, w, h, interleaved, &max_hs, &max_vs);
+    uint8_t* planes = (uint8_t*)scratch(0, total);
+    int16_t* coef = (int16_t*)scratch(1, total * sizeof(int16_t));
+    memset(planes, 0, total);
+    for ( int y = 0; y < h; y++ )
+        for ( int x = 0; x < w; x++ ) {
+            int c[3];
+            raw_load_pixel(raw, fmt, rc, fhs, fvs, x, y, c);
+            cs_transform(cs, CS_601_256, c);
+            for ( int k = 0; k < 3; k++ ) {
+                int dh = max_hs / g[k].hs, dv = max_vs / g[k].vs;
+                if ( x % dh || y % dv ) continue;
+                planes[g[k].off + (size_t)(y / dv) * g[k].dw + x / dh] = (uint8_t)c[k];
+            }
+        }
+    size_t n = encode_from_planes(planes, g, comps, hs, vs, w, h, quality, rst, interleaved, out, coef);
+#ifdef _OPENMP
+    omp_set_num_threads(saved_threads);
+#endif
+    return n;
+}
+
+/* ------------------------------------------------------------------------------------------- */
 /* Huffman decoding of one restart segment (JPEG Annex F.2.2; behaviour on valid streams equals
  * [ref: src/gpujpeg_huffman_cpu_decoder.c:75-303])                                              */
 
@@ -1548,6 +1648,59 @@ int orc_decode_ycc(const uint8_t* jpeg, size_t size, int idct_flavour, int threa
             for ( int y = 0; y < g[c].h; y++ )
                 for ( int x = 0; x < g[c].w; x++ )
                     raw[rc[c].off + (size_t)y * rc[c].pitch + (size_t)x * rc[c].xs] = planes[g[c].off + (size_t)y * g[c].dw + x];
+    }
+#ifdef _OPENMP
+    omp_set_num_threads(saved_threads);
+#endif
+    return planes ? 0 : -1;
+}
+
+/* Decode to any pixel format / colour space: per pixel, the component samples at (x / dh, y / dv), colour transform
+ * from the JPEG's YCbCr, store by the format's rule [ref: src/gpujpeg_postprocessor.cu:183-216,
+ * src/gpujpeg_preprocessor_common.cuh:125-203].  Even widths only for the formats that share chroma horizontally. */
+int orc_decode_any(const uint8_t* jpeg, size_t size, int idct_flavour, int threads, int fmt, int cs, uint8_t* raw)
+{
+    struct parsed P;
+    if ( parse_stream(jpeg, size, &P) != 0 ) return -1;
+    struct rawcomp rc[3];
+    int fhs[4], fvs[4];
+    size_t rsize;
+    const int fcomps = raw_layout(fmt, P.w, P.h, 0, rc, fhs, fvs, &rsize);
+    if ( !fcomps || (fcomps == 1 && P.comps != 1) ) return -1;
+#ifdef _OPENMP
+    int saved_threads = omp_get_max_threads();
+    omp_set_num_threads(threads > 1 ? threads : 1);
+#else
+    (void)threads;
+#endif
+    struct ogeo g[4];
+    int max_hs, max_vs;
+    uint8_t* planes = decode_to_planes(&P, jpeg, idct_flavour, g, &max_hs, &max_vs, NULL, 1);
+    if ( planes ) {
+        for ( int y = 0; y < P.h; y++ )
+            for ( int x = 0; x < P.w; x++ ) {
+                int c[3] = {0, 128, 128};
+                for ( int k = 0; k < P.comps; k++ ) {
+                    int dh = max_hs / g[k].hs, dv = max_vs / g[k].vs;
+                    c[k] = planes[g[k].off + (size_t)(y / dv) * g[k].dw + x / dh];
+                }
+                if ( P.comps == 3 ) cs_transform(CS_601_256, cs, c);
+                if ( fcomps == 1 ) {
+                    raw[rc[0].off + (size_t)y * rc[0].pitch + x] = (uint8_t)c[0];
+                    continue;
+                }
+                raw[rc[0].off + (size_t)y * rc[0].pitch + (size_t)x * rc[0].xs] = (uint8_t)c[0];
+                const int dh = fhs[0], dv = fvs[0];   /* chroma of the format: every dh-th pixel of every dv-th row */
+                if ( fmt == 3 ) {
+                    /* U from even pixels, V from odd pixels [ref: src/gpujpeg_preprocessor_common.cuh:179-189] */
+                    if ( x % 2 == 0 ) raw[rc[1].off + (size_t)y * rc[1].pitch + (size_t)(x / 2) * rc[1].xs] = (uint8_t)c[1];
+                    else raw[rc[2].off + (size_t)y * rc[2].pitch + (size_t)(x / 2) * rc[2].xs] = (uint8_t)c[2];
+                }
+                else if ( x % dh == 0 && y % dv == 0 ) {
+                    raw[rc[1].off + (size_t)(y / dv) * rc[1].pitch + (size_t)(x / dh) * rc[1].xs] = (uint8_t)c[1];
+                    raw[rc[2].off + (size_t)(y / dv) * rc[2].pitch + (size_t)(x / dh) * rc[2].xs] = (uint8_t)c[2];
+                }
+            }
     }
 #ifdef _OPENMP
     omp_set_num_threads(saved_threads);

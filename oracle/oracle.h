@@ -84,6 +84,12 @@ size_t orc_raw_size(int fmt, int w, int h, int pad);
 size_t orc_encode_ycc(const uint8_t* raw, int w, int h, int pad, int fmt, int quality, int rst, int interleaved,
                       int threads, uint8_t* out, int16_t* coef_out);
 int orc_decode_ycc(const uint8_t* jpeg, size_t size, int idct_flavour, int threads, int fmt, int pad, uint8_t* raw);
+/* Generic path: any of those pixel formats in colour space cs (the reference's enum gpujpeg_color_space value: 0 none,
+ * 1 RGB, 2 BT.601, 3 BT.601 full range = JPEG, 4 BT.709), transformed per pixel to / from the JPEG's YCbCr, with any
+ * luminance sampling lhs x lvs in {1,2}.  Widths must be even for the formats that share chroma horizontally. */
+size_t orc_encode_any(const uint8_t* raw, int w, int h, int fmt, int cs, int quality, int rst, int interleaved, int lhs,
+                      int lvs, int threads, uint8_t* out);
+int orc_decode_any(const uint8_t* jpeg, size_t size, int idct_flavour, int threads, int fmt, int cs, uint8_t* raw);
 /* Decode a baseline JPEG produced by this codec family (3 comp, any of the above samplings, or 1 comp) to RGB/gray u8.
  * Returns 0 on success; fills w,h,comps.  rgb may be NULL to probe. coef_out optional. */
 int orc_decode_rgb(const uint8_t* jpeg, size_t size, int idct_flavour, int threads, uint8_t* rgb,

@@ -52,6 +52,9 @@ lib.orc_raw_size.restype = C.c_size_t
 lib.orc_encode_ycc.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_void_p]
 lib.orc_encode_ycc.restype = C.c_size_t
 lib.orc_decode_ycc.argtypes = [_u8p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]
+lib.orc_encode_any.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]
+lib.orc_encode_any.restype = C.c_size_t
+lib.orc_decode_any.argtypes = [_u8p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]
 lib.orc_decode_rgb.argtypes = [_u8p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int),
                                C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
 lib.orc_probe.argtypes = [_u8p, C.c_size_t, C.POINTER(StreamInfo)]
@@ -204,6 +207,26 @@ class huffman_override:
 
     def __exit__(self, *exc):
         lib.orc_set_huffman_override(0, 0, None, None, 0)
+
+
+CS_NONE, CS_RGB, CS_601, CS_JPEG, CS_709 = range(5)
+
+
+def encode_any(raw, w, h, fmt, cs, quality=75, rst=8, interleaved=0, sampling=(1, 1), threads=1):
+    """generic path of the reference: pixel format x colour space x JPEG sampling, per-pixel colour transform"""
+    out = np.empty(4096 + w * h * 6 + 4096, np.uint8)
+    n = lib.orc_encode_any(np.ascontiguousarray(raw).reshape(-1), w, h, fmt, cs, quality, rst, interleaved, sampling[0],
+                           sampling[1], threads, out)
+    assert n > 0
+    return out[:n].copy()
+
+
+def decode_any(jpeg, fmt, cs, flavour=IDCT_INT, threads=1):
+    jpeg = np.ascontiguousarray(jpeg, np.uint8)
+    info = probe(jpeg)
+    raw = np.zeros(lib.orc_raw_size(fmt, info.width, info.height, 0), np.uint8)
+    assert lib.orc_decode_any(jpeg, jpeg.size, flavour, threads, fmt, cs, raw) == 0
+    return raw
 
 
 def stream_sampling(jpeg):

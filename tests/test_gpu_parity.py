@@ -217,6 +217,35 @@ def test_ycbcr_stream_decodes_to_rgb_by_default(gj, enc, dec):
     assert np.array_equal(dec.decode(jpeg), o.decode(jpeg))
 
 
+# ---- generic path: colour spaces other than RGB / JPEG-YCbCr, or a JPEG sampling other than the pixel format's ----
+GENERIC = [  # fmt, colour space, JPEG subsampling name (None = the format's), w, h
+    (o.FMT_444_P012, o.CS_709, None, 320, 200), (o.FMT_444_P012, o.CS_601, "4:2:0", 322, 201),
+    (o.FMT_444_P0P1P2, o.CS_RGB, "4:2:2", 320, 200), (o.FMT_422_P1020, o.CS_709, None, 320, 200),
+    (o.FMT_422_P1020, o.CS_601, "4:4:4", 64, 48), (o.FMT_422_P0P1P2, o.CS_RGB, None, 320, 200),
+    (o.FMT_420_P0P1P2, o.CS_601, None, 320, 200), (o.FMT_420_P0P1P2, o.CS_JPEG, "4:4:4", 161, 97),
+    (o.FMT_444_P012, o.CS_JPEG, "4:2:0", 1919, 1079),
+]
+SUB = {None: None, "4:4:4": (1, 1), "4:2:2": (2, 1), "4:2:0": (2, 2)}
+
+
+@pytest.mark.parametrize("il", [0, 1])
+@pytest.mark.parametrize("fmt,cs,sub,w,h", GENERIC)
+def test_generic_colour_spaces_and_resampling(gj, enc, fmt, cs, sub, w, h, il):
+    raw = o.gen_raw(fmt, w, h)
+    samp = SUB[sub] or o.FMT_SAMPLING[fmt]
+    want = o.encode_any(raw, w, h, fmt, cs, 85, 6, il, samp, threads=4)
+    got = enc.encode_samples(raw, w, h, fmt, 85, 6, il, color_space=cs, subsampling=sub)
+    assert got.size == want.size and np.array_equal(got, want), "JPEG bytes differ from the oracle"
+    d = gj.Decoder()
+    try:
+        d.set_output_format(cs, fmt)
+        out, pi = d.decode_samples(want)
+        assert pi.pixel_format == fmt and pi.color_space == cs
+        assert np.array_equal(out, o.decode_any(want, fmt, cs, threads=4)), "decoded image differs from the oracle"
+    finally:
+        d.close()
+
+
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
 
 

@@ -110,3 +110,32 @@ def test_reference_gpu_raw_formats(tmp_path, w, h, q, rst, fmt, il):
     out, _ = d.decode_samples(ref)
     assert np.array_equal(out, pix), "product decode != reference GPU decoder"
     d.close()
+
+
+@pytest.mark.skipif(not os.path.exists(SO), reason="oracle/_ref/libgpujpeg_refgpu.so not built")
+@pytest.mark.parametrize("il", [0, 1])
+@pytest.mark.parametrize("fmt,cs,w,h", [(1, 4, 640, 360), (1, 2, 322, 201), (3, 4, 640, 360), (3, 1, 320, 200), (2, 1, 640, 360),
+                                        (4, 2, 640, 360), (5, 4, 640, 360), (5, 1, 322, 200)])
+def test_reference_gpu_colour_spaces(tmp_path, fmt, cs, w, h, il):
+    """input in RGB / BT.601 / BT.709 in every pixel format (colour transform to the JPEG's YCbCr, the JPEG takes the
+    format's sampling): reference GPU encoder bytes == oracle == product, and the reference GPU decoder asked for the
+    same format and colour space == float flavour of oracle and product"""
+    raw = o.gen_raw(fmt, w, h)
+    src, path, dst = tmp_path / "in.raw", tmp_path / "ref.jpg", tmp_path / "out.raw"
+    raw.tofile(src)
+    run_ref("encode_raw", src, fmt, cs, w, h, 85, 6, il, path)
+    ref = np.fromfile(path, np.uint8)
+    want = o.encode_any(raw, w, h, fmt, cs, 85, 6, il, o.FMT_SAMPLING[fmt], threads=4)
+    assert ref.size == want.size and np.array_equal(ref, want), "oracle restatement != reference GPU library output"
+    import gpujpeg_b200 as g
+    e = g.Encoder()
+    assert np.array_equal(e.encode_samples(raw, w, h, fmt, 85, 6, il, color_space=cs), ref), "product != reference GPU library"
+    e.close()
+    run_ref("decode_fmt", path, cs, fmt, dst)
+    pix = np.fromfile(dst, np.uint8)
+    assert np.array_equal(pix, o.decode_any(ref, fmt, cs, o.IDCT_FLOAT_GPUREF, threads=4)), "oracle != reference GPU decoder"
+    d = g.Decoder(idct="float_gpuref")
+    d.set_output_format(cs, fmt)
+    out, _ = d.decode_samples(ref)
+    assert np.array_equal(out, pix), "product decode != reference GPU decoder"
+    d.close()
