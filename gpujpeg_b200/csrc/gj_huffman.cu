@@ -337,6 +337,233 @@ k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzm
     }
 }
 
+/* ------------------------------------------------------------------------------------------- */
+/* k_huff_encode_packed: the same coder for SHORT segments (at most HP_MAXBLK blocks: every RESTART_AUTO setting of
+ * the reference).  With one lane per block and one warp per segment a 36-block segment costs two warp rounds, the
+ * second one with 4 of 32 lanes busy -- and building the blocks' bit strings, the divergent part of the kernel, does
+ * not depend on the segment at all.  So a CTA takes HE_WARPS consecutive segments and splits the work differently:
+ *   phase A  all blocks of the CTA's segments, densely packed onto the threads (288 blocks = 9 full warp rounds
+ *            instead of 16 half-empty ones): each thread builds its block's bit string in shared memory;
+ *   phase B  one warp per segment: prefix sum over the string lengths, placement into the stream buffer, byte
+ *            stuffing -- steps 2-4 of k_huff_encode, unchanged. */
+constexpr int HP_MAXBLK = 40;   // blocks per segment the packed kernel takes
+constexpr int HP_THREADS_MAX = HE_WARPS * HP_MAXBLK;   // one thread per block of the CTA's segments (rounded to warps)
+/* the per-thread coefficient heads (phase A) live in the stream buffers (phase B): 8 x 512 words >= 256 x 12 words */
+static_assert(HE_WARPS * HE_WORDS >= HP_THREADS_MAX * HE_HEAD, "heads must fit into the stream buffers");
+constexpr int HP_SMEM = (2 * 256 + 2 * 16 + HE_WARPS * HE_WORDS + HE_WARPS * HP_MAXBLK * HE_PRIV + HE_WARPS * HP_MAXBLK) * 4;
+
+__global__ void __launch_bounds__(HP_THREADS_MAX)
+k_huff_encode_packed(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzmask,
+                     const __grid_constant__ gj_scan_layout lay, int seg_mcu, int seg_count, uint8_t* __restrict__ tmp,
+                     size_t slot_stride, uint32_t* __restrict__ seg_bytes, uint32_t* __restrict__ spill_all,
+                     const gj_dev_enc_tables* __restrict__ tables)
+{
+    extern __shared__ __align__(16) uint32_t he_smem[];
+    uint32_t (*s_ac)[256] = reinterpret_cast<uint32_t (*)[256]>(he_smem);
+    uint32_t (*s_dc)[16] = reinterpret_cast<uint32_t (*)[16]>(he_smem + 512);
+    uint32_t* s_buf = he_smem + 512 + 32;
+    uint32_t* s_priv = s_buf + HE_WARPS * HE_WORDS;
+    uint32_t* s_head = s_buf;   // phase A only; 16-byte aligned: all region sizes in front are multiples of 4 words
+    uint32_t* s_len = s_priv + HE_WARPS * HP_MAXBLK * HE_PRIV;
+
+    for ( int i = threadIdx.x; i < 512; i += blockDim.x )
+        s_ac[i >> 8][i & 255] = tables->lut[i >> 8].ac[i & 255];
+    if ( threadIdx.x < 32 ) s_dc[threadIdx.x >> 4][threadIdx.x & 15] = tables->lut[threadIdx.x >> 4].dc[threadIdx.x & 15];
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g0 = blockIdx.x * HE_WARPS;
+    const int segblk = seg_mcu * lay.bpm;           // blocks of a full segment (<= HP_MAXBLK)
+
+    /* ---- phase A: one thread per block ---- */
+    {
+        uint32_t* head = s_head + threadIdx.x * HE_HEAD;
+        const int16_t* head16 = reinterpret_cast<const int16_t*>(head);
+        for ( int lb = threadIdx.x; lb < HE_WARPS * segblk; lb += blockDim.x ) {
+            const int sl = lb / segblk, j = lb - sl * segblk;
+            const int g = g0 + sl;
+            if ( g >= seg_count ) break;
+            const int scan = scan_of_segment(lay, g), s = g - lay.scan_seg_begin[scan];
+            const int first_mcu = s * seg_mcu;
+            const int nblocks = min(seg_mcu, lay.scan_mcus[scan] - first_mcu) * lay.bpm;
+            if ( j >= nblocks ) continue;   // the last segment of a scan may be shorter
+            size_t bi;
+            int comp, pd;
+            segment_block(lay, scan, first_mcu, j, bi, comp, pd);
+            const int tbl = comp == 0 ? 0 : 1;
+            const int16_t* blk = coef + bi * 64;
+            const uint64_t nz = __ldg(nzmask + bi);
+            const uint4 ha = __ldg(reinterpret_cast<const uint4*>(blk)), hb = __ldg(reinterpret_cast<const uint4*>(blk) + 1);
+            /* DC predictor: previous block of the same component inside the segment, 0 at its start
+             * [ref: src/gpujpeg_huffman_cpu_encoder.c:147-148, 361-364] */
+            int pred = 0;
+            if ( j >= pd ) {
+                size_t bp;
+                int cp, pp;
+                segment_block(lay, scan, first_mcu, j - pd, bp, cp, pp);
+                pred = __ldg(coef + bp * 64);
+            }
+            reinterpret_cast<uint4*>(head)[0] = ha;   // only this thread reads its head
+            reinterpret_cast<uint4*>(head)[1] = hb;
+            const int dc = (int)(short)(ha.x & 0xFFFFu);
+            uint32_t* priv = s_priv + lb * HE_PRIV;
+            uint32_t* spill = spill_all + ((size_t)g * HP_MAXBLK + j) * HE_SPILL;
+            uint64_t acc = 0;
+            int nb = 0, wi = 0;
+#define GJ_PUT(bits_, len_)                                        \
+    do {                                                           \
+        acc = (acc << (len_)) | (uint64_t)(bits_);                 \
+        nb += (len_);                                              \
+        if ( nb >= 32 ) {                                          \
+            const uint32_t w_ = (uint32_t)(acc >> (nb - 32));      \
+            if ( wi < HE_PRIV ) priv[wi] = w_;                     \
+            else spill[wi - HE_PRIV] = w_;                         \
+            wi++;                                                  \
+            nb -= 32;                                              \
+        }                                                          \
+    } while ( 0 )
+            const int diff = dc - pred;
+            const int dcat = gj_category(diff);
+            const uint32_t de = s_dc[tbl][dcat];
+            GJ_PUT(((de >> 5) << dcat) | (dcat ? gj_value_bits(diff, dcat) : 0u), (int)(de & 31u) + dcat);
+            uint32_t mlo = (uint32_t)nz & ~1u, mhi = (uint32_t)(nz >> 32);
+            int last = 0;
+            const uint32_t zrl = s_ac[tbl][0xF0];
+            while ( mlo | mhi ) {
+                int k;
+                if ( mlo ) { k = __ffs((int)mlo) - 1; mlo &= mlo - 1; }
+                else { k = 32 + __ffs((int)mhi) - 1; mhi &= mhi - 1; }
+                int run = k - last - 1;
+                last = k;
+                const int v = k < 16 ? (int)head16[k] : (int)__ldg(blk + k);
+                const int size = gj_category(v);
+                while ( run > 15 ) {
+                    GJ_PUT(zrl >> 5, (int)(zrl & 31u));
+                    run -= 16;
+                }
+                const uint32_t e = s_ac[tbl][(run << 4) | size];
+                GJ_PUT(((e >> 5) << size) | gj_value_bits(v, size), (int)(e & 31u) + size);
+            }
+            if ( last < 63 ) {
+                const uint32_t e = s_ac[tbl][0];
+                GJ_PUT(e >> 5, (int)(e & 31u));
+            }
+#undef GJ_PUT
+            if ( nb ) {   // left-aligned tail, low bits zero
+                const uint32_t w_ = (uint32_t)(acc << (32 - nb));
+                if ( wi < HE_PRIV ) priv[wi] = w_;
+                else spill[wi - HE_PRIV] = w_;
+            }
+            s_len[lb] = (uint32_t)(32 * wi + nb);
+        }
+    }
+    __syncthreads();
+
+    /* ---- phase B: one warp per segment ---- */
+    const int g = g0 + warp;
+    if ( warp >= HE_WARPS || g >= seg_count ) return;
+    const int scan = scan_of_segment(lay, g), s = g - lay.scan_seg_begin[scan];
+    const int nblocks = min(seg_mcu, lay.scan_mcus[scan] - s * seg_mcu) * lay.bpm;
+    uint32_t* buf = s_buf + warp * HE_WORDS;
+    uint8_t* out = tmp + (size_t)g * slot_stride;
+    uint32_t out_pos = 0;
+    int carry = 0;  // bits already sitting in buf[0] (always < 32 between rounds)
+    for ( int i = lane; i < HE_WORDS; i += 32 )
+        buf[i] = 0;
+    __syncwarp();
+    /* place one block's string at bit `mypos` of the stream buffer (interior words plain stores, edges atomicOr) */
+    auto place = [&](const uint32_t* priv, const uint32_t* spill, int mypos, int len) {
+        const int nw = (len + 31) >> 5;
+        const int d0 = mypos >> 5, sh = mypos & 31;
+        const int endbit = mypos + len;
+        uint32_t prev = 0;
+        for ( int q = 0; q <= nw; q++ ) {
+            const uint32_t w = q < nw ? (q < HE_PRIV ? priv[q] : spill[q - HE_PRIV]) : 0u;
+            const uint32_t o = sh ? (prev | (w >> sh)) : w;
+            prev = sh ? (w << (32 - sh)) : 0u;
+            const int d = d0 + q;
+            if ( 32 * d >= endbit ) break;              // nothing of this block reaches word d
+            if ( 32 * d >= mypos && 32 * d + 32 <= endbit ) buf[d] = o;   // word lies inside this block
+            else atomicOr(&buf[d], o);                                    // shared with a neighbour
+        }
+    };
+    /* fast path: the whole segment (<= 40 blocks: lane L takes blocks L and L + 32) fits into the stream buffer --
+     * one prefix sum, one placement, one flush */
+    {
+        const int j0 = lane, j1 = lane + 32;
+        const int len0 = j0 < nblocks ? (int)s_len[warp * segblk + j0] : 0;
+        const int len1 = j1 < nblocks ? (int)s_len[warp * segblk + j1] : 0;
+        const int incl0 = warp_incl_scan(len0, lane);
+        const int total0 = __shfl_sync(FULL, incl0, 31);
+        const int incl1 = warp_incl_scan(len1, lane);
+        const int total = total0 + __shfl_sync(FULL, incl1, 31);
+        if ( total <= HE_CAP_BITS ) {
+            if ( len0 > 0 )
+                place(s_priv + (warp * segblk + j0) * HE_PRIV, spill_all + ((size_t)g * HP_MAXBLK + j0) * HE_SPILL, incl0 - len0, len0);
+            if ( len1 > 0 )
+                place(s_priv + (warp * segblk + j1) * HE_PRIV, spill_all + ((size_t)g * HP_MAXBLK + j1) * HE_SPILL,
+                      total0 + incl1 - len1, len1);
+            __syncwarp();
+            const int nwords = total >> 5;
+            out_pos = flush_words(buf, nwords, out, out_pos, lane);
+            __syncwarp();
+            carry = total & 31;
+            if ( lane == 0 ) buf[0] = buf[nwords];   // the trailing partial word, finished below
+            __syncwarp();
+        }
+        else {
+            /* dense content: stream the segment through the buffer in rounds, as k_huff_encode does */
+            for ( int base = 0; base < nblocks; base += 32 ) {
+                const int j = base + lane;
+                const bool active = j < nblocks;
+                const int len = active ? (int)s_len[warp * segblk + j] : 0;
+                const uint32_t* priv = s_priv + (warp * segblk + (active ? j : 0)) * HE_PRIV;
+                const uint32_t* spill = spill_all + ((size_t)g * HP_MAXBLK + (active ? j : 0)) * HE_SPILL;
+                const int incl = warp_incl_scan(len, lane);
+                const int excl = incl - len;
+                int lane0 = 0;
+                while ( lane0 < 32 ) {
+                    const int rel0 = __shfl_sync(FULL, excl, lane0);
+                    const int mypos = carry + (excl - rel0);
+                    const bool fits = lane >= lane0 && mypos + len <= HE_CAP_BITS;
+                    const int nfit = __popc(__ballot_sync(FULL, fits));   // fits is monotone in lane
+                    if ( nfit == 0 ) break;  // cannot happen (a block is < 2 Kbit, the buffer 16 Kbit); never spin
+                    const bool mine = lane >= lane0 && lane < lane0 + nfit;
+                    if ( mine && len > 0 ) place(priv, spill, mypos, len);
+                    __syncwarp();
+                    const int lastl = lane0 + nfit - 1;
+                    const int newbits = carry + (__shfl_sync(FULL, incl, lastl) - rel0);
+                    const int nwords = newbits >> 5;
+                    out_pos = flush_words(buf, nwords, out, out_pos, lane);
+                    __syncwarp();
+                    const uint32_t tail = buf[nwords];
+                    __syncwarp();
+                    for ( int i = lane; i <= nwords; i += 32 )
+                        buf[i] = 0;
+                    __syncwarp();
+                    if ( lane == 0 ) buf[0] = tail;
+                    __syncwarp();
+                    carry = newbits & 31;
+                    lane0 += nfit;
+                }
+            }
+        }
+    }
+    /* segment end: pad with 1-bits to a byte boundary [ref: src/gpujpeg_huffman_cpu_encoder.c:115-128] */
+    if ( lane == 0 ) {
+        uint32_t w = buf[0];
+        const int nbytes = (carry + 7) >> 3;
+        if ( carry & 7 ) w |= ((1u << (8 - (carry & 7))) - 1u) << (32 - nbytes * 8);
+        uint8_t* o = out + out_pos;
+        for ( int q = 0; q < nbytes; q++ ) {
+            const uint8_t b = (uint8_t)(w >> (24 - 8 * q));
+            *o++ = b;
+            if ( b == 0xFF ) *o++ = 0;
+        }
+        seg_bytes[g] = (uint32_t)(o - out);
+    }
+}
+
 /* exclusive scan over segment sizes -> byte offsets in the finished stream.  A single CTA walking the
  * array is a chain of dependent memory latencies (measured 23-30 us for the 43 200 segments of an 8K frame),
  * so the array is cut into one chunk per CTA; a CTA first adds up everything in front of its chunk
@@ -749,9 +976,24 @@ extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_str
         if ( cudaFuncSetAttribute(k_huff_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, HE_SMEM) != cudaSuccess ) return -1;
         attr_done[dev] = true;
     }
-    k_huff_encode<<<(seg_count + HE_WARPS - 1) / HE_WARPS, HE_WARPS * 32, HE_SMEM, stream>>>(
-        a->d_coef, a->d_nzmask, a->lay, a->seg_mcu, seg_count, a->d_tmp, a->slot_stride, a->d_seg_bytes, a->d_spill,
-        a->d_tables);
+    if ( a->seg_mcu * a->lay.bpm <= HP_MAXBLK ) {
+        static bool attr_done_p[64] = {false};
+        if ( !attr_done_p[dev] ) {
+            if ( cudaFuncSetAttribute(k_huff_encode_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, HP_SMEM) != cudaSuccess )
+                return -1;
+            attr_done_p[dev] = true;
+        }
+        /* one thread per block of the CTA's segments: 288 blocks -> 9 warps, all busy in phase A */
+        const int hp_threads = max(HE_WARPS * 32, (HE_WARPS * a->seg_mcu * a->lay.bpm + 31) / 32 * 32);
+        k_huff_encode_packed<<<(seg_count + HE_WARPS - 1) / HE_WARPS, hp_threads, HP_SMEM, stream>>>(
+            a->d_coef, a->d_nzmask, a->lay, a->seg_mcu, seg_count, a->d_tmp, a->slot_stride, a->d_seg_bytes, a->d_spill,
+            a->d_tables);
+    }
+    else {
+        k_huff_encode<<<(seg_count + HE_WARPS - 1) / HE_WARPS, HE_WARPS * 32, HE_SMEM, stream>>>(
+            a->d_coef, a->d_nzmask, a->lay, a->seg_mcu, seg_count, a->d_tmp, a->slot_stride, a->d_seg_bytes, a->d_spill,
+            a->d_tables);
+    }
     /* one chunk (a multiple of the 1024-segment tile) per CTA, at most one CTA per SM */
     int off_chunk = (seg_count + 147) / 148;
     off_chunk = ((off_chunk + OFF_THREADS - 1) / OFF_THREADS) * OFF_THREADS;
