@@ -706,8 +706,10 @@ constexpr int HD_THREADS = 128;
 #ifndef GJ_HD_SPW
 #define GJ_HD_SPW 16
 #endif
-/* measured on B200, 8K 4:4:4 frame, photo-like / random content: 32 owners per warp 207 / 538 us, 16: 190 / 526 us,
- * 8: 189 / 878 us (issue-bound on dense streams), 4: 255 / 1318 us */
+/* measured on B200, photo-like / random content, owners per warp 32 | 16 | 8 | 4:
+ *   8K  (43 200 segments)  207/538 | 190/526 | 189/878 | 255/1318 us   -> 16
+ *   4K  (16 200 segments)     -    | 111/291 | 103/289 |  95/365  us   -> 8
+ *   HD  ( 4 050 segments)     -    | 109/277 |  95/253 |  83/239  us   -> 4 */
 constexpr int HD_SEGMENTS_PER_WARP = GJ_HD_SPW;
 
 struct DecTabs {
@@ -1007,15 +1009,24 @@ extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_str
 
 extern "C" int gj_launch_huffman_decode(const struct gj_huff_dec_args* a, gj_stream_t stream)
 {
-    constexpr int SPW = HD_SEGMENTS_PER_WARP;
-    const int per_cta = (HD_THREADS / 32) * SPW;
-    const dim3 grid((a->seg_count + per_cta - 1) / per_cta);
-    if ( a->dequantize )
-        k_huff_decode<true, SPW><<<grid, HD_THREADS, 0, stream>>>(a->d_file, a->d_file + a->file_size, a->d_seg_off, a->seg_count,
-                                                                  a->seg_mcu, *a, a->d_coef, a->d_tables);
-    else
-        k_huff_decode<false, SPW><<<grid, HD_THREADS, 0, stream>>>(a->d_file, a->d_file + a->file_size, a->d_seg_off, a->seg_count,
-                                                                   a->seg_mcu, *a, a->d_coef, a->d_tables);
+    /* segment owners per warp: few segments cannot fill the machine, so the shorter lock-step chains of fewer owners
+     * win; many dense segments need the lanes (see the measurements at HD_SEGMENTS_PER_WARP) */
+#define GJ_K3(DEQ_, SPW_)                                                                                              \
+    do {                                                                                                               \
+        const int per_cta = (HD_THREADS / 32) * (SPW_);                                                                \
+        k_huff_decode<DEQ_, SPW_><<<(a->seg_count + per_cta - 1) / per_cta, HD_THREADS, 0, stream>>>(                  \
+            a->d_file, a->d_file + a->file_size, a->d_seg_off, a->seg_count, a->seg_mcu, *a, a->d_coef, a->d_tables);  \
+    } while ( 0 )
+    if ( a->seg_count <= 8000 ) {
+        if ( a->dequantize ) GJ_K3(true, 4); else GJ_K3(false, 4);
+    }
+    else if ( a->seg_count <= 24000 ) {
+        if ( a->dequantize ) GJ_K3(true, 8); else GJ_K3(false, 8);
+    }
+    else {
+        if ( a->dequantize ) GJ_K3(true, HD_SEGMENTS_PER_WARP); else GJ_K3(false, HD_SEGMENTS_PER_WARP);
+    }
+#undef GJ_K3
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -323,10 +323,18 @@ def test_row_padding(enc):
 def test_unsupported_parameters_fail_loudly(gj, enc):
     p = gj.api.default_parameters()
     pi = gj.api.image_parameters(64, 64)
-    pi.pixel_format = gj.api.GPUJPEG_422_U8_P1020   # packed 4:2:2 samples cannot be GPUJPEG_RGB
-    img = np.zeros((64, 64, 3), np.uint8)
+    pi.pixel_format = 6                      # GPUJPEG_4444_U8_P0123: 4-component images are outside this build
+    img = np.zeros((64, 64, 4), np.uint8)
     with pytest.raises(gj.GpuJpegError):
         enc.encode_raw(img, p, pi)
+    p = gj.api.default_parameters()
+    p.color_space_internal = gj.api.GPUJPEG_RGB   # RGB-internal JPEG would need the Adobe header path
+    with pytest.raises(gj.GpuJpegError):
+        enc.encode_raw(np.zeros((64, 64, 3), np.uint8), p, gj.api.image_parameters(64, 64))
+    p = gj.api.default_parameters()
+    p.segment_info = 1
+    with pytest.raises(gj.GpuJpegError):
+        enc.encode_raw(np.zeros((64, 64, 3), np.uint8), p, gj.api.image_parameters(64, 64))
     with pytest.raises(gj.GpuJpegError):
         gj.Decoder().decode(np.zeros(100, np.uint8))
 
