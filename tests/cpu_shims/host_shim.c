@@ -138,3 +138,26 @@ int shim_geometry_ss(int width, int height, int rst, int interleaved, int lhs, i
         out[20 + i] = i < g.lay.bpm ? g.lay.idx_pred[i] : 0;
     return 0;
 }
+
+/* raw image layout of a pixel format: out = {comp_count, size, then per component off, pitch, xs, sampling h, v} */
+int shim_raw_layout(int fmt, int width, int height, int pad, long* out /*[17]*/)
+{
+    struct gpujpeg_image_parameters pi;
+    memset(&pi, 0, sizeof pi);
+    pi.width = width;
+    pi.height = height;
+    pi.width_padding = pad;
+    pi.pixel_format = (enum gpujpeg_pixel_format)fmt;
+    struct gj_raw_layout l;
+    if ( gj_raw_layout_init(&l, &pi) ) return -1;
+    out[0] = l.comp_count;
+    out[1] = (long)l.size;
+    for ( int c = 0; c < 3; c++ ) {
+        out[2 + 5 * c] = (long)l.comp[c].off;
+        out[3 + 5 * c] = (long)l.comp[c].pitch;
+        out[4 + 5 * c] = l.comp[c].xs;
+        out[5 + 5 * c] = l.sampling[c].horizontal;
+        out[6 + 5 * c] = l.sampling[c].vertical;
+    }
+    return 0;
+}

@@ -348,3 +348,42 @@ def test_stats_are_populated(gj):
     s = e.stats()
     assert s is not None and s.duration_in_gpu > 0 and s.duration_huffman_coder > 0
     e.close()
+
+
+def test_independent_coders_in_concurrent_host_threads(gj):
+    """one coder = one stream, instances share nothing: four host threads, each with its own encoder + decoder on its
+    own CUDA stream and its own image / parameters, all produce the oracle's bytes and pixels"""
+    import threading
+
+    import torch
+    jobs = [("photo", 640, 360, 75, 8, 0, "4:4:4", (1, 1)), ("random", 322, 201, 90, 4, 1, "4:2:0", (2, 2)),
+            ("photo", 1280, 720, 60, 12, 0, "4:2:2", (2, 1)), ("random", 200, 120, 85, 0, 1, "4:4:4", (1, 1))]
+    want = []
+    for kind, w, h, q, rst, il, name, samp in jobs:
+        img = o.gen_image(kind, w, h)
+        j = o.encode(img, q, rst, il, sampling=samp)
+        want.append((img, j, o.decode(j)))
+    errors = []
+
+    def work(i):
+        try:
+            torch.cuda.set_device(0)
+            st = torch.cuda.Stream()
+            e, d = gj.Encoder(stream=st.cuda_stream), gj.Decoder(stream=st.cuda_stream)
+            kind, w, h, q, rst, il, name, samp = jobs[i]
+            img, j, pix = want[i]
+            for _ in range(25):
+                got = e.encode(img, q, rst, il, subsampling=name)
+                assert np.array_equal(got, j), "thread %d: JPEG bytes differ" % i
+                assert np.array_equal(d.decode(got), pix), "thread %d: pixels differ" % i
+            e.close()
+            d.close()
+        except Exception as exc:
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors

@@ -148,3 +148,33 @@ def test_get_image_info_reports_the_stream_as_the_reference_does(fmt, il, native
     lh, lv = o.FMT_SAMPLING[fmt]
     assert (p.sampling_factor[0].horizontal, p.sampling_factor[0].vertical) == (lh, lv)
     assert nseg.value == o.probe(jpeg).segment_count
+
+
+@pytest.mark.parametrize("fmt", range(6))
+@pytest.mark.parametrize("w,h", [(64, 48), (1920, 1080), (322, 201), (16, 2)])
+def test_raw_layout_matches_the_reference_size_rule_and_the_oracle(fmt, w, h):
+    """where the samples of a pixel format live: total size against gpujpeg_image_calculate_size (the reference's own
+    rule, src/gpujpeg_common.c:1180-1205) and against the oracle's independent layout; every sample address in range"""
+    import ctypes as C
+    import gpujpeg_b200.api as api
+    out = np.zeros(17, np.int64)
+    assert hs.shim_raw_layout(fmt, w, h, 0, out) == 0
+    pi = api.image_parameters(w, h, 0, fmt)
+    assert out[1] == api.lib.gpujpeg_image_calculate_size(C.byref(pi)) == o.lib.orc_raw_size(fmt, w, h, 0)
+    comps = int(out[0])
+    assert comps == (1 if fmt == o.FMT_U8 else 3)
+    lh, lv = o.FMT_SAMPLING[fmt]
+    assert (out[5], out[6]) == (lh, lv)
+    for c in range(comps):
+        off, pitch, xs = (int(v) for v in out[2 + 5 * c:5 + 5 * c])
+        cw = w if c == 0 else (w + lh - 1) // lh
+        ch = h if c == 0 else (h + lv - 1) // lv
+        assert off + (ch - 1) * pitch + (cw - 1) * xs < out[1]
+
+
+def test_raw_layout_refuses_what_is_ambiguous():
+    out = np.zeros(17, np.int64)
+    assert hs.shim_raw_layout(o.FMT_422_P1020, 33, 16, 0, out) == -1      # odd width of packed 4:2:2
+    assert hs.shim_raw_layout(o.FMT_420_P0P1P2, 32, 16, 4, out) == -1     # row padding of planar formats
+    assert hs.shim_raw_layout(6, 32, 16, 0, out) == -1                     # 4 components
+    assert hs.shim_raw_layout(o.FMT_444_P012, 33, 17, 5, out) == 0 and out[3] == 3 * 33 + 5
