@@ -15,8 +15,10 @@
  *       -> K4 dequant + IDCT + colour transform + interleave (one launch)
  *     D2H pixels (unless a device output was requested)
  *
- * Supported: baseline 8-bit, 3 components 4:4:4, YCbCr-JPEG -> GPUJPEG_RGB / GPUJPEG_444_U8_P012,
- * interleaved or not, any restart interval, any DHT/DQT tables with ids 0..3.
+ * Supported: baseline 8-bit YCbCr-JPEG or grey streams, 1 or 3 components, 4:4:4 / 4:2:2 / 4:2:0 / 4:4:0, interleaved or
+ * not, any restart interval (or none), any DHT/DQT tables with ids 0..3; output negotiated in choose_output():
+ * GPUJPEG_RGB 444-u8-p012 through the fused kernel, the stream's own samples in a matching pixel format straight from
+ * the IDCT, every other pixel format x colour space combination through the generic pass.
  */
 #include <stdlib.h>
 #include <string.h>

@@ -11,9 +11,11 @@
  *              ->  D2H 32-byte info, D2H payload (one copy; the reference copies 43 200 segments
  *                  one by one on the host, src/gpujpeg_encoder.c:567-623)
  *
- * Supported on this path (anything else fails loudly with GPUJPEG_ERROR, never a CPU fallback):
- *   pixel format GPUJPEG_444_U8_P012, colour space GPUJPEG_RGB -> internal YCbCr JPEG (BT.601 full
- *   range), 3 components 4:4:4, interleaved or not, any restart interval, JFIF header.
+ * Supported (anything else fails loudly with GPUJPEG_ERROR, never a CPU fallback): see params_supported() --
+ * internal colour space YCbCr JPEG (BT.601 full range), JFIF header, 1 or 3 components, 4:4:4 / 4:2:2 / 4:2:0 /
+ * 4:4:0, interleaved or not, any restart interval; input GPUJPEG_RGB 444-u8-p012 through the fused kernels, grey /
+ * planar / packed YCbCr input without colour transform straight into the DCT, every other pixel format x colour
+ * space combination through the generic pass.
  */
 #include <assert.h>
 #include <stdlib.h>

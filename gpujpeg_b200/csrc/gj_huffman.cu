@@ -4,13 +4,13 @@
  * ENCODER (replaces the reference's three kernels src/gpujpeg_huffman_gpu_encoder.cu:299-404,
  * 416-502, 562-615 and the host re-ordering loop src/gpujpeg_encoder.c:567-626):
  *
- *   k_huff_encode   one WARP per restart segment, one LANE per 8x8 block, one pass per block: each
- *                   lane turns its block into a private bit string (sparse walk over the 64-bit
- *                   non-zero mask K1 wrote next to the zig-zag ordered coefficients), a warp prefix
- *                   sum over the lengths places the strings, lanes funnel-shift them into a per-warp
- *                   shared-memory stream buffer, and the warp byte-stuffs the buffer into the
- *                   segment's slot.  The buffer is flushed in rounds, so segments of any length
- *                   (even restart_interval = 0) stream through 2 KB of shared memory.
+ *   k_huff_encode_packed  segments of at most 40 blocks (every RESTART_AUTO setting): a CTA takes 8 consecutive
+ *                   segments; phase A builds the bit string of every block, one THREAD per block, densely
+ *                   packed (sparse walk over the 64-bit non-zero mask K1 wrote next to the zig-zag ordered
+ *                   coefficients); phase B, one WARP per segment, places the strings by a prefix sum over
+ *                   their lengths into a shared-memory stream buffer and byte-stuffs it into the segment's slot.
+ *   k_huff_encode   segments of any length (even restart_interval = 0): one WARP per segment, one LANE per block,
+ *                   the same steps per round of 32 blocks, streaming through the 2 KB buffer.
  *   k_huff_offsets  exclusive scan of the segment sizes -> final byte offsets (deterministic,
  *                   unlike the reference's atomicAdd compaction).
  *   k_huff_compact  copies every segment to its final place and writes RSTn markers, the SOS
@@ -18,11 +18,14 @@
  *                   finished scan data and the host does a single D2H copy.
  *
  * DECODER (replaces src/gpujpeg_huffman_gpu_decoder.cu:390-537, 596-610):
- *   k_huff_decode   one THREAD per restart segment (sequential by nature); lanes advance block
- *                   by block in lock step, each decoding into a private shared-memory block that
- *                   the warp then writes out as whole 128-byte lines (no memset of the coefficient
+ *   k_huff_decode   one THREAD per restart segment (sequential by nature); the owner lanes of a warp advance
+ *                   block by block in lock step, each decoding into a private shared-memory block that
+ *                   the whole warp then writes out as 128-byte lines (no memset of the coefficient
  *                   buffer, no scattered 2-byte stores).  Tables: 9-bit lookahead + canonical
  *                   bounds (1.4 KB per table) instead of the reference's 4 x 64 Ki-entry tables.
+ *
+ * Scans, segments and the block order inside them (4:4:4 or subsampled, interleaved or not) come from the
+ * gj_scan_layout the host passes by value; see segment_block().
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
