@@ -808,19 +808,25 @@ __device__ __forceinline__ int decode_symbol(BitSource& r, const gj_dec_lut& t)
 /* DEQ: store coefficient * quantiser wrapped to int16 -- exactly what the reference's integer IDCT
  * starts from (src/gpujpeg_dct_cpu.c:180-182) -- so the multiply is paid per NON-ZERO coefficient here
  * instead of 64 times per block in K4.  DEQ = false keeps raw quantised values (float IDCT flavour). */
+struct SegOwners {
+    int segs0;     // segments [0, segs0) use spw0 owners per warp, the rest spw1
+    int warps0;    // warps that take segments [0, segs0)
+    int spw0, spw1;
+};
+
 /* SPW = segments per warp: only the first SPW lanes of a warp own a segment, the others just help to move the finished
  * blocks out.  Fewer owners per warp make the warp's instruction stream shorter (the lock-step block loop runs as
  * long as its slowest lane, and every rarely-taken path is executed whenever ANY lane takes it), and that stream,
  * not the issue rate, is what bounds this kernel: 43 200 segments cannot fill the machine anyway. */
-template <bool DEQ, int SPW>
+template <bool DEQ>
 __global__ void __launch_bounds__(HD_THREADS)
 k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file_end, const uint32_t* __restrict__ seg_off,
-              int seg_count, int seg_mcu, const __grid_constant__ gj_huff_dec_args a,
+              int seg_count, int seg_mcu, const __grid_constant__ gj_huff_dec_args a, const __grid_constant__ SegOwners own,
               int16_t* __restrict__ coef, const gj_dev_dec_tables* __restrict__ tables)
 {
     __shared__ DecTabs s_tab;
     __shared__ uint16_t s_q[4][64];
-    __shared__ __align__(16) uint32_t s_blk[(HD_THREADS / 32) * SPW * 32];   // one private 8x8 block (128 B) per owner lane
+    __shared__ __align__(16) uint32_t s_blk[HD_THREADS * 32];   // one private 8x8 block (128 B) per owner lane
 
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(&tables->lut[0][0]);
@@ -829,17 +835,30 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file
             dst[i] = src[i];
         for ( int i = threadIdx.x; i < 256; i += HD_THREADS )
             s_q[i >> 6][i & 63] = tables->qinv_zz[i >> 6][i & 63];
-        for ( int i = threadIdx.x; i < (HD_THREADS / 32) * SPW * 32; i += HD_THREADS )
+        for ( int i = threadIdx.x; i < HD_THREADS * 32; i += HD_THREADS )
             s_blk[i] = 0;
     }
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g0 = (blockIdx.x * (HD_THREADS / 32) + warp) * SPW;  // first segment of this warp
-    if ( g0 >= seg_count ) return;
+    /* this warp's segments: the first scan (luminance when every component has its own scan) may use fewer owners per
+     * warp than the others; a warp never spans the boundary */
+    const int wg = blockIdx.x * (HD_THREADS / 32) + warp;
+    int g0, SPW, g_end;
+    if ( wg < own.warps0 ) {
+        SPW = own.spw0;
+        g0 = wg * SPW;
+        g_end = own.segs0;
+    }
+    else {
+        SPW = own.spw1;
+        g0 = own.segs0 + (wg - own.warps0) * SPW;
+        g_end = seg_count;
+    }
+    if ( g0 >= g_end ) return;
     if ( !seg_off && *a.d_error ) return;   // restart structure does not match the geometry: list ranks are meaningless
     const int g = g0 + lane;
-    const bool live = lane < SPW && g < seg_count;
+    const bool live = lane < SPW && g < g_end;
     const gj_scan_layout& L = a.lay;
     const int bpm = L.bpm;
     const bool general = !L.simple && L.interleaved;   // MCUs of several blocks per component
@@ -878,8 +897,8 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file
     /* private block: 16-byte chunk c of lane L lives at chunk (c ^ (L & 7)) so that the warp-wide
      * 16-byte reads of the flush below are bank-conflict free */
     const int sw = lane & 7;
-    int16_t* mine = reinterpret_cast<int16_t*>(s_blk + (warp * SPW + (lane < SPW ? lane : 0)) * 32);
-    uint4* wbase = reinterpret_cast<uint4*>(s_blk + warp * SPW * 32);
+    int16_t* mine = reinterpret_cast<int16_t*>(s_blk + (warp * 32 + (lane < SPW ? lane : 0)) * 32);
+    uint4* wbase = reinterpret_cast<uint4*>(s_blk + warp * 32 * 32);
     int pred[GJ_MAX_COMP] = {0, 0, 0, 0};
 
     int mcu = 0, bi_in_mcu = 0;   // block b = mcu * bpm + bi_in_mcu, the same in every lane
@@ -930,7 +949,6 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file
             target = mybase + (L.interleaved ? L.blk_off[a.scan_comp[0][ci]] : 0) + mcu;
         }
         /* write the warp's SPW private blocks out as 128-byte lines, four blocks per step, and clear them */
-#pragma unroll
         for ( int j = 0; j < SPW / 4; j++ ) {
             const int i = 4 * j + (lane >> 3);   // owner lane of the block this lane helps to move
             const int c = lane & 7;              // its 16-byte chunk
@@ -1013,23 +1031,29 @@ extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_str
 extern "C" int gj_launch_huffman_decode(const struct gj_huff_dec_args* a, gj_stream_t stream)
 {
     /* segment owners per warp: few segments cannot fill the machine, so the shorter lock-step chains of fewer owners
-     * win; many dense segments need the lanes (see the measurements at HD_SEGMENTS_PER_WARP) */
-#define GJ_K3(DEQ_, SPW_)                                                                                              \
-    do {                                                                                                               \
-        const int per_cta = (HD_THREADS / 32) * (SPW_);                                                                \
-        k_huff_decode<DEQ_, SPW_><<<(a->seg_count + per_cta - 1) / per_cta, HD_THREADS, 0, stream>>>(                  \
-            a->d_file, a->d_file + a->file_size, a->d_seg_off, a->seg_count, a->seg_mcu, *a, a->d_coef, a->d_tables);  \
-    } while ( 0 )
-    if ( a->seg_count <= 8000 ) {
-        if ( a->dequantize ) GJ_K3(true, 4); else GJ_K3(false, 4);
+     * win; many dense segments need the lanes (see the measurements at HD_SEGMENTS_PER_WARP).  With one scan per
+     * component the luminance scan carries most of the bits and finishes last: it gets fewer owners per warp than
+     * the chrominance scans. */
+    SegOwners own;
+    const int spw_all = a->seg_count <= 8000 ? 4 : a->seg_count <= 24000 ? 8 : HD_SEGMENTS_PER_WARP;
+    own.segs0 = a->seg_count;
+    own.spw0 = own.spw1 = spw_all;
+    if ( a->lay.scan_count > 1 ) {
+        /* measured, K3 in us for luminance/chrominance owners 16/16 | 8/32 | 4/32 (photo-like content; random content
+         * prefers more owners at 8K: 519 | 564 | 910):  8K 189 | 175 | 225,  4K 113 | 99 | 89,  HD 111 | 95 | 83 */
+        own.segs0 = a->lay.scan_seg_begin[1];
+        own.spw0 = a->seg_count > 24000 ? 8 : 4;
+        own.spw1 = 32;
     }
-    else if ( a->seg_count <= 24000 ) {
-        if ( a->dequantize ) GJ_K3(true, 8); else GJ_K3(false, 8);
-    }
-    else {
-        if ( a->dequantize ) GJ_K3(true, HD_SEGMENTS_PER_WARP); else GJ_K3(false, HD_SEGMENTS_PER_WARP);
-    }
-#undef GJ_K3
+    own.warps0 = (own.segs0 + own.spw0 - 1) / own.spw0;
+    const int warps = own.warps0 + (a->seg_count - own.segs0 + own.spw1 - 1) / own.spw1;
+    const dim3 grid((warps + HD_THREADS / 32 - 1) / (HD_THREADS / 32));
+    if ( a->dequantize )
+        k_huff_decode<true><<<grid, HD_THREADS, 0, stream>>>(a->d_file, a->d_file + a->file_size, a->d_seg_off, a->seg_count,
+                                                             a->seg_mcu, *a, own, a->d_coef, a->d_tables);
+    else
+        k_huff_decode<false><<<grid, HD_THREADS, 0, stream>>>(a->d_file, a->d_file + a->file_size, a->d_seg_off, a->seg_count,
+                                                              a->seg_mcu, *a, own, a->d_coef, a->d_tables);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
