@@ -283,7 +283,7 @@ def main():
     #      step n's kernels and step n-1's D2H (PCIe is full duplex).  Every step still copies its 99.5 MB in and its
     #      99.5 MB out inside the timed region; nothing is cached between steps. ----
     workers = max(1, args.e2e_workers)
-    e2e_ms = e2e_sync_ms
+    e2e_pipe_ms = None
     if workers > 1:
         pool = []
         for _ in range(workers):
@@ -326,11 +326,15 @@ def main():
         dt = torch.tensor([time.perf_counter() - t0], device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e_ms = float(dt.item()) / args.steps * 1e3
+        e2e_pipe_ms = float(dt.item()) / args.steps * 1e3
         for e, d, out, _ in pool:
             assert np.array_equal(out.numpy(), h_out.numpy()), "pipelined and serial end-to-end results disagree"
             e.close()
             d.close()
+    # several coders in flight help while PCIe is the limit (1-2 GPUs per host); with 8 GPUs the host's memory system
+    # is the limit and serial calls are faster: report the better of the two ways of calling the same API, and both
+    e2e_ms = e2e_sync_ms if e2e_pipe_ms is None or e2e_sync_ms <= e2e_pipe_ms else e2e_pipe_ms
+    used_workers = 1 if e2e_ms == e2e_sync_ms else workers
     e2e_value = world * npix / (e2e_ms * 1e-3) / 1e6
     clocks = sampler.stop() if rank == 0 else None
     assert np.array_equal(h_out.numpy(), d_out.cpu().numpy()), "e2e and resident paths disagree"
@@ -371,10 +375,13 @@ def main():
                          "path_achieved_gbs": round(path_gbs, 1), "path_frac": round(path_gbs / peak, 4)},
             "e2e": {"value": round(e2e_value, 1), "unit": "Mpix/s", "ms_per_step": round(e2e_ms, 3),
                     "h2d_bytes_per_step": int(npix * 3 + jpeg_size), "d2h_bytes_per_step": int(jpeg_size + npix * 3),
-                    "workers": workers,
-                    "how": "gpujpeg_encoder_encode + gpujpeg_decoder_decode with pinned host buffers; %d coder pairs, one host "
-                           "thread and one CUDA stream each (1 = strictly serial calls)" % workers,
-                    "serial_value": round(world * npix / (e2e_sync_ms * 1e-3) / 1e6, 1), "serial_ms_per_step": round(e2e_sync_ms, 3)},
+                    "workers": used_workers,
+                    "how": "gpujpeg_encoder_encode + gpujpeg_decoder_decode with pinned host buffers; the better of strictly "
+                           "serial calls on one coder pair and %d coder pairs in flight (one host thread and one CUDA stream "
+                           "each); both are listed" % workers,
+                    "serial_value": round(world * npix / (e2e_sync_ms * 1e-3) / 1e6, 1), "serial_ms_per_step": round(e2e_sync_ms, 3),
+                    "pipelined_value": round(world * npix / (e2e_pipe_ms * 1e-3) / 1e6, 1) if e2e_pipe_ms else None,
+                    "pipelined_ms_per_step": round(e2e_pipe_ms, 3) if e2e_pipe_ms else None, "pipelined_workers": workers},
             "gpu_launches": 6 * args.steps,
             "clocks": clocks,
         }
