@@ -327,10 +327,14 @@ static int encoder_init_image(struct gpujpeg_encoder* e, const struct gpujpeg_pa
     const struct gj_geometry* g = &e->geo;
     size_t coef_bytes = g->coef_count * sizeof(int16_t);
     size_t tmp_bytes = (size_t)g->seg_count * g->slot_stride + 256;
+    /* overflow area of the per-block bit strings: 32 words per block of a short segment (packed kernel, <= 40 blocks),
+     * per lane of a warp otherwise (streaming kernel) */
+    const int segblk = g->seg_mcu * g->lay.bpm;
+    size_t spill_bytes = (size_t)g->seg_count * (segblk <= 40 ? segblk : 32) * 32 * sizeof(uint32_t);
     if ( grow((void**)&e->d_coef, &e->d_coef_size, coef_bytes) ||
          grow((void**)&e->d_nzmask, &e->d_nzmask_size, g->coef_count / 64 * sizeof(uint64_t)) ||
          grow((void**)&e->d_tmp, &e->d_tmp_size, tmp_bytes) ||
-         grow((void**)&e->d_spill, &e->d_spill_size, (size_t)g->seg_count * 40 * 32 * sizeof(uint32_t)) ||
+         grow((void**)&e->d_spill, &e->d_spill_size, spill_bytes) ||
          grow((void**)&e->d_stream, &e->d_stream_size, g->stream_cap + 64) ) {
         GJ_ERR("Encoder device allocation failed (%zu + %zu + %zu bytes): %s\n", coef_bytes, tmp_bytes, g->stream_cap,
                gj_cuda_last_error());

@@ -410,7 +410,7 @@ k_huff_encode_packed(const int16_t* __restrict__ coef, const uint64_t* __restric
             reinterpret_cast<uint4*>(head)[1] = hb;
             const int dc = (int)(short)(ha.x & 0xFFFFu);
             uint32_t* priv = s_priv + lb * HE_PRIV;
-            uint32_t* spill = spill_all + ((size_t)g * HP_MAXBLK + j) * HE_SPILL;
+            uint32_t* spill = spill_all + ((size_t)g * segblk + j) * HE_SPILL;
             uint64_t acc = 0;
             int nb = 0, wi = 0;
 #define GJ_PUT(bits_, len_)                                        \
@@ -502,9 +502,9 @@ k_huff_encode_packed(const int16_t* __restrict__ coef, const uint64_t* __restric
         const int total = total0 + __shfl_sync(FULL, incl1, 31);
         if ( total <= HE_CAP_BITS ) {
             if ( len0 > 0 )
-                place(s_priv + (warp * segblk + j0) * HE_PRIV, spill_all + ((size_t)g * HP_MAXBLK + j0) * HE_SPILL, incl0 - len0, len0);
+                place(s_priv + (warp * segblk + j0) * HE_PRIV, spill_all + ((size_t)g * segblk + j0) * HE_SPILL, incl0 - len0, len0);
             if ( len1 > 0 )
-                place(s_priv + (warp * segblk + j1) * HE_PRIV, spill_all + ((size_t)g * HP_MAXBLK + j1) * HE_SPILL,
+                place(s_priv + (warp * segblk + j1) * HE_PRIV, spill_all + ((size_t)g * segblk + j1) * HE_SPILL,
                       total0 + incl1 - len1, len1);
             __syncwarp();
             const int nwords = total >> 5;
@@ -521,7 +521,7 @@ k_huff_encode_packed(const int16_t* __restrict__ coef, const uint64_t* __restric
                 const bool active = j < nblocks;
                 const int len = active ? (int)s_len[warp * segblk + j] : 0;
                 const uint32_t* priv = s_priv + (warp * segblk + (active ? j : 0)) * HE_PRIV;
-                const uint32_t* spill = spill_all + ((size_t)g * HP_MAXBLK + (active ? j : 0)) * HE_SPILL;
+                const uint32_t* spill = spill_all + ((size_t)g * segblk + (active ? j : 0)) * HE_SPILL;
                 const int incl = warp_incl_scan(len, lane);
                 const int excl = incl - len;
                 int lane0 = 0;

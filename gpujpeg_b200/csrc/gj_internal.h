@@ -217,7 +217,8 @@ struct gj_huff_enc_args {
     int seg_mcu;
     uint8_t* d_tmp;
     size_t slot_stride;
-    uint32_t* d_spill;      /* [seg_count][40 blocks][32 words]: overflow of the per-block bit strings (rarely touched) */
+    uint32_t* d_spill;      /* [seg_count][blocks per segment, or 32 lanes for long segments][32 words]: overflow of the
+                             * per-block bit strings (rarely touched) */
     uint32_t* d_seg_bytes;  /* [seg_count] */
     uint64_t* d_seg_off;    /* [seg_count] */
     uint8_t* d_stream;

@@ -387,3 +387,14 @@ def test_independent_coders_in_concurrent_host_threads(gj):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_full_size_16k_round_trip(enc, dec):
+    """BASELINE config 5 frame size (15360x8640, RESTART_AUTO = 36): 172 800 segments, 6.2 M blocks"""
+    w, h = 15360, 8640
+    img = o.gen_image("photo", w, h)
+    want = o.encode(img, 75, 36, threads=8)
+    got = enc.encode(img, 75, 36)
+    assert got.size == want.size and np.array_equal(got, want)
+    assert np.array_equal(dec.decode(got), o.decode(want, threads=8))
+    assert o.probe(got).segment_count == 172800
