@@ -398,3 +398,26 @@ def test_full_size_16k_round_trip(enc, dec):
     assert got.size == want.size and np.array_equal(got, want)
     assert np.array_equal(dec.decode(got), o.decode(want, threads=8))
     assert o.probe(got).segment_count == 172800
+
+
+def test_one_decoder_across_output_formats_and_streams(gj):
+    """re-initialisation inside one decoder instance: output format, colour space, sampling, component count and size
+    change from call to call"""
+    d = gj.Decoder()
+    try:
+        raw420 = o.gen_raw(o.FMT_420_P0P1P2, 320, 200)
+        j420 = o.encode_ycc(raw420, 320, 200, o.FMT_420_P0P1P2, 85, 6, 1)
+        jgrey = o.encode_ycc(o.gen_raw(o.FMT_U8, 100, 60), 100, 60, o.FMT_U8, 80, 4)
+        j444 = o.encode(o.gen_image("photo", 640, 360), 75, 12)
+        for _ in range(2):
+            assert np.array_equal(d.decode(j420), o.decode(j420))                                  # default: RGB
+            d.set_output_format(gj.api.GPUJPEG_YCBCR_JPEG, o.FMT_420_P0P1P2)
+            assert np.array_equal(d.decode_samples(j420)[0], o.decode_ycc(j420, o.FMT_420_P0P1P2, 320, 200))
+            d.set_output_format(gj.api.GPUJPEG_YCBCR_BT709, o.FMT_422_P1020)                        # generic pass
+            assert np.array_equal(d.decode_samples(j420)[0], o.decode_any(j420, o.FMT_422_P1020, o.CS_709))
+            d.set_output_format(gj.api.GPUJPEG_CS_DEFAULT, -2)                                      # GPUJPEG_PIXFMT_AUTODETECT
+            out, pi = d.decode_samples(jgrey)
+            assert pi.pixel_format == o.FMT_U8 and np.array_equal(out, o.decode_ycc(jgrey, o.FMT_U8, 100, 60))
+            assert np.array_equal(d.decode(j444), o.decode(j444))
+    finally:
+        d.close()
