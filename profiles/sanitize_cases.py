@@ -1,0 +1,46 @@
+"""Small encode/decode cases that touch every kernel and both Huffman encoders, for compute-sanitizer:
+    compute-sanitizer --tool memcheck  python profiles/sanitize_cases.py
+    compute-sanitizer --tool racecheck python profiles/sanitize_cases.py quick
+Every result is still checked against the oracle."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+
+import _oracle as o  # noqa: E402
+import gpujpeg_b200 as g  # noqa: E402
+
+quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
+enc, dec, decf = g.Encoder(), g.Decoder(), g.Decoder(idct="float_gpuref")
+cases = [("photo", 200, 120, 75, 8, 0, "4:4:4", (1, 1)), ("random", 33, 17, 90, 2, 0, "4:4:4", (1, 1)),
+         ("random", 100, 50, 60, 0, 0, "4:4:4", (1, 1)), ("photo", 256, 16, 95, 300, 0, "4:4:4", (1, 1)),
+         ("random", 161, 97, 85, 4, 1, "4:2:0", (2, 2)), ("photo", 130, 70, 75, 3, 0, "4:2:2", (2, 1)),
+         ("random", 64, 40, 75, 50, 1, "4:4:0", (1, 2))]
+if quick:
+    cases = cases[:2] + cases[4:5]
+for kind, w, h, q, rst, il, name, samp in cases:
+    img = o.gen_image(kind, w, h)
+    want = o.encode(img, q, rst, il, sampling=samp)
+    got = enc.encode(img, q, rst, il, subsampling=name)
+    assert np.array_equal(got, want), (kind, w, h, name)
+    assert np.array_equal(dec.decode(want), o.decode(want))
+    assert np.array_equal(decf.decode(want), o.decode(want, o.IDCT_FLOAT_GPUREF))
+    print("ok", kind, w, h, q, rst, il, name, flush=True)
+for fmt, cs, sub in [(o.FMT_U8, o.CS_JPEG, None), (o.FMT_420_P0P1P2, o.CS_JPEG, None), (o.FMT_422_P1020, o.CS_709, None),
+                     (o.FMT_444_P0P1P2, o.CS_RGB, "4:2:0")][:2 if quick else 4]:
+    w, h = 98, 54
+    raw = o.gen_raw(fmt, w, h)
+    samp = {"4:2:0": (2, 2), None: o.FMT_SAMPLING[fmt]}[sub]
+    want = o.encode_any(raw, w, h, fmt, cs, 80, 5, 1 if fmt else 0, samp) if fmt else o.encode_ycc(raw, w, h, fmt, 80, 5, 0)
+    got = enc.encode_samples(raw, w, h, fmt, 80, 5, 1 if fmt else 0, color_space=cs, subsampling=sub)
+    assert np.array_equal(got, want), (fmt, cs, sub)
+    d = g.Decoder()
+    d.set_output_format(cs, fmt)
+    out, _ = d.decode_samples(want)
+    assert np.array_equal(out, o.decode_any(want, fmt, cs) if fmt else o.decode_ycc(want, fmt, w, h))
+    d.close()
+    print("ok fmt", fmt, cs, sub, flush=True)
+print("all sanitizer cases ok")
