@@ -137,6 +137,8 @@ int gj_geometry_init(struct gj_geometry* g, const struct gpujpeg_parameters* par
         l->bcx[c] = k->bcx;
         l->comp_hs[c] = (uint8_t)k->hs;
         l->comp_vs[c] = (uint8_t)k->vs;
+        /* [ref: src/gpujpeg_common.c:689-692] every component of an RGB-internal JPEG is coded like luminance */
+        l->comp_tbl[c] = (uint8_t)((param->color_space_internal == GPUJPEG_RGB || c == 0 || c == 3) ? 0 : 1);
     }
     g->bcx = g->comp[0].bcx;
     g->bcy = g->comp[0].bcy;

@@ -36,6 +36,7 @@ struct ConvertParams {
     int jpeg_comps;
     int width, height;
     int cs;                 /* colour space of the raw image (enum gpujpeg_color_space) */
+    int cs_internal;        /* colour space of the JPEG's components */
 };
 
 __constant__ int c_to_rgb[5][9] = {{0}, {0}, {298, 0, 409, 298, -100, -208, 298, 516, 0},
@@ -79,7 +80,7 @@ k_convert_in(const uint8_t* __restrict__ raw, uint8_t* __restrict__ planes, cons
     int c[3] = {0, 128, 128};
     for ( int k = 0; k < p.raw_comps; k++ )
         c[k] = raw[p.off[k] + (size_t)(y / p.rdv[k]) * p.pitch[k] + (size_t)(x / p.rdh[k]) * p.xs[k]];
-    if ( p.raw_comps == 3 ) cs_transform(p.cs, GPUJPEG_YCBCR_BT601_256LVLS, c);
+    if ( p.raw_comps == 3 ) cs_transform(p.cs, p.cs_internal, c);
     for ( int k = 0; k < p.jpeg_comps; k++ )
         if ( x % p.pdh[k] == 0 && y % p.pdv[k] == 0 )
             planes[p.poff[k] + (size_t)(y / p.pdv[k]) * p.ppitch[k] + x / p.pdh[k]] = (uint8_t)c[k];
@@ -93,7 +94,7 @@ k_convert_out(const uint8_t* __restrict__ planes, uint8_t* __restrict__ raw, con
     int c[3] = {0, 128, 128};
     for ( int k = 0; k < p.jpeg_comps; k++ )
         c[k] = planes[p.poff[k] + (size_t)(y / p.pdv[k]) * p.ppitch[k] + x / p.pdh[k]];
-    if ( p.jpeg_comps == 3 ) cs_transform(GPUJPEG_YCBCR_BT601_256LVLS, p.cs, c);
+    if ( p.jpeg_comps == 3 ) cs_transform(p.cs_internal, p.cs, c);
     raw[p.off[0] + (size_t)y * p.pitch[0] + (size_t)x * p.xs[0]] = (uint8_t)c[0];
     if ( p.raw_comps == 1 ) return;
     if ( p.uyvy ) {
@@ -106,10 +107,13 @@ k_convert_out(const uint8_t* __restrict__ planes, uint8_t* __restrict__ raw, con
     }
 }
 
-int fill_params(ConvertParams* p, const struct gj_raw_layout* raw, enum gpujpeg_pixel_format fmt, int color_space, int width,
-                int height, const struct gj_comp_geo* comp, int comp_count, int max_hs, int max_vs)
+int fill_params(ConvertParams* p, const struct gj_raw_layout* raw, enum gpujpeg_pixel_format fmt, int color_space,
+                int color_space_internal, int width, int height, const struct gj_comp_geo* comp, int comp_count, int max_hs,
+                int max_vs)
 {
     memset(p, 0, sizeof *p);
+    if ( color_space_internal < GPUJPEG_RGB || color_space_internal > GPUJPEG_YCBCR_BT709 ) return -1;
+    p->cs_internal = color_space_internal;
     if ( comp_count < 1 || comp_count > 3 || (raw->comp_count != 1 && raw->comp_count != 3) ) return -1;
     if ( color_space < GPUJPEG_NONE || color_space > GPUJPEG_YCBCR_BT709 ) return -1;
     p->raw_comps = raw->comp_count;
@@ -137,11 +141,12 @@ int fill_params(ConvertParams* p, const struct gj_raw_layout* raw, enum gpujpeg_
 }  // namespace
 
 extern "C" int gj_launch_convert_in(const uint8_t* d_raw, const struct gj_raw_layout* raw, enum gpujpeg_pixel_format fmt,
-                                    int color_space, int width, int height, uint8_t* d_planes, size_t planes_size,
-                                    const struct gj_comp_geo* comp, int comp_count, int max_hs, int max_vs, gj_stream_t stream)
+                                    int color_space, int color_space_internal, int width, int height, uint8_t* d_planes,
+                                    size_t planes_size, const struct gj_comp_geo* comp, int comp_count, int max_hs, int max_vs,
+                                    gj_stream_t stream)
 {
     ConvertParams p;
-    if ( fill_params(&p, raw, fmt, color_space, width, height, comp, comp_count, max_hs, max_vs) ) return -1;
+    if ( fill_params(&p, raw, fmt, color_space, color_space_internal, width, height, comp, comp_count, max_hs, max_vs) ) return -1;
     /* samples outside the image are 0 [ref: src/gpujpeg_common.c:941-944] */
     if ( cudaMemsetAsync(d_planes, 0, planes_size, stream) != cudaSuccess ) return -1;
     k_convert_in<<<dim3((width + 255) / 256, height), 256, 0, stream>>>(d_raw, d_planes, p);
@@ -149,11 +154,12 @@ extern "C" int gj_launch_convert_in(const uint8_t* d_raw, const struct gj_raw_la
 }
 
 extern "C" int gj_launch_convert_out(const uint8_t* d_planes, uint8_t* d_raw, const struct gj_raw_layout* raw,
-                                     enum gpujpeg_pixel_format fmt, int color_space, int width, int height,
-                                     const struct gj_comp_geo* comp, int comp_count, int max_hs, int max_vs, gj_stream_t stream)
+                                     enum gpujpeg_pixel_format fmt, int color_space, int color_space_internal, int width,
+                                     int height, const struct gj_comp_geo* comp, int comp_count, int max_hs, int max_vs,
+                                     gj_stream_t stream)
 {
     ConvertParams p;
-    if ( fill_params(&p, raw, fmt, color_space, width, height, comp, comp_count, max_hs, max_vs) ) return -1;
+    if ( fill_params(&p, raw, fmt, color_space, color_space_internal, width, height, comp, comp_count, max_hs, max_vs) ) return -1;
     k_convert_out<<<dim3((width + 255) / 256, height), 256, 0, stream>>>(d_planes, d_raw, p);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

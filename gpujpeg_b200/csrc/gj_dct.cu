@@ -807,7 +807,8 @@ extern "C" int gj_launch_idct_rgb_ss(const int16_t* d_coef, const struct gj_comp
 }
 
 /* ---- no colour transform: grey, planar and packed YCbCr formats ---- */
-static int sample_grid(SampleGrid* sg, const struct gj_raw_layout* raw, const struct gj_comp_geo* comp, int comp_count)
+static int sample_grid(SampleGrid* sg, const struct gj_raw_layout* raw, const struct gj_comp_geo* comp, int comp_count,
+                       const uint8_t* comp_tbl)
 {
     if ( comp_count < 1 || comp_count > 3 || raw->comp_count != comp_count ) return -1;
     memset(sg, 0, sizeof *sg);
@@ -820,7 +821,7 @@ static int sample_grid(SampleGrid* sg, const struct gj_raw_layout* raw, const st
         sg->cw[c] = comp[k].width;
         sg->ch[c] = comp[k].height;
         sg->bcx[c] = comp[k].bcx;
-        sg->table[c] = c == 0 ? 0 : 1;
+        sg->table[c] = comp_tbl ? comp_tbl[k] : (c == 0 ? 0 : 1);
         if ( c < comp_count ) {
             sg->blk_off[c] = comp[c].blk_off;
             total = comp[c].blk_off + comp[c].nblk;
@@ -833,12 +834,12 @@ static int sample_grid(SampleGrid* sg, const struct gj_raw_layout* raw, const st
 
 extern "C" int gj_launch_fdct_samples(const uint8_t* d_raw, const struct gj_raw_layout* raw, int16_t* d_coef,
                                       uint64_t* d_nzmask, const struct gj_comp_geo* comp, int comp_count,
-                                      const struct gj_dev_enc_tables* h_tables, gj_stream_t stream)
+                                      const uint8_t* comp_tbl, const struct gj_dev_enc_tables* h_tables, gj_stream_t stream)
 {
     FdctParams prm;
     memcpy(prm.fwd_zz, h_tables->fwd_zz, sizeof prm.fwd_zz);
     SampleGrid sg;
-    const int total = sample_grid(&sg, raw, comp, comp_count);
+    const int total = sample_grid(&sg, raw, comp, comp_count, comp_tbl);
     if ( total <= 0 ) return -1;
     k_fdct_samples<<<(total + SG_THREADS - 1) / SG_THREADS, SG_THREADS, 0, stream>>>(d_raw, sg, total, d_coef, d_nzmask, prm);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
@@ -852,7 +853,7 @@ extern "C" int gj_launch_idct_samples(const int16_t* d_coef, const struct gj_com
     for ( int c = 0; c < 3; c++ )
         memcpy(prm.q_zz[c], h_tables->qinv_zz[comp_tq[c < comp_count ? c : 0]], sizeof prm.q_zz[c]);
     SampleGrid sg;
-    const int total = sample_grid(&sg, raw, comp, comp_count);
+    const int total = sample_grid(&sg, raw, comp, comp_count, nullptr);
     if ( total <= 0 ) return -1;
     if ( idct_flavour != 0 && coef_dequantized ) return -1;
     const int grid = (total + SG_THREADS - 1) / SG_THREADS;

@@ -254,7 +254,7 @@ static int choose_output(const struct gpujpeg_decoder* d, const struct gj_stream
     }
     pi->pixel_format = pf;
     pi->color_space = cs;
-    if ( cs == GPUJPEG_RGB && pf == GPUJPEG_444_U8_P012 ) return GJ_OUT_RGB;
+    if ( cs == GPUJPEG_RGB && pf == GPUJPEG_444_U8_P012 && st->color_space == GPUJPEG_YCBCR_BT601_256LVLS ) return GJ_OUT_RGB;
     if ( cs != GPUJPEG_RGB && cs != GPUJPEG_YCBCR_BT601 && cs != GPUJPEG_YCBCR_BT601_256LVLS && cs != GPUJPEG_YCBCR_BT709 ) {
         GJ_ERR("Colour space %s is not produced by this build.\n", gpujpeg_color_space_get_name(cs));
         return 0;
@@ -290,6 +290,7 @@ static int launch_k4(struct gpujpeg_decoder* d, const int comp_tq[3], uint8_t* d
                                     coef_dequantized, &d->h_tab, d->stream) )
             return -1;
         return gj_launch_convert_out(d->d_planes, d_out, &d->raw, d->param_image.pixel_format, d->param_image.color_space,
+                                     d->param.color_space_internal,
                                      g->width, g->height, g->comp, g->comp_count, g->max_hs, g->max_vs, d->stream);
     }
     if ( g->lay.simple )
@@ -356,18 +357,23 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
         p.sampling_factor[c].horizontal = (uint8_t)(st.comp_hv[c] >> 4);
         p.sampling_factor[c].vertical = (uint8_t)(st.comp_hv[c] & 15);
     }
-    p.color_space_internal = GPUJPEG_YCBCR_BT601_256LVLS;
+    /* colour space of the components: Adobe APP14 / component ids seen so far decide (the same rule gj_reader_finish
+     * applies at the end; a stream that changes its mind after the first SOS is refused below) */
+    const enum gpujpeg_color_space early_cs =
+        (st.comp_count == 3 && (adobe == 0 || (st.comp_id[0] == 'R' && st.comp_id[1] == 'G' && st.comp_id[2] == 'B')))
+            ? GPUJPEG_RGB : GPUJPEG_YCBCR_BT601_256LVLS;
+    st.color_space = early_cs;
+    p.color_space_internal = early_cs;
     struct gpujpeg_image_parameters pi;
     gpujpeg_image_set_default_parameters(&pi);
     pi.width = st.width;
     pi.height = st.height;
-    /* the stream's colour space is only known for certain after all markers (an Adobe segment may follow); the
-     * streams this build takes are YCbCr-JPEG, which is verified below before anything is launched */
     const int out_mode = choose_output(d, &st, &pi);
     if ( !out_mode ) return GPUJPEG_ERROR;
 
     if ( !d->initialised || d->param_image.width != pi.width || d->param_image.height != pi.height ||
          d->param_image.pixel_format != pi.pixel_format || d->param.comp_count != p.comp_count ||
+         d->param.color_space_internal != p.color_space_internal ||
          d->param.restart_interval != p.restart_interval || d->param.interleaved != p.interleaved ||
          memcmp(d->param.sampling_factor, p.sampling_factor, sizeof p.sampling_factor) != 0 ) {
         if ( d->initialised ) GJ_VERBOSE(d->verbose, "Reinitializing decoder.\n");
@@ -444,8 +450,9 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
         if ( r == 0 ) break; /* EOI (or end of data) */
     }
     if ( gj_reader_finish(&st, adobe, d->verbose) ) return GPUJPEG_ERROR;
-    if ( st.color_space != GPUJPEG_YCBCR_BT601_256LVLS ) {
-        GJ_ERR("This build decodes YCbCr JPEG streams only (stream is %s).\n", gpujpeg_color_space_get_name(st.color_space));
+    if ( st.color_space != early_cs ) {
+        GJ_ERR("The stream's colour space (%s) is announced after its first scan header; not supported.\n",
+               gpujpeg_color_space_get_name(st.color_space));
         return GPUJPEG_ERROR;
     }
     if ( st.scan_count != g->scan_count ) {

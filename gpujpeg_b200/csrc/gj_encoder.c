@@ -213,16 +213,19 @@ static int params_supported(const struct gpujpeg_parameters* p, const struct gpu
         GJ_ERR("segment_info headers are not implemented in this build.\n");
         return GJ_IN_UNSUPPORTED;
     }
-    if ( p->color_space_internal != GPUJPEG_YCBCR_BT601_256LVLS ) {
-        GJ_ERR("This build encodes to internal color space %s only.\n",
-               gpujpeg_color_space_get_name(GPUJPEG_YCBCR_BT601_256LVLS));
+    /* YCbCr JPEG (JFIF header) or RGB (Adobe APP14 header, every component coded with the luminance tables); the
+     * limited-range spaces would need the SPIFF header [ref: src/gpujpeg_writer.c:456-475] */
+    if ( p->color_space_internal != GPUJPEG_YCBCR_BT601_256LVLS && !(p->color_space_internal == GPUJPEG_RGB && p->comp_count == 3) ) {
+        GJ_ERR("This build encodes to the internal color spaces %s and %s only.\n",
+               gpujpeg_color_space_get_name(GPUJPEG_YCBCR_BT601_256LVLS), gpujpeg_color_space_get_name(GPUJPEG_RGB));
         return GJ_IN_UNSUPPORTED;
     }
     if ( p->comp_count != 3 && p->comp_count != 1 ) {
         GJ_ERR("This build encodes 1- and 3-component images only (comp_count = %d).\n", p->comp_count);
         return GJ_IN_UNSUPPORTED;
     }
-    if ( pi->pixel_format == GPUJPEG_444_U8_P012 && pi->color_space == GPUJPEG_RGB && p->comp_count == 3 ) {
+    if ( pi->pixel_format == GPUJPEG_444_U8_P012 && pi->color_space == GPUJPEG_RGB && p->comp_count == 3 &&
+         p->color_space_internal == GPUJPEG_YCBCR_BT601_256LVLS ) {
         /* luminance 1x1, 2x1, 1x2 or 2x2 with 1x1 chrominance: the sampling modes the reference has precompiled
          * preprocessor kernels for [ref: src/gpujpeg_preprocessor.cu:241-253] */
         const int lh = p->sampling_factor[0].horizontal, lv = p->sampling_factor[0].vertical;
@@ -278,15 +281,18 @@ static int launch_k1(struct gpujpeg_encoder* e, const uint8_t* d_raw)
 {
     const struct gj_geometry* g = &e->geo;
     if ( e->input_mode == GJ_IN_SAMPLES )
-        return gj_launch_fdct_samples(d_raw, &e->raw, e->d_coef, e->d_nzmask, g->comp, g->comp_count, &e->h_tab, e->stream);
+        return gj_launch_fdct_samples(d_raw, &e->raw, e->d_coef, e->d_nzmask, g->comp, g->comp_count, g->lay.comp_tbl, &e->h_tab,
+                                      e->stream);
     if ( e->input_mode == GJ_IN_GENERIC ) {
         struct gj_raw_layout pl;
         struct gj_comp_geo padded[GJ_MAX_COMP];
         gj_planes_layout(&pl, padded, g->comp, g->comp_count);
-        if ( gj_launch_convert_in(d_raw, &e->raw, e->param_image.pixel_format, e->param_image.color_space, g->width, g->height,
+        if ( gj_launch_convert_in(d_raw, &e->raw, e->param_image.pixel_format, e->param_image.color_space,
+                                  e->param.color_space_internal, g->width, g->height,
                                   e->d_planes, pl.size, g->comp, g->comp_count, g->max_hs, g->max_vs, e->stream) )
             return -1;
-        return gj_launch_fdct_samples(e->d_planes, &pl, e->d_coef, e->d_nzmask, padded, g->comp_count, &e->h_tab, e->stream);
+        return gj_launch_fdct_samples(e->d_planes, &pl, e->d_coef, e->d_nzmask, padded, g->comp_count, g->lay.comp_tbl, &e->h_tab,
+                                      e->stream);
     }
     if ( g->lay.simple )
         return gj_launch_fdct_rgb444(d_raw, g->width, g->height, g->pitch, e->d_coef, e->d_nzmask, g->bcx, g->bcy, &e->h_tab,

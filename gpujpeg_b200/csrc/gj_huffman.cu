@@ -200,7 +200,7 @@ k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzm
         const int j = base + lane;
         const bool active = j < nblocks;
         const int comp = comp_next, pd = pd_next;
-        const int tbl = comp == 0 ? 0 : 1;
+        const int tbl = lay.comp_tbl[comp];
         const int16_t* blk = coef + bi_next * 64;
 
         const uint64_t nz = nz_next;
@@ -393,7 +393,7 @@ k_huff_encode_packed(const int16_t* __restrict__ coef, const uint64_t* __restric
             size_t bi;
             int comp, pd;
             segment_block(lay, scan, first_mcu, j, bi, comp, pd);
-            const int tbl = comp == 0 ? 0 : 1;
+            const int tbl = lay.comp_tbl[comp];
             const int16_t* blk = coef + bi * 64;
             const uint64_t nz = __ldg(nzmask + bi);
             const uint4 ha = __ldg(reinterpret_cast<const uint4*>(blk)), hb = __ldg(reinterpret_cast<const uint4*>(blk) + 1);

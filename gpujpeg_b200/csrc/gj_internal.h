@@ -108,6 +108,7 @@ struct gj_scan_layout {
      * same component = the DC predictor */
     uint8_t idx_comp[GJ_MAX_MCU_BLOCKS], idx_dx[GJ_MAX_MCU_BLOCKS], idx_dy[GJ_MAX_MCU_BLOCKS], idx_pred[GJ_MAX_MCU_BLOCKS];
     uint8_t comp_hs[GJ_MAX_COMP], comp_vs[GJ_MAX_COMP];
+    uint8_t comp_tbl[GJ_MAX_COMP];   /* quantisation / Huffman table class of the component: 0 luminance, 1 chrominance */
 };
 
 struct gj_geometry {
@@ -286,8 +287,8 @@ int gj_launch_idct_rgb_ss(const int16_t* d_coef, const struct gj_comp_geo comp[3
  * [replaces the "matching format" memcpy path + DCT launches, ref: src/gpujpeg_preprocessor.cu:409-455,
  *  src/gpujpeg_postprocessor.cu:406-433, and the GPUJPEG_NONE colour-transform kernels] */
 int gj_launch_fdct_samples(const uint8_t* d_raw, const struct gj_raw_layout* raw, int16_t* d_coef, uint64_t* d_nzmask,
-                           const struct gj_comp_geo* comp, int comp_count, const struct gj_dev_enc_tables* h_tables,
-                           gj_stream_t stream);
+                           const struct gj_comp_geo* comp, int comp_count, const uint8_t* comp_tbl,
+                           const struct gj_dev_enc_tables* h_tables, gj_stream_t stream);
 int gj_launch_idct_samples(const int16_t* d_coef, const struct gj_comp_geo* comp, int comp_count, const int* comp_tq,
                            uint8_t* d_raw, const struct gj_raw_layout* raw, int idct_flavour, int coef_dequantized,
                            const struct gj_dev_dec_tables* h_tables, gj_stream_t stream);
@@ -296,11 +297,11 @@ int gj_launch_idct_samples(const int16_t* d_coef, const struct gj_comp_geo* comp
  * component planes of the YCbCr JPEG (plane c at byte comp[c].blk_off * 64, pitch comp[c].bcx * 8)
  * [replaces the generic kernels of ref: src/gpujpeg_preprocessor.cu:163-201, src/gpujpeg_postprocessor.cu:183-216] */
 int gj_launch_convert_in(const uint8_t* d_raw, const struct gj_raw_layout* raw, enum gpujpeg_pixel_format fmt, int color_space,
-                         int width, int height, uint8_t* d_planes, size_t planes_size, const struct gj_comp_geo* comp,
-                         int comp_count, int max_hs, int max_vs, gj_stream_t stream);
+                         int color_space_internal, int width, int height, uint8_t* d_planes, size_t planes_size,
+                         const struct gj_comp_geo* comp, int comp_count, int max_hs, int max_vs, gj_stream_t stream);
 int gj_launch_convert_out(const uint8_t* d_planes, uint8_t* d_raw, const struct gj_raw_layout* raw, enum gpujpeg_pixel_format fmt,
-                          int color_space, int width, int height, const struct gj_comp_geo* comp, int comp_count, int max_hs,
-                          int max_vs, gj_stream_t stream);
+                          int color_space, int color_space_internal, int width, int height, const struct gj_comp_geo* comp,
+                          int comp_count, int max_hs, int max_vs, gj_stream_t stream);
 /* the planes above described as a raw layout, so that the sample kernels can run on them */
 void gj_planes_layout(struct gj_raw_layout* l, struct gj_comp_geo padded[GJ_MAX_COMP], const struct gj_comp_geo* comp,
                       int comp_count);

@@ -642,20 +642,34 @@ static inline uint8_t* put8(uint8_t* p, int v) { *p++ = (uint8_t)v; return p; }
 static inline uint8_t* put16(uint8_t* p, int v) { *p++ = (uint8_t)(v >> 8); *p++ = (uint8_t)v; return p; }
 static inline uint8_t* putm(uint8_t* p, int m) { *p++ = 0xFF; *p++ = (uint8_t)m; return p; }
 
+/* RGB-internal streams: Adobe APP14 (transform 0) instead of JFIF, component ids 'R','G','B', every component coded with
+ * the luminance tables [ref: src/gpujpeg_writer.c:255-276, 305-313, 462-470; src/gpujpeg_common.c:689-692] */
+static int g_rgb_internal = 0;
+
 size_t orc_write_header(uint8_t* out, int w, int h, int quality, int rst, int comp_count)
 {
     uint8_t raw[2][64];
     orc_quant_tables(quality, raw, NULL, NULL);
     uint8_t* p = out;
     p = putm(p, 0xD8);
-    p = putm(p, 0xE0);
-    p = put16(p, 16);
-    memcpy(p, "JFIF", 5);
-    p += 5;
-    p = put8(p, 1); p = put8(p, 1); p = put8(p, 1);
-    p = put16(p, 300); p = put16(p, 300);
-    p = put8(p, 0); p = put8(p, 0);
-    int ntypes = comp_count > 1 ? 2 : 1;
+    if ( g_rgb_internal ) {
+        p = putm(p, 0xEE);
+        p = put16(p, 14);
+        memcpy(p, "Adobe", 5);
+        p += 5;
+        p = put16(p, 100); p = put16(p, 0); p = put16(p, 0);
+        p = put8(p, 0);
+    }
+    else {
+        p = putm(p, 0xE0);
+        p = put16(p, 16);
+        memcpy(p, "JFIF", 5);
+        p += 5;
+        p = put8(p, 1); p = put8(p, 1); p = put8(p, 1);
+        p = put16(p, 300); p = put16(p, 300);
+        p = put8(p, 0); p = put8(p, 0);
+    }
+    int ntypes = (comp_count > 1 && !g_rgb_internal) ? 2 : 1;
     for ( int t = 0; t < ntypes; t++ ) {
         p = putm(p, 0xDB);
         p = put16(p, 67);
@@ -670,9 +684,9 @@ size_t orc_write_header(uint8_t* out, int w, int h, int quality, int rst, int co
     p = put16(p, w);
     p = put8(p, comp_count);
     for ( int c = 0; c < comp_count; c++ ) {
-        p = put8(p, c + 1);
+        p = put8(p, g_rgb_internal ? "RGB"[c] : c + 1);
         p = put8(p, 0x11);
-        p = put8(p, c == 0 ? 0 : 1);
+        p = put8(p, (c == 0 || g_rgb_internal) ? 0 : 1);
     }
     for ( int t = 0; t < ntypes; t++ ) {
         for ( int k = 0; k < 2; k++ ) {
@@ -723,15 +737,15 @@ static uint8_t* write_sos(uint8_t* p, int interleaved, int comp_count, int scan_
         p = put16(p, 6 + 2 * comp_count);
         p = put8(p, comp_count);
         for ( int c = 0; c < comp_count; c++ ) {
-            p = put8(p, c + 1);
-            p = put8(p, c == 0 ? 0x00 : 0x11);
+            p = put8(p, g_rgb_internal ? "RGB"[c] : c + 1);
+            p = put8(p, (c == 0 || g_rgb_internal) ? 0x00 : 0x11);
         }
     }
     else {
         p = put16(p, 8);
         p = put8(p, 1);
-        p = put8(p, scan_comp + 1);
-        p = put8(p, scan_comp == 0 ? 0x00 : 0x11);
+        p = put8(p, g_rgb_internal ? "RGB"[scan_comp] : scan_comp + 1);
+        p = put8(p, (scan_comp == 0 || g_rgb_internal) ? 0x00 : 0x11);
     }
     p = put8(p, 0);
     p = put8(p, 0x3F);
@@ -932,7 +946,7 @@ static size_t encode_from_planes(const uint8_t* planes, const struct ogeo g[4], 
     float fwd[2][64];
     orc_quant_tables(quality, raw, fwd, NULL);
     for ( int c = 0; c < comps; c++ )
-        orc_fdct_quant_plane(planes + g[c].off, g[c].dw, g[c].dh, fwd[c == 0 ? 0 : 1], coef + g[c].off);
+        orc_fdct_quant_plane(planes + g[c].off, g[c].dw, g[c].dh, fwd[(c == 0 || g_rgb_internal) ? 0 : 1], coef + g[c].off);
 
     /* header: as orc_write_header, with the sampling factors patched into SOF0 */
     size_t hl = orc_write_header(out, w, h, quality, rst, comps);
@@ -977,17 +991,19 @@ static size_t encode_from_planes(const uint8_t* planes, const struct ogeo g[4], 
         int cnt = rst > 0 ? (scan_mcus[scan] - first < seg_mcu ? scan_mcus[scan] - first : seg_mcu) : scan_mcus[scan];
         uint8_t* o = tmp + (size_t)si * slot;
         if ( !interleaved ) {
-            seg_len[si] = orc_huff_encode_segment(coef + g[scan].off + (size_t)first * 64, cnt, scan == 0 ? 0 : 1, o);
+            seg_len[si] = orc_huff_encode_segment(coef + g[scan].off + (size_t)first * 64, cnt,
+                                                  (scan == 0 || g_rgb_internal) ? 0 : 1, o);
         }
         else {
             struct bitw bw = {o, 0, 0};
             int pred[3] = {0, 0, 0};
             for ( int m = first; m < first + cnt; m++ )
-                for ( int c = 0; c < comps; c++ )
+                for ( int c = 0; c < comps; c++ ) {
+                    const int cls = (c == 0 || g_rgb_internal) ? 0 : 1;
                     for ( int y = 0; y < g[c].vs; y++ )
                         for ( int x = 0; x < g[c].hs; x++ )
-                            encode_block(&bw, mcu_block(coef, &g[c], mcu_x, m, x, y), &pred[c], &g_enc[c == 0 ? 0 : 1][0],
-                                         &g_enc[c == 0 ? 0 : 1][1]);
+                            encode_block(&bw, mcu_block(coef, &g[c], mcu_x, m, x, y), &pred[c], &g_enc[cls][0], &g_enc[cls][1]);
+                }
             flush_bits(&bw);
             seg_len[si] = (size_t)(bw.p - o);
         }
@@ -1196,9 +1212,19 @@ static void raw_load_pixel(const uint8_t* raw, int fmt, const struct rawcomp rc[
     }
 }
 
+size_t orc_encode_any2(const uint8_t* raw, int w, int h, int fmt, int cs, int internal, int quality, int rst, int interleaved,
+                       int lhs, int lvs, int threads, uint8_t* out);
 size_t orc_encode_any(const uint8_t* raw, int w, int h, int fmt, int cs, int quality, int rst, int interleaved, int lhs,
                       int lvs, int threads, uint8_t* out)
 {
+    return orc_encode_any2(raw, w, h, fmt, cs, CS_601_256, quality, rst, interleaved, lhs, lvs, threads, out);
+}
+
+/* internal = colour space of the JPEG's components: CS_601_256 (JFIF) or CS_RGB (Adobe APP14) */
+size_t orc_encode_any2(const uint8_t* raw, int w, int h, int fmt, int cs, int internal, int quality, int rst, int interleaved,
+                       int lhs, int lvs, int threads, uint8_t* out)
+{
+    if ( internal != CS_601_256 && internal != CS_RGB ) return 0;
     if ( w <= 0 || h <= 0 || w > 65535 || h > 65535 || rst < 0 || rst > 65535 ) return 0;
     struct rawcomp rc[3];
     int fhs[4], fvs[4];
@@ -1224,14 +1250,16 @@ size_t orc_encode_any(const uint8_t* raw, int w, int h, int fmt, int cs, int qua
         for ( int x = 0; x < w; x++ ) {
             int c[3];
             raw_load_pixel(raw, fmt, rc, fhs, fvs, x, y, c);
-            cs_transform(cs, CS_601_256, c);
+            cs_transform(cs, internal, c);
             for ( int k = 0; k < 3; k++ ) {
                 int dh = max_hs / g[k].hs, dv = max_vs / g[k].vs;
                 if ( x % dh || y % dv ) continue;
                 planes[g[k].off + (size_t)(y / dv) * g[k].dw + x / dh] = (uint8_t)c[k];
             }
         }
+    g_rgb_internal = internal == CS_RGB;
     size_t n = encode_from_planes(planes, g, comps, hs, vs, w, h, quality, rst, interleaved, out, coef);
+    g_rgb_internal = 0;
 #ifdef _OPENMP
     omp_set_num_threads(saved_threads);
 #endif
@@ -1355,6 +1383,7 @@ struct parsed {
     uint8_t hbits[2][4][17];
     uint8_t hvals[2][4][256];
     int comp_id[4], comp_tq[4], comp_hv[4];
+    int adobe_transform;   /* -1: no APP14 Adobe segment */
     int nscan;
     struct {
         int ncomp, comp[4], td[4], ta[4];
@@ -1370,6 +1399,7 @@ static inline int rd16(const uint8_t* p) { return (p[0] << 8) | p[1]; }
 static int parse_stream(const uint8_t* j, size_t size, struct parsed* P)
 {
     memset(P, 0, sizeof *P);
+    P->adobe_transform = -1;
     size_t i = 0;
     if ( size < 4 || j[0] != 0xFF || j[1] != 0xD8 ) return -1;
     i = 2;
@@ -1422,6 +1452,9 @@ static int parse_stream(const uint8_t* j, size_t size, struct parsed* P)
         }
         else if ( m == 0xDD ) {
             P->rst = rd16(d);
+        }
+        else if ( m == 0xEE && len >= 14 && memcmp(d, "Adobe", 5) == 0 ) {
+            P->adobe_transform = d[11];   /* [ref: src/gpujpeg_reader.c:560-640] */
         }
         else if ( m == 0xDA ) {
             if ( P->nscan == 0 ) P->header_size = i;
@@ -1673,6 +1706,9 @@ int orc_decode_any(const uint8_t* jpeg, size_t size, int idct_flavour, int threa
 #else
     (void)threads;
 #endif
+    /* colour space of the components: Adobe transform 0 or ids 'R','G','B' mean RGB [ref: src/gpujpeg_reader.c:264-640] */
+    const int stream_cs = (P.comps == 3 && (P.adobe_transform == 0 || (P.comp_id[0] == 'R' && P.comp_id[1] == 'G' && P.comp_id[2] == 'B')))
+                              ? CS_RGB : CS_601_256;
     struct ogeo g[4];
     int max_hs, max_vs;
     uint8_t* planes = decode_to_planes(&P, jpeg, idct_flavour, g, &max_hs, &max_vs, NULL, 1);
@@ -1684,7 +1720,7 @@ int orc_decode_any(const uint8_t* jpeg, size_t size, int idct_flavour, int threa
                     int dh = max_hs / g[k].hs, dv = max_vs / g[k].vs;
                     c[k] = planes[g[k].off + (size_t)(y / dv) * g[k].dw + x / dh];
                 }
-                if ( P.comps == 3 ) cs_transform(CS_601_256, cs, c);
+                if ( P.comps == 3 ) cs_transform(stream_cs, cs, c);
                 if ( fcomps == 1 ) {
                     raw[rc[0].off + (size_t)y * rc[0].pitch + x] = (uint8_t)c[0];
                     continue;

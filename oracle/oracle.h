@@ -90,6 +90,10 @@ int orc_decode_ycc(const uint8_t* jpeg, size_t size, int idct_flavour, int threa
 size_t orc_encode_any(const uint8_t* raw, int w, int h, int fmt, int cs, int quality, int rst, int interleaved, int lhs,
                       int lvs, int threads, uint8_t* out);
 int orc_decode_any(const uint8_t* jpeg, size_t size, int idct_flavour, int threads, int fmt, int cs, uint8_t* raw);
+/* the same with the colour space of the JPEG's components chosen: 3 = YCbCr JPEG (JFIF header) or 1 = RGB (Adobe APP14
+ * header, component ids 'R','G','B', luminance tables for every component); orc_decode_any detects it from the stream */
+size_t orc_encode_any2(const uint8_t* raw, int w, int h, int fmt, int cs, int internal, int quality, int rst, int interleaved,
+                       int lhs, int lvs, int threads, uint8_t* out);
 /* Decode a baseline JPEG produced by this codec family (3 comp, any of the above samplings, or 1 comp) to RGB/gray u8.
  * Returns 0 on success; fills w,h,comps.  rgb may be NULL to probe. coef_out optional. */
 int orc_decode_rgb(const uint8_t* jpeg, size_t size, int idct_flavour, int threads, uint8_t* rgb,

@@ -54,6 +54,9 @@ lib.orc_encode_ycc.restype = C.c_size_t
 lib.orc_decode_ycc.argtypes = [_u8p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]
 lib.orc_encode_any.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]
 lib.orc_encode_any.restype = C.c_size_t
+lib.orc_encode_any2.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                _u8p]
+lib.orc_encode_any2.restype = C.c_size_t
 lib.orc_decode_any.argtypes = [_u8p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]
 lib.orc_decode_rgb.argtypes = [_u8p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int),
                                C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
@@ -212,11 +215,12 @@ class huffman_override:
 CS_NONE, CS_RGB, CS_601, CS_JPEG, CS_709 = range(5)
 
 
-def encode_any(raw, w, h, fmt, cs, quality=75, rst=8, interleaved=0, sampling=(1, 1), threads=1):
-    """generic path of the reference: pixel format x colour space x JPEG sampling, per-pixel colour transform"""
+def encode_any(raw, w, h, fmt, cs, quality=75, rst=8, interleaved=0, sampling=(1, 1), threads=1, internal=3):
+    """generic path of the reference: pixel format x colour space x JPEG sampling, per-pixel colour transform;
+    internal = colour space of the JPEG's components (3 = YCbCr JPEG / JFIF, 1 = RGB / Adobe APP14)"""
     out = np.empty(4096 + w * h * 6 + 4096, np.uint8)
-    n = lib.orc_encode_any(np.ascontiguousarray(raw).reshape(-1), w, h, fmt, cs, quality, rst, interleaved, sampling[0],
-                           sampling[1], threads, out)
+    n = lib.orc_encode_any2(np.ascontiguousarray(raw).reshape(-1), w, h, fmt, cs, internal, quality, rst, interleaved,
+                            sampling[0], sampling[1], threads, out)
     assert n > 0
     return out[:n].copy()
 
@@ -284,4 +288,7 @@ if os.path.exists(_REF_SO):
                                        C.c_int, np.ctypeslib.ndpointer(np.int32), np.ctypeslib.ndpointer(np.int32),
                                        np.ctypeslib.ndpointer(np.uint64), np.ctypeslib.ndpointer(np.uint64),
                                        _u8p, _u8p, _i16p]
+    ref.ref_encode_from_coef_rgb.argtypes = [_i16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p,
+                                             C.c_size_t]
+    ref.ref_encode_from_coef_rgb.restype = C.c_size_t
     ref.ref_idct_block.argtypes = [_i16p, np.ctypeslib.ndpointer(np.uint16)]

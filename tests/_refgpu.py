@@ -109,6 +109,8 @@ def main():
         enc = lib.gpujpeg_encoder_create(None)
         p, pi = params(lib, w, h, q, rst, il)
         pi.pixel_format, pi.color_space = fmt, cs   # comp_count stays 0: sampling follows the pixel format
+        if len(sys.argv) > 11:
+            p.color_space_internal = int(sys.argv[11])   # e.g. 1 = GPUJPEG_RGB: RGB-internal JPEG (Adobe APP14)
         encode(lib, enc, raw, p, pi).tofile(path)
         lib.gpujpeg_encoder_destroy(enc)
     elif mode == "decode_fmt":

@@ -328,7 +328,7 @@ def test_unsupported_parameters_fail_loudly(gj, enc):
     with pytest.raises(gj.GpuJpegError):
         enc.encode_raw(img, p, pi)
     p = gj.api.default_parameters()
-    p.color_space_internal = gj.api.GPUJPEG_RGB   # RGB-internal JPEG would need the Adobe header path
+    p.color_space_internal = gj.api.GPUJPEG_YCBCR_BT709   # limited-range internal spaces would need the SPIFF header
     with pytest.raises(gj.GpuJpegError):
         enc.encode_raw(np.zeros((64, 64, 3), np.uint8), p, gj.api.image_parameters(64, 64))
     p = gj.api.default_parameters()
@@ -419,5 +419,27 @@ def test_one_decoder_across_output_formats_and_streams(gj):
             out, pi = d.decode_samples(jgrey)
             assert pi.pixel_format == o.FMT_U8 and np.array_equal(out, o.decode_ycc(jgrey, o.FMT_U8, 100, 60))
             assert np.array_equal(d.decode(j444), o.decode(j444))
+    finally:
+        d.close()
+
+
+@pytest.mark.parametrize("il,sub", [(0, None), (1, None), (1, "4:2:0")])
+def test_rgb_internal_jpeg(gj, enc, il, sub):
+    """color_space_internal = GPUJPEG_RGB: RGB samples go into the JPEG untransformed (Adobe APP14 header, luminance
+    tables for all components); decoding gives them back as RGB by default, or in another colour space on request"""
+    w, h = 322, 200
+    img = o.gen_image("photo", w, h)
+    samp = {None: (1, 1), "4:2:0": (2, 2)}[sub]
+    want = o.encode_any(img, w, h, o.FMT_444_P012, o.CS_RGB, 85, 6, il, samp, threads=4, internal=o.CS_RGB)
+    p = gj.api.default_parameters(85, 6, il, sub or "4:4:4")
+    p.color_space_internal = gj.api.GPUJPEG_RGB
+    addr, size = enc.encode_raw(img, p, gj.api.image_parameters(w, h))
+    got = np.ctypeslib.as_array((__import__("ctypes").c_uint8 * size).from_address(addr)).copy()
+    assert got.size == want.size and np.array_equal(got, want)
+    d = gj.Decoder()
+    try:
+        assert np.array_equal(d.decode(want).reshape(-1), o.decode_any(want, o.FMT_444_P012, o.CS_RGB, threads=4))
+        d.set_output_format(gj.api.GPUJPEG_YCBCR_BT709, o.FMT_444_P0P1P2)
+        assert np.array_equal(d.decode_samples(want)[0], o.decode_any(want, o.FMT_444_P0P1P2, o.CS_709, threads=4))
     finally:
         d.close()

@@ -66,6 +66,24 @@ def test_subsampled_encode_bytes_and_decode_coefficients(kind, w, h, q, rst, sam
     assert np.array_equal(coef_dec, coef) and out.shape == (h, w, 3)
 
 
+@pytest.mark.parametrize("il,sampling", [(0, (1, 1)), (1, (1, 1)), (1, (2, 2))])
+def test_rgb_internal_stream_bytes(il, sampling):
+    """RGB-internal JPEG (no colour transform of RGB input): Adobe APP14 header, component ids 'R','G','B', one DQT and
+    one DHT pair, luminance tables for all three components -- oracle bytes against the reference's header writer +
+    CPU Huffman encoder fed with the same coefficients [ref: src/gpujpeg_writer.c:255-276, 462-470, 487-505]"""
+    w, h, q, rst = 100, 60, 85, 5
+    img = o.gen_image("photo", w, h)
+    jpeg = o.encode_any(img, w, h, o.FMT_444_P012, o.CS_RGB, q, rst, il, sampling, internal=o.CS_RGB)
+    assert jpeg[2:4].tobytes() == b"\xff\xee" and b"Adobe" in jpeg[:20].tobytes()
+    _, coef = o.decode(jpeg, want_coef=True)          # pixels are meaningless here (RGB samples), coefficients are not
+    out = np.empty(4096 + coef.size * 8, np.uint8)
+    n = o.ref.ref_encode_from_coef_rgb(np.ascontiguousarray(coef).reshape(-1), w, h, q, rst, il, sampling[0], sampling[1], out,
+                                       out.size)
+    assert n > 0 and np.array_equal(out[:n], jpeg)
+    back = o.decode_any(jpeg, o.FMT_444_P012, o.CS_RGB).reshape(h, w, 3).astype(int)
+    assert np.abs(back - img).mean() < 12
+
+
 def test_subsampled_chroma_is_point_sampled():
     """the preprocessor keeps every second chroma sample unfiltered and the postprocessor replicates it
     [ref: src/gpujpeg_preprocessor.cu:50-64, src/gpujpeg_postprocessor.cu:55-76]: an image whose colour only changes

@@ -139,3 +139,36 @@ def test_reference_gpu_colour_spaces(tmp_path, fmt, cs, w, h, il):
     out, _ = d.decode_samples(ref)
     assert np.array_equal(out, pix), "product decode != reference GPU decoder"
     d.close()
+
+
+@pytest.mark.skipif(not os.path.exists(SO), reason="oracle/_ref/libgpujpeg_refgpu.so not built")
+@pytest.mark.parametrize("fmt,cs,il", [(1, 1, 0), (1, 1, 1), (2, 1, 0), (1, 4, 1)])
+def test_reference_gpu_rgb_internal_jpeg(tmp_path, fmt, cs, il):
+    """color_space_internal = GPUJPEG_RGB (Adobe APP14 header, luminance tables for every component): reference GPU
+    encoder bytes == oracle == product; reference GPU decoder == oracle == product for the same output request"""
+    w, h = 640, 360
+    raw = o.gen_raw(fmt, w, h) if cs != 1 else np.ascontiguousarray(o.gen_image("photo", w, h)).reshape(-1)
+    if fmt == 2:    # planar RGB
+        raw = np.ascontiguousarray(raw.reshape(h, w, 3).transpose(2, 0, 1)).reshape(-1)
+    src, path, dst = tmp_path / "in.raw", tmp_path / "ref.jpg", tmp_path / "out.raw"
+    raw.tofile(src)
+    run_ref("encode_raw", src, fmt, cs, w, h, 85, 6, il, path, 1)
+    ref = np.fromfile(path, np.uint8)
+    want = o.encode_any(raw, w, h, fmt, cs, 85, 6, il, (1, 1), threads=4, internal=o.CS_RGB)
+    assert ref.size == want.size and np.array_equal(ref, want), "oracle restatement != reference GPU library output"
+    import gpujpeg_b200 as g
+    e = g.Encoder()
+    p = g.api.default_parameters(85, 6, il)
+    p.color_space_internal = g.api.GPUJPEG_RGB
+    addr, size = e.encode_raw(raw, p, g.api.image_parameters(w, h, 0, fmt, cs))
+    got = np.ctypeslib.as_array((__import__("ctypes").c_uint8 * size).from_address(addr)).copy()
+    assert np.array_equal(got, ref), "product != reference GPU library output"
+    e.close()
+    run_ref("decode_fmt", path, cs, fmt, dst)
+    pix = np.fromfile(dst, np.uint8)
+    assert np.array_equal(pix, o.decode_any(ref, fmt, cs, o.IDCT_FLOAT_GPUREF, threads=4)), "oracle != reference GPU decoder"
+    d = g.Decoder(idct="float_gpuref")
+    d.set_output_format(cs, fmt)
+    out, _ = d.decode_samples(ref)
+    assert np.array_equal(out, pix), "product decode != reference GPU decoder"
+    d.close()
