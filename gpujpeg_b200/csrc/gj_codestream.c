@@ -230,7 +230,30 @@ size_t gj_write_header(uint8_t* out, const struct gpujpeg_parameters* param,
 {
     uint8_t* p = out;
     p = wmark(p, 0xD8);
-    if ( param->color_space_internal == GPUJPEG_RGB ) {
+    if ( param->color_space_internal == GPUJPEG_YCBCR_BT601 || param->color_space_internal == GPUJPEG_YCBCR_BT709 ) {
+        /* SPIFF (T.84) names the colour space: APP8 "SPIFF\0" header, end-of-directory entry, second SOI
+         * [ref: src/gpujpeg_writer.c:171-245] */
+        p = wmark(p, 0xE8);
+        p = w16(p, 32);
+        memcpy(p, "SPIFF", 6);
+        p += 6;
+        p = w16(p, 0x100);                                                     /* version 1.00 */
+        p = w8(p, 0);                                                          /* no profile */
+        p = w8(p, param->comp_count);
+        p = w16(p, 0); p = w16(p, pi->height);
+        p = w16(p, 0); p = w16(p, pi->width);
+        p = w8(p, param->color_space_internal == GPUJPEG_YCBCR_BT709 ? 1 : 4);
+        p = w8(p, 8);                                                          /* bits per sample */
+        p = w8(p, 5);                                                          /* compression: JPEG */
+        p = w8(p, 0);                                                          /* resolution units: ratio */
+        p = w16(p, 0); p = w16(p, 1);
+        p = w16(p, 0); p = w16(p, 1);
+        p = wmark(p, 0xE8);
+        p = w16(p, 8);
+        p = w16(p, 0); p = w16(p, 1);                                          /* end of directory */
+        p = wmark(p, 0xD8);
+    }
+    else if ( param->color_space_internal == GPUJPEG_RGB ) {
         /* Adobe APP14, transform 0 [ref: src/gpujpeg_writer.c:258-276] */
         p = wmark(p, 0xEE);
         p = w16(p, 14);
@@ -303,6 +326,12 @@ size_t gj_write_header(uint8_t* out, const struct gpujpeg_parameters* param,
     p = w16(p, 2 + n + 1);
     memcpy(p, com, (size_t)n + 1);
     p += n + 1;
+    if ( param->color_space_internal == GPUJPEG_YCBCR_BT601 ) {   /* [ref: src/gpujpeg_writer.c:513-515] */
+        p = wmark(p, 0xFE);
+        p = w16(p, 2 + 10);
+        memcpy(p, "CS=ITU601", 10);
+        p += 10;
+    }
     return (size_t)(p - out);
 }
 
@@ -395,6 +424,21 @@ int gj_reader_walk(const uint8_t* d, size_t size, size_t* pos, struct gj_stream*
         switch ( m ) {
             case 0xE0:
                 if ( n >= 5 && memcmp(b, "JFIF", 5) == 0 ) s->header_type = GPUJPEG_HEADER_JFIF;
+                break;
+            case 0xE8:   /* SPIFF header: colour space code [ref: src/gpujpeg_reader.c:393-443, 504-543] */
+                if ( len == 32 && memcmp(b, "SPIFF", 6) == 0 && s->header_type != GPUJPEG_HEADER_SPIFF ) {
+                    s->header_type = GPUJPEG_HEADER_SPIFF;
+                    switch ( b[18] ) {
+                        case 1: s->spiff_color_space = GPUJPEG_YCBCR_BT709; break;
+                        case 3: case 8: s->spiff_color_space = GPUJPEG_YCBCR_BT601_256LVLS; break;
+                        case 4: s->spiff_color_space = GPUJPEG_YCBCR_BT601; break;
+                        case 10: s->spiff_color_space = GPUJPEG_RGB; break;
+                        case 2: break;
+                        default:
+                            GJ_ERR("Unsupported or unrecongnized SPIFF color space %d!\n", b[18]);
+                            return -1;
+                    }
+                }
                 break;
             case 0xEE:
                 if ( n >= 12 && memcmp(b, "Adobe", 5) == 0 ) {
@@ -525,6 +569,17 @@ void gj_reader_begin(struct gj_stream* s)
     s->header_type = GPUJPEG_HEADER_DEFAULT;
 }
 
+/* colour space of the components from what the markers seen so far say: a SPIFF header names it; Adobe transform 0
+ * or component ids 'R','G','B' mean RGB; otherwise YCbCr JPEG [ref: src/gpujpeg_reader.c:264-640, 1660-1700] */
+enum gpujpeg_color_space gj_stream_color_space(const struct gj_stream* s, int adobe_transform)
+{
+    if ( s->spiff_color_space != GPUJPEG_NONE && s->comp_count != 1 ) return (enum gpujpeg_color_space)s->spiff_color_space;
+    if ( s->comp_count == 3 &&
+         (adobe_transform == 0 || (s->comp_id[0] == 'R' && s->comp_id[1] == 'G' && s->comp_id[2] == 'B')) )
+        return GPUJPEG_RGB;
+    return GPUJPEG_YCBCR_BT601_256LVLS;
+}
+
 /* colour space detection subset [ref: src/gpujpeg_reader.c:264-640]: Adobe transform 0 or component ids
  * 'R','G','B' => RGB; everything else => YCbCr JPEG (full range BT.601) */
 int gj_reader_finish(struct gj_stream* s, int adobe_transform, int verbose)
@@ -533,9 +588,7 @@ int gj_reader_finish(struct gj_stream* s, int adobe_transform, int verbose)
         GJ_ERR("JPEG data contains no image!\n");
         return -1;
     }
-    if ( s->comp_count == 3 &&
-         (adobe_transform == 0 || (s->comp_id[0] == 'R' && s->comp_id[1] == 'G' && s->comp_id[2] == 'B')) )
-        s->color_space = GPUJPEG_RGB;
+    s->color_space = gj_stream_color_space(s, adobe_transform);
     s->interleaved = s->scan[0].ncomp > 1;
     GJ_DEBUG(verbose, "parsed %dx%d, %d comps, %d scans, rst %d\n", s->width, s->height, s->comp_count,
              s->scan_count, s->restart_interval);

@@ -357,11 +357,9 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
         p.sampling_factor[c].horizontal = (uint8_t)(st.comp_hv[c] >> 4);
         p.sampling_factor[c].vertical = (uint8_t)(st.comp_hv[c] & 15);
     }
-    /* colour space of the components: Adobe APP14 / component ids seen so far decide (the same rule gj_reader_finish
+    /* colour space of the components: SPIFF header / Adobe APP14 / component ids seen so far decide (the same rule gj_reader_finish
      * applies at the end; a stream that changes its mind after the first SOS is refused below) */
-    const enum gpujpeg_color_space early_cs =
-        (st.comp_count == 3 && (adobe == 0 || (st.comp_id[0] == 'R' && st.comp_id[1] == 'G' && st.comp_id[2] == 'B')))
-            ? GPUJPEG_RGB : GPUJPEG_YCBCR_BT601_256LVLS;
+    const enum gpujpeg_color_space early_cs = gj_stream_color_space(&st, adobe);
     st.color_space = early_cs;
     p.color_space_internal = early_cs;
     struct gpujpeg_image_parameters pi;

@@ -213,11 +213,17 @@ static int params_supported(const struct gpujpeg_parameters* p, const struct gpu
         GJ_ERR("segment_info headers are not implemented in this build.\n");
         return GJ_IN_UNSUPPORTED;
     }
-    /* YCbCr JPEG (JFIF header) or RGB (Adobe APP14 header, every component coded with the luminance tables); the
-     * limited-range spaces would need the SPIFF header [ref: src/gpujpeg_writer.c:456-475] */
-    if ( p->color_space_internal != GPUJPEG_YCBCR_BT601_256LVLS && !(p->color_space_internal == GPUJPEG_RGB && p->comp_count == 3) ) {
-        GJ_ERR("This build encodes to the internal color spaces %s and %s only.\n",
-               gpujpeg_color_space_get_name(GPUJPEG_YCBCR_BT601_256LVLS), gpujpeg_color_space_get_name(GPUJPEG_RGB));
+    /* YCbCr JPEG (JFIF header), RGB (Adobe APP14 header, every component coded with the luminance tables), or the
+     * limited-range YCbCr spaces BT.601 / BT.709 (SPIFF header) [ref: src/gpujpeg_writer.c:456-475] */
+    if ( p->color_space_internal != GPUJPEG_YCBCR_BT601_256LVLS &&
+         !(p->comp_count == 3 && (p->color_space_internal == GPUJPEG_RGB || p->color_space_internal == GPUJPEG_YCBCR_BT601 ||
+                                  p->color_space_internal == GPUJPEG_YCBCR_BT709)) ) {
+        GJ_ERR("Internal color space %s is not taken by this build.\n", gpujpeg_color_space_get_name(p->color_space_internal));
+        return GJ_IN_UNSUPPORTED;
+    }
+    if ( pi->color_space == GPUJPEG_YCBCR_BT601 && p->color_space_internal == GPUJPEG_YCBCR_BT709 ) {
+        /* the reference converts this pair with the full-range matrix (src/gpujpeg_colorspace.h:386-394); not restated */
+        GJ_ERR("BT.601 input into a BT.709-internal JPEG is not taken by this build.\n");
         return GJ_IN_UNSUPPORTED;
     }
     if ( p->comp_count != 3 && p->comp_count != 1 ) {

@@ -176,6 +176,7 @@ struct gj_stream {
     int scan_count;
     struct gj_scan_info scan[GJ_MAX_COMP];
     enum gpujpeg_color_space color_space;
+    int spiff_color_space;   /* colour space named by a SPIFF header, GPUJPEG_NONE (0) if there is none */
     enum gpujpeg_header_type header_type;
     const char* comment;
     size_t header_size;
@@ -185,6 +186,7 @@ struct gj_stream {
 void gj_reader_begin(struct gj_stream* s);
 int gj_reader_walk(const uint8_t* data, size_t size, size_t* pos, struct gj_stream* s, int* adobe_transform);
 int gj_reader_finish(struct gj_stream* s, int adobe_transform, int verbose);
+enum gpujpeg_color_space gj_stream_color_space(const struct gj_stream* s, int adobe_transform);
 /* parse all markers; does not split scans into segments */
 int gj_reader_parse(const uint8_t* data, size_t size, struct gj_stream* s, int verbose);
 /* split scan data at RSTn markers: fills seg_off/seg_len (file offsets of stuffed entropy bytes) */

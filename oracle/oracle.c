@@ -645,6 +645,10 @@ static inline uint8_t* putm(uint8_t* p, int m) { *p++ = 0xFF; *p++ = (uint8_t)m;
 /* RGB-internal streams: Adobe APP14 (transform 0) instead of JFIF, component ids 'R','G','B', every component coded with
  * the luminance tables [ref: src/gpujpeg_writer.c:255-276, 305-313, 462-470; src/gpujpeg_common.c:689-692] */
 static int g_rgb_internal = 0;
+/* limited-range YCbCr internal colour spaces: SPIFF header naming the space (T.84 code 4 = BT.601, 1 = BT.709), a
+ * second SOI behind the end-of-directory entry, and a "CS=ITU601" comment for BT.601
+ * [ref: src/gpujpeg_writer.c:171-245, 462-466, 513-515] */
+static int g_spiff_cs = 0;
 
 size_t orc_write_header(uint8_t* out, int w, int h, int quality, int rst, int comp_count)
 {
@@ -652,7 +656,26 @@ size_t orc_write_header(uint8_t* out, int w, int h, int quality, int rst, int co
     orc_quant_tables(quality, raw, NULL, NULL);
     uint8_t* p = out;
     p = putm(p, 0xD8);
-    if ( g_rgb_internal ) {
+    if ( g_spiff_cs ) {
+        p = putm(p, 0xE8);
+        p = put16(p, 32);
+        memcpy(p, "SPIFF", 6);
+        p += 6;
+        p = put16(p, 0x100);
+        p = put8(p, 0);
+        p = put8(p, comp_count);
+        p = put16(p, 0); p = put16(p, h);
+        p = put16(p, 0); p = put16(p, w);
+        p = put8(p, g_spiff_cs);
+        p = put8(p, 8); p = put8(p, 5); p = put8(p, 0);
+        p = put16(p, 0); p = put16(p, 1);
+        p = put16(p, 0); p = put16(p, 1);
+        p = putm(p, 0xE8);
+        p = put16(p, 8);
+        p = put16(p, 0); p = put16(p, 1);
+        p = putm(p, 0xD8);
+    }
+    else if ( g_rgb_internal ) {
         p = putm(p, 0xEE);
         p = put16(p, 14);
         memcpy(p, "Adobe", 5);
@@ -726,6 +749,12 @@ size_t orc_write_header(uint8_t* out, int w, int h, int quality, int rst, int co
     p = put16(p, 2 + len + 1);
     memcpy(p, com, len + 1);
     p += len + 1;
+    if ( g_spiff_cs == 4 ) {
+        p = putm(p, 0xFE);
+        p = put16(p, 12);
+        memcpy(p, "CS=ITU601", 10);
+        p += 10;
+    }
     return (size_t)(p - out);
 }
 
@@ -1224,7 +1253,7 @@ size_t orc_encode_any(const uint8_t* raw, int w, int h, int fmt, int cs, int qua
 size_t orc_encode_any2(const uint8_t* raw, int w, int h, int fmt, int cs, int internal, int quality, int rst, int interleaved,
                        int lhs, int lvs, int threads, uint8_t* out)
 {
-    if ( internal != CS_601_256 && internal != CS_RGB ) return 0;
+    if ( internal != CS_601_256 && internal != CS_RGB && internal != CS_601 && internal != CS_709 ) return 0;
     if ( w <= 0 || h <= 0 || w > 65535 || h > 65535 || rst < 0 || rst > 65535 ) return 0;
     struct rawcomp rc[3];
     int fhs[4], fvs[4];
@@ -1258,8 +1287,9 @@ size_t orc_encode_any2(const uint8_t* raw, int w, int h, int fmt, int cs, int in
             }
         }
     g_rgb_internal = internal == CS_RGB;
+    g_spiff_cs = internal == CS_601 ? 4 : internal == CS_709 ? 1 : 0;
     size_t n = encode_from_planes(planes, g, comps, hs, vs, w, h, quality, rst, interleaved, out, coef);
-    g_rgb_internal = 0;
+    g_rgb_internal = g_spiff_cs = 0;
 #ifdef _OPENMP
     omp_set_num_threads(saved_threads);
 #endif
@@ -1384,6 +1414,7 @@ struct parsed {
     uint8_t hvals[2][4][256];
     int comp_id[4], comp_tq[4], comp_hv[4];
     int adobe_transform;   /* -1: no APP14 Adobe segment */
+    int spiff_cs;          /* colour space code of a SPIFF header, 0 if none */
     int nscan;
     struct {
         int ncomp, comp[4], td[4], ta[4];
@@ -1452,6 +1483,9 @@ static int parse_stream(const uint8_t* j, size_t size, struct parsed* P)
         }
         else if ( m == 0xDD ) {
             P->rst = rd16(d);
+        }
+        else if ( m == 0xE8 && len == 32 && memcmp(d, "SPIFF", 6) == 0 && !P->spiff_cs ) {
+            P->spiff_cs = d[18];   /* [ref: src/gpujpeg_reader.c:393-443] */
         }
         else if ( m == 0xEE && len >= 14 && memcmp(d, "Adobe", 5) == 0 ) {
             P->adobe_transform = d[11];   /* [ref: src/gpujpeg_reader.c:560-640] */
@@ -1707,8 +1741,10 @@ int orc_decode_any(const uint8_t* jpeg, size_t size, int idct_flavour, int threa
     (void)threads;
 #endif
     /* colour space of the components: Adobe transform 0 or ids 'R','G','B' mean RGB [ref: src/gpujpeg_reader.c:264-640] */
-    const int stream_cs = (P.comps == 3 && (P.adobe_transform == 0 || (P.comp_id[0] == 'R' && P.comp_id[1] == 'G' && P.comp_id[2] == 'B')))
-                              ? CS_RGB : CS_601_256;
+    int stream_cs = (P.comps == 3 && (P.adobe_transform == 0 || (P.comp_id[0] == 'R' && P.comp_id[1] == 'G' && P.comp_id[2] == 'B')))
+                        ? CS_RGB : CS_601_256;
+    if ( P.comps == 3 && P.spiff_cs )
+        stream_cs = P.spiff_cs == 1 ? CS_709 : P.spiff_cs == 4 ? CS_601 : P.spiff_cs == 10 ? CS_RGB : CS_601_256;
     struct ogeo g[4];
     int max_hs, max_vs;
     uint8_t* planes = decode_to_planes(&P, jpeg, idct_flavour, g, &max_hs, &max_vs, NULL, 1);

@@ -137,6 +137,7 @@ int ref_huff_encoder_table(int cls, int kind, uint32_t code[256], uint8_t size[2
  * [ref: src/gpujpeg_encoder.c:504-534, 626; src/gpujpeg_writer.c:456-518;
  *       src/gpujpeg_huffman_cpu_encoder.c:296-376] */
 static int g_internal_rgb = 0;   /* components of an RGB-internal JPEG are all of the luminance type */
+static int g_internal_cs = 0;    /* other internal colour space (enum gpujpeg_color_space), 0 = YCbCr JPEG */
 
 size_t ref_encode_from_coef_ss(int16_t* coef, int w, int h, int comps, int quality, int rst, int interleaved, int lhs,
                                int lvs, uint8_t* out, size_t out_cap)
@@ -155,7 +156,8 @@ size_t ref_encode_from_coef_ss(int16_t* coef, int w, int h, int comps, int quali
         enc->coder.param.sampling_factor[c].horizontal = c == 0 ? lhs : 1;
         enc->coder.param.sampling_factor[c].vertical = c == 0 ? lvs : 1;
     }
-    enc->coder.param.color_space_internal = g_internal_rgb ? GPUJPEG_RGB : GPUJPEG_YCBCR_BT601_256LVLS;
+    enc->coder.param.color_space_internal = g_internal_rgb ? GPUJPEG_RGB : g_internal_cs ? (enum gpujpeg_color_space)g_internal_cs
+                                                                                         : GPUJPEG_YCBCR_BT601_256LVLS;
     if ( g_internal_rgb )
         for ( int c = 0; c < comps; c++ )
             g.comp[c].type = GPUJPEG_COMPONENT_LUMINANCE;   /* [ref: src/gpujpeg_common.c:689-692] */
@@ -200,6 +202,16 @@ size_t ref_encode_from_coef_rgb(int16_t* coef, int w, int h, int quality, int rs
     g_internal_rgb = 1;
     size_t n = ref_encode_from_coef_ss(coef, w, h, 3, quality, rst, interleaved, lhs, lvs, out, out_cap);
     g_internal_rgb = 0;
+    return n;
+}
+
+/* the same for the limited-range internal colour spaces (SPIFF header): cs = GPUJPEG_YCBCR_BT601 or _BT709 */
+size_t ref_encode_from_coef_cs(int16_t* coef, int w, int h, int quality, int rst, int interleaved, int lhs, int lvs, int cs,
+                               uint8_t* out, size_t out_cap)
+{
+    g_internal_cs = cs;
+    size_t n = ref_encode_from_coef_ss(coef, w, h, 3, quality, rst, interleaved, lhs, lvs, out, out_cap);
+    g_internal_cs = 0;
     return n;
 }
 

@@ -291,4 +291,7 @@ if os.path.exists(_REF_SO):
     ref.ref_encode_from_coef_rgb.argtypes = [_i16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p,
                                              C.c_size_t]
     ref.ref_encode_from_coef_rgb.restype = C.c_size_t
+    ref.ref_encode_from_coef_cs.argtypes = [_i16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p,
+                                            C.c_size_t]
+    ref.ref_encode_from_coef_cs.restype = C.c_size_t
     ref.ref_idct_block.argtypes = [_i16p, np.ctypeslib.ndpointer(np.uint16)]

@@ -328,9 +328,9 @@ def test_unsupported_parameters_fail_loudly(gj, enc):
     with pytest.raises(gj.GpuJpegError):
         enc.encode_raw(img, p, pi)
     p = gj.api.default_parameters()
-    p.color_space_internal = gj.api.GPUJPEG_YCBCR_BT709   # limited-range internal spaces would need the SPIFF header
+    p.color_space_internal = gj.api.GPUJPEG_YCBCR_BT709   # this pair is converted with the wrong matrix by the reference
     with pytest.raises(gj.GpuJpegError):
-        enc.encode_raw(np.zeros((64, 64, 3), np.uint8), p, gj.api.image_parameters(64, 64))
+        enc.encode_raw(np.zeros((64, 64, 3), np.uint8), p, gj.api.image_parameters(64, 64, 0, 1, gj.api.GPUJPEG_YCBCR_BT601))
     p = gj.api.default_parameters()
     p.segment_info = 1
     with pytest.raises(gj.GpuJpegError):
@@ -441,5 +441,32 @@ def test_rgb_internal_jpeg(gj, enc, il, sub):
         assert np.array_equal(d.decode(want).reshape(-1), o.decode_any(want, o.FMT_444_P012, o.CS_RGB, threads=4))
         d.set_output_format(gj.api.GPUJPEG_YCBCR_BT709, o.FMT_444_P0P1P2)
         assert np.array_equal(d.decode_samples(want)[0], o.decode_any(want, o.FMT_444_P0P1P2, o.CS_709, threads=4))
+    finally:
+        d.close()
+
+
+@pytest.mark.parametrize("internal,fmt,cs,sub,il", [(o.CS_709, o.FMT_422_P1020, o.CS_709, None, 1),      # UYVY BT.709 video, untransformed
+                                                    (o.CS_709, o.FMT_444_P012, o.CS_RGB, "4:2:0", 1),     # RGB -> BT.709
+                                                    (o.CS_601, o.FMT_420_P0P1P2, o.CS_JPEG, None, 0),     # JPEG range -> BT.601
+                                                    (o.CS_601, o.FMT_444_P012, o.CS_601, None, 0)])
+def test_limited_range_internal_colour_spaces(gj, enc, internal, fmt, cs, sub, il):
+    """color_space_internal = BT.601 / BT.709 (SPIFF header names the space): bytes against the oracle; the decoder
+    reads the space from the SPIFF header and converts to what is asked for"""
+    w, h = 320, 200
+    raw = o.gen_raw(fmt, w, h)
+    samp = SUB[sub] or o.FMT_SAMPLING[fmt]
+    want = o.encode_any(raw, w, h, fmt, cs, 85, 6, il, samp, threads=4, internal=internal)
+    p = gj.api.default_parameters(85, 6, il, sub or "4:4:4")
+    if sub is None:
+        p.comp_count = 0          # sampling from the pixel format
+    p.color_space_internal = internal
+    addr, size = enc.encode_raw(raw, p, gj.api.image_parameters(w, h, 0, fmt, cs))
+    got = np.ctypeslib.as_array((__import__("ctypes").c_uint8 * size).from_address(addr)).copy()
+    assert got.size == want.size and np.array_equal(got, want)
+    d = gj.Decoder()
+    try:
+        assert np.array_equal(d.decode(want).reshape(-1), o.decode_any(want, o.FMT_444_P012, o.CS_RGB, threads=4))   # default: RGB
+        d.set_output_format(cs, fmt)
+        assert np.array_equal(d.decode_samples(want)[0], o.decode_any(want, fmt, cs, threads=4))
     finally:
         d.close()

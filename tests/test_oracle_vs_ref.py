@@ -84,6 +84,24 @@ def test_rgb_internal_stream_bytes(il, sampling):
     assert np.abs(back - img).mean() < 12
 
 
+@pytest.mark.parametrize("internal,il,sampling", [(o.CS_709, 1, (2, 1)), (o.CS_601, 0, (1, 1)), (o.CS_709, 1, (2, 2))])
+def test_spiff_stream_bytes(internal, il, sampling):
+    """BT.601 / BT.709 internal colour space: SPIFF APP8 header + end-of-directory + second SOI (and the CS=ITU601
+    comment) -- oracle bytes against the reference's header writer + CPU Huffman encoder on the same coefficients
+    [ref: src/gpujpeg_writer.c:171-245, 462-466, 513-515]"""
+    w, h, q, rst = 100, 60, 85, 5
+    img = o.gen_image("photo", w, h)
+    jpeg = o.encode_any(img, w, h, o.FMT_444_P012, o.CS_RGB, q, rst, il, sampling, internal=internal)
+    assert jpeg[2:4].tobytes() == b"\xff\xe8" and jpeg[6:12].tobytes() == b"SPIFF\x00"
+    _, coef = o.decode(jpeg, want_coef=True)          # coefficients only; the pixels of o.decode assume YCbCr JPEG
+    out = np.empty(4096 + coef.size * 8, np.uint8)
+    n = o.ref.ref_encode_from_coef_cs(np.ascontiguousarray(coef).reshape(-1), w, h, q, rst, il, sampling[0], sampling[1],
+                                      internal, out, out.size)
+    assert n > 0 and np.array_equal(out[:n], jpeg)
+    back = o.decode_any(jpeg, o.FMT_444_P012, o.CS_RGB).reshape(h, w, 3).astype(int)
+    assert np.abs(back - img).mean() < 12
+
+
 def test_subsampled_chroma_is_point_sampled():
     """the preprocessor keeps every second chroma sample unfiltered and the postprocessor replicates it
     [ref: src/gpujpeg_preprocessor.cu:50-64, src/gpujpeg_postprocessor.cu:55-76]: an image whose colour only changes

@@ -142,24 +142,26 @@ def test_reference_gpu_colour_spaces(tmp_path, fmt, cs, w, h, il):
 
 
 @pytest.mark.skipif(not os.path.exists(SO), reason="oracle/_ref/libgpujpeg_refgpu.so not built")
-@pytest.mark.parametrize("fmt,cs,il", [(1, 1, 0), (1, 1, 1), (2, 1, 0), (1, 4, 1)])
-def test_reference_gpu_rgb_internal_jpeg(tmp_path, fmt, cs, il):
-    """color_space_internal = GPUJPEG_RGB (Adobe APP14 header, luminance tables for every component): reference GPU
-    encoder bytes == oracle == product; reference GPU decoder == oracle == product for the same output request"""
+@pytest.mark.parametrize("fmt,cs,il,internal", [(1, 1, 0, 1), (1, 1, 1, 1), (2, 1, 0, 1), (1, 4, 1, 1), (3, 4, 1, 4), (1, 1, 0, 4),
+                                                (5, 3, 1, 2), (1, 2, 0, 2)])
+def test_reference_gpu_rgb_internal_jpeg(tmp_path, fmt, cs, il, internal):
+    """color_space_internal = GPUJPEG_RGB (Adobe APP14 header, luminance tables for every component) or BT.601 / BT.709
+    (SPIFF header): reference GPU encoder bytes == oracle == product; reference GPU decoder == oracle == product for
+    the same output request"""
     w, h = 640, 360
     raw = o.gen_raw(fmt, w, h) if cs != 1 else np.ascontiguousarray(o.gen_image("photo", w, h)).reshape(-1)
     if fmt == 2:    # planar RGB
         raw = np.ascontiguousarray(raw.reshape(h, w, 3).transpose(2, 0, 1)).reshape(-1)
     src, path, dst = tmp_path / "in.raw", tmp_path / "ref.jpg", tmp_path / "out.raw"
     raw.tofile(src)
-    run_ref("encode_raw", src, fmt, cs, w, h, 85, 6, il, path, 1)
+    run_ref("encode_raw", src, fmt, cs, w, h, 85, 6, il, path, internal)
     ref = np.fromfile(path, np.uint8)
-    want = o.encode_any(raw, w, h, fmt, cs, 85, 6, il, (1, 1), threads=4, internal=o.CS_RGB)
+    want = o.encode_any(raw, w, h, fmt, cs, 85, 6, il, o.FMT_SAMPLING[fmt], threads=4, internal=internal)
     assert ref.size == want.size and np.array_equal(ref, want), "oracle restatement != reference GPU library output"
     import gpujpeg_b200 as g
     e = g.Encoder()
     p = g.api.default_parameters(85, 6, il)
-    p.color_space_internal = g.api.GPUJPEG_RGB
+    p.color_space_internal = internal
     addr, size = e.encode_raw(raw, p, g.api.image_parameters(w, h, 0, fmt, cs))
     got = np.ctypeslib.as_array((__import__("ctypes").c_uint8 * size).from_address(addr)).copy()
     assert np.array_equal(got, ref), "product != reference GPU library output"
