@@ -45,6 +45,7 @@ hs.shim_enc_lut.argtypes = [C.c_int, np.ctypeslib.ndpointer(np.uint32), np.ctype
 hs.shim_dec_lut_symbol.argtypes = [C.c_int, C.c_int, C.c_uint, C.POINTER(C.c_int)]
 hs.shim_parse.argtypes = [_u8p, C.c_size_t, np.ctypeslib.ndpointer(np.int32), np.ctypeslib.ndpointer(np.uint32),
                           np.ctypeslib.ndpointer(np.uint32), C.c_int]
+hs.shim_header2.argtypes = [C.c_int] * 9 + [np.ctypeslib.ndpointer(np.uint8)]
 hs.shim_raw_layout.argtypes = [C.c_int] * 4 + [np.ctypeslib.ndpointer(np.int64)]
 hs.shim_geometry.argtypes = [C.c_int] * 4 + [np.ctypeslib.ndpointer(np.int64)]
 hs.shim_geometry_ss.argtypes = [C.c_int] * 6 + [np.ctypeslib.ndpointer(np.int64)]

@@ -161,3 +161,34 @@ int shim_raw_layout(int fmt, int width, int height, int pad, long* out /*[17]*/)
     }
     return 0;
 }
+
+/* header + first SOS for any component count, sampling and internal colour space (JFIF / Adobe / SPIFF flavours) */
+int shim_header2(int width, int height, int quality, int rst, int interleaved, int comps, int lhs, int lvs, int internal,
+                 unsigned char* out)
+{
+    struct gpujpeg_parameters p;
+    struct gpujpeg_image_parameters pi;
+    memset(&p, 0, sizeof p);
+    memset(&pi, 0, sizeof pi);
+    p.quality = quality;
+    p.restart_interval = rst;
+    p.interleaved = interleaved;
+    p.comp_count = comps;
+    for ( int c = 0; c < comps; c++ ) {
+        p.sampling_factor[c].horizontal = (uint8_t)(c == 0 ? lhs : 1);
+        p.sampling_factor[c].vertical = (uint8_t)(c == 0 ? lvs : 1);
+    }
+    p.color_space_internal = (enum gpujpeg_color_space)internal;
+    pi.width = width;
+    pi.height = height;
+    uint8_t raw[2][64];
+    struct gj_huff_spec spec[2][2];
+    for ( int t = 0; t < 2; t++ ) {
+        gj_quant_raw(t, quality, raw[t]);
+        for ( int k = 0; k < 2; k++ )
+            gj_huff_spec_default(t, k, &spec[t][k]);
+    }
+    size_t n = gj_write_header(out, &p, &pi, raw, spec);
+    n += gj_write_sos(out + n, &p, 0);
+    return (int)n;
+}

@@ -178,3 +178,21 @@ def test_raw_layout_refuses_what_is_ambiguous():
     assert hs.shim_raw_layout(o.FMT_420_P0P1P2, 32, 16, 4, out) == -1     # row padding of planar formats
     assert hs.shim_raw_layout(6, 32, 16, 0, out) == -1                     # 4 components
     assert hs.shim_raw_layout(o.FMT_444_P012, 33, 17, 5, out) == 0 and out[3] == 3 * 33 + 5
+
+
+@pytest.mark.parametrize("internal,fmt,il,samp", [(o.CS_JPEG, o.FMT_U8, 0, (1, 1)), (o.CS_JPEG, o.FMT_444_P012, 1, (2, 2)),
+                                                  (o.CS_RGB, o.FMT_444_P012, 0, (1, 1)), (o.CS_RGB, o.FMT_444_P012, 1, (2, 1)),
+                                                  (o.CS_601, o.FMT_444_P012, 1, (2, 2)), (o.CS_709, o.FMT_444_P012, 0, (1, 2))])
+def test_header_flavours_match_oracle_streams(internal, fmt, il, samp):
+    """the host writer's JFIF / Adobe APP14 / SPIFF headers, SOF0 sampling factors, table selectors and the first SOS
+    against the first bytes of an oracle stream of the same parameters (the oracle's headers are pinned against the
+    reference writer in tests/test_oracle_vs_ref.py)"""
+    w, h, q, rst = 70, 50, 80, 3
+    comps = 1 if fmt == o.FMT_U8 else 3
+    if comps == 1:
+        jpeg = o.encode_ycc(o.gen_raw(fmt, w, h), w, h, fmt, q, rst, 0)
+    else:
+        jpeg = o.encode_any(o.gen_image("photo", w, h), w, h, fmt, o.CS_RGB, q, rst, il, samp, internal=internal)
+    mine = np.zeros(4096, np.uint8)
+    n = hs.shim_header2(w, h, q, rst, il, comps, samp[0], samp[1], internal, mine)
+    assert n > 300 and np.array_equal(mine[:n], jpeg[:n])
