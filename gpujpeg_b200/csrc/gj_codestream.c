@@ -33,6 +33,16 @@ int gj_raw_layout_init(struct gj_raw_layout* l, const struct gpujpeg_image_param
                 l->comp[c] = (struct gj_raw_comp){(size_t)c, 3 * w + pad, 3};
             l->size = (3 * w + pad) * h;
             return 0;
+        case GPUJPEG_4444_U8_P0123:
+            /* three colour samples + alpha per pixel; a 3-component JPEG (what comp_count = 0 gives,
+             * src/gpujpeg_encoder.c:325-327) ignores the alpha on the way in and gets 255 on the way out
+             * [ref: src/gpujpeg_postprocessor.cu:122-131] */
+            l->comp_count = 3;
+            for ( int c = 0; c < 3; c++ )
+                l->comp[c] = (struct gj_raw_comp){(size_t)c, 4 * w + pad, 4};
+            l->alpha_off = 3;
+            l->size = (4 * w + pad) * h;
+            return 0;
         default: break;
     }
     /* planar and packed 4:2:2 formats: plane pitches with row padding are not pinned down by the reference's size

@@ -29,6 +29,7 @@ struct ConvertParams {
     int xs[3], rdh[3], rdv[3];
     int raw_comps;          /* 1: grey */
     int uyvy;               /* 422-u8-p1020: U is stored by even pixels, V by odd pixels */
+    int alpha_off;          /* 4444-u8-p0123: offset of the alpha byte inside a pixel, 0 = none */
     /* component planes of the JPEG: sample (x, y) of component c at poff + y * ppitch + x; a pixel contributes to /
      * reads from plane c at (x / pdh, y / pdv) */
     unsigned long long poff[3];
@@ -96,6 +97,7 @@ k_convert_out(const uint8_t* __restrict__ planes, uint8_t* __restrict__ raw, con
         c[k] = planes[p.poff[k] + (size_t)(y / p.pdv[k]) * p.ppitch[k] + x / p.pdh[k]];
     if ( p.jpeg_comps == 3 ) cs_transform(p.cs_internal, p.cs, c);
     raw[p.off[0] + (size_t)y * p.pitch[0] + (size_t)x * p.xs[0]] = (uint8_t)c[0];
+    if ( p.alpha_off ) raw[p.off[0] + (size_t)y * p.pitch[0] + (size_t)x * p.xs[0] + p.alpha_off] = 0xFF;
     if ( p.raw_comps == 1 ) return;
     if ( p.uyvy ) {
         const int k = (x & 1) ? 2 : 1;
@@ -118,6 +120,7 @@ int fill_params(ConvertParams* p, const struct gj_raw_layout* raw, enum gpujpeg_
     if ( color_space < GPUJPEG_NONE || color_space > GPUJPEG_YCBCR_BT709 ) return -1;
     p->raw_comps = raw->comp_count;
     p->uyvy = fmt == GPUJPEG_422_U8_P1020;
+    p->alpha_off = raw->alpha_off;
     for ( int k = 0; k < 3; k++ ) {
         const int r = k < raw->comp_count ? k : 0;
         p->off[k] = raw->comp[r].off;

@@ -265,7 +265,7 @@ static int choose_output(const struct gpujpeg_decoder* d, const struct gj_stream
                pi->height);
         return 0;
     }
-    if ( cs != st->color_space || rl.sampling[0].horizontal != lh || rl.sampling[0].vertical != lv ) {
+    if ( cs != st->color_space || rl.sampling[0].horizontal != lh || rl.sampling[0].vertical != lv || rl.alpha_off ) {
         if ( (pi->width & 1) && rl.sampling[0].horizontal == 2 && pf != GPUJPEG_420_U8_P0P1P2 ) {
             GJ_ERR("Odd widths are only produced without colour / sampling conversion for this pixel format.\n");
             return 0;

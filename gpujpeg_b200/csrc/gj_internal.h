@@ -144,6 +144,7 @@ struct gj_raw_layout {
     struct gj_raw_comp comp[GJ_MAX_COMP];
     struct gpujpeg_component_sampling_factor sampling[GJ_MAX_COMP];  /* the format's own sampling */
     size_t size;   /* bytes of the whole image */
+    int alpha_off; /* 4444-u8-p0123: byte offset of the alpha sample inside a pixel (ignored on input, 255 on output); 0 = none */
 };
 /* 0 on success, -1 for a format/size combination this build does not take */
 int gj_raw_layout_init(struct gj_raw_layout* l, const struct gpujpeg_image_parameters* pi);

@@ -1106,6 +1106,11 @@ static int raw_layout(int fmt, int w, int h, int pad, struct rawcomp rc[3], int 
                 rc[c] = (struct rawcomp){(size_t)c, 3, (size_t)3 * w + pad};
             *size = ((size_t)3 * w + pad) * h;
             return 3;
+        case 6:   /* 4444-u8-p0123 as a 3-component image: alpha ignored on input, 255 on output */
+            for ( int c = 0; c < 3; c++ )
+                rc[c] = (struct rawcomp){(size_t)c, 4, (size_t)4 * w + pad};
+            *size = ((size_t)4 * w + pad) * h;
+            return 3;
         case 2:
             for ( int c = 0; c < 3; c++ )
                 rc[c] = (struct rawcomp){(size_t)c * ((size_t)w + pad) * h, 1, (size_t)w + pad};
@@ -1762,6 +1767,7 @@ int orc_decode_any(const uint8_t* jpeg, size_t size, int idct_flavour, int threa
                     continue;
                 }
                 raw[rc[0].off + (size_t)y * rc[0].pitch + (size_t)x * rc[0].xs] = (uint8_t)c[0];
+                if ( fmt == 6 ) raw[rc[0].off + (size_t)y * rc[0].pitch + (size_t)x * 4 + 3] = 0xFF;   /* alpha */
                 const int dh = fhs[0], dv = fvs[0];   /* chroma of the format: every dh-th pixel of every dv-th row */
                 if ( fmt == 3 ) {
                     /* U from even pixels, V from odd pixels [ref: src/gpujpeg_preprocessor_common.cuh:179-189] */

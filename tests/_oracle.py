@@ -133,9 +133,9 @@ def encode(rgb, quality=75, rst=24, interleaved=0, threads=1, want_coef=False, p
 
 
 # ---- raw formats that enter the JPEG without a colour transform (grey, planar / packed YCbCr) ----
-FMT_U8, FMT_444_P012, FMT_444_P0P1P2, FMT_422_P1020, FMT_422_P0P1P2, FMT_420_P0P1P2 = range(6)
+FMT_U8, FMT_444_P012, FMT_444_P0P1P2, FMT_422_P1020, FMT_422_P0P1P2, FMT_420_P0P1P2, FMT_4444_P0123 = range(7)
 FMT_SAMPLING = {FMT_U8: (1, 1), FMT_444_P012: (1, 1), FMT_444_P0P1P2: (1, 1), FMT_422_P1020: (2, 1), FMT_422_P0P1P2: (2, 1),
-                FMT_420_P0P1P2: (2, 2)}
+                FMT_420_P0P1P2: (2, 2), FMT_4444_P0123: (1, 1)}
 
 
 def gen_raw(fmt, w, h, seed=777, smooth=True):

@@ -323,7 +323,10 @@ def test_row_padding(enc):
 def test_unsupported_parameters_fail_loudly(gj, enc):
     p = gj.api.default_parameters()
     pi = gj.api.image_parameters(64, 64)
-    pi.pixel_format = 6                      # GPUJPEG_4444_U8_P0123: 4-component images are outside this build
+    pi.pixel_format = 6                      # GPUJPEG_4444_U8_P0123 ...
+    p.comp_count = 4                         # ... as a 4-component JPEG: alpha planes are outside this build
+    for c in range(4):
+        p.sampling_factor[c].horizontal = p.sampling_factor[c].vertical = 1
     img = np.zeros((64, 64, 4), np.uint8)
     with pytest.raises(gj.GpuJpegError):
         enc.encode_raw(img, p, pi)
@@ -468,5 +471,31 @@ def test_limited_range_internal_colour_spaces(gj, enc, internal, fmt, cs, sub, i
         assert np.array_equal(d.decode(want).reshape(-1), o.decode_any(want, o.FMT_444_P012, o.CS_RGB, threads=4))   # default: RGB
         d.set_output_format(cs, fmt)
         assert np.array_equal(d.decode_samples(want)[0], o.decode_any(want, fmt, cs, threads=4))
+    finally:
+        d.close()
+
+
+@pytest.mark.parametrize("il,sub", [(0, None), (1, "4:2:0")])
+def test_rgba_input_and_output(gj, enc, il, sub):
+    """4444-u8-p0123 with the default 3-component JPEG: the alpha sample is ignored on the way in (the stream equals
+    the one made from the same pixels as 444-u8-p012) and comes back as 255 [ref: src/gpujpeg_encoder.c:325-327,
+    src/gpujpeg_postprocessor.cu:122-131]"""
+    w, h = 322, 200
+    img = o.gen_image("photo", w, h)
+    rgba = np.concatenate([img, np.random.default_rng(3).integers(0, 256, (h, w, 1), dtype=np.uint8)], axis=2)
+    samp = SUB[sub] or (1, 1)
+    want = o.encode(img, 80, 6, il, sampling=samp)
+    assert np.array_equal(o.encode_any(rgba, w, h, o.FMT_4444_P0123, o.CS_RGB, 80, 6, il, samp), want)
+    got = enc.encode_samples(np.ascontiguousarray(rgba).reshape(-1), w, h, o.FMT_4444_P0123, 80, 6, il, color_space=o.CS_RGB,
+                             subsampling=sub or "4:4:4")
+    assert np.array_equal(got, want)
+    d = gj.Decoder()
+    try:
+        d.set_output_format(gj.api.GPUJPEG_RGB, o.FMT_4444_P0123)
+        out, pi = d.decode_samples(want)
+        out = out.reshape(h, w, 4)
+        assert pi.pixel_format == o.FMT_4444_P0123
+        assert np.array_equal(out[:, :, :3], o.decode(want)) and np.all(out[:, :, 3] == 255)
+        assert np.array_equal(out.reshape(-1), o.decode_any(want, o.FMT_4444_P0123, o.CS_RGB))
     finally:
         d.close()

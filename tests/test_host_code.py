@@ -176,7 +176,8 @@ def test_raw_layout_refuses_what_is_ambiguous():
     out = np.zeros(17, np.int64)
     assert hs.shim_raw_layout(o.FMT_422_P1020, 33, 16, 0, out) == -1      # odd width of packed 4:2:2
     assert hs.shim_raw_layout(o.FMT_420_P0P1P2, 32, 16, 4, out) == -1     # row padding of planar formats
-    assert hs.shim_raw_layout(6, 32, 16, 0, out) == -1                     # 4 components
+    assert hs.shim_raw_layout(7, 32, 16, 0, out) == -1                     # not a pixel format
+    assert hs.shim_raw_layout(6, 32, 16, 0, out) == 0 and out[0] == 3 and out[1] == 4 * 32 * 16   # RGBA: 3 components + alpha
     assert hs.shim_raw_layout(o.FMT_444_P012, 33, 17, 5, out) == 0 and out[3] == 3 * 33 + 5
 
 

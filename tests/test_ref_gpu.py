@@ -174,3 +174,27 @@ def test_reference_gpu_rgb_internal_jpeg(tmp_path, fmt, cs, il, internal):
     out, _ = d.decode_samples(ref)
     assert np.array_equal(out, pix), "product decode != reference GPU decoder"
     d.close()
+
+
+@pytest.mark.skipif(not os.path.exists(SO), reason="oracle/_ref/libgpujpeg_refgpu.so not built")
+def test_reference_gpu_rgba(tmp_path):
+    """4444-u8-p0123 input / output with the default 3-component JPEG: reference GPU library == oracle == product"""
+    w, h = 640, 360
+    img = o.gen_image("photo", w, h)
+    rgba = np.ascontiguousarray(np.concatenate([img, np.full((h, w, 1), 77, np.uint8)], axis=2)).reshape(-1)
+    src, path, dst = tmp_path / "in.raw", tmp_path / "ref.jpg", tmp_path / "out.raw"
+    rgba.tofile(src)
+    run_ref("encode_raw", src, 6, 1, w, h, 85, 6, 1, path)
+    ref = np.fromfile(path, np.uint8)
+    assert np.array_equal(ref, o.encode_any(rgba, w, h, 6, 1, 85, 6, 1, (1, 1), threads=4)), "oracle != reference GPU library"
+    import gpujpeg_b200 as g
+    e = g.Encoder()
+    assert np.array_equal(e.encode_samples(rgba, w, h, 6, 85, 6, 1, color_space=1), ref), "product != reference GPU library"
+    e.close()
+    run_ref("decode_fmt", path, 1, 6, dst)
+    pix = np.fromfile(dst, np.uint8)
+    assert np.array_equal(pix, o.decode_any(ref, 6, 1, o.IDCT_FLOAT_GPUREF, threads=4)), "oracle != reference GPU decoder"
+    d = g.Decoder(idct="float_gpuref")
+    d.set_output_format(1, 6)
+    assert np.array_equal(d.decode_samples(ref)[0], pix), "product decode != reference GPU decoder"
+    d.close()
