@@ -456,9 +456,15 @@ int gj_reader_walk(const uint8_t* d, size_t size, size_t* pos, struct gj_stream*
                     *adobe_transform = b[11];
                 }
                 break;
-            case 0xFE:
-                s->comment = (const char*)b;
+            case 0xFE: {  /* [ref: src/gpujpeg_reader.c:641-672] */
+                /* FFmpeg's "CS=ITU601" (with or without the terminating NUL): limited-range BT.601, or BT.709 on request */
+                static const char cs_itu601[] = "CS=ITU601";
+                if ( (n == (int)sizeof cs_itu601 || n == (int)sizeof cs_itu601 - 1) && strncmp((const char*)b, cs_itu601, (size_t)n) == 0 )
+                    s->com_color_space = s->ff_cs_itu601_is_709 ? GPUJPEG_YCBCR_BT709 : GPUJPEG_YCBCR_BT601;
+                /* the comment is handed out as a C string: only NUL-terminated ones are kept */
+                if ( n > 0 && b[n - 1] == '\0' ) s->comment = (const char*)b;
                 break;
+            }
             case 0xDB: { /* [ref: src/gpujpeg_reader.c:681-730] 8-bit tables only */
                 int off = 0;
                 while ( off < n ) {
@@ -541,6 +547,10 @@ int gj_reader_walk(const uint8_t* d, size_t size, size_t* pos, struct gj_stream*
                     return -1;
                 }
                 if ( s->scan_count == 0 ) s->header_size = i;
+                if ( n < 6 ) {
+                    GJ_ERR("SOS marker is too short (%d bytes)!\n", len);
+                    return -1;
+                }
                 struct gj_scan_info* sc = &s->scan[s->scan_count++];
                 memset(sc, 0, sizeof *sc);
                 sc->ncomp = b[0];
@@ -572,9 +582,10 @@ int gj_reader_walk(const uint8_t* d, size_t size, size_t* pos, struct gj_stream*
     return 0;
 }
 
-void gj_reader_begin(struct gj_stream* s)
+void gj_reader_begin(struct gj_stream* s, int ff_cs_itu601_is_709)
 {
     memset(s, 0, sizeof *s);
+    s->ff_cs_itu601_is_709 = ff_cs_itu601_is_709;
     s->color_space = GPUJPEG_YCBCR_BT601_256LVLS; /* JFIF default */
     s->header_type = GPUJPEG_HEADER_DEFAULT;
 }
@@ -584,6 +595,7 @@ void gj_reader_begin(struct gj_stream* s)
 enum gpujpeg_color_space gj_stream_color_space(const struct gj_stream* s, int adobe_transform)
 {
     if ( s->spiff_color_space != GPUJPEG_NONE && s->comp_count != 1 ) return (enum gpujpeg_color_space)s->spiff_color_space;
+    if ( s->com_color_space != GPUJPEG_NONE && s->comp_count == 3 ) return (enum gpujpeg_color_space)s->com_color_space;
     if ( s->comp_count == 3 &&
          (adobe_transform == 0 || (s->comp_id[0] == 'R' && s->comp_id[1] == 'G' && s->comp_id[2] == 'B')) )
         return GPUJPEG_RGB;
@@ -609,7 +621,7 @@ int gj_reader_finish(struct gj_stream* s, int adobe_transform, int verbose)
  * functions and the tests; the decoder finds scan extents on the GPU instead, gj_markers.cu) */
 int gj_reader_parse(const uint8_t* d, size_t size, struct gj_stream* s, int verbose)
 {
-    gj_reader_begin(s);
+    gj_reader_begin(s, 0);
     if ( size < 4 || d[0] != 0xFF || d[1] != 0xD8 ) {
         GJ_ERR("JPEG data should begin with SOI marker!\n");
         return -1;

@@ -38,6 +38,7 @@ struct gpujpeg_decoder {
     enum gpujpeg_pixel_format req_pixel_format;
     enum gpujpeg_color_space req_color_space;
     int idct_flavour;
+    int ff_cs_itu601_is_709;      /* [ref: libgpujpeg/gpujpeg_decoder.h:95] */
     int out_mode;                 /* GJ_OUT_RGB, GJ_OUT_SAMPLES or GJ_OUT_GENERIC: which K4 runs */
     uint8_t* d_planes; size_t d_planes_size;   /* component planes between the IDCT and the generic pass */
     struct gj_raw_layout raw;     /* where the samples go (GJ_OUT_SAMPLES) */
@@ -112,6 +113,7 @@ struct gpujpeg_decoder* gpujpeg_decoder_create_with_params(const struct gpujpeg_
     d->stream = (gj_stream_t)params->stream;
     d->verbose = params->verbose;
     d->perf_stats = params->perf_stats;
+    d->ff_cs_itu601_is_709 = params->ff_cs_itu601_is_709;
     d->device = gj_cuda_get_device();
     d->req_pixel_format = GPUJPEG_PIXFMT_AUTODETECT;
     d->req_color_space = GPUJPEG_CS_DEFAULT;
@@ -184,7 +186,12 @@ int gpujpeg_decoder_init(struct gpujpeg_decoder* d, const struct gpujpeg_paramet
 {
     d->verbose = param->verbose;
     d->perf_stats = param->perf_stats || param->verbose >= GPUJPEG_LL_STATUS;
-    if ( param_image->width * param_image->height * param->comp_count == 0 ) return 0;
+    if ( param_image->width <= 0 || param_image->height <= 0 || param->comp_count <= 0 ) return 0;
+    /* stream-supplied dimensions: all index arithmetic below is sized for frames of at most 2^30 pixels */
+    if ( (size_t)param_image->width * (size_t)param_image->height > ((size_t)1 << 30) ) {
+        GJ_ERR("Image size %dx%d exceeds the supported maximum of 2^30 pixels.\n", param_image->width, param_image->height);
+        return -1;
+    }
     struct gpujpeg_parameters p = *param;
     struct gpujpeg_image_parameters pi = *param_image;
     if ( p.comp_count != 3 && p.comp_count != 1 ) {
@@ -310,7 +317,7 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
 
     /* ---- host reader, part 1: marker segments up to the first SOS (never touches entropy-coded data) ---- */
     struct gj_stream st;
-    gj_reader_begin(&st);
+    gj_reader_begin(&st, d->ff_cs_itu601_is_709);
     if ( image_size < 4 || image[0] != 0xFF || image[1] != 0xD8 ) {
         GJ_ERR("JPEG data should begin with SOI marker!\n");
         return GPUJPEG_ERROR;
@@ -484,6 +491,13 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
                 GJ_ERR("Unsupported scan structure (components of the interleaved scan are not in frame order).\n");
                 return GPUJPEG_ERROR;
             }
+        }
+        /* one scan per component: scan s must code component s, so that every component is coded exactly once and
+         * the segment / block counts of scan s (geometry) are those of the plane K3 writes to */
+        if ( !g->interleaved && st.scan[s].comp[0] != s ) {
+            GJ_ERR("Unsupported scan structure (scan %d codes component %d; scans must follow the frame's component order).\n",
+                   s, st.scan[s].comp[0]);
+            return GPUJPEG_ERROR;
         }
         for ( int k = 0; k < st.scan[s].ncomp; k++ ) {
             const int td = st.scan[s].td[k], ta = st.scan[s].ta[k];

@@ -178,13 +178,15 @@ struct gj_stream {
     struct gj_scan_info scan[GJ_MAX_COMP];
     enum gpujpeg_color_space color_space;
     int spiff_color_space;   /* colour space named by a SPIFF header, GPUJPEG_NONE (0) if there is none */
+    int com_color_space;     /* colour space named by FFmpeg's COM "CS=ITU601", GPUJPEG_NONE (0) if there is none */
+    int ff_cs_itu601_is_709; /* in: read that comment as BT.709 [ref: libgpujpeg/gpujpeg_decoder.h:95] */
     enum gpujpeg_header_type header_type;
     const char* comment;
     size_t header_size;
     int interleaved;
 };
 /* incremental pieces: begin, walk marker segments up to the next SOS, finish */
-void gj_reader_begin(struct gj_stream* s);
+void gj_reader_begin(struct gj_stream* s, int ff_cs_itu601_is_709);
 int gj_reader_walk(const uint8_t* data, size_t size, size_t* pos, struct gj_stream* s, int* adobe_transform);
 int gj_reader_finish(struct gj_stream* s, int adobe_transform, int verbose);
 enum gpujpeg_color_space gj_stream_color_space(const struct gj_stream* s, int adobe_transform);

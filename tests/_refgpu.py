@@ -7,6 +7,8 @@ Test/bench infrastructure only.
     python tests/_refgpu.py encode_raw <in.raw> <pixfmt> <colorspace> <w> <h> <q> <rst> <interleaved> <out.jpg>
     python tests/_refgpu.py decode_fmt <in.jpg> <colorspace> <pixfmt> <out.raw>
     python tests/_refgpu.py bench  <kind> <w> <h> <q> <rst> <iters>      -> prints JSON with ms per frame
+    python tests/_refgpu.py serve        one JSON list of the arguments above per stdin line, one JSON reply per line
+                                         (one process, one CUDA context for a whole test session)
 """
 import ctypes as C
 import json
@@ -90,57 +92,102 @@ def encode(lib, enc, img, p, pi):
     return np.ctypeslib.as_array((C.c_uint8 * size.value).from_address(out.value))
 
 
+def pinned_copy(lib, arr):
+    """a copy of `arr` in page-locked host memory obtained exactly as the reference's own harness obtains it:
+    written to a scratch file and read back by the reference library's gpujpeg_image_load_from_file
+    (cudaMallocHost, src/gpujpeg_common.c:1217-1254; gpujpegtool does the same, src/main.c:786-797).
+    Returns (numpy view, pinned?, owner address for gpujpeg_image_destroy)."""
+    import tempfile
+    lib.gpujpeg_image_load_from_file.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    with tempfile.NamedTemporaryFile(suffix=".rgb") as f:
+        np.ascontiguousarray(arr).reshape(-1).tofile(f.name)
+        ptr, size = C.c_void_p(), C.c_size_t(0)
+        if lib.gpujpeg_image_load_from_file(f.name.encode(), C.byref(ptr), C.byref(size)) != 0 or size.value != arr.size:
+            return np.ascontiguousarray(arr).reshape(-1).copy(), False, None
+    return np.ctypeslib.as_array((C.c_uint8 * size.value).from_address(ptr.value)), True, ptr
+
+
 def main():
     mode = sys.argv[1]
     lib = load()
+    if mode == "serve":
+        sys.stdout.write(json.dumps({"ready": True}) + "\n")
+        sys.stdout.flush()
+        for line in sys.stdin:
+            line = line.strip()
+            if not line:
+                continue
+            try:
+                reply = {"ok": True, "reply": run(lib, [str(a) for a in json.loads(line)])}
+            except BaseException as exc:   # noqa: BLE001 -- the client turns it into a test failure
+                reply = {"ok": False, "error": repr(exc)}
+            sys.stdout.write(json.dumps(reply) + "\n")
+            sys.stdout.flush()
+        return
+    reply = run(lib, sys.argv[1:])
+    if reply is not None:
+        print(json.dumps(reply))
+
+
+def run(lib, a):
+    """one command: a = [mode, arguments...] as on the command line; returns a JSON-able reply or None"""
+    mode = a[0]
     if mode == "encode":
-        kind, w, h, q, rst, il, path = sys.argv[2], *map(int, sys.argv[3:8]), sys.argv[8]
+        kind, w, h, q, rst, il, path = a[1], *map(int, a[2:7]), a[7]
         img = gen(kind, w, h)
         enc = lib.gpujpeg_encoder_create(None)
         p, pi = params(lib, w, h, q, rst, il)
-        if len(sys.argv) > 10:   # chroma subsampling: GPUJPEG_SUBSAMPLING_xxx packing, first component on top
+        if len(a) > 9:   # chroma subsampling: GPUJPEG_SUBSAMPLING_xxx packing, first component on top
             lib.gpujpeg_parameters_chroma_subsampling.argtypes = [C.POINTER(Param), C.c_uint32]
-            lib.gpujpeg_parameters_chroma_subsampling(C.byref(p), int(sys.argv[9]) << 28 | int(sys.argv[10]) << 24 | 0x111100)
+            lib.gpujpeg_parameters_chroma_subsampling(C.byref(p), int(a[8]) << 28 | int(a[9]) << 24 | 0x111100)
         encode(lib, enc, img, p, pi).tofile(path)
         lib.gpujpeg_encoder_destroy(enc)
     elif mode == "encode_raw":
-        src, fmt, cs, w, h, q, rst, il, path = sys.argv[2], *map(int, sys.argv[3:10]), sys.argv[10]
+        src, fmt, cs, w, h, q, rst, il, path = a[1], *map(int, a[2:9]), a[9]
         raw = np.fromfile(src, np.uint8)
         enc = lib.gpujpeg_encoder_create(None)
         p, pi = params(lib, w, h, q, rst, il)
         pi.pixel_format, pi.color_space = fmt, cs   # comp_count stays 0: sampling follows the pixel format
-        if len(sys.argv) > 11:
-            p.color_space_internal = int(sys.argv[11])   # e.g. 1 = GPUJPEG_RGB: RGB-internal JPEG (Adobe APP14)
+        if len(a) > 10:
+            p.color_space_internal = int(a[10])   # e.g. 1 = GPUJPEG_RGB: RGB-internal JPEG (Adobe APP14)
         encode(lib, enc, raw, p, pi).tofile(path)
         lib.gpujpeg_encoder_destroy(enc)
     elif mode == "decode_fmt":
-        data = np.fromfile(sys.argv[2], np.uint8)
+        data = np.fromfile(a[1], np.uint8)
         dec = lib.gpujpeg_decoder_create(None)
-        lib.gpujpeg_decoder_set_output_format(dec, int(sys.argv[3]), int(sys.argv[4]))
+        lib.gpujpeg_decoder_set_output_format(dec, int(a[2]), int(a[3]))
         out = DecOut()
         out.type = 0
         assert lib.gpujpeg_decoder_decode(dec, data.ctypes.data, data.size, C.byref(out)) == 0
-        np.ctypeslib.as_array((C.c_uint8 * out.data_size).from_address(out.data)).tofile(sys.argv[5])
-        print(json.dumps({"pixel_format": out.param_image.pixel_format, "color_space": out.param_image.color_space,
-                          "size": out.data_size}))
+        np.ctypeslib.as_array((C.c_uint8 * out.data_size).from_address(out.data)).tofile(a[4])
+        reply = {"pixel_format": out.param_image.pixel_format, "color_space": out.param_image.color_space,
+                 "size": out.data_size}
         lib.gpujpeg_decoder_destroy(dec)
+        return reply
     elif mode == "decode":
-        data = np.fromfile(sys.argv[2], np.uint8)
+        data = np.fromfile(a[1], np.uint8)
         dec = lib.gpujpeg_decoder_create(None)
         lib.gpujpeg_decoder_set_output_format(dec, 1, 1)  # GPUJPEG_RGB, GPUJPEG_444_U8_P012
         out = DecOut()
         out.type = 0
         assert lib.gpujpeg_decoder_decode(dec, data.ctypes.data, data.size, C.byref(out)) == 0
-        np.ctypeslib.as_array((C.c_uint8 * out.data_size).from_address(out.data)).tofile(sys.argv[3])
+        np.ctypeslib.as_array((C.c_uint8 * out.data_size).from_address(out.data)).tofile(a[2])
         lib.gpujpeg_decoder_destroy(dec)
     elif mode == "bench":
-        kind, w, h, q, rst, iters = sys.argv[2], *map(int, sys.argv[3:8])
-        img = gen(kind, w, h)
+        kind, w, h, q, rst, iters = a[1], *map(int, a[2:7])
+        img, pinned, _keep = pinned_copy(lib, gen(kind, w, h))
         enc = lib.gpujpeg_encoder_create(None)
-        dec = lib.gpujpeg_decoder_create(None)
+        # the decoder takes perf_stats at create time (gpujpeg_decoder_init_parameters); with plain
+        # gpujpeg_decoder_create its timers stay off and get_stats reports nothing (round 1: decode_ms_gpu 0.0)
+        class DecInit(C.Structure):
+            _fields_ = [("stream", C.c_void_p), ("verbose", C.c_int), ("perf_stats", C.c_bool), ("ff_cs_itu601_is_709", C.c_bool)]
+        lib.gpujpeg_decoder_create_with_params.restype = C.c_void_p
+        lib.gpujpeg_decoder_create_with_params.argtypes = [C.POINTER(DecInit)]
+        di = DecInit(None, -1, True, False)
+        dec = lib.gpujpeg_decoder_create_with_params(C.byref(di))
         lib.gpujpeg_decoder_set_output_format(dec, 1, 1)
         p, pi = params(lib, w, h, q, rst, 0, perf=1)
-        jpeg = encode(lib, enc, img, p, pi).copy()
+        jpeg, _, _keep2 = pinned_copy(lib, encode(lib, enc, img, p, pi))
         te, tg = [], []
         for _ in range(iters):
             t = time.perf_counter()
@@ -160,9 +207,14 @@ def main():
             if lib.gpujpeg_decoder_get_stats(dec, C.byref(s)) == 0:
                 tdg.append(s.in_gpu)
         med = lambda x: float(np.median(x)) if len(x) else None
-        print(json.dumps({"impl": "reference-gpu", "w": w, "h": h, "kind": kind, "jpeg_bytes": int(jpeg.size),
-                          "encode_ms_e2e": med(te), "encode_ms_gpu": med(tg), "decode_ms_e2e": med(td),
-                          "decode_ms_gpu": med(tdg), "iters": iters}))
+        lib.gpujpeg_encoder_destroy(enc)
+        lib.gpujpeg_decoder_destroy(dec)
+        return {"impl": "reference-gpu", "w": w, "h": h, "kind": kind, "jpeg_bytes": int(jpeg.size),
+                "encode_ms_e2e": med(te), "encode_ms_gpu": med(tg), "decode_ms_e2e": med(td),
+                "decode_ms_gpu": med(tdg), "iters": iters, "input": "pinned" if pinned else "pageable",
+                "method": "serial gpujpeg_encoder_encode / gpujpeg_decoder_decode calls, host buffers, median of %d "
+                          "(the reference's own `gpujpegtool -n` loop, src/main.c:805-815)" % iters}
+    return None
 
 
 if __name__ == "__main__":

@@ -188,3 +188,47 @@ def test_decoder_survives_garbage_entropy_data(gj, dec):
         pass
     good = o.encode(o.gen_image("photo", 64, 64), 75, 4)
     assert np.array_equal(dec.decode(good), o.decode(good)), "the coder must stay usable afterwards"
+
+
+def test_scans_in_another_component_order_are_refused(gj):
+    """one scan per component, but the first scan codes Cb: the per-scan block counts of the geometry would no longer
+    belong to the plane the scan is written to (with 4:2:0 that was an out-of-bounds write) -- refused, not decoded"""
+    jpeg = o.encode(o.gen_image("photo", 64, 48), 75, 0, 0, sampling=(2, 2))
+    j = bytearray(jpeg)
+    sos = [i for i in range(len(j) - 1) if j[i] == 0xFF and j[i + 1] == 0xDA]
+    assert len(sos) == 3
+    # swap the component selectors (and table selectors) of the first two scan headers
+    a, b = sos[0], sos[1]
+    j[a + 5], j[b + 5] = j[b + 5], j[a + 5]
+    j[a + 6], j[b + 6] = j[b + 6], j[a + 6]
+    d = gj.Decoder()
+    try:
+        with pytest.raises(gj.GpuJpegError):
+            d.decode(np.frombuffer(bytes(j), np.uint8))
+        assert np.array_equal(d.decode(jpeg), o.decode(jpeg))   # the decoder instance is still usable
+    finally:
+        d.close()
+
+
+def test_ffmpeg_cs_itu601_comment_selects_limited_range(gj):
+    """a JFIF stream carrying FFmpeg's COM "CS=ITU601" holds limited-range BT.601 samples
+    [ref: src/gpujpeg_reader.c:655-661]: the RGB the decoder returns is the BT.601 conversion, and the same stream
+    read with ff_cs_itu601_is_709 is converted with the BT.709 matrix"""
+    w, h = 64, 48
+    raw = o.gen_raw(o.FMT_444_P012, w, h)
+    jpeg = o.encode_any(raw, w, h, o.FMT_444_P012, o.CS_601, 90, 4, 1, (1, 1), internal=o.CS_601)
+    assert b"CS=ITU601" in bytes(jpeg)
+    # strip the SPIFF header so that only the comment names the colour space: re-wrap the scan under a JFIF header
+    own = o.encode_any(raw, w, h, o.FMT_444_P012, o.CS_JPEG, 90, 4, 1, (1, 1))
+    body = bytes(own)
+    com = b"\xff\xfe\x00\x0cCS=ITU601\x00"
+    tagged = np.frombuffer(body[:2] + body[2:20] + com + body[20:], np.uint8)   # after the 18-byte JFIF APP0
+    d = gj.Decoder()
+    try:
+        d.set_output_format(gj.api.GPUJPEG_YCBCR_BT601, o.FMT_444_P012)
+        out, pi = d.decode_samples(tagged)          # asked for BT.601: the samples come back untransformed
+        d.set_output_format(gj.api.GPUJPEG_YCBCR_JPEG, o.FMT_444_P012)
+        plain, _ = d.decode_samples(own)            # the same scan read as full-range YCbCr, asked for full-range
+        assert np.array_equal(out, plain)
+    finally:
+        d.close()

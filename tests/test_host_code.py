@@ -197,3 +197,47 @@ def test_header_flavours_match_oracle_streams(internal, fmt, il, samp):
     mine = np.zeros(4096, np.uint8)
     n = hs.shim_header2(w, h, q, rst, il, comps, samp[0], samp[1], internal, mine)
     assert n > 300 and np.array_equal(mine[:n], jpeg[:n])
+
+
+class _ImageInfo(__import__("ctypes").Structure):
+    """struct gpujpeg_image_info (512 bytes) [ref: libgpujpeg/gpujpeg_decoder.h:243-260]"""
+    import ctypes as _C
+    import gpujpeg_b200.api as _api
+    _fields_ = [("param_image", _api.ImageParameters), ("param", _api.Parameters), ("segment_count", _C.c_int),
+                ("header_type", _C.c_int), ("comment", _C.c_char_p), ("pad", _C.c_char * 512)]
+
+
+def _with_com(jpeg, payload):
+    """the stream with a COM segment of `payload` inserted right after SOI"""
+    n = len(payload) + 2
+    return np.frombuffer(bytes(jpeg[:2]) + b"\xff\xfe" + bytes([n >> 8, n & 255]) + payload + bytes(jpeg[2:]), np.uint8)
+
+
+def test_com_marker_is_a_c_string_or_nothing_and_ffmpeg_colour_space_comment():
+    """COM handling of the reference reader [ref: src/gpujpeg_reader.c:641-672]: the comment is handed out only when
+    it is NUL-terminated (callers read it as a C string); FFmpeg's "CS=ITU601" (with or without NUL) names the colour
+    space of the components: limited-range BT.601"""
+    import ctypes as C
+    import gpujpeg_b200.api as api
+    fn = api.lib.gpujpeg_decoder_get_image_info2
+    fn.restype, fn.argtypes = C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(_ImageInfo), C.c_int, C.c_uint]
+    base = o.encode(o.gen_image("photo", 64, 48), 75, 4)
+
+    def info(j):
+        i = _ImageInfo()
+        assert fn(j.ctypes.data, j.size, C.byref(i), 0, 0) == 0
+        return i
+    own = info(base)
+    assert own.comment == b"CREATOR: GPUJPEG, quality = 75" and own.param_image.color_space == api.GPUJPEG_YCBCR_JPEG
+    # a later COM without terminator replaces nothing: the first NUL-terminated one stays ... and a stream whose only
+    # comment is unterminated has none (the reader must not hand out a pointer into the following file bytes)
+    strip = bytes(base).replace(b"\xff\xfe\x00\x21CREATOR: GPUJPEG, quality = 75\x00", b"")
+    assert len(strip) < base.size
+    j = _with_com(np.frombuffer(strip, np.uint8), b"Lavc60.3.100")
+    assert info(j).comment is None
+    j = _with_com(np.frombuffer(strip, np.uint8), b"")
+    assert info(j).comment is None
+    for payload in (b"CS=ITU601", b"CS=ITU601\x00"):
+        i = info(_with_com(base, payload))
+        assert i.param_image.color_space == api.GPUJPEG_YCBCR_BT601 and i.param.color_space_internal == api.GPUJPEG_YCBCR_BT601
+    assert info(_with_com(base, b"CS=ITU6010")).param_image.color_space == api.GPUJPEG_YCBCR_JPEG

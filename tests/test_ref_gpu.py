@@ -16,8 +16,27 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libgpujpeg_refgpu.so")
 
 
+_server = None
+
+
 def run_ref(*args):
-    subprocess.check_call([sys.executable, os.path.join(HERE, "_refgpu.py")] + [str(a) for a in args], timeout=600)
+    """one command for the reference GPU library; all commands of a session go to ONE child process (`_refgpu.py
+    serve`: one interpreter start, one CUDA context -- 70 separate children cost 2-3 s each, most of the GPU suite)"""
+    import atexit
+    import json
+    global _server
+    if _server is None or _server.poll() is not None:
+        _server = subprocess.Popen([sys.executable, os.path.join(HERE, "_refgpu.py"), "serve"], stdin=subprocess.PIPE,
+                                   stdout=subprocess.PIPE, text=True)
+        assert json.loads(_server.stdout.readline()).get("ready"), "reference GPU library did not start"
+        atexit.register(lambda p=_server: (p.stdin.close(), p.wait(timeout=30)))
+    _server.stdin.write(json.dumps([str(a) for a in args]) + "\n")
+    _server.stdin.flush()
+    line = _server.stdout.readline()
+    assert line, "reference GPU library process died"
+    reply = json.loads(line)
+    assert reply["ok"], reply.get("error")
+    return reply["reply"]
 
 
 @pytest.mark.skipif(not os.path.exists(SO), reason="oracle/_ref/libgpujpeg_refgpu.so not built")
