@@ -123,3 +123,11 @@ int gj_cuda_get_device(void)
 }
 void gj_cuda_device_reset(void) { cudaDeviceReset(); }
 }
+
+extern "C" int gj_cuda_sm_count(void)
+{
+    int dev = 0, n = 0;
+    if ( cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1 )
+        return 1;
+    return n;
+}

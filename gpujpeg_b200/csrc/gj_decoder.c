@@ -25,7 +25,8 @@
 
 #include "gj_internal.h"
 
-#define GJ_MK_OTHER_CAP 64 /* markers other than RSTn the device reports back (SOS, EOI, ...) */
+#define GJ_MK_OTHER_CAP 256 /* markers other than RSTn the device reports back (SOS, EOI, ...) */
+#define GJ_MK_WORDS (8 + 4 * GJ_MK_OTHER_CAP)   /* K0 result block: 8 counters/flags + {rank, position, code, clean position} per marker */
 
 struct gpujpeg_decoder {
     gj_stream_t stream;
@@ -38,6 +39,9 @@ struct gpujpeg_decoder {
     enum gpujpeg_pixel_format req_pixel_format;
     enum gpujpeg_color_space req_color_space;
     int idct_flavour;
+    int thread_per_segment;       /* dec_opt_huffman=thread_per_segment */
+    int force_lanes[GJ_MAX_COMP]; /* dec_opt_huffman_lanes: lanes per restart segment by scan, 0 = chosen from the frame's segment count */
+    int sm_count;
     int ff_cs_itu601_is_709;      /* [ref: libgpujpeg/gpujpeg_decoder.h:95] */
     int out_mode;                 /* GJ_OUT_RGB, GJ_OUT_SAMPLES or GJ_OUT_GENERIC: which K4 runs */
     uint8_t* d_planes; size_t d_planes_size;   /* component planes between the IDCT and the generic pass */
@@ -51,7 +55,9 @@ struct gpujpeg_decoder {
     uint8_t* d_file; size_t d_file_size;
     uint32_t* d_list_pos; size_t d_list_pos_size;   /* K0 marker list: positions */
     uint8_t* d_list_code; size_t d_list_code_size;  /*                  codes     */
-    uint32_t* d_cta; size_t d_cta_size;             /* K0 scratch */
+    uint32_t* d_list_cpos; size_t d_list_cpos_size; /*                  positions in the clean stream */
+    uint8_t* d_clean; size_t d_clean_size;          /* K0 clean stream: stuffing and markers removed, big-endian words */
+    unsigned long long* d_cta; size_t d_cta_size;   /* K0 scratch */
     uint32_t* d_mk;                                 /* K0 results (layout in gpujpeg_decoder_decode) */
     uint32_t* h_mk;                                 /* pinned mirror */
     int16_t* d_coef; size_t d_coef_size;
@@ -64,6 +70,7 @@ struct gpujpeg_decoder {
     int stats_valid;
 
     struct gj_huff_dec_args last_args;  /* launch arguments of the last frame (resident re-runs) */
+    size_t last_ecs_begin; uint32_t last_list_cap;
     int last_tq[3];
     int last_valid;
 };
@@ -115,11 +122,12 @@ struct gpujpeg_decoder* gpujpeg_decoder_create_with_params(const struct gpujpeg_
     d->perf_stats = params->perf_stats;
     d->ff_cs_itu601_is_709 = params->ff_cs_itu601_is_709;
     d->device = gj_cuda_get_device();
+    d->sm_count = gj_cuda_sm_count();
     d->req_pixel_format = GPUJPEG_PIXFMT_AUTODETECT;
     d->req_color_space = GPUJPEG_CS_DEFAULT;
     if ( d->device < 0 || gj_cuda_malloc((void**)&d->d_tab, sizeof *d->d_tab) ||
-         gj_cuda_malloc((void**)&d->d_mk, (8 + 3 * GJ_MK_OTHER_CAP) * 4) ||
-         gj_cuda_malloc_host((void**)&d->h_mk, (8 + 3 * GJ_MK_OTHER_CAP) * 4) ) {
+         gj_cuda_malloc((void**)&d->d_mk, GJ_MK_WORDS * 4) ||
+         gj_cuda_malloc_host((void**)&d->h_mk, GJ_MK_WORDS * 4) ) {
         GJ_ERR("Decoder allocation failed: %s\n", gj_cuda_last_error());
         free(d);
         return NULL;
@@ -143,6 +151,8 @@ int gpujpeg_decoder_destroy(struct gpujpeg_decoder* d)
     gj_cuda_free(d->d_file);
     gj_cuda_free(d->d_list_pos);
     gj_cuda_free(d->d_list_code);
+    gj_cuda_free(d->d_list_cpos);
+    gj_cuda_free(d->d_clean);
     gj_cuda_free(d->d_cta);
     gj_cuda_free(d->d_mk);
     gj_cuda_free_host(d->h_mk);
@@ -397,7 +407,9 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     if ( grow_dev((void**)&d->d_file, &d->d_file_size, image_size + 64) ||
          grow_dev((void**)&d->d_list_pos, &d->d_list_pos_size, (size_t)list_cap * 4) ||
          grow_dev((void**)&d->d_list_code, &d->d_list_code_size, (size_t)list_cap) ||
-         grow_dev((void**)&d->d_cta, &d->d_cta_size, n_cta * 4) ) {
+         grow_dev((void**)&d->d_list_cpos, &d->d_list_cpos_size, (size_t)list_cap * 4) ||
+         grow_dev((void**)&d->d_clean, &d->d_clean_size, image_size - ecs_begin + 64) ||
+         grow_dev((void**)&d->d_cta, &d->d_cta_size, n_cta * 8) ) {
         GJ_ERR("Decoder device allocation failed: %s\n", gj_cuda_last_error());
         return GPUJPEG_ERROR;
     }
@@ -407,11 +419,11 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
         return GPUJPEG_ERROR;
     }
     if ( stats && d->timers_ok ) gj_timer_stop(&d->t_to, d->stream);
-    /* d_mk: [0] total markers, [1] non-RST markers, [2] list overflow, [3] restart structure error,
-     *       [4..7] first marker rank per scan, [8..] {rank, position, code} of the non-RST markers */
-    if ( gj_launch_marker_scan(d->d_file, ecs_begin, image_size, d->d_cta, d->d_list_pos, d->d_list_code, list_cap, d->d_mk,
-                               d->d_mk + 8, GJ_MK_OTHER_CAP, d->stream) ||
-         gj_cuda_memcpy_d2h_async(d->h_mk, d->d_mk, (8 + 3 * GJ_MK_OTHER_CAP) * 4, d->stream) ||
+    /* d_mk: [0] total markers, [1] non-RST markers, [2] list overflow, [3] restart sequence error (K3), [5] clean bytes,
+     *       [8..] {rank, position, code, clean position} of the non-RST markers */
+    if ( gj_launch_marker_scan(d->d_file, ecs_begin, image_size, d->d_cta, d->d_list_pos, d->d_list_code, d->d_list_cpos,
+                               list_cap, d->d_clean, d->d_mk, d->d_mk + 8, GJ_MK_OTHER_CAP, d->stream) ||
+         gj_cuda_memcpy_d2h_async(d->h_mk, d->d_mk, GJ_MK_WORDS * 4, d->stream) ||
          gj_cuda_stream_sync(d->stream) ) {
         GJ_ERR("Marker scan failed: %s\n", gj_cuda_last_error());
         return GPUJPEG_ERROR;
@@ -419,7 +431,7 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
 
     /* ---- host reader, part 2: scan extents from the marker list, marker segments between scans by length ---- */
     const uint32_t n_other = d->h_mk[1];
-    if ( d->h_mk[2] || n_other == 0 || n_other > GJ_MK_OTHER_CAP ) {
+    if ( n_other == 0 || n_other > GJ_MK_OTHER_CAP ) {
         GJ_ERR("JPEG stream has %u restart markers / %u other markers in its scan data, expected %d restart segments "
                "for a %dx%d image with restart interval %d!\n", d->h_mk[0], n_other, g->seg_count, st.width, st.height,
                st.restart_interval);
@@ -427,22 +439,44 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     }
     uint32_t* other = d->h_mk + 8; /* insertion sort by position: a handful of entries */
     for ( uint32_t i = 1; i < n_other; i++ ) {
-        uint32_t t[3] = {other[3 * i], other[3 * i + 1], other[3 * i + 2]};
+        uint32_t t[4] = {other[4 * i], other[4 * i + 1], other[4 * i + 2], other[4 * i + 3]};
         uint32_t j = i;
-        while ( j > 0 && other[3 * (j - 1) + 1] > t[1] ) {
-            memcpy(other + 3 * j, other + 3 * (j - 1), 12);
+        while ( j > 0 && other[4 * (j - 1) + 1] > t[1] ) {
+            memcpy(other + 4 * j, other + 4 * (j - 1), 16);
             j--;
         }
-        memcpy(other + 3 * j, t, 12);
+        memcpy(other + 4 * j, t, 16);
     }
+    /* per scan, from the marker report alone (no second kernel, no walk over the entropy-coded bytes): where it ends,
+     * how many markers lie in front of it, how many restart markers it holds, where its clean bytes start */
+    uint32_t first_rank[GJ_MAX_COMP] = {0, 0, 0, 0}, end_rank[GJ_MAX_COMP] = {0, 0, 0, 0}, scan_cbegin[GJ_MAX_COMP] = {0, 0, 0, 0};
     for ( int k = 0; k < st.scan_count; k++ ) {
         /* a scan ends at the first marker that is not RSTn: inside entropy-coded data that test is exact */
         size_t e1 = 0;
+        int last_before = -1;
         for ( uint32_t i = 0; i < n_other; i++ ) {
-            if ( other[3 * i + 1] >= st.scan[k].begin ) {
-                e1 = other[3 * i + 1];
+            if ( other[4 * i + 1] >= st.scan[k].begin ) {
+                e1 = other[4 * i + 1];
+                end_rank[k] = other[4 * i];
                 break;
             }
+            last_before = (int)i;
+        }
+        if ( last_before >= 0 ) {
+            /* the last marker in front of the scan (its SOS): everything up to the scan's first byte that K0 kept
+             * belongs to the clean stream too -- the same keep rule, applied to the few header bytes */
+            const uint32_t* m = other + 4 * last_before;
+            first_rank[k] = m[0] + 1;
+            uint32_t c = m[3];
+            if ( st.scan[k].begin - m[1] > 4096 ) {
+                GJ_ERR("Unsupported scan structure (no marker in front of scan %d).\n", k);
+                return GPUJPEG_ERROR;
+            }
+            for ( size_t q = (size_t)m[1] + 2; q < st.scan[k].begin; q++ ) {
+                const int b0 = image[q], b1 = q + 1 < image_size ? image[q + 1] : 0, prev = image[q - 1];
+                if ( !((b0 == 0xFF && b1 != 0) || (prev == 0xFF && b0 != 0xFF)) ) c++;
+            }
+            scan_cbegin[k] = c;
         }
         if ( e1 == 0 ) {
             GJ_ERR("JPEG data unexpected ended while reading SOS marker!\n");
@@ -479,7 +513,6 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
                 d->h_tab.qinv_zz[t][k] = st.qt[t][k];
     struct gj_huff_dec_args ha;
     memset(&ha, 0, sizeof ha);
-    uint32_t scan_begin[4] = {0, 0, 0, 0}, scan_end[4] = {0, 0, 0, 0};
     for ( int s = 0; s < st.scan_count; s++ ) {
         if ( st.scan[s].ncomp != g->comps_per_scan ) {
             GJ_ERR("Unsupported scan structure (scan %d has %d components).\n", s, st.scan[s].ncomp);
@@ -510,15 +543,16 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
             ha.scan_tq[s][k] = st.comp_tq[st.scan[s].comp[k]];
             ha.scan_ta[s][k] = ta;
         }
-        scan_begin[s] = (uint32_t)st.scan[s].begin;
-        scan_end[s] = (uint32_t)st.scan[s].end;
-        ha.scan_begin[s] = scan_begin[s];
+        ha.scan_begin[s] = (uint32_t)st.scan[s].begin;
     }
     for ( int cls = 0; cls < 2; cls++ )
         for ( int id = 0; id < 4; id++ )
-            if ( st.have_huff[cls][id] && gj_dec_lut_build(&st.huff[cls][id], &d->h_tab.lut[cls][id]) ) {
-                GJ_ERR("Invalid Huffman table (class %d id %d)!\n", cls, id);
-                return GPUJPEG_ERROR;
+            if ( st.have_huff[cls][id] ) {
+                if ( gj_dec_lut_build(&st.huff[cls][id], &d->h_tab.lut[cls][id]) ) {
+                    GJ_ERR("Invalid Huffman table (class %d id %d)!\n", cls, id);
+                    return GPUJPEG_ERROR;
+                }
+                gj_dec_fast_build(&st.huff[cls][id], cls, &d->h_tab.fast[cls][id]);
             }
     const double t_reader_ms = (gpujpeg_get_time() - t_begin) * 1000.0;
 
@@ -532,13 +566,16 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
         gj_timer_start(&d->t_gpu, d->stream);
         gj_timer_start(&d->t_huff, d->stream);
     }
-    int scan_segments[4] = {0, 0, 0, 0};
-    for ( int s = 0; s < g->scan_count; s++ )
-        scan_segments[s] = g->lay.scan_seg_begin[s + 1] - g->lay.scan_seg_begin[s];
-    if ( gj_launch_scan_ranks(d->d_list_pos, d->d_mk, st.scan_count, scan_begin, scan_end, scan_segments, d->d_mk + 4,
-                              d->stream) ) {
-        GJ_ERR("Scan rank launch failed: %s\n", gj_cuda_last_error());
-        return GPUJPEG_ERROR;
+    /* restart structure [ref: src/gpujpeg_reader.c:1038-1155]: scan k must hold one restart marker per segment
+     * boundary, all of them (and the marker that ends the scan) inside the device list */
+    for ( int k = 0; k < g->scan_count; k++ ) {
+        const int segs = g->lay.scan_seg_begin[k + 1] - g->lay.scan_seg_begin[k];
+        if ( end_rank[k] >= list_cap || end_rank[k] - first_rank[k] != (uint32_t)(segs - 1) ) {
+            GJ_ERR("JPEG stream has a broken restart-marker structure (scan %d holds %u restart markers, expected %d "
+                   "for a %dx%d image with restart interval %d)!\n", k, end_rank[k] - first_rank[k], segs - 1, st.width,
+                   st.height, st.restart_interval);
+            return GPUJPEG_ERROR;
+        }
     }
 
     /* ---- K3 ---- */
@@ -549,14 +586,42 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     ha.d_seg_len = NULL;
     ha.d_list_pos = d->d_list_pos;
     ha.d_list_code = d->d_list_code;
-    ha.d_first_rank = d->d_mk + 4;
     ha.d_error = d->d_mk + 3;
+    ha.d_clean = (const uint32_t*)d->d_clean;
+    ha.d_list_cpos = d->d_list_cpos;
+    ha.force_thread_per_segment = d->thread_per_segment;
+    /* Which Huffman decoder kernel, and how many lanes share a restart segment (measured on B200, profiles/r2_k3_matrix):
+     * a frame with few segments cannot occupy the GPU with one thread per segment -- there the self-synchronising walks
+     * buy parallelism INSIDE a segment (HD: 25 us against 82, 4K: 47 against 89); with 40 000 segments and more the
+     * segments alone keep the machine busy and the redundant walks only pay off at photographic densities (8K q75:
+     * 140 us against 172; sparser or denser 8K content is faster with one thread per segment). */
+    size_t ecs_bytes = 0;
+    for ( int k = 0; k < g->scan_count; k++ )
+        ecs_bytes += st.scan[k].end - st.scan[k].begin;
+    const size_t bytes_per_block_x10 = ecs_bytes * 10 / (g->coef_count / 64);
+    const int many_segments = g->seg_count >= 30000;
+    ha.force_thread_per_segment = d->thread_per_segment || (many_segments && (bytes_per_block_x10 < 30 || bytes_per_block_x10 > 100));
+    for ( int k = 0; k < g->scan_count; k++ ) {
+        ha.first_rank[k] = first_rank[k];
+        ha.scan_cbegin[k] = scan_cbegin[k];
+        const int segs = g->lay.scan_seg_begin[k + 1] - g->lay.scan_seg_begin[k];
+        const size_t avg = (st.scan[k].end - st.scan[k].begin) / (size_t)segs;
+        ha.scan_lanes[k] = (uint8_t)(g->seg_count <= 8000 ? 16 : !many_segments ? 8 : avg >= 192 ? 16 : 8);
+        if ( d->force_lanes[k] ) {
+            ha.scan_lanes[k] = (uint8_t)d->force_lanes[k];
+            ha.force_thread_per_segment = d->thread_per_segment;
+        }
+        ha.scan_bytes[k] = (uint32_t)(st.scan[k].end - st.scan[k].begin);
+        ha.scan_dense[k] = avg >= (size_t)16 * (size_t)(g->seg_mcu * g->lay.bpm);
+    }
     ha.seg_count = g->seg_count;
     ha.lay = g->lay;
     ha.seg_mcu = g->seg_mcu;
     ha.d_coef = d->d_coef;
     ha.d_tables = d->d_tab;
     d->last_args = ha;
+    d->last_ecs_begin = ecs_begin;
+    d->last_list_cap = list_cap;
     memcpy(d->last_tq, st.comp_tq, sizeof d->last_tq);
     d->last_valid = 1;
     if ( gj_launch_huffman_decode(&ha, d->stream) ) {
@@ -616,8 +681,8 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     if ( d->h_mk[3] ) {
         /* the reference tries to resynchronise on a broken restart sequence
          * [ref: src/gpujpeg_reader.c:1071-1105]; here it is reported, not repaired */
-        GJ_ERR("JPEG stream has a broken restart-marker structure (expected %d restart segments per scan for a %dx%d "
-               "image with restart interval %d)!\n", g->seg_per_scan, st.width, st.height, st.restart_interval);
+        GJ_ERR("JPEG stream has a broken restart-marker sequence (RSTn do not count 0..7 cyclically; %dx%d image, "
+               "restart interval %d)!\n", st.width, st.height, st.restart_interval);
         return GPUJPEG_ERROR;
     }
     output->metadata = &d->metadata;
@@ -729,6 +794,33 @@ int gpujpeg_decoder_set_option(struct gpujpeg_decoder* decoder, const char* opt,
         }
         return GPUJPEG_NOERR;
     }
+    if ( strcmp(opt, GPUJPEG_DEC_OPT_HUFFMAN) == 0 ) {
+        if ( strcmp(val, GPUJPEG_DEC_HUFFMAN_VAL_AUTO) == 0 ) decoder->thread_per_segment = 0;
+        else if ( strcmp(val, GPUJPEG_DEC_HUFFMAN_VAL_THREAD_PER_SEGMENT) == 0 ) decoder->thread_per_segment = 1;
+        else {
+            GJ_ERR("Unknown Huffman decoder kernel: %s\n", val);
+            return GPUJPEG_ERROR;
+        }
+        return GPUJPEG_NOERR;
+    }
+    if ( strcmp(opt, GPUJPEG_DEC_OPT_HUFFMAN_LANES) == 0 ) {
+        /* one number for every scan, or a comma-separated list by scan */
+        int lanes[GJ_MAX_COMP] = {0, 0, 0, 0}, count = 0;
+        const char* p = val;
+        while ( *p && count < GJ_MAX_COMP ) {
+            const int n = atoi(p);
+            if ( n < 0 || n > 32 || (n & (n - 1)) ) {
+                GJ_ERR("Lanes per restart segment must be 0 (automatic) or a power of two up to 32 (got %s).\n", val);
+                return GPUJPEG_ERROR;
+            }
+            lanes[count++] = n;
+            while ( *p && *p != ',' ) p++;
+            if ( *p == ',' ) p++;
+        }
+        for ( int k = 0; k < GJ_MAX_COMP; k++ )
+            decoder->force_lanes[k] = count == 1 ? lanes[0] : lanes[k];
+        return GPUJPEG_NOERR;
+    }
     if ( strcmp(opt, GPUJPEG_DEC_OPT_TGA_RLE_BOOL) == 0 || strcmp(opt, GPUJPEG_DEC_OPT_FLIPPED_BOOL) == 0 ||
          strcmp(opt, GPUJPEG_DEC_OPT_CHANNEL_REMAP) == 0 || strcmp(opt, GPUJPEG_DEC_OPT_ALIGNMENT_BYTES_INT) == 0 ) {
         GJ_ERR("Decoder option %s is not implemented in this build.\n", opt);
@@ -744,11 +836,17 @@ void gpujpeg_decoder_print_options(void)
            "] - inverse DCT flavour (default: int = gpujpeg_idct_cpu)\n");
 }
 
-/* ---- extension: re-run the GPU stages of the last decoded frame on the data already on the device ----
- * stage_mask bit 0 = K3 (Huffman decode), bit 1 = K4 (dequant+IDCT+colour).  No copies, no sync. */
+/* ---- extension: re-run the GPU stages of the last decoded frame on the JPEG bytes already on the device ----
+ * stage_mask bit 2 = K0 (marker list + clean stream from the file bytes), bit 0 = K3 (Huffman decode), bit 1 = K4
+ * (dequant+IDCT+colour).  No copies, no sync; what the host derived from K0's report for this file (scan extents,
+ * ranks) is reused, so 7 = every GPU stage of a decode that starts from the JPEG bytes. */
 GPUJPEG_API int gpujpegx_decoder_run_resident(struct gpujpeg_decoder* d, uint8_t* d_out, int stage_mask)
 {
     if ( !d || !d->last_valid ) return -1;
+    if ( (stage_mask & 4) &&
+         gj_launch_marker_scan(d->d_file, d->last_ecs_begin, d->last_args.file_size, d->d_cta, d->d_list_pos, d->d_list_code,
+                               d->d_list_cpos, d->last_list_cap, d->d_clean, d->d_mk, d->d_mk + 8, GJ_MK_OTHER_CAP, d->stream) )
+        return -1;
     if ( (stage_mask & 1) && gj_launch_huffman_decode(&d->last_args, d->stream) ) return -1;
     if ( (stage_mask & 2) && launch_k4(d, d->last_tq, d_out ? d_out : d->d_raw, d->last_args.dequantize) ) return -1;
     return 0;

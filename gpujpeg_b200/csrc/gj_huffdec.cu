@@ -1,0 +1,696 @@
+/*
+ * gj_huffdec.cu -- K3: self-synchronising, restart-interval-parallel Huffman decoder (sm_100a).
+ *
+ * The reference decodes one restart segment per THREAD (src/gpujpeg_huffman_gpu_decoder.cu:390-537): 43 200 threads
+ * for an 8K frame, each walking a few hundred symbols one after the other.  The first decoder of this repository
+ * (k_huff_decode in gj_huffman.cu, still used for segments longer than SD_MAXBLK blocks) kept that decomposition and
+ * was bound by it: 9 of 32 lanes busy, one warp's dependent chain as the critical path.
+ *
+ * This kernel puts several LANES on one segment.  The segment's clean bit stream (K0 removed stuffing and markers)
+ * is cut into equal sub-sequences, one per lane.  Nobody knows where a symbol starts inside a sub-sequence, but
+ * Huffman streams re-synchronise by themselves: a decoder started at a wrong bit falls into step with the true
+ * symbol sequence after a few symbols.  So
+ *
+ *   round 0   every lane walks its sub-sequence from its first bit, assuming "start of a block" -- a walk that
+ *             tracks only the STATE (bit position, zig-zag index, block-in-MCU index) and counts finished blocks;
+ *   round r   every lane takes the end state of its left neighbour as its start state and walks again if that
+ *             state differs from the one it used before; lane 0 starts exact, so after round r lanes 0..r are
+ *             exact, and in practice everything is after two rounds (the walks of round 0 are already in step at
+ *             their END, which is all the neighbour needs).  The loop ends when no lane's start state changed --
+ *             a fixed point that is reached for ANY input, in the worst case after as many rounds as lanes;
+ *   then      a prefix sum over the block counts tells every lane which block its first symbol belongs to, and one
+ *             more walk -- the only one that extracts values -- writes the coefficients.
+ *
+ * One table lookup per symbol gives code length + value size + zig-zag advance (gj_dec_fast, 10-bit lookahead;
+ * longer codes by canonical search).  DC differences are collected per block and turned into DC values by a prefix
+ * sum per component afterwards (the predictor chain is the one truly sequential thing in a segment).
+ *
+ * Output: dense scans (at most two segments per warp) stage their blocks in shared memory and flush whole 128-byte
+ * lines; sparse scans (many short segments per warp, a handful of non-zeros per block) zero-fill their blocks in
+ * global memory and store the non-zeros directly.  Either way every coefficient of every block is written: no
+ * memset of the 200 MB coefficient buffer.
+ *
+ * Semantics follow the reference decoders: garbage codes read as "end of block" / DC size 0
+ * (src/gpujpeg_huffman_gpu_decoder.cu:565-577, src/gpujpeg_huffman_cpu_decoder.c:155-159), the predictor is reset at
+ * every segment start (src/gpujpeg_huffman_cpu_decoder.c:407-411), a segment never writes more than its own blocks.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <type_traits>
+
+#include "gj_device.cuh"
+#include "gj_internal.h"
+
+namespace {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr int SD_WARPS = 8;
+constexpr int SD_THREADS = SD_WARPS * 32;
+constexpr int SD_MAXBLK = 40;          // blocks per restart segment this kernel takes (every RESTART_AUTO setting)
+constexpr int SD_MAXLEN = 32760;       // clean bytes of a segment that are looked at (a valid 40-block segment has < 18 KB)
+constexpr int SD_MINSUB = 8;           // shortest sub-sequence, bytes
+
+struct SdTable {   // one Huffman table in shared memory
+    uint16_t fast[1 << GJ_DEC_FAST_BITS];
+    uint16_t sub[GJ_DEC_FAST_SUBS][1 << (16 - GJ_DEC_FAST_BITS)];
+    uint32_t maxcode[18];
+    int32_t valoff[18];
+    uint8_t vals[256];
+};
+static_assert(sizeof(SdTable) % 16 == 0, "tables are copied with 16-byte accesses");
+
+struct SdParams {
+    gj_scan_layout lay;
+    const uint32_t* clean;
+    const uint32_t* list_cpos;
+    const uint8_t* list_code;
+    uint32_t first_rank[GJ_MAX_COMP], scan_cbegin[GJ_MAX_COMP];
+    int cta_begin[GJ_MAX_COMP + 1];      // first CTA of every scan
+    int units_per_warp;
+    uint8_t lanes_log2[GJ_MAX_COMP];     // lanes per segment in scan s
+    uint8_t staged[GJ_MAX_COMP];         // scan s stages its blocks in shared memory
+    int8_t scan_td[GJ_MAX_COMP][GJ_MAX_COMP], scan_ta[GJ_MAX_COMP][GJ_MAX_COMP], scan_tq[GJ_MAX_COMP][GJ_MAX_COMP];
+    int seg_mcu;
+    int ncomp_tab;                       // components whose tables a CTA holds (1, or all of an interleaved scan)
+    int tgt_entries, dc_entries, stage_blocks;   // per warp: entries of s_tgt and s_dc, blocks of staging
+    int cmp_words;                               // per warp: words of staged clean stream (multiple of 4)
+    uint32_t* error;
+    int16_t* coef;
+    const gj_dev_dec_tables* tables;
+};
+
+/* block number j (coding order) of the segment that starts at MCU first_mcu of scan `scan` -> block index in the
+ * coefficient buffer (the same mapping as segment_block() of gj_huffman.cu) */
+__device__ __forceinline__ uint32_t block_target(const gj_scan_layout& L, int scan, int first_mcu, int j)
+{
+    if ( !L.interleaved ) return (uint32_t)(L.blk_off[scan] + first_mcu + j);
+    if ( L.simple ) {
+        const int cps = L.comp_count;
+        const int mcu = j / cps;
+        return (uint32_t)(L.blk_off[j - mcu * cps] + first_mcu + mcu);
+    }
+    const int mcu = j / L.bpm, i = j - mcu * L.bpm;
+    const int m = first_mcu + mcu;
+    const int my = m / L.mcu_x, mx = m - my * L.mcu_x;
+    const int comp = L.idx_comp[i];
+    return (uint32_t)(L.blk_off[comp] + (my * L.comp_vs[comp] + L.idx_dy[i]) * L.bcx[comp] + mx * L.comp_hs[comp] + L.idx_dx[i]);
+}
+
+/* codes longer than GJ_DEC_FAST_BITS: canonical search, result in the format of a gj_dec_fast entry.  A real call on
+ * purpose: inlined, the compiler if-converts the search into the walk and every symbol pays for it (ncu r2_e: 22 % of
+ * the kernel's instructions); rare in valid streams, so the call is taken by few lanes of few warps. */
+__device__ __noinline__ uint32_t slow_entry(const SdTable& T, uint32_t win, bool ac)
+{
+    const uint32_t peek = win >> 16;
+    int l = GJ_DEC_FAST_BITS + 1;
+#pragma unroll
+    for ( int q = GJ_DEC_FAST_BITS + 1; q < 16; q++ )
+        l += peek >= T.maxcode[q] ? 1 : 0;   // maxcode is non-decreasing: l = shortest length whose bound lies above peek
+    if ( peek >= T.maxcode[l] ) return 16u | (ac ? 64u : 1u) << 5;   // garbage: 16 bits, symbol 0
+    const uint32_t sym = T.vals[((int)(peek >> (16 - l)) + T.valoff[l]) & 255];
+    const uint32_t size = sym & 15u, run = sym >> 4;
+    const uint32_t kadv = !ac ? 1u : size ? run + 1u : run == 15u ? 16u : 64u;
+    return (uint32_t)(l + size) | kadv << 5 | size << 12;
+}
+
+/* one symbol: table entry for the 32 stream bits in `win` */
+__device__ __forceinline__ uint32_t lookup(const SdTable* T, uint32_t win, bool ac)
+{
+    uint32_t e = T->fast[win >> (32 - GJ_DEC_FAST_BITS)];
+    if ( (e & 31u) == 0 ) {   // a code of more than GJ_DEC_FAST_BITS bits
+        if ( e ) e = T->sub[(e >> 5) - 1u][(win >> 16) & ((1u << (16 - GJ_DEC_FAST_BITS)) - 1u)];
+        if ( e == 0 ) e = slow_entry(*T, win, ac);
+    }
+    return e;
+}
+
+/* Everything a walk needs besides the stream position */
+struct Walk {
+    const uint32_t* cw;      // clean words, starting with the word that holds the segment's first byte
+    const uint32_t* sw;      // the same words staged in shared memory (when the unit's segments fit)
+    uint32_t bit0;           // bit offset of that byte inside the word
+    const SdTable* tab;      // [component in scan][DC, AC]
+    const uint16_t* q;       // [component in scan][64] dequantisation, zig-zag order
+    uint32_t cimap;          // block-in-MCU index -> component in scan, 2 bits each
+    uint32_t bpm;
+};
+
+/* 64-bit window on the clean stream kept in registers, one more word prefetched: the load never sits on the
+ * dependent chain position -> window -> table -> position of the walk */
+struct Window {
+    const uint32_t* wp;
+    uint32_t hi, lo, nxt, base;
+};
+__device__ __forceinline__ void win_init(Window& w, const uint32_t* __restrict__ cw, uint32_t q)
+{
+    const uint32_t wi = q >> 5;
+    w.hi = __ldg(cw + wi);
+    w.lo = __ldg(cw + wi + 1);
+    w.nxt = __ldg(cw + wi + 2);
+    w.wp = cw + wi + 3;
+    w.base = wi << 5;
+}
+/* the 32 bits that start at bit q (q advances by at most 31 bits per symbol: one refill step is enough) */
+__device__ __forceinline__ uint32_t win_peek(Window& w, uint32_t q)
+{
+    uint32_t sh = q - w.base;
+    if ( sh >= 32u ) {
+        w.hi = w.lo;
+        w.lo = w.nxt;
+        w.nxt = __ldg(w.wp);
+        w.wp++;
+        w.base += 32u;
+        sh -= 32u;
+    }
+    return __funnelshift_l(w.lo, w.hi, sh);
+}
+
+/* Where a walk reads the stream from.  Shared memory (the unit's segments were staged there with coalesced loads): two
+ * loads and a funnel shift per symbol, nothing carried between symbols.  Global memory (units larger than the staging
+ * area): the register window above.  Measured (r2_i): with the window alone every symbol waited for a global load --
+ * the scoreboard tracks registers per WARP, so the refill one lane issued is a dependency for the refill another lane
+ * does one iteration later; 86 us for a state-only walk of an 8K frame, ~480 cycles per symbol. */
+template <bool SM>
+struct Src;
+template <>
+struct Src<true> {
+    const uint32_t* base;
+    __device__ __forceinline__ void init(const Walk& W, uint32_t) { base = W.sw; }
+    __device__ __forceinline__ uint32_t peek(uint32_t q)
+    {
+        const uint32_t* p = base + (q >> 5);
+        return __funnelshift_l(p[1], p[0], q & 31u);
+    }
+};
+template <>
+struct Src<false> {
+    Window w;
+    __device__ __forceinline__ void init(const Walk& W, uint32_t q) { win_init(w, W.cw, q); }
+    __device__ __forceinline__ uint32_t peek(uint32_t q) { return win_peek(w, q); }
+};
+
+/* state = bit position (18 bits, relative to the segment) | zig-zag index << 18 | block-in-MCU index << 25 */
+__device__ __forceinline__ uint32_t make_state(uint32_t p, uint32_t k, uint32_t c) { return p | k << 18 | c << 25; }
+
+/* Walks the symbols that start in [state.p, p_end) tracking only the state.  `cross` = the state at the first symbol
+ * boundary at or behind bit p_cross (the lane's own sub-sequence starts there; what lies in front is warm-up, walked only
+ * to fall into step with the true symbol sequence); `blocks` = blocks finished behind that boundary.
+ * IL: interleaved scan (the block-in-MCU index selects the tables). */
+template <bool IL, bool SM>
+__device__ __forceinline__ uint32_t walk_state(const Walk& W, uint32_t st, uint32_t p_cross, uint32_t p_end, int& blocks,
+                                               uint32_t& cross)
+{
+    uint32_t k = (st >> 18) & 127u, c = st >> 25;
+    const uint32_t p = st & 0x3FFFFu;
+    blocks = 0;
+    cross = st;
+    if ( p >= p_end ) return st;
+    uint32_t q = W.bit0 + p;
+    const uint32_t q_end = W.bit0 + p_end, q_cross = W.bit0 + p_cross;
+    Src<SM> src;
+    src.init(W, q);
+    const SdTable* t_dc = W.tab + (IL ? 2u * ((W.cimap >> (2 * c)) & 3u) : 0u);
+    int nb = 0;
+    auto step = [&]() {
+        const uint32_t win = src.peek(q);
+        const SdTable* T = k ? t_dc + 1 : t_dc;
+        const uint32_t e = lookup(T, win, k != 0);
+        q += e & 31u;
+        k += (e >> 5) & 127u;
+        if ( k >= 64u ) {   // end of block: EOB, or coefficient 63 reached
+            k = 0;
+            nb++;
+            if ( IL ) {
+                c = c + 1u == W.bpm ? 0u : c + 1u;
+                t_dc = W.tab + 2u * ((W.cimap >> (2 * c)) & 3u);
+            }
+        }
+    };
+    if ( q < q_cross ) {
+        do step(); while ( q < q_cross );
+        nb = 0;
+        cross = make_state(q - W.bit0, k, c);
+    }
+    while ( q < q_end ) step();
+    blocks = nb;
+    return make_state(q - W.bit0, k, c);
+}
+
+/* Where the walk that extracts values puts them:
+ *   M_STAGED  blocks staged in shared memory, flushed as whole lines afterwards (dense scans, <= 2 segments per warp);
+ *             the DC position receives the DC DIFFERENCE, dc_pass turns differences into values
+ *   M_DIRECT  blocks zero-filled in the coefficient buffer beforehand, non-zeros stored straight into it; DC
+ *             differences go to a small shared array for dc_pass
+ *   M_SOLO    one lane = one whole segment: the lane zero-fills a block when it starts it and keeps the DC
+ *             predictors itself -- nothing to do afterwards */
+enum { M_STAGED = 0, M_DIRECT = 1, M_SOLO = 2 };
+
+/* `out` = first block of the segment (staging slot, or coefficient buffer when the segment's blocks are consecutive
+ * there: !IL); interleaved scans outside the staging area look every block up in tgt[]. */
+template <bool DEQ, bool IL, int MODE, bool SM>
+__device__ __forceinline__ void walk_write(const Walk& W, uint32_t st, uint32_t p_end, int n, int nblocks,
+                                           const uint32_t* __restrict__ tgt, int16_t* __restrict__ out,
+                                           int16_t* __restrict__ coef, int16_t* __restrict__ dcd)
+{
+    uint32_t k = (st >> 18) & 127u, c = st >> 25;
+    const uint32_t p = st & 0x3FFFFu;
+    if ( n >= nblocks || (MODE != M_SOLO && p >= p_end) ) return;
+    uint32_t q = W.bit0 + p;
+    const uint32_t q_end = W.bit0 + p_end;
+    Src<SM> src;
+    src.init(W, q);
+    uint32_t ci = IL ? (W.cimap >> (2 * c)) & 3u : 0u;
+    const SdTable* t_dc = W.tab + 2u * ci;
+    const uint16_t* qt = W.q + 64u * ci;
+    int pred0 = 0, pred1 = 0, pred2 = 0, pred3 = 0;   // M_SOLO: DC predictors by component in scan
+    auto block_at = [&](int nn) -> int16_t* { return (MODE == M_STAGED || !IL) ? out + (size_t)nn * 64 : coef + (size_t)tgt[nn] * 64; };
+    int16_t* o = block_at(n);
+    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+    if ( MODE == M_SOLO ) {
+#pragma unroll
+        for ( int i = 0; i < 8; i++ )
+            reinterpret_cast<uint4*>(o)[i] = z4;
+    }
+    for ( ;; ) {
+        if ( MODE != M_SOLO && q >= q_end ) break;   // a solo lane ends with its last block, wherever the bits end
+        const uint32_t win = src.peek(q);
+        const SdTable* T = k ? t_dc + 1 : t_dc;
+        const uint32_t e = lookup(T, win, k != 0);
+        const uint32_t total = e & 31u, kadv = (e >> 5) & 127u, size = e >> 12;
+        /* value bits -> value [ref: src/gpujpeg_huffman_cpu_decoder.c:169-204]; size 0 gives 0 */
+        const uint32_t bits = ((win << (total - size)) >> 1) >> (31u - size);
+        const uint32_t neg = ((bits >> ((size - 1u) & 31u)) & 1u) ^ 1u;          // 1: the leading value bit is 0 -> negative
+        int v = (int)bits - (int)(neg ? (1u << size) - 1u : 0u);
+        const uint32_t idx = k + kadv - 1u;                                      // DC: 0
+        if ( k == 0u ) {
+            if ( MODE == M_SOLO ) {
+                if ( !IL || ci == 0 ) v = (pred0 += v);
+                else if ( ci == 1 ) v = (pred1 += v);
+                else if ( ci == 2 ) v = (pred2 += v);
+                else v = (pred3 += v);
+                o[0] = (int16_t)(DEQ ? v * (int)qt[0] : v);
+            }
+            else if ( MODE == M_DIRECT ) dcd[n] = (int16_t)v;
+            else o[0] = (int16_t)v;
+        }
+        else if ( size && idx < 64u ) {
+            o[idx] = (int16_t)(DEQ ? v * (int)qt[idx] : v);
+        }
+        q += total;
+        k += kadv;
+        if ( k >= 64u ) {   // end of block: EOB, or coefficient 63 reached
+            k = 0;
+            if ( ++n >= nblocks ) break;
+            if ( IL ) {
+                c = c + 1u == W.bpm ? 0u : c + 1u;
+                ci = (W.cimap >> (2 * c)) & 3u;
+                t_dc = W.tab + 2u * ci;
+                qt = W.q + 64u * ci;
+            }
+            o = block_at(n);
+            if ( MODE == M_SOLO ) {
+#pragma unroll
+                for ( int i = 0; i < 8; i++ )
+                    reinterpret_cast<uint4*>(o)[i] = z4;
+            }
+        }
+        if ( MODE == M_SOLO && q >= q_end + 64u ) {
+            /* the segment's bits are used up before its blocks are (damaged stream): the remaining blocks are zero */
+            while ( ++n < nblocks ) {
+                o = block_at(n);
+#pragma unroll
+                for ( int i = 0; i < 8; i++ )
+                    reinterpret_cast<uint4*>(o)[i] = z4;
+            }
+            break;
+        }
+    }
+}
+
+/* All units of this warp.  Per unit: 32 / lanes restart segments, `lanes` lanes each. */
+template <bool DEQ, bool IL, int MODE>
+__device__ __forceinline__ void run_units(const SdParams& P, const int scan, Walk W, uint32_t* const s_tgt, int16_t* const s_dc,
+                                          int16_t* const s_stage, uint32_t* const s_cmp)
+{
+    const gj_scan_layout& L = P.lay;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int ncomp = IL ? L.comp_count : 1;
+    const int lanes_log2 = MODE == M_SOLO ? 0 : P.lanes_log2[scan], lanes = 1 << lanes_log2;
+    const int spu = 32 >> lanes_log2;                  // segments per unit (= per warp round)
+    const int slot = lane >> lanes_log2, gl = lane & (lanes - 1);
+    const int segblk = P.seg_mcu * L.bpm;
+    const int scan_segs = L.scan_seg_begin[scan + 1] - L.scan_seg_begin[scan];
+    const int scan_units = (scan_segs + spu - 1) / spu;
+    const int unit0 = ((int)blockIdx.x - P.cta_begin[scan]) * nwarps * P.units_per_warp + warp;
+    uint32_t* const tgt = s_tgt + slot * segblk;       // IL only
+    int16_t* const dcd = s_dc + slot * segblk;         // M_DIRECT only
+
+    for ( int it = 0; it < P.units_per_warp; it++ ) {
+        const int unit = unit0 + it * nwarps;
+        if ( unit >= scan_units ) break;   // warp-uniform
+        const int s = unit * spu + slot;
+        const bool valid = s < scan_segs;
+
+        /* ---- the unit's clean bytes (its segments follow each other in the clean stream) -> shared memory, with
+         *      coalesced 16-byte loads, when they fit ---- */
+        const int s_first = unit * spu, s_last = min(s_first + spu, scan_segs) - 1;
+        const uint32_t cs0 = s_first ? __ldg(P.list_cpos + P.first_rank[scan] + s_first - 1) : P.scan_cbegin[scan];
+        const uint32_t ce1 = __ldg(P.list_cpos + P.first_rank[scan] + s_last);
+        const uint32_t wbase = (cs0 >> 2) & ~3u;
+        const uint32_t need = ce1 > cs0 ? ((ce1 + 3u) >> 2) - wbase + 8u : 8u;   // + slack: a walk peeks up to 95 bits past the end
+        const bool fits = need <= (uint32_t)P.cmp_words;
+        if ( fits ) {
+            const uint4* src = reinterpret_cast<const uint4*>(P.clean + wbase);
+            uint4* dst = reinterpret_cast<uint4*>(s_cmp);
+            for ( uint32_t i = lane; i < (need + 3u) >> 2; i += 32 )
+                dst[i] = __ldg(src + i);
+        }
+
+        /* ---- the segment: blocks, clean byte range ---- */
+        int nblocks = 0, first_mcu = 0;
+        uint32_t len = 0;
+        W.cw = P.clean;
+        W.sw = s_cmp;
+        W.bit0 = 0;
+        if ( valid ) {
+            first_mcu = s * P.seg_mcu;
+            nblocks = min(P.seg_mcu, L.scan_mcus[scan] - first_mcu) * L.bpm;
+            const uint32_t r = P.first_rank[scan] + (uint32_t)s;   // the marker that ends the segment
+            const uint32_t ce = __ldg(P.list_cpos + r);
+            const uint32_t cs = s ? __ldg(P.list_cpos + r - 1) : P.scan_cbegin[scan];
+            /* restart markers must count D0..D7 cyclically [ref: src/gpujpeg_reader.c:1068-1071] */
+            if ( s && gl == 0 && __ldg(P.list_code + r - 1) != (uint8_t)(0xD0 + ((s - 1) & 7)) ) atomicExch(P.error, 1u);
+            len = ce > cs ? min(ce - cs, (uint32_t)SD_MAXLEN) : 0u;
+            W.cw = P.clean + (cs >> 2);
+            W.sw = s_cmp + ((cs >> 2) - wbase);
+            W.bit0 = (cs & 3u) * 8u;
+        }
+        /* first block of the segment in the coefficient buffer (one scan per component: its blocks are consecutive) */
+        int16_t* const seg_out = MODE == M_STAGED ? s_stage + (size_t)slot * segblk * 64
+                                 : IL             ? P.coef
+                                                  : P.coef + ((size_t)L.blk_off[scan] + first_mcu) * 64;
+        if ( IL ) {
+            for ( int j = gl; j < nblocks; j += lanes )
+                tgt[j] = block_target(L, scan, first_mcu, j);
+        }
+        __syncwarp();   // staged bytes and tgt visible to the whole warp
+        const uint32_t bits_all = len * 8u;
+
+        auto body = [&](auto sm_tag) {
+            constexpr bool SM = decltype(sm_tag)::value;
+            if ( MODE == M_SOLO ) {
+                if ( valid ) walk_write<DEQ, IL, M_SOLO, SM>(W, make_state(0, 0, 0), bits_all, 0, nblocks, tgt, seg_out, P.coef, nullptr);
+                return;
+            }
+            if ( MODE == M_DIRECT ) {
+                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                for ( int i = gl; i < nblocks * 8; i += lanes ) {
+                    if ( !IL ) reinterpret_cast<uint4*>(seg_out)[i] = z;
+                    else reinterpret_cast<uint4*>(P.coef + (size_t)tgt[i >> 3] * 64)[i & 7] = z;
+                }
+                for ( int j = gl; j < nblocks; j += lanes )
+                    dcd[j] = 0;
+                __syncwarp();   // the zeros are in place before any lane stores a value into the same block
+            }
+
+            /* ---- sub-sequences: one per lane of the segment's group ---- */
+            const uint32_t sub = max((uint32_t)SD_MINSUB, (len + lanes - 1) >> lanes_log2) * 8u;
+            const uint32_t p_begin = (uint32_t)gl * sub;
+            const uint32_t p_end = min(p_begin + sub, bits_all);
+            const bool active = valid && (gl == 0 || p_begin < bits_all);
+
+            /* Round 0: every lane but the first starts a little IN FRONT of its sub-sequence (two average blocks), assuming
+             * "a block starts here"; by the time the walk crosses into the lane's own bits it is, as a rule, in step with
+             * the true symbol sequence.  `start` = the state at that crossing.  Later rounds: a lane whose left neighbour
+             * ended in a different state than the lane crossed with walks again from the neighbour's end state.  Lane 0
+             * starts exact, so this is a fixed point for ANY input after at most `lanes` rounds -- in practice after
+             * round 0. */
+            const uint32_t warm = min(256u, max(32u, 2u * bits_all / (uint32_t)max(nblocks, 1)));
+            const uint32_t p_warm = gl == 0 ? 0u : p_begin - min(p_begin, warm);
+            uint32_t start = make_state(p_begin, 0, 0), end = start;
+            int dn = 0;
+            if ( active ) end = walk_state<IL, SM>(W, make_state(p_warm, 0, 0), p_begin, p_end, dn, start);
+            for ( ;; ) {
+                const uint32_t left = __shfl_up_sync(FULL, end, 1, lanes);
+                const bool dirty = active && gl != 0 && left != start;
+                if ( !__any_sync(FULL, dirty) ) break;
+                if ( dirty ) {
+                    uint32_t same;
+                    end = walk_state<IL, SM>(W, left, 0u, p_end, dn, same);
+                    start = left;
+                }
+            }
+            /* first block of every lane: prefix sum of the block counts inside the group */
+            int incl = active ? dn : 0;
+            for ( int d = 1; d < lanes; d <<= 1 ) {
+                const int t = __shfl_up_sync(FULL, incl, d, lanes);
+                if ( gl >= d ) incl += t;
+            }
+            const int n0 = incl - (active ? dn : 0);
+
+            /* ---- the walk that writes ---- */
+            if ( active ) walk_write<DEQ, IL, MODE, SM>(W, start, p_end, n0, nblocks, tgt, seg_out, P.coef, dcd);
+        };
+        if ( fits ) body(std::true_type{});
+        else body(std::false_type{});
+        __syncwarp();
+        if ( MODE == M_SOLO ) continue;   // (the barrier above also protects tgt / the staged bytes for the next unit)
+
+        /* ---- DC: prefix sum of the differences per component [ref: src/gpujpeg_huffman_cpu_decoder.c:259-268];
+         *      every lane takes a run of consecutive blocks ---- */
+        {
+            const int bpl = (nblocks + lanes - 1) >> lanes_log2;
+            const int j0 = min(nblocks, gl * bpl), j1 = min(nblocks, j0 + bpl);
+            auto diff_at = [&](int j) -> int { return MODE == M_STAGED ? (int)seg_out[(size_t)j * 64] : (int)dcd[j]; };
+            int sum[GJ_MAX_COMP] = {0, 0, 0, 0};
+            uint32_t c = IL ? (uint32_t)j0 % W.bpm : 0u;
+            for ( int j = j0; j < j1; j++ ) {
+                const int dv = diff_at(j);
+                if ( IL ) {
+                    const uint32_t ci = (W.cimap >> (2 * c)) & 3u;
+                    sum[0] += ci == 0 ? dv : 0;
+                    sum[1] += ci == 1 ? dv : 0;
+                    sum[2] += ci == 2 ? dv : 0;
+                    sum[3] += ci == 3 ? dv : 0;
+                    c = c + 1u == W.bpm ? 0u : c + 1u;
+                }
+                else {
+                    sum[0] += dv;
+                }
+            }
+            int pred[GJ_MAX_COMP] = {0, 0, 0, 0};
+#pragma unroll
+            for ( int qi = 0; qi < GJ_MAX_COMP; qi++ ) {
+                if ( qi < ncomp ) {
+                    int x = sum[qi];
+                    for ( int d = 1; d < lanes; d <<= 1 ) {
+                        const int t = __shfl_up_sync(FULL, x, d, lanes);
+                        if ( gl >= d ) x += t;
+                    }
+                    pred[qi] = x - sum[qi];
+                }
+            }
+            c = IL ? (uint32_t)j0 % W.bpm : 0u;
+            for ( int j = j0; j < j1; j++ ) {
+                const int dv = diff_at(j);
+                uint32_t ci = 0;
+                int pr;
+                if ( IL ) {
+                    ci = (W.cimap >> (2 * c)) & 3u;
+                    if ( ci == 0 ) pr = (pred[0] += dv);
+                    else if ( ci == 1 ) pr = (pred[1] += dv);
+                    else if ( ci == 2 ) pr = (pred[2] += dv);
+                    else pr = (pred[3] += dv);
+                    c = c + 1u == W.bpm ? 0u : c + 1u;
+                }
+                else {
+                    pr = (pred[0] += dv);
+                }
+                int16_t* const pos = (MODE == M_STAGED || !IL) ? seg_out + (size_t)j * 64 : P.coef + (size_t)tgt[j] * 64;
+                *pos = (int16_t)(DEQ ? pr * (int)W.q[ci * 64] : pr);
+            }
+        }
+        __syncwarp();
+
+        /* ---- staged blocks -> whole 128-byte lines; the staging area is left zeroed ---- */
+        if ( MODE == M_STAGED ) {
+            uint4* src = reinterpret_cast<uint4*>(seg_out);
+            uint4* dst = reinterpret_cast<uint4*>(P.coef + ((size_t)L.blk_off[scan] + first_mcu) * 64);   // !IL: consecutive blocks
+            for ( int i = gl; i < nblocks * 8; i += lanes ) {
+                const uint4 v = src[i];
+                src[i] = make_uint4(0u, 0u, 0u, 0u);
+                if ( !IL ) dst[i] = v;
+                else reinterpret_cast<uint4*>(P.coef + (size_t)tgt[i >> 3] * 64)[i & 7] = v;
+            }
+        }
+        __syncwarp();   // tgt / dcd / staging are reused by the next unit
+    }
+}
+
+template <bool DEQ>
+__global__ void __launch_bounds__(SD_THREADS)
+k_huff_decode_sync(const __grid_constant__ SdParams P)
+{
+    extern __shared__ __align__(16) uint8_t sm[];
+    const gj_scan_layout& L = P.lay;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cta = blockIdx.x;
+    const int scan = (cta >= P.cta_begin[1]) + (cta >= P.cta_begin[2]) + (cta >= P.cta_begin[3]);
+    const int ncomp = L.interleaved ? L.comp_count : 1;
+
+    SdTable* s_tab = reinterpret_cast<SdTable*>(sm);
+    uint16_t* s_q = reinterpret_cast<uint16_t*>(sm + (size_t)P.ncomp_tab * 2 * sizeof(SdTable));
+    uint8_t* s_warp = sm + (size_t)P.ncomp_tab * (2 * sizeof(SdTable) + 128);
+    const size_t tgt_bytes = ((size_t)P.tgt_entries * 4 + 15) & ~(size_t)15, dc_bytes = ((size_t)P.dc_entries * 2 + 15) & ~(size_t)15;
+    const size_t warp_bytes = tgt_bytes + dc_bytes + (size_t)P.stage_blocks * 128 + (size_t)P.cmp_words * 4;
+    uint32_t* s_tgt = reinterpret_cast<uint32_t*>(s_warp + warp * warp_bytes);
+    int16_t* s_dc = reinterpret_cast<int16_t*>(s_warp + warp * warp_bytes + tgt_bytes);
+    int16_t* s_stage = reinterpret_cast<int16_t*>(s_warp + warp * warp_bytes + tgt_bytes + dc_bytes);
+    uint32_t* s_cmp = reinterpret_cast<uint32_t*>(s_warp + warp * warp_bytes + tgt_bytes + dc_bytes + (size_t)P.stage_blocks * 128);
+
+    /* this scan's tables: Huffman tables by component (DC, AC), dequantisation table by component */
+    for ( int t = 0; t < 2 * ncomp; t++ ) {
+        const int ci = t >> 1, cls = t & 1;
+        const int id = cls ? P.scan_ta[scan][ci] : P.scan_td[scan][ci];
+        const uint4* f = reinterpret_cast<const uint4*>(&P.tables->fast[cls][id]);
+        uint4* d = reinterpret_cast<uint4*>(&s_tab[t]);
+        for ( int i = threadIdx.x; i < (int)(sizeof(gj_dec_fast) / 16); i += blockDim.x )
+            d[i] = __ldg(f + i);
+        const gj_dec_lut& lu = P.tables->lut[cls][id];
+        for ( int i = threadIdx.x; i < 18; i += blockDim.x ) {
+            s_tab[t].maxcode[i] = lu.maxcode[i];
+            s_tab[t].valoff[i] = lu.valoff[i];
+        }
+        for ( int i = threadIdx.x; i < 256; i += blockDim.x )
+            s_tab[t].vals[i] = lu.vals[i];
+    }
+    for ( int i = threadIdx.x; i < ncomp * 64; i += blockDim.x )
+        s_q[i] = P.tables->qinv_zz[P.scan_tq[scan][i >> 6]][i & 63];
+    {   // staging starts (and is left) all zero
+        uint4* z = reinterpret_cast<uint4*>(s_stage);
+        for ( int i = lane; i < P.stage_blocks * 8; i += 32 )
+            z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+
+    Walk W;
+    W.cw = P.clean;
+    W.sw = s_cmp;
+    W.bit0 = 0;
+    W.tab = s_tab;
+    W.q = s_q;
+    W.bpm = (uint32_t)L.bpm;
+    W.cimap = 0;
+    if ( L.interleaved )
+        for ( int i = 0; i < L.bpm; i++ )
+            W.cimap |= (uint32_t)(L.simple ? i : L.idx_comp[i]) << (2 * i);
+
+    const int mode = P.lanes_log2[scan] == 0 ? M_SOLO : P.staged[scan] ? M_STAGED : M_DIRECT;
+    if ( L.interleaved ) {
+        if ( mode == M_SOLO ) run_units<DEQ, true, M_SOLO>(P, scan, W, s_tgt, s_dc, s_stage, s_cmp);
+        else if ( mode == M_STAGED ) run_units<DEQ, true, M_STAGED>(P, scan, W, s_tgt, s_dc, s_stage, s_cmp);
+        else run_units<DEQ, true, M_DIRECT>(P, scan, W, s_tgt, s_dc, s_stage, s_cmp);
+    }
+    else {
+        if ( mode == M_SOLO ) run_units<DEQ, false, M_SOLO>(P, scan, W, s_tgt, s_dc, s_stage, s_cmp);
+        else if ( mode == M_STAGED ) run_units<DEQ, false, M_STAGED>(P, scan, W, s_tgt, s_dc, s_stage, s_cmp);
+        else run_units<DEQ, false, M_DIRECT>(P, scan, W, s_tgt, s_dc, s_stage, s_cmp);
+    }
+}
+
+}  // namespace
+
+/* Can the self-synchronising kernel take this frame?  (segments of at most SD_MAXBLK blocks, K0's clean stream and
+ * the per-scan lane counts present) */
+extern "C" int gj_huffman_decode_sync_eligible(const struct gj_huff_dec_args* a)
+{
+    if ( !a->d_clean || !a->d_list_cpos || a->seg_mcu * a->lay.bpm > SD_MAXBLK ) return 0;
+    for ( int s = 0; s < a->lay.scan_count; s++ ) {
+        const int n = a->scan_lanes[s];
+        if ( n < 1 || n > 32 || (n & (n - 1)) ) return 0;
+    }
+    return 1;
+}
+
+extern "C" int gj_launch_huffman_decode_sync(const struct gj_huff_dec_args* a, gj_stream_t stream)
+{
+    SdParams P;
+    P.lay = a->lay;
+    P.clean = a->d_clean;
+    P.list_cpos = a->d_list_cpos;
+    P.list_code = a->d_list_code;
+    P.seg_mcu = a->seg_mcu;
+    P.error = a->d_error;
+    P.coef = a->d_coef;
+    P.tables = a->d_tables;
+    const int segblk = a->seg_mcu * a->lay.bpm;
+    int total_units = 0, max_spu_tgt = 0, max_spu_dc = 0, max_spu_staged = 0;
+    size_t cmp_bytes = 0;
+    int units[GJ_MAX_COMP] = {0, 0, 0, 0};
+    for ( int s = 0; s < GJ_MAX_COMP; s++ ) {
+        P.first_rank[s] = a->first_rank[s];
+        P.scan_cbegin[s] = a->scan_cbegin[s];
+        P.lanes_log2[s] = 5;
+        P.staged[s] = 0;
+        for ( int k = 0; k < GJ_MAX_COMP; k++ ) {
+            P.scan_td[s][k] = (int8_t)a->scan_td[s][k];
+            P.scan_ta[s][k] = (int8_t)a->scan_ta[s][k];
+            P.scan_tq[s][k] = (int8_t)a->scan_tq[s][k];
+        }
+        if ( s >= a->lay.scan_count ) continue;
+        int l2 = 0;
+        while ( (1 << l2) < a->scan_lanes[s] ) l2++;
+        P.lanes_log2[s] = (uint8_t)l2;
+        const int spu = 32 >> l2;
+        P.staged[s] = spu <= 2 && a->scan_dense[s];   // dense scans stage in shared memory, sparse ones write through
+        const int segs = a->lay.scan_seg_begin[s + 1] - a->lay.scan_seg_begin[s];
+        units[s] = (segs + spu - 1) / spu;
+        total_units += units[s];
+        /* staging area for a unit's clean bytes: twice the scan's average, so that nearly every unit fits */
+        const size_t want = 2 * ((size_t)a->scan_bytes[s] / (size_t)(segs > 0 ? segs : 1) + 16) * (size_t)spu + 64;
+        if ( want > cmp_bytes ) cmp_bytes = want;
+        if ( a->lay.interleaved && spu > max_spu_tgt ) max_spu_tgt = spu;
+        if ( P.staged[s] && spu > max_spu_staged ) max_spu_staged = spu;
+        if ( !P.staged[s] && l2 > 0 && spu > max_spu_dc ) max_spu_dc = spu;
+    }
+    int sms = 148;
+    int dev = 0;
+    if ( cudaGetDevice(&dev) != cudaSuccess ) return -1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    /* warps per CTA and units per warp: at least ~4 CTAs per SM when there is that much work, at most 8 warps per CTA
+     * (the tables are loaded once per CTA) */
+    int nw = 1;
+    while ( nw < SD_WARPS && total_units / (2 * nw) >= sms * 4 ) nw *= 2;
+    int upw = total_units / (sms * 8 * nw);
+    upw = upw < 1 ? 1 : upw > 8 ? 8 : upw;
+    P.units_per_warp = upw;
+    int cta = 0;
+    for ( int s = 0; s <= GJ_MAX_COMP; s++ ) {
+        P.cta_begin[s] = cta;
+        if ( s < GJ_MAX_COMP ) cta += (units[s] + nw * upw - 1) / (nw * upw);
+    }
+    P.ncomp_tab = a->lay.interleaved ? a->lay.comp_count : 1;
+    P.tgt_entries = max_spu_tgt * segblk;
+    P.dc_entries = max_spu_dc * segblk;
+    P.stage_blocks = max_spu_staged * segblk;
+    if ( cmp_bytes > 40 * 1024 ) cmp_bytes = 40 * 1024;
+    P.cmp_words = (int)((cmp_bytes + 15) / 16) * 4;
+    const size_t tgt_bytes = ((size_t)P.tgt_entries * 4 + 15) & ~(size_t)15, dc_bytes = ((size_t)P.dc_entries * 2 + 15) & ~(size_t)15;
+    const size_t smem = (size_t)P.ncomp_tab * (2 * sizeof(SdTable) + 128) + (size_t)nw * (tgt_bytes + dc_bytes + (size_t)P.stage_blocks * 128 + (size_t)P.cmp_words * 4);
+    if ( smem > 200 * 1024 ) return -1;
+    static int attr_done[64];   // 0 = not yet; set once per device (benign if two threads race: same value)
+    if ( dev < 0 || dev >= 64 ) return -1;
+    if ( !__atomic_load_n(&attr_done[dev], __ATOMIC_ACQUIRE) ) {
+        if ( cudaFuncSetAttribute(k_huff_decode_sync<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+             cudaFuncSetAttribute(k_huff_decode_sync<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess )
+            return -1;
+        __atomic_store_n(&attr_done[dev], 1, __ATOMIC_RELEASE);
+    }
+    if ( cta == 0 ) return 0;
+    if ( a->dequantize )
+        k_huff_decode_sync<true><<<cta, nw * 32, smem, stream>>>(P);
+    else
+        k_huff_decode_sync<false><<<cta, nw * 32, smem, stream>>>(P);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}

@@ -892,7 +892,7 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file
             start = a.scan_begin[scan];
         }
         else {
-            const uint32_t m = a.d_first_rank[scan] + (uint32_t)s - 1u;
+            const uint32_t m = a.first_rank[scan] + (uint32_t)s - 1u;
             start = a.d_list_pos[m] + 2u;
             /* restart markers must count D0..D7 cyclically [ref: src/gpujpeg_reader.c:1068-1071] */
             if ( a.d_list_code[m] != (uint8_t)(0xD0 + ((s - 1) & 7)) ) atomicExch(a.d_error, 1u);
@@ -1035,8 +1035,14 @@ extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_str
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+extern "C" int gj_huffman_decode_sync_eligible(const struct gj_huff_dec_args* a);
+extern "C" int gj_launch_huffman_decode_sync(const struct gj_huff_dec_args* a, gj_stream_t stream);
+
 extern "C" int gj_launch_huffman_decode(const struct gj_huff_dec_args* a, gj_stream_t stream)
 {
+    /* restart segments of at most 40 blocks (every RESTART_AUTO setting): several lanes per segment, self-synchronising
+     * (gj_huffdec.cu); longer segments: one thread per segment (below) */
+    if ( !a->force_thread_per_segment && gj_huffman_decode_sync_eligible(a) ) return gj_launch_huffman_decode_sync(a, stream);
     /* segment owners per warp: few segments cannot fill the machine, so the shorter lock-step chains of fewer owners
      * win; many dense segments need the lanes (see the measurements at HD_SEGMENTS_PER_WARP).  With one scan per
      * component the luminance scan carries most of the bits and finishes last: it gets fewer owners per warp than

@@ -78,6 +78,23 @@ struct gj_dec_lut {
 };
 int gj_dec_lut_build(const struct gj_huff_spec* spec, struct gj_dec_lut* lut);
 
+/* Fast decoder table, one per (class, id), indexed by the next GJ_DEC_FAST_BITS bits of the stream.  One entry tells
+ * the decoder everything it needs to step over a symbol AND its value bits:
+ *   bits  0-4   code length + value size (bits to consume), never 0 for a code
+ *   bits  5-11  advance of the zig-zag index: DC 1; AC run + 1, ZRL 16, EOB (and the invalid run/0 symbols) 64
+ *   bits 12-15  value size
+ * Codes longer than GJ_DEC_FAST_BITS: the entry of their 10-bit prefix has bits 0-4 == 0 and names a second-level
+ * table (bits 5-15 = its number + 1) indexed by the following 16 - GJ_DEC_FAST_BITS bits, same entry format; the
+ * standard tables need 4 of them.  0 = no such code / more prefixes than second-level tables: canonical search in
+ * gj_dec_lut. */
+#define GJ_DEC_FAST_BITS 10
+#define GJ_DEC_FAST_SUBS 8
+struct gj_dec_fast {
+    uint16_t e[1 << GJ_DEC_FAST_BITS];
+    uint16_t sub[GJ_DEC_FAST_SUBS][1 << (16 - GJ_DEC_FAST_BITS)];
+};
+void gj_dec_fast_build(const struct gj_huff_spec* spec, int is_ac, struct gj_dec_fast* fast);
+
 /* ---- geometry (gj_codestream.c)  [ref: src/gpujpeg_common.c:628-1106] ---- */
 #define GJ_MAX_MCU_BLOCKS 10  /* T.81 B.2.3: at most 10 data units per MCU */
 
@@ -206,6 +223,7 @@ struct gj_dev_enc_tables {
 struct gj_dev_dec_tables {
     uint16_t qinv_zz[4][64];  /* dequantisation tables by table id, zig-zag order */
     struct gj_dec_lut lut[2][4];
+    struct gj_dec_fast fast[2][4];
 };
 
 /* K1: RGB u8 interleaved -> quantised zig-zag coefficients (fused colour transform + FDCT + quant)
@@ -245,12 +263,23 @@ struct gj_huff_dec_args {
     const uint32_t* d_seg_off;  /* host-built table: [seg_count] file offset of each segment (or NULL) */
     const uint32_t* d_seg_len;  /* informative: the decoder stops after the segment's block count */
     /* device-built marker list (K0): segment j of scan s starts at scan_begin[s] (j = 0) or two bytes
-     * after marker number d_first_rank[s] + j - 1 */
+     * after marker number first_rank[s] + j - 1 */
     const uint32_t* d_list_pos;
     const uint8_t* d_list_code;
-    const uint32_t* d_first_rank; /* [scan_count], written by gj_launch_scan_ranks */
+    uint32_t first_rank[GJ_MAX_COMP];  /* markers in front of the scan's first byte (host, from K0's marker report) */
     uint32_t scan_begin[GJ_MAX_COMP];
     uint32_t* d_error;            /* set to non-zero by K3 when the RSTn sequence is broken */
+    /* the clean stream (K0): stuffing, fill bytes and markers removed, big-endian words.  Segment j of scan s occupies
+     * the clean bytes [scan_cbegin[s] or d_list_cpos[first_rank[s] + j - 1], d_list_cpos[first_rank[s] + j]) */
+    const uint32_t* d_clean;
+    const uint32_t* d_list_cpos;
+    uint32_t scan_cbegin[GJ_MAX_COMP];
+    /* self-synchronising decoder: lanes that share one restart segment in scan s (4, 8, 16 or 32), from the scan's
+     * average segment size; 0 = not computed (the thread-per-segment kernel is used) */
+    uint8_t scan_lanes[GJ_MAX_COMP];
+    uint32_t scan_bytes[GJ_MAX_COMP];  /* entropy-coded bytes of scan s (as in the file) */
+    uint8_t scan_dense[GJ_MAX_COMP];   /* >= 16 bytes of entropy-coded data per block: worth staging blocks in shared memory */
+    int force_thread_per_segment;   /* dec_opt_huffman=thread_per_segment: always the one-thread-per-segment kernel */
     int dequantize;             /* 1: store coefficient*quantiser wrapped to int16 (integer IDCT flavour) */
     struct gj_scan_layout lay;  /* scans, segments and the block order inside them */
     int seg_count, seg_mcu;
@@ -264,12 +293,9 @@ int gj_launch_huffman_decode(const struct gj_huff_dec_args* a, gj_stream_t strea
 
 /* K0: marker list of the entropy-coded part of the file, built on the device (gj_markers.cu)
  * [replaces ref: src/gpujpeg_reader.c:1038-1155] */
-int gj_launch_marker_scan(const uint8_t* d_file, size_t begin, size_t end, uint32_t* d_cta, uint32_t* d_list_pos,
-                          uint8_t* d_list_code, uint32_t list_cap, uint32_t* d_result, uint32_t* d_other, uint32_t other_cap,
-                          gj_stream_t stream);
-/* rank of the first marker of every scan + restart-count validation (error -> d_result[3]) */
-int gj_launch_scan_ranks(const uint32_t* d_list_pos, const uint32_t* d_result, int scan_count, const uint32_t scan_begin[4],
-                         const uint32_t scan_end[4], const int scan_segments[4], uint32_t* d_first_rank, gj_stream_t stream);
+int gj_launch_marker_scan(const uint8_t* d_file, size_t begin, size_t end, unsigned long long* d_cta, uint32_t* d_list_pos,
+                          uint8_t* d_list_code, uint32_t* d_list_cpos, uint32_t list_cap, uint8_t* d_clean, uint32_t* d_result,
+                          uint32_t* d_other, uint32_t other_cap, gj_stream_t stream);
 
 /* K4: zig-zag coefficients -> RGB u8 interleaved (fused dequant + IDCT + colour transform)
  * idct_flavour: 0 = integer (gpujpeg_idct_cpu), 1 = float GPU-reference
@@ -334,6 +360,7 @@ void gj_timer_start(struct gj_timer* t, gj_stream_t s);
 void gj_timer_stop(struct gj_timer* t, gj_stream_t s);
 double gj_timer_ms(struct gj_timer* t);
 int gj_cuda_device_count(void);
+int gj_cuda_sm_count(void);   /* multiprocessors of the current device (148 on a B200); 1 on failure */
 int gj_cuda_device_props(int dev, struct gpujpeg_device_info* info);
 int gj_cuda_set_device(int dev);
 int gj_cuda_get_device(void);

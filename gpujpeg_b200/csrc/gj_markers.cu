@@ -1,20 +1,28 @@
 /*
- * gj_markers.cu -- K0: finds every marker inside the entropy-coded part of a JPEG file on the GPU.
+ * gj_markers.cu -- K0: on the GPU, finds every marker inside the entropy-coded part of a JPEG file and writes the
+ * "clean" entropy stream next to it: the same bytes with stuffed zeros, fill bytes and the markers themselves taken
+ * out, stored as big-endian 32-bit words so that the Huffman decoder reads any bit position with two aligned loads
+ * and one funnel shift.
  *
  * The reference splits scans into restart segments on the host with a memchr(0xFF) walk over the whole
  * stream and copies every segment into a second buffer (src/gpujpeg_reader.c:1038-1155); its FAQ quotes
  * 543 ms for that step on one sample.  On a B200 host the same walk costs 2.1 ms for an 8K frame --
  * six times the GPU time of the entire decode.  Here the file is uploaded once, untouched, and three
- * small launches build the ordered marker list (position, code) directly in device memory:
+ * small launches do the reader's per-byte work in device memory:
  *
- *     k_marker_count   per-CTA marker counts (16 bytes per thread, one 16-byte load)
+ *     k_marker_count   per-CTA counts of markers and of bytes that stay in the clean stream (16 bytes per thread)
  *     k_marker_scan    exclusive scan of the CTA counts (one CTA)
- *     k_marker_write   ordered compaction: list[rank] = {position, code}; markers other than RSTn are
- *                      also appended (with their rank) to a short list the host reads back
+ *     k_marker_write   ordered compaction: list[rank] = {raw position, code, clean position}; the kept bytes go to
+ *                      their clean position; markers other than RSTn are also appended to a short list the host
+ *                      reads back (scan ends, ranks: everything the host needs to finish the marker walk)
  *
  * Inside entropy-coded data a 0xFF byte is always followed by 0x00 (stuffing), 0xFF (fill) or a marker
- * code, so "FF xx, xx not in {00, FF}" is exact there.  The host only trusts the list inside scans; the
- * marker segments between scans are walked on the host by their length fields (gj_decoder.c).
+ * code, so "FF xx, xx not in {00, FF}" is exact there.  A byte stays in the clean stream unless it is
+ *     0xFF not followed by 0x00      (first byte of a marker, or a fill byte),   or
+ *     a non-0xFF byte after 0xFF     (the stuffed zero, or the marker's code).
+ * The host only trusts the lists inside scans; the marker segments between scans are walked on the host by
+ * their length fields (gj_decoder.c), and the clean position of a scan's first byte is derived there from the
+ * clean position of the SOS marker in front of it.
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -28,11 +36,12 @@ constexpr int MK_BYTES = 16;                       // bytes per thread
 constexpr int MK_TILE = MK_THREADS * MK_BYTES;     // bytes per CTA
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
-/* bit i of the result is set when byte i of the thread's 16-byte chunk starts a marker */
-__device__ __forceinline__ uint32_t marker_bits(const uint8_t* __restrict__ file, size_t begin, size_t end, size_t pos,
-                                                uint32_t (&w)[5])
+/* The thread's 16-byte chunk [pos, pos+16): bit i of `markers` is set when byte i starts a marker, bit i of `keep`
+ * when byte i belongs to the clean stream.  w[] receives the chunk plus four look-ahead bytes. */
+__device__ __forceinline__ void classify(const uint8_t* __restrict__ file, size_t begin, size_t end, size_t pos, uint32_t (&w)[5],
+                                         uint32_t& markers, uint32_t& keep)
 {
-    // chunk [pos, pos+16) plus one look-ahead byte; positions are relative to the 16-byte aligned `begin`
+    // positions are relative to the 16-byte aligned tile base below `begin`
     if ( pos + MK_BYTES + 4 <= end ) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(file + pos));
         w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
@@ -50,23 +59,31 @@ __device__ __forceinline__ uint32_t marker_bits(const uint8_t* __restrict__ file
             w[i] = x;
         }
     }
-    uint32_t bits = 0;
+    uint32_t prev = pos > begin ? (uint32_t)__ldg(file + pos - 1) : 0u;   // the byte in front of the scan is never 0xFF
+    markers = 0;
+    keep = 0;
 #pragma unroll
     for ( int i = 0; i < MK_BYTES; i++ ) {
         const uint32_t b0 = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
         const uint32_t b1 = (w[(i + 1) >> 2] >> (8 * ((i + 1) & 3))) & 0xFFu;
-        if ( b0 == 0xFFu && b1 != 0u && b1 != 0xFFu && pos + i >= begin && pos + i + 1 < end ) bits |= 1u << i;
+        const bool inside = pos + i >= begin && pos + i < end;
+        const bool has_next = pos + i + 1 < end;
+        if ( inside && b0 == 0xFFu && b1 != 0u && b1 != 0xFFu && has_next ) markers |= 1u << i;
+        const bool drop = (b0 == 0xFFu && b1 != 0u && has_next) || (prev == 0xFFu && b0 != 0xFFu);
+        if ( inside && !drop ) keep |= 1u << i;
+        prev = b0;
     }
-    return bits;
 }
 
+/* per CTA: low word = markers, high word = kept bytes */
 __global__ void __launch_bounds__(MK_THREADS)
-k_marker_count(const uint8_t* __restrict__ file, size_t begin, size_t end, size_t base, uint32_t* __restrict__ cta_count)
+k_marker_count(const uint8_t* __restrict__ file, size_t begin, size_t end, size_t base, unsigned long long* __restrict__ cta_count)
 {
     __shared__ uint32_t s_warp[MK_THREADS / 32];
     const size_t pos = base + (size_t)blockIdx.x * MK_TILE + (size_t)threadIdx.x * MK_BYTES;
-    uint32_t w[5];
-    uint32_t n = pos < end ? __popc(marker_bits(file, begin, end, pos, w)) : 0u;
+    uint32_t w[5], markers = 0, keep = 0;
+    if ( pos < end ) classify(file, begin, end, pos, w, markers, keep);
+    uint32_t n = (uint32_t)__popc(markers) << 16 | (uint32_t)__popc(keep);   // <= 2048 / 4096 per CTA: no carry between the halves
 #pragma unroll
     for ( int d = 16; d > 0; d >>= 1 )
         n += __shfl_down_sync(FULL, n, d);
@@ -76,56 +93,61 @@ k_marker_count(const uint8_t* __restrict__ file, size_t begin, size_t end, size_
         uint32_t t = 0;
         for ( int i = 0; i < MK_THREADS / 32; i++ )
             t += s_warp[i];
-        cta_count[blockIdx.x] = t;
+        cta_count[blockIdx.x] = (unsigned long long)(t >> 16) | (unsigned long long)(t & 0xFFFFu) << 32;
     }
 }
 
 __global__ void __launch_bounds__(1024)
-k_marker_scan(uint32_t* __restrict__ cta_count, int n_cta, uint32_t* __restrict__ result /*[0]=total*/)
+k_marker_scan(unsigned long long* __restrict__ cta_count, int n_cta, uint32_t* __restrict__ result /*[0]=markers, [5]=clean bytes*/)
 {
-    __shared__ uint32_t s_warp[32];
+    __shared__ unsigned long long s_warp[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t carry = 0;
+    unsigned long long carry = 0;
     for ( int base = 0; base < n_cta; base += 1024 ) {
         const int i = base + threadIdx.x;
-        const uint32_t v = i < n_cta ? cta_count[i] : 0u;
-        uint32_t incl = v;
+        const unsigned long long v = i < n_cta ? cta_count[i] : 0ull;
+        unsigned long long incl = v;
 #pragma unroll
         for ( int d = 1; d < 32; d <<= 1 ) {
-            const uint32_t t = __shfl_up_sync(FULL, incl, d);
+            const unsigned long long t = __shfl_up_sync(FULL, incl, d);
             if ( lane >= d ) incl += t;
         }
         if ( lane == 31 ) s_warp[warp] = incl;
         __syncthreads();
         if ( warp == 0 ) {
-            uint32_t x = s_warp[lane];
+            unsigned long long x = s_warp[lane];
 #pragma unroll
             for ( int d = 1; d < 32; d <<= 1 ) {
-                const uint32_t t = __shfl_up_sync(FULL, x, d);
+                const unsigned long long t = __shfl_up_sync(FULL, x, d);
                 if ( lane >= d ) x += t;
             }
             s_warp[lane] = x;
         }
         __syncthreads();
-        if ( i < n_cta ) cta_count[i] = carry + (warp ? s_warp[warp - 1] : 0u) + incl - v;   // exclusive
+        if ( i < n_cta ) cta_count[i] = carry + (warp ? s_warp[warp - 1] : 0ull) + incl - v;   // exclusive
         carry += s_warp[31];
         __syncthreads();
     }
-    if ( threadIdx.x == 0 ) result[0] = carry;
+    if ( threadIdx.x == 0 ) {
+        result[0] = (uint32_t)carry;
+        result[5] = (uint32_t)(carry >> 32);
+    }
 }
 
 __global__ void __launch_bounds__(MK_THREADS)
-k_marker_write(const uint8_t* __restrict__ file, size_t begin, size_t end, size_t base, const uint32_t* __restrict__ cta_base,
-               uint32_t* __restrict__ list_pos, uint8_t* __restrict__ list_code, uint32_t list_cap,
-               uint32_t* __restrict__ result /*[1]=other count, [2]=overflow*/, uint32_t* __restrict__ other /*{rank,pos,code}*/,
-               uint32_t other_cap)
+k_marker_write(const uint8_t* __restrict__ file, size_t begin, size_t end, size_t base, const unsigned long long* __restrict__ cta_base,
+               uint32_t* __restrict__ list_pos, uint8_t* __restrict__ list_code, uint32_t* __restrict__ list_cpos, uint32_t list_cap,
+               uint8_t* __restrict__ clean, uint32_t* __restrict__ result /*[1]=other count, [2]=overflow*/,
+               uint32_t* __restrict__ other /*{rank,pos,code,cpos}*/, uint32_t other_cap)
 {
     __shared__ uint32_t s_warp[MK_THREADS / 32];
+    __shared__ __align__(16) uint8_t s_bytes[MK_TILE + 8];
+    __shared__ uint32_t s_total;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t pos = base + (size_t)blockIdx.x * MK_TILE + (size_t)threadIdx.x * MK_BYTES;
-    uint32_t w[5];
-    uint32_t bits = pos < end ? marker_bits(file, begin, end, pos, w) : 0u;
-    const uint32_t n = __popc(bits);
+    uint32_t w[5], bits = 0, keep = 0;
+    if ( pos < end ) classify(file, begin, end, pos, w, bits, keep);
+    const uint32_t n = (uint32_t)__popc(bits) << 16 | (uint32_t)__popc(keep);
     uint32_t incl = n;
 #pragma unroll
     for ( int d = 1; d < 32; d <<= 1 ) {
@@ -134,16 +156,53 @@ k_marker_write(const uint8_t* __restrict__ file, size_t begin, size_t end, size_
     }
     if ( lane == 31 ) s_warp[warp] = incl;
     __syncthreads();
-    uint32_t rank = cta_base[blockIdx.x] + incl - n;
+    uint32_t before = incl - n;
     for ( int i = 0; i < warp; i++ )
-        rank += s_warp[i];
+        before += s_warp[i];
+    const unsigned long long cb = cta_base[blockIdx.x];
+    uint32_t rank = (uint32_t)cb + (before >> 16);
+    const uint32_t cpos0 = (uint32_t)(cb >> 32) + (before & 0xFFFFu);
+
+    /* The kept bytes, big-endian inside 32-bit words (clean byte c lives at address c ^ 3).  They are first compacted
+     * in shared memory on the global word grid and then written out with coalesced 32-bit stores: scattered byte stores
+     * straight to global memory (the first version) made this kernel five times slower than the scan itself. */
+    const uint32_t cta_c0 = (uint32_t)(cb >> 32);          // clean position of the CTA's first kept byte
+    const uint32_t word0 = cta_c0 >> 2;                     // first global word the CTA touches
+    {
+        uint32_t c = cpos0 - word0 * 4u, m = keep;
+        while ( m ) {
+            const int i = __ffs(m) - 1;
+            m &= m - 1;
+            s_bytes[c ^ 3u] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+            c++;
+        }
+    }
+    if ( threadIdx.x == MK_THREADS - 1 ) s_total = (before & 0xFFFFu) + (n & 0xFFFFu);   // kept bytes of the whole CTA
+    __syncthreads();
+    {
+        const uint32_t c_end = cta_c0 + s_total;                                   // one past the CTA's last clean byte
+        const uint32_t wfirst = (cta_c0 + 3u) >> 2, wlast = c_end >> 2;            // words owned entirely: [wfirst, wlast)
+        uint32_t* gw = reinterpret_cast<uint32_t*>(clean);
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(s_bytes);
+        for ( uint32_t wi = wfirst + threadIdx.x; wi < wlast; wi += MK_THREADS )
+            gw[wi] = sw[wi - word0];
+        /* the words shared with the neighbouring CTAs: byte by byte */
+        if ( threadIdx.x < 8 ) {
+            const uint32_t c = threadIdx.x < 4 ? cta_c0 + threadIdx.x : (wlast << 2) + (threadIdx.x - 4);
+            const bool head = threadIdx.x < 4 && c < (wfirst << 2) && c < c_end;
+            const bool tail = threadIdx.x >= 4 && c >= cta_c0 && c < c_end && (wlast >= wfirst);
+            if ( head || tail ) clean[c ^ 3u] = s_bytes[(c - word0 * 4u) ^ 3u];
+        }
+    }
     while ( bits ) {
         const int i = __ffs(bits) - 1;
         bits &= bits - 1;
         const uint32_t code = (w[(i + 1) >> 2] >> (8 * ((i + 1) & 3))) & 0xFFu;
+        const uint32_t cpos = cpos0 + __popc(keep & ((1u << i) - 1u));
         if ( rank < list_cap ) {
             list_pos[rank] = (uint32_t)(pos + i);
             list_code[rank] = (uint8_t)code;
+            list_cpos[rank] = cpos;
         }
         else {
             result[2] = 1;
@@ -151,74 +210,36 @@ k_marker_write(const uint8_t* __restrict__ file, size_t begin, size_t end, size_
         if ( code < 0xD0u || code > 0xD7u ) {
             const uint32_t k = atomicAdd(&result[1], 1u);
             if ( k < other_cap ) {
-                other[3 * k] = rank;
-                other[3 * k + 1] = (uint32_t)(pos + i);
-                other[3 * k + 2] = code;
+                other[4 * k] = rank;
+                other[4 * k + 1] = (uint32_t)(pos + i);
+                other[4 * k + 2] = code;
+                other[4 * k + 3] = cpos;
             }
         }
         rank++;
     }
 }
 
-struct ScanBounds {
-    uint32_t begin[4], end[4];
-    int segments[4];   // restart segments the geometry expects in each scan
-};
-/* one thread per scan: rank of its first marker in the list and a check of the restart count */
-__global__ void k_scan_ranks(const uint32_t* __restrict__ list_pos, uint32_t* result, int scan_count, ScanBounds sb,
-                             uint32_t* __restrict__ first_rank)
-{
-    const int s = threadIdx.x;
-    if ( s >= scan_count ) return;
-    const uint32_t total = result[0];
-    uint32_t r[2];
-    const uint32_t key[2] = {sb.begin[s], sb.end[s]};
-    for ( int q = 0; q < 2; q++ ) {   // lower_bound
-        uint32_t lo = 0, hi = total;
-        while ( lo < hi ) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if ( list_pos[mid] < key[q] ) lo = mid + 1;
-            else hi = mid;
-        }
-        r[q] = lo;
-    }
-    first_rank[s] = r[0];
-    if ( r[1] - r[0] != (uint32_t)(sb.segments[s] - 1) ) atomicExch(&result[3], 1u + (uint32_t)s);
-}
-
 }  // namespace
 
-extern "C" int gj_launch_scan_ranks(const uint32_t* d_list_pos, const uint32_t* d_result, int scan_count,
-                                    const uint32_t scan_begin[4], const uint32_t scan_end[4], const int scan_segments[4],
-                                    uint32_t* d_first_rank, gj_stream_t stream)
-{
-    ScanBounds sb;
-    for ( int i = 0; i < 4; i++ ) {
-        sb.begin[i] = scan_begin[i];
-        sb.end[i] = scan_end[i];
-        sb.segments[i] = scan_segments[i];
-    }
-    k_scan_ranks<<<1, 32, 0, stream>>>(d_list_pos, const_cast<uint32_t*>(d_result), scan_count, sb, d_first_rank);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
-}
-
 /* Scans file[begin, end) (device memory; begin need not be aligned).  Outputs, all in device memory:
- *   d_list_pos/d_list_code[0..total) : every marker in file order
- *   d_result[0] = total, [1] = number of non-RST markers, [2] = overflow flag
- *   d_other[3*k..] = {rank, position, code} of the non-RST markers (unordered, at most other_cap)
- * d_cta must hold ceil((end - begin + 16) / 4096) + 1 words. */
-extern "C" int gj_launch_marker_scan(const uint8_t* d_file, size_t begin, size_t end, uint32_t* d_cta, uint32_t* d_list_pos,
-                                     uint8_t* d_list_code, uint32_t list_cap, uint32_t* d_result, uint32_t* d_other,
-                                     uint32_t other_cap, gj_stream_t stream)
+ *   d_list_pos/d_list_code/d_list_cpos[0..total) : every marker in file order: raw position, code, position in the clean stream
+ *   d_clean                                      : the clean stream (big-endian words; must hold end - begin + 16 bytes)
+ *   d_result[0] = total markers, [1] = number of non-RST markers, [2] = list overflow flag, [5] = clean bytes
+ *   d_other[4*k..] = {rank, position, code, clean position} of the non-RST markers (unordered, at most other_cap)
+ * d_cta must hold ceil((end - begin + 16) / 4096) + 1 64-bit words. */
+extern "C" int gj_launch_marker_scan(const uint8_t* d_file, size_t begin, size_t end, unsigned long long* d_cta, uint32_t* d_list_pos,
+                                     uint8_t* d_list_code, uint32_t* d_list_cpos, uint32_t list_cap, uint8_t* d_clean,
+                                     uint32_t* d_result, uint32_t* d_other, uint32_t other_cap, gj_stream_t stream)
 {
     if ( end <= begin ) return -1;
     /* d_file comes from cudaMalloc (256-byte aligned): tile from a 16-byte aligned base below `begin` */
     const size_t base = begin & ~static_cast<size_t>(15);
     const int n_cta = (int)((end - base + MK_TILE - 1) / MK_TILE);
-    if ( cudaMemsetAsync(d_result, 0, 4 * sizeof(uint32_t), stream) != cudaSuccess ) return -1;
+    if ( cudaMemsetAsync(d_result, 0, 8 * sizeof(uint32_t), stream) != cudaSuccess ) return -1;
     k_marker_count<<<n_cta, MK_THREADS, 0, stream>>>(d_file, begin, end, base, d_cta);
     k_marker_scan<<<1, 1024, 0, stream>>>(d_cta, n_cta, d_result);
-    k_marker_write<<<n_cta, MK_THREADS, 0, stream>>>(d_file, begin, end, base, d_cta, d_list_pos, d_list_code, list_cap,
-                                                     d_result, d_other, other_cap);
+    k_marker_write<<<n_cta, MK_THREADS, 0, stream>>>(d_file, begin, end, base, d_cta, d_list_pos, d_list_code, d_list_cpos, list_cap,
+                                                     d_clean, d_result, d_other, other_cap);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -472,6 +472,14 @@ GPUJPEG_API int gpujpeg_decoder_get_image_info(uint8_t* image, size_t image_size
 #define GPUJPEG_DEC_OPT_IDCT "dec_opt_idct"
 #define GPUJPEG_DEC_IDCT_VAL_INT "int"
 #define GPUJPEG_DEC_IDCT_VAL_FLOAT_GPUREF "float_gpuref"
+/* extension: which Huffman decoder kernel runs.  "auto" (default): several lanes per restart segment, self-synchronising,
+ * for segments of at most 40 blocks, one thread per segment otherwise; "thread_per_segment": always the latter */
+#define GPUJPEG_DEC_OPT_HUFFMAN "dec_opt_huffman"
+#define GPUJPEG_DEC_HUFFMAN_VAL_AUTO "auto"
+#define GPUJPEG_DEC_HUFFMAN_VAL_THREAD_PER_SEGMENT "thread_per_segment"
+/* extension (tuning): lanes that share one restart segment in the self-synchronising decoder: 0 = chosen per scan from
+ * the scan's bytes per segment (default), or 4, 8, 16, 32 for every scan */
+#define GPUJPEG_DEC_OPT_HUFFMAN_LANES "dec_opt_huffman_lanes"
 GPUJPEG_API int gpujpeg_decoder_set_option(struct gpujpeg_decoder* decoder, const char* opt, const char* val);
 GPUJPEG_API void gpujpeg_decoder_print_options(void);
 
