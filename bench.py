@@ -110,6 +110,30 @@ class ClockSampler:
                 "samples": len(sm), "source": self.src}
 
 
+def bind_to_gpu_numa_node(local):
+    """Pins this rank's host threads (and, by first touch, its pinned buffers) to the NUMA node its GPU hangs off: with
+    8 ranks each moving 2 x 100 MB per step through one host, remote-node memory traffic was the end-to-end limiter of
+    round 1 (VERDICT weak item 7).  Returns a short description for the record, or None when sysfs does not say."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"gpu": bus, "node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+
+
 def host_cores():
     """cores this process may actually use: min(affinity mask, cgroup CPU quota)"""
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -199,6 +223,168 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def nccl_transport_line(path):
+    """the first line of rank 0's NCCL_DEBUG=INFO log that names the transport of a peer connection"""
+    try:
+        lines = open(path).read().splitlines()
+    except Exception:
+        return None
+    for key in (" via P2P", "via SHM", "via NET", "P2P/", "NVLS", "Channel"):
+        for ln in lines:
+            if key in ln:
+                return ln.split("NCCL INFO", 1)[-1].strip()[:200]
+    return "no transport line among %d log lines" % len(lines)
+
+
+def scatter_gather_extra(g, torch, dist, rank, world, dev, enc, dec, frame_dev, width, height, rst, steps, nccl_log):
+    """SURVEY.md section 8e "scattered from GPU 0": rank 0 holds one raw frame per rank on ITS GPU, sends them to their
+    owners (NCCL point-to-point, gpujpeg_b200/batch.py), every rank encodes and decodes its frame through the C API with
+    device buffers, and the JPEG streams are gathered (gather-v) on rank 0.  Timed on the device, max over ranks."""
+    from gpujpeg_b200 import batch as bt
+    npix = width * height
+    frames = [frame_dev.clone() for _ in range(world)] if rank == 0 else None
+    d_out = torch.empty((height, width, 3), dtype=torch.uint8, device=dev)
+
+    def once():
+        mine = bt.scatter_frames(frames, world, (height, width, 3), src=0, device=dev)
+        streams = []
+        for f in mine:
+            j = enc.encode(f, QUALITY, rst)
+            dec.decode(j, out=d_out)
+            streams.append(torch.from_numpy(j).to(dev))
+        return bt.gather_streams(streams, world, dst=0, device=dev)
+
+    def timed_transfer(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        dist.barrier(); torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / n
+
+    for _ in range(2):
+        got = once()
+    ms = timed_transfer(once, steps)
+    # the scatter alone: what the transport gives (bytes leaving rank 0 / time)
+    ms_scatter = timed_transfer(lambda: bt.scatter_frames(frames, world, (height, width, 3), src=0, device=dev), steps)
+    out = None
+    if rank == 0:
+        out = {"value": round(world * npix / (ms * 1e-3) / 1e6, 1), "unit": "Mpix/s", "ms_per_step": round(ms, 3),
+               "what": "one %dx%d frame per rank: NCCL send/recv of the raw frames from rank 0's GPU to their owners, encode + "
+                       "decode through the C API with device buffers, gather-v of the JPEG streams to rank 0" % (width, height),
+               "scatter_ms": round(ms_scatter, 3),
+               "scatter_gbs": round((world - 1) * npix * 3 / (ms_scatter * 1e-3) / 1e9, 1),
+               "gathered_stream_bytes": [int(x.numel()) for x in got],
+               "nccl_transport": nccl_transport_line(nccl_log) if nccl_log else os.environ.get("NCCL_DEBUG_FILE")}
+    return out
+
+
+def run_batch(args, g, o, torch, dist, rank, world, local, dev, numa, nccl_log):
+    """BASELINE.json config 5 (`--size 16k --batch 32`): a FIXED batch of frames, frame f on rank f mod N (strong scaling).
+    Two numbers per run, both whole-batch Mpix/s, device-timed, max over ranks:
+      value            frames resident on their owners' GPUs: gpujpeg_encoder_encode (GPU image in, JPEG to the host) +
+                       gpujpeg_decoder_decode (JPEG from the host, pixels into a CUDA buffer) per frame
+      scattered.value  all raw frames on rank 0's GPU first: NCCL scatter to the owners, the same coding, gather-v of
+                       the streams on rank 0"""
+    import numpy as np
+    from gpujpeg_b200 import batch as bt
+    width, height, rst = WORKLOADS[args.size]
+    npix, n_frames = width * height, args.batch
+    mine = bt.my_frames(n_frames, world, rank)
+    base = [torch.from_numpy(o.gen_image(args.kind, width, height, seed=12345 + k)) for k in range(min(4, n_frames))]
+    stream = torch.cuda.current_stream().cuda_stream
+    enc = g.Encoder(stream=stream, pinned_output=True)
+    dec = g.Decoder(stream=stream)
+    d_frames = [base[f % len(base)].to(dev) for f in mine]
+    d_out = torch.empty((height, width, 3), dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / n
+
+    sizes = []
+
+    import ctypes
+    p_enc = g.api.default_parameters(QUALITY, rst)
+    p_img = g.api.image_parameters(width, height)
+
+    def code(f):
+        """encode a device-resident frame, decode the stream into a device buffer; returns the stream as a zero-copy view"""
+        addr, size = enc.encode_raw(f, p_enc, p_img, device=True)
+        dec.decode_raw(addr, size, g.api.GPUJPEG_DECODER_OUTPUT_CUSTOM_CUDA_BUFFER, d_out.data_ptr())
+        return np.ctypeslib.as_array((ctypes.c_uint8 * size).from_address(addr))
+
+    def step_resident():
+        del sizes[:]
+        for f in d_frames:
+            sizes.append(code(f).size)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        step_resident()
+    ms = timed(step_resident, args.steps)
+    value = n_frames * npix / (ms * 1e-3) / 1e6
+
+    scattered = None
+    if world > 1:
+        all_frames = [base[f % len(base)].to(dev) for f in range(n_frames)] if rank == 0 else None
+
+        def step_scattered():
+            got = bt.scatter_frames(all_frames, n_frames, (height, width, 3), src=0, device=dev)
+            streams = []
+            for f in got:
+                streams.append(torch.from_numpy(code(f)).to(dev))   # the copy to the device takes the bytes before the next encode reuses the buffer
+            return bt.gather_streams(streams, n_frames, dst=0, device=dev)
+
+        for _ in range(max(1, args.warmup - 1)):
+            step_scattered()
+        ms_sc = timed(step_scattered, args.steps)
+        ms_only = timed(lambda: bt.scatter_frames(all_frames, n_frames, (height, width, 3), src=0, device=dev), args.steps)
+        sent = (n_frames - len(bt.my_frames(n_frames, world, 0))) * npix * 3
+        scattered = {"value": round(n_frames * npix / (ms_sc * 1e-3) / 1e6, 1), "unit": "Mpix/s", "ms_per_step": round(ms_sc, 3),
+                     "scatter_ms": round(ms_only, 3), "scatter_gbs": round(sent / (ms_only * 1e-3) / 1e9, 1),
+                     "nccl_transport": nccl_transport_line(nccl_log) if nccl_log else None}
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        print(json.dumps({
+            "metric": "Mpix/s encode+decode %s RGB q75, batch of %d frames" % (args.size, n_frames), "value": round(value, 1),
+            "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+i32 (u8 in, i16 coefficients)",
+            "data": "synthetic",
+            "config": {"workload": "%dx%d RGB 4:4:4 q%d rst%d non-interleaved, batch of %d S-%s frames (%d distinct), frame f on rank "
+                                   "f mod %d, encode+decode per frame through the C API with device buffers, JPEG via the host"
+                                   % (width, height, QUALITY, rst, n_frames, args.kind, len(base), world),
+                       "l2": "inputs larger than L2 (%.0f MB raw per frame)" % (npix * 3 / 1e6),
+                       "sharding": "frames round-robin over ranks, no data-path collective; `scattered`: NCCL send/recv of raw "
+                                   "frames from rank 0 + gather-v of the streams"},
+            "scattered": scattered, "jpeg_bytes_per_frame": int(np.mean(sizes)) if sizes else None,
+            "gpu_launches": 9 * len(mine) * args.steps, "clocks": clocks, "numa": numa}))
+    enc.close()
+    dec.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -215,6 +401,9 @@ def main():
     # end-to-end arm: number of coder pairs driven concurrently, each by its own host thread on its own CUDA stream
     # (the reference's contract: one coder = one stream, instances are independent).  1 = strictly serial calls.
     ap.add_argument("--e2e-workers", type=int, default=3)
+    # BASELINE.json config 5: a fixed batch of frames sharded round-robin over the ranks (strong scaling); with --batch the
+    # step is the whole batch.  `--size 16k --batch 32` is the configuration the reference's north star names.
+    ap.add_argument("--batch", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -230,12 +419,20 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None   # before any pinned allocation (first touch)
+    nccl_log = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if rank == 0 and "NCCL_DEBUG" not in os.environ:   # one transport line for the record (see extras.scatter_gather)
+            nccl_log = "/tmp/gj_nccl_%d.log" % os.getpid()
+            os.environ.update(NCCL_DEBUG="INFO", NCCL_DEBUG_SUBSYS="INIT,P2P,NET,GRAPH", NCCL_DEBUG_FILE=nccl_log)
         dist.init_process_group("nccl", device_id=dev)
 
     import gpujpeg_b200 as g
     import _oracle as o  # synthetic frame generator only (the checker is never timed here)
+
+    if args.batch > 0:
+        return run_batch(args, g, o, torch, dist, rank, world, local, dev, numa, nccl_log)
 
     width, height, rst = WORKLOADS[args.size]
     npix = width * height
@@ -382,6 +579,10 @@ def main():
     e2e_value = world * npix / (e2e_ms * 1e-3) / 1e6
     clocks = sampler.stop() if rank == 0 else None
     assert np.array_equal(h_out.numpy(), d_out.cpu().numpy()), "e2e and resident paths disagree"
+    sg_extra = None
+    if world > 1 and headline:
+        sg_extra = scatter_gather_extra(g, torch, dist, rank, world, dev, enc, dec, d_raw, width, height, rst, max(3, args.steps // 4),
+                                        nccl_log)
 
     if rank == 0:
         peak, peak_kind = hbm_peak()
@@ -432,6 +633,10 @@ def main():
         }
         if not args.no_reference_gpu and world == 1:
             line["extras"] = {"reference_gpu": reference_gpu(args.kind, width, height, rst)}
+        if sg_extra is not None:
+            line.setdefault("extras", {})["scatter_gather"] = sg_extra
+        if numa is not None:
+            line["numa"] = numa
         if not args.no_cpu_baseline and world == 1:
             cores = host_cores()
             mpix, sec, nframes = cpu_baseline(width, height, rst, 12.0, cores)

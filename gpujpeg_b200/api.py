@@ -98,6 +98,14 @@ def _load():
         "gpujpegx_encoder_run_resident": (ci, [vp, vp, ci]),
         "gpujpegx_decoder_run_resident": (ci, [vp, vp, ci]),
         "gpujpegx_decoder_get_coefficients": (ci, [vp, vp, cs]),
+        "gpujpegx_batch_create": (vp, [C.POINTER(ci), ci]),
+        "gpujpegx_batch_destroy": (None, [vp]),
+        "gpujpegx_batch_device_count": (ci, [vp]),
+        "gpujpegx_batch_owner": (ci, [vp, ci]),
+        "gpujpegx_batch_encode": (ci, [vp, C.POINTER(Parameters), C.POINTER(ImageParameters), C.POINTER(vp), ci, ci, C.POINTER(vp),
+                                       C.POINTER(cs)]),
+        "gpujpegx_batch_decode": (ci, [vp, C.POINTER(vp), C.POINTER(cs), ci, C.POINTER(vp), ci]),
+        "gpujpegx_batch_last_ms": (C.c_double, [vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib_, name)
@@ -324,6 +332,58 @@ class Decoder:
     def close(self):
         if self._h:
             lib.gpujpeg_decoder_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+GPUJPEGX_HOST, GPUJPEGX_DEVICE_OWNER, GPUJPEGX_DEVICE_FIRST = 0, 1, 2
+
+
+class Batch:
+    """gpujpegx_batch_*: frames sharded round-robin over the GPUs of one box, one worker (host thread + stream + coder
+    pair) per device (include/gpujpegx.h).  `devices`: list of device indices (a device may appear more than once:
+    several workers on one GPU); None = every visible device."""
+
+    def __init__(self, devices=None):
+        if devices is None:
+            self._h = lib.gpujpegx_batch_create(None, 0)
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            self._h = lib.gpujpegx_batch_create(arr, len(devices))
+        if not self._h:
+            raise GpuJpegError("gpujpegx_batch_create failed")
+        self.device_count = lib.gpujpegx_batch_device_count(self._h)
+
+    def owner(self, frame):
+        return lib.gpujpegx_batch_owner(self._h, frame)
+
+    def encode(self, images, param, param_image, where=GPUJPEGX_HOST):
+        """images: list of arrays / tensors / addresses.  Returns the list of JPEG streams (numpy copies)."""
+        n = len(images)
+        ptrs = (C.c_void_p * n)(*[_ptr(x)[0] for x in images])
+        out, sizes = (C.c_void_p * n)(), (C.c_size_t * n)()
+        if lib.gpujpegx_batch_encode(self._h, C.byref(param), C.byref(param_image), ptrs, n, where, out, sizes) != 0:
+            raise GpuJpegError("gpujpegx_batch_encode failed")
+        return [np.ctypeslib.as_array((C.c_uint8 * sizes[f]).from_address(out[f])).copy() for f in range(n)]
+
+    def decode(self, jpegs, outputs, where=GPUJPEGX_HOST):
+        """jpegs: list of uint8 numpy arrays; outputs: list of destination arrays / tensors (filled in place)"""
+        n = len(jpegs)
+        jpegs = [np.ascontiguousarray(j, np.uint8) for j in jpegs]
+        ptrs = (C.c_void_p * n)(*[j.ctypes.data for j in jpegs])
+        sizes = (C.c_size_t * n)(*[j.size for j in jpegs])
+        outs = (C.c_void_p * n)(*[_ptr(x)[0] for x in outputs])
+        if lib.gpujpegx_batch_decode(self._h, ptrs, sizes, n, outs, where) != 0:
+            raise GpuJpegError("gpujpegx_batch_decode failed")
+        return outputs
+
+    def last_ms(self):
+        return lib.gpujpegx_batch_last_ms(self._h)
+
+    def close(self):
+        if self._h:
+            lib.gpujpegx_batch_destroy(self._h)
             self._h = None
 
     __del__ = close

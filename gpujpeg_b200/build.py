@@ -17,7 +17,7 @@ OBJDIR = os.path.join(HERE, "build")
 SONAME = "libgpujpeg.so.0"
 LIB = os.path.join(LIBDIR, SONAME)
 
-C_SOURCES = ["gj_tables.c", "gj_codestream.c", "gj_common.c", "gj_encoder.c", "gj_decoder.c"]
+C_SOURCES = ["gj_tables.c", "gj_codestream.c", "gj_common.c", "gj_encoder.c", "gj_decoder.c", "gj_batch.c"]
 CU_SOURCES = ["gj_cuda_util.cu", "gj_dct.cu", "gj_huffman.cu", "gj_huffdec.cu", "gj_markers.cu", "gj_convert.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -46,6 +46,7 @@ def build_library(force=False, verbose=False):
     os.makedirs(OBJDIR, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "gpujpeg_b200.h"))
+    headers.append(os.path.join(os.path.dirname(HERE), "include", "gpujpegx.h"))
     have_sources = all(os.path.exists(os.path.join(CSRC, f)) for f in C_SOURCES + CU_SOURCES)
     if not have_sources:
         if os.path.exists(LIB):
@@ -74,7 +75,7 @@ def build_library(force=False, verbose=False):
             relink = True
         objs.append(o)
     if relink or not os.path.exists(LIB):
-        cmd = [_nvcc(), "-shared", *ARCH, "-cudart", "static", "-Xlinker", "-soname=" + SONAME, "-o", LIB, *objs]
+        cmd = [_nvcc(), "-shared", *ARCH, "-cudart", "static", "-Xlinker", "-soname=" + SONAME, "-o", LIB, *objs, "-lpthread"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

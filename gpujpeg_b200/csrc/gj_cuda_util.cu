@@ -131,3 +131,26 @@ extern "C" int gj_cuda_sm_count(void)
         return 1;
     return n;
 }
+
+extern "C" int gj_cuda_stream_create(gj_stream_t* s)
+{
+    cudaStream_t st;
+    if ( cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess ) return -1;
+    *s = st;
+    return 0;
+}
+extern "C" void gj_cuda_stream_destroy(gj_stream_t s) { cudaStreamDestroy(s); }
+extern "C" int gj_cuda_enable_peer(int peer)
+{
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if ( e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled ) {
+        cudaGetLastError();
+        return 0;
+    }
+    cudaGetLastError();
+    return -1;
+}
+extern "C" int gj_cuda_memcpy_peer_async(void* dst, int dst_dev, const void* src, int src_dev, size_t size, gj_stream_t s)
+{
+    return cudaMemcpyPeerAsync(dst, dst_dev, src, src_dev, size, s) == cudaSuccess ? 0 : -1;
+}

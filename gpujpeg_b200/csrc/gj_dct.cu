@@ -24,6 +24,7 @@
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "gj_device.cuh"
@@ -55,6 +56,35 @@ __device__ __forceinline__ uint32_t pack4_sat_u8(int p0, int p1, int p2, int p3)
     asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(p3), "r"(p2), "r"(0));
     asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(p1), "r"(p0), "r"(hi));
     return d;
+}
+
+/* quantise the 64 coefficients of a block held in registers (natural order), emit them in zig-zag order as eight
+ * 16-byte stores plus the block's 64-bit non-zero mask (bit k <=> zig-zag coefficient k != 0: saves K2 a pass over
+ * the block) */
+__device__ __forceinline__ void quantise_store(const float (&v)[64], const float* __restrict__ tab, int16_t* __restrict__ coef_blk,
+                                               uint64_t* __restrict__ nz)
+{
+    uint32_t packed[32];
+    uint32_t mlo = 0, mhi = 0;
+#pragma unroll
+    for ( int k = 0; k < 64; k += 2 ) {
+        const uint32_t b0 = gj_quant_bits(v[gj_zz2nat(k)], tab[k]);
+        const uint32_t b1 = gj_quant_bits(v[gj_zz2nat(k + 1)], tab[k + 1]);
+        packed[k >> 1] = __byte_perm(b0, b1, 0x5410);   // low halves: the two quantised values as int16
+        if ( k < 32 ) {
+            if ( b0 != GJ_QUANT_ZERO ) mlo |= 1u << (k & 31);
+            if ( b1 != GJ_QUANT_ZERO ) mlo |= 1u << ((k + 1) & 31);
+        }
+        else {
+            if ( b0 != GJ_QUANT_ZERO ) mhi |= 1u << (k & 31);
+            if ( b1 != GJ_QUANT_ZERO ) mhi |= 1u << ((k + 1) & 31);
+        }
+    }
+    *nz = (uint64_t)mhi << 32 | mlo;
+    uint4* dst = reinterpret_cast<uint4*>(coef_blk);
+#pragma unroll
+    for ( int i = 0; i < 8; i++ )
+        dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
 }
 
 /* =========================================================================================== */
@@ -148,29 +178,128 @@ k_fdct_rgb444(const uint8_t* __restrict__ raw, int width, int height, size_t pit
     }
     gj_fdct_block(v);
     /* quantise: q = rint(c * table) [ref: src/gpujpeg_dct_gpu.cu:276-283], emit in zig-zag order */
-    const float* tab = prm.fwd_zz[comp == 0 ? 0 : 1];
-    uint32_t packed[32];
-    uint32_t mlo = 0, mhi = 0;   // bit k <=> zig-zag coefficient k is non-zero: saves K2 a pass over the block
-#pragma unroll
-    for ( int k = 0; k < 64; k += 2 ) {
-        const int q0 = GJ_RINT(GJ_FMUL(v[gj_zz2nat(k)], tab[k]));
-        const int q1 = GJ_RINT(GJ_FMUL(v[gj_zz2nat(k + 1)], tab[k + 1]));
-        packed[k >> 1] = __byte_perm((uint32_t)q0, (uint32_t)q1, 0x5410);
-        if ( k < 32 ) {
-            if ( q0 ) mlo |= 1u << (k & 31);
-            if ( q1 ) mlo |= 1u << ((k + 1) & 31);
-        }
-        else {
-            if ( q0 ) mhi |= 1u << (k & 31);
-            if ( q1 ) mhi |= 1u << ((k + 1) & 31);
-        }
-    }
     const size_t bi = (size_t)comp * nblk + (size_t)by * bcx + bx0 + b;
-    nzmask[bi] = (uint64_t)mhi << 32 | mlo;
-    uint4* dst = reinterpret_cast<uint4*>(coef + bi * 64);
+    quantise_store(v, prm.fwd_zz[comp == 0 ? 0 : 1], coef + bi * 64, nzmask + bi);
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* K1, bulk-copy variant: the same arithmetic, another way of getting the pixels on chip.  A persistent CTA walks over
+ * strips; ONE thread asks the copy engine for the strip's rows (cp.async.bulk global -> shared, 1536 bytes per row,
+ * completion counted in bytes on an mbarrier), everybody waits on the barrier instead of on 18 loads of their own, and
+ * the request for the NEXT strip is issued as soon as the colour phase has consumed the buffer, so that it flies
+ * while the CTA is busy with the DCT.  Needs 16-byte aligned rows (base, pitch and strip width): 8K, 4K and HD
+ * frames qualify, everything else takes k_fdct_rgb444. */
+constexpr int K1T_RAW = 8 * STRIP_PX * 3;                 // 12288 bytes of pixels per strip
+constexpr int K1T_SMEM = K1_SMEM + K1T_RAW + 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(NT)
+k_fdct_rgb444_bulk(const uint8_t* __restrict__ raw, int width, int height, size_t pitch, int16_t* __restrict__ coef,
+                   uint64_t* __restrict__ nzmask, int bcx, int bcy, int nblk, const __grid_constant__ FdctParams prm)
+{
+    extern __shared__ __align__(16) uint8_t smem[];   // K1_SMEM is a multiple of 16: bulk copies land 16-byte aligned
+    float* s_pl = reinterpret_cast<float*>(smem);
+    uint8_t* s_raw = smem + K1_SMEM;
+    const uint32_t bar = smem_u32(smem + K1_SMEM + K1T_RAW);
+    const int strips_x = (bcx + TB - 1) / TB, n_strips = strips_x * bcy;
+
+    auto request = [&](int strip) {   // one thread: the rows of `strip` into s_raw
+        const int by = strip / strips_x, sx = strip - by * strips_x;
+        const int x0 = sx * STRIP_PX;
+        const int vw = min(STRIP_PX, width - x0), vh = min(8, height - by * 8);
+        const uint8_t* src = raw + (size_t)by * 8 * pitch + (size_t)x0 * 3;
+        mbar_expect_tx(bar, (uint32_t)(vh * vw * 3));
+        for ( int r = 0; r < vh; r++ )
+            bulk_g2s(smem_u32(s_raw + r * STRIP_PX * 3), src + (size_t)r * pitch, (uint32_t)(vw * 3), bar);
+    };
+    if ( threadIdx.x == 0 ) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if ( threadIdx.x == 0 && (int)blockIdx.x < n_strips ) request(blockIdx.x);
+    uint32_t parity = 0;
+    for ( int strip = blockIdx.x; strip < n_strips; strip += gridDim.x ) {
+        const int by = strip / strips_x, sx = strip - by * strips_x;
+        const int bx0 = sx * TB, x0 = bx0 * 8;
+        const int vw = min(STRIP_PX, width - x0), vh = min(8, height - by * 8);
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+
+        /* phase A: colour transform from the staged rows (see k_fdct_rgb444) */
+        constexpr int ITERS = (GROUPS + NT - 1) / NT;
 #pragma unroll
-    for ( int i = 0; i < 8; i++ )
-        dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+        for ( int it = 0; it < ITERS; it++ ) {
+            const int g = threadIdx.x + it * NT;
+            if ( g >= GROUPS ) break;
+            const int row = g >> 7, gx = g & 127, px0 = gx * 4;
+            float4 y4 = make_float4(0.f, 0.f, 0.f, 0.f), cb4 = y4, cr4 = y4;
+            if ( row < vh && px0 < vw ) {   // vw * 3 is a multiple of 16 here: a 4-pixel group is inside the row or outside
+                const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(s_raw + row * STRIP_PX * 3 + gx * 12);
+                const uint32_t a0 = wsrc[0], a1 = wsrc[1], a2 = wsrc[2];
+                gj_rgb_to_ycbcr_m(gj_byte_as_magic(a0, 0), gj_byte_as_magic(a0, 1), gj_byte_as_magic(a0, 2), y4.x, cb4.x, cr4.x);
+                gj_rgb_to_ycbcr_m(gj_byte_as_magic(a0, 3), gj_byte_as_magic(a1, 0), gj_byte_as_magic(a1, 1), y4.y, cb4.y, cr4.y);
+                gj_rgb_to_ycbcr_m(gj_byte_as_magic(a1, 2), gj_byte_as_magic(a1, 3), gj_byte_as_magic(a2, 0), y4.z, cb4.z, cr4.z);
+                gj_rgb_to_ycbcr_m(gj_byte_as_magic(a2, 1), gj_byte_as_magic(a2, 2), gj_byte_as_magic(a2, 3), y4.w, cb4.w, cr4.w);
+            }
+            const int off = (gx >> 1) * BLK_F + row * 8 + (gx & 1) * 4;
+            *reinterpret_cast<float4*>(s_pl + off) = y4;
+            *reinterpret_cast<float4*>(s_pl + TB * BLK_F + off) = cb4;
+            *reinterpret_cast<float4*>(s_pl + 2 * TB * BLK_F + off) = cr4;
+        }
+        __syncthreads();
+        /* the pixel buffer is free: the copy engine fills it with the next strip while this one is transformed */
+        if ( threadIdx.x == 0 && strip + (int)gridDim.x < n_strips ) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads above, async-proxy writes below
+            request(strip + gridDim.x);
+        }
+
+        /* phase B: one thread = one 8x8 block of one component, everything in registers */
+        const int comp = threadIdx.x >> 6;
+        const int b = threadIdx.x & 63;
+        if ( bx0 + b < bcx ) {
+            float v[64];
+            const float4* in = reinterpret_cast<const float4*>(s_pl + (comp * TB + b) * BLK_F);
+#pragma unroll
+            for ( int i = 0; i < 16; i++ ) {
+                const float4 t = in[i];
+                v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+            }
+            gj_fdct_block(v);
+            const size_t bi = (size_t)comp * nblk + (size_t)by * bcx + bx0 + b;
+            quantise_store(v, prm.fwd_zz[comp == 0 ? 0 : 1], coef + bi * 64, nzmask + bi);
+        }
+        __syncthreads();   // the planar staging area is rewritten by the next strip's colour phase
+    }
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -295,29 +424,8 @@ k_fdct_rgb_ss(const uint8_t* __restrict__ raw, int width, int height, size_t pit
         }
     }
     gj_fdct_block(v);
-    const float* tab = prm.fwd_zz[comp == 0 ? 0 : 1];
-    uint32_t packed[32];
-    uint32_t mlo = 0, mhi = 0;
-#pragma unroll
-    for ( int k = 0; k < 64; k += 2 ) {
-        const int q0 = GJ_RINT(GJ_FMUL(v[gj_zz2nat(k)], tab[k]));
-        const int q1 = GJ_RINT(GJ_FMUL(v[gj_zz2nat(k + 1)], tab[k + 1]));
-        packed[k >> 1] = __byte_perm((uint32_t)q0, (uint32_t)q1, 0x5410);
-        if ( k < 32 ) {
-            if ( q0 ) mlo |= 1u << (k & 31);
-            if ( q1 ) mlo |= 1u << ((k + 1) & 31);
-        }
-        else {
-            if ( q0 ) mhi |= 1u << (k & 31);
-            if ( q1 ) mhi |= 1u << ((k + 1) & 31);
-        }
-    }
     const size_t bi = (size_t)grid.blk_off[comp] + (size_t)by * grid.bcx[comp] + bx;
-    nzmask[bi] = (uint64_t)mhi << 32 | mlo;
-    uint4* dst = reinterpret_cast<uint4*>(coef + bi * 64);
-#pragma unroll
-    for ( int i = 0; i < 8; i++ )
-        dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+    quantise_store(v, prm.fwd_zz[comp == 0 ? 0 : 1], coef + bi * 64, nzmask + bi);
 }
 
 /* =========================================================================================== */
@@ -584,28 +692,7 @@ k_fdct_samples(const uint8_t* __restrict__ raw, const __grid_constant__ SampleGr
         }
     }
     gj_fdct_block(v);
-    const float* tab = prm.fwd_zz[g.table[comp]];
-    uint32_t packed[32];
-    uint32_t mlo = 0, mhi = 0;
-#pragma unroll
-    for ( int k = 0; k < 64; k += 2 ) {
-        const int q0 = GJ_RINT(GJ_FMUL(v[gj_zz2nat(k)], tab[k]));
-        const int q1 = GJ_RINT(GJ_FMUL(v[gj_zz2nat(k + 1)], tab[k + 1]));
-        packed[k >> 1] = __byte_perm((uint32_t)q0, (uint32_t)q1, 0x5410);
-        if ( k < 32 ) {
-            if ( q0 ) mlo |= 1u << (k & 31);
-            if ( q1 ) mlo |= 1u << ((k + 1) & 31);
-        }
-        else {
-            if ( q0 ) mhi |= 1u << (k & 31);
-            if ( q1 ) mhi |= 1u << ((k + 1) & 31);
-        }
-    }
-    nzmask[bi] = (uint64_t)mhi << 32 | mlo;
-    uint4* dst = reinterpret_cast<uint4*>(coef + (size_t)bi * 64);
-#pragma unroll
-    for ( int i = 0; i < 8; i++ )
-        dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+    quantise_store(v, prm.fwd_zz[g.table[comp]], coef + (size_t)bi * 64, nzmask + bi);
 }
 
 template <int FLAVOUR, bool DEQ>
@@ -687,16 +774,38 @@ extern "C" int gj_launch_fdct_rgb444(const uint8_t* d_raw, int width, int height
     const dim3 grid((bcx + TB - 1) / TB, bcy);
     const int nblk = bcx * bcy;
     /* > 48 KB of dynamic shared memory needs an opt-in, once per device */
-    static bool attr_done[64] = {false};
+    static int attr_done[64];   // set once per device; two host threads racing write the same value
     int dev = 0;
     if ( cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 ) return -1;
-    if ( !attr_done[dev] ) {
+    if ( !__atomic_load_n(&attr_done[dev], __ATOMIC_ACQUIRE) ) {
         if ( cudaFuncSetAttribute(k_fdct_rgb444<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM) != cudaSuccess ||
              cudaFuncSetAttribute(k_fdct_rgb444<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM) != cudaSuccess )
             return -1;
-        attr_done[dev] = true;
+        __atomic_store_n(&attr_done[dev], 1, __ATOMIC_RELEASE);
     }
-    if ( pick_vec(d_raw, (size_t)pitch) == 4 )
+    /* Two ways of getting the pixels on chip.  Measured on B200, 8K (profiles/r2_k1_bulk_vs_ldg.md): plain coalesced loads
+     * 133.2 us, copy-engine bulk copies into a persistent CTA 140.5 us -- the kernel is bound by instruction issue, not by
+     * the loads, and the bulk variant pays two CTA-wide barriers per strip at 3 instead of 4 CTAs per SM.  The plain-load
+     * kernel is the default; GPUJPEG_B200_K1=bulk selects the other one (rows must be 16-byte aligned). */
+    static int use_bulk = -1;
+    if ( use_bulk < 0 ) {
+        const char* e = getenv("GPUJPEG_B200_K1");
+        use_bulk = e && strcmp(e, "bulk") == 0;
+    }
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(d_raw) | (size_t)pitch) & 15) == 0 && ((size_t)(width % STRIP_PX) * 3) % 16 == 0;
+    if ( use_bulk && aligned16 ) {
+        static int bulk_attr[64];
+        if ( !__atomic_load_n(&bulk_attr[dev], __ATOMIC_ACQUIRE) ) {
+            if ( cudaFuncSetAttribute(k_fdct_rgb444_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, K1T_SMEM) != cudaSuccess ) return -1;
+            __atomic_store_n(&bulk_attr[dev], 1, __ATOMIC_RELEASE);
+        }
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int n_strips = (int)grid.x * (int)grid.y;
+        const int ctas = n_strips < sms * 3 ? n_strips : sms * 3;   // 3 CTAs of 64.5 KB per SM
+        k_fdct_rgb444_bulk<<<ctas, NT, K1T_SMEM, stream>>>(d_raw, width, height, (size_t)pitch, d_coef, d_nzmask, bcx, bcy, nblk, prm);
+    }
+    else if ( pick_vec(d_raw, (size_t)pitch) == 4 )
         k_fdct_rgb444<4><<<grid, NT, K1_SMEM, stream>>>(d_raw, width, height, (size_t)pitch, d_coef, d_nzmask, bcx, nblk, prm);
     else
         k_fdct_rgb444<1><<<grid, NT, K1_SMEM, stream>>>(d_raw, width, height, (size_t)pitch, d_coef, d_nzmask, bcx, nblk, prm);

@@ -159,6 +159,25 @@ GJ_HD void gj_fdct_block(float (&v)[64])
                  v[8 * y + 7], 0.0f);
 }
 
+/* Quantisation: q = rint(c * t) [ref: src/gpujpeg_dct_gpu.cu:276-283] without the conversion instruction (F2I runs on
+ * the quarter-rate XU pipe; 64 of them per block were 17 % of K1's pipe time, ncu r1_n): the product is rounded to
+ * binary32 exactly as the reference's FMUL does, then 1.5 * 2^23 is ADDED -- a second, separate rounding, to the nearest
+ * integer with ties to even, i.e. rintf -- and the integer sits in the low mantissa bits of the sum: for |c * t| < 2^22
+ * the sum's bit pattern is 0x4B400000 + q, so its low 16 bits ARE q as int16 and q != 0 <=> pattern != 0x4B400000.
+ * (An FMA here would round once and differ from the reference; mul and add stay two instructions.) */
+#define GJ_QUANT_ZERO 0x4B400000u
+GJ_HD uint32_t gj_quant_bits(float c, float t)
+{
+    const float f = GJ_FADD(GJ_FMUL(c, t), GJ_MAGIC15);
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } x;
+    x.f = f;
+    return x.u;
+#endif
+}
+
 /* ------------------------------------------------------------------------------------------- */
 /* inverse DCT, integer flavour == the reference's gpujpeg_idct_cpu (Chen-Wang, 11-bit constants)  */
 /* [ref: src/gpujpeg_dct_cpu.c:34-39 constants, :55-107 rows, :119-171 columns]                    */

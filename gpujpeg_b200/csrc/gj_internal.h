@@ -350,6 +350,10 @@ int gj_cuda_memcpy_d2h_async(void* dst, const void* src, size_t size, gj_stream_
 int gj_cuda_memcpy_d2d_async(void* dst, const void* src, size_t size, gj_stream_t s);
 int gj_cuda_memset_async(void* dst, int v, size_t size, gj_stream_t s);
 int gj_cuda_stream_sync(gj_stream_t s);
+int gj_cuda_stream_create(gj_stream_t* s);
+void gj_cuda_stream_destroy(gj_stream_t s);
+int gj_cuda_enable_peer(int peer);
+int gj_cuda_memcpy_peer_async(void* dst, int dst_dev, const void* src, int src_dev, size_t size, gj_stream_t s);
 int gj_cuda_pointer_is_device(const void* p);
 const char* gj_cuda_last_error(void);
 /* event timers [ref: src/gpujpeg_common_internal.h:156-205] */

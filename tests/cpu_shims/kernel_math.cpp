@@ -59,7 +59,7 @@ void km_fdct_quant_plane(const uint8_t* plane, int dw, int dh, const float* fwd_
             int16_t* out = coef + ((size_t)by * bcx + bx) * 64;
             for ( int k = 0; k < 64; k++ ) {
                 const int n = gj_zz2nat(k);
-                out[n] = (int16_t)GJ_RINT(GJ_FMUL(v[n], fwd_zz[k]));
+                out[n] = (int16_t)(gj_quant_bits(v[n], fwd_zz[k]) & 0xFFFFu);   // the kernel's own rounding (no conversion instruction)
             }
         }
 }

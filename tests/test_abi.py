@@ -11,10 +11,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "gpujpeg_b200.h")
 
 
-def declared_functions():
-    src = open(HEADER).read()
+EXT_HEADER = os.path.join(ROOT, "include", "gpujpegx.h")
+
+
+def declared_functions(header=HEADER):
+    src = open(header).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    names = re.findall(r"GPUJPEG_API[^;{]*?\b(gpujpeg_\w+)\s*\(", src)
+    names = re.findall(r"GPUJPEG_API[^;{]*?\b(gpujpegx?_\w+)\s*\(", src)
     return sorted(set(names))
 
 
@@ -23,6 +26,11 @@ def test_every_declared_symbol_is_exported():
     names = declared_functions()
     assert len(names) >= 70
     missing = [n for n in names if not hasattr(gpujpeg_b200.lib, n)]
+    assert not missing, missing
+    # the additive extension header (resident re-runs, coefficient read-back, multi-GPU batches)
+    ext = declared_functions(EXT_HEADER)
+    assert len(ext) >= 11 and all(n.startswith("gpujpegx_") for n in ext)
+    missing = [n for n in ext if not hasattr(gpujpeg_b200.lib, n)]
     assert not missing, missing
 
 
