@@ -231,28 +231,37 @@ static int comp_id(const struct gpujpeg_parameters* param, int c)
     return param->color_space_internal == GPUJPEG_RGB ? rgb_ids[c] : c + 1;
 }
 
-/* Everything before the first SOS.  Only the JFIF flavour (YCbCr-JPEG internal colour space, no
- * orientation metadata) and the Adobe flavour (RGB internal) are produced; SPIFF/Exif are outside
- * the hot path.  [ref: src/gpujpeg_writer.c:456-518] */
+/* Everything before the first SOS.  The header flavour follows the internal colour space unless the caller forces one
+ * (enc_hdr option): SPIFF names the colour space (BT.601 / BT.709 need it), Adobe APP14 marks RGB, JFIF is the default for
+ * YCbCr JPEG.  Exif and orientation metadata are outside the hot path.  [ref: src/gpujpeg_writer.c:451-518] */
 size_t gj_write_header(uint8_t* out, const struct gpujpeg_parameters* param,
                        const struct gpujpeg_image_parameters* pi, const uint8_t raw_q[2][64],
-                       const struct gj_huff_spec spec[2][2])
+                       const struct gj_huff_spec spec[2][2], enum gpujpeg_header_type header_type)
 {
     uint8_t* p = out;
     p = wmark(p, 0xD8);
-    if ( param->color_space_internal == GPUJPEG_YCBCR_BT601 || param->color_space_internal == GPUJPEG_YCBCR_BT709 ) {
-        /* SPIFF (T.84) names the colour space: APP8 "SPIFF\0" header, end-of-directory entry, second SOI
-         * [ref: src/gpujpeg_writer.c:171-245] */
+    if ( header_type == GPUJPEG_HEADER_DEFAULT )
+        header_type = (param->color_space_internal == GPUJPEG_YCBCR_BT601 || param->color_space_internal == GPUJPEG_YCBCR_BT709)
+                          ? GPUJPEG_HEADER_SPIFF
+                          : param->color_space_internal == GPUJPEG_RGB ? GPUJPEG_HEADER_ADOBE : GPUJPEG_HEADER_JFIF;
+    if ( header_type == GPUJPEG_HEADER_SPIFF ) {
+        /* SPIFF (T.84): APP8 "SPIFF\0" header, end-of-directory entry, second SOI [ref: src/gpujpeg_writer.c:171-245] */
+        int cs = 2;   /* no colour space specified */
+        if ( param->comp_count == 1 ) cs = 8;
+        else if ( param->color_space_internal == GPUJPEG_YCBCR_BT709 ) cs = 1;
+        else if ( param->color_space_internal == GPUJPEG_YCBCR_BT601_256LVLS ) cs = 3;
+        else if ( param->color_space_internal == GPUJPEG_YCBCR_BT601 ) cs = 4;
+        else if ( param->color_space_internal == GPUJPEG_RGB ) cs = 10;
         p = wmark(p, 0xE8);
         p = w16(p, 32);
         memcpy(p, "SPIFF", 6);
         p += 6;
         p = w16(p, 0x100);                                                     /* version 1.00 */
-        p = w8(p, 0);                                                          /* no profile */
+        p = w8(p, cs == 3 || cs == 8 ? 1 : 0);                                 /* profile */
         p = w8(p, param->comp_count);
         p = w16(p, 0); p = w16(p, pi->height);
         p = w16(p, 0); p = w16(p, pi->width);
-        p = w8(p, param->color_space_internal == GPUJPEG_YCBCR_BT709 ? 1 : 4);
+        p = w8(p, cs);
         p = w8(p, 8);                                                          /* bits per sample */
         p = w8(p, 5);                                                          /* compression: JPEG */
         p = w8(p, 0);                                                          /* resolution units: ratio */
@@ -263,8 +272,9 @@ size_t gj_write_header(uint8_t* out, const struct gpujpeg_parameters* param,
         p = w16(p, 0); p = w16(p, 1);                                          /* end of directory */
         p = wmark(p, 0xD8);
     }
-    else if ( param->color_space_internal == GPUJPEG_RGB ) {
-        /* Adobe APP14, transform 0 [ref: src/gpujpeg_writer.c:258-276] */
+    else if ( header_type == GPUJPEG_HEADER_ADOBE ) {
+        /* Adobe APP14, transform 0 -- also when forced onto a YCbCr stream, as the reference writes it
+         * [ref: src/gpujpeg_writer.c:258-276] */
         p = wmark(p, 0xEE);
         p = w16(p, 14);
         memcpy(p, "Adobe", 5);

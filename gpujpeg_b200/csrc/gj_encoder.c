@@ -34,7 +34,8 @@ struct gpujpeg_encoder {
     uint8_t* d_planes; size_t d_planes_size;   /* component planes between the generic pass and the DCT */
     struct gj_raw_layout raw;        /* where the samples live (GJ_IN_SAMPLES) */
     int quality;                               /* quality the tables were built for (-1 = none) */
-    enum gpujpeg_header_type header_type;
+    enum gpujpeg_header_type header_type;      /* enc_hdr: forced header flavour, GPUJPEG_HEADER_DEFAULT = by colour space */
+    enum gpujpeg_header_type header_written;   /* flavour the cached header bytes were composed with */
     int out_pinned;
 
     uint8_t raw_q[2][64];
@@ -533,9 +534,10 @@ int gpujpeg_encoder_encode(struct gpujpeg_encoder* e, const struct gpujpeg_param
     e->param.perf_stats = a.perf_stats;
     const struct gj_geometry* g = &e->geo;
 
-    if ( tables_dirty || geometry_dirty ) {
+    if ( tables_dirty || geometry_dirty || e->header_written != e->header_type ) {
+        e->header_written = e->header_type;
         /* host codestream writer: file header + SOS headers, composed once per parameter change */
-        e->header_size = gj_write_header(e->header, &e->param, &e->param_image, e->raw_q, e->spec);
+        e->header_size = gj_write_header(e->header, &e->param, &e->param_image, e->raw_q, e->spec, e->header_type);
         uint8_t sos_flat[GJ_MAX_COMP * 16];
         e->sos_len = 0;
         for ( int s = 0; s < g->scan_count; s++ ) {
@@ -665,11 +667,14 @@ int gpujpeg_encoder_get_stats(struct gpujpeg_encoder* encoder, struct gpujpeg_du
     return 0;
 }
 
+/* [ref: src/gpujpeg_encoder.c:728-733] */
 void gpujpeg_encoder_set_jpeg_header(struct gpujpeg_encoder* encoder, enum gpujpeg_header_type header_type)
 {
-    if ( header_type != GPUJPEG_HEADER_DEFAULT && header_type != GPUJPEG_HEADER_JFIF )
-        GJ_WARN("Only the JFIF header is implemented in this build; request ignored.\n");
-    encoder->header_type = GPUJPEG_HEADER_DEFAULT;
+    if ( header_type == GPUJPEG_HEADER_EXIF ) {
+        GJ_WARN("The Exif header is not implemented in this build; request ignored.\n");
+        return;
+    }
+    encoder->header_type = header_type;
 }
 
 /* [ref: src/gpujpeg_encoder.c:736-800] */
@@ -689,10 +694,18 @@ int gpujpeg_encoder_set_option(struct gpujpeg_encoder* encoder, const char* opt,
         encoder->out_pinned = strcmp(val, GPUJPEG_VAL_TRUE) == 0;
         return GPUJPEG_NOERR;
     }
-    if ( strcmp(opt, GPUJPEG_ENC_OPT_HDR) == 0 ) {
-        if ( strcmp(val, GPUJPEG_ENC_HDR_VAL_JFIF) == 0 ) return GPUJPEG_NOERR;
-        GJ_ERR("Header type %s is not implemented in this build (JFIF only).\n", val);
-        return GPUJPEG_ERROR;
+    if ( strcmp(opt, GPUJPEG_ENC_OPT_HDR) == 0 ) {   /* [ref: src/gpujpeg_encoder.c:759-766] */
+        const enum gpujpeg_header_type t = gpujpeg_header_type_by_name(val);
+        if ( t == GPUJPEG_HEADER_DEFAULT ) {
+            GJ_ERR("Unknown encoder header type: %s\n", val);
+            return GPUJPEG_ERROR;
+        }
+        if ( t == GPUJPEG_HEADER_EXIF ) {
+            GJ_ERR("The Exif header is not implemented in this build.\n");
+            return GPUJPEG_ERROR;
+        }
+        encoder->header_type = t;
+        return GPUJPEG_NOERR;
     }
     if ( strcmp(opt, GPUJPEG_ENC_OPT_FLIPPED_BOOL) == 0 || strcmp(opt, GPUJPEG_ENC_OPT_CHANNEL_REMAP) == 0 ||
          strcmp(opt, GPUJPEG_ENC_OPT_EXIF_TAG) == 0 || strcmp(opt, GPUJPEG_ENC_OPT_METADATA) == 0 ) {
@@ -707,7 +720,8 @@ void gpujpeg_encoder_print_options(void)
 {
     printf("\t" GPUJPEG_ENC_OPT_OUT "=[" GPUJPEG_ENC_OUT_VAL_PAGEABLE "|" GPUJPEG_ENC_OUT_VAL_PINNED
            "] - output buffer in pageable or pinned host memory\n");
-    printf("\t" GPUJPEG_ENC_OPT_HDR "=[" GPUJPEG_ENC_HDR_VAL_JFIF "] - JPEG header type (JFIF only in this build)\n");
+    printf("\t" GPUJPEG_ENC_OPT_HDR "=[" GPUJPEG_ENC_HDR_VAL_JFIF "|" GPUJPEG_ENC_HDR_VAL_ADOBE "|" GPUJPEG_ENC_HDR_VAL_SPIFF
+           "] - output JPEG header (default: by internal colour space)\n");
 }
 
 /* ---- extension: re-run the GPU stages of the last configured frame on device-resident data ----

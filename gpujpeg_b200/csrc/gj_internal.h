@@ -172,7 +172,7 @@ int gj_geometry_init(struct gj_geometry* g, const struct gpujpeg_parameters* par
 /* ---- codestream writer (gj_writer.c)  [ref: src/gpujpeg_writer.c] ---- */
 size_t gj_write_header(uint8_t* out, const struct gpujpeg_parameters* param,
                        const struct gpujpeg_image_parameters* param_image, const uint8_t raw_q[2][64],
-                       const struct gj_huff_spec spec[2][2]);
+                       const struct gj_huff_spec spec[2][2], enum gpujpeg_header_type header_type);
 size_t gj_write_sos(uint8_t* out, const struct gpujpeg_parameters* param, int scan_index);
 
 /* ---- codestream reader (gj_reader.c)  [ref: src/gpujpeg_reader.c] ---- */

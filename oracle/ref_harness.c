@@ -138,6 +138,8 @@ int ref_huff_encoder_table(int cls, int kind, uint32_t code[256], uint8_t size[2
  *       src/gpujpeg_huffman_cpu_encoder.c:296-376] */
 static int g_internal_rgb = 0;   /* components of an RGB-internal JPEG are all of the luminance type */
 static int g_internal_cs = 0;    /* other internal colour space (enum gpujpeg_color_space), 0 = YCbCr JPEG */
+static int g_header_type = 0;    /* forced header flavour (enum gpujpeg_header_type), 0 = by colour space */
+void ref_set_header_type(int t) { g_header_type = t; }
 
 size_t ref_encode_from_coef_ss(int16_t* coef, int w, int h, int comps, int quality, int rst, int interleaved, int lhs,
                                int lvs, uint8_t* out, size_t out_cap)
@@ -169,7 +171,7 @@ size_t ref_encode_from_coef_ss(int16_t* coef, int w, int h, int comps, int quali
     enc->coder.component = g.comp;
     enc->coder.segment = g.seg;
     enc->coder.segment_count = g.seg_count;
-    enc->header_type = GPUJPEG_HEADER_DEFAULT;
+    enc->header_type = (enum gpujpeg_header_type)g_header_type;
     float fwd[64];
     uint16_t dinv[64];
     for ( int t = 0; t < 2; t++ ) {

@@ -4,6 +4,9 @@
 
 #include "../../gpujpeg_b200/csrc/gj_internal.h"
 
+static int g_header_type = 0;   /* GPUJPEG_HEADER_DEFAULT; shim_set_header_type forces a flavour (enc_hdr option) */
+void shim_set_header_type(int t) { g_header_type = t; }
+
 int shim_header(int width, int height, int quality, int rst, int interleaved, unsigned char* out)
 {
     struct gpujpeg_parameters p;
@@ -28,7 +31,7 @@ int shim_header(int width, int height, int quality, int rst, int interleaved, un
         for ( int k = 0; k < 2; k++ )
             gj_huff_spec_default(t, k, &spec[t][k]);
     }
-    size_t n = gj_write_header(out, &p, &pi, raw, spec);
+    size_t n = gj_write_header(out, &p, &pi, raw, spec, (enum gpujpeg_header_type)g_header_type);
     n += gj_write_sos(out + n, &p, 0);
     return (int)n;
 }
@@ -188,7 +191,7 @@ int shim_header2(int width, int height, int quality, int rst, int interleaved, i
         for ( int k = 0; k < 2; k++ )
             gj_huff_spec_default(t, k, &spec[t][k]);
     }
-    size_t n = gj_write_header(out, &p, &pi, raw, spec);
+    size_t n = gj_write_header(out, &p, &pi, raw, spec, (enum gpujpeg_header_type)g_header_type);
     n += gj_write_sos(out + n, &p, 0);
     return (int)n;
 }

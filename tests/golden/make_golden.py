@@ -7,8 +7,9 @@ Each fixture holds: the synthetic RGB input recipe, the quantised coefficients f
 Huffman encoder, the JPEG bytes the reference header writer + CPU Huffman encoder produced, the
 coefficients the reference CPU Huffman decoder recovered, and the planes the reference integer IDCT
 (gpujpeg_idct_cpu_perform, +128, clamp) produced.  The forward DCT / colour stages have no CPU
-implementation in the reference, so the coefficients themselves come from the oracle restatement
-(validated against the reference GPU library on the GPU box, tests/test_ref_gpu.py).
+implementation in the reference, so the coefficients fed in here come from the oracle restatement; that
+restatement is pinned separately against committed outputs of the reference GPU library
+(tests/golden/refgpu_*.npz, made by make_golden_refgpu.py on a B200) and live on the GPU box (tests/test_ref_gpu.py).
 """
 import os
 import sys

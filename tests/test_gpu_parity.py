@@ -233,7 +233,32 @@ def test_generic_colour_spaces_and_resampling(gj, enc, fmt, cs, sub, w, h, il):
         d.close()
 
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                if not os.path.basename(p).startswith("refgpu_"))
+REFGPU = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "refgpu_*.npz")))
+
+
+@pytest.mark.parametrize("path", REFGPU, ids=[os.path.basename(p)[7:-4] for p in REFGPU])
+def test_golden_vectors_from_reference_gpu_library(gj, enc, path):
+    """committed outputs of the reference GPU library (tests/golden/make_golden_refgpu.py): the product's bytes equal its
+    encoder's, the product's float-flavour pixels equal its decoder's"""
+    import hashlib
+    g = np.load(path)
+    w, h, q, rst, il = int(g["w"]), int(g["h"]), int(g["quality"]), int(g["rst"]), int(g["interleaved"])
+    samp = tuple(int(v) for v in g["sampling"])
+    name = {(1, 1): "4:4:4", (2, 2): "4:2:0", (2, 1): "4:2:2", (1, 2): "4:4:0"}[samp]
+    img = o.gen_image(str(g["kind"]), w, h)
+    assert np.array_equal(enc.encode(img, q, rst, il, subsampling=name), g["jpeg"]), "bytes differ from the reference GPU encoder"
+    d = gj.Decoder(idct="float_gpuref")
+    try:
+        rgb = d.decode(g["jpeg"])
+    finally:
+        d.close()
+    if "pixels" in g:
+        assert np.array_equal(rgb, g["pixels"]), "pixels differ from the reference GPU decoder"
+    else:
+        assert hashlib.sha256(np.ascontiguousarray(rgb).tobytes()).hexdigest() == str(g["pixels_sha256"])
+
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])

@@ -1,5 +1,9 @@
-"""Pins the CPU oracle against golden vectors produced by the REFERENCE's own CPU code
-(tests/golden/*.npz, generated by tests/golden/make_golden.py from oracle/_ref).  CPU only."""
+"""Pins the CPU oracle against golden vectors produced by the REFERENCE's own code.  CPU only.
+  tests/golden/<name>.npz          the reference's CPU sources (Huffman coders, integer IDCT, writer), generated here by
+                                   tests/golden/make_golden.py from oracle/_ref
+  tests/golden/refgpu_<name>.npz   the reference's GPU library on a B200 (tests/golden/make_golden_refgpu.py): JPEG bytes of
+                                   its encoder and pixels of its decoder -- what pins the oracle's restated colour
+                                   transforms, float FDCT and float IDCT without a GPU"""
 import glob
 import os
 
@@ -8,7 +12,9 @@ import pytest
 
 import _oracle as o
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+ALL = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = [p for p in ALL if not os.path.basename(p).startswith("refgpu_")]
+REFGPU = [p for p in ALL if os.path.basename(p).startswith("refgpu_")]
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
@@ -43,3 +49,25 @@ def test_oracle_matches_reference_golden(path):
 
 def test_golden_present():
     assert len(GOLDEN) >= 5
+
+
+@pytest.mark.parametrize("path", REFGPU, ids=[os.path.basename(p)[7:-4] for p in REFGPU])
+def test_oracle_matches_reference_gpu_library_outputs(path):
+    """the encode front half (colour transform + float FDCT + quantisation) and the float IDCT have no CPU code in the
+    reference; these bytes and pixels were produced by its CUDA kernels on a B200"""
+    import hashlib
+    g = np.load(path)
+    w, h, q, rst, il = int(g["w"]), int(g["h"]), int(g["quality"]), int(g["rst"]), int(g["interleaved"])
+    samp = tuple(int(v) for v in g["sampling"])
+    img = o.gen_image(str(g["kind"]), w, h)
+    jpeg = o.encode(img, q, rst, il, sampling=samp)
+    assert jpeg.size == g["jpeg"].size and np.array_equal(jpeg, g["jpeg"]), "oracle JPEG bytes differ from the reference GPU encoder"
+    rgb = o.decode(g["jpeg"], o.IDCT_FLOAT_GPUREF)
+    if "pixels" in g:
+        assert np.array_equal(rgb, g["pixels"]), "oracle float-IDCT decode differs from the reference GPU decoder"
+    else:
+        assert hashlib.sha256(np.ascontiguousarray(rgb).tobytes()).hexdigest() == str(g["pixels_sha256"])
+
+
+def test_reference_gpu_fixtures_present():
+    assert len(REFGPU) >= 10

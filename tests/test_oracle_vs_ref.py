@@ -143,3 +143,39 @@ def test_idct_saturating_blocks():
         o.lib.orc_idct_int_block(a, inv[0])
         o.ref.ref_idct_block(b, inv[0])
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("hdr", [1, 2, 4])           # GPUJPEG_HEADER_JFIF, _SPIFF, _ADOBE
+@pytest.mark.parametrize("internal", [0, 1, 2, 4])   # YCbCr JPEG, RGB, BT.601, BT.709
+def test_forced_header_flavours_equal_the_reference_writer(hdr, internal):
+    """enc_hdr=JFIF|SPIFF|Adobe [ref: src/gpujpeg_encoder.c:759-766, src/gpujpeg_writer.c:451-518]: the product's host writer
+    (gj_write_header through the host shim) against the reference's own gpujpeg_writer.c compiled in place, for every
+    internal colour space -- including the combinations that make little sense (Adobe transform 0 on a YCbCr stream),
+    which the reference writes just the same"""
+    from _shims import hs
+    w, h, q, rst = 64, 48, 75, 4
+    coef = np.zeros((3, 64 * 48), np.int16)
+    o.ref.ref_set_header_type.argtypes = [__import__("ctypes").c_int]
+    o.ref.ref_set_header_type(hdr)
+    try:
+        if internal == 1:
+            out = np.empty(1 << 16, np.uint8)
+            n = o.ref.ref_encode_from_coef_rgb(coef.reshape(-1), w, h, q, rst, 0, 1, 1, out, out.size)
+        elif internal in (2, 4):
+            out = np.empty(1 << 16, np.uint8)
+            n = o.ref.ref_encode_from_coef_cs(coef.reshape(-1), w, h, q, rst, 0, 1, 1, internal, out, out.size)
+        else:
+            out = np.empty(1 << 16, np.uint8)
+            n = o.ref.ref_encode_from_coef_ss(coef.reshape(-1), w, h, 3, q, rst, 0, 1, 1, out, out.size)
+    finally:
+        o.ref.ref_set_header_type(0)
+    ref = bytes(out[:n])
+    sos = ref.index(b"\xff\xda")
+    got = np.zeros(4096, np.uint8)
+    hs.shim_set_header_type(hdr)
+    try:
+        m = hs.shim_header2(w, h, q, rst, 0, 3, 1, 1, internal if internal else 3, got)
+    finally:
+        hs.shim_set_header_type(0)
+    assert bytes(got[:sos]) == ref[:sos], "header bytes differ from the reference writer"
+    assert m >= sos
