@@ -637,3 +637,35 @@ uint8_t* gpujpeg_opengl_texture_map(struct gpujpeg_opengl_texture* texture, size
     return NULL;
 }
 void gpujpeg_opengl_texture_unmap(struct gpujpeg_opengl_texture* texture) { (void)texture; }
+
+/* [ref: src/gpujpeg_common.c:2325-2338] */
+int gj_parse_bool(const char* val, const char* optname)
+{
+    if ( strcasecmp(val, GPUJPEG_VAL_TRUE) == 0 ) return 1;
+    if ( strcasecmp(val, GPUJPEG_VAL_FALSE) == 0 ) return 0;
+    GJ_ERR("Unknown option %s for %s\n", val, optname);
+    return -1;
+}
+
+/* [ref: src/gpujpeg_encoder.c:662-698] "XYZ[W]": output channel i takes input channel <digit i>; 'F' = all ones,
+ * 'Z' = all zeros */
+unsigned gj_parse_channel_remap(const char* val, const char* optname)
+{
+    const int count = (int)strlen(val);
+    if ( count < 1 || count > GPUJPEG_MAX_COMPONENT_COUNT ) {
+        GJ_ERR("Mapping for more than %d channels specified!\n", GPUJPEG_MAX_COMPONENT_COUNT);
+        return 0;
+    }
+    unsigned map = 0;
+    for ( int i = count - 1; i >= 0; i-- ) {
+        int src = val[i] - '0';
+        if ( val[i] == 'F' ) src = 4;
+        else if ( val[i] == 'Z' ) src = 5;
+        else if ( src < 0 || src >= count ) {
+            GJ_ERR("Invalid channel index %c for %s (mapping %d channels)!\n", val[i], optname, count);
+            return 0;
+        }
+        map = map << 4 | (unsigned)src;
+    }
+    return map | (unsigned)count << 24;
+}

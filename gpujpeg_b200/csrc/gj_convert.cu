@@ -109,6 +109,45 @@ k_convert_out(const uint8_t* __restrict__ planes, uint8_t* __restrict__ raw, con
     }
 }
 
+/* vertical flip of the component planes, each over its own padded height [ref: src/gpujpeg_preprocessor.cu:456-485] */
+struct FlipParams {
+    unsigned long long off[GJ_MAX_COMP];
+    int pitch[GJ_MAX_COMP], rows[GJ_MAX_COMP];
+    int comps;
+};
+__global__ void __launch_bounds__(256)
+k_flip_planes(uint8_t* __restrict__ planes, const __grid_constant__ FlipParams p)
+{
+    const int c = blockIdx.z, y = blockIdx.y, x = blockIdx.x * 256 + threadIdx.x;
+    if ( c >= p.comps || y >= p.rows[c] / 2 || x * 4 >= p.pitch[c] ) return;   // pitch is a multiple of 8
+    uint32_t* a = reinterpret_cast<uint32_t*>(planes + p.off[c] + (size_t)y * p.pitch[c]) + x;
+    uint32_t* b = reinterpret_cast<uint32_t*>(planes + p.off[c] + (size_t)(p.rows[c] - 1 - y) * p.pitch[c]) + x;
+    const uint32_t t = *a;
+    *a = *b;
+    *b = t;
+}
+
+/* channel permutation of the raw image, in place: out channel i = in channel (map >> 4i) & 15, 4 = 0xFF, 5 = 0x00
+ * [ref: src/gpujpeg_preprocessor.cu:488-514] */
+struct RemapParams {
+    unsigned long long off[4], pitch[4];
+    int xs[4];
+    int channels, width, height;
+    unsigned map;
+};
+__global__ void __launch_bounds__(256)
+k_channel_remap(uint8_t* __restrict__ raw, const __grid_constant__ RemapParams p)
+{
+    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+    if ( x >= p.width ) return;
+    uint32_t val = 0;
+    for ( int k = 0; k < p.channels; k++ )
+        val |= (uint32_t)raw[p.off[k] + (size_t)y * p.pitch[k] + (size_t)x * p.xs[k]] << (8 * k);
+    val = __byte_perm(val, 0xFFu, p.map);
+    for ( int k = 0; k < p.channels; k++ )
+        raw[p.off[k] + (size_t)y * p.pitch[k] + (size_t)x * p.xs[k]] = (uint8_t)(val >> (8 * k));
+}
+
 int fill_params(ConvertParams* p, const struct gj_raw_layout* raw, enum gpujpeg_pixel_format fmt, int color_space,
                 int color_space_internal, int width, int height, const struct gj_comp_geo* comp, int comp_count, int max_hs,
                 int max_vs)
@@ -164,5 +203,53 @@ extern "C" int gj_launch_convert_out(const uint8_t* d_planes, uint8_t* d_raw, co
     ConvertParams p;
     if ( fill_params(&p, raw, fmt, color_space, color_space_internal, width, height, comp, comp_count, max_hs, max_vs) ) return -1;
     k_convert_out<<<dim3((width + 255) / 256, height), 256, 0, stream>>>(d_planes, d_raw, p);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+/* planes as gj_planes_layout describes them (padded geometry) */
+extern "C" int gj_launch_flip_planes(uint8_t* d_planes, const struct gj_comp_geo* padded, int comp_count, gj_stream_t stream)
+{
+    FlipParams p;
+    memset(&p, 0, sizeof p);
+    if ( comp_count < 1 || comp_count > GJ_MAX_COMP ) return -1;
+    p.comps = comp_count;
+    int max_pitch = 0, max_rows = 0;
+    for ( int c = 0; c < comp_count; c++ ) {
+        p.off[c] = (unsigned long long)padded[c].blk_off * 64;
+        p.pitch[c] = padded[c].bcx * 8;
+        p.rows[c] = padded[c].bcy * 8;
+        if ( p.pitch[c] > max_pitch ) max_pitch = p.pitch[c];
+        if ( p.rows[c] > max_rows ) max_rows = p.rows[c];
+    }
+    k_flip_planes<<<dim3((max_pitch / 4 + 255) / 256, max_rows / 2 > 0 ? max_rows / 2 : 1, comp_count), 256, 0, stream>>>(d_planes, p);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+/* remap = (channel count << 24) | selector nibbles, as the reference's option parser builds it.  Only formats whose
+ * every pixel owns all of its channels (no chroma subsampling inside the pixel format). */
+extern "C" int gj_launch_channel_remap(uint8_t* d_raw, const struct gj_raw_layout* raw, enum gpujpeg_pixel_format fmt, int width,
+                                       int height, unsigned remap, gj_stream_t stream)
+{
+    RemapParams p;
+    memset(&p, 0, sizeof p);
+    const int channels = (int)(remap >> 24);
+    const int have = fmt == GPUJPEG_4444_U8_P0123 ? 4 : raw->comp_count;
+    if ( channels != have ) return -2;   /* [ref: src/gpujpeg_preprocessor.cu:525-531] */
+    for ( int k = 0; k < raw->comp_count; k++ ) {
+        if ( raw->sampling[k].horizontal != raw->sampling[0].horizontal || raw->sampling[k].vertical != raw->sampling[0].vertical ) return -3;
+        p.off[k] = raw->comp[k].off;
+        p.pitch[k] = raw->comp[k].pitch;
+        p.xs[k] = raw->comp[k].xs;
+    }
+    if ( fmt == GPUJPEG_4444_U8_P0123 ) {
+        p.off[3] = raw->comp[0].off + (unsigned)raw->alpha_off;
+        p.pitch[3] = raw->comp[0].pitch;
+        p.xs[3] = raw->comp[0].xs;
+    }
+    p.channels = channels;
+    p.width = width;
+    p.height = height;
+    p.map = remap & 0xFFFFu;
+    k_channel_remap<<<dim3((width + 255) / 256, height), 256, 0, stream>>>(d_raw, p);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

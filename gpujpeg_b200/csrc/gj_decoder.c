@@ -39,6 +39,8 @@ struct gpujpeg_decoder {
     enum gpujpeg_pixel_format req_pixel_format;
     enum gpujpeg_color_space req_color_space;
     int idct_flavour;
+    int flipped;                  /* dec_opt_flipped */
+    unsigned channel_remap;       /* dec_opt_channel_remap: (count << 24) | selector nibbles, 0 = none */
     int thread_per_segment;       /* dec_opt_huffman=thread_per_segment */
     int force_lanes[GJ_MAX_COMP]; /* dec_opt_huffman_lanes: lanes per restart segment by scan, 0 = chosen from the frame's segment count */
     int sm_count;
@@ -306,6 +308,7 @@ static int launch_k4(struct gpujpeg_decoder* d, const int comp_tq[3], uint8_t* d
         if ( gj_launch_idct_samples(d->d_coef, padded, g->comp_count, comp_tq, d->d_planes, &pl, d->idct_flavour,
                                     coef_dequantized, &d->h_tab, d->stream) )
             return -1;
+        if ( d->flipped && gj_launch_flip_planes(d->d_planes, padded, g->comp_count, d->stream) ) return -1;
         return gj_launch_convert_out(d->d_planes, d_out, &d->raw, d->param_image.pixel_format, d->param_image.color_space,
                                      d->param.color_space_internal,
                                      g->width, g->height, g->comp, g->comp_count, g->max_hs, g->max_vs, d->stream);
@@ -383,8 +386,11 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     gpujpeg_image_set_default_parameters(&pi);
     pi.width = st.width;
     pi.height = st.height;
-    const int out_mode = choose_output(d, &st, &pi);
+    int out_mode = choose_output(d, &st, &pi);
     if ( !out_mode ) return GPUJPEG_ERROR;
+    /* the flip acts on the component planes, in front of the postprocessor [ref: src/gpujpeg_postprocessor.cu:447]: only the
+     * pass that has planes can do it */
+    if ( d->flipped ) out_mode = GJ_OUT_GENERIC;
 
     if ( !d->initialised || d->param_image.width != pi.width || d->param_image.height != pi.height ||
          d->param_image.pixel_format != pi.pixel_format || d->param.comp_count != p.comp_count ||
@@ -647,6 +653,15 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
         GJ_ERR("Inverse DCT launch failed: %s\n", gj_cuda_last_error());
         return GPUJPEG_ERROR;
     }
+    if ( d->channel_remap ) {   /* on the finished raw image, in place [ref: src/gpujpeg_postprocessor.cu:450, 493] */
+        struct gj_raw_layout rl;
+        if ( gj_raw_layout_init(&rl, &pi) ) return GPUJPEG_ERROR;
+        const int rc = gj_launch_channel_remap(d_out, &rl, pi.pixel_format, pi.width, pi.height, d->channel_remap, d->stream);
+        if ( rc == -2 ) GJ_ERR("Wrong channel remapping given, given %u channels but pixel format has %d!\n", d->channel_remap >> 24,
+                               gpujpeg_pixel_format_get_comp_count(pi.pixel_format));
+        else if ( rc == -3 ) GJ_ERR("Channel remapping is not implemented for chroma-subsampled pixel formats in this build.\n");
+        if ( rc ) return GPUJPEG_ERROR;
+    }
     if ( stats && d->timers_ok ) {
         gj_timer_stop(&d->t_dct, d->stream);
         gj_timer_stop(&d->t_gpu, d->stream);
@@ -821,8 +836,19 @@ int gpujpeg_decoder_set_option(struct gpujpeg_decoder* decoder, const char* opt,
             decoder->force_lanes[k] = count == 1 ? lanes[0] : lanes[k];
         return GPUJPEG_NOERR;
     }
-    if ( strcmp(opt, GPUJPEG_DEC_OPT_TGA_RLE_BOOL) == 0 || strcmp(opt, GPUJPEG_DEC_OPT_FLIPPED_BOOL) == 0 ||
-         strcmp(opt, GPUJPEG_DEC_OPT_CHANNEL_REMAP) == 0 || strcmp(opt, GPUJPEG_DEC_OPT_ALIGNMENT_BYTES_INT) == 0 ) {
+    if ( strcmp(opt, GPUJPEG_DEC_OPT_FLIPPED_BOOL) == 0 ) {   /* [ref: src/gpujpeg_decoder.c:499-501] */
+        const int b = gj_parse_bool(val, GPUJPEG_DEC_OPT_FLIPPED_BOOL);
+        if ( b < 0 ) return GPUJPEG_ERROR;
+        decoder->flipped = b;
+        return GPUJPEG_NOERR;
+    }
+    if ( strcmp(opt, GPUJPEG_DEC_OPT_CHANNEL_REMAP) == 0 ) {   /* [ref: src/gpujpeg_decoder.c:502-504] */
+        const unsigned m = gj_parse_channel_remap(val, GPUJPEG_DEC_OPT_CHANNEL_REMAP);
+        if ( !m ) return GPUJPEG_ERROR;
+        decoder->channel_remap = m;
+        return GPUJPEG_NOERR;
+    }
+    if ( strcmp(opt, GPUJPEG_DEC_OPT_TGA_RLE_BOOL) == 0 || strcmp(opt, GPUJPEG_DEC_OPT_ALIGNMENT_BYTES_INT) == 0 ) {
         GJ_ERR("Decoder option %s is not implemented in this build.\n", opt);
         return GPUJPEG_ERROR;
     }
@@ -834,6 +860,8 @@ void gpujpeg_decoder_print_options(void)
 {
     printf("\t" GPUJPEG_DEC_OPT_IDCT "=[" GPUJPEG_DEC_IDCT_VAL_INT "|" GPUJPEG_DEC_IDCT_VAL_FLOAT_GPUREF
            "] - inverse DCT flavour (default: int = gpujpeg_idct_cpu)\n");
+    printf("\t" GPUJPEG_DEC_OPT_FLIPPED_BOOL "=[" GPUJPEG_VAL_FALSE "|" GPUJPEG_VAL_TRUE "] - flip the decoded image vertically\n");
+    printf("\t" GPUJPEG_DEC_OPT_CHANNEL_REMAP "=XYZ[W] - output channel mapping (as the encoder option)\n");
 }
 
 /* ---- extension: re-run the GPU stages of the last decoded frame on the JPEG bytes already on the device ----

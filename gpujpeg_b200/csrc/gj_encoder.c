@@ -36,6 +36,9 @@ struct gpujpeg_encoder {
     int quality;                               /* quality the tables were built for (-1 = none) */
     enum gpujpeg_header_type header_type;      /* enc_hdr: forced header flavour, GPUJPEG_HEADER_DEFAULT = by colour space */
     enum gpujpeg_header_type header_written;   /* flavour the cached header bytes were composed with */
+    int flipped;                               /* enc_opt_flipped */
+    int flip_mode;                             /* the input mode was chosen with the flip on */
+    unsigned channel_remap;                    /* enc_opt_channel_remap: (count << 24) | selector nibbles, 0 = none */
     int out_pinned;
 
     uint8_t raw_q[2][64];
@@ -298,6 +301,7 @@ static int launch_k1(struct gpujpeg_encoder* e, const uint8_t* d_raw)
                                   e->param.color_space_internal, g->width, g->height,
                                   e->d_planes, pl.size, g->comp, g->comp_count, g->max_hs, g->max_vs, e->stream) )
             return -1;
+        if ( e->flipped && gj_launch_flip_planes(e->d_planes, padded, g->comp_count, e->stream) ) return -1;
         return gj_launch_fdct_samples(e->d_planes, &pl, e->d_coef, e->d_nzmask, padded, g->comp_count, g->lay.comp_tbl, &e->h_tab,
                                       e->stream);
     }
@@ -335,6 +339,9 @@ static int encoder_init_image(struct gpujpeg_encoder* e, const struct gpujpeg_pa
 {
     gj_geometry_init(&e->geo, p, pi);
     e->input_mode = params_supported(p, pi);
+    /* the flip acts on the component planes [ref: src/gpujpeg_preprocessor.cu:474-485]: only the pass that has planes can do it */
+    if ( e->flipped && e->input_mode != GJ_IN_UNSUPPORTED ) e->input_mode = GJ_IN_GENERIC;
+    e->flip_mode = e->flipped != 0;
     if ( e->input_mode != GJ_IN_RGB && gj_raw_layout_init(&e->raw, pi) ) return -1;
     if ( e->input_mode == GJ_IN_GENERIC && grow((void**)&e->d_planes, &e->d_planes_size, e->geo.coef_count) ) return -1;
     const struct gj_geometry* g = &e->geo;
@@ -525,7 +532,8 @@ int gpujpeg_encoder_encode(struct gpujpeg_encoder* e, const struct gpujpeg_param
         tables_dirty = 1;
     }
     int geometry_dirty = 0;
-    if ( img_changed || !same_param(&e->param, &a) || e->out_is_pinned != e->out_pinned || !e->out ) {
+    if ( img_changed || !same_param(&e->param, &a) || e->out_is_pinned != e->out_pinned || !e->out ||
+         (e->flipped != 0) != e->flip_mode ) {
         if ( encoder_init_image(e, &a, param_image) ) return GPUJPEG_ERROR;
         geometry_dirty = 1;
     }
@@ -580,6 +588,23 @@ int gpujpeg_encoder_encode(struct gpujpeg_encoder* e, const struct gpujpeg_param
         return GPUJPEG_ERROR;
     }
 
+    if ( e->channel_remap ) {
+        /* the permutation works in place on the encoder's own copy of the image [ref: src/gpujpeg_preprocessor.cu:516-559];
+         * a caller's GPU image is copied first instead of being modified */
+        struct gj_raw_layout rl;
+        if ( gj_raw_layout_init(&rl, &e->param_image) ) return GPUJPEG_ERROR;
+        if ( d_raw != e->d_raw ) {
+            if ( grow((void**)&e->d_raw, &e->d_raw_size, g->raw_size) || gj_cuda_memcpy_d2d_async(e->d_raw, d_raw, g->raw_size, e->stream) )
+                return GPUJPEG_ERROR;
+            d_raw = e->d_raw;
+        }
+        const int rc = gj_launch_channel_remap(e->d_raw, &rl, e->param_image.pixel_format, g->width, g->height, e->channel_remap,
+                                               e->stream);
+        if ( rc == -2 ) GJ_ERR("Wrong channel remapping given, given %u channels but pixel format has %d!\n", e->channel_remap >> 24,
+                               gpujpeg_pixel_format_get_comp_count(e->param_image.pixel_format));
+        else if ( rc == -3 ) GJ_ERR("Channel remapping is not implemented for chroma-subsampled pixel formats in this build.\n");
+        if ( rc ) return GPUJPEG_ERROR;
+    }
     if ( stats && e->timers_ok ) {
         gj_timer_start(&e->t_gpu, e->stream);
         gj_timer_start(&e->t_pre, e->stream);
@@ -707,8 +732,19 @@ int gpujpeg_encoder_set_option(struct gpujpeg_encoder* encoder, const char* opt,
         encoder->header_type = t;
         return GPUJPEG_NOERR;
     }
-    if ( strcmp(opt, GPUJPEG_ENC_OPT_FLIPPED_BOOL) == 0 || strcmp(opt, GPUJPEG_ENC_OPT_CHANNEL_REMAP) == 0 ||
-         strcmp(opt, GPUJPEG_ENC_OPT_EXIF_TAG) == 0 || strcmp(opt, GPUJPEG_ENC_OPT_METADATA) == 0 ) {
+    if ( strcmp(opt, GPUJPEG_ENC_OPT_FLIPPED_BOOL) == 0 ) {   /* [ref: src/gpujpeg_encoder.c:767-769] */
+        const int b = gj_parse_bool(val, GPUJPEG_ENC_OPT_FLIPPED_BOOL);
+        if ( b < 0 ) return GPUJPEG_ERROR;
+        encoder->flipped = b;
+        return GPUJPEG_NOERR;
+    }
+    if ( strcmp(opt, GPUJPEG_ENC_OPT_CHANNEL_REMAP) == 0 ) {   /* [ref: src/gpujpeg_encoder.c:770-772] */
+        const unsigned m = gj_parse_channel_remap(val, GPUJPEG_ENC_OPT_CHANNEL_REMAP);
+        if ( !m ) return GPUJPEG_ERROR;
+        encoder->channel_remap = m;
+        return GPUJPEG_NOERR;
+    }
+    if ( strcmp(opt, GPUJPEG_ENC_OPT_EXIF_TAG) == 0 || strcmp(opt, GPUJPEG_ENC_OPT_METADATA) == 0 ) {
         GJ_ERR("Encoder option %s is not implemented in this build.\n", opt);
         return GPUJPEG_ERROR;
     }
@@ -722,6 +758,10 @@ void gpujpeg_encoder_print_options(void)
            "] - output buffer in pageable or pinned host memory\n");
     printf("\t" GPUJPEG_ENC_OPT_HDR "=[" GPUJPEG_ENC_HDR_VAL_JFIF "|" GPUJPEG_ENC_HDR_VAL_ADOBE "|" GPUJPEG_ENC_HDR_VAL_SPIFF
            "] - output JPEG header (default: by internal colour space)\n");
+    printf("\t" GPUJPEG_ENC_OPT_FLIPPED_BOOL "=[" GPUJPEG_VAL_FALSE "|" GPUJPEG_VAL_TRUE
+           "] - whether is the input image should be vertically flipped (prior encode)\n");
+    printf("\t" GPUJPEG_ENC_OPT_CHANNEL_REMAP "=XYZ[W] - input channel mapping, eg. '210F' for GBRX,\n"
+           "\t\t'210' for GBR; special placeholders 'F' and 'Z' to set a channel to all-ones or all-zeros\n");
 }
 
 /* ---- extension: re-run the GPU stages of the last configured frame on device-resident data ----

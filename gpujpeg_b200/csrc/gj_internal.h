@@ -333,6 +333,16 @@ int gj_launch_convert_in(const uint8_t* d_raw, const struct gj_raw_layout* raw, 
 int gj_launch_convert_out(const uint8_t* d_planes, uint8_t* d_raw, const struct gj_raw_layout* raw, enum gpujpeg_pixel_format fmt,
                           int color_space, int color_space_internal, int width, int height, const struct gj_comp_geo* comp,
                           int comp_count, int max_hs, int max_vs, gj_stream_t stream);
+/* enc/dec_opt_flipped: vertical flip of the (padded) component planes; enc/dec_opt_channel_remap: channel permutation of
+ * the raw image in place.  gj_launch_channel_remap returns -2 when the channel count does not match the pixel format and
+ * -3 for pixel formats with chroma subsampling [replaces ref: src/gpujpeg_preprocessor.cu:456-559] */
+int gj_launch_flip_planes(uint8_t* d_planes, const struct gj_comp_geo* padded, int comp_count, gj_stream_t stream);
+int gj_launch_channel_remap(uint8_t* d_raw, const struct gj_raw_layout* raw, enum gpujpeg_pixel_format fmt, int width, int height,
+                            unsigned remap, gj_stream_t stream);
+/* option value -> (channel count << 24) | selector nibbles [ref: src/gpujpeg_encoder.c:662-698]; 0 on error */
+unsigned gj_parse_channel_remap(const char* val, const char* optname);
+/* "1" / "0" / "true" / "false" ... -> 0 / 1, -1 on error [ref: src/gpujpeg_common.c gpujpeg_parse_bool_opt] */
+int gj_parse_bool(const char* val, const char* optname);
 /* the planes above described as a raw layout, so that the sample kernels can run on them */
 void gj_planes_layout(struct gj_raw_layout* l, struct gj_comp_geo padded[GJ_MAX_COMP], const struct gj_comp_geo* comp,
                       int comp_count);

@@ -1232,6 +1232,40 @@ static void cs_transform(int from, int to, int c[3])
 }
 
 /* the sample triple the reference loads for pixel (x, y) [ref: src/gpujpeg_preprocessor.cu:88-160] */
+/* enc_opt_flipped / enc_opt_channel_remap, dec_opt_flipped / dec_opt_channel_remap of the reference, for the generic
+ * paths below (orc_encode_any*, orc_decode_any):
+ *   channel remap  on the RAW image, pixel by pixel: out channel i = in channel (map >> 4i) & 15, 4 = 0xFF, 5 = 0x00
+ *                  (__byte_perm of the packed pixel against 0x000000FF) [ref: src/gpujpeg_preprocessor.cu:488-514,
+ *                  src/gpujpeg_encoder.c:662-698]; the encoder remaps before its colour transform, the decoder after
+ *   flip           on the COMPONENT PLANES, each over its own padded height: row y <-> data_height - 1 - y
+ *                  [ref: src/gpujpeg_preprocessor.cu:456-485]; the encoder flips after the preprocessor, the decoder before
+ *                  the postprocessor [ref: src/gpujpeg_postprocessor.cu:447] */
+static int g_flipped = 0;
+static unsigned g_remap = 0;   /* (channel count << 24) | nibbles, 0 = none */
+void orc_set_flip_remap(int flipped, unsigned remap)
+{
+    g_flipped = flipped;
+    g_remap = remap;
+}
+static void remap_channels(int c[4], int count)
+{
+    if ( !g_remap || (int)(g_remap >> 24) != count ) return;
+    int in[4] = {c[0], c[1], c[2], c[3]};
+    for ( int i = 0; i < count; i++ ) {
+        const unsigned sel = (g_remap >> (4 * i)) & 15u;
+        c[i] = sel < 4 ? in[sel] : sel == 4 ? 0xFF : 0;
+    }
+}
+static void flip_plane(uint8_t* plane, int dw, int dh)
+{
+    for ( int y = 0; y < dh / 2; y++ )
+        for ( int x = 0; x < dw; x++ ) {
+            const uint8_t t = plane[(size_t)y * dw + x];
+            plane[(size_t)y * dw + x] = plane[(size_t)(dh - 1 - y) * dw + x];
+            plane[(size_t)(dh - 1 - y) * dw + x] = t;
+        }
+}
+
 static void raw_load_pixel(const uint8_t* raw, int fmt, const struct rawcomp rc[3], const int fhs[4], const int fvs[4], int x,
                            int y, int c[3])
 {
@@ -1282,8 +1316,10 @@ size_t orc_encode_any2(const uint8_t* raw, int w, int h, int fmt, int cs, int in
     memset(planes, 0, total);
     for ( int y = 0; y < h; y++ )
         for ( int x = 0; x < w; x++ ) {
-            int c[3];
+            int c[4] = {0, 0, 0, 0};
             raw_load_pixel(raw, fmt, rc, fhs, fvs, x, y, c);
+            if ( fmt == 6 ) c[3] = raw[rc[0].off + (size_t)y * rc[0].pitch + (size_t)x * 4 + 3];
+            remap_channels(c, fmt == 6 ? 4 : fmt == 0 ? 1 : 3);
             cs_transform(cs, internal, c);
             for ( int k = 0; k < 3; k++ ) {
                 int dh = max_hs / g[k].hs, dv = max_vs / g[k].vs;
@@ -1291,6 +1327,9 @@ size_t orc_encode_any2(const uint8_t* raw, int w, int h, int fmt, int cs, int in
                 planes[g[k].off + (size_t)(y / dv) * g[k].dw + x / dh] = (uint8_t)c[k];
             }
         }
+    if ( g_flipped )
+        for ( int k = 0; k < comps; k++ )
+            flip_plane(planes + g[k].off, g[k].dw, g[k].dh);
     g_rgb_internal = internal == CS_RGB;
     g_spiff_cs = internal == CS_601 ? 4 : internal == CS_709 ? 1 : 0;
     size_t n = encode_from_planes(planes, g, comps, hs, vs, w, h, quality, rst, interleaved, out, coef);
@@ -1753,21 +1792,25 @@ int orc_decode_any(const uint8_t* jpeg, size_t size, int idct_flavour, int threa
     struct ogeo g[4];
     int max_hs, max_vs;
     uint8_t* planes = decode_to_planes(&P, jpeg, idct_flavour, g, &max_hs, &max_vs, NULL, 1);
+    if ( planes && g_flipped )
+        for ( int k = 0; k < P.comps; k++ )
+            flip_plane(planes + g[k].off, g[k].dw, g[k].dh);
     if ( planes ) {
         for ( int y = 0; y < P.h; y++ )
             for ( int x = 0; x < P.w; x++ ) {
-                int c[3] = {0, 128, 128};
+                int c[4] = {0, 128, 128, 0xFF};
                 for ( int k = 0; k < P.comps; k++ ) {
                     int dh = max_hs / g[k].hs, dv = max_vs / g[k].vs;
                     c[k] = planes[g[k].off + (size_t)(y / dv) * g[k].dw + x / dh];
                 }
                 if ( P.comps == 3 ) cs_transform(stream_cs, cs, c);
+                remap_channels(c, fmt == 6 ? 4 : fcomps == 1 ? 1 : 3);
                 if ( fcomps == 1 ) {
                     raw[rc[0].off + (size_t)y * rc[0].pitch + x] = (uint8_t)c[0];
                     continue;
                 }
                 raw[rc[0].off + (size_t)y * rc[0].pitch + (size_t)x * rc[0].xs] = (uint8_t)c[0];
-                if ( fmt == 6 ) raw[rc[0].off + (size_t)y * rc[0].pitch + (size_t)x * 4 + 3] = 0xFF;   /* alpha */
+                if ( fmt == 6 ) raw[rc[0].off + (size_t)y * rc[0].pitch + (size_t)x * 4 + 3] = (uint8_t)c[3];   /* alpha: 0xFF unless remapped */
                 const int dh = fhs[0], dv = fvs[0];   /* chroma of the format: every dh-th pixel of every dv-th row */
                 if ( fmt == 3 ) {
                     /* U from even pixels, V from odd pixels [ref: src/gpujpeg_preprocessor_common.cuh:179-189] */

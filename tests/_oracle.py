@@ -295,3 +295,26 @@ if os.path.exists(_REF_SO):
                                             C.c_size_t]
     ref.ref_encode_from_coef_cs.restype = C.c_size_t
     ref.ref_idct_block.argtypes = [_i16p, np.ctypeslib.ndpointer(np.uint16)]
+
+
+def remap_code(val):
+    """the reference's option value -> (channel count << 24) | selector nibbles [ref: src/gpujpeg_encoder.c:662-698]"""
+    m = 0
+    for ch in reversed(val):
+        m = m << 4 | (4 if ch == "F" else 5 if ch == "Z" else int(ch))
+    return m | len(val) << 24
+
+
+class flip_remap:
+    """with flip_remap(flipped, "210"): ... -- the generic oracle paths (encode_any, decode_any) apply enc/dec_opt_flipped and
+    enc/dec_opt_channel_remap inside the block"""
+
+    def __init__(self, flipped=False, remap=None):
+        self.args = (1 if flipped else 0, remap_code(remap) if remap else 0)
+
+    def __enter__(self):
+        lib.orc_set_flip_remap.argtypes = [C.c_int, C.c_uint]
+        lib.orc_set_flip_remap(*self.args)
+
+    def __exit__(self, *exc):
+        lib.orc_set_flip_remap(0, 0)

@@ -129,8 +129,19 @@ def main():
         print(json.dumps(reply))
 
 
+def apply_options(lib, coder, opts, decoder):
+    fn = lib.gpujpeg_decoder_set_option if decoder else lib.gpujpeg_encoder_set_option
+    fn.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+    for o in opts:
+        key, _, val = o.partition("=")
+        assert fn(coder, key.encode(), val.encode()) == 0, o
+
+
 def run(lib, a):
-    """one command: a = [mode, arguments...] as on the command line; returns a JSON-able reply or None"""
+    """one command: a = [mode, arguments...] as on the command line; returns a JSON-able reply or None.
+    Arguments of the form opt:<key>=<value> are passed to gpujpeg_{en,de}coder_set_option of the coder the command creates."""
+    opts = [x[4:] for x in a if x.startswith("opt:")]
+    a = [x for x in a if not x.startswith("opt:")]
     mode = a[0]
     if mode == "encode":
         kind, w, h, q, rst, il, path = a[1], *map(int, a[2:7]), a[7]
@@ -146,6 +157,7 @@ def run(lib, a):
         src, fmt, cs, w, h, q, rst, il, path = a[1], *map(int, a[2:9]), a[9]
         raw = np.fromfile(src, np.uint8)
         enc = lib.gpujpeg_encoder_create(None)
+        apply_options(lib, enc, opts, False)
         p, pi = params(lib, w, h, q, rst, il)
         pi.pixel_format, pi.color_space = fmt, cs   # comp_count stays 0: sampling follows the pixel format
         if len(a) > 10:
@@ -155,6 +167,7 @@ def run(lib, a):
     elif mode == "decode_fmt":
         data = np.fromfile(a[1], np.uint8)
         dec = lib.gpujpeg_decoder_create(None)
+        apply_options(lib, dec, opts, True)
         lib.gpujpeg_decoder_set_output_format(dec, int(a[2]), int(a[3]))
         out = DecOut()
         out.type = 0

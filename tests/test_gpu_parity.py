@@ -491,3 +491,64 @@ def test_rgba_input_and_output(gj, enc, il, sub):
         assert np.array_equal(out.reshape(-1), o.decode_any(want, o.FMT_4444_P0123, o.CS_RGB))
     finally:
         d.close()
+
+
+# ---- enc/dec_opt_flipped, enc/dec_opt_channel_remap [ref: src/gpujpeg_preprocessor.cu:456-559] ----
+FLIP_REMAP = [  # fmt, colour space, JPEG subsampling, w, h, flipped, remap
+    (o.FMT_444_P012, o.CS_RGB, "4:4:4", 322, 201, True, None),     # height not a multiple of 8: the flip acts on padded planes
+    (o.FMT_444_P012, o.CS_RGB, "4:2:0", 320, 200, True, None),
+    (o.FMT_444_P012, o.CS_RGB, "4:4:4", 160, 96, False, "210"),    # BGR input
+    (o.FMT_444_P012, o.CS_RGB, "4:2:2", 322, 200, True, "2Z0"),
+    (o.FMT_4444_P0123, o.CS_RGB, "4:4:4", 128, 64, False, "1230"), # ARGB -> RGBA
+    (o.FMT_444_P0P1P2, o.CS_JPEG, "4:4:4", 160, 90, True, "021"),
+    (o.FMT_420_P0P1P2, o.CS_JPEG, None, 320, 200, True, None),     # samples as they are, flipped
+]
+
+
+@pytest.mark.parametrize("fmt,cs,sub,w,h,flipped,remap", FLIP_REMAP)
+def test_flip_and_channel_remap(gj, fmt, cs, sub, w, h, flipped, remap):
+    raw = o.gen_raw(fmt, w, h) if fmt != o.FMT_4444_P0123 else np.random.default_rng(7).integers(0, 256, w * h * 4, dtype=np.uint8)
+    if cs == o.CS_RGB and fmt == o.FMT_444_P012:
+        raw = np.ascontiguousarray(o.gen_image("photo", w, h)).reshape(-1)
+    samp = SUB[sub] or o.FMT_SAMPLING[fmt]
+    with o.flip_remap(flipped, remap):
+        want = o.encode_any(raw, w, h, fmt, cs, 85, 6, 1, samp, threads=4)
+    e = gj.Encoder()
+    try:
+        if flipped:
+            e.set_option("enc_opt_flipped", "1")
+        if remap:
+            e.set_option("enc_opt_channel_remap", remap)
+        got = e.encode_samples(raw, w, h, fmt, 85, 6, 1, color_space=cs, subsampling=sub)
+        assert got.size == want.size and np.array_equal(got, want), "JPEG bytes differ from the oracle"
+        e.set_option("enc_opt_flipped", "0")     # the same encoder without the options: back to the plain stream
+        if remap:
+            e.set_option("enc_opt_channel_remap", "012" if fmt != o.FMT_4444_P0123 else "0123")
+        plain = o.encode_any(raw, w, h, fmt, cs, 85, 6, 1, samp, threads=4)
+        assert np.array_equal(e.encode_samples(raw, w, h, fmt, 85, 6, 1, color_space=cs, subsampling=sub), plain)
+    finally:
+        e.close()
+    d = gj.Decoder()
+    try:
+        if flipped:
+            d.set_option("dec_opt_flipped", "1")
+        if remap:
+            d.set_option("dec_opt_channel_remap", remap)
+        d.set_output_format(cs, fmt)
+        out, pi = d.decode_samples(plain)
+        with o.flip_remap(flipped, remap):
+            assert np.array_equal(out, o.decode_any(plain, fmt, cs, threads=4)), "decoded image differs from the oracle"
+    finally:
+        d.close()
+
+
+def test_channel_remap_needs_the_formats_channel_count(gj):
+    e = gj.Encoder()
+    try:
+        e.set_option("enc_opt_channel_remap", "0123")
+        with pytest.raises(gj.GpuJpegError):
+            e.encode(o.gen_image("photo", 64, 48))
+        with pytest.raises(gj.GpuJpegError):
+            e.set_option("enc_opt_channel_remap", "015")
+    finally:
+        e.close()

@@ -217,3 +217,37 @@ def test_reference_gpu_rgba(tmp_path):
     d.set_output_format(1, 6)
     assert np.array_equal(d.decode_samples(ref)[0], pix), "product decode != reference GPU decoder"
     d.close()
+
+
+@pytest.mark.skipif(not os.path.exists(SO), reason="oracle/_ref/libgpujpeg_refgpu.so not built")
+@pytest.mark.parametrize("fmt,cs,w,h,flipped,remap", [(1, 1, 322, 201, True, None), (1, 1, 160, 96, False, "210"), (1, 1, 322, 200, True, "2Z0"),
+                                                      (6, 1, 128, 64, False, "1230"), (5, 3, 320, 200, True, None)])
+def test_reference_gpu_flip_and_channel_remap(tmp_path, fmt, cs, w, h, flipped, remap):
+    """enc/dec_opt_flipped and enc/dec_opt_channel_remap: reference GPU library == oracle == product"""
+    raw = o.gen_raw(fmt, w, h) if fmt not in (1, 6) else np.ascontiguousarray(o.gen_image("photo", w, h)).reshape(-1)
+    if fmt == 6:
+        raw = np.random.default_rng(7).integers(0, 256, w * h * 4, dtype=np.uint8)
+    src, path, dst = tmp_path / "in.raw", tmp_path / "ref.jpg", tmp_path / "out.raw"
+    raw.tofile(src)
+    eopts = (["opt:enc_opt_flipped=1"] if flipped else []) + (["opt:enc_opt_channel_remap=" + remap] if remap else [])
+    dopts = (["opt:dec_opt_flipped=1"] if flipped else []) + (["opt:dec_opt_channel_remap=" + remap] if remap else [])
+    run_ref("encode_raw", src, fmt, cs, w, h, 85, 6, 1, path, *eopts)
+    ref = np.fromfile(path, np.uint8)
+    with o.flip_remap(flipped, remap):
+        want = o.encode_any(raw, w, h, fmt, cs, 85, 6, 1, o.FMT_SAMPLING[fmt] if fmt != 6 else (1, 1), threads=4)
+    assert ref.size == want.size and np.array_equal(ref, want), "oracle restatement != reference GPU library output"
+    run_ref("decode_fmt", path, cs, fmt, dst, *dopts)
+    pix = np.fromfile(dst, np.uint8)
+    with o.flip_remap(flipped, remap):
+        assert np.array_equal(pix, o.decode_any(ref, fmt, cs, o.IDCT_FLOAT_GPUREF, threads=4)), "oracle != reference GPU decoder"
+    import gpujpeg_b200 as g
+    d = g.Decoder(idct="float_gpuref")
+    try:
+        if flipped:
+            d.set_option("dec_opt_flipped", "1")
+        if remap:
+            d.set_option("dec_opt_channel_remap", remap)
+        d.set_output_format(cs, fmt)
+        assert np.array_equal(d.decode_samples(ref)[0], pix), "product decode != reference GPU decoder"
+    finally:
+        d.close()
