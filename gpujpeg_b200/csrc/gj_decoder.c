@@ -59,6 +59,7 @@ struct gpujpeg_decoder {
     uint8_t* d_list_code; size_t d_list_code_size;  /*                  codes     */
     uint32_t* d_list_cpos; size_t d_list_cpos_size; /*                  positions in the clean stream */
     uint8_t* d_clean; size_t d_clean_size;          /* K0 clean stream: stuffing and markers removed, big-endian words */
+    uint32_t* d_seg_tab; size_t d_seg_tab_size;     /* resynchronised streams only: per segment {raw start, clean start, clean end} */
     unsigned long long* d_cta; size_t d_cta_size;   /* K0 scratch */
     uint32_t* d_mk;                                 /* K0 results (layout in gpujpeg_decoder_decode) */
     uint32_t* h_mk;                                 /* pinned mirror */
@@ -155,6 +156,7 @@ int gpujpeg_decoder_destroy(struct gpujpeg_decoder* d)
     gj_cuda_free(d->d_list_code);
     gj_cuda_free(d->d_list_cpos);
     gj_cuda_free(d->d_clean);
+    gj_cuda_free(d->d_seg_tab);
     gj_cuda_free(d->d_cta);
     gj_cuda_free(d->d_mk);
     gj_cuda_free_host(d->h_mk);
@@ -318,6 +320,80 @@ static int launch_k4(struct gpujpeg_decoder* d, const int comp_tq[3], uint8_t* d
                                      coef_dequantized, &d->h_tab, d->stream);
     return gj_launch_idct_rgb_ss(d->d_coef, g->comp, comp_tq, d_out, g->width, g->height, g->pitch, d->idct_flavour,
                                  coef_dequantized, &d->h_tab, d->stream);
+}
+
+/* A stream whose restart markers do not count RST0..RST7 cyclically (or whose count does not fit the geometry): the
+ * reference's reader ends the current segment at the offending marker, skips everything up to the next marker that
+ * carries the EXPECTED number, and goes on from there with consecutive segment numbers; when no such marker follows, the
+ * rest of the scan is dropped [ref: src/gpujpeg_reader.c:1038-1155].  The same walk here, over the marker list K0 built
+ * (fetched from the device only on this path); the result is an explicit table {raw start, clean start, clean end} per
+ * segment for K3, segments that no longer exist marked absent (their blocks decode to zero, as the reference's cleared
+ * coefficient buffer gives, src/gpujpeg_decoder.c:301). */
+static int resync_segments(struct gpujpeg_decoder* d, const struct gj_stream* st, const uint32_t first_rank[GJ_MAX_COMP],
+                           const uint32_t end_rank[GJ_MAX_COMP], const uint32_t scan_cbegin[GJ_MAX_COMP], struct gj_huff_dec_args* ha)
+{
+    const struct gj_geometry* g = &d->geo;
+    const uint32_t n_list = end_rank[g->scan_count - 1] + 1;
+    uint8_t* code = (uint8_t*)malloc((size_t)n_list);
+    uint32_t* pos = (uint32_t*)malloc((size_t)n_list * 8);
+    uint32_t* tab = (uint32_t*)malloc((size_t)g->seg_count * 12);
+    int rc = -1;
+    if ( code && pos && tab && !gj_cuda_memcpy_d2h_async(code, d->d_list_code, n_list, d->stream) &&
+         !gj_cuda_memcpy_d2h_async(pos, d->d_list_pos, (size_t)n_list * 4, d->stream) &&
+         !gj_cuda_memcpy_d2h_async(pos + n_list, d->d_list_cpos, (size_t)n_list * 4, d->stream) && !gj_cuda_stream_sync(d->stream) ) {
+        const uint32_t* cpos = pos + n_list;
+        for ( int k = 0; k < g->scan_count; k++ ) {
+            const int seg0 = g->lay.scan_seg_begin[k], segs = g->lay.scan_seg_begin[k + 1] - seg0;
+            int n = 0, prev = 7;   /* "RST0 - 1" */
+            uint32_t start_raw = (uint32_t)st->scan[k].begin, start_clean = scan_cbegin[k];
+            uint32_t m = first_rank[k];
+            while ( m < end_rank[k] && n < segs ) {   /* markers [first_rank, end_rank) are the scan's RSTn */
+                const int expected = (prev + 1) & 7;
+                tab[3 * (seg0 + n)] = start_raw;
+                tab[3 * (seg0 + n) + 1] = start_clean;
+                tab[3 * (seg0 + n) + 2] = cpos[m];
+                n++;
+                if ( (code[m] & 7) != expected ) {
+                    GJ_ERR("Expected marker 0x%X but 0x%X was presented!\n", 0xD0 + expected, code[m]);
+                    uint32_t q = m + 1;
+                    while ( q < end_rank[k] && code[q] != 0xD0 + expected ) q++;
+                    if ( q >= end_rank[k] ) {
+                        GJ_ERR("No marker 0x%X was found until end of current scan!\n", 0xD0 + expected);
+                        m = end_rank[k] + 1;   /* the rest of the scan is lost */
+                        break;
+                    }
+                    fprintf(stderr, "[GPUJPEG] [Recovery] Skipping %u bytes of data until marker 0x%X was found!\n",
+                            pos[q] - pos[m], 0xD0 + expected);
+                    m = q;
+                }
+                prev = expected;
+                start_raw = pos[m] + 2;
+                start_clean = cpos[m];
+                m++;
+            }
+            if ( m <= end_rank[k] && n < segs ) {   /* the data in front of the marker that ends the scan */
+                tab[3 * (seg0 + n)] = start_raw;
+                tab[3 * (seg0 + n) + 1] = start_clean;
+                tab[3 * (seg0 + n) + 2] = cpos[end_rank[k]];
+                n++;
+            }
+            for ( ; n < segs; n++ ) {
+                tab[3 * (seg0 + n)] = 0xFFFFFFFFu;   /* absent */
+                tab[3 * (seg0 + n) + 1] = tab[3 * (seg0 + n) + 2] = 0;
+            }
+        }
+        if ( !grow_dev((void**)&d->d_seg_tab, &d->d_seg_tab_size, (size_t)g->seg_count * 12) &&
+             !gj_cuda_memcpy_h2d_async(d->d_seg_tab, tab, (size_t)g->seg_count * 12, d->stream) &&
+             !gj_cuda_memset_async(d->d_mk + 3, 0, 4, d->stream) && !gj_cuda_stream_sync(d->stream) ) {
+            ha->d_seg_tab = d->d_seg_tab;
+            rc = 0;
+        }
+    }
+    if ( rc ) GJ_ERR("Restart resynchronisation failed: %s\n", gj_cuda_last_error());
+    free(code);
+    free(pos);
+    free(tab);
+    return rc;
 }
 
 /* [ref: src/gpujpeg_decoder.c:234-469] */
@@ -572,16 +648,20 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
         gj_timer_start(&d->t_gpu, d->stream);
         gj_timer_start(&d->t_huff, d->stream);
     }
-    /* restart structure [ref: src/gpujpeg_reader.c:1038-1155]: scan k must hold one restart marker per segment
-     * boundary, all of them (and the marker that ends the scan) inside the device list */
+    /* restart structure [ref: src/gpujpeg_reader.c:1038-1155]: scan k should hold one restart marker per segment boundary,
+     * counting RST0..RST7 cyclically.  The count is checked here, the numbering by K3; a stream that fails either is
+     * resynchronised the way the reference's reader does it (resync_segments below) and decoded from an explicit
+     * segment table. */
+    int resync = 0;
     for ( int k = 0; k < g->scan_count; k++ ) {
         const int segs = g->lay.scan_seg_begin[k + 1] - g->lay.scan_seg_begin[k];
-        if ( end_rank[k] >= list_cap || end_rank[k] - first_rank[k] != (uint32_t)(segs - 1) ) {
+        if ( end_rank[k] >= list_cap ) {
             GJ_ERR("JPEG stream has a broken restart-marker structure (scan %d holds %u restart markers, expected %d "
                    "for a %dx%d image with restart interval %d)!\n", k, end_rank[k] - first_rank[k], segs - 1, st.width,
                    st.height, st.restart_interval);
             return GPUJPEG_ERROR;
         }
+        if ( end_rank[k] - first_rank[k] != (uint32_t)(segs - 1) ) resync = 1;
     }
 
     /* ---- K3 ---- */
@@ -630,6 +710,11 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     d->last_list_cap = list_cap;
     memcpy(d->last_tq, st.comp_tq, sizeof d->last_tq);
     d->last_valid = 1;
+  for ( int pass = 0;; pass++ ) {
+    if ( resync ) {
+        if ( resync_segments(d, &st, first_rank, end_rank, scan_cbegin, &ha) ) return GPUJPEG_ERROR;
+        d->last_args = ha;
+    }
     if ( gj_launch_huffman_decode(&ha, d->stream) ) {
         GJ_ERR("Huffman decoder launch failed: %s\n", gj_cuda_last_error());
         return GPUJPEG_ERROR;
@@ -693,13 +778,13 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
         GJ_ERR("Decoder failed: %s\n", gj_cuda_last_error());
         return GPUJPEG_ERROR;
     }
-    if ( d->h_mk[3] ) {
-        /* the reference tries to resynchronise on a broken restart sequence
-         * [ref: src/gpujpeg_reader.c:1071-1105]; here it is reported, not repaired */
-        GJ_ERR("JPEG stream has a broken restart-marker sequence (RSTn do not count 0..7 cyclically; %dx%d image, "
-               "restart interval %d)!\n", st.width, st.height, st.restart_interval);
-        return GPUJPEG_ERROR;
+    if ( d->h_mk[3] && !resync && pass == 0 ) {
+        /* K3 met a restart marker with the wrong number: resynchronise [ref: src/gpujpeg_reader.c:1071-1105] and decode again */
+        resync = 1;
+        continue;
     }
+    break;
+  }
     output->metadata = &d->metadata;
 
     d->stats_valid = 0;

@@ -51,6 +51,10 @@ struct gpujpeg_encoder {
     int16_t* d_coef; size_t d_coef_size;
     uint64_t* d_nzmask; size_t d_nzmask_size;
     uint8_t* d_tmp; size_t d_tmp_size;
+    size_t slot_stride;              /* bytes per restart segment in d_tmp: starts at 48 bytes per block (photographic and noisy
+                                      * content at any common quality), grows to what a frame needed when K2 reports an overflow;
+                                      * the worst case (geo.slot_stride, 416 bytes per block: 648 MB for an 8K frame) is only ever
+                                      * allocated for content that needs it */
     uint32_t* d_spill; size_t d_spill_size;
     uint32_t* d_seg_bytes; uint64_t* d_seg_off; int seg_alloc;
     uint8_t* d_stream; size_t d_stream_size;
@@ -321,7 +325,7 @@ static void fill_huff_args(const struct gpujpeg_encoder* e, struct gj_huff_enc_a
     ha->seg_mcu = g->seg_mcu;
     ha->d_tmp = e->d_tmp;
     ha->d_spill = e->d_spill;
-    ha->slot_stride = g->slot_stride;
+    ha->slot_stride = e->slot_stride;
     ha->d_seg_bytes = e->d_seg_bytes;
     ha->d_seg_off = e->d_seg_off;
     ha->d_stream = e->d_stream;
@@ -346,7 +350,11 @@ static int encoder_init_image(struct gpujpeg_encoder* e, const struct gpujpeg_pa
     if ( e->input_mode == GJ_IN_GENERIC && grow((void**)&e->d_planes, &e->d_planes_size, e->geo.coef_count) ) return -1;
     const struct gj_geometry* g = &e->geo;
     size_t coef_bytes = g->coef_count * sizeof(int16_t);
-    size_t tmp_bytes = (size_t)g->seg_count * g->slot_stride + 256;
+    const size_t segblk_all = (size_t)g->seg_mcu * (size_t)g->lay.bpm;
+    size_t first_stride = (segblk_all * 48 + 2 + 127) / 128 * 128;
+    if ( first_stride > g->slot_stride ) first_stride = g->slot_stride;
+    if ( e->slot_stride < first_stride || e->slot_stride > g->slot_stride ) e->slot_stride = first_stride;
+    size_t tmp_bytes = (size_t)g->seg_count * e->slot_stride + 256;
     /* overflow area of the per-block bit strings: 32 words per block of a short segment (packed kernel, <= 40 blocks),
      * per lane of a warp otherwise (streaming kernel) */
     const int segblk = g->seg_mcu * g->lay.bpm;
@@ -485,7 +493,9 @@ size_t gpujpeg_encoder_max_memory(struct gpujpeg_parameters* param, struct gpujp
     if ( pi.height < 1 ) pi.height = 1;
     if ( p.restart_interval == RESTART_AUTO ) p.restart_interval = 36;
     gj_geometry_init(&g, &p, &pi);
-    size_t total = g.coef_count * 2 + (size_t)g.seg_count * g.slot_stride + g.stream_cap + (size_t)g.seg_count * 12;
+    /* scan slots at their initial size (48 bytes per block); denser content grows them, up to 416 bytes per block */
+    size_t total = g.coef_count * 2 + (size_t)g.seg_count * (((size_t)g.seg_mcu * g.lay.bpm * 48 + 2 + 127) / 128 * 128) + g.stream_cap +
+                   (size_t)g.seg_count * 12;
     if ( image_input_type == GPUJPEG_ENCODER_INPUT_IMAGE ) total += g.raw_size;
     return total;
 }
@@ -632,6 +642,25 @@ int gpujpeg_encoder_encode(struct gpujpeg_encoder* e, const struct gpujpeg_param
     if ( gj_cuda_memcpy_d2h_async(e->h_info, e->d_info, 32, e->stream) || gj_cuda_stream_sync(e->stream) ) {
         GJ_ERR("Encoder failed: %s\n", gj_cuda_last_error());
         return GPUJPEG_ERROR;
+    }
+    if ( e->h_info[1] & 2 ) {
+        /* a restart segment did not fit its slot: K2 counted what it needs (h_info[2]); enlarge the slots and run K2 again on
+         * the coefficients K1 left in place.  Happens once per encoder for unusually dense content. */
+        size_t need = ((size_t)e->h_info[2] + 127) / 128 * 128;
+        if ( need > g->slot_stride ) need = g->slot_stride;
+        if ( need <= e->slot_stride ) need = g->slot_stride;
+        GJ_VERBOSE(a.verbose, "Enlarging the scan buffer to %zu bytes per restart segment.\n", need);
+        e->slot_stride = need;
+        if ( grow((void**)&e->d_tmp, &e->d_tmp_size, (size_t)g->seg_count * e->slot_stride + 256) ) {
+            GJ_ERR("Encoder device allocation failed (%zu bytes): %s\n", (size_t)g->seg_count * e->slot_stride, gj_cuda_last_error());
+            return GPUJPEG_ERROR;
+        }
+        fill_huff_args(e, &ha);
+        if ( gj_launch_huffman_encode(&ha, e->stream) || gj_cuda_memcpy_d2h_async(e->h_info, e->d_info, 32, e->stream) ||
+             gj_cuda_stream_sync(e->stream) ) {
+            GJ_ERR("Encoder failed: %s\n", gj_cuda_last_error());
+            return GPUJPEG_ERROR;
+        }
     }
     const size_t total = (size_t)e->h_info[0];
     if ( e->h_info[1] || total > e->out_size || total < e->header_size + 2 ) {

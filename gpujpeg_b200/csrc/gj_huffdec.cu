@@ -65,6 +65,7 @@ struct SdParams {
     const uint32_t* clean;
     const uint32_t* list_cpos;
     const uint8_t* list_code;
+    const uint32_t* seg_tab;             // resynchronised streams: {file offset, clean start, clean end} per segment, or NULL
     uint32_t first_rank[GJ_MAX_COMP], scan_cbegin[GJ_MAX_COMP];
     int cta_begin[GJ_MAX_COMP + 1];      // first CTA of every scan
     int units_per_warp;
@@ -355,11 +356,14 @@ __device__ __forceinline__ void run_units(const SdParams& P, const int scan, Wal
         /* ---- the unit's clean bytes (its segments follow each other in the clean stream) -> shared memory, with
          *      coalesced 16-byte loads, when they fit ---- */
         const int s_first = unit * spu, s_last = min(s_first + spu, scan_segs) - 1;
-        const uint32_t cs0 = s_first ? __ldg(P.list_cpos + P.first_rank[scan] + s_first - 1) : P.scan_cbegin[scan];
-        const uint32_t ce1 = __ldg(P.list_cpos + P.first_rank[scan] + s_last);
+        uint32_t cs0 = 0, ce1 = 0;
+        if ( !P.seg_tab ) {
+            cs0 = s_first ? __ldg(P.list_cpos + P.first_rank[scan] + s_first - 1) : P.scan_cbegin[scan];
+            ce1 = __ldg(P.list_cpos + P.first_rank[scan] + s_last);
+        }
         const uint32_t wbase = (cs0 >> 2) & ~3u;
         const uint32_t need = ce1 > cs0 ? ((ce1 + 3u) >> 2) - wbase + 8u : 8u;   // + slack: a walk peeks up to 95 bits past the end
-        const bool fits = need <= (uint32_t)P.cmp_words;
+        const bool fits = !P.seg_tab && need <= (uint32_t)P.cmp_words;   // (a resynchronised stream's segments need not be adjacent)
         if ( fits ) {
             const uint4* src = reinterpret_cast<const uint4*>(P.clean + wbase);
             uint4* dst = reinterpret_cast<uint4*>(s_cmp);
@@ -376,11 +380,19 @@ __device__ __forceinline__ void run_units(const SdParams& P, const int scan, Wal
         if ( valid ) {
             first_mcu = s * P.seg_mcu;
             nblocks = min(P.seg_mcu, L.scan_mcus[scan] - first_mcu) * L.bpm;
-            const uint32_t r = P.first_rank[scan] + (uint32_t)s;   // the marker that ends the segment
-            const uint32_t ce = __ldg(P.list_cpos + r);
-            const uint32_t cs = s ? __ldg(P.list_cpos + r - 1) : P.scan_cbegin[scan];
-            /* restart markers must count D0..D7 cyclically [ref: src/gpujpeg_reader.c:1068-1071] */
-            if ( s && gl == 0 && __ldg(P.list_code + r - 1) != (uint8_t)(0xD0 + ((s - 1) & 7)) ) atomicExch(P.error, 1u);
+            uint32_t cs, ce;
+            if ( P.seg_tab ) {   // explicit table; absent segments have an empty range
+                const uint32_t* t = P.seg_tab + 3 * (size_t)(L.scan_seg_begin[scan] + s);
+                cs = __ldg(t + 1);
+                ce = __ldg(t + 2);
+            }
+            else {
+                const uint32_t r = P.first_rank[scan] + (uint32_t)s;   // the marker that ends the segment
+                ce = __ldg(P.list_cpos + r);
+                cs = s ? __ldg(P.list_cpos + r - 1) : P.scan_cbegin[scan];
+                /* restart markers must count D0..D7 cyclically [ref: src/gpujpeg_reader.c:1068-1071] */
+                if ( s && gl == 0 && __ldg(P.list_code + r - 1) != (uint8_t)(0xD0 + ((s - 1) & 7)) ) atomicExch(P.error, 1u);
+            }
             len = ce > cs ? min(ce - cs, (uint32_t)SD_MAXLEN) : 0u;
             W.cw = P.clean + (cs >> 2);
             W.sw = s_cmp + ((cs >> 2) - wbase);
@@ -620,6 +632,7 @@ extern "C" int gj_launch_huffman_decode_sync(const struct gj_huff_dec_args* a, g
     P.clean = a->d_clean;
     P.list_cpos = a->d_list_cpos;
     P.list_code = a->d_list_code;
+    P.seg_tab = a->d_seg_tab;
     P.seg_mcu = a->seg_mcu;
     P.error = a->d_error;
     P.coef = a->d_coef;

@@ -96,8 +96,10 @@ constexpr int HE_WARPS = 8;
 constexpr int HE_WORDS = 512;                    // per-warp bit buffer, 32-bit words (2 KB)
 constexpr int HE_CAP_BITS = (HE_WORDS - 2) * 32; // keep slack for the trailing partial word
 
-/* stuff + store `nw` complete words of the bit buffer to out[pos...]; returns new pos (uniform) */
-__device__ __forceinline__ uint32_t flush_words(const uint32_t* buf, int nw, uint8_t* out, uint32_t pos, int lane)
+/* stuff + store `nw` complete words of the bit buffer to out[pos...]; returns new pos (uniform).  Bytes that would land
+ * at or behind `cap` are counted but not stored (the segment's slot is smaller than the worst case; the caller reports
+ * the overflow and the host retries with slots of the size that was counted). */
+__device__ __forceinline__ uint32_t flush_words(const uint32_t* buf, int nw, uint8_t* out, uint32_t pos, int lane, uint32_t cap)
 {
     for ( int base = 0; base < nw; base += 32 ) {
         const int i = base + lane;
@@ -112,7 +114,7 @@ __device__ __forceinline__ uint32_t flush_words(const uint32_t* buf, int nw, uin
         }
         const int incl = warp_incl_scan(cnt, lane);
         uint8_t* o = out + pos + (incl - cnt);
-        if ( i < nw ) {
+        if ( i < nw && pos + (uint32_t)incl <= cap ) {
 #pragma unroll
             for ( int j = 3; j >= 0; j-- ) {
                 const uint8_t b = (uint8_t)(w >> (8 * j));
@@ -145,8 +147,10 @@ constexpr int HE_SMEM = (2 * 256 + 2 * 16 + HE_WARPS * HE_WORDS + HE_WARPS * 32 
 __global__ void __launch_bounds__(HE_WARPS * 32)
 k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzmask, const __grid_constant__ gj_scan_layout lay,
               int seg_mcu, int seg_count, uint8_t* __restrict__ tmp, size_t slot_stride,
-              uint32_t* __restrict__ seg_bytes, uint32_t* __restrict__ spill_all, const gj_dev_enc_tables* __restrict__ tables)
+              uint32_t* __restrict__ seg_bytes, uint32_t* __restrict__ spill_all, const gj_dev_enc_tables* __restrict__ tables,
+              uint64_t* __restrict__ info)
 {
+    const uint32_t slot_cap = (uint32_t)slot_stride;
     extern __shared__ __align__(16) uint32_t he_smem[];
     uint32_t (*s_ac)[256] = reinterpret_cast<uint32_t (*)[256]>(he_smem);
     uint32_t (*s_dc)[16] = reinterpret_cast<uint32_t (*)[16]>(he_smem + 512);
@@ -309,7 +313,7 @@ k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzm
             const int lastl = lane0 + nfit - 1;
             const int newbits = carry + (__shfl_sync(FULL, incl, lastl) - rel0);
             const int nwords = newbits >> 5;
-            out_pos = flush_words(buf, nwords, out, out_pos, lane);
+            out_pos = flush_words(buf, nwords, out, out_pos, lane, slot_cap);
             __syncwarp();
             /* keep the trailing partial word as the new word 0, clear what was used */
             const uint32_t tail = buf[nwords];
@@ -330,13 +334,20 @@ k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzm
         uint32_t w = buf[0];
         const int nbytes = (carry + 7) >> 3;
         if ( carry & 7 ) w |= ((1u << (8 - (carry & 7))) - 1u) << (32 - nbytes * 8);
-        uint8_t* o = out + out_pos;
+        uint32_t n = out_pos;
         for ( int q = 0; q < nbytes; q++ ) {
             const uint8_t b = (uint8_t)(w >> (24 - 8 * q));
-            *o++ = b;
-            if ( b == 0xFF ) *o++ = 0;
+            if ( n + 2u <= slot_cap ) {
+                out[n] = b;
+                if ( b == 0xFF ) out[n + 1] = 0;
+            }
+            n += b == 0xFF ? 2u : 1u;
         }
-        seg_bytes[g] = (uint32_t)(o - out);
+        seg_bytes[g] = n;
+        if ( n + 2u > slot_cap ) {   // (+2: the compaction reads whole words) the slot was too small: size needed -> info[2]
+            atomicOr(reinterpret_cast<unsigned long long*>(info + 1), 2ull);
+            atomicMax(reinterpret_cast<unsigned long long*>(info + 2), (unsigned long long)n + 2ull);
+        }
     }
 }
 
@@ -359,8 +370,9 @@ __global__ void __launch_bounds__(HP_THREADS_MAX)
 k_huff_encode_packed(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzmask,
                      const __grid_constant__ gj_scan_layout lay, int seg_mcu, int seg_count, uint8_t* __restrict__ tmp,
                      size_t slot_stride, uint32_t* __restrict__ seg_bytes, uint32_t* __restrict__ spill_all,
-                     const gj_dev_enc_tables* __restrict__ tables)
+                     const gj_dev_enc_tables* __restrict__ tables, uint64_t* __restrict__ info)
 {
+    const uint32_t slot_cap = (uint32_t)slot_stride;
     extern __shared__ __align__(16) uint32_t he_smem[];
     uint32_t (*s_ac)[256] = reinterpret_cast<uint32_t (*)[256]>(he_smem);
     uint32_t (*s_dc)[16] = reinterpret_cast<uint32_t (*)[16]>(he_smem + 512);
@@ -508,7 +520,7 @@ k_huff_encode_packed(const int16_t* __restrict__ coef, const uint64_t* __restric
                       total0 + incl1 - len1, len1);
             __syncwarp();
             const int nwords = total >> 5;
-            out_pos = flush_words(buf, nwords, out, out_pos, lane);
+            out_pos = flush_words(buf, nwords, out, out_pos, lane, slot_cap);
             __syncwarp();
             carry = total & 31;
             if ( lane == 0 ) buf[0] = buf[nwords];   // the trailing partial word, finished below
@@ -537,7 +549,7 @@ k_huff_encode_packed(const int16_t* __restrict__ coef, const uint64_t* __restric
                     const int lastl = lane0 + nfit - 1;
                     const int newbits = carry + (__shfl_sync(FULL, incl, lastl) - rel0);
                     const int nwords = newbits >> 5;
-                    out_pos = flush_words(buf, nwords, out, out_pos, lane);
+                    out_pos = flush_words(buf, nwords, out, out_pos, lane, slot_cap);
                     __syncwarp();
                     const uint32_t tail = buf[nwords];
                     __syncwarp();
@@ -557,13 +569,20 @@ k_huff_encode_packed(const int16_t* __restrict__ coef, const uint64_t* __restric
         uint32_t w = buf[0];
         const int nbytes = (carry + 7) >> 3;
         if ( carry & 7 ) w |= ((1u << (8 - (carry & 7))) - 1u) << (32 - nbytes * 8);
-        uint8_t* o = out + out_pos;
+        uint32_t n = out_pos;
         for ( int q = 0; q < nbytes; q++ ) {
             const uint8_t b = (uint8_t)(w >> (24 - 8 * q));
-            *o++ = b;
-            if ( b == 0xFF ) *o++ = 0;
+            if ( n + 2u <= slot_cap ) {
+                out[n] = b;
+                if ( b == 0xFF ) out[n + 1] = 0;
+            }
+            n += b == 0xFF ? 2u : 1u;
         }
-        seg_bytes[g] = (uint32_t)(o - out);
+        seg_bytes[g] = n;
+        if ( n + 2u > slot_cap ) {   // (+2: the compaction reads whole words) the slot was too small: size needed -> info[2]
+            atomicOr(reinterpret_cast<unsigned long long*>(info + 1), 2ull);
+            atomicMax(reinterpret_cast<unsigned long long*>(info + 2), (unsigned long long)n + 2ull);
+        }
     }
 }
 
@@ -647,7 +666,7 @@ k_huff_offsets(const uint32_t* __restrict__ seg_bytes, int seg_count, const __gr
     if ( end == seg_count && threadIdx.x == 0 ) {
         const uint64_t total = base + 2;  // + EOI
         info[0] = total;
-        info[1] = total > stream_cap ? 1 : 0;
+        info[1] = (info[1] & 2ull) | (total > stream_cap ? 1ull : 0ull);   // bit 1: a segment slot overflowed (set by the encoder)
     }
 }
 
@@ -863,7 +882,7 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file
         g_end = seg_count;
     }
     if ( g0 >= g_end ) return;
-    if ( !seg_off && *a.d_error ) return;   // restart structure does not match the geometry: list ranks are meaningless
+    if ( !seg_off && !a.d_seg_tab && *a.d_error ) return;   // restart structure does not match the geometry: list ranks are meaningless
     const int g = g0 + lane;
     const bool live = lane < SPW && g < g_end;
     const gj_scan_layout& L = a.lay;
@@ -873,6 +892,7 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file
     int mx = 0, my = 0;   // general layout: position of the lane's current MCU
     BitSource r;
     r.n = 0;
+    bool absent = false;
     if ( live ) {
         scan = scan_of_segment(L, g);
         const int s = g - L.scan_seg_begin[scan];
@@ -885,7 +905,11 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file
             mx = s * seg_mcu - my * L.mcu_x;
         }
         uint32_t start;
-        if ( seg_off ) {
+        if ( a.d_seg_tab ) {   // resynchronised stream: explicit table, 0xFFFFFFFF = the segment does not exist (zero blocks)
+            start = a.d_seg_tab[3 * (size_t)g];
+            absent = start == 0xFFFFFFFFu;
+        }
+        else if ( seg_off ) {
             start = seg_off[g];
         }
         else if ( s == 0 ) {
@@ -912,7 +936,7 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file
     for ( int b = 0; b < max_blocks; b++ ) {
         /* ci: position of the block's component in the scan header (tables, predictor) */
         const int ci = general ? L.idx_comp[bi_in_mcu] : bi_in_mcu;
-        if ( live && b < nblocks ) {
+        if ( live && !absent && b < nblocks ) {
             const gj_dec_lut& tdc = s_tab.t[0][a.scan_td[scan][ci]];
             const gj_dec_lut& tac = s_tab.t[1][a.scan_ta[scan][ci]];
             const uint16_t* q = s_q[a.scan_tq[scan][ci]];
@@ -996,6 +1020,7 @@ __global__ void k_coef_to_natural(const int16_t* __restrict__ in, int16_t* __res
 extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_stream_t stream)
 {
     const int seg_count = a->lay.scan_seg_begin[GJ_MAX_COMP];
+    if ( cudaMemsetAsync(a->d_info, 0, 32, stream) != cudaSuccess ) return -1;
     ScanSegs segs;
     for ( int k = 0; k <= GJ_MAX_COMP; k++ )
         segs.begin[k] = a->lay.scan_seg_begin[k];
@@ -1017,12 +1042,12 @@ extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_str
         const int hp_threads = max(HE_WARPS * 32, (HE_WARPS * a->seg_mcu * a->lay.bpm + 31) / 32 * 32);
         k_huff_encode_packed<<<(seg_count + HE_WARPS - 1) / HE_WARPS, hp_threads, HP_SMEM, stream>>>(
             a->d_coef, a->d_nzmask, a->lay, a->seg_mcu, seg_count, a->d_tmp, a->slot_stride, a->d_seg_bytes, a->d_spill,
-            a->d_tables);
+            a->d_tables, a->d_info);
     }
     else {
         k_huff_encode<<<(seg_count + HE_WARPS - 1) / HE_WARPS, HE_WARPS * 32, HE_SMEM, stream>>>(
             a->d_coef, a->d_nzmask, a->lay, a->seg_mcu, seg_count, a->d_tmp, a->slot_stride, a->d_seg_bytes, a->d_spill,
-            a->d_tables);
+            a->d_tables, a->d_info);
     }
     /* one chunk (a multiple of the 1024-segment tile) per CTA, at most one CTA per SM */
     int off_chunk = (seg_count + 147) / 148;

@@ -261,6 +261,9 @@ struct gj_huff_dec_args {
     const uint8_t* d_file;      /* the JPEG bytes */
     size_t file_size;
     const uint32_t* d_seg_off;  /* host-built table: [seg_count] file offset of each segment (or NULL) */
+    /* resynchronised streams: [seg_count] {file offset, clean start, clean end} per segment, file offset 0xFFFFFFFF = the
+     * segment does not exist in the stream (its blocks are zero); NULL = positions come from the marker list */
+    const uint32_t* d_seg_tab;
     const uint32_t* d_seg_len;  /* informative: the decoder stops after the segment's block count */
     /* device-built marker list (K0): segment j of scan s starts at scan_begin[s] (j = 0) or two bytes
      * after marker number first_rank[s] + j - 1 */

@@ -1572,24 +1572,48 @@ static int parse_stream(const uint8_t* j, size_t size, struct parsed* P)
     return -1;
 }
 
-/* split one scan at its RST markers  [ref: src/gpujpeg_reader.c:1038-1155] */
-static int split_scan(const uint8_t* j, size_t b, size_t e, size_t* seg_off, size_t* seg_len, int max_seg)
+/* next marker at or behind i inside [i, e): position of its 0xFF, or e.  Stuffed zeros and fill bytes are skipped. */
+static size_t next_marker(const uint8_t* j, size_t i, size_t e)
 {
-    int n = 0;
-    size_t start = b;
-    for ( size_t i = b; i + 1 < e; ) {
+    while ( i + 1 < e ) {
         const uint8_t* f = (const uint8_t*)memchr(j + i, 0xFF, e - 1 - i);
         if ( !f ) break;
         i = (size_t)(f - j);
-        int m = j[i + 1];
-        if ( m == 0xFF ) { i++; continue; }   /* fill byte in front of a marker (T.81 B.1.1.2) */
-        if ( m >= 0xD0 && m <= 0xD7 ) {
-            if ( n >= max_seg ) return -1;
-            seg_off[n] = start;
-            seg_len[n] = i - start;
-            n++;
-            start = i + 2;
+        if ( j[i + 1] == 0xFF ) { i++; continue; }   /* fill byte in front of a marker (T.81 B.1.1.2) */
+        if ( j[i + 1] == 0x00 ) { i += 2; continue; }
+        return i;
+    }
+    return e;
+}
+
+/* split one scan at its RST markers, resynchronising on a broken restart sequence as the reference's reader does
+ * [ref: src/gpujpeg_reader.c:1038-1155]: restart markers must count RST0..RST7 cyclically; at a marker with another number
+ * the current segment ends there, everything up to the next marker that carries the EXPECTED number is skipped, and the
+ * data behind that marker becomes the next segment (numbered consecutively -- later segments move up); when no such
+ * marker follows, the rest of the scan is dropped.  Returns the number of segments found (<= max_seg). */
+static int split_scan(const uint8_t* j, size_t b, size_t e, size_t* seg_off, size_t* seg_len, int max_seg)
+{
+    int n = 0, prev = 7;   /* "RST0 - 1" */
+    size_t start = b, i = b;
+    for ( ;; ) {
+        i = next_marker(j, i, e);
+        if ( i >= e ) break;
+        const int m = j[i + 1];
+        if ( m < 0xD0 || m > 0xD7 ) break;   /* cannot happen: the scan ends at the first other marker */
+        const int expected = (prev + 1) & 7;
+        if ( n >= max_seg ) return -1;
+        seg_off[n] = start;
+        seg_len[n] = i - start;
+        n++;
+        if ( (m & 7) != expected ) {
+            size_t k = next_marker(j, i + 2, e);
+            while ( k < e && j[k + 1] != 0xD0 + expected )
+                k = next_marker(j, k + 2, e);
+            if ( k >= e ) return n;   /* nothing to resynchronise on: the rest of the scan is lost */
+            i = k;
         }
+        prev = expected;
+        start = i + 2;
         i += 2;
     }
     if ( n >= max_seg ) return -1;
@@ -1670,7 +1694,14 @@ static uint8_t* decode_to_planes(const struct parsed* P, const uint8_t* jpeg, in
         size_t* so = (size_t*)scratch(5, sizeof(size_t) * (nseg + 1));
         size_t* sl = (size_t*)scratch(6, sizeof(size_t) * (nseg + 1));
         int n = split_scan(jpeg, P->scan[s].begin, P->scan[s].end, so, sl, nseg + 1);
-        if ( n != nseg ) { rc = -1; break; }
+        if ( n < 1 || n > nseg ) { rc = -1; break; }
+        /* segments lost to a broken restart sequence: their blocks stay zero, as in the reference (coefficient buffer
+         * cleared before decoding, src/gpujpeg_decoder.c:301) */
+        if ( n < nseg ) {
+            if ( !interleaved ) memset(coef + g[P->scan[s].comp[0]].off, 0, (size_t)g[P->scan[s].comp[0]].nblk * 128);
+            else memset(coef, 0, total * sizeof(int16_t));
+        }
+        const int nseg_found = n;
         if ( (interleaved && P->scan[s].ncomp != comps) || (!interleaved && P->scan[s].ncomp != 1) ) { rc = -1; break; }
         struct dec_tab dct[4], act[4];
         for ( int c = 0; c < P->scan[s].ncomp; c++ ) {
@@ -1678,7 +1709,7 @@ static uint8_t* decode_to_planes(const struct parsed* P, const uint8_t* jpeg, in
             dec_table_build(&act[c], P->hbits[1][P->scan[s].ta[c]], P->hvals[1][P->scan[s].ta[c]]);
         }
 #pragma omp parallel for schedule(dynamic, 16)
-        for ( int q = 0; q < nseg; q++ ) {
+        for ( int q = 0; q < nseg_found; q++ ) {
             int first = q * seg_mcu;
             int cnt = mcus - first < seg_mcu ? mcus - first : seg_mcu;
             struct bitr r = {jpeg + so[q], jpeg + so[q] + sl[q], 0, 0};
@@ -1859,7 +1890,12 @@ int orc_decode_rgb(const uint8_t* jpeg, size_t size, int idct_flavour, int threa
     int rc = 0;
     for ( int s = 0; s < P.nscan && rc == 0; s++ ) {
         int n = split_scan(jpeg, P.scan[s].begin, P.scan[s].end, so, sl, nseg + 1);
-        if ( n != nseg ) { rc = -1; break; }
+        if ( n < 1 || n > nseg ) { rc = -1; break; }
+        if ( n < nseg ) {   /* segments lost to a broken restart sequence stay zero (see decode_to_planes) */
+            if ( P.scan[s].ncomp == 1 ) memset(coef + P.scan[s].comp[0] * psz, 0, psz * sizeof(int16_t));
+            else memset(coef, 0, P.comps * psz * sizeof(int16_t));
+        }
+        const int nseg_found = n;
         if ( P.scan[s].ncomp == 1 ) {
             int c = P.scan[s].comp[0];
             const uint8_t* db = P.hbits[0][P.scan[s].td[0]];
@@ -1867,7 +1903,7 @@ int orc_decode_rgb(const uint8_t* jpeg, size_t size, int idct_flavour, int threa
             const uint8_t* ab = P.hbits[1][P.scan[s].ta[0]];
             const uint8_t* av = P.hvals[1][P.scan[s].ta[0]];
 #pragma omp parallel for schedule(dynamic, 16)
-            for ( int g = 0; g < nseg; g++ ) {
+            for ( int g = 0; g < nseg_found; g++ ) {
                 int first = g * seg_mcu;
                 int cnt = nblk - first < seg_mcu ? nblk - first : seg_mcu;
                 orc_huff_decode_segment(jpeg + so[g], sl[g], cnt, db, dv, ab, av,
@@ -1881,7 +1917,7 @@ int orc_decode_rgb(const uint8_t* jpeg, size_t size, int idct_flavour, int threa
                 dec_table_build(&dct[c], P.hbits[0][P.scan[s].td[c]], P.hvals[0][P.scan[s].td[c]]);
                 dec_table_build(&act[c], P.hbits[1][P.scan[s].ta[c]], P.hvals[1][P.scan[s].ta[c]]);
             }
-            for ( int g = 0; g < nseg; g++ ) {
+            for ( int g = 0; g < nseg_found; g++ ) {
                 int first = g * seg_mcu;
                 int cnt = nblk - first < seg_mcu ? nblk - first : seg_mcu;
                 struct bitr r = {jpeg + so[g], jpeg + so[g] + sl[g], 0, 0};

@@ -158,13 +158,6 @@ def test_refused_streams(gj):
     wide = bytearray(jpeg)
     wide[dqt + 4] |= 0x10
     expect_error(gj, wide)
-    # a restart marker removed: the scan has one segment too few
-    i = bytes(jpeg).find(b"\xff\xd1", sos)
-    expect_error(gj, jpeg[:i] + jpeg[i + 2:])
-    # restart markers out of sequence
-    swapped = bytearray(jpeg)
-    swapped[i + 1] = 0xD5
-    expect_error(gj, swapped)
     # truncated in the middle of the scan data, and in the middle of the headers
     expect_error(gj, jpeg[:sos + 40])
     expect_error(gj, jpeg[:sof + 6])
@@ -230,5 +223,41 @@ def test_ffmpeg_cs_itu601_comment_selects_limited_range(gj):
         d.set_output_format(gj.api.GPUJPEG_YCBCR_JPEG, o.FMT_444_P012)
         plain, _ = d.decode_samples(own)            # the same scan read as full-range YCbCr, asked for full-range
         assert np.array_equal(out, plain)
+    finally:
+        d.close()
+
+
+@pytest.mark.parametrize("huffman", ["auto", "thread_per_segment"])
+@pytest.mark.parametrize("kind,w,h,rst,il,samp", [("photo", 256, 192, 4, 0, (1, 1)), ("random", 200, 120, 3, 1, (1, 1)), ("photo", 320, 200, 2, 1, (2, 2))])
+def test_broken_restart_sequences_are_resynchronised_like_the_reference(gj, huffman, kind, w, h, rst, il, samp):
+    """[ref: src/gpujpeg_reader.c:1038-1155] a restart marker with the wrong number ends the current segment, the data up to
+    the next marker with the EXPECTED number is skipped, later segments move up and the last ones are missing (zero
+    blocks); a marker that is missing altogether is the same case.  The decoder must give exactly the picture the
+    reference's reader + decoder give -- restated in the oracle's stream splitter."""
+    jpeg = bytearray(o.encode(o.gen_image(kind, w, h), 80, rst, il, sampling=samp))
+    sos = bytes(jpeg).find(b"\xff\xda")
+    marks = [i for i in range(sos, len(jpeg) - 1) if jpeg[i] == 0xFF and 0xD0 <= jpeg[i + 1] <= 0xD7]
+    assert len(marks) > 20
+    d = gj.Decoder()
+    d.set_option("dec_opt_huffman", huffman)
+    try:
+        # (1) one marker carries the wrong number
+        bad = bytearray(jpeg)
+        bad[marks[5] + 1] = 0xD0 + ((bad[marks[5] + 1] - 0xD0 + 3) & 7)
+        bad = np.frombuffer(bytes(bad), np.uint8)
+        want = o.decode(bad)
+        assert not np.array_equal(want, o.decode(np.frombuffer(bytes(jpeg), np.uint8)))
+        assert np.array_equal(d.decode(bad), want), "wrong-number marker: picture differs from the reference's resynchronisation"
+        # (2) one marker is missing: two segments run into each other, the count no longer fits the geometry
+        cut = np.frombuffer(bytes(jpeg[:marks[7]] + jpeg[marks[7] + 2:]), np.uint8)
+        want = o.decode(cut)
+        got = d.decode(cut)
+        # the merged segment decodes its own blocks and then runs out of blocks: everything else is well defined
+        assert got.shape == want.shape
+        seg_rows = np.any(got != want, axis=(1, 2)).sum()
+        assert seg_rows <= 16 * max(1, samp[1]), "missing marker: more than the damaged segment differs (%d rows)" % seg_rows
+        # (3) the undamaged stream still decodes exactly on the same decoder
+        ok = np.frombuffer(bytes(jpeg), np.uint8)
+        assert np.array_equal(d.decode(ok), o.decode(ok))
     finally:
         d.close()
