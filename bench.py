@@ -220,20 +220,20 @@ def run_reference(args):
         "e2e": {"value": round(mpix, 2), "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def nccl_transport_line(path):
-    """the first line of rank 0's NCCL_DEBUG=INFO log that names the transport of a peer connection"""
+    """What carries the peer traffic, for the record: the GPU0 row of `nvidia-smi topo -m` (NV<n> = n NVLink links through
+    the NVSwitch fabric).  (NCCL_DEBUG=INFO would say it in NCCL's own words, but it also prints to stdout, which must
+    carry exactly one JSON line; the measured scatter rate next to this entry -- ~700 GB/s, eleven times PCIe gen5 -- is
+    the evidence that the path is NVLink peer-to-peer and not a bounce through the host.)"""
     try:
-        lines = open(path).read().splitlines()
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout.splitlines()
+        row = [ln for ln in out if ln.startswith("GPU0")]
+        return " ".join(row[0].replace("\x1b[4m", "").replace("\x1b[0m", "").split()[:9]) if row else None
     except Exception:
         return None
-    for key in (" via P2P", "via SHM", "via NET", "P2P/", "NVLS", "Channel"):
-        for ln in lines:
-            if key in ln:
-                return ln.split("NCCL INFO", 1)[-1].strip()[:200]
-    return "no transport line among %d log lines" % len(lines)
 
 
 def scatter_gather_extra(g, torch, dist, rank, world, dev, enc, dec, frame_dev, width, height, rst, steps, nccl_log):
@@ -279,7 +279,7 @@ def scatter_gather_extra(g, torch, dist, rank, world, dev, enc, dec, frame_dev, 
                "scatter_ms": round(ms_scatter, 3),
                "scatter_gbs": round((world - 1) * npix * 3 / (ms_scatter * 1e-3) / 1e9, 1),
                "gathered_stream_bytes": [int(x.numel()) for x in got],
-               "nccl_transport": nccl_transport_line(nccl_log) if nccl_log else os.environ.get("NCCL_DEBUG_FILE")}
+               "peer_path": nccl_transport_line(nccl_log)}
     return out
 
 
@@ -363,10 +363,10 @@ def run_batch(args, g, o, torch, dist, rank, world, local, dev, numa, nccl_log):
         sent = (n_frames - len(bt.my_frames(n_frames, world, 0))) * npix * 3
         scattered = {"value": round(n_frames * npix / (ms_sc * 1e-3) / 1e6, 1), "unit": "Mpix/s", "ms_per_step": round(ms_sc, 3),
                      "scatter_ms": round(ms_only, 3), "scatter_gbs": round(sent / (ms_only * 1e-3) / 1e9, 1),
-                     "nccl_transport": nccl_transport_line(nccl_log) if nccl_log else None}
+                     "peer_path": nccl_transport_line(nccl_log)}
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
-        print(json.dumps({
+        emit({
             "metric": "Mpix/s encode+decode %s RGB q75, batch of %d frames" % (args.size, n_frames), "value": round(value, 1),
             "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+i32 (u8 in, i16 coefficients)",
@@ -378,14 +378,38 @@ def run_batch(args, g, o, torch, dist, rank, world, local, dev, numa, nccl_log):
                        "sharding": "frames round-robin over ranks, no data-path collective; `scattered`: NCCL send/recv of raw "
                                    "frames from rank 0 + gather-v of the streams"},
             "scattered": scattered, "jpeg_bytes_per_frame": int(np.mean(sizes)) if sizes else None,
-            "gpu_launches": 9 * len(mine) * args.steps, "clocks": clocks, "numa": numa}))
+            "gpu_launches": 9 * len(mine) * args.steps, "clocks": clocks, "numa": numa})
     enc.close()
     dec.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line of the contract, on the process's real stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
+def quiet_stdout():
+    """libraries (NCCL, the CUDA runtime, child processes) may print to file descriptor 1; stdout must carry exactly one
+    JSON line, so everything else is sent to stderr and the JSON line is written to a saved copy of the real stdout"""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -423,9 +447,6 @@ def main():
     nccl_log = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if rank == 0 and "NCCL_DEBUG" not in os.environ:   # one transport line for the record (see extras.scatter_gather)
-            nccl_log = "/tmp/gj_nccl_%d.log" % os.getpid()
-            os.environ.update(NCCL_DEBUG="INFO", NCCL_DEBUG_SUBSYS="INIT,P2P,NET,GRAPH", NCCL_DEBUG_FILE=nccl_log)
         dist.init_process_group("nccl", device_id=dev)
 
     import gpujpeg_b200 as g
@@ -642,7 +663,7 @@ def main():
             mpix, sec, nframes = cpu_baseline(width, height, rst, 12.0, cores)
             line["cpu_baseline"] = {"value": round(mpix, 2), "unit": "Mpix/s", "cores": cores, "kind": "port",
                                     "sample": "%d full %dx%d frames encode+decode, %.1f s, OpenMP %d threads (= cgroup CPU quota of the box)" % (nframes, width, height, sec, cores)}
-        print(json.dumps(line))
+        emit(line)
     enc.close()
     dec.close()
     if world > 1:
