@@ -62,6 +62,7 @@ struct gpujpeg_decoder {
     uint32_t* d_seg_tab; size_t d_seg_tab_size;     /* resynchronised streams only: per segment {raw start, clean start, clean end} */
     unsigned long long* d_cta; size_t d_cta_size;   /* K0 scratch */
     uint32_t* d_mk;                                 /* K0 results (layout in gpujpeg_decoder_decode) */
+    uint32_t* d_k3_ctr;                             /* K3 work counters (8 words, zero between launches) */
     uint32_t* h_mk;                                 /* pinned mirror */
     int16_t* d_coef; size_t d_coef_size;
     uint8_t* d_raw; size_t d_raw_size;
@@ -129,7 +130,8 @@ struct gpujpeg_decoder* gpujpeg_decoder_create_with_params(const struct gpujpeg_
     d->req_pixel_format = GPUJPEG_PIXFMT_AUTODETECT;
     d->req_color_space = GPUJPEG_CS_DEFAULT;
     if ( d->device < 0 || gj_cuda_malloc((void**)&d->d_tab, sizeof *d->d_tab) ||
-         gj_cuda_malloc((void**)&d->d_mk, GJ_MK_WORDS * 4) ||
+         gj_cuda_malloc((void**)&d->d_mk, GJ_MK_WORDS * 4) || gj_cuda_malloc((void**)&d->d_k3_ctr, 32) ||
+         gj_cuda_memset_async(d->d_k3_ctr, 0, 32, d->stream) || gj_cuda_stream_sync(d->stream) ||
          gj_cuda_malloc_host((void**)&d->h_mk, GJ_MK_WORDS * 4) ) {
         GJ_ERR("Decoder allocation failed: %s\n", gj_cuda_last_error());
         free(d);
@@ -159,6 +161,7 @@ int gpujpeg_decoder_destroy(struct gpujpeg_decoder* d)
     gj_cuda_free(d->d_seg_tab);
     gj_cuda_free(d->d_cta);
     gj_cuda_free(d->d_mk);
+    gj_cuda_free(d->d_k3_ctr);
     gj_cuda_free_host(d->h_mk);
     gj_cuda_free(d->d_coef);
     gj_cuda_free(d->d_planes);
@@ -673,6 +676,7 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     ha.d_list_pos = d->d_list_pos;
     ha.d_list_code = d->d_list_code;
     ha.d_error = d->d_mk + 3;
+    ha.d_unit_ctr = d->d_k3_ctr;
     ha.d_clean = (const uint32_t*)d->d_clean;
     ha.d_list_cpos = d->d_list_cpos;
     ha.force_thread_per_segment = d->thread_per_segment;

@@ -35,7 +35,9 @@
  * every segment start (src/gpujpeg_huffman_cpu_decoder.c:407-411), a segment never writes more than its own blocks.
  */
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -45,15 +47,16 @@
 namespace {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
-constexpr int SD_WARPS = 8;
+constexpr int SD_WARPS = 16;
 constexpr int SD_THREADS = SD_WARPS * 32;
 constexpr int SD_MAXBLK = 40;          // blocks per restart segment this kernel takes (every RESTART_AUTO setting)
 constexpr int SD_MAXLEN = 32760;       // clean bytes of a segment that are looked at (a valid 40-block segment has < 18 KB)
 constexpr int SD_MINSUB = 8;           // shortest sub-sequence, bytes
+constexpr int SD_HEAD = 16;            // M_SPLIT: coefficients of a block (zig-zag order) that are staged in shared memory
 
 struct SdTable {   // one Huffman table in shared memory
-    uint16_t fast[1 << GJ_DEC_FAST_BITS];
-    uint16_t sub[GJ_DEC_FAST_SUBS][1 << (16 - GJ_DEC_FAST_BITS)];
+    uint32_t fast[1 << GJ_DEC_FAST_BITS];
+    uint32_t sub[GJ_DEC_FAST_SUBS][1 << (16 - GJ_DEC_FAST_BITS)];
     uint32_t maxcode[18];
     int32_t valoff[18];
     uint8_t vals[256];
@@ -68,14 +71,16 @@ struct SdParams {
     const uint32_t* seg_tab;             // resynchronised streams: {file offset, clean start, clean end} per segment, or NULL
     uint32_t first_rank[GJ_MAX_COMP], scan_cbegin[GJ_MAX_COMP];
     int cta_begin[GJ_MAX_COMP + 1];      // first CTA of every scan
-    int units_per_warp;
+    int dynamic;                         // more units than resident warps: warps fetch further units from unit_ctr
+    uint32_t* unit_ctr;                  // [scan] next unit to hand out, [4] CTAs that are done; all zero between launches
     uint8_t lanes_log2[GJ_MAX_COMP];     // lanes per segment in scan s
     uint8_t staged[GJ_MAX_COMP];         // scan s stages its blocks in shared memory
     int8_t scan_td[GJ_MAX_COMP][GJ_MAX_COMP], scan_ta[GJ_MAX_COMP][GJ_MAX_COMP], scan_tq[GJ_MAX_COMP][GJ_MAX_COMP];
     int seg_mcu;
     int ncomp_tab;                       // components whose tables a CTA holds (1, or all of an interleaved scan)
-    int tgt_entries, dc_entries, stage_blocks;   // per warp: entries of s_tgt and s_dc, blocks of staging
+    int tgt_entries, stage_bytes;                // per warp: entries of s_tgt, bytes of block staging (multiple of 16)
     int cmp_words;                               // per warp: words of staged clean stream (multiple of 4)
+    int warm_x8;                                 // warm-up of a sub-sequence's first walk, in eighths of an average block
     uint32_t* error;
     int16_t* coef;
     const gj_dev_dec_tables* tables;
@@ -98,31 +103,77 @@ __device__ __forceinline__ uint32_t block_target(const gj_scan_layout& L, int sc
     return (uint32_t)(L.blk_off[comp] + (my * L.comp_vs[comp] + L.idx_dy[i]) * L.bcx[comp] + mx * L.comp_hs[comp] + L.idx_dx[i]);
 }
 
-/* codes longer than GJ_DEC_FAST_BITS: canonical search, result in the format of a gj_dec_fast entry.  A real call on
- * purpose: inlined, the compiler if-converts the search into the walk and every symbol pays for it (ncu r2_e: 22 % of
- * the kernel's instructions); rare in valid streams, so the call is taken by few lanes of few warps. */
-__device__ __noinline__ uint32_t slow_entry(const SdTable& T, uint32_t win, bool ac)
+/* entry fields (gj_internal.h: struct gj_dec_fast) */
+constexpr uint32_t E_TOTAL = GJ_DEC_FAST_TOTAL_MASK;
+__device__ __forceinline__ uint32_t make_entry(uint32_t kadv, uint32_t total, uint32_t size)
 {
-    const uint32_t peek = win >> 16;
-    int l = GJ_DEC_FAST_BITS + 1;
-#pragma unroll
-    for ( int q = GJ_DEC_FAST_BITS + 1; q < 16; q++ )
-        l += peek >= T.maxcode[q] ? 1 : 0;   // maxcode is non-decreasing: l = shortest length whose bound lies above peek
-    if ( peek >= T.maxcode[l] ) return 16u | (ac ? 64u : 1u) << 5;   // garbage: 16 bits, symbol 0
-    const uint32_t sym = T.vals[((int)(peek >> (16 - l)) + T.valoff[l]) & 255];
-    const uint32_t size = sym & 15u, run = sym >> 4;
-    const uint32_t kadv = !ac ? 1u : size ? run + 1u : run == 15u ? 16u : 64u;
-    return (uint32_t)(l + size) | kadv << 5 | size << 12;
+    return kadv | total << GJ_DEC_FAST_TOTAL_SHIFT | size << GJ_DEC_FAST_SIZE_SHIFT;
 }
 
-/* one symbol: table entry for the 32 stream bits in `win` */
+/* shared memory by 32-bit address: the walks below keep their table and stream positions as shared-window offsets, so
+ * that no 64-bit generic pointer is formed or re-derived inside a loop (ncu r2_n: the compiler re-materialised the
+ * shared window base from SR_CgaCtaId + SR_SWINHI for every symbol) */
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32_next(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v)); }
+
+/* codes that no table entry covers: canonical search, result in the format of a gj_dec_fast entry.  `T` = shared
+ * address of the SdTable.  A real call on purpose: inlined, the compiler if-converts the search into the walk and every
+ * symbol pays for it (ncu r2_e: 22 % of the kernel's instructions); it is taken by garbage and by tables with more long
+ * prefixes than second-level tables only. */
+__device__ __noinline__ uint32_t search_code(uint32_t T, uint32_t win, uint32_t ac)
+{
+    const uint32_t peek = win >> 16;
+    const uint32_t mc = T + (uint32_t)offsetof(SdTable, maxcode);
+    uint32_t l = GJ_DEC_FAST_BITS + 1;
+#pragma unroll
+    for ( int q = GJ_DEC_FAST_BITS + 1; q < 16; q++ )
+        l += peek >= lds32(mc + 4u * q) ? 1u : 0u;   // maxcode is non-decreasing: l = shortest length whose bound lies above peek
+    if ( peek >= lds32(mc + 4u * l) ) return make_entry(ac ? 64u : 1u, 16u, 0u);   // garbage: 16 bits, symbol 0
+    const int off = (int)lds32(T + (uint32_t)offsetof(SdTable, valoff) + 4u * l);
+    const uint32_t sym = lds8(T + (uint32_t)offsetof(SdTable, vals) + (uint32_t)(((int)(peek >> (16u - l)) + off) & 255));
+    const uint32_t size = sym & 15u, run = sym >> 4;
+    const uint32_t kadv = !ac ? 1u : size ? run + 1u : run == 15u ? 16u : 64u;
+    return make_entry(kadv, l + size, size);
+}
+
+/* codes longer than GJ_DEC_FAST_BITS (about 1 % of the symbols of a photographic frame -- but one lane in a warp is
+ * enough to send the warp here, r2_o: every fifth symbol step): `e` = the first-level entry -> second-level table */
+__device__ __forceinline__ uint32_t long_code(uint32_t T, uint32_t win, uint32_t e, uint32_t ac)
+{
+    if ( e ) e = lds32(T + (uint32_t)offsetof(SdTable, sub) - 256u + (e & 127u) * 256u + ((win >> 14) & 0xFCu));
+    if ( e == 0 ) e = search_code(T, win, ac);
+    return e;
+}
+
+/* one symbol: table entry for the 32 stream bits in `win` (generic-pointer flavour for the walks on global memory) */
 __device__ __forceinline__ uint32_t lookup(const SdTable* T, uint32_t win, bool ac)
 {
     uint32_t e = T->fast[win >> (32 - GJ_DEC_FAST_BITS)];
-    if ( (e & 31u) == 0 ) {   // a code of more than GJ_DEC_FAST_BITS bits
-        if ( e ) e = T->sub[(e >> 5) - 1u][(win >> 16) & ((1u << (16 - GJ_DEC_FAST_BITS)) - 1u)];
-        if ( e == 0 ) e = slow_entry(*T, win, ac);
-    }
+    if ( (e & E_TOTAL) == 0 ) e = long_code(smem_addr(T), win, e, ac);
     return e;
 }
 
@@ -133,6 +184,8 @@ struct Walk {
     uint32_t bit0;           // bit offset of that byte inside the word
     const SdTable* tab;      // [component in scan][DC, AC]
     const uint16_t* q;       // [component in scan][64] dequantisation, zig-zag order
+    uint32_t stab, sq;       // shared addresses of tab and q
+    uint32_t sbit0;          // shared BIT address of the segment's first bit in the staged stream
     uint32_t cimap;          // block-in-MCU index -> component in scan, 2 bits each
     uint32_t bpm;
 };
@@ -217,8 +270,8 @@ __device__ __forceinline__ uint32_t walk_state(const Walk& W, uint32_t st, uint3
         const uint32_t win = src.peek(q);
         const SdTable* T = k ? t_dc + 1 : t_dc;
         const uint32_t e = lookup(T, win, k != 0);
-        q += e & 31u;
-        k += (e >> 5) & 127u;
+        q += (e >> GJ_DEC_FAST_TOTAL_SHIFT) & 31u;
+        k += e & 127u;
         if ( k >= 64u ) {   // end of block: EOB, or coefficient 63 reached
             k = 0;
             nb++;
@@ -238,21 +291,101 @@ __device__ __forceinline__ uint32_t walk_state(const Walk& W, uint32_t st, uint3
     return make_state(q - W.bit0, k, c);
 }
 
+/* 96 bits of the staged stream in registers: the two words the current symbol can touch and the one behind them, which
+ * was requested a symbol earlier -- no load between the state and the table lookup of a symbol (r2_o: with two loads
+ * per symbol in front of the lookup the walks waited for shared memory 45 % of the time). */
+struct RegWindow {
+    uint32_t hi, lo, nxt;
+    __device__ __forceinline__ void init(uint32_t S)
+    {
+        const uint32_t a = (S >> 10) & 0x3FFFCu;
+        hi = lds32(a);
+        lo = lds32_next(a);
+        nxt = lds32(a + 8u);
+    }
+    __device__ __forceinline__ uint32_t peek(uint32_t S) const { return __funnelshift_l(lo, hi, S >> 7); }
+    /* a symbol is at most 31 bits: the position moves on by at most one word */
+    __device__ __forceinline__ void advance(uint32_t S_old, uint32_t S_new)
+    {
+        if ( (S_old ^ S_new) & 0x1000u ) {
+            hi = lo;
+            lo = nxt;
+            nxt = lds32(((S_new >> 10) & 0x3FFFCu) + 8u);
+        }
+    }
+};
+
+/* The same walk on the staged stream in shared memory, written for the length of the dependent chain: the state is ONE
+ * register S = zig-zag index | (absolute bit address in shared memory) << 7 and a symbol is
+ *     funnel shift (window in registers), one table load, S += entry, end-of-block test
+ * -- the entry's low half is (advance of the zig-zag index | bits to consume << 7), see gj_dec_fast.  `T` follows the
+ * state (DC table after an end of block, AC table otherwise) so that the table select needs no test of its own. */
+template <bool IL>
+__device__ __forceinline__ uint32_t walk_state_sm(const Walk& W, uint32_t st, uint32_t p_cross, uint32_t p_end, int& blocks,
+                                                  uint32_t& cross)
+{
+    uint32_t c = st >> 25;
+    const uint32_t p = st & 0x3FFFFu;
+    blocks = 0;
+    cross = st;
+    if ( p >= p_end ) return st;
+    constexpr uint32_t TS = (uint32_t)sizeof(SdTable);
+    uint32_t S = ((st >> 18) & 127u) | (W.sbit0 + p) << 7;
+    const uint32_t S_end = (W.sbit0 + p_end) << 7, S_cross = (W.sbit0 + p_cross) << 7;
+    uint32_t tdc = W.stab + (IL ? 2u * TS * ((W.cimap >> (2 * c)) & 3u) : 0u);
+    uint32_t T = (S & 127u) ? tdc + TS : tdc;
+    int nb = 0;
+    RegWindow R;
+    R.init(S);
+    auto step = [&]() {
+        const uint32_t win = R.peek(S);
+        uint32_t e = lds16(T + ((win >> 20) & 0xFFCu));
+        if ( __builtin_expect((e & E_TOTAL) == 0, 0) ) e = long_code(T, win, e, S & 127u) & 0xFFFFu;
+        const uint32_t S_old = S;
+        S += e;
+        R.advance(S_old, S);
+        const bool eob = (S & 64u) != 0;   // end of block: EOB, or coefficient 63 reached
+        if ( eob ) {
+            S &= ~127u;
+            nb++;
+            if ( IL ) {
+                c = c + 1u == W.bpm ? 0u : c + 1u;
+                tdc = W.stab + 2u * TS * ((W.cimap >> (2 * c)) & 3u);
+            }
+        }
+        T = eob ? tdc : tdc + TS;
+    };
+    if ( S < S_cross ) {
+        do step(); while ( S < S_cross );
+        nb = 0;
+        cross = make_state((S >> 7) - W.sbit0, S & 127u, c);
+    }
+    while ( S < S_end ) step();
+    blocks = nb;
+    return make_state((S >> 7) - W.sbit0, S & 127u, c);
+}
+
 /* Where the walk that extracts values puts them:
  *   M_STAGED  blocks staged in shared memory, flushed as whole lines afterwards (dense scans, <= 2 segments per warp);
  *             the DC position receives the DC DIFFERENCE, dc_pass turns differences into values
- *   M_DIRECT  blocks zero-filled in the coefficient buffer beforehand, non-zeros stored straight into it; DC
- *             differences go to a small shared array for dc_pass
+ *   M_SPLIT   the first SD_HEAD coefficients of every block (zig-zag order: the low frequencies, where nearly all
+ *             non-zeros of a sparse block are) staged in shared memory and flushed as whole 32-byte sectors; the rest
+ *             of the block zero-filled in the coefficient buffer beforehand, the few non-zeros up there stored straight
+ *             into it.  (Everything stored straight -- r2_o: 141 us, of which 21 us the scattered 2-byte stores of the AC
+ *             values and 11 us those of the DC values: a warp's store to 20-odd different lines occupies the memory
+ *             pipe 20-odd times as long as a shared-memory store, and the walks' table lookups queue behind it.)
  *   M_SOLO    one lane = one whole segment: the lane zero-fills a block when it starts it and keeps the DC
  *             predictors itself -- nothing to do afterwards */
-enum { M_STAGED = 0, M_DIRECT = 1, M_SOLO = 2 };
+enum { M_STAGED = 0, M_SPLIT = 1, M_SOLO = 2 };
+template <int MODE>
+struct StageStride { static constexpr int value = MODE == M_STAGED ? 64 : SD_HEAD; };   // staged coefficients per block
 
-/* `out` = first block of the segment (staging slot, or coefficient buffer when the segment's blocks are consecutive
- * there: !IL); interleaved scans outside the staging area look every block up in tgt[]. */
+/* `stage` = the segment's slot of the staging area, `glob` = the segment's first block in the coefficient buffer when
+ * its blocks are consecutive there (!IL); interleaved scans look every block up in tgt[]. */
 template <bool DEQ, bool IL, int MODE, bool SM>
 __device__ __forceinline__ void walk_write(const Walk& W, uint32_t st, uint32_t p_end, int n, int nblocks,
-                                           const uint32_t* __restrict__ tgt, int16_t* __restrict__ out,
-                                           int16_t* __restrict__ coef, int16_t* __restrict__ dcd)
+                                           const uint32_t* __restrict__ tgt, int16_t* __restrict__ stage,
+                                           int16_t* __restrict__ glob, int16_t* __restrict__ coef)
 {
     uint32_t k = (st >> 18) & 127u, c = st >> 25;
     const uint32_t p = st & 0x3FFFFu;
@@ -265,8 +398,10 @@ __device__ __forceinline__ void walk_write(const Walk& W, uint32_t st, uint32_t 
     const SdTable* t_dc = W.tab + 2u * ci;
     const uint16_t* qt = W.q + 64u * ci;
     int pred0 = 0, pred1 = 0, pred2 = 0, pred3 = 0;   // M_SOLO: DC predictors by component in scan
-    auto block_at = [&](int nn) -> int16_t* { return (MODE == M_STAGED || !IL) ? out + (size_t)nn * 64 : coef + (size_t)tgt[nn] * 64; };
+    constexpr int SS = StageStride<MODE>::value;
+    auto block_at = [&](int nn) -> int16_t* { return MODE == M_STAGED ? stage + (size_t)nn * 64 : !IL ? glob + (size_t)nn * 64 : coef + (size_t)tgt[nn] * 64; };
     int16_t* o = block_at(n);
+    int16_t* so = stage + (size_t)n * SS;   // M_SPLIT: the block's head in the staging area
     const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
     if ( MODE == M_SOLO ) {
 #pragma unroll
@@ -278,7 +413,7 @@ __device__ __forceinline__ void walk_write(const Walk& W, uint32_t st, uint32_t 
         const uint32_t win = src.peek(q);
         const SdTable* T = k ? t_dc + 1 : t_dc;
         const uint32_t e = lookup(T, win, k != 0);
-        const uint32_t total = e & 31u, kadv = (e >> 5) & 127u, size = e >> 12;
+        const uint32_t total = (e >> GJ_DEC_FAST_TOTAL_SHIFT) & 31u, kadv = e & 127u, size = e >> GJ_DEC_FAST_SIZE_SHIFT;
         /* value bits -> value [ref: src/gpujpeg_huffman_cpu_decoder.c:169-204]; size 0 gives 0 */
         const uint32_t bits = ((win << (total - size)) >> 1) >> (31u - size);
         const uint32_t neg = ((bits >> ((size - 1u) & 31u)) & 1u) ^ 1u;          // 1: the leading value bit is 0 -> negative
@@ -292,11 +427,12 @@ __device__ __forceinline__ void walk_write(const Walk& W, uint32_t st, uint32_t 
                 else v = (pred3 += v);
                 o[0] = (int16_t)(DEQ ? v * (int)qt[0] : v);
             }
-            else if ( MODE == M_DIRECT ) dcd[n] = (int16_t)v;
-            else o[0] = (int16_t)v;
+            else so[0] = (int16_t)v;
         }
         else if ( size && idx < 64u ) {
-            o[idx] = (int16_t)(DEQ ? v * (int)qt[idx] : v);
+            const int16_t dv = (int16_t)(DEQ ? v * (int)qt[idx] : v);
+            if ( MODE == M_SPLIT && idx < (uint32_t)SD_HEAD ) so[idx] = dv;
+            else o[idx] = dv;
         }
         q += total;
         k += kadv;
@@ -310,6 +446,7 @@ __device__ __forceinline__ void walk_write(const Walk& W, uint32_t st, uint32_t 
                 qt = W.q + 64u * ci;
             }
             o = block_at(n);
+            so = stage + (size_t)n * SS;
             if ( MODE == M_SOLO ) {
 #pragma unroll
                 for ( int i = 0; i < 8; i++ )
@@ -329,9 +466,94 @@ __device__ __forceinline__ void walk_write(const Walk& W, uint32_t st, uint32_t 
     }
 }
 
+/* The writing walk on the staged stream (see walk_state_sm); M_STAGED and M_SPLIT only. */
+template <bool DEQ, bool IL, int MODE>
+__device__ __forceinline__ void walk_write_sm(const Walk& W, uint32_t st, uint32_t p_end, int n, int nblocks,
+                                              const uint32_t* __restrict__ tgt, int16_t* __restrict__ stage,
+                                              int16_t* __restrict__ glob, int16_t* __restrict__ coef)
+{
+    uint32_t c = st >> 25;
+    const uint32_t p = st & 0x3FFFFu;
+    if ( n >= nblocks || p >= p_end ) return;
+    constexpr uint32_t TS = (uint32_t)sizeof(SdTable);
+    uint32_t S = ((st >> 18) & 127u) | (W.sbit0 + p) << 7;
+    const uint32_t S_end = (W.sbit0 + p_end) << 7;
+    uint32_t ci = IL ? (W.cimap >> (2 * c)) & 3u : 0u;
+    uint32_t tdc = W.stab + 2u * TS * ci;
+    uint32_t T = (S & 127u) ? tdc + TS : tdc;
+    uint32_t qt = W.sq + 128u * ci;
+    /* staging: the segment's slot, blocks in coding order, SS coefficients each; coefficient buffer (M_SPLIT, zig-zag
+     * index >= SD_HEAD): the segment's first block (!IL), or block tgt[n] of the whole buffer (IL) */
+    constexpr uint32_t SS = (uint32_t)StageStride<MODE>::value;
+    const uint32_t s_out = smem_addr(stage);
+    int16_t* const g_out = IL ? coef : glob;
+    auto block_at = [&](int nn) -> uint32_t { return IL ? tgt[nn] * 64u : (uint32_t)nn * 64u; };
+    uint32_t sb = s_out + 2u * SS * (uint32_t)n;          // shared address of the current block's staged coefficients
+    uint32_t gb = MODE == M_SPLIT ? block_at(n) : 0u;     // its first coefficient in g_out
+    RegWindow R;
+    R.init(S);
+    /* an AC coefficient is stored one symbol late: its dequantisation factor is requested when the symbol is decoded and
+     * used when the next symbol's table entry is under way (r2_o: the multiply waited for that load as long as the
+     * lookup for its own) */
+    bool pend = false;
+    uint32_t pend_at = 0, pend_q = 1;   // pend_at: zig-zag index; < SS: in the staged block at pend_sb, else in g_out at pend_gb
+    uint32_t pend_sb = 0, pend_gb = 0;
+    int pend_v = 0;
+    auto flush = [&]() {
+        if ( pend ) {
+            const int dv = DEQ ? pend_v * (int)pend_q : pend_v;
+            if ( MODE == M_STAGED || pend_at < SS ) sts16(pend_sb + 2u * pend_at, (uint32_t)dv);
+            else g_out[pend_gb + pend_at] = (int16_t)dv;
+        }
+    };
+    while ( S < S_end ) {
+        const uint32_t win = R.peek(S);
+        uint32_t e = lds32(T + ((win >> 20) & 0xFFCu));
+        flush();
+        if ( __builtin_expect((e & E_TOTAL) == 0, 0) ) e = long_code(T, win, e, S & 127u);
+        /* value bits -> value [ref: src/gpujpeg_huffman_cpu_decoder.c:169-204]: the `size` bits behind the code; a
+         * leading 0 bit means negative.  size 0 gives 0 */
+        const uint32_t size = e >> GJ_DEC_FAST_SIZE_SHIFT;
+        const uint32_t mask = (1u << size) - 1u;
+        const uint32_t bits = __funnelshift_l(win, 0u, e >> GJ_DEC_FAST_TOTAL_SHIFT) & mask;   // the top `total` bits of win, masked
+        const int v = (int)bits - (int)(2u * bits <= mask ? mask : 0u);
+        const bool dc = (S & 127u) == 0u;
+        const uint32_t S_old = S;
+        S += e & 0xFFFFu;
+        R.advance(S_old, S);
+        const uint32_t kn = S & 127u;   // zig-zag index + 1 of the coefficient this symbol ends on
+        pend = !dc && size && kn <= 64u;
+        if ( dc ) {
+            sts16(sb, (uint32_t)v);
+        }
+        else if ( pend ) {
+            if ( DEQ ) pend_q = lds16(qt + 2u * kn - 2u);
+            pend_v = v;
+            pend_at = kn - 1u;
+            pend_sb = sb;
+            pend_gb = gb;
+        }
+        const bool eob = (S & 64u) != 0;   // end of block: EOB, or coefficient 63 reached
+        if ( eob ) {
+            S &= ~127u;
+            if ( ++n >= nblocks ) break;
+            if ( IL ) {
+                c = c + 1u == W.bpm ? 0u : c + 1u;
+                ci = (W.cimap >> (2 * c)) & 3u;
+                tdc = W.stab + 2u * TS * ci;
+                qt = W.sq + 128u * ci;
+            }
+            sb += 2u * SS;
+            if ( MODE == M_SPLIT ) gb = block_at(n);
+        }
+        T = eob ? tdc : tdc + TS;
+    }
+    flush();
+}
+
 /* All units of this warp.  Per unit: 32 / lanes restart segments, `lanes` lanes each. */
 template <bool DEQ, bool IL, int MODE>
-__device__ __forceinline__ void run_units(const SdParams& P, const int scan, Walk W, uint32_t* const s_tgt, int16_t* const s_dc,
+__device__ __forceinline__ void run_units(const SdParams& P, const int scan, Walk W, uint32_t* const s_tgt,
                                           int16_t* const s_stage, uint32_t* const s_cmp)
 {
     const gj_scan_layout& L = P.lay;
@@ -343,13 +565,21 @@ __device__ __forceinline__ void run_units(const SdParams& P, const int scan, Wal
     const int segblk = P.seg_mcu * L.bpm;
     const int scan_segs = L.scan_seg_begin[scan + 1] - L.scan_seg_begin[scan];
     const int scan_units = (scan_segs + spu - 1) / spu;
-    const int unit0 = ((int)blockIdx.x - P.cta_begin[scan]) * nwarps * P.units_per_warp + warp;
+    /* units are handed out by a counter per scan: the CTAs stay (tables and staging are set up once) and a warp that
+     * got a cheap unit simply takes the next one */
+    uint32_t* const ctr = P.unit_ctr + scan;
+    const int scan_warps = (P.cta_begin[scan + 1] - P.cta_begin[scan]) * nwarps;
+    int unit = ((int)blockIdx.x - P.cta_begin[scan]) * nwarps + warp;   // the first one: no counter needed
     uint32_t* const tgt = s_tgt + slot * segblk;       // IL only
-    int16_t* const dcd = s_dc + slot * segblk;         // M_DIRECT only
+    constexpr int SS = StageStride<MODE>::value;
+    int16_t* const seg_stage = s_stage + (size_t)slot * segblk * SS;   // the segment's staged blocks (not M_SOLO)
 
-    for ( int it = 0; it < P.units_per_warp; it++ ) {
-        const int unit = unit0 + it * nwarps;
+    for ( ;; ) {
         if ( unit >= scan_units ) break;   // warp-uniform
+        /* the next one: requested now, needed when this unit is done.  (Not when every unit has a warp of its own:
+         * thousands of additions to one address take their time even if nobody waits for the result.) */
+        int next_unit = scan_units;
+        if ( P.dynamic && lane == 0 ) next_unit = scan_warps + (int)atomicAdd(ctr, 1u);
         const int s = unit * spu + slot;
         const bool valid = s < scan_segs;
 
@@ -377,6 +607,7 @@ __device__ __forceinline__ void run_units(const SdParams& P, const int scan, Wal
         W.cw = P.clean;
         W.sw = s_cmp;
         W.bit0 = 0;
+        W.sbit0 = smem_addr(s_cmp) * 8u;
         if ( valid ) {
             first_mcu = s * P.seg_mcu;
             nblocks = min(P.seg_mcu, L.scan_mcus[scan] - first_mcu) * L.bpm;
@@ -397,11 +628,10 @@ __device__ __forceinline__ void run_units(const SdParams& P, const int scan, Wal
             W.cw = P.clean + (cs >> 2);
             W.sw = s_cmp + ((cs >> 2) - wbase);
             W.bit0 = (cs & 3u) * 8u;
+            W.sbit0 = (smem_addr(s_cmp) + 4u * ((cs >> 2) - wbase)) * 8u + W.bit0;
         }
         /* first block of the segment in the coefficient buffer (one scan per component: its blocks are consecutive) */
-        int16_t* const seg_out = MODE == M_STAGED ? s_stage + (size_t)slot * segblk * 64
-                                 : IL             ? P.coef
-                                                  : P.coef + ((size_t)L.blk_off[scan] + first_mcu) * 64;
+        int16_t* const seg_glob = IL ? P.coef : P.coef + ((size_t)L.blk_off[scan] + first_mcu) * 64;
         if ( IL ) {
             for ( int j = gl; j < nblocks; j += lanes )
                 tgt[j] = block_target(L, scan, first_mcu, j);
@@ -412,17 +642,30 @@ __device__ __forceinline__ void run_units(const SdParams& P, const int scan, Wal
         auto body = [&](auto sm_tag) {
             constexpr bool SM = decltype(sm_tag)::value;
             if ( MODE == M_SOLO ) {
-                if ( valid ) walk_write<DEQ, IL, M_SOLO, SM>(W, make_state(0, 0, 0), bits_all, 0, nblocks, tgt, seg_out, P.coef, nullptr);
+                if ( valid ) walk_write<DEQ, IL, M_SOLO, SM>(W, make_state(0, 0, 0), bits_all, 0, nblocks, tgt, seg_stage, seg_glob, P.coef);
                 return;
             }
-            if ( MODE == M_DIRECT ) {
+            if ( MODE == M_SPLIT ) {
+                /* zero the part of every block that is not staged: uint4 number 2..7 of its eight.  Four stores per round
+                 * with addresses of their own: a store holds its address registers until the memory pipe has taken it
+                 * (r2_o: 8.5 % of the kernel waited in a one-store loop) */
                 const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-                for ( int i = gl; i < nblocks * 8; i += lanes ) {
-                    if ( !IL ) reinterpret_cast<uint4*>(seg_out)[i] = z;
+                constexpr int H16 = SD_HEAD / 8;   // staged uint4 per block
+                const int n16 = nblocks * 8;
+                auto zero_at = [&](int i) {
+                    if ( (i & 7) < H16 ) return;
+                    if ( !IL ) reinterpret_cast<uint4*>(seg_glob)[i] = z;
                     else reinterpret_cast<uint4*>(P.coef + (size_t)tgt[i >> 3] * 64)[i & 7] = z;
+                };
+                int i = gl;
+                for ( ; i + 3 * lanes < n16; i += 4 * lanes ) {
+                    zero_at(i);
+                    zero_at(i + lanes);
+                    zero_at(i + 2 * lanes);
+                    zero_at(i + 3 * lanes);
                 }
-                for ( int j = gl; j < nblocks; j += lanes )
-                    dcd[j] = 0;
+                for ( ; i < n16; i += lanes )
+                    zero_at(i);
                 __syncwarp();   // the zeros are in place before any lane stores a value into the same block
             }
 
@@ -438,18 +681,22 @@ __device__ __forceinline__ void run_units(const SdParams& P, const int scan, Wal
              * ended in a different state than the lane crossed with walks again from the neighbour's end state.  Lane 0
              * starts exact, so this is a fixed point for ANY input after at most `lanes` rounds -- in practice after
              * round 0. */
-            const uint32_t warm = min(256u, max(32u, 2u * bits_all / (uint32_t)max(nblocks, 1)));
+            const uint32_t warm = min(256u, max(32u, (uint32_t)P.warm_x8 * bits_all / (8u * (uint32_t)max(nblocks, 1))));
             const uint32_t p_warm = gl == 0 ? 0u : p_begin - min(p_begin, warm);
             uint32_t start = make_state(p_begin, 0, 0), end = start;
             int dn = 0;
-            if ( active ) end = walk_state<IL, SM>(W, make_state(p_warm, 0, 0), p_begin, p_end, dn, start);
+            if ( active ) {
+                if constexpr ( SM ) end = walk_state_sm<IL>(W, make_state(p_warm, 0, 0), p_begin, p_end, dn, start);
+                else end = walk_state<IL, false>(W, make_state(p_warm, 0, 0), p_begin, p_end, dn, start);
+            }
             for ( ;; ) {
                 const uint32_t left = __shfl_up_sync(FULL, end, 1, lanes);
                 const bool dirty = active && gl != 0 && left != start;
                 if ( !__any_sync(FULL, dirty) ) break;
                 if ( dirty ) {
                     uint32_t same;
-                    end = walk_state<IL, SM>(W, left, 0u, p_end, dn, same);
+                    if constexpr ( SM ) end = walk_state_sm<IL>(W, left, 0u, p_end, dn, same);
+                    else end = walk_state<IL, false>(W, left, 0u, p_end, dn, same);
                     start = left;
                 }
             }
@@ -462,19 +709,25 @@ __device__ __forceinline__ void run_units(const SdParams& P, const int scan, Wal
             const int n0 = incl - (active ? dn : 0);
 
             /* ---- the walk that writes ---- */
-            if ( active ) walk_write<DEQ, IL, MODE, SM>(W, start, p_end, n0, nblocks, tgt, seg_out, P.coef, dcd);
+            if ( active ) {
+                if constexpr ( SM ) walk_write_sm<DEQ, IL, MODE == M_SOLO ? M_SPLIT : MODE>(W, start, p_end, n0, nblocks, tgt, seg_stage, seg_glob, P.coef);
+                else walk_write<DEQ, IL, MODE, false>(W, start, p_end, n0, nblocks, tgt, seg_stage, seg_glob, P.coef);
+            }
         };
         if ( fits ) body(std::true_type{});
         else body(std::false_type{});
         __syncwarp();
-        if ( MODE == M_SOLO ) continue;   // (the barrier above also protects tgt / the staged bytes for the next unit)
+        if ( MODE == M_SOLO ) {   // (the barrier above also protects tgt / the staged bytes for the next unit)
+            unit = __shfl_sync(FULL, next_unit, 0);
+            continue;
+        }
 
         /* ---- DC: prefix sum of the differences per component [ref: src/gpujpeg_huffman_cpu_decoder.c:259-268];
          *      every lane takes a run of consecutive blocks ---- */
         {
             const int bpl = (nblocks + lanes - 1) >> lanes_log2;
             const int j0 = min(nblocks, gl * bpl), j1 = min(nblocks, j0 + bpl);
-            auto diff_at = [&](int j) -> int { return MODE == M_STAGED ? (int)seg_out[(size_t)j * 64] : (int)dcd[j]; };
+            auto diff_at = [&](int j) -> int { return (int)seg_stage[j * SS]; };
             int sum[GJ_MAX_COMP] = {0, 0, 0, 0};
             uint32_t c = IL ? (uint32_t)j0 % W.bpm : 0u;
             for ( int j = j0; j < j1; j++ ) {
@@ -519,24 +772,34 @@ __device__ __forceinline__ void run_units(const SdParams& P, const int scan, Wal
                 else {
                     pr = (pred[0] += dv);
                 }
-                int16_t* const pos = (MODE == M_STAGED || !IL) ? seg_out + (size_t)j * 64 : P.coef + (size_t)tgt[j] * 64;
-                *pos = (int16_t)(DEQ ? pr * (int)W.q[ci * 64] : pr);
+                seg_stage[j * SS] = (int16_t)(DEQ ? pr * (int)W.q[ci * 64] : pr);
             }
         }
         __syncwarp();
 
-        /* ---- staged blocks -> whole 128-byte lines; the staging area is left zeroed ---- */
-        if ( MODE == M_STAGED ) {
-            uint4* src = reinterpret_cast<uint4*>(seg_out);
-            uint4* dst = reinterpret_cast<uint4*>(P.coef + ((size_t)L.blk_off[scan] + first_mcu) * 64);   // !IL: consecutive blocks
-            for ( int i = gl; i < nblocks * 8; i += lanes ) {
+        /* ---- staged coefficients -> whole 128-byte lines (M_STAGED) / 32-byte sectors (M_SPLIT: the head of every
+         *      block); the staging area is left zeroed ---- */
+        {
+            constexpr int S16 = SS / 8;   // staged uint4 per block
+            uint4* const src = reinterpret_cast<uint4*>(seg_stage);
+            uint4* const dst = reinterpret_cast<uint4*>(seg_glob);   // !IL: consecutive blocks
+            const int n16 = nblocks * S16;
+            auto flush_at = [&](int i) {
                 const uint4 v = src[i];
                 src[i] = make_uint4(0u, 0u, 0u, 0u);
-                if ( !IL ) dst[i] = v;
-                else reinterpret_cast<uint4*>(P.coef + (size_t)tgt[i >> 3] * 64)[i & 7] = v;
+                const int blk = i / S16, part = i % S16;
+                if ( !IL ) dst[blk * 8 + part] = v;
+                else reinterpret_cast<uint4*>(P.coef + (size_t)tgt[blk] * 64)[part] = v;
+            };
+            int i = gl;
+            for ( ; i + lanes < n16; i += 2 * lanes ) {
+                flush_at(i);
+                flush_at(i + lanes);
             }
+            if ( i < n16 ) flush_at(i);
         }
-        __syncwarp();   // tgt / dcd / staging are reused by the next unit
+        __syncwarp();   // tgt / staging are reused by the next unit
+        unit = __shfl_sync(FULL, next_unit, 0);
     }
 }
 
@@ -554,12 +817,11 @@ k_huff_decode_sync(const __grid_constant__ SdParams P)
     SdTable* s_tab = reinterpret_cast<SdTable*>(sm);
     uint16_t* s_q = reinterpret_cast<uint16_t*>(sm + (size_t)P.ncomp_tab * 2 * sizeof(SdTable));
     uint8_t* s_warp = sm + (size_t)P.ncomp_tab * (2 * sizeof(SdTable) + 128);
-    const size_t tgt_bytes = ((size_t)P.tgt_entries * 4 + 15) & ~(size_t)15, dc_bytes = ((size_t)P.dc_entries * 2 + 15) & ~(size_t)15;
-    const size_t warp_bytes = tgt_bytes + dc_bytes + (size_t)P.stage_blocks * 128 + (size_t)P.cmp_words * 4;
+    const size_t tgt_bytes = ((size_t)P.tgt_entries * 4 + 15) & ~(size_t)15;
+    const size_t warp_bytes = tgt_bytes + (size_t)P.stage_bytes + (size_t)P.cmp_words * 4;
     uint32_t* s_tgt = reinterpret_cast<uint32_t*>(s_warp + warp * warp_bytes);
-    int16_t* s_dc = reinterpret_cast<int16_t*>(s_warp + warp * warp_bytes + tgt_bytes);
-    int16_t* s_stage = reinterpret_cast<int16_t*>(s_warp + warp * warp_bytes + tgt_bytes + dc_bytes);
-    uint32_t* s_cmp = reinterpret_cast<uint32_t*>(s_warp + warp * warp_bytes + tgt_bytes + dc_bytes + (size_t)P.stage_blocks * 128);
+    int16_t* s_stage = reinterpret_cast<int16_t*>(s_warp + warp * warp_bytes + tgt_bytes);
+    uint32_t* s_cmp = reinterpret_cast<uint32_t*>(s_warp + warp * warp_bytes + tgt_bytes + (size_t)P.stage_bytes);
 
     /* this scan's tables: Huffman tables by component (DC, AC), dequantisation table by component */
     for ( int t = 0; t < 2 * ncomp; t++ ) {
@@ -581,7 +843,7 @@ k_huff_decode_sync(const __grid_constant__ SdParams P)
         s_q[i] = P.tables->qinv_zz[P.scan_tq[scan][i >> 6]][i & 63];
     {   // staging starts (and is left) all zero
         uint4* z = reinterpret_cast<uint4*>(s_stage);
-        for ( int i = lane; i < P.stage_blocks * 8; i += 32 )
+        for ( int i = lane; i < P.stage_bytes / 16; i += 32 )
             z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
@@ -592,22 +854,36 @@ k_huff_decode_sync(const __grid_constant__ SdParams P)
     W.bit0 = 0;
     W.tab = s_tab;
     W.q = s_q;
+    W.stab = smem_addr(s_tab);
+    W.sq = smem_addr(s_q);
+    W.sbit0 = 0;
     W.bpm = (uint32_t)L.bpm;
     W.cimap = 0;
     if ( L.interleaved )
         for ( int i = 0; i < L.bpm; i++ )
             W.cimap |= (uint32_t)(L.simple ? i : L.idx_comp[i]) << (2 * i);
 
-    const int mode = P.lanes_log2[scan] == 0 ? M_SOLO : P.staged[scan] ? M_STAGED : M_DIRECT;
+    const int mode = P.lanes_log2[scan] == 0 ? M_SOLO : P.staged[scan] ? M_STAGED : M_SPLIT;
     if ( L.interleaved ) {
-        if ( mode == M_SOLO ) run_units<DEQ, true, M_SOLO>(P, scan, W, s_tgt, s_dc, s_stage, s_cmp);
-        else if ( mode == M_STAGED ) run_units<DEQ, true, M_STAGED>(P, scan, W, s_tgt, s_dc, s_stage, s_cmp);
-        else run_units<DEQ, true, M_DIRECT>(P, scan, W, s_tgt, s_dc, s_stage, s_cmp);
+        if ( mode == M_SOLO ) run_units<DEQ, true, M_SOLO>(P, scan, W, s_tgt, s_stage, s_cmp);
+        else if ( mode == M_STAGED ) run_units<DEQ, true, M_STAGED>(P, scan, W, s_tgt, s_stage, s_cmp);
+        else run_units<DEQ, true, M_SPLIT>(P, scan, W, s_tgt, s_stage, s_cmp);
     }
     else {
-        if ( mode == M_SOLO ) run_units<DEQ, false, M_SOLO>(P, scan, W, s_tgt, s_dc, s_stage, s_cmp);
-        else if ( mode == M_STAGED ) run_units<DEQ, false, M_STAGED>(P, scan, W, s_tgt, s_dc, s_stage, s_cmp);
-        else run_units<DEQ, false, M_DIRECT>(P, scan, W, s_tgt, s_dc, s_stage, s_cmp);
+        if ( mode == M_SOLO ) run_units<DEQ, false, M_SOLO>(P, scan, W, s_tgt, s_stage, s_cmp);
+        else if ( mode == M_STAGED ) run_units<DEQ, false, M_STAGED>(P, scan, W, s_tgt, s_stage, s_cmp);
+        else run_units<DEQ, false, M_SPLIT>(P, scan, W, s_tgt, s_stage, s_cmp);
+    }
+    /* the last CTA to get here leaves the counters zeroed for the next launch */
+    if ( !P.dynamic ) return;
+    __syncthreads();
+    if ( threadIdx.x == 0 ) {
+        __threadfence();
+        if ( atomicAdd(P.unit_ctr + 4, 1u) == gridDim.x - 1 ) {
+            for ( int i = 0; i < 5; i++ )
+                P.unit_ctr[i] = 0;
+            __threadfence();
+        }
     }
 }
 
@@ -617,7 +893,7 @@ k_huff_decode_sync(const __grid_constant__ SdParams P)
  * the per-scan lane counts present) */
 extern "C" int gj_huffman_decode_sync_eligible(const struct gj_huff_dec_args* a)
 {
-    if ( !a->d_clean || !a->d_list_cpos || a->seg_mcu * a->lay.bpm > SD_MAXBLK ) return 0;
+    if ( !a->d_clean || !a->d_list_cpos || !a->d_unit_ctr || a->seg_mcu * a->lay.bpm > SD_MAXBLK ) return 0;
     for ( int s = 0; s < a->lay.scan_count; s++ ) {
         const int n = a->scan_lanes[s];
         if ( n < 1 || n > 32 || (n & (n - 1)) ) return 0;
@@ -638,7 +914,8 @@ extern "C" int gj_launch_huffman_decode_sync(const struct gj_huff_dec_args* a, g
     P.coef = a->d_coef;
     P.tables = a->d_tables;
     const int segblk = a->seg_mcu * a->lay.bpm;
-    int total_units = 0, max_spu_tgt = 0, max_spu_dc = 0, max_spu_staged = 0;
+    int total_units = 0, max_spu_tgt = 0;
+    size_t stage_bytes = 0;
     size_t cmp_bytes = 0;
     int units[GJ_MAX_COMP] = {0, 0, 0, 0};
     for ( int s = 0; s < GJ_MAX_COMP; s++ ) {
@@ -664,8 +941,10 @@ extern "C" int gj_launch_huffman_decode_sync(const struct gj_huff_dec_args* a, g
         const size_t want = 2 * ((size_t)a->scan_bytes[s] / (size_t)(segs > 0 ? segs : 1) + 16) * (size_t)spu + 64;
         if ( want > cmp_bytes ) cmp_bytes = want;
         if ( a->lay.interleaved && spu > max_spu_tgt ) max_spu_tgt = spu;
-        if ( P.staged[s] && spu > max_spu_staged ) max_spu_staged = spu;
-        if ( !P.staged[s] && l2 > 0 && spu > max_spu_dc ) max_spu_dc = spu;
+        if ( l2 > 0 ) {   // staged coefficients of a unit's segments: whole blocks, or their first SD_HEAD coefficients
+            const size_t sb = (size_t)spu * segblk * (P.staged[s] ? 128 : SD_HEAD * 2);
+            if ( sb > stage_bytes ) stage_bytes = sb;
+        }
     }
     int sms = 148;
     int dev = 0;
@@ -673,24 +952,32 @@ extern "C" int gj_launch_huffman_decode_sync(const struct gj_huff_dec_args* a, g
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     /* warps per CTA and units per warp: at least ~4 CTAs per SM when there is that much work, at most 8 warps per CTA
      * (the tables are loaded once per CTA) */
-    int nw = 1;
-    while ( nw < SD_WARPS && total_units / (2 * nw) >= sms * 4 ) nw *= 2;
-    int upw = total_units / (sms * 8 * nw);
-    upw = upw < 1 ? 1 : upw > 8 ? 8 : upw;
-    P.units_per_warp = upw;
-    int cta = 0;
-    for ( int s = 0; s <= GJ_MAX_COMP; s++ ) {
-        P.cta_begin[s] = cta;
-        if ( s < GJ_MAX_COMP ) cta += (units[s] + nw * upw - 1) / (nw * upw);
+    P.unit_ctr = a->d_unit_ctr;
+    {
+        const char* e = getenv("GPUJPEG_B200_K3_WARM");   // experiments only
+        const int w = e ? atoi(e) : 0;
+        P.warm_x8 = w >= 1 && w <= 64 ? w : 16;
     }
     P.ncomp_tab = a->lay.interleaved ? a->lay.comp_count : 1;
     P.tgt_entries = max_spu_tgt * segblk;
-    P.dc_entries = max_spu_dc * segblk;
-    P.stage_blocks = max_spu_staged * segblk;
+    P.stage_bytes = (int)stage_bytes;
     if ( cmp_bytes > 40 * 1024 ) cmp_bytes = 40 * 1024;
     P.cmp_words = (int)((cmp_bytes + 15) / 16) * 4;
-    const size_t tgt_bytes = ((size_t)P.tgt_entries * 4 + 15) & ~(size_t)15, dc_bytes = ((size_t)P.dc_entries * 2 + 15) & ~(size_t)15;
-    const size_t smem = (size_t)P.ncomp_tab * (2 * sizeof(SdTable) + 128) + (size_t)nw * (tgt_bytes + dc_bytes + (size_t)P.stage_blocks * 128 + (size_t)P.cmp_words * 4);
+    const size_t tgt_bytes = ((size_t)P.tgt_entries * 4 + 15) & ~(size_t)15;
+    const size_t warp_bytes = tgt_bytes + (size_t)P.stage_bytes + (size_t)P.cmp_words * 4;
+    const size_t cta_bytes = (size_t)P.ncomp_tab * (2 * sizeof(SdTable) + 128);
+    /* warps per CTA: at most 8 (the tables are loaded once per CTA), fewer for small frames (>= ~4 CTAs per SM when
+     * there is that much work) and when the per-warp areas would not fit */
+    int max_nw = 8;
+    {
+        const char* e = getenv("GPUJPEG_B200_K3_WARPS");   // experiments only
+        const int w = e ? atoi(e) : 0;
+        if ( w == 1 || w == 2 || w == 4 || w == 8 || w == 16 ) max_nw = w;
+    }
+    int nw = 1;
+    while ( nw < max_nw && total_units / (2 * nw) >= sms * 4 ) nw *= 2;
+    while ( nw > 1 && cta_bytes + (size_t)nw * warp_bytes > 200 * 1024 ) nw /= 2;
+    const size_t smem = cta_bytes + (size_t)nw * warp_bytes;
     if ( smem > 200 * 1024 ) return -1;
     static int attr_done[64];   // 0 = not yet; set once per device (benign if two threads race: same value)
     if ( dev < 0 || dev >= 64 ) return -1;
@@ -699,6 +986,34 @@ extern "C" int gj_launch_huffman_decode_sync(const struct gj_huff_dec_args* a, g
              cudaFuncSetAttribute(k_huff_decode_sync<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess )
             return -1;
         __atomic_store_n(&attr_done[dev], 1, __ATOMIC_RELEASE);
+    }
+    /* grid: what the device holds at once; every scan gets CTAs in proportion to its work (stream bytes, and a constant
+     * per block for zero-fill, flush and DC pass), never more than it has units for */
+    int occ = 0;
+    if ( (a->dequantize ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_huff_decode_sync<true>, nw * 32, smem)
+                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_huff_decode_sync<false>, nw * 32, smem)) != cudaSuccess || occ < 1 )
+        occ = 1;
+    int resident = occ * sms;
+    if ( getenv("GPUJPEG_B200_K3_STATIC") ) resident = 1 << 30;   // experiments only: one unit per warp
+    int want[GJ_MAX_COMP], total_want = 0;
+    double weight[GJ_MAX_COMP], total_weight = 0;
+    for ( int s = 0; s < GJ_MAX_COMP; s++ ) {
+        want[s] = (units[s] + nw - 1) / nw;
+        total_want += want[s];
+        weight[s] = units[s] ? (double)a->scan_bytes[s] + 3.0 * (double)a->lay.scan_mcus[s] * (a->lay.interleaved ? a->lay.bpm : 1) : 0.0;
+        total_weight += weight[s];
+    }
+    P.dynamic = total_want > resident;
+    int cta = 0;
+    for ( int s = 0; s <= GJ_MAX_COMP; s++ ) {
+        P.cta_begin[s] = cta;
+        if ( s == GJ_MAX_COMP || want[s] == 0 ) continue;
+        int n = want[s];
+        if ( total_want > resident ) {
+            n = (int)(resident * weight[s] / total_weight + 0.5);
+            n = n < 1 ? 1 : n > want[s] ? want[s] : n;
+        }
+        cta += n;
     }
     if ( cta == 0 ) return 0;
     if ( a->dequantize )

@@ -80,18 +80,23 @@ int gj_dec_lut_build(const struct gj_huff_spec* spec, struct gj_dec_lut* lut);
 
 /* Fast decoder table, one per (class, id), indexed by the next GJ_DEC_FAST_BITS bits of the stream.  One entry tells
  * the decoder everything it needs to step over a symbol AND its value bits:
- *   bits  0-4   code length + value size (bits to consume), never 0 for a code
- *   bits  5-11  advance of the zig-zag index: DC 1; AC run + 1, ZRL 16, EOB (and the invalid run/0 symbols) 64
- *   bits 12-15  value size
- * Codes longer than GJ_DEC_FAST_BITS: the entry of their 10-bit prefix has bits 0-4 == 0 and names a second-level
- * table (bits 5-15 = its number + 1) indexed by the following 16 - GJ_DEC_FAST_BITS bits, same entry format; the
+ *   bits  0-6   advance of the zig-zag index: DC 1; AC run + 1, ZRL 16, EOB (and the invalid run/0 symbols) 64
+ *   bits  7-11  code length + value size (bits to consume), never 0 for a code
+ *   bits 16-19  value size
+ * so that a decoder which keeps its state as (zig-zag index | bit position << 7) advances it with ONE addition of the
+ * entry's low half (a 16-bit load of it for a walk that does not need the value).
+ * Codes longer than GJ_DEC_FAST_BITS: the entry of their 10-bit prefix has bits 7-11 == 0 and names a second-level
+ * table (bits 0-6 = its number + 1) indexed by the following 16 - GJ_DEC_FAST_BITS bits, same entry format; the
  * standard tables need 4 of them.  0 = no such code / more prefixes than second-level tables: canonical search in
  * gj_dec_lut. */
 #define GJ_DEC_FAST_BITS 10
 #define GJ_DEC_FAST_SUBS 8
+#define GJ_DEC_FAST_TOTAL_SHIFT 7
+#define GJ_DEC_FAST_TOTAL_MASK (31u << GJ_DEC_FAST_TOTAL_SHIFT)
+#define GJ_DEC_FAST_SIZE_SHIFT 16
 struct gj_dec_fast {
-    uint16_t e[1 << GJ_DEC_FAST_BITS];
-    uint16_t sub[GJ_DEC_FAST_SUBS][1 << (16 - GJ_DEC_FAST_BITS)];
+    uint32_t e[1 << GJ_DEC_FAST_BITS];
+    uint32_t sub[GJ_DEC_FAST_SUBS][1 << (16 - GJ_DEC_FAST_BITS)];
 };
 void gj_dec_fast_build(const struct gj_huff_spec* spec, int is_ac, struct gj_dec_fast* fast);
 
@@ -264,6 +269,7 @@ struct gj_huff_dec_args {
     /* resynchronised streams: [seg_count] {file offset, clean start, clean end} per segment, file offset 0xFFFFFFFF = the
      * segment does not exist in the stream (its blocks are zero); NULL = positions come from the marker list */
     const uint32_t* d_seg_tab;
+    uint32_t* d_unit_ctr;       /* 8 words, all zero between launches: work counters of the self-synchronising kernel */
     const uint32_t* d_seg_len;  /* informative: the decoder stops after the segment's block count */
     /* device-built marker list (K0): segment j of scan s starts at scan_begin[s] (j = 0) or two bytes
      * after marker number first_rank[s] + j - 1 */

@@ -155,11 +155,11 @@ int gj_dec_lut_build(const struct gj_huff_spec* spec, struct gj_dec_lut* lut)
 /* [see gj_internal.h: struct gj_dec_fast]  Symbols follow the decoders of the reference: a DC symbol's low nibble is
  * the size of the difference (src/gpujpeg_huffman_cpu_decoder.c:259-268); an AC symbol is run/size, size 0 means ZRL
  * for run 15 and end-of-block otherwise (:283-303). */
-static uint16_t fast_entry(int sym, int len, int is_ac)
+static uint32_t fast_entry(int sym, int len, int is_ac)
 {
     const int size = sym & 15, run = sym >> 4;
     const int kadv = !is_ac ? 1 : size ? run + 1 : run == 15 ? 16 : 64;
-    return (uint16_t)((len + size) | kadv << 5 | size << 12);
+    return (uint32_t)kadv | (uint32_t)(len + size) << GJ_DEC_FAST_TOTAL_SHIFT | (uint32_t)size << GJ_DEC_FAST_SIZE_SHIFT;
 }
 
 void gj_dec_fast_build(const struct gj_huff_spec* spec, int is_ac, struct gj_dec_fast* fast)
@@ -170,7 +170,7 @@ void gj_dec_fast_build(const struct gj_huff_spec* spec, int is_ac, struct gj_dec
     for ( int l = 1; l <= 16; l++ ) {
         for ( int i = 0; i < spec->bits[l] && p < 256; i++, p++ ) {
             if ( code >= (1u << l) ) return;   /* over-subscribed: gj_dec_lut_build reports it */
-            const uint16_t e = fast_entry(spec->vals[p], l, is_ac);
+            const uint32_t e = fast_entry(spec->vals[p], l, is_ac);
             if ( l <= GJ_DEC_FAST_BITS ) {
                 const uint32_t first = code << (GJ_DEC_FAST_BITS - l), count = 1u << (GJ_DEC_FAST_BITS - l);
                 for ( uint32_t j = 0; j < count; j++ )
@@ -178,10 +178,10 @@ void gj_dec_fast_build(const struct gj_huff_spec* spec, int is_ac, struct gj_dec
             }
             else {
                 const uint32_t prefix = code >> (l - GJ_DEC_FAST_BITS);
-                uint16_t link = fast->e[prefix];
-                if ( link == 0 && subs < GJ_DEC_FAST_SUBS ) link = fast->e[prefix] = (uint16_t)(++subs << 5);
-                if ( link != 0 && (link & 31) == 0 ) {
-                    uint16_t* sub = fast->sub[(link >> 5) - 1];
+                uint32_t link = fast->e[prefix];
+                if ( link == 0 && subs < GJ_DEC_FAST_SUBS ) link = fast->e[prefix] = (uint32_t)++subs;
+                if ( link != 0 && (link & GJ_DEC_FAST_TOTAL_MASK) == 0 ) {
+                    uint32_t* sub = fast->sub[link - 1];
                     const int rest = 16 - l;   /* free bits below the code inside the second-level index */
                     const uint32_t first = (code & ((1u << (l - GJ_DEC_FAST_BITS)) - 1u)) << rest;
                     for ( uint32_t j = 0; j < (1u << rest); j++ )
