@@ -680,23 +680,26 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     ha.d_clean = (const uint32_t*)d->d_clean;
     ha.d_list_cpos = d->d_list_cpos;
     ha.force_thread_per_segment = d->thread_per_segment;
-    /* Which Huffman decoder kernel, and how many lanes share a restart segment (measured on B200, profiles/r2_k3_matrix):
+    /* Which Huffman decoder kernel, and how many lanes share a restart segment (measured on B200, profiles/r2_k3_matrix.md):
      * a frame with few segments cannot occupy the GPU with one thread per segment -- there the self-synchronising walks
-     * buy parallelism INSIDE a segment (HD: 25 us against 82, 4K: 47 against 89); with 40 000 segments and more the
-     * segments alone keep the machine busy and the redundant walks only pay off at photographic densities (8K q75:
-     * 140 us against 172; sparser or denser 8K content is faster with one thread per segment). */
+     * buy parallelism INSIDE a segment (HD: 27 us against 82, 4K: 41 against 90); with 40 000 segments and more the
+     * segments alone keep the machine busy and the redundant walks pay off from photographic densities on (8K q75:
+     * 119 us against 174, q90: 268 against 332), not for very sparse (q50: 97 either way) or random content (562 against
+     * 731). */
     size_t ecs_bytes = 0;
     for ( int k = 0; k < g->scan_count; k++ )
         ecs_bytes += st.scan[k].end - st.scan[k].begin;
     const size_t bytes_per_block_x10 = ecs_bytes * 10 / (g->coef_count / 64);
     const int many_segments = g->seg_count >= 30000;
-    ha.force_thread_per_segment = d->thread_per_segment || (many_segments && (bytes_per_block_x10 < 30 || bytes_per_block_x10 > 100));
+    ha.force_thread_per_segment = d->thread_per_segment || (many_segments && (bytes_per_block_x10 < 20 || bytes_per_block_x10 > 200));
     for ( int k = 0; k < g->scan_count; k++ ) {
         ha.first_rank[k] = first_rank[k];
         ha.scan_cbegin[k] = scan_cbegin[k];
         const int segs = g->lay.scan_seg_begin[k + 1] - g->lay.scan_seg_begin[k];
         const size_t avg = (st.scan[k].end - st.scan[k].begin) / (size_t)segs;
-        ha.scan_lanes[k] = (uint8_t)(g->seg_count <= 8000 ? 16 : !many_segments ? 8 : avg >= 192 ? 16 : 8);
+        ha.scan_lanes[k] = (uint8_t)(g->seg_count <= 8000 ? 16
+                                     : !many_segments     ? (bytes_per_block_x10 > 100 ? 16 : 8)
+                                     : bytes_per_block_x10 > 80 ? 8 : avg >= 192 ? 16 : 8);
         if ( d->force_lanes[k] ) {
             ha.scan_lanes[k] = (uint8_t)d->force_lanes[k];
             ha.force_thread_per_segment = d->thread_per_segment;

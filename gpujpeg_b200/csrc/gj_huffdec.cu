@@ -553,7 +553,7 @@ __device__ __forceinline__ void walk_write_sm(const Walk& W, uint32_t st, uint32
 
 /* All units of this warp.  Per unit: 32 / lanes restart segments, `lanes` lanes each. */
 template <bool DEQ, bool IL, int MODE>
-__device__ __forceinline__ void run_units(const SdParams& P, const int scan, Walk W, uint32_t* const s_tgt,
+__device__ __forceinline__ void run_units(const SdParams& P, const int scan, const bool at_home, Walk W, uint32_t* const s_tgt,
                                           int16_t* const s_stage, uint32_t* const s_cmp)
 {
     const gj_scan_layout& L = P.lay;
@@ -570,6 +570,10 @@ __device__ __forceinline__ void run_units(const SdParams& P, const int scan, Wal
     uint32_t* const ctr = P.unit_ctr + scan;
     const int scan_warps = (P.cta_begin[scan + 1] - P.cta_begin[scan]) * nwarps;
     int unit = ((int)blockIdx.x - P.cta_begin[scan]) * nwarps + warp;   // the first one: no counter needed
+    if ( !at_home ) {   // a guest in this scan: every unit comes from the counter
+        if ( lane == 0 ) unit = scan_warps + (int)atomicAdd(ctr, 1u);
+        unit = __shfl_sync(FULL, unit, 0);
+    }
     uint32_t* const tgt = s_tgt + slot * segblk;       // IL only
     constexpr int SS = StageStride<MODE>::value;
     int16_t* const seg_stage = s_stage + (size_t)slot * segblk * SS;   // the segment's staged blocks (not M_SOLO)
@@ -811,8 +815,9 @@ k_huff_decode_sync(const __grid_constant__ SdParams P)
     const gj_scan_layout& L = P.lay;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cta = blockIdx.x;
-    const int scan = (cta >= P.cta_begin[1]) + (cta >= P.cta_begin[2]) + (cta >= P.cta_begin[3]);
+    const int home = (cta >= P.cta_begin[1]) + (cta >= P.cta_begin[2]) + (cta >= P.cta_begin[3]);
     const int ncomp = L.interleaved ? L.comp_count : 1;
+    __shared__ int s_go;
 
     SdTable* s_tab = reinterpret_cast<SdTable*>(sm);
     uint16_t* s_q = reinterpret_cast<uint16_t*>(sm + (size_t)P.ncomp_tab * 2 * sizeof(SdTable));
@@ -823,6 +828,42 @@ k_huff_decode_sync(const __grid_constant__ SdParams P)
     int16_t* s_stage = reinterpret_cast<int16_t*>(s_warp + warp * warp_bytes + tgt_bytes);
     uint32_t* s_cmp = reinterpret_cast<uint32_t*>(s_warp + warp * warp_bytes + tgt_bytes + (size_t)P.stage_bytes);
 
+    {   // staging starts (and is left) all zero
+        uint4* z = reinterpret_cast<uint4*>(s_stage);
+        for ( int i = lane; i < P.stage_bytes / 16; i += 32 )
+            z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    Walk W;
+    W.cw = P.clean;
+    W.sw = s_cmp;
+    W.bit0 = 0;
+    W.tab = s_tab;
+    W.q = s_q;
+    W.stab = smem_addr(s_tab);
+    W.sq = smem_addr(s_q);
+    W.sbit0 = 0;
+    W.bpm = (uint32_t)L.bpm;
+    W.cimap = 0;
+    if ( L.interleaved )
+        for ( int i = 0; i < L.bpm; i++ )
+            W.cimap |= (uint32_t)(L.simple ? i : L.idx_comp[i]) << (2 * i);
+
+    /* The CTA starts on its home scan; when that scan's units are handed out it moves on to the other scans (their tables
+     * replace the ones in shared memory) as long as one of them still has units to give. */
+    for ( int round = 0; round < L.scan_count; round++ ) {
+    const int scan = home + round < L.scan_count ? home + round : home + round - L.scan_count;
+    if ( round > 0 ) {
+        if ( !P.dynamic ) break;
+        __syncthreads();   // nobody reads the previous scan's tables any more
+        if ( threadIdx.x == 0 ) {
+            const int spu = 32 >> P.lanes_log2[scan];
+            const int units = (L.scan_seg_begin[scan + 1] - L.scan_seg_begin[scan] + spu - 1) / spu;
+            const int handed = (P.cta_begin[scan + 1] - P.cta_begin[scan]) * (int)(blockDim.x >> 5) + (int)*(volatile uint32_t*)(P.unit_ctr + scan);
+            s_go = handed < units;
+        }
+        __syncthreads();
+        if ( !s_go ) continue;
+    }
     /* this scan's tables: Huffman tables by component (DC, AC), dequantisation table by component */
     for ( int t = 0; t < 2 * ncomp; t++ ) {
         const int ci = t >> 1, cls = t & 1;
@@ -841,39 +882,20 @@ k_huff_decode_sync(const __grid_constant__ SdParams P)
     }
     for ( int i = threadIdx.x; i < ncomp * 64; i += blockDim.x )
         s_q[i] = P.tables->qinv_zz[P.scan_tq[scan][i >> 6]][i & 63];
-    {   // staging starts (and is left) all zero
-        uint4* z = reinterpret_cast<uint4*>(s_stage);
-        for ( int i = lane; i < P.stage_bytes / 16; i += 32 )
-            z[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
     __syncthreads();
-
-    Walk W;
-    W.cw = P.clean;
-    W.sw = s_cmp;
-    W.bit0 = 0;
-    W.tab = s_tab;
-    W.q = s_q;
-    W.stab = smem_addr(s_tab);
-    W.sq = smem_addr(s_q);
-    W.sbit0 = 0;
-    W.bpm = (uint32_t)L.bpm;
-    W.cimap = 0;
-    if ( L.interleaved )
-        for ( int i = 0; i < L.bpm; i++ )
-            W.cimap |= (uint32_t)(L.simple ? i : L.idx_comp[i]) << (2 * i);
 
     const int mode = P.lanes_log2[scan] == 0 ? M_SOLO : P.staged[scan] ? M_STAGED : M_SPLIT;
     if ( L.interleaved ) {
-        if ( mode == M_SOLO ) run_units<DEQ, true, M_SOLO>(P, scan, W, s_tgt, s_stage, s_cmp);
-        else if ( mode == M_STAGED ) run_units<DEQ, true, M_STAGED>(P, scan, W, s_tgt, s_stage, s_cmp);
-        else run_units<DEQ, true, M_SPLIT>(P, scan, W, s_tgt, s_stage, s_cmp);
+        if ( mode == M_SOLO ) run_units<DEQ, true, M_SOLO>(P, scan, round == 0, W, s_tgt, s_stage, s_cmp);
+        else if ( mode == M_STAGED ) run_units<DEQ, true, M_STAGED>(P, scan, round == 0, W, s_tgt, s_stage, s_cmp);
+        else run_units<DEQ, true, M_SPLIT>(P, scan, round == 0, W, s_tgt, s_stage, s_cmp);
     }
     else {
-        if ( mode == M_SOLO ) run_units<DEQ, false, M_SOLO>(P, scan, W, s_tgt, s_stage, s_cmp);
-        else if ( mode == M_STAGED ) run_units<DEQ, false, M_STAGED>(P, scan, W, s_tgt, s_stage, s_cmp);
-        else run_units<DEQ, false, M_SPLIT>(P, scan, W, s_tgt, s_stage, s_cmp);
+        if ( mode == M_SOLO ) run_units<DEQ, false, M_SOLO>(P, scan, round == 0, W, s_tgt, s_stage, s_cmp);
+        else if ( mode == M_STAGED ) run_units<DEQ, false, M_STAGED>(P, scan, round == 0, W, s_tgt, s_stage, s_cmp);
+        else run_units<DEQ, false, M_SPLIT>(P, scan, round == 0, W, s_tgt, s_stage, s_cmp);
     }
+    }   // scans
     /* the last CTA to get here leaves the counters zeroed for the next launch */
     if ( !P.dynamic ) return;
     __syncthreads();
@@ -966,19 +988,6 @@ extern "C" int gj_launch_huffman_decode_sync(const struct gj_huff_dec_args* a, g
     const size_t tgt_bytes = ((size_t)P.tgt_entries * 4 + 15) & ~(size_t)15;
     const size_t warp_bytes = tgt_bytes + (size_t)P.stage_bytes + (size_t)P.cmp_words * 4;
     const size_t cta_bytes = (size_t)P.ncomp_tab * (2 * sizeof(SdTable) + 128);
-    /* warps per CTA: at most 8 (the tables are loaded once per CTA), fewer for small frames (>= ~4 CTAs per SM when
-     * there is that much work) and when the per-warp areas would not fit */
-    int max_nw = 8;
-    {
-        const char* e = getenv("GPUJPEG_B200_K3_WARPS");   // experiments only
-        const int w = e ? atoi(e) : 0;
-        if ( w == 1 || w == 2 || w == 4 || w == 8 || w == 16 ) max_nw = w;
-    }
-    int nw = 1;
-    while ( nw < max_nw && total_units / (2 * nw) >= sms * 4 ) nw *= 2;
-    while ( nw > 1 && cta_bytes + (size_t)nw * warp_bytes > 200 * 1024 ) nw /= 2;
-    const size_t smem = cta_bytes + (size_t)nw * warp_bytes;
-    if ( smem > 200 * 1024 ) return -1;
     static int attr_done[64];   // 0 = not yet; set once per device (benign if two threads race: same value)
     if ( dev < 0 || dev >= 64 ) return -1;
     if ( !__atomic_load_n(&attr_done[dev], __ATOMIC_ACQUIRE) ) {
@@ -987,12 +996,41 @@ extern "C" int gj_launch_huffman_decode_sync(const struct gj_huff_dec_args* a, g
             return -1;
         __atomic_store_n(&attr_done[dev], 1, __ATOMIC_RELEASE);
     }
+    /* warps per CTA (the tables are loaded once per CTA): the count that keeps most warps on an SM -- the kernel lives on
+     * hiding the latency of one warp's symbol chain behind other warps, and the per-warp staging areas decide how many fit
+     * (r2_q: 8 warps x 3 CTAs = 24 warps per SM, 10 x 3 = 30 in the same shared memory).  Small frames: at least ~4 CTAs
+     * per SM.  The answer is remembered per thread for the next frame of the same shape. */
+    int cap = total_units / (4 * sms);
+    cap = cap < 1 ? 1 : cap > SD_WARPS ? SD_WARPS : cap;
+    {
+        const char* e = getenv("GPUJPEG_B200_K3_WARPS");   // experiments only
+        const int w = e ? atoi(e) : 0;
+        if ( w >= 1 && w <= SD_WARPS ) cap = -w;
+    }
+    struct Pick { int dev, deq, cap, nw, occ; size_t cta_bytes, warp_bytes; };
+    static thread_local Pick last = {-1, 0, 0, 0, 0, 0, 0};
+    if ( last.dev != dev || last.deq != a->dequantize || last.cap != cap || last.cta_bytes != cta_bytes || last.warp_bytes != warp_bytes ) {
+        Pick best = {dev, a->dequantize, cap, 0, 0, cta_bytes, warp_bytes};
+        for ( int w = cap < 0 ? -cap : 1; w <= (cap < 0 ? -cap : cap); w++ ) {
+            const size_t bytes = cta_bytes + (size_t)w * warp_bytes;
+            if ( bytes > 200 * 1024 ) break;
+            int o = 0;
+            if ( (a->dequantize ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_huff_decode_sync<true>, w * 32, bytes)
+                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_huff_decode_sync<false>, w * 32, bytes)) != cudaSuccess )
+                o = 0;
+            if ( o >= 1 && w * o >= best.nw * best.occ ) {
+                best.nw = w;
+                best.occ = o;
+            }
+        }
+        if ( best.nw == 0 ) return -1;   // not even one warp's areas fit
+        last = best;
+    }
+    const int nw = last.nw;
+    const size_t smem = cta_bytes + (size_t)nw * warp_bytes;
     /* grid: what the device holds at once; every scan gets CTAs in proportion to its work (stream bytes, and a constant
      * per block for zero-fill, flush and DC pass), never more than it has units for */
-    int occ = 0;
-    if ( (a->dequantize ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_huff_decode_sync<true>, nw * 32, smem)
-                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_huff_decode_sync<false>, nw * 32, smem)) != cudaSuccess || occ < 1 )
-        occ = 1;
+    const int occ = last.occ;
     int resident = occ * sms;
     if ( getenv("GPUJPEG_B200_K3_STATIC") ) resident = 1 << 30;   // experiments only: one unit per warp
     int want[GJ_MAX_COMP], total_want = 0;

@@ -35,7 +35,7 @@ for size, kind, q in CASES:
     enc.close()
     d_out = torch.empty((h, w, 3), dtype=torch.uint8, device=dev)
     ref = None
-    row = {"size": size, "kind": kind, "quality": q, "jpeg_bytes": int(jpeg.size), "segments": 3 * ((w // 8) * (h // 8) + rst - 1) // rst,
+    row = {"size": size, "kind": kind, "quality": q, "jpeg_bytes": int(jpeg.size), "segments": 3 * (((w // 8) * (h // 8) + rst - 1) // rst),
            "bytes_per_block": round(jpeg.size / (3 * (w // 8) * (h // 8)), 2), "us": {}}
     for lanes in LANES + ["thread_per_segment"]:
         dec = g.Decoder(stream=stream)
