@@ -7,14 +7,15 @@
  * The reference splits scans into restart segments on the host with a memchr(0xFF) walk over the whole
  * stream and copies every segment into a second buffer (src/gpujpeg_reader.c:1038-1155); its FAQ quotes
  * 543 ms for that step on one sample.  On a B200 host the same walk costs 2.1 ms for an 8K frame --
- * six times the GPU time of the entire decode.  Here the file is uploaded once, untouched, and three
- * small launches do the reader's per-byte work in device memory:
- *
- *     k_marker_count   per-CTA counts of markers and of bytes that stay in the clean stream (16 bytes per thread)
- *     k_marker_scan    exclusive scan of the CTA counts (one CTA)
- *     k_marker_write   ordered compaction: list[rank] = {raw position, code, clean position}; the kept bytes go to
- *                      their clean position; markers other than RSTn are also appended to a short list the host
- *                      reads back (scan ends, ranks: everything the host needs to finish the marker walk)
+ * six times the GPU time of the entire decode.  Here the file is uploaded once, untouched, and ONE launch does the
+ * reader's per-byte work in device memory (k_marker_scan_write): every CTA classifies a 4 KB tile (16 bytes per
+ * thread), counts its markers and the bytes that stay in the clean stream, learns how many of both lie in front of it by
+ * a decoupled look-back over the tiles before it (each tile publishes its own counts at once and its inclusive prefix
+ * as soon as it knows it; a warp inspects 32 predecessors per step), and then does the ordered compaction:
+ * list[rank] = {raw position, code, clean position}; the kept bytes go to their clean position; markers other than
+ * RSTn are also appended to a short list the host reads back (scan ends, ranks: everything the host needs to finish
+ * the marker walk).  (Round 1 and the first half of round 2: count, single-CTA scan and write as three launches,
+ * 7 + 6 + 14 us for a 6 MB stream -- latency of three dependent launches, not work.)
  *
  * Inside entropy-coded data a 0xFF byte is always followed by 0x00 (stuffing), 0xFF (fill) or a marker
  * code, so "FF xx, xx not in {00, FF}" is exact there.  A byte stays in the clean stream unless it is
@@ -88,79 +89,28 @@ __device__ __forceinline__ void classify(const uint8_t* __restrict__ file, size_
     keep = inside & ~drop & 0xFFFFu;
 }
 
-/* per CTA: low word = markers, high word = kept bytes */
-__global__ void __launch_bounds__(MK_THREADS)
-k_marker_count(const uint8_t* __restrict__ file, size_t begin, size_t end, size_t base, unsigned long long* __restrict__ cta_count)
-{
-    __shared__ uint32_t s_warp[MK_THREADS / 32];
-    const size_t pos = base + (size_t)blockIdx.x * MK_TILE + (size_t)threadIdx.x * MK_BYTES;
-    uint32_t w[5], markers = 0, keep = 0;
-    if ( pos < end ) classify(file, begin, end, pos, w, markers, keep);
-    uint32_t n = (uint32_t)__popc(markers) << 16 | (uint32_t)__popc(keep);   // <= 2048 / 4096 per CTA: no carry between the halves
-#pragma unroll
-    for ( int d = 16; d > 0; d >>= 1 )
-        n += __shfl_down_sync(FULL, n, d);
-    if ( (threadIdx.x & 31) == 0 ) s_warp[threadIdx.x >> 5] = n;
-    __syncthreads();
-    if ( threadIdx.x == 0 ) {
-        uint32_t t = 0;
-        for ( int i = 0; i < MK_THREADS / 32; i++ )
-            t += s_warp[i];
-        cta_count[blockIdx.x] = (unsigned long long)(t >> 16) | (unsigned long long)(t & 0xFFFFu) << 32;
-    }
-}
-
-__global__ void __launch_bounds__(1024)
-k_marker_scan(unsigned long long* __restrict__ cta_count, int n_cta, uint32_t* __restrict__ result /*[0]=markers, [5]=clean bytes*/)
-{
-    __shared__ unsigned long long s_warp[32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long carry = 0;
-    for ( int base = 0; base < n_cta; base += 1024 ) {
-        const int i = base + threadIdx.x;
-        const unsigned long long v = i < n_cta ? cta_count[i] : 0ull;
-        unsigned long long incl = v;
-#pragma unroll
-        for ( int d = 1; d < 32; d <<= 1 ) {
-            const unsigned long long t = __shfl_up_sync(FULL, incl, d);
-            if ( lane >= d ) incl += t;
-        }
-        if ( lane == 31 ) s_warp[warp] = incl;
-        __syncthreads();
-        if ( warp == 0 ) {
-            unsigned long long x = s_warp[lane];
-#pragma unroll
-            for ( int d = 1; d < 32; d <<= 1 ) {
-                const unsigned long long t = __shfl_up_sync(FULL, x, d);
-                if ( lane >= d ) x += t;
-            }
-            s_warp[lane] = x;
-        }
-        __syncthreads();
-        if ( i < n_cta ) cta_count[i] = carry + (warp ? s_warp[warp - 1] : 0ull) + incl - v;   // exclusive
-        carry += s_warp[31];
-        __syncthreads();
-    }
-    if ( threadIdx.x == 0 ) {
-        result[0] = (uint32_t)carry;
-        result[5] = (uint32_t)(carry >> 32);
-    }
-}
+/* Tile status for the look-back: flag << 62 | kept bytes << 31 | markers (both < 2^31: the launcher refuses longer
+ * streams); a 64-bit word is written and read in one piece, so the flag and the counts it vouches for cannot be torn. */
+#define ST_AGGREGATE (1ull << 62)
+#define ST_PREFIX (2ull << 62)
+#define ST_VALUE ((1ull << 62) - 1ull)
 
 __global__ void __launch_bounds__(MK_THREADS)
-k_marker_write(const uint8_t* __restrict__ file, size_t begin, size_t end, size_t base, const unsigned long long* __restrict__ cta_base,
-               uint32_t* __restrict__ list_pos, uint8_t* __restrict__ list_code, uint32_t* __restrict__ list_cpos, uint32_t list_cap,
-               uint8_t* __restrict__ clean, uint32_t* __restrict__ result /*[1]=other count, [2]=overflow*/,
-               uint32_t* __restrict__ other /*{rank,pos,code,cpos}*/, uint32_t other_cap)
+k_marker_scan_write(const uint8_t* __restrict__ file, size_t begin, size_t end, size_t base, volatile unsigned long long* status,
+                    uint32_t* __restrict__ list_pos, uint8_t* __restrict__ list_code, uint32_t* __restrict__ list_cpos, uint32_t list_cap,
+                    uint8_t* __restrict__ clean, uint32_t* __restrict__ result /*[0]=markers, [1]=other count, [2]=overflow, [5]=clean bytes*/,
+                    uint32_t* __restrict__ other /*{rank,pos,code,cpos}*/, uint32_t other_cap)
 {
     __shared__ uint32_t s_warp[MK_THREADS / 32];
     __shared__ __align__(16) uint8_t s_bytes[MK_TILE + 8];
     __shared__ uint32_t s_total;
+    __shared__ unsigned long long s_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t pos = base + (size_t)blockIdx.x * MK_TILE + (size_t)threadIdx.x * MK_BYTES;
+    const int tile = blockIdx.x;   // CTAs are dispatched in index order: every predecessor is running or done
+    const size_t pos = base + (size_t)tile * MK_TILE + (size_t)threadIdx.x * MK_BYTES;
     uint32_t w[5], bits = 0, keep = 0;
     if ( pos < end ) classify(file, begin, end, pos, w, bits, keep);
-    const uint32_t n = (uint32_t)__popc(bits) << 16 | (uint32_t)__popc(keep);
+    const uint32_t n = (uint32_t)__popc(bits) << 16 | (uint32_t)__popc(keep);   // <= 2048 / 4096 per CTA: no carry between the halves
     uint32_t incl = n;
 #pragma unroll
     for ( int d = 1; d < 32; d <<= 1 ) {
@@ -172,14 +122,47 @@ k_marker_write(const uint8_t* __restrict__ file, size_t begin, size_t end, size_
     uint32_t before = incl - n;
     for ( int i = 0; i < warp; i++ )
         before += s_warp[i];
-    const unsigned long long cb = cta_base[blockIdx.x];
-    uint32_t rank = (uint32_t)cb + (before >> 16);
-    const uint32_t cpos0 = (uint32_t)(cb >> 32) + (before & 0xFFFFu);
+    if ( warp == 0 ) {
+        uint32_t t = 0;
+        for ( int i = 0; i < MK_THREADS / 32; i++ )
+            t += s_warp[i];
+        const unsigned long long own = (unsigned long long)(t & 0xFFFFu) << 31 | (unsigned long long)(t >> 16);
+        if ( lane == 0 ) status[tile] = tile ? ST_AGGREGATE | own : ST_PREFIX | own;
+        /* look back: lane l inspects tile j - l; sums the counts of the tiles behind the nearest one that knows its prefix */
+        unsigned long long excl = 0;
+        for ( int j = tile - 1; j >= 0; j -= 32 ) {
+            unsigned long long st;
+            do {
+                st = j - lane >= 0 ? status[j - lane] : ST_PREFIX;   // in front of the stream: prefix 0
+            } while ( __any_sync(FULL, (st >> 62) == 0ull) );
+            const unsigned known = __ballot_sync(FULL, (st >> 62) == 2ull);
+            const int nearest = __ffs((int)known) - 1;              // >= 0: lane 31 at the latest when j - 31 < 0 ... or known == 0
+            unsigned long long v = (known == 0u || lane <= nearest) ? (st & ST_VALUE) : 0ull;
+#pragma unroll
+            for ( int d = 16; d > 0; d >>= 1 )
+                v += __shfl_xor_sync(FULL, v, d);
+            excl += v;
+            if ( known ) break;
+        }
+        if ( lane == 0 ) {
+            if ( tile ) status[tile] = ST_PREFIX | (excl + own);
+            s_base = excl;
+            if ( tile == (int)gridDim.x - 1 ) {
+                const unsigned long long total = excl + own;
+                result[0] = (uint32_t)(total & 0x7FFFFFFFull);
+                result[5] = (uint32_t)(total >> 31);
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned long long cb = s_base;
+    uint32_t rank = (uint32_t)(cb & 0x7FFFFFFFull) + (before >> 16);
+    const uint32_t cta_c0 = (uint32_t)(cb >> 31);          // clean position of the CTA's first kept byte
+    const uint32_t cpos0 = cta_c0 + (before & 0xFFFFu);
 
     /* The kept bytes, big-endian inside 32-bit words (clean byte c lives at address c ^ 3).  They are first compacted
      * in shared memory on the global word grid and then written out with coalesced 32-bit stores: scattered byte stores
      * straight to global memory (the first version) made this kernel five times slower than the scan itself. */
-    const uint32_t cta_c0 = (uint32_t)(cb >> 32);          // clean position of the CTA's first kept byte
     const uint32_t word0 = cta_c0 >> 2;                     // first global word the CTA touches
     {
         uint32_t c = cpos0 - word0 * 4u, m = keep;
@@ -249,10 +232,11 @@ extern "C" int gj_launch_marker_scan(const uint8_t* d_file, size_t begin, size_t
     /* d_file comes from cudaMalloc (256-byte aligned): tile from a 16-byte aligned base below `begin` */
     const size_t base = begin & ~static_cast<size_t>(15);
     const int n_cta = (int)((end - base + MK_TILE - 1) / MK_TILE);
-    if ( cudaMemsetAsync(d_result, 0, 8 * sizeof(uint32_t), stream) != cudaSuccess ) return -1;
-    k_marker_count<<<n_cta, MK_THREADS, 0, stream>>>(d_file, begin, end, base, d_cta);
-    k_marker_scan<<<1, 1024, 0, stream>>>(d_cta, n_cta, d_result);
-    k_marker_write<<<n_cta, MK_THREADS, 0, stream>>>(d_file, begin, end, base, d_cta, d_list_pos, d_list_code, d_list_cpos, list_cap,
-                                                     d_clean, d_result, d_other, other_cap);
+    if ( end - base >= ((size_t)1 << 31) ) return -1;   // the tile status holds 31-bit counts
+    if ( cudaMemsetAsync(d_result, 0, 8 * sizeof(uint32_t), stream) != cudaSuccess ||
+         cudaMemsetAsync(d_cta, 0, (size_t)n_cta * sizeof(unsigned long long), stream) != cudaSuccess )
+        return -1;
+    k_marker_scan_write<<<n_cta, MK_THREADS, 0, stream>>>(d_file, begin, end, base, d_cta, d_list_pos, d_list_code, d_list_cpos, list_cap,
+                                                          d_clean, d_result, d_other, other_cap);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -18,9 +18,11 @@ enc, dec, decf = g.Encoder(), g.Decoder(), g.Decoder(idct="float_gpuref")
 cases = [("photo", 200, 120, 75, 8, 0, "4:4:4", (1, 1)), ("random", 33, 17, 90, 2, 0, "4:4:4", (1, 1)),
          ("random", 100, 50, 60, 0, 0, "4:4:4", (1, 1)), ("photo", 256, 16, 95, 300, 0, "4:4:4", (1, 1)),
          ("random", 161, 97, 85, 4, 1, "4:2:0", (2, 2)), ("photo", 130, 70, 75, 3, 0, "4:2:2", (2, 1)),
-         ("random", 64, 40, 75, 50, 1, "4:4:0", (1, 2))]
+         ("random", 64, 40, 75, 50, 1, "4:4:0", (1, 2)),
+         # more units than resident warps: K3's unit counters, CTAs moving on to other scans (24 576 one-block segments)
+         ("photo", 1024, 512, 75, 1, 0, "4:4:4", (1, 1))]
 if quick:
-    cases = cases[:2] + cases[4:5]
+    cases = cases[:2] + cases[4:5] + cases[7:8]
 for kind, w, h, q, rst, il, name, samp in cases:
     img = o.gen_image(kind, w, h)
     want = o.encode(img, q, rst, il, sampling=samp)
