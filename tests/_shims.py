@@ -43,6 +43,7 @@ hs.shim_header.argtypes = [C.c_int] * 5 + [_u8p]
 hs.shim_forward_table_zz.argtypes = [C.c_int, C.c_int, np.ctypeslib.ndpointer(np.float32), _u8p]
 hs.shim_enc_lut.argtypes = [C.c_int, np.ctypeslib.ndpointer(np.uint32), np.ctypeslib.ndpointer(np.uint32)]
 hs.shim_dec_lut_symbol.argtypes = [C.c_int, C.c_int, C.c_uint, C.POINTER(C.c_int)]
+hs.shim_dec_fast_symbol.argtypes = [C.c_int, C.c_int, C.c_uint, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
 hs.shim_parse.argtypes = [_u8p, C.c_size_t, np.ctypeslib.ndpointer(np.int32), np.ctypeslib.ndpointer(np.uint32),
                           np.ctypeslib.ndpointer(np.uint32), C.c_int]
 hs.shim_header2.argtypes = [C.c_int] * 9 + [np.ctypeslib.ndpointer(np.uint8)]

@@ -75,6 +75,33 @@ int shim_dec_lut_symbol(int cls, int kind, unsigned peek16, int* len)
     return t.vals[((int)(peek16 >> (16 - l)) + t.valoff[l]) & 255];
 }
 
+/* decode one symbol from a 16-bit peek with the self-synchronising decoder's table (mirrors lookup / long_code in
+ * gj_huffdec.cu): returns the symbol's zig-zag advance, *total = code length + value size, *size = value size, *how =
+ * 1 first-level entry, 2 second-level table, 3 canonical search needed (entry 0) */
+int shim_dec_fast_symbol(int cls, int kind, unsigned peek16, int* total, int* size, int* how)
+{
+    struct gj_huff_spec spec;
+    static struct gj_dec_fast f;
+    gj_huff_spec_default(cls, kind, &spec);
+    gj_dec_fast_build(&spec, kind, &f);
+    unsigned e = f.e[peek16 >> (16 - GJ_DEC_FAST_BITS)];
+    *how = 1;
+    if ( (e & GJ_DEC_FAST_TOTAL_MASK) == 0 ) {
+        *how = 2;
+        if ( e ) {
+            if ( (e & 127u) < 1 || (e & 127u) > GJ_DEC_FAST_SUBS ) return -2;
+            e = f.sub[(e & 127u) - 1][peek16 & ((1u << (16 - GJ_DEC_FAST_BITS)) - 1u)];
+        }
+        if ( e == 0 ) {
+            *how = 3;
+            return -1;
+        }
+    }
+    *total = (int)((e >> GJ_DEC_FAST_TOTAL_SHIFT) & 31u);
+    *size = (int)(e >> GJ_DEC_FAST_SIZE_SHIFT);
+    return (int)(e & 127u);
+}
+
 /* parse + split; returns number of segments, fills a few fields */
 int shim_parse(const unsigned char* data, size_t size, int* info /*[8]*/, unsigned* seg_off, unsigned* seg_len, int max_seg)
 {

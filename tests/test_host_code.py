@@ -52,6 +52,32 @@ def test_decoder_lut_decodes_every_code(cls, kind):
             assert ln.value == size[sym]
 
 
+@pytest.mark.parametrize("cls,kind", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_fast_decoder_table_steps_over_every_code(cls, kind):
+    """gj_dec_fast (the table of the self-synchronising K3): for every code of the standard tables, followed by random
+    bits, one entry gives the bits to consume (code + value), the value size and the zig-zag advance; the standard
+    tables never need the canonical search."""
+    code, size = np.zeros(256, np.uint16), np.zeros(256, np.uint8)
+    o.lib.orc_huff_encoder_table(cls, kind, code, size)
+    rng = np.random.default_rng(4)
+    levels = set()
+    for sym in range(256):
+        sz = int(size[sym])
+        if sz == 0:
+            continue
+        vsize, run = sym & 15, sym >> 4
+        kadv = 1 if kind == 0 else run + 1 if vsize else 16 if run == 15 else 64
+        for _ in range(4):
+            tail = int(rng.integers(0, 1 << (16 - sz))) if sz < 16 else 0
+            peek = (int(code[sym]) << (16 - sz)) | tail
+            total, vs, how = C.c_int(), C.c_int(), C.c_int()
+            assert hs.shim_dec_fast_symbol(cls, kind, peek, C.byref(total), C.byref(vs), C.byref(how)) == kadv
+            assert (total.value, vs.value) == (sz + vsize, vsize)
+            assert how.value == (1 if sz <= 10 else 2)
+            levels.add(how.value)
+    assert levels == ({1} if (cls, kind) == (0, 0) else {1, 2})   # longest code: DC luminance 9 bits, DC chrominance 11, AC 16
+
+
 @pytest.mark.parametrize("kind,w,h,rst,il", [("random", 1920, 1080, 24, 0), ("photo", 640, 360, 7, 1),
                                              ("random", 100, 50, 0, 0), ("gradient", 64, 64, 1, 0)])
 def test_reader_finds_every_segment(kind, w, h, rst, il):
