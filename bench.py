@@ -378,7 +378,7 @@ def run_batch(args, g, o, torch, dist, rank, world, local, dev, numa, nccl_log):
                        "sharding": "frames round-robin over ranks, no data-path collective; `scattered`: NCCL send/recv of raw "
                                    "frames from rank 0 + gather-v of the streams"},
             "scattered": scattered, "jpeg_bytes_per_frame": int(np.mean(sizes)) if sizes else None,
-            "gpu_launches": 7 * len(mine) * args.steps, "clocks": clocks, "numa": numa})
+            "gpu_launches": 6 * len(mine) * args.steps, "clocks": clocks, "numa": numa})
     enc.close()
     dec.close()
     if world > 1:
@@ -649,7 +649,7 @@ def main():
                     "pipelined_value": round(world * npix / (e2e_pipe_ms * 1e-3) / 1e6, 1) if e2e_pipe_ms else None,
                     "pipelined_ms_per_step": round(e2e_pipe_ms, 3) if e2e_pipe_ms else None, "pipelined_workers": workers},
             # per step: K1, K2 (encode, offsets, compaction), K0 (count, scan, write), K3, K4 -- plus one 32-byte memset node
-            "gpu_launches": 7 * args.steps,
+            "gpu_launches": 6 * args.steps,
             "clocks": clocks,
         }
         if not args.no_reference_gpu and world == 1:

@@ -11,11 +11,10 @@
  *                   their lengths into a shared-memory stream buffer and byte-stuffs it into the segment's slot.
  *   k_huff_encode   segments of any length (even restart_interval = 0): one WARP per segment, one LANE per block,
  *                   the same steps per round of 32 blocks, streaming through the 2 KB buffer.
- *   k_huff_offsets  exclusive scan of the segment sizes -> final byte offsets (deterministic,
- *                   unlike the reference's atomicAdd compaction).
- *   k_huff_compact  copies every segment to its final place and writes RSTn markers, the SOS
- *                   headers prepared by the host writer and EOI: the device buffer then holds the
- *                   finished scan data and the host does a single D2H copy.
+ *   k_huff_place    final byte offsets of the segments by a decoupled look-back over the CTAs' byte counts
+ *                   (deterministic, unlike the reference's atomicAdd compaction), then every segment to its final
+ *                   place with its RSTn marker, the SOS headers prepared by the host writer and EOI: the device
+ *                   buffer then holds the finished scan data and the host does a single D2H copy.
  *
  * DECODER (replaces src/gpujpeg_huffman_gpu_decoder.cu:390-537, 596-610):
  *   k_huff_decode   one THREAD per restart segment (sequential by nature); the owner lanes of a warp advance
@@ -148,8 +147,9 @@ __global__ void __launch_bounds__(HE_WARPS * 32)
 k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzmask, const __grid_constant__ gj_scan_layout lay,
               int seg_mcu, int seg_count, uint8_t* __restrict__ tmp, size_t slot_stride,
               uint32_t* __restrict__ seg_bytes, uint32_t* __restrict__ spill_all, const gj_dev_enc_tables* __restrict__ tables,
-              uint64_t* __restrict__ info)
+              uint64_t* __restrict__ info, unsigned long long* __restrict__ place_status, int n_status)
 {
+    if ( threadIdx.x == 0 && (int)blockIdx.x < n_status ) place_status[blockIdx.x] = 0ull;   // for k_huff_place, the next launch
     const uint32_t slot_cap = (uint32_t)slot_stride;
     extern __shared__ __align__(16) uint32_t he_smem[];
     uint32_t (*s_ac)[256] = reinterpret_cast<uint32_t (*)[256]>(he_smem);
@@ -370,8 +370,10 @@ __global__ void __launch_bounds__(HP_THREADS_MAX)
 k_huff_encode_packed(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzmask,
                      const __grid_constant__ gj_scan_layout lay, int seg_mcu, int seg_count, uint8_t* __restrict__ tmp,
                      size_t slot_stride, uint32_t* __restrict__ seg_bytes, uint32_t* __restrict__ spill_all,
-                     const gj_dev_enc_tables* __restrict__ tables, uint64_t* __restrict__ info)
+                     const gj_dev_enc_tables* __restrict__ tables, uint64_t* __restrict__ info,
+                     unsigned long long* __restrict__ place_status, int n_status)
 {
+    if ( threadIdx.x == 0 && (int)blockIdx.x < n_status ) place_status[blockIdx.x] = 0ull;   // for k_huff_place, the next launch
     const uint32_t slot_cap = (uint32_t)slot_stride;
     extern __shared__ __align__(16) uint32_t he_smem[];
     uint32_t (*s_ac)[256] = reinterpret_cast<uint32_t (*)[256]>(he_smem);
@@ -586,14 +588,6 @@ k_huff_encode_packed(const int16_t* __restrict__ coef, const uint64_t* __restric
     }
 }
 
-/* exclusive scan over segment sizes -> byte offsets in the finished stream.  A single CTA walking the
- * array is a chain of dependent memory latencies (measured 23-30 us for the 43 200 segments of an 8K frame),
- * so the array is cut into one chunk per CTA; a CTA first adds up everything in front of its chunk
- * (independent coalesced loads of an array that sits in L2 -- redundant between CTAs, but only
- * grid * n / 2 four-byte reads) and then scans its own chunk in tiles of 1024.  The grid is capped at the SM
- * count, so the redundant part stays O(148 n).  Deterministic order (the reference's atomicAdd compaction
- * is not). */
-constexpr int OFF_THREADS = 1024;
 /* first global segment of every scan; entries past the last scan hold seg_count */
 struct ScanSegs {
     int begin[GJ_MAX_COMP + 1];
@@ -602,93 +596,84 @@ __device__ __forceinline__ int scan_of_segment(const ScanSegs& S, int g)
 {
     return (g >= S.begin[1]) + (g >= S.begin[2]) + (g >= S.begin[3]);
 }
-__global__ void __launch_bounds__(OFF_THREADS)
-k_huff_offsets(const uint32_t* __restrict__ seg_bytes, int seg_count, const __grid_constant__ ScanSegs segs, int chunk,
-               uint32_t header_size, int sos_len, uint64_t stream_cap, uint64_t* __restrict__ seg_off,
-               uint64_t* __restrict__ info)
+
+/* k_huff_place: every segment to its final offset in the stream, with the RSTn / SOS / EOI bytes around it.
+ * A segment as it appears in the stream: [SOS header if first of its scan] bytes [RSTn unless last of its scan].  The
+ * offset of a segment is the sum of everything in front of it -- an exclusive scan over 43 200 sizes at 8K.  Round 1
+ * ran that scan as a kernel of its own (a single CTA: 23-30 us of dependent latencies; 43 CTAs that each re-add the
+ * sizes in front of their chunk: 9 us) and the copy as another (10 us).  Here the CTA that copies 32 segments finds its
+ * own base itself: it publishes the bytes of its 32 segments at once and adds up what the CTAs before it have published.
+ * Deterministic order (the reference's atomicAdd compaction is not).  Eight lanes per segment (a segment of photographic
+ * content is ~140 bytes). */
+constexpr int CP_LANES = 8;                       // lanes per segment
+constexpr int CP_SEGS = 256 / CP_LANES;           // segments per CTA
+#define PL_VALID (1ull << 62)
+#define PL_VALUE ((1ull << 62) - 1ull)
+__global__ void __launch_bounds__(256)
+k_huff_place(const uint8_t* __restrict__ tmp, size_t slot_stride, const uint32_t* __restrict__ seg_bytes, int seg_count,
+             const __grid_constant__ ScanSegs segs, const uint8_t* __restrict__ sos, int sos_len, uint32_t header_size,
+             uint64_t stream_cap, uint8_t* __restrict__ stream, volatile unsigned long long* status /* zeroed by the encoder kernel */,
+             uint64_t* __restrict__ info)
 {
-    __shared__ uint64_t s_warp[32];
-    __shared__ uint32_t s_tile[32];
+    __shared__ uint32_t s_excl[CP_SEGS];
+    __shared__ unsigned long long s_part[8];
+    __shared__ uint32_t s_own;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int begin = blockIdx.x * chunk, end = min(seg_count, begin + chunk);
-
-    /* everything in front of the chunk: entropy bytes summed with 16-byte loads (begin is a multiple of 1024,
-     * cudaMalloc aligns the array), the SOS headers and RSTn markers in closed form */
-    uint64_t sum = 0;
-    const uint4* v4 = reinterpret_cast<const uint4*>(seg_bytes);
-#pragma unroll 4
-    for ( int q = threadIdx.x; q < begin / 4; q += OFF_THREADS ) {
-        const uint4 t = __ldg(v4 + q);
-        sum += (uint64_t)t.x + t.y + t.z + t.w;
-    }
-#pragma unroll
-    for ( int d = 16; d > 0; d >>= 1 )
-        sum += __shfl_down_sync(FULL, sum, d);
-    if ( lane == 0 ) s_warp[warp] = sum;
+    const int tile = blockIdx.x;   // CTAs are dispatched in index order: every predecessor is running or done
+    const int sl = threadIdx.x & (CP_LANES - 1), ls = threadIdx.x / CP_LANES;   // lane in segment, segment in CTA
+    const int g = blockIdx.x * CP_SEGS + ls;
+    const bool valid = g < seg_count;
+    const int scan = valid ? scan_of_segment(segs, g) : 0, s = g - segs.begin[scan];
+    const bool first_of_scan = valid && s == 0, last_of_scan = valid && g + 1 == segs.begin[scan + 1];
+    const uint32_t n = valid ? __ldg(seg_bytes + g) : 0u;
+    const uint32_t v = valid ? n + (first_of_scan ? (uint32_t)sos_len : 0u) + (last_of_scan ? 0u : 2u) : 0u;
+    if ( sl == 0 ) s_excl[ls] = v;
     __syncthreads();
-    /* a segment as it appears in the stream: [SOS header if first of its scan] bytes [RSTn unless last of its scan] */
-    int started = 0, finished = 0;   // scans with a segment in front of the chunk / lying completely in front of it
-#pragma unroll
-    for ( int k = 0; k < GJ_MAX_COMP; k++ ) {
-        if ( segs.begin[k] < begin && segs.begin[k] < seg_count ) started++;
-        if ( segs.begin[k + 1] <= begin && segs.begin[k] < seg_count ) finished++;
-    }
-    uint64_t base = header_size + (uint64_t)started * (uint64_t)sos_len + 2ull * (uint64_t)(begin - finished);
-#pragma unroll
-    for ( int w = 0; w < 32; w++ )
-        base += s_warp[w];
-
-    for ( int t0 = begin; t0 < end; t0 += OFF_THREADS ) {
-        const int g = t0 + threadIdx.x;
-        const int scan = scan_of_segment(segs, g);
-        const bool first = g == segs.begin[scan], last = g + 1 == segs.begin[scan + 1];
-        const uint32_t v = g < end ? __ldg(seg_bytes + g) + (first ? (uint32_t)sos_len : 0u) + (last ? 0u : 2u) : 0u;
-        uint32_t incl = v;
+    if ( warp == 0 ) {
+        const uint32_t mine = s_excl[lane];
+        uint32_t incl = mine;
 #pragma unroll
         for ( int d = 1; d < 32; d <<= 1 ) {
             const uint32_t t = __shfl_up_sync(FULL, incl, d);
             if ( lane >= d ) incl += t;
         }
-        __syncthreads();   // s_tile of the previous tile fully consumed
-        if ( lane == 31 ) s_tile[warp] = incl;
-        __syncthreads();
-        uint32_t before = 0, tile_total = 0;
-#pragma unroll
-        for ( int w = 0; w < 32; w++ ) {
-            const uint32_t t = s_tile[w];
-            if ( w < warp ) before += t;
-            tile_total += t;
+        s_excl[lane] = incl - mine;
+        if ( lane == 31 ) {
+            status[tile] = PL_VALID | (unsigned long long)incl;
+            s_own = incl;
         }
-        /* the segment's bytes start after its SOS header (if any) */
-        if ( g < end ) seg_off[g] = base + before + (incl - v) + (first ? (uint32_t)sos_len : 0u);
-        base += tile_total;
     }
-    if ( end == seg_count && threadIdx.x == 0 ) {
-        const uint64_t total = base + 2;  // + EOI
+    /* everything in front of this CTA: the published counts of ALL CTAs before it, 256 at a time (they are published within
+     * a microsecond of the launch; waiting for a predecessor's running prefix instead chains ~40 dependent round trips
+     * through L2 at this tile count and measured 26 us) */
+    unsigned long long sum = 0;
+    for ( int j = threadIdx.x; j < tile; j += 256 ) {
+        unsigned long long st;
+        do {
+            st = status[j];
+        } while ( st == 0ull );
+        sum += st & PL_VALUE;
+    }
+#pragma unroll
+    for ( int d = 16; d > 0; d >>= 1 )
+        sum += __shfl_xor_sync(FULL, sum, d);
+    if ( lane == 0 ) s_part[warp] = sum;
+    __syncthreads();
+    unsigned long long base = 0;
+#pragma unroll
+    for ( int i = 0; i < 8; i++ )
+        base += s_part[i];
+    if ( threadIdx.x == 0 && tile == (int)gridDim.x - 1 ) {
+        const uint64_t total = (uint64_t)header_size + base + s_own + 2;   // + EOI
         info[0] = total;
         info[1] = (info[1] & 2ull) | (total > stream_cap ? 1ull : 0ull);   // bit 1: a segment slot overflowed (set by the encoder)
     }
-}
-
-/* move every segment to its final offset; add RSTn / SOS / EOI.  Eight lanes per segment (a segment of photographic
- * content is ~140 bytes: a whole warp per segment mostly waited for its three dependent loads, 17.6 us; four segments
- * per warp quarter the number of waves). */
-constexpr int CP_LANES = 8;                       // lanes per segment
-constexpr int CP_SEGS = 256 / CP_LANES;           // segments per CTA
-__global__ void __launch_bounds__(256)
-k_huff_compact(const uint8_t* __restrict__ tmp, size_t slot_stride, const uint32_t* __restrict__ seg_bytes,
-               const uint64_t* __restrict__ seg_off, int seg_count, const __grid_constant__ ScanSegs segs,
-               const uint8_t* __restrict__ sos, int sos_len, uint8_t* __restrict__ stream, const uint64_t* __restrict__ info)
-{
-    if ( info[1] ) return;  // would overflow the stream buffer: host reports the error
-    const int sl = threadIdx.x & (CP_LANES - 1);
-    const int g = blockIdx.x * CP_SEGS + threadIdx.x / CP_LANES;
-    if ( g >= seg_count ) return;
-    const int scan = scan_of_segment(segs, g), s = g - segs.begin[scan];
-    const bool last_of_scan = g + 1 == segs.begin[scan + 1];
+    if ( !valid || (info[1] & 2ull) ) return;   // slots too small: their contents are truncated, the host encodes again
+    /* the segment's bytes start after its SOS header (if any) */
+    const uint64_t off = (uint64_t)header_size + base + s_excl[ls] + (first_of_scan ? (uint32_t)sos_len : 0u);
+    if ( off + n + 2u > stream_cap ) return;   // would overflow the stream buffer: the host reports the error (info[1] bit 0)
     const uint8_t* src = tmp + (size_t)g * slot_stride;
-    const uint32_t n = seg_bytes[g];
-    uint8_t* dst = stream + seg_off[g];
+    uint8_t* dst = stream + off;
     /* head bytes up to 16-byte alignment of dst, then 16 B stores assembled from 4 B loads */
     const uint32_t head = min(n, (uint32_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15));
     for ( uint32_t q = sl; q < head; q += CP_LANES )
@@ -697,8 +682,8 @@ k_huff_compact(const uint8_t* __restrict__ tmp, size_t slot_stride, const uint32
     const uint32_t sh = (i & 3) * 8;
     const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src + (i & ~3u));
     const uint32_t nvec = (n - i) >> 4;
-    for ( uint32_t v = sl; v < nvec; v += CP_LANES ) {
-        const uint32_t* p = s32 + v * 4;
+    for ( uint32_t q = sl; q < nvec; q += CP_LANES ) {
+        const uint32_t* p = s32 + q * 4;
         uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3];
         if ( sh ) {
             const uint32_t w4 = p[4];
@@ -707,7 +692,7 @@ k_huff_compact(const uint8_t* __restrict__ tmp, size_t slot_stride, const uint32
             w2 = __funnelshift_r(w2, w3, sh);
             w3 = __funnelshift_r(w3, w4, sh);
         }
-        reinterpret_cast<uint4*>(dst + i)[v] = make_uint4(w0, w1, w2, w3);
+        reinterpret_cast<uint4*>(dst + i)[q] = make_uint4(w0, w1, w2, w3);
     }
     i += nvec << 4;
     for ( uint32_t q = i + sl; q < n; q += CP_LANES )   // tail < 16 bytes
@@ -1024,6 +1009,10 @@ extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_str
     ScanSegs segs;
     for ( int k = 0; k <= GJ_MAX_COMP; k++ )
         segs.begin[k] = a->lay.scan_seg_begin[k];
+    /* tile status of k_huff_place's look-back: one word per 32 segments, in the (otherwise unused) offset array; zeroed by
+     * the encoder kernel, whose grid (one CTA per 8 segments) is larger */
+    const int n_status = (seg_count + CP_SEGS - 1) / CP_SEGS;
+    unsigned long long* const place_status = reinterpret_cast<unsigned long long*>(a->d_seg_off);
     static bool attr_done[64] = {false};
     int dev = 0;
     if ( cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 ) return -1;
@@ -1042,21 +1031,15 @@ extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_str
         const int hp_threads = max(HE_WARPS * 32, (HE_WARPS * a->seg_mcu * a->lay.bpm + 31) / 32 * 32);
         k_huff_encode_packed<<<(seg_count + HE_WARPS - 1) / HE_WARPS, hp_threads, HP_SMEM, stream>>>(
             a->d_coef, a->d_nzmask, a->lay, a->seg_mcu, seg_count, a->d_tmp, a->slot_stride, a->d_seg_bytes, a->d_spill,
-            a->d_tables, a->d_info);
+            a->d_tables, a->d_info, place_status, n_status);
     }
     else {
         k_huff_encode<<<(seg_count + HE_WARPS - 1) / HE_WARPS, HE_WARPS * 32, HE_SMEM, stream>>>(
             a->d_coef, a->d_nzmask, a->lay, a->seg_mcu, seg_count, a->d_tmp, a->slot_stride, a->d_seg_bytes, a->d_spill,
-            a->d_tables, a->d_info);
+            a->d_tables, a->d_info, place_status, n_status);
     }
-    /* one chunk (a multiple of the 1024-segment tile) per CTA, at most one CTA per SM */
-    int off_chunk = (seg_count + 147) / 148;
-    off_chunk = ((off_chunk + OFF_THREADS - 1) / OFF_THREADS) * OFF_THREADS;
-    const int off_grid = (seg_count + off_chunk - 1) / off_chunk;
-    k_huff_offsets<<<off_grid, OFF_THREADS, 0, stream>>>(a->d_seg_bytes, seg_count, segs, off_chunk, a->header_size, a->sos_len,
-                                                         (uint64_t)a->stream_cap, a->d_seg_off, a->d_info);
-    k_huff_compact<<<(seg_count + CP_SEGS - 1) / CP_SEGS, 256, 0, stream>>>(a->d_tmp, a->slot_stride, a->d_seg_bytes, a->d_seg_off, seg_count,
-                                                            segs, a->d_sos, a->sos_len, a->d_stream, a->d_info);
+    k_huff_place<<<n_status, 256, 0, stream>>>(a->d_tmp, a->slot_stride, a->d_seg_bytes, seg_count, segs, a->d_sos, a->sos_len,
+                                               a->header_size, (uint64_t)a->stream_cap, a->d_stream, place_status, a->d_info);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

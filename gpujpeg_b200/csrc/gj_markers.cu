@@ -9,9 +9,9 @@
  * 543 ms for that step on one sample.  On a B200 host the same walk costs 2.1 ms for an 8K frame --
  * six times the GPU time of the entire decode.  Here the file is uploaded once, untouched, and ONE launch does the
  * reader's per-byte work in device memory (k_marker_scan_write): every CTA classifies a 4 KB tile (16 bytes per
- * thread), counts its markers and the bytes that stay in the clean stream, learns how many of both lie in front of it by
- * a decoupled look-back over the tiles before it (each tile publishes its own counts at once and its inclusive prefix
- * as soon as it knows it; a warp inspects 32 predecessors per step), and then does the ordered compaction:
+ * thread), counts its markers and the bytes that stay in the clean stream, publishes both, adds up what the tiles in
+ * front of it have published (no chain: every tile sums its predecessors' counts itself, ~3 loads per thread on average
+ * for the 1440 tiles of a 6 MB stream), and then does the ordered compaction:
  * list[rank] = {raw position, code, clean position}; the kept bytes go to their clean position; markers other than
  * RSTn are also appended to a short list the host reads back (scan ends, ranks: everything the host needs to finish
  * the marker walk).  (Round 1 and the first half of round 2: count, single-CTA scan and write as three launches,
@@ -89,10 +89,10 @@ __device__ __forceinline__ void classify(const uint8_t* __restrict__ file, size_
     keep = inside & ~drop & 0xFFFFu;
 }
 
-/* Tile status for the look-back: flag << 62 | kept bytes << 31 | markers (both < 2^31: the launcher refuses longer
- * streams); a 64-bit word is written and read in one piece, so the flag and the counts it vouches for cannot be torn. */
-#define ST_AGGREGATE (1ull << 62)
-#define ST_PREFIX (2ull << 62)
+/* Published tile counts: valid flag << 62 | kept bytes << 31 | markers (sums of both stay < 2^31: the launcher refuses
+ * longer streams); a 64-bit word is written and read in one piece, so the flag and the counts it vouches for cannot be
+ * torn. */
+#define ST_VALID (1ull << 62)
 #define ST_VALUE ((1ull << 62) - 1ull)
 
 __global__ void __launch_bounds__(MK_THREADS)
@@ -104,7 +104,7 @@ k_marker_scan_write(const uint8_t* __restrict__ file, size_t begin, size_t end, 
     __shared__ uint32_t s_warp[MK_THREADS / 32];
     __shared__ __align__(16) uint8_t s_bytes[MK_TILE + 8];
     __shared__ uint32_t s_total;
-    __shared__ unsigned long long s_base;
+    __shared__ unsigned long long s_part[MK_THREADS / 32], s_own;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile = blockIdx.x;   // CTAs are dispatched in index order: every predecessor is running or done
     const size_t pos = base + (size_t)tile * MK_TILE + (size_t)threadIdx.x * MK_BYTES;
@@ -122,40 +122,39 @@ k_marker_scan_write(const uint8_t* __restrict__ file, size_t begin, size_t end, 
     uint32_t before = incl - n;
     for ( int i = 0; i < warp; i++ )
         before += s_warp[i];
-    if ( warp == 0 ) {
+    if ( threadIdx.x == 0 ) {
         uint32_t t = 0;
         for ( int i = 0; i < MK_THREADS / 32; i++ )
             t += s_warp[i];
         const unsigned long long own = (unsigned long long)(t & 0xFFFFu) << 31 | (unsigned long long)(t >> 16);
-        if ( lane == 0 ) status[tile] = tile ? ST_AGGREGATE | own : ST_PREFIX | own;
-        /* look back: lane l inspects tile j - l; sums the counts of the tiles behind the nearest one that knows its prefix */
-        unsigned long long excl = 0;
-        for ( int j = tile - 1; j >= 0; j -= 32 ) {
-            unsigned long long st;
-            do {
-                st = j - lane >= 0 ? status[j - lane] : ST_PREFIX;   // in front of the stream: prefix 0
-            } while ( __any_sync(FULL, (st >> 62) == 0ull) );
-            const unsigned known = __ballot_sync(FULL, (st >> 62) == 2ull);
-            const int nearest = __ffs((int)known) - 1;              // >= 0: lane 31 at the latest when j - 31 < 0 ... or known == 0
-            unsigned long long v = (known == 0u || lane <= nearest) ? (st & ST_VALUE) : 0ull;
-#pragma unroll
-            for ( int d = 16; d > 0; d >>= 1 )
-                v += __shfl_xor_sync(FULL, v, d);
-            excl += v;
-            if ( known ) break;
-        }
-        if ( lane == 0 ) {
-            if ( tile ) status[tile] = ST_PREFIX | (excl + own);
-            s_base = excl;
-            if ( tile == (int)gridDim.x - 1 ) {
-                const unsigned long long total = excl + own;
-                result[0] = (uint32_t)(total & 0x7FFFFFFFull);
-                result[5] = (uint32_t)(total >> 31);
-            }
-        }
+        status[tile] = ST_VALID | own;
+        s_own = own;
     }
+    /* everything in front of this tile: the published counts of ALL tiles before it, 256 at a time (they are published
+     * within a microsecond of the launch; waiting for a predecessor's running prefix instead chains ~45 dependent round
+     * trips through L2 at this tile count) */
+    unsigned long long sum = 0;
+    for ( int j = threadIdx.x; j < tile; j += MK_THREADS ) {
+        unsigned long long st;
+        do {
+            st = status[j];
+        } while ( st == 0ull );
+        sum += st & ST_VALUE;
+    }
+#pragma unroll
+    for ( int d = 16; d > 0; d >>= 1 )
+        sum += __shfl_xor_sync(FULL, sum, d);
+    if ( lane == 0 ) s_part[warp] = sum;
     __syncthreads();
-    const unsigned long long cb = s_base;
+    unsigned long long cb = 0;
+#pragma unroll
+    for ( int i = 0; i < MK_THREADS / 32; i++ )
+        cb += s_part[i];
+    if ( threadIdx.x == 0 && tile == (int)gridDim.x - 1 ) {
+        const unsigned long long total = cb + s_own;
+        result[0] = (uint32_t)(total & 0x7FFFFFFFull);
+        result[5] = (uint32_t)(total >> 31);
+    }
     uint32_t rank = (uint32_t)(cb & 0x7FFFFFFFull) + (before >> 16);
     const uint32_t cta_c0 = (uint32_t)(cb >> 31);          // clean position of the CTA's first kept byte
     const uint32_t cpos0 = cta_c0 + (before & 0xFFFFu);

@@ -1,7 +1,7 @@
 """Minimal driver for profiling: sets up one 8K (or other) frame and runs N resident encode+decode steps.
-    ncu --set full --clock-control none --import-source on -k regex:k_ -s 14 -c 7 -o gpurun_out/prof python profiles/run_step.py
-Kernel launch order per step: k_fdct_rgb444, k_huff_encode_packed, k_huff_offsets, k_huff_compact, k_marker_scan_write,
-k_huff_decode_sync, k_idct_rgb444 (7 launches)."""
+    ncu --set full --clock-control none --import-source on -k regex:k_ -s 12 -c 6 -o gpurun_out/prof python profiles/run_step.py
+Kernel launch order per step: k_fdct_rgb444, k_huff_encode_packed, k_huff_place, k_marker_scan_write,
+k_huff_decode_sync, k_idct_rgb444 (6 launches)."""
 import os
 import sys
 
