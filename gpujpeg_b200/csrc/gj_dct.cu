@@ -40,6 +40,7 @@ constexpr int BLK_F = 68;              // floats per block in K1's planar stagin
                                        // stride 272 B puts the 16 B row reads of consecutive blocks on
                                        // distinct bank groups)
 constexpr int K1_SMEM = 3 * TB * BLK_F * 4;   // 52224 B
+constexpr int K1_OUT_STRIDE = 9;              // uint4 per block slot of K1's output staging (8 + 1 pad: 144-byte stride)
 constexpr int K4_PLANE = 8 * STRIP_PX;        // bytes per component plane of a strip
 
 struct FdctParams {
@@ -61,10 +62,8 @@ __device__ __forceinline__ uint32_t pack4_sat_u8(int p0, int p1, int p2, int p3)
 /* quantise the 64 coefficients of a block held in registers (natural order), emit them in zig-zag order as eight
  * 16-byte stores plus the block's 64-bit non-zero mask (bit k <=> zig-zag coefficient k != 0: saves K2 a pass over
  * the block) */
-__device__ __forceinline__ void quantise_store(const float (&v)[64], const float* __restrict__ tab, int16_t* __restrict__ coef_blk,
-                                               uint64_t* __restrict__ nz)
+__device__ __forceinline__ uint64_t quantise_pack(const float (&v)[64], const float* __restrict__ tab, uint32_t (&packed)[32])
 {
-    uint32_t packed[32];
     uint32_t mlo = 0, mhi = 0;
 #pragma unroll
     for ( int k = 0; k < 64; k += 2 ) {
@@ -80,7 +79,13 @@ __device__ __forceinline__ void quantise_store(const float (&v)[64], const float
             if ( b1 != GJ_QUANT_ZERO ) mhi |= 1u << ((k + 1) & 31);
         }
     }
-    *nz = (uint64_t)mhi << 32 | mlo;
+    return (uint64_t)mhi << 32 | mlo;
+}
+__device__ __forceinline__ void quantise_store(const float (&v)[64], const float* __restrict__ tab, int16_t* __restrict__ coef_blk,
+                                               uint64_t* __restrict__ nz)
+{
+    uint32_t packed[32];
+    *nz = quantise_pack(v, tab, packed);
     uint4* dst = reinterpret_cast<uint4*>(coef_blk);
 #pragma unroll
     for ( int i = 0; i < 8; i++ )
@@ -166,7 +171,7 @@ k_fdct_rgb444(const uint8_t* __restrict__ raw, int width, int height, size_t pit
     /* phase B: one thread = one 8x8 block of one component, everything in registers */
     const int comp = threadIdx.x >> 6;
     const int b = threadIdx.x & 63;
-    if ( bx0 + b >= bcx ) return;
+    const bool active = bx0 + b < bcx;
     float v[64];
     {
         const float4* in = reinterpret_cast<const float4*>(s_pl + (comp * TB + b) * BLK_F);
@@ -176,10 +181,32 @@ k_fdct_rgb444(const uint8_t* __restrict__ raw, int width, int height, size_t pit
             v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
         }
     }
+    __syncthreads();   // the planes are in registers: their memory becomes the output staging area
     gj_fdct_block(v);
-    /* quantise: q = rint(c * table) [ref: src/gpujpeg_dct_gpu.cu:276-283], emit in zig-zag order */
-    const size_t bi = (size_t)comp * nblk + (size_t)by * bcx + bx0 + b;
-    quantise_store(v, prm.fwd_zz[comp == 0 ? 0 : 1], coef + bi * 64, nzmask + bi);
+    /* quantise: q = rint(c * table) [ref: src/gpujpeg_dct_gpu.cu:276-283], zig-zag order.  The block (128 bytes) goes to
+     * shared memory first and from there to the coefficient buffer as whole lines: a thread storing its own block
+     * straight away makes every store instruction of the warp touch 32 different lines, 16 bytes each. */
+    uint4* const s_out = reinterpret_cast<uint4*>(smem);   // slot = thread, K1_OUT_STRIDE uint4 apart (bank-conflict-free)
+    {
+        uint32_t packed[32];
+        const uint64_t nz = quantise_pack(v, prm.fwd_zz[comp == 0 ? 0 : 1], packed);
+        const size_t bi = (size_t)comp * nblk + (size_t)by * bcx + bx0 + b;
+        if ( active ) nzmask[bi] = nz;
+#pragma unroll
+        for ( int i = 0; i < 8; i++ )
+            s_out[threadIdx.x * K1_OUT_STRIDE + i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+    }
+    __syncthreads();
+#pragma unroll
+    for ( int k = 0; k < 8; k++ ) {
+        const int q = threadIdx.x + k * NT;
+        const int slot = q >> 3, part = q & 7;
+        const int c2 = slot >> 6, b2 = slot & 63;
+        if ( bx0 + b2 < bcx ) {
+            const size_t bi = (size_t)c2 * nblk + (size_t)by * bcx + bx0 + b2;
+            reinterpret_cast<uint4*>(coef + bi * 64)[part] = s_out[slot * K1_OUT_STRIDE + part];
+        }
+    }
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -398,34 +425,53 @@ k_fdct_rgb_ss(const uint8_t* __restrict__ raw, int width, int height, size_t pit
     __syncthreads();
 
     /* phase B: one thread = one block */
-    int comp, bx, by, sblk;
-    if ( threadIdx.x < TB * VS ) {
-        comp = 0;
-        const int b = threadIdx.x & (TB - 1), byl = threadIdx.x / TB;
-        bx = bx0 + b;
-        by = blockIdx.y * VS + byl;
-        sblk = threadIdx.x;
-    }
-    else {
-        const int u = threadIdx.x - TB * VS;
-        comp = 1 + u / CB;
-        bx = bx0 / HS + u % CB;
-        by = blockIdx.y;
-        sblk = TB * VS + u;
-    }
-    if ( bx >= grid.bcx[comp] || by >= grid.bcy[comp] ) return;
+    auto locate = [&](int t, int& comp, int& bx, int& by) {   // block of thread / staging slot t
+        if ( t < TB * VS ) {
+            comp = 0;
+            bx = bx0 + (t & (TB - 1));
+            by = blockIdx.y * VS + t / TB;
+        }
+        else {
+            const int u = t - TB * VS;
+            comp = 1 + u / CB;
+            bx = bx0 / HS + u % CB;
+            by = blockIdx.y;
+        }
+        return bx < grid.bcx[comp] && by < grid.bcy[comp];
+    };
+    int comp, bx, by;
+    const bool active = locate(threadIdx.x, comp, bx, by);
     float v[64];
     {
-        const float4* in = reinterpret_cast<const float4*>(s_y + sblk * BLK_F);
+        const float4* in = reinterpret_cast<const float4*>(s_y + threadIdx.x * BLK_F);
 #pragma unroll
         for ( int i = 0; i < 16; i++ ) {
             const float4 t = in[i];
             v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
         }
     }
+    __syncthreads();   // the planes are in registers: their memory becomes the output staging area (see k_fdct_rgb444)
     gj_fdct_block(v);
-    const size_t bi = (size_t)grid.blk_off[comp] + (size_t)by * grid.bcx[comp] + bx;
-    quantise_store(v, prm.fwd_zz[comp == 0 ? 0 : 1], coef + bi * 64, nzmask + bi);
+    uint4* const s_out = reinterpret_cast<uint4*>(smem);
+    {
+        uint32_t packed[32];
+        const uint64_t nz = quantise_pack(v, prm.fwd_zz[comp == 0 ? 0 : 1], packed);
+        if ( active ) nzmask[(size_t)grid.blk_off[comp] + (size_t)by * grid.bcx[comp] + bx] = nz;
+#pragma unroll
+        for ( int i = 0; i < 8; i++ )
+            s_out[threadIdx.x * K1_OUT_STRIDE + i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+    }
+    __syncthreads();
+#pragma unroll
+    for ( int k = 0; k < 8; k++ ) {
+        const int q = threadIdx.x + k * NTS;
+        const int slot = q >> 3, part = q & 7;
+        int c2, bx2, by2;
+        if ( locate(slot, c2, bx2, by2) ) {
+            const size_t bi = (size_t)grid.blk_off[c2] + (size_t)by2 * grid.bcx[c2] + bx2;
+            reinterpret_cast<uint4*>(coef + bi * 64)[part] = s_out[slot * K1_OUT_STRIDE + part];
+        }
+    }
 }
 
 /* =========================================================================================== */
@@ -452,6 +498,8 @@ k_idct_rgb444(const int16_t* __restrict__ coef, int bcx, int nblk, uint8_t* __re
         const int comp = threadIdx.x >> 6;
         const int b = threadIdx.x & 63;
         if ( bx0 + b < bcx ) {
+            /* (each thread fetches its own block: 32 lines per load instruction, but L1 serves the second half of every
+             * sector; staging the strip in shared memory with whole-line loads measured 99.5 us against 88.4) */
             const uint4* src = reinterpret_cast<const uint4*>(coef + ((size_t)comp * nblk + (size_t)by * bcx + bx0 + b) * 64);
             uint32_t packed[32];
 #pragma unroll

@@ -691,7 +691,11 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
         ecs_bytes += st.scan[k].end - st.scan[k].begin;
     const size_t bytes_per_block_x10 = ecs_bytes * 10 / (g->coef_count / 64);
     const int many_segments = g->seg_count >= 30000;
-    ha.force_thread_per_segment = d->thread_per_segment || (many_segments && (bytes_per_block_x10 < 20 || bytes_per_block_x10 > 200));
+    /* interleaved scans: a walk that starts inside the stream also has to guess which component's block it is in, and a
+     * wrong guess does not heal by itself (other Huffman tables) -- exactness then spreads one lane per round; one thread
+     * per segment is faster at every size measured (8K 4:2:0: 150 us against 258, 4K: 108 / 170, HD: 97 / 99) */
+    ha.force_thread_per_segment = d->thread_per_segment || g->lay.interleaved ||
+                                  (many_segments && (bytes_per_block_x10 < 20 || bytes_per_block_x10 > 200));
     for ( int k = 0; k < g->scan_count; k++ ) {
         ha.first_rank[k] = first_rank[k];
         ha.scan_cbegin[k] = scan_cbegin[k];

@@ -605,7 +605,10 @@ __device__ __forceinline__ int scan_of_segment(const ScanSegs& S, int g)
  * own base itself: it publishes the bytes of its 32 segments at once and adds up what the CTAs before it have published.
  * Deterministic order (the reference's atomicAdd compaction is not).  Eight lanes per segment (a segment of photographic
  * content is ~140 bytes). */
-constexpr int CP_LANES = 8;                       // lanes per segment
+#ifndef GJ_CP_LANES
+#define GJ_CP_LANES 8
+#endif
+constexpr int CP_LANES = GJ_CP_LANES;             // lanes per segment
 constexpr int CP_SEGS = 256 / CP_LANES;           // segments per CTA
 #define PL_VALID (1ull << 62)
 #define PL_VALUE ((1ull << 62) - 1ull)
@@ -630,14 +633,25 @@ k_huff_place(const uint8_t* __restrict__ tmp, size_t slot_stride, const uint32_t
     if ( sl == 0 ) s_excl[ls] = v;
     __syncthreads();
     if ( warp == 0 ) {
-        const uint32_t mine = s_excl[lane];
+        constexpr int R = CP_SEGS / 32;   // segments per lane of this scan
+        uint32_t part[R], mine = 0;
+#pragma unroll
+        for ( int r = 0; r < R; r++ ) {
+            part[r] = s_excl[lane * R + r];
+            mine += part[r];
+        }
         uint32_t incl = mine;
 #pragma unroll
         for ( int d = 1; d < 32; d <<= 1 ) {
             const uint32_t t = __shfl_up_sync(FULL, incl, d);
             if ( lane >= d ) incl += t;
         }
-        s_excl[lane] = incl - mine;
+        uint32_t run = incl - mine;
+#pragma unroll
+        for ( int r = 0; r < R; r++ ) {
+            s_excl[lane * R + r] = run;
+            run += part[r];
+        }
         if ( lane == 31 ) {
             status[tile] = PL_VALID | (unsigned long long)incl;
             s_own = incl;

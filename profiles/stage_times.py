@@ -11,7 +11,9 @@ dev = torch.device("cuda", 0)
 d_raw = torch.from_numpy(img).to(dev)
 stream = torch.cuda.current_stream().cuda_stream
 enc = g.Encoder(stream=stream, pinned_output=True)
-jpeg = enc.encode(d_raw, Q, rst, 0)
+SS = os.environ.get("GJ_SS", "4:4:4"); IL = int(os.environ.get("GJ_IL", "0"))
+if "GJ_RST" in os.environ: rst = int(os.environ["GJ_RST"])
+jpeg = enc.encode(d_raw, Q, rst, IL, subsampling=SS)
 h_jpeg = torch.from_numpy(jpeg).pin_memory()
 d_out = torch.empty((h, w, 3), dtype=torch.uint8, device=dev)
 def timeit(fn, n=20):

@@ -137,6 +137,37 @@ def test_subsampled_decode_bit_exact(gj, dec, kind, w, h, q, rst, name, sampling
     assert got.shape == want.shape and np.array_equal(got, want), "decoded pixels differ from the oracle (int IDCT)"
 
 
+K3_CONFIGS = ["1", "2", "4", "8", "16", "32", "16,8,8", "thread_per_segment"]
+K3_STREAMS = [  # kind, w, h, quality, rst, interleaved, sampling
+    ("photo", 640, 360, 75, 12, 0, (1, 1)),      # sparse blocks: heads staged, tails written through
+    ("random", 333, 177, 92, 5, 0, (1, 1)),      # dense blocks: whole blocks staged when two segments share a warp
+    ("photo", 640, 368, 75, 6, 1, (2, 2)),       # interleaved 4:2:0 (one thread per segment by default: the lanes are forced here)
+    ("random", 200, 120, 85, 3, 1, (1, 1)),      # interleaved 4:4:4, dense
+    ("photo", 1024, 512, 75, 1, 0, (1, 1)),      # 24 576 one-block segments: more units than resident warps
+]
+
+
+@pytest.mark.parametrize("config", K3_CONFIGS)
+@pytest.mark.parametrize("kind,w,h,q,rst,il,sampling", K3_STREAMS)
+def test_every_huffman_decoder_configuration_gives_the_oracle_picture(gj, kind, w, h, q, rst, il, sampling, config):
+    """The Huffman decoder picks a kernel and the lanes per restart segment from the frame's shape; every choice it can
+    make (and the ones only `dec_opt_huffman*` can force) must decode the same coefficients and pixels."""
+    jpeg = o.encode(o.gen_image(kind, w, h), q, rst, il, threads=4, sampling=sampling)
+    want, want_coef = o.decode(jpeg, o.IDCT_INT, want_coef=True, threads=4)
+    d = gj.Decoder()
+    try:
+        if config == "thread_per_segment":
+            d.set_option("dec_opt_huffman", config)
+        else:
+            d.set_option("dec_opt_huffman_lanes", config)
+        got = d.decode(jpeg)
+        got_coef, deq = d.coefficients(w, h, sampling, il)
+        assert np.array_equal(got_coef, dequantized(want_coef, q, w, h, sampling, il) if deq else want_coef), "K3 differs"
+        assert np.array_equal(got, want)
+    finally:
+        d.close()
+
+
 @pytest.mark.parametrize("name,sampling", SS_MODES)
 def test_subsampled_decode_float_flavour(gj, name, sampling):
     jpeg = o.encode(o.gen_image("photo", 333, 77), 85, 6, 1, sampling=sampling)
