@@ -220,23 +220,12 @@ __device__ __forceinline__ uint32_t win_peek(Window& w, uint32_t q)
     return __funnelshift_l(w.lo, w.hi, sh);
 }
 
-/* Where a walk reads the stream from.  Shared memory (the unit's segments were staged there with coalesced loads): two
- * loads and a funnel shift per symbol, nothing carried between symbols.  Global memory (units larger than the staging
- * area): the register window above.  Measured (r2_i): with the window alone every symbol waited for a global load --
- * the scoreboard tracks registers per WARP, so the refill one lane issued is a dependency for the refill another lane
+/* Where the generic walks (units larger than the staging area, resynchronised streams) read the stream from: global
+ * memory through the register window above; the walks on the staged stream are walk_state_sm / walk_write_sm below.
+ * Measured (r2_i): with the window alone every symbol waited for a global load -- the scoreboard tracks registers per WARP, so the refill one lane issued is a dependency for the refill another lane
  * does one iteration later; 86 us for a state-only walk of an 8K frame, ~480 cycles per symbol. */
 template <bool SM>
 struct Src;
-template <>
-struct Src<true> {
-    const uint32_t* base;
-    __device__ __forceinline__ void init(const Walk& W, uint32_t) { base = W.sw; }
-    __device__ __forceinline__ uint32_t peek(uint32_t q)
-    {
-        const uint32_t* p = base + (q >> 5);
-        return __funnelshift_l(p[1], p[0], q & 31u);
-    }
-};
 template <>
 struct Src<false> {
     Window w;
@@ -374,9 +363,9 @@ __device__ __forceinline__ uint32_t walk_state_sm(const Walk& W, uint32_t st, ui
  *             into it.  (Everything stored straight -- r2_o: 141 us, of which 21 us the scattered 2-byte stores of the AC
  *             values and 11 us those of the DC values: a warp's store to 20-odd different lines occupies the memory
  *             pipe 20-odd times as long as a shared-memory store, and the walks' table lookups queue behind it.)
- *   M_SOLO    one lane = one whole segment: the lane zero-fills a block when it starts it and keeps the DC
- *             predictors itself -- nothing to do afterwards */
-enum { M_STAGED = 0, M_SPLIT = 1, M_SOLO = 2 };
+ * (One lane per segment was a third mode until r2_r: 242 us at 8K against 174 for k_huff_decode, which is built for that
+ * decomposition -- a request for one lane now goes there.) */
+enum { M_STAGED = 0, M_SPLIT = 1 };
 template <int MODE>
 struct StageStride { static constexpr int value = MODE == M_STAGED ? 64 : SD_HEAD; };   // staged coefficients per block
 
@@ -389,7 +378,7 @@ __device__ __forceinline__ void walk_write(const Walk& W, uint32_t st, uint32_t 
 {
     uint32_t k = (st >> 18) & 127u, c = st >> 25;
     const uint32_t p = st & 0x3FFFFu;
-    if ( n >= nblocks || (MODE != M_SOLO && p >= p_end) ) return;
+    if ( n >= nblocks || p >= p_end ) return;
     uint32_t q = W.bit0 + p;
     const uint32_t q_end = W.bit0 + p_end;
     Src<SM> src;
@@ -397,19 +386,11 @@ __device__ __forceinline__ void walk_write(const Walk& W, uint32_t st, uint32_t 
     uint32_t ci = IL ? (W.cimap >> (2 * c)) & 3u : 0u;
     const SdTable* t_dc = W.tab + 2u * ci;
     const uint16_t* qt = W.q + 64u * ci;
-    int pred0 = 0, pred1 = 0, pred2 = 0, pred3 = 0;   // M_SOLO: DC predictors by component in scan
     constexpr int SS = StageStride<MODE>::value;
     auto block_at = [&](int nn) -> int16_t* { return MODE == M_STAGED ? stage + (size_t)nn * 64 : !IL ? glob + (size_t)nn * 64 : coef + (size_t)tgt[nn] * 64; };
     int16_t* o = block_at(n);
     int16_t* so = stage + (size_t)n * SS;   // M_SPLIT: the block's head in the staging area
-    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-    if ( MODE == M_SOLO ) {
-#pragma unroll
-        for ( int i = 0; i < 8; i++ )
-            reinterpret_cast<uint4*>(o)[i] = z4;
-    }
-    for ( ;; ) {
-        if ( MODE != M_SOLO && q >= q_end ) break;   // a solo lane ends with its last block, wherever the bits end
+    while ( q < q_end ) {
         const uint32_t win = src.peek(q);
         const SdTable* T = k ? t_dc + 1 : t_dc;
         const uint32_t e = lookup(T, win, k != 0);
@@ -420,14 +401,7 @@ __device__ __forceinline__ void walk_write(const Walk& W, uint32_t st, uint32_t 
         int v = (int)bits - (int)(neg ? (1u << size) - 1u : 0u);
         const uint32_t idx = k + kadv - 1u;                                      // DC: 0
         if ( k == 0u ) {
-            if ( MODE == M_SOLO ) {
-                if ( !IL || ci == 0 ) v = (pred0 += v);
-                else if ( ci == 1 ) v = (pred1 += v);
-                else if ( ci == 2 ) v = (pred2 += v);
-                else v = (pred3 += v);
-                o[0] = (int16_t)(DEQ ? v * (int)qt[0] : v);
-            }
-            else so[0] = (int16_t)v;
+            so[0] = (int16_t)v;
         }
         else if ( size && idx < 64u ) {
             const int16_t dv = (int16_t)(DEQ ? v * (int)qt[idx] : v);
@@ -447,21 +421,6 @@ __device__ __forceinline__ void walk_write(const Walk& W, uint32_t st, uint32_t 
             }
             o = block_at(n);
             so = stage + (size_t)n * SS;
-            if ( MODE == M_SOLO ) {
-#pragma unroll
-                for ( int i = 0; i < 8; i++ )
-                    reinterpret_cast<uint4*>(o)[i] = z4;
-            }
-        }
-        if ( MODE == M_SOLO && q >= q_end + 64u ) {
-            /* the segment's bits are used up before its blocks are (damaged stream): the remaining blocks are zero */
-            while ( ++n < nblocks ) {
-                o = block_at(n);
-#pragma unroll
-                for ( int i = 0; i < 8; i++ )
-                    reinterpret_cast<uint4*>(o)[i] = z4;
-            }
-            break;
         }
     }
 }
@@ -559,7 +518,7 @@ __device__ __forceinline__ void run_units(const SdParams& P, const int scan, con
     const gj_scan_layout& L = P.lay;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int ncomp = IL ? L.comp_count : 1;
-    const int lanes_log2 = MODE == M_SOLO ? 0 : P.lanes_log2[scan], lanes = 1 << lanes_log2;
+    const int lanes_log2 = P.lanes_log2[scan], lanes = 1 << lanes_log2;
     const int spu = 32 >> lanes_log2;                  // segments per unit (= per warp round)
     const int slot = lane >> lanes_log2, gl = lane & (lanes - 1);
     const int segblk = P.seg_mcu * L.bpm;
@@ -576,7 +535,7 @@ __device__ __forceinline__ void run_units(const SdParams& P, const int scan, con
     }
     uint32_t* const tgt = s_tgt + slot * segblk;       // IL only
     constexpr int SS = StageStride<MODE>::value;
-    int16_t* const seg_stage = s_stage + (size_t)slot * segblk * SS;   // the segment's staged blocks (not M_SOLO)
+    int16_t* const seg_stage = s_stage + (size_t)slot * segblk * SS;   // the segment's staged blocks
 
     for ( ;; ) {
         if ( unit >= scan_units ) break;   // warp-uniform
@@ -645,10 +604,6 @@ __device__ __forceinline__ void run_units(const SdParams& P, const int scan, con
 
         auto body = [&](auto sm_tag) {
             constexpr bool SM = decltype(sm_tag)::value;
-            if ( MODE == M_SOLO ) {
-                if ( valid ) walk_write<DEQ, IL, M_SOLO, SM>(W, make_state(0, 0, 0), bits_all, 0, nblocks, tgt, seg_stage, seg_glob, P.coef);
-                return;
-            }
             if ( MODE == M_SPLIT ) {
                 /* zero the part of every block that is not staged: uint4 number 2..7 of its eight.  Four stores per round
                  * with addresses of their own: a store holds its address registers until the memory pipe has taken it
@@ -714,17 +669,13 @@ __device__ __forceinline__ void run_units(const SdParams& P, const int scan, con
 
             /* ---- the walk that writes ---- */
             if ( active ) {
-                if constexpr ( SM ) walk_write_sm<DEQ, IL, MODE == M_SOLO ? M_SPLIT : MODE>(W, start, p_end, n0, nblocks, tgt, seg_stage, seg_glob, P.coef);
+                if constexpr ( SM ) walk_write_sm<DEQ, IL, MODE>(W, start, p_end, n0, nblocks, tgt, seg_stage, seg_glob, P.coef);
                 else walk_write<DEQ, IL, MODE, false>(W, start, p_end, n0, nblocks, tgt, seg_stage, seg_glob, P.coef);
             }
         };
         if ( fits ) body(std::true_type{});
         else body(std::false_type{});
         __syncwarp();
-        if ( MODE == M_SOLO ) {   // (the barrier above also protects tgt / the staged bytes for the next unit)
-            unit = __shfl_sync(FULL, next_unit, 0);
-            continue;
-        }
 
         /* ---- DC: prefix sum of the differences per component [ref: src/gpujpeg_huffman_cpu_decoder.c:259-268];
          *      every lane takes a run of consecutive blocks ---- */
@@ -884,15 +835,13 @@ k_huff_decode_sync(const __grid_constant__ SdParams P)
         s_q[i] = P.tables->qinv_zz[P.scan_tq[scan][i >> 6]][i & 63];
     __syncthreads();
 
-    const int mode = P.lanes_log2[scan] == 0 ? M_SOLO : P.staged[scan] ? M_STAGED : M_SPLIT;
+    const int mode = P.staged[scan] ? M_STAGED : M_SPLIT;
     if ( L.interleaved ) {
-        if ( mode == M_SOLO ) run_units<DEQ, true, M_SOLO>(P, scan, round == 0, W, s_tgt, s_stage, s_cmp);
-        else if ( mode == M_STAGED ) run_units<DEQ, true, M_STAGED>(P, scan, round == 0, W, s_tgt, s_stage, s_cmp);
+        if ( mode == M_STAGED ) run_units<DEQ, true, M_STAGED>(P, scan, round == 0, W, s_tgt, s_stage, s_cmp);
         else run_units<DEQ, true, M_SPLIT>(P, scan, round == 0, W, s_tgt, s_stage, s_cmp);
     }
     else {
-        if ( mode == M_SOLO ) run_units<DEQ, false, M_SOLO>(P, scan, round == 0, W, s_tgt, s_stage, s_cmp);
-        else if ( mode == M_STAGED ) run_units<DEQ, false, M_STAGED>(P, scan, round == 0, W, s_tgt, s_stage, s_cmp);
+        if ( mode == M_STAGED ) run_units<DEQ, false, M_STAGED>(P, scan, round == 0, W, s_tgt, s_stage, s_cmp);
         else run_units<DEQ, false, M_SPLIT>(P, scan, round == 0, W, s_tgt, s_stage, s_cmp);
     }
     }   // scans
@@ -918,7 +867,7 @@ extern "C" int gj_huffman_decode_sync_eligible(const struct gj_huff_dec_args* a)
     if ( !a->d_clean || !a->d_list_cpos || !a->d_unit_ctr || a->seg_mcu * a->lay.bpm > SD_MAXBLK ) return 0;
     for ( int s = 0; s < a->lay.scan_count; s++ ) {
         const int n = a->scan_lanes[s];
-        if ( n < 1 || n > 32 || (n & (n - 1)) ) return 0;
+        if ( n < 2 || n > 32 || (n & (n - 1)) ) return 0;   // (one lane per segment: k_huff_decode)
     }
     return 1;
 }
@@ -963,7 +912,7 @@ extern "C" int gj_launch_huffman_decode_sync(const struct gj_huff_dec_args* a, g
         const size_t want = 2 * ((size_t)a->scan_bytes[s] / (size_t)(segs > 0 ? segs : 1) + 16) * (size_t)spu + 64;
         if ( want > cmp_bytes ) cmp_bytes = want;
         if ( a->lay.interleaved && spu > max_spu_tgt ) max_spu_tgt = spu;
-        if ( l2 > 0 ) {   // staged coefficients of a unit's segments: whole blocks, or their first SD_HEAD coefficients
+        {   // staged coefficients of a unit's segments: whole blocks, or their first SD_HEAD coefficients
             const size_t sb = (size_t)spu * segblk * (P.staged[s] ? 128 : SD_HEAD * 2);
             if ( sb > stage_bytes ) stage_bytes = sb;
         }

@@ -161,8 +161,11 @@ def test_every_huffman_decoder_configuration_gives_the_oracle_picture(gj, kind, 
         else:
             d.set_option("dec_opt_huffman_lanes", config)
         got = d.decode(jpeg)
-        got_coef, deq = d.coefficients(w, h, sampling, il)
-        assert np.array_equal(got_coef, dequantized(want_coef, q, w, h, sampling, il) if deq else want_coef), "K3 differs"
+        if sampling == (1, 1):
+            assert np.array_equal(*decoded_coefficients(d, w, h, q, want_coef)), "K3 differs"
+        else:
+            got_coef, deq = d.coefficients(w, h, sampling, il)
+            assert np.array_equal(got_coef, dequantized(want_coef, q, w, h, sampling, il) if deq else want_coef), "K3 differs"
         assert np.array_equal(got, want)
     finally:
         d.close()
