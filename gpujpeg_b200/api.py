@@ -209,12 +209,13 @@ class Encoder:
         return out.value, size.value
 
     def encode(self, image, quality=75, restart_interval=RESTART_AUTO, interleaved=0, width=None, height=None,
-               width_padding=0, verbose=0, subsampling="4:4:4"):
+               width_padding=0, verbose=0, subsampling="4:4:4", segment_info=0):
         """image: HxWx3 uint8 numpy array / torch tensor (host or cuda).  Returns the JPEG as numpy uint8 (a copy)."""
         if width is None:
             height, width = image.shape[0], image.shape[1]
         p = default_parameters(quality, restart_interval, interleaved, subsampling)
         p.verbose = verbose
+        p.segment_info = segment_info
         addr, size = self.encode_raw(image, p, image_parameters(width, height, width_padding))
         return np.ctypeslib.as_array((C.c_uint8 * size).from_address(addr)).copy()
 

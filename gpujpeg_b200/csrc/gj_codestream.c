@@ -209,6 +209,7 @@ int gj_geometry_init(struct gj_geometry* g, const struct gpujpeg_parameters* par
     g->slot_stride = ((size_t)g->seg_mcu * (g->interleaved ? l->bpm : 1) * 416 + 2 + 127) / 128 * 128;
     /* same budget as the reference's output buffer [ref: src/gpujpeg_writer.c:63-89] */
     g->stream_cap = 4096 + (size_t)pi->width * pi->height * g->comp_count * 2;
+    if ( param->segment_info ) g->stream_cap += ((size_t)g->seg_count + GJ_MAX_COMP) * 4 + 5 * ((size_t)g->seg_count * 4 / GJ_SEGINFO_CHUNK + 2 * GJ_MAX_COMP);
     return 0;
 }
 
@@ -378,6 +379,34 @@ size_t gj_write_sos(uint8_t* out, const struct gpujpeg_parameters* param, int sc
     p = w8(p, 0x3F);
     p = w8(p, 0);
     return (size_t)(p - out);
+}
+
+/* [ref: src/gpujpeg_writer.c:553-599] one APP13 header per GJ_SEGINFO_CHUNK bytes of the (segment_count + 1) 32-bit
+ * positions: FF ED, length = 3 + bytes, scan index, bytes */
+size_t gj_write_segment_info_headers(uint8_t* out, int scan_index, int segment_count)
+{
+    size_t n = 0;
+    long data = ((long)segment_count + 1) * 4;
+    while ( data > 0 ) {
+        const long chunk = data > GJ_SEGINFO_CHUNK ? GJ_SEGINFO_CHUNK : data;
+        data -= chunk;
+        if ( out ) {
+            uint8_t* p = out + n;
+            p = wmark(p, 0xED);
+            p = w16(p, (int)(3 + chunk));
+            p = w8(p, scan_index);
+            memset(p, 0, (size_t)chunk);
+        }
+        n += 5 + (size_t)chunk;
+    }
+    return n;
+}
+
+/* [ref: src/gpujpeg_writer.c:532-541] */
+size_t gj_segment_info_entry_offset(int index)
+{
+    const long b = (long)index * 4;
+    return (size_t)(b / GJ_SEGINFO_CHUNK) * (5 + GJ_SEGINFO_CHUNK) + 5 + (size_t)(b % GJ_SEGINFO_CHUNK);
 }
 
 /* ------------------------------------------------------------------------------------------- */

@@ -58,14 +58,17 @@ struct gpujpeg_encoder {
     uint32_t* d_spill; size_t d_spill_size;
     uint32_t* d_seg_bytes; uint64_t* d_seg_off; int seg_alloc;
     uint8_t* d_stream; size_t d_stream_size;
-    uint8_t* d_sos;
+    uint8_t* d_sos; size_t d_sos_size;        /* per scan: [APP13 segment-info headers] SOS header */
+    uint8_t* h_pre; size_t h_pre_size;         /* the same on the host */
+    int pre_len[GJ_MAX_COMP], pre_off[GJ_MAX_COMP];
+    int with_segment_info;                     /* param.segment_info && restart_interval > 0 [ref: src/gpujpeg_writer.c:553] */
+    uint64_t* d_seg_pos; uint64_t* h_seg_pos; size_t seg_pos_size;   /* segment info: stream offset of every segment (pinned copy) */
     uint64_t* d_info;
     uint64_t* h_info;                          /* pinned */
 
     /* host output */
     uint8_t* out; size_t out_size; int out_is_pinned;
     uint8_t header[1024]; size_t header_size;
-    uint8_t sos[GJ_MAX_COMP][16]; int sos_len;
 
     /* timers [ref: src/gpujpeg_common_internal.h:414-422] */
     struct gj_timer t_to, t_from, t_pre, t_huff, t_gpu;
@@ -133,7 +136,7 @@ struct gpujpeg_encoder* gpujpeg_encoder_create(cudaStream_t stream)
     for ( int t = 0; t < 2; t++ )
         gj_enc_lut_build(&e->spec[t][0], &e->spec[t][1], &e->h_tab.lut[t]);
     if ( gj_cuda_malloc((void**)&e->d_tab, sizeof *e->d_tab) || gj_cuda_malloc((void**)&e->d_info, 64) ||
-         gj_cuda_malloc((void**)&e->d_sos, 64) || gj_cuda_malloc_host((void**)&e->h_info, 64) ) {
+         gj_cuda_malloc_host((void**)&e->h_info, 64) ) {
         GJ_ERR("Encoder allocation failed: %s\n", gj_cuda_last_error());
         gpujpeg_encoder_destroy(e);
         return NULL;
@@ -149,6 +152,9 @@ int gpujpeg_encoder_destroy(struct gpujpeg_encoder* e)
     gj_cuda_free(e->d_tab);
     gj_cuda_free(e->d_info);
     gj_cuda_free(e->d_sos);
+    free(e->h_pre);
+    gj_cuda_free(e->d_seg_pos);
+    if ( e->h_seg_pos ) gj_cuda_free_host(e->h_seg_pos);
     gj_cuda_free_host(e->h_info);
     gj_cuda_free(e->d_raw);
     gj_cuda_free(e->d_coef);
@@ -215,10 +221,6 @@ static int params_supported(const struct gpujpeg_parameters* p, const struct gpu
     }
     if ( p->restart_interval < 0 || p->restart_interval > 65535 ) {
         GJ_ERR("Restart interval %d cannot be stored in a DRI marker.\n", p->restart_interval);
-        return GJ_IN_UNSUPPORTED;
-    }
-    if ( p->segment_info ) {
-        GJ_ERR("segment_info headers are not implemented in this build.\n");
         return GJ_IN_UNSUPPORTED;
     }
     /* YCbCr JPEG (JFIF header), RGB (Adobe APP14 header, every component coded with the luminance tables), or the
@@ -332,7 +334,11 @@ static void fill_huff_args(const struct gpujpeg_encoder* e, struct gj_huff_enc_a
     ha->stream_cap = g->stream_cap;
     ha->header_size = (uint32_t)e->header_size;
     ha->d_sos = e->d_sos;
-    ha->sos_len = e->sos_len;
+    for ( int s = 0; s < GJ_MAX_COMP; s++ ) {
+        ha->pre_len[s] = e->pre_len[s];
+        ha->pre_off[s] = e->pre_off[s];
+    }
+    ha->d_seg_pos = e->with_segment_info ? e->d_seg_pos : NULL;
     ha->d_info = e->d_info;
     ha->d_tables = e->d_tab;
 }
@@ -556,14 +562,51 @@ int gpujpeg_encoder_encode(struct gpujpeg_encoder* e, const struct gpujpeg_param
         e->header_written = e->header_type;
         /* host codestream writer: file header + SOS headers, composed once per parameter change */
         e->header_size = gj_write_header(e->header, &e->param, &e->param_image, e->raw_q, e->spec, e->header_type);
-        uint8_t sos_flat[GJ_MAX_COMP * 16];
-        e->sos_len = 0;
+        /* what precedes every scan's data: [APP13 segment-info headers, positions filled in after the frame is coded] SOS */
+        e->with_segment_info = e->param.segment_info && e->param.restart_interval > 0;
+        size_t pre_total = 0;
+        for ( int s = 0; s < GJ_MAX_COMP; s++ ) {
+            e->pre_off[s] = (int)pre_total;
+            e->pre_len[s] = 0;
+            if ( s >= g->scan_count ) continue;
+            const int segs = g->lay.scan_seg_begin[s + 1] - g->lay.scan_seg_begin[s];
+            e->pre_len[s] = (int)((e->with_segment_info ? gj_write_segment_info_headers(NULL, s, segs) : 0) + 16);
+            pre_total += (size_t)e->pre_len[s];
+        }
+        if ( pre_total > e->h_pre_size ) {
+            free(e->h_pre);
+            e->h_pre = (uint8_t*)malloc(pre_total);
+            e->h_pre_size = e->h_pre ? pre_total : 0;
+        }
+        if ( !e->h_pre || grow((void**)&e->d_sos, &e->d_sos_size, pre_total) ) {
+            GJ_ERR("Encoder scan header allocation failed (%zu bytes).\n", pre_total);
+            return GPUJPEG_ERROR;
+        }
+        pre_total = 0;
         for ( int s = 0; s < g->scan_count; s++ ) {
-            e->sos_len = (int)gj_write_sos(e->sos[s], &e->param, s);
-            memcpy(sos_flat + s * e->sos_len, e->sos[s], (size_t)e->sos_len);
+            const int segs = g->lay.scan_seg_begin[s + 1] - g->lay.scan_seg_begin[s];
+            uint8_t* p = e->h_pre + pre_total;
+            size_t n = e->with_segment_info ? gj_write_segment_info_headers(p, s, segs) : 0;
+            n += gj_write_sos(p + n, &e->param, s);
+            e->pre_off[s] = (int)pre_total;
+            e->pre_len[s] = (int)n;
+            pre_total += n;
+        }
+        if ( e->with_segment_info && (size_t)g->seg_count * 8 > e->seg_pos_size ) {
+            gj_cuda_free(e->d_seg_pos);
+            if ( e->h_seg_pos ) gj_cuda_free_host(e->h_seg_pos);
+            e->d_seg_pos = NULL;
+            e->h_seg_pos = NULL;
+            e->seg_pos_size = 0;
+            if ( gj_cuda_malloc((void**)&e->d_seg_pos, (size_t)g->seg_count * 8) ||
+                 gj_cuda_malloc_host((void**)&e->h_seg_pos, (size_t)g->seg_count * 8) ) {
+                GJ_ERR("Encoder segment info allocation failed: %s\n", gj_cuda_last_error());
+                return GPUJPEG_ERROR;
+            }
+            e->seg_pos_size = (size_t)g->seg_count * 8;
         }
         if ( gj_cuda_memcpy_h2d_async(e->d_tab, &e->h_tab, sizeof e->h_tab, e->stream) ||
-             gj_cuda_memcpy_h2d_async(e->d_sos, sos_flat, (size_t)g->scan_count * e->sos_len, e->stream) ||
+             gj_cuda_memcpy_h2d_async(e->d_sos, e->h_pre, pre_total, e->stream) ||
              gj_cuda_stream_sync(e->stream) ) {
             GJ_ERR("Encoder table upload failed: %s\n", gj_cuda_last_error());
             return GPUJPEG_ERROR;
@@ -668,7 +711,8 @@ int gpujpeg_encoder_encode(struct gpujpeg_encoder* e, const struct gpujpeg_param
         return GPUJPEG_ERROR;
     }
     if ( gj_cuda_memcpy_d2h_async(e->out + e->header_size, e->d_stream + e->header_size, total - e->header_size,
-                                  e->stream) ) {
+                                  e->stream) ||
+         (e->with_segment_info && gj_cuda_memcpy_d2h_async(e->h_seg_pos, e->d_seg_pos, (size_t)g->seg_count * 8, e->stream)) ) {
         GJ_ERR("Encoder copy of compressed data failed: %s\n", gj_cuda_last_error());
         return GPUJPEG_ERROR;
     }
@@ -679,6 +723,25 @@ int gpujpeg_encoder_encode(struct gpujpeg_encoder* e, const struct gpujpeg_param
     if ( gj_cuda_stream_sync(e->stream) ) {
         GJ_ERR("Encoder copy of compressed data failed: %s\n", gj_cuda_last_error());
         return GPUJPEG_ERROR;
+    }
+    if ( e->with_segment_info ) {
+        /* the APP13 tables in front of every scan: position of every segment relative to the scan's first byte, then the
+         * scan's end [ref: src/gpujpeg_writer.c:522-546, src/gpujpeg_encoder.c:575-621] */
+        for ( int s = 0; s < g->scan_count; s++ ) {
+            const int first = g->lay.scan_seg_begin[s], segs = g->lay.scan_seg_begin[s + 1] - first;
+            const uint64_t scan_start = e->h_seg_pos[first];
+            const uint64_t scan_end = s + 1 < g->scan_count ? e->h_seg_pos[g->lay.scan_seg_begin[s + 1]] - (uint64_t)e->pre_len[s + 1]
+                                                            : (uint64_t)total - 2;
+            uint8_t* table = e->out + scan_start - (uint64_t)e->pre_len[s];
+            for ( int i = 0; i <= segs; i++ ) {
+                const uint32_t pos = (uint32_t)((i < segs ? e->h_seg_pos[first + i] : scan_end) - scan_start);
+                uint8_t* q = table + gj_segment_info_entry_offset(i);
+                q[0] = (uint8_t)(pos >> 24);
+                q[1] = (uint8_t)(pos >> 16);
+                q[2] = (uint8_t)(pos >> 8);
+                q[3] = (uint8_t)pos;
+            }
+        }
     }
     *image_compressed = e->out;
     *image_compressed_size = total;

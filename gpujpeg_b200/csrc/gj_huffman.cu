@@ -592,6 +592,10 @@ k_huff_encode_packed(const int16_t* __restrict__ coef, const uint64_t* __restric
 struct ScanSegs {
     int begin[GJ_MAX_COMP + 1];
 };
+/* what precedes every scan's data ([APP13 segment-info headers] SOS header): length, and offset in the `sos` buffer */
+struct ScanPrefix {
+    int len[GJ_MAX_COMP], off[GJ_MAX_COMP];
+};
 __device__ __forceinline__ int scan_of_segment(const ScanSegs& S, int g)
 {
     return (g >= S.begin[1]) + (g >= S.begin[2]) + (g >= S.begin[3]);
@@ -614,8 +618,9 @@ constexpr int CP_SEGS = 256 / CP_LANES;           // segments per CTA
 #define PL_VALUE ((1ull << 62) - 1ull)
 __global__ void __launch_bounds__(256)
 k_huff_place(const uint8_t* __restrict__ tmp, size_t slot_stride, const uint32_t* __restrict__ seg_bytes, int seg_count,
-             const __grid_constant__ ScanSegs segs, const uint8_t* __restrict__ sos, int sos_len, uint32_t header_size,
-             uint64_t stream_cap, uint8_t* __restrict__ stream, volatile unsigned long long* status /* zeroed by the encoder kernel */,
+             const __grid_constant__ ScanSegs segs, const uint8_t* __restrict__ sos, const __grid_constant__ ScanPrefix pre,
+             uint32_t header_size, uint64_t stream_cap, uint8_t* __restrict__ stream,
+             volatile unsigned long long* status /* zeroed by the encoder kernel */, uint64_t* __restrict__ seg_pos /* or NULL */,
              uint64_t* __restrict__ info)
 {
     __shared__ uint32_t s_excl[CP_SEGS];
@@ -629,7 +634,8 @@ k_huff_place(const uint8_t* __restrict__ tmp, size_t slot_stride, const uint32_t
     const int scan = valid ? scan_of_segment(segs, g) : 0, s = g - segs.begin[scan];
     const bool first_of_scan = valid && s == 0, last_of_scan = valid && g + 1 == segs.begin[scan + 1];
     const uint32_t n = valid ? __ldg(seg_bytes + g) : 0u;
-    const uint32_t v = valid ? n + (first_of_scan ? (uint32_t)sos_len : 0u) + (last_of_scan ? 0u : 2u) : 0u;
+    const uint32_t sos_len = first_of_scan ? (uint32_t)pre.len[scan] : 0u;
+    const uint32_t v = valid ? n + sos_len + (last_of_scan ? 0u : 2u) : 0u;
     if ( sl == 0 ) s_excl[ls] = v;
     __syncthreads();
     if ( warp == 0 ) {
@@ -682,10 +688,24 @@ k_huff_place(const uint8_t* __restrict__ tmp, size_t slot_stride, const uint32_t
         info[0] = total;
         info[1] = (info[1] & 2ull) | (total > stream_cap ? 1ull : 0ull);   // bit 1: a segment slot overflowed (set by the encoder)
     }
-    if ( !valid || (info[1] & 2ull) ) return;   // slots too small: their contents are truncated, the host encodes again
+    if ( info[1] & 2ull ) return;   // slots too small: their contents are truncated, the host encodes again
+    /* what precedes the data of a scan that starts in this tile ([APP13 segment-info headers] SOS header; with segment
+     * info tens of kilobytes): the whole CTA copies it */
+#pragma unroll
+    for ( int k = 0; k < GJ_MAX_COMP; k++ ) {
+        const int g0 = segs.begin[k] - (int)blockIdx.x * CP_SEGS;
+        if ( g0 < 0 || g0 >= CP_SEGS || segs.begin[k] >= seg_count || segs.begin[k] >= segs.begin[k + 1] ) continue;
+        const uint64_t at = (uint64_t)header_size + base + s_excl[g0];
+        if ( at + (uint64_t)pre.len[k] > stream_cap ) continue;
+        const uint8_t* from = sos + pre.off[k];
+        for ( int q = threadIdx.x; q < pre.len[k]; q += 256 )
+            stream[at + q] = from[q];
+    }
+    if ( !valid ) return;
     /* the segment's bytes start after its SOS header (if any) */
-    const uint64_t off = (uint64_t)header_size + base + s_excl[ls] + (first_of_scan ? (uint32_t)sos_len : 0u);
+    const uint64_t off = (uint64_t)header_size + base + s_excl[ls] + sos_len;
     if ( off + n + 2u > stream_cap ) return;   // would overflow the stream buffer: the host reports the error (info[1] bit 0)
+    if ( seg_pos && sl == 0 ) seg_pos[g] = off;
     const uint8_t* src = tmp + (size_t)g * slot_stride;
     uint8_t* dst = stream + off;
     /* head bytes up to 16-byte alignment of dst, then 16 B stores assembled from 4 B loads */
@@ -722,9 +742,6 @@ k_huff_place(const uint8_t* __restrict__ tmp, size_t slot_stride, const uint32_t
             dst[n + 1] = 0xD9;
         }
     }
-    if ( s == 0 )
-        for ( int q = sl; q < sos_len; q += CP_LANES )
-            (dst - sos_len)[q] = sos[scan * sos_len + q];
 }
 
 /* =========================================================================================== */
@@ -1052,8 +1069,13 @@ extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_str
             a->d_coef, a->d_nzmask, a->lay, a->seg_mcu, seg_count, a->d_tmp, a->slot_stride, a->d_seg_bytes, a->d_spill,
             a->d_tables, a->d_info, place_status, n_status);
     }
-    k_huff_place<<<n_status, 256, 0, stream>>>(a->d_tmp, a->slot_stride, a->d_seg_bytes, seg_count, segs, a->d_sos, a->sos_len,
-                                               a->header_size, (uint64_t)a->stream_cap, a->d_stream, place_status, a->d_info);
+    ScanPrefix pre;
+    for ( int k = 0; k < GJ_MAX_COMP; k++ ) {
+        pre.len[k] = a->pre_len[k];
+        pre.off[k] = a->pre_off[k];
+    }
+    k_huff_place<<<n_status, 256, 0, stream>>>(a->d_tmp, a->slot_stride, a->d_seg_bytes, seg_count, segs, a->d_sos, pre, a->header_size,
+                                               (uint64_t)a->stream_cap, a->d_stream, place_status, a->d_seg_pos, a->d_info);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

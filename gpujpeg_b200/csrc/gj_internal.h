@@ -179,6 +179,11 @@ size_t gj_write_header(uint8_t* out, const struct gpujpeg_parameters* param,
                        const struct gpujpeg_image_parameters* param_image, const uint8_t raw_q[2][64],
                        const struct gj_huff_spec spec[2][2], enum gpujpeg_header_type header_type);
 size_t gj_write_sos(uint8_t* out, const struct gpujpeg_parameters* param, int scan_index);
+/* APP13 "segment info" headers of a scan (the positions left zero) [ref: src/gpujpeg_writer.c:553-599]; out == NULL: size only */
+#define GJ_SEGINFO_CHUNK (65536 - 100)   /* position bytes per header [ref: src/gpujpeg_common_internal.h:91] */
+size_t gj_write_segment_info_headers(uint8_t* out, int scan_index, int segment_count);
+/* where position number `index` of a scan's table lies, relative to the first header's first byte */
+size_t gj_segment_info_entry_offset(int index);
 
 /* ---- codestream reader (gj_reader.c)  [ref: src/gpujpeg_reader.c] ---- */
 struct gj_scan_info {
@@ -253,8 +258,10 @@ struct gj_huff_enc_args {
     uint8_t* d_stream;
     size_t stream_cap;
     uint32_t header_size;
-    const uint8_t* d_sos;   /* scan_count SOS headers, sos_len bytes each */
-    int sos_len;
+    const uint8_t* d_sos;   /* what precedes every scan's data: [APP13 segment-info headers] SOS header; scan s: pre_len[s]
+                             * bytes at d_sos + pre_off[s] */
+    int pre_len[GJ_MAX_COMP], pre_off[GJ_MAX_COMP];
+    uint64_t* d_seg_pos;    /* [seg_count] or NULL: receives the stream offset of every segment's first byte (segment info) */
     uint64_t* d_info;       /* [4]: total, error, reserved */
     const struct gj_dev_enc_tables* d_tables;
 };

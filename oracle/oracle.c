@@ -758,6 +758,45 @@ size_t orc_write_header(uint8_t* out, int w, int h, int quality, int rst, int co
     return (size_t)(p - out);
 }
 
+/* "segment info": in front of every SOS the encoder can place APP13 headers holding the byte position of every restart
+ * segment inside the scan (and the scan's end), big-endian 32 bit, relative to the first byte behind the SOS header; a
+ * header carries at most 65436 bytes of positions, so long tables are cut into several headers
+ * [ref: src/gpujpeg_writer.c:553-599 (headers), :522-546 (positions), src/gpujpeg_encoder.c:575-621 (one position in
+ * front of every segment, one more behind the scan's last segment, whose RSTn is dropped)] */
+static int g_segment_info = 0;
+void orc_set_segment_info(int on) { g_segment_info = on; }
+#define ORC_MAX_HEADER_SIZE (65536 - 100)   /* [ref: src/gpujpeg_common_internal.h:91] */
+#define ORC_MAX_SEGINFO_HEADERS 256
+struct seginfo {
+    uint8_t* block[ORC_MAX_SEGINFO_HEADERS];
+    int count;
+};
+static uint8_t* write_segment_info_headers(uint8_t* p, int scan_index, int segment_count, struct seginfo* si)
+{
+    int data_size = (segment_count + 1) * 4;
+    si->count = 0;
+    while ( data_size > 0 && si->count < ORC_MAX_SEGINFO_HEADERS ) {
+        const int header_size = data_size > ORC_MAX_HEADER_SIZE ? ORC_MAX_HEADER_SIZE : data_size;
+        data_size -= header_size;
+        p = putm(p, 0xED);
+        p = put16(p, 3 + header_size);
+        p = put8(p, scan_index);
+        si->block[si->count++] = p;
+        memset(p, 0, (size_t)header_size);
+        p += header_size;
+    }
+    return p;
+}
+static void put_segment_position(struct seginfo* si, int index, size_t position)
+{
+    const int h = (index * 4) / ORC_MAX_HEADER_SIZE, d = (index * 4) % ORC_MAX_HEADER_SIZE;
+    if ( h >= si->count ) return;
+    si->block[h][d] = (uint8_t)(position >> 24);
+    si->block[h][d + 1] = (uint8_t)(position >> 16);
+    si->block[h][d + 2] = (uint8_t)(position >> 8);
+    si->block[h][d + 3] = (uint8_t)position;
+}
+
 /* scan header  [ref: src/gpujpeg_writer.c:600-658] */
 static uint8_t* write_sos(uint8_t* p, int interleaved, int comp_count, int scan_comp)
 {
@@ -847,13 +886,19 @@ size_t orc_encode_rgb(const uint8_t* rgb, int w, int h, int pad, int quality, in
         }
     }
     for ( int scan = 0; scan < nscan; scan++ ) {
+        struct seginfo info;
+        const int with_info = g_segment_info && rst > 0;
+        if ( with_info ) p = write_segment_info_headers(p, scan, nseg, &info);
         p = write_sos(p, interleaved, comps, scan);
+        const uint8_t* scan_start = p;
         for ( int s = 0; s < nseg; s++ ) {
             size_t si = (size_t)scan * nseg + s;
+            if ( with_info ) put_segment_position(&info, s, (size_t)(p - scan_start));
             memcpy(p, tmp + si * slot, seg_len[si]);
             p += seg_len[si];
             if ( s + 1 < nseg ) p = putm(p, 0xD0 + (s & 7));
         }
+        if ( with_info ) put_segment_position(&info, nseg, (size_t)(p - scan_start));
     }
     p = putm(p, 0xD9);
 #ifdef _OPENMP
@@ -1038,13 +1083,19 @@ static size_t encode_from_planes(const uint8_t* planes, const struct ogeo g[4], 
         }
     }
     for ( int scan = 0; scan < nscan; scan++ ) {
+        struct seginfo info;
+        const int with_info = g_segment_info && rst > 0;
+        if ( with_info ) p = write_segment_info_headers(p, scan, scan_seg[scan], &info);
         p = write_sos(p, interleaved, comps, scan);
+        const uint8_t* scan_start = p;
         for ( int s = 0; s < scan_seg[scan]; s++ ) {
             size_t si = (size_t)seg_begin[scan] + s;
+            if ( with_info ) put_segment_position(&info, s, (size_t)(p - scan_start));
             memcpy(p, tmp + si * slot, seg_len[si]);
             p += seg_len[si];
             if ( s + 1 < scan_seg[scan] ) p = putm(p, 0xD0 + (s & 7));
         }
+        if ( with_info ) put_segment_position(&info, scan_seg[scan], (size_t)(p - scan_start));
     }
     p = putm(p, 0xD9);
     return (size_t)(p - out);

@@ -117,7 +117,7 @@ def encode(rgb, quality=75, rst=24, interleaved=0, threads=1, want_coef=False, p
     component after component for subsampled modes)."""
     h, w = rgb.shape[:2]
     rgb = np.ascontiguousarray(rgb)
-    out = np.empty(1000 + w * h * 6 + 4096, np.uint8)
+    out = np.empty(1000 + w * h * 6 + 4096 + (w * h // 16 + 64) * (1 + _segment_info_on[0]), np.uint8)
     if tuple(sampling) == (1, 1):
         dw, dh = (w + 7) // 8 * 8, (h + 7) // 8 * 8
         coef = np.zeros((3, dw * dh), np.int16) if want_coef else None
@@ -234,12 +234,18 @@ def decode_any(jpeg, fmt, cs, flavour=IDCT_INT, threads=1):
 
 
 def stream_sampling(jpeg):
-    """(luma_h, luma_v) and interleaved flag read from SOF0 / the first SOS of a stream of this codec family."""
-    j = bytes(jpeg[:2048])
-    i = j.index(b"\xff\xc0")
-    hv = j[i + 2 + 8 + 1]
-    k = j.index(b"\xff\xda")
-    return (hv >> 4, hv & 15), int(j[k + 4] > 1)
+    """(luma_h, luma_v) and interleaved flag read from SOF0 / the first SOS of a stream of this codec family (walks the
+    marker segments: with segment info the first SOS can lie far behind the file header)."""
+    j, i, hv = bytes(jpeg), 2, 0x11
+    while i + 4 <= len(j):
+        assert j[i] == 0xFF
+        m, n = j[i + 1], (j[i + 2] << 8) | j[i + 3]
+        if m == 0xC0:
+            hv = j[i + 2 + 8 + 1]
+        if m == 0xDA:
+            return (hv >> 4, hv & 15), int(j[i + 4] > 1)
+        i += 2 + n
+    raise ValueError("no SOS marker")
 
 
 def decode(jpeg, flavour=IDCT_INT, threads=1, want_coef=False):
@@ -303,6 +309,23 @@ def remap_code(val):
     for ch in reversed(val):
         m = m << 4 | (4 if ch == "F" else 5 if ch == "Z" else int(ch))
     return m | len(val) << 24
+
+
+_segment_info_on = [0]
+
+
+class segment_info:
+    """with segment_info(): ... -- the oracle's encoders put the APP13 table of restart-segment positions in front of every
+    scan (struct gpujpeg_parameters.segment_info)"""
+
+    def __enter__(self):
+        lib.orc_set_segment_info.argtypes = [C.c_int]
+        lib.orc_set_segment_info(1)
+        _segment_info_on[0] = 1
+
+    def __exit__(self, *exc):
+        lib.orc_set_segment_info(0)
+        _segment_info_on[0] = 0
 
 
 class flip_remap:

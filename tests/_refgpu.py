@@ -141,13 +141,16 @@ def run(lib, a):
     """one command: a = [mode, arguments...] as on the command line; returns a JSON-able reply or None.
     Arguments of the form opt:<key>=<value> are passed to gpujpeg_{en,de}coder_set_option of the coder the command creates."""
     opts = [x[4:] for x in a if x.startswith("opt:")]
-    a = [x for x in a if not x.startswith("opt:")]
+    pars = dict(x[4:].split("=") for x in a if x.startswith("par:"))   # par:<field>=<int>: struct gpujpeg_parameters fields
+    a = [x for x in a if not x.startswith(("opt:", "par:"))]
     mode = a[0]
     if mode == "encode":
         kind, w, h, q, rst, il, path = a[1], *map(int, a[2:7]), a[7]
         img = gen(kind, w, h)
         enc = lib.gpujpeg_encoder_create(None)
         p, pi = params(lib, w, h, q, rst, il)
+        for k, v in pars.items():
+            setattr(p, k, int(v))
         if len(a) > 9:   # chroma subsampling: GPUJPEG_SUBSAMPLING_xxx packing, first component on top
             lib.gpujpeg_parameters_chroma_subsampling.argtypes = [C.POINTER(Param), C.c_uint32]
             lib.gpujpeg_parameters_chroma_subsampling(C.byref(p), int(a[8]) << 28 | int(a[9]) << 24 | 0x111100)

@@ -369,10 +369,6 @@ def test_unsupported_parameters_fail_loudly(gj, enc):
     p.color_space_internal = gj.api.GPUJPEG_YCBCR_BT709   # this pair is converted with the wrong matrix by the reference
     with pytest.raises(gj.GpuJpegError):
         enc.encode_raw(np.zeros((64, 64, 3), np.uint8), p, gj.api.image_parameters(64, 64, 0, 1, gj.api.GPUJPEG_YCBCR_BT601))
-    p = gj.api.default_parameters()
-    p.segment_info = 1
-    with pytest.raises(gj.GpuJpegError):
-        enc.encode_raw(np.zeros((64, 64, 3), np.uint8), p, gj.api.image_parameters(64, 64))
     with pytest.raises(gj.GpuJpegError):
         gj.Decoder().decode(np.zeros(100, np.uint8))
 

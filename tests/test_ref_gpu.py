@@ -251,3 +251,36 @@ def test_reference_gpu_flip_and_channel_remap(tmp_path, fmt, cs, w, h, flipped, 
         assert np.array_equal(d.decode_samples(ref)[0], pix), "product decode != reference GPU decoder"
     finally:
         d.close()
+
+
+@pytest.mark.skipif(not os.path.exists(SO), reason="oracle/_ref/libgpujpeg_refgpu.so not built")
+@pytest.mark.parametrize("kind,w,h,q,rst,il,name,sampling", [("photo", 640, 360, 75, 12, 0, "4:4:4", (1, 1)), ("random", 333, 177, 85, 3, 1, "4:4:4", (1, 1)),
+                                                             ("photo", 640, 368, 75, 4, 0, "4:2:0", (2, 2)),
+                                                             ("photo", 1024, 1032, 60, 1, 0, "4:4:4", (1, 1))])   # 16 512 segments per scan: two APP13 headers each
+def test_reference_gpu_segment_info(tmp_path, kind, w, h, q, rst, il, name, sampling):
+    """struct gpujpeg_parameters.segment_info: APP13 tables of the restart segments' positions in front of every scan
+    [ref: src/gpujpeg_writer.c:522-599]: reference GPU encoder bytes == oracle == product, and the reference decoder -- which
+    then splits the scans by the table instead of searching for markers, src/gpujpeg_reader.c:1168-1215 -- decodes the
+    product's stream to the same picture"""
+    path, mine, dst = tmp_path / "ref.jpg", tmp_path / "mine.jpg", tmp_path / "out.rgb"
+    extra = (sampling[0], sampling[1]) if sampling != (1, 1) else ()
+    run_ref("encode", kind, w, h, q, rst, il, path, *extra, "par:segment_info=1")
+    ref = np.fromfile(path, np.uint8)
+    img = o.gen_image(kind, w, h)
+    with o.segment_info():
+        want = o.encode(img, q, rst, il, threads=4, sampling=sampling)
+    plain = o.encode(img, q, rst, il, threads=4, sampling=sampling)
+    assert ref.size > plain.size
+    assert ref.size == want.size and np.array_equal(ref, want), "oracle restatement != reference GPU library output"
+    import gpujpeg_b200 as g
+    e = g.Encoder()
+    got = e.encode(img, q, rst, il, subsampling=name, segment_info=1)
+    assert got.size == ref.size and np.array_equal(got, ref), "product != reference GPU library output"
+    assert np.array_equal(e.encode(img, q, rst, il, subsampling=name), plain), "the same encoder without segment info afterwards"
+    e.close()
+    got.tofile(mine)
+    run_ref("decode", mine, dst)
+    pix = np.fromfile(dst, np.uint8).reshape(h, w, 3)
+    d = g.Decoder(idct="float_gpuref")
+    assert np.array_equal(d.decode(got), pix), "product decode != reference GPU decoder on a stream with segment info"
+    d.close()
