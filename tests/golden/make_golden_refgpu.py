@@ -4,7 +4,8 @@ seeded inputs.  The colour transform and the float forward DCT exist in the refe
 the one place their results can be taken from; the committed fixtures then pin oracle.c's restatement of that arithmetic
 in the GPU-less test run (tests/test_oracle_golden.py) -- no "the golden coefficients come from the oracle" caveat.
 
-    python tests/golden/make_golden_refgpu.py [outdir]        (default: gpurun_out/golden, which gpurun brings back)
+    python tests/golden/make_golden_refgpu.py [outdir [name-suffix]]   (default: gpurun_out/golden, which gpurun brings back;
+                                                                        with a suffix only the cases whose name ends in it)
 
 Each fixture: the generator call that makes the input (kind, w, h -> _oracle.gen_image), the encoder parameters, the
 reference GPU encoder's JPEG bytes, and the reference GPU decoder's pixels for that stream (its float IDCT)."""
@@ -31,6 +32,10 @@ CASES = [  # name, kind, w, h, quality, rst, interleaved, luminance sampling (h,
     ("random_33x17_q90", "random", 33, 17, 90, 2, 0, (1, 1)),
     ("photo_64x48_q1", "photo", 64, 48, 1, 5, 0, (1, 1)),
     ("zero_256x256", "zero", 256, 256, 75, 36, 0, (1, 1)),
+    # param.segment_info = 1: APP13 tables of the restart segments' positions in front of every scan
+    ("photo_256x192_seginfo", "photo", 256, 192, 75, 4, 0, (1, 1), 1),
+    ("photo_320x208_420_seginfo", "photo", 320, 208, 75, 2, 0, (2, 2), 1),
+    ("random_200x120_il_seginfo", "random", 200, 120, 90, 3, 1, (1, 1), 1),
 ]
 
 
@@ -49,15 +54,19 @@ def main():
         return r["reply"]
 
     with tempfile.TemporaryDirectory() as tmp:
-        for name, kind, w, h, q, rst, il, samp in CASES:
+        for name, kind, w, h, q, rst, il, samp, *rest in CASES:
+            seginfo = rest[0] if rest else 0
+            if len(sys.argv) > 2 and not name.endswith(sys.argv[2]):
+                continue
             jpg, rgb = os.path.join(tmp, "a.jpg"), os.path.join(tmp, "a.rgb")
+            extra = ["par:segment_info=1"] if seginfo else []
             if samp == (1, 1):
-                call("encode", kind, w, h, q, rst, il, jpg)
+                call("encode", kind, w, h, q, rst, il, jpg, *extra)
             else:
-                call("encode", kind, w, h, q, rst, il, jpg, samp[0], samp[1])
+                call("encode", kind, w, h, q, rst, il, jpg, samp[0], samp[1], *extra)
             call("decode", jpg, rgb)
             np.savez_compressed(os.path.join(out_dir, "refgpu_%s.npz" % name), kind=kind, w=w, h=h, quality=q, rst=rst,
-                                interleaved=il, sampling=np.array(samp), jpeg=np.fromfile(jpg, np.uint8),
+                                interleaved=il, sampling=np.array(samp), segment_info=seginfo, jpeg=np.fromfile(jpg, np.uint8),
                                 pixels=np.fromfile(rgb, np.uint8).reshape(h, w, 3))
             print(name, os.path.getsize(jpg), "bytes")
     srv.stdin.close()

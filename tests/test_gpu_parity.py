@@ -282,7 +282,8 @@ def test_golden_vectors_from_reference_gpu_library(gj, enc, path):
     samp = tuple(int(v) for v in g["sampling"])
     name = {(1, 1): "4:4:4", (2, 2): "4:2:0", (2, 1): "4:2:2", (1, 2): "4:4:0"}[samp]
     img = o.gen_image(str(g["kind"]), w, h)
-    assert np.array_equal(enc.encode(img, q, rst, il, subsampling=name), g["jpeg"]), "bytes differ from the reference GPU encoder"
+    seginfo = int(g["segment_info"]) if "segment_info" in g else 0
+    assert np.array_equal(enc.encode(img, q, rst, il, subsampling=name, segment_info=seginfo), g["jpeg"]), "bytes differ from the reference GPU encoder"
     d = gj.Decoder(idct="float_gpuref")
     try:
         rgb = d.decode(g["jpeg"])

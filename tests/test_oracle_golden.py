@@ -60,7 +60,11 @@ def test_oracle_matches_reference_gpu_library_outputs(path):
     w, h, q, rst, il = int(g["w"]), int(g["h"]), int(g["quality"]), int(g["rst"]), int(g["interleaved"])
     samp = tuple(int(v) for v in g["sampling"])
     img = o.gen_image(str(g["kind"]), w, h)
-    jpeg = o.encode(img, q, rst, il, sampling=samp)
+    if "segment_info" in g and int(g["segment_info"]):
+        with o.segment_info():
+            jpeg = o.encode(img, q, rst, il, sampling=samp)
+    else:
+        jpeg = o.encode(img, q, rst, il, sampling=samp)
     assert jpeg.size == g["jpeg"].size and np.array_equal(jpeg, g["jpeg"]), "oracle JPEG bytes differ from the reference GPU encoder"
     rgb = o.decode(g["jpeg"], o.IDCT_FLOAT_GPUREF)
     if "pixels" in g:
