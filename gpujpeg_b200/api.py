@@ -98,6 +98,7 @@ def _load():
         "gpujpegx_encoder_run_resident": (ci, [vp, vp, ci]),
         "gpujpegx_decoder_run_resident": (ci, [vp, vp, ci]),
         "gpujpegx_decoder_get_coefficients": (ci, [vp, vp, cs]),
+        "gpujpegx_decoder_used_segment_info": (ci, [vp]),
         "gpujpegx_batch_create": (vp, [C.POINTER(ci), ci]),
         "gpujpegx_batch_destroy": (None, [vp]),
         "gpujpegx_batch_device_count": (ci, [vp]),
@@ -312,6 +313,10 @@ class Decoder:
         addr = _ptr(d_out)[0] if d_out is not None else None
         if lib.gpujpegx_decoder_run_resident(self._h, addr, stage_mask) != 0:
             raise GpuJpegError("gpujpegx_decoder_run_resident failed")
+
+    def used_segment_info(self):
+        """True if the last frame's scans were split by the stream's own segment-info tables (no marker scan on the device)"""
+        return lib.gpujpegx_decoder_used_segment_info(self._h) == 1
 
     def coefficients(self, width, height, sampling=(1, 1), interleaved=0):
         """coefficients of the last frame, natural order: (array, dequantized) -- with the integer IDCT flavour

@@ -489,6 +489,15 @@ int gj_reader_walk(const uint8_t* d, size_t size, size_t* pos, struct gj_stream*
                     }
                 }
                 break;
+            case 0xED:   /* segment info: scan index, positions [ref: src/gpujpeg_reader.c:229-249]; advisory, checked by the user */
+                if ( n > 1 && s->seginfo_pending.pieces < GJ_SEGINFO_MAX_PIECES ) {
+                    struct gj_seginfo* t = &s->seginfo_pending;
+                    t->piece[t->pieces] = b + 1;
+                    t->piece_bytes[t->pieces] = (uint32_t)(n - 1);
+                    t->pieces++;
+                    t->bytes += (size_t)(n - 1);
+                }
+                break;
             case 0xEE:
                 if ( n >= 12 && memcmp(b, "Adobe", 5) == 0 ) {
                     s->header_type = GPUJPEG_HEADER_ADOBE;
@@ -590,6 +599,8 @@ int gj_reader_walk(const uint8_t* d, size_t size, size_t* pos, struct gj_stream*
                     GJ_ERR("SOS marker is too short (%d bytes)!\n", len);
                     return -1;
                 }
+                s->seginfo[s->scan_count] = s->seginfo_pending;   /* the table belongs to the scan that follows it */
+                memset(&s->seginfo_pending, 0, sizeof s->seginfo_pending);
                 struct gj_scan_info* sc = &s->scan[s->scan_count++];
                 memset(sc, 0, sizeof *sc);
                 sc->ncomp = b[0];

@@ -60,6 +60,8 @@ struct gpujpeg_decoder {
     uint32_t* d_list_cpos; size_t d_list_cpos_size; /*                  positions in the clean stream */
     uint8_t* d_clean; size_t d_clean_size;          /* K0 clean stream: stuffing and markers removed, big-endian words */
     uint32_t* d_seg_tab; size_t d_seg_tab_size;     /* resynchronised streams only: per segment {raw start, clean start, clean end} */
+    uint32_t* d_seg_off; uint32_t* h_seg_off; size_t seg_off_size;   /* streams with segment info: file offset of every segment (h: pinned) */
+    int used_segment_info;                          /* the last frame's scans were split by the stream's own tables */
     unsigned long long* d_cta; size_t d_cta_size;   /* K0 scratch */
     uint32_t* d_mk;                                 /* K0 results (layout in gpujpeg_decoder_decode) */
     uint32_t* d_k3_ctr;                             /* K3 work counters (8 words, zero between launches) */
@@ -159,6 +161,8 @@ int gpujpeg_decoder_destroy(struct gpujpeg_decoder* d)
     gj_cuda_free(d->d_list_cpos);
     gj_cuda_free(d->d_clean);
     gj_cuda_free(d->d_seg_tab);
+    gj_cuda_free(d->d_seg_off);
+    if ( d->h_seg_off ) gj_cuda_free_host(d->h_seg_off);
     gj_cuda_free(d->d_cta);
     gj_cuda_free(d->d_mk);
     gj_cuda_free(d->d_k3_ctr);
@@ -399,6 +403,97 @@ static int resync_segments(struct gpujpeg_decoder* d, const struct gj_stream* st
     return rc;
 }
 
+/* Which Huffman decoder kernel (measured on B200, profiles/r2_k3_matrix.md): a frame with few segments cannot occupy the
+ * GPU with one thread per segment -- there the self-synchronising walks buy parallelism INSIDE a segment (HD: 27 us
+ * against 82, 4K: 41 against 90); with 40 000 segments and more the segments alone keep the machine busy and the redundant
+ * walks pay off from photographic densities on (8K q75: 119 us against 174, q90: 268 against 332), not for very sparse
+ * (q50: 97 either way) or random content (562 against 731).  Interleaved scans: a walk that starts inside the stream also
+ * has to guess which component's block it is in, and a wrong guess does not heal by itself (other Huffman tables) --
+ * exactness then spreads one lane per round; one thread per segment is faster at every size measured (8K 4:2:0: 150 us
+ * against 258, 4K: 108 / 170, HD: 97 / 99). */
+static int wants_thread_per_segment(const struct gpujpeg_decoder* d, const struct gj_geometry* g, size_t ecs_bytes)
+{
+    const size_t bytes_per_block_x10 = ecs_bytes * 10 / (g->coef_count / 64);
+    const int many_segments = g->seg_count >= 30000;
+    return d->thread_per_segment || g->lay.interleaved || g->seg_mcu * g->lay.bpm > 40 ||
+           (many_segments && (bytes_per_block_x10 < 20 || bytes_per_block_x10 > 200));
+}
+
+/* Segment info [ref: src/gpujpeg_reader.c:1168-1215]: a stream can carry, in front of every scan, the position of every
+ * restart segment.  The reference's reader then splits the scan by that table instead of searching for markers; here the
+ * search is K0's job on the device, and the table only pays when K3 runs one thread per segment on the file bytes (the
+ * self-synchronising kernel reads K0's clean stream): then K0 and the round trip for its report are skipped altogether.
+ * The table is advisory: count, order and range are checked, and anything odd sends the frame down the K0 path.
+ * Walks the remaining scans on the host (extents from the tables, marker segments between scans by length), fills
+ * d->h_seg_off.  Returns 1 if the frame can be decoded from the tables (st / pos / adobe advanced to the end of the
+ * stream), 0 to use K0 (st / pos / adobe untouched). */
+static int split_by_segment_info(struct gpujpeg_decoder* d, const uint8_t* image, size_t image_size, struct gj_stream* st,
+                                 size_t* pos, int* adobe)
+{
+    const struct gj_geometry* g = &d->geo;
+    if ( !st->seginfo[0].pieces || g->seg_mcu <= 0 || st->restart_interval <= 0 ) return 0;
+    for ( int k = 0; k < GJ_MAX_COMP; k++ )
+        if ( d->force_lanes[k] ) return 0;   /* the self-synchronising kernel was asked for */
+    if ( (size_t)g->seg_count * 4 > d->seg_off_size ) {
+        gj_cuda_free(d->d_seg_off);
+        if ( d->h_seg_off ) gj_cuda_free_host(d->h_seg_off);
+        d->d_seg_off = NULL;
+        d->h_seg_off = NULL;
+        d->seg_off_size = 0;
+        if ( gj_cuda_malloc((void**)&d->d_seg_off, (size_t)g->seg_count * 4) ||
+             gj_cuda_malloc_host((void**)&d->h_seg_off, (size_t)g->seg_count * 4) )
+            return 0;
+        d->seg_off_size = (size_t)g->seg_count * 4;
+    }
+    struct gj_stream t = *st;
+    size_t p = *pos;
+    int ad = *adobe;
+    size_t ecs_bytes = 0;
+    for ( int k = 0;; k++ ) {
+        if ( k >= g->scan_count || k >= t.scan_count ) return 0;
+        const struct gj_seginfo* si = &t.seginfo[k];
+        const int first = g->lay.scan_seg_begin[k], segs = g->lay.scan_seg_begin[k + 1] - first;
+        if ( si->bytes != ((size_t)segs + 1) * 4 ) return 0;
+        /* the positions, piece by piece (a piece boundary falls on an entry boundary in the reference's writer; any other
+         * cut is read byte-wise all the same) */
+        const size_t begin = t.scan[k].begin;
+        uint32_t prev = 0;
+        int piece = 0;
+        uint32_t at = 0;
+        for ( int i = 0; i <= segs; i++ ) {
+            uint32_t v = 0;
+            for ( int b = 0; b < 4; b++ ) {
+                while ( piece < si->pieces && at >= si->piece_bytes[piece] ) {
+                    piece++;
+                    at = 0;
+                }
+                if ( piece >= si->pieces ) return 0;
+                v = v << 8 | si->piece[piece][at++];
+            }
+            if ( (i == 0 && v != 0) || v < prev || begin + v + 2 > image_size ) return 0;
+            /* a segment starts behind the previous segment's RSTn marker */
+            if ( i > 0 && i < segs && (v < prev + 2 || image[begin + v - 2] != 0xFF || image[begin + v - 1] != 0xD0 + ((i - 1) & 7)) ) return 0;
+            if ( i < segs ) d->h_seg_off[first + i] = (uint32_t)(begin + v);
+            prev = v;
+        }
+        t.scan[k].end = begin + prev;
+        if ( image[t.scan[k].end] != 0xFF ) return 0;   /* a marker follows the scan */
+        ecs_bytes += prev;
+        p = t.scan[k].end;
+        const int r = gj_reader_walk(image, image_size, &p, &t, &ad);
+        if ( r < 0 ) return 0;
+        if ( r == 0 ) {
+            if ( k + 1 != g->scan_count ) return 0;
+            break;
+        }
+    }
+    if ( !wants_thread_per_segment(d, g, ecs_bytes) ) return 0;
+    *st = t;
+    *pos = p;
+    *adobe = ad;
+    return 1;
+}
+
 /* [ref: src/gpujpeg_decoder.c:234-469] */
 int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t image_size,
                            struct gpujpeg_decoder_output* output)
@@ -504,6 +599,19 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
         return GPUJPEG_ERROR;
     }
     if ( stats && d->timers_ok ) gj_timer_stop(&d->t_to, d->stream);
+    uint32_t first_rank[GJ_MAX_COMP] = {0, 0, 0, 0}, end_rank[GJ_MAX_COMP] = {0, 0, 0, 0}, scan_cbegin[GJ_MAX_COMP] = {0, 0, 0, 0};
+    /* ---- scans split by the stream's own segment-info tables (no K0, no round trip), or ... ---- */
+    const int by_table = split_by_segment_info(d, image, image_size, &st, &pos, &adobe);
+    d->used_segment_info = by_table;
+    if ( by_table ) {
+        if ( gj_cuda_memcpy_h2d_async(d->d_seg_off, d->h_seg_off, (size_t)g->seg_count * 4, d->stream) ||
+             gj_cuda_memset_async(d->d_mk, 0, 32, d->stream) ) {
+            GJ_ERR("Decoder copy of the segment table failed: %s\n", gj_cuda_last_error());
+            return GPUJPEG_ERROR;
+        }
+    }
+    else {
+    /* ---- ... K0 builds the marker list and the clean stream on the device ---- */
     /* d_mk: [0] total markers, [1] non-RST markers, [2] list overflow, [3] restart sequence error (K3), [5] clean bytes,
      *       [8..] {rank, position, code, clean position} of the non-RST markers */
     if ( gj_launch_marker_scan(d->d_file, ecs_begin, image_size, d->d_cta, d->d_list_pos, d->d_list_code, d->d_list_cpos,
@@ -534,7 +642,6 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     }
     /* per scan, from the marker report alone (no second kernel, no walk over the entropy-coded bytes): where it ends,
      * how many markers lie in front of it, how many restart markers it holds, where its clean bytes start */
-    uint32_t first_rank[GJ_MAX_COMP] = {0, 0, 0, 0}, end_rank[GJ_MAX_COMP] = {0, 0, 0, 0}, scan_cbegin[GJ_MAX_COMP] = {0, 0, 0, 0};
     for ( int k = 0; k < st.scan_count; k++ ) {
         /* a scan ends at the first marker that is not RSTn: inside entropy-coded data that test is exact */
         size_t e1 = 0;
@@ -573,6 +680,7 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
         if ( r < 0 ) return GPUJPEG_ERROR;
         if ( r == 0 ) break; /* EOI (or end of data) */
     }
+    }   /* K0 path */
     if ( gj_reader_finish(&st, adobe, d->verbose) ) return GPUJPEG_ERROR;
     if ( st.color_space != early_cs ) {
         GJ_ERR("The stream's colour space (%s) is announced after its first scan header; not supported.\n",
@@ -656,7 +764,7 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
      * resynchronised the way the reference's reader does it (resync_segments below) and decoded from an explicit
      * segment table. */
     int resync = 0;
-    for ( int k = 0; k < g->scan_count; k++ ) {
+    for ( int k = 0; k < g->scan_count && !by_table; k++ ) {
         const int segs = g->lay.scan_seg_begin[k + 1] - g->lay.scan_seg_begin[k];
         if ( end_rank[k] >= list_cap ) {
             GJ_ERR("JPEG stream has a broken restart-marker structure (scan %d holds %u restart markers, expected %d "
@@ -671,7 +779,7 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     ha.d_file = d->d_file;
     ha.file_size = image_size;
     ha.dequantize = d->idct_flavour == 0;
-    ha.d_seg_off = NULL; /* segment starts come from the device-built marker list */
+    ha.d_seg_off = by_table ? d->d_seg_off : NULL; /* segment starts: the stream's own table, or the device-built marker list */
     ha.d_seg_len = NULL;
     ha.d_list_pos = d->d_list_pos;
     ha.d_list_code = d->d_list_code;
@@ -680,22 +788,14 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     ha.d_clean = (const uint32_t*)d->d_clean;
     ha.d_list_cpos = d->d_list_cpos;
     ha.force_thread_per_segment = d->thread_per_segment;
-    /* Which Huffman decoder kernel, and how many lanes share a restart segment (measured on B200, profiles/r2_k3_matrix.md):
-     * a frame with few segments cannot occupy the GPU with one thread per segment -- there the self-synchronising walks
-     * buy parallelism INSIDE a segment (HD: 27 us against 82, 4K: 41 against 90); with 40 000 segments and more the
-     * segments alone keep the machine busy and the redundant walks pay off from photographic densities on (8K q75:
-     * 119 us against 174, q90: 268 against 332), not for very sparse (q50: 97 either way) or random content (562 against
-     * 731). */
+    /* which kernel (wants_thread_per_segment), and for the self-synchronising one how many lanes share a restart segment
+     * (profiles/r2_k3_matrix.md) */
     size_t ecs_bytes = 0;
     for ( int k = 0; k < g->scan_count; k++ )
         ecs_bytes += st.scan[k].end - st.scan[k].begin;
     const size_t bytes_per_block_x10 = ecs_bytes * 10 / (g->coef_count / 64);
     const int many_segments = g->seg_count >= 30000;
-    /* interleaved scans: a walk that starts inside the stream also has to guess which component's block it is in, and a
-     * wrong guess does not heal by itself (other Huffman tables) -- exactness then spreads one lane per round; one thread
-     * per segment is faster at every size measured (8K 4:2:0: 150 us against 258, 4K: 108 / 170, HD: 97 / 99) */
-    ha.force_thread_per_segment = d->thread_per_segment || g->lay.interleaved ||
-                                  (many_segments && (bytes_per_block_x10 < 20 || bytes_per_block_x10 > 200));
+    ha.force_thread_per_segment = by_table || wants_thread_per_segment(d, g, ecs_bytes);
     for ( int k = 0; k < g->scan_count; k++ ) {
         ha.first_rank[k] = first_rank[k];
         ha.scan_cbegin[k] = scan_cbegin[k];
@@ -704,7 +804,7 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
         ha.scan_lanes[k] = (uint8_t)(g->seg_count <= 8000 ? 16
                                      : !many_segments     ? (bytes_per_block_x10 > 100 ? 16 : 8)
                                      : bytes_per_block_x10 > 80 ? 8 : avg >= 192 ? 16 : 8);
-        if ( d->force_lanes[k] ) {
+        if ( d->force_lanes[k] ) {   /* (never with by_table: split_by_segment_info declines then) */
             ha.scan_lanes[k] = (uint8_t)d->force_lanes[k];
             ha.force_thread_per_segment = d->thread_per_segment;
         }
@@ -960,6 +1060,11 @@ void gpujpeg_decoder_print_options(void)
     printf("\t" GPUJPEG_DEC_OPT_CHANNEL_REMAP "=XYZ[W] - output channel mapping (as the encoder option)\n");
 }
 
+GPUJPEG_API int gpujpegx_decoder_used_segment_info(const struct gpujpeg_decoder* d)
+{
+    return d && d->last_valid ? d->used_segment_info : -1;
+}
+
 /* ---- extension: re-run the GPU stages of the last decoded frame on the JPEG bytes already on the device ----
  * stage_mask bit 2 = K0 (marker list + clean stream from the file bytes), bit 0 = K3 (Huffman decode), bit 1 = K4
  * (dequant+IDCT+colour).  No copies, no sync; what the host derived from K0's report for this file (scan extents,
@@ -967,7 +1072,7 @@ void gpujpeg_decoder_print_options(void)
 GPUJPEG_API int gpujpegx_decoder_run_resident(struct gpujpeg_decoder* d, uint8_t* d_out, int stage_mask)
 {
     if ( !d || !d->last_valid ) return -1;
-    if ( (stage_mask & 4) &&
+    if ( (stage_mask & 4) && !d->used_segment_info &&
          gj_launch_marker_scan(d->d_file, d->last_ecs_begin, d->last_args.file_size, d->d_cta, d->d_list_pos, d->d_list_code,
                                d->d_list_cpos, d->last_list_cap, d->d_clean, d->d_mk, d->d_mk + 8, GJ_MK_OTHER_CAP, d->stream) )
         return -1;

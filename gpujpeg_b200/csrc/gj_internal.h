@@ -193,6 +193,15 @@ struct gj_scan_info {
     size_t begin, end; /* entropy-coded bytes [begin,end) in the file */
     int first_segment, segment_count;
 };
+/* APP13 "segment info" headers met in front of a scan [ref: src/gpujpeg_reader.c:229-249]: pieces of one table of
+ * big-endian 32-bit positions (every restart segment's first byte relative to the scan's first byte, then the scan's end) */
+#define GJ_SEGINFO_MAX_PIECES 64
+struct gj_seginfo {
+    const uint8_t* piece[GJ_SEGINFO_MAX_PIECES];
+    uint32_t piece_bytes[GJ_SEGINFO_MAX_PIECES];
+    int pieces;
+    size_t bytes;
+};
 struct gj_stream {
     int width, height, comp_count;
     int restart_interval;
@@ -203,6 +212,8 @@ struct gj_stream {
     int have_huff[2][4];
     int scan_count;
     struct gj_scan_info scan[GJ_MAX_COMP];
+    struct gj_seginfo seginfo[GJ_MAX_COMP];   /* [scan]: the table in front of the scan's SOS, if any */
+    struct gj_seginfo seginfo_pending;        /* headers met since the last SOS */
     enum gpujpeg_color_space color_space;
     int spiff_color_space;   /* colour space named by a SPIFF header, GPUJPEG_NONE (0) if there is none */
     int com_color_space;     /* colour space named by FFmpeg's COM "CS=ITU601", GPUJPEG_NONE (0) if there is none */

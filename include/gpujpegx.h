@@ -30,6 +30,10 @@ GPUJPEG_API int gpujpegx_decoder_run_resident(struct gpujpeg_decoder* decoder, u
  * when the values are already multiplied by the quantiser (integer IDCT flavour), 0 otherwise, -1 on error */
 GPUJPEG_API int gpujpegx_encoder_get_coefficients(struct gpujpeg_encoder* encoder, int16_t* out, size_t count);
 GPUJPEG_API int gpujpegx_decoder_get_coefficients(struct gpujpeg_decoder* decoder, int16_t* out, size_t count);
+/* 1 if the scans of the last decoded frame were split by the stream's own segment-info tables (struct
+ * gpujpeg_parameters.segment_info of the encoder; reference: src/gpujpeg_reader.c:1168-1215) -- then no marker scan ran on
+ * the device --, 0 if by the marker scan, -1 on error */
+GPUJPEG_API int gpujpegx_decoder_used_segment_info(const struct gpujpeg_decoder* decoder);
 
 /* ---- batches of independent frames over several GPUs ---- */
 struct gpujpegx_batch;

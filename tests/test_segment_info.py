@@ -88,3 +88,60 @@ def test_product_writes_the_oracles_tables(gj, kind, w, h, q, rst, il, name, sam
     finally:
         e.close()
         d.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,w,h,q,rst,il,sampling,forced", [("photo", 640, 368, 75, 6, 1, (2, 2), None),        # interleaved: one thread per segment anyway
+                                                               ("random", 333, 177, 85, 3, 1, (1, 1), None),
+                                                               ("photo", 640, 360, 75, 12, 0, (1, 1), "thread_per_segment"),
+                                                               ("photo", 1024, 1032, 60, 1, 0, (1, 1), "thread_per_segment"),   # two table pieces per scan
+                                                               ("photo", 640, 360, 75, 12, 0, (1, 1), None)])      # self-synchronising kernel: needs K0, table unused
+def test_decoder_splits_scans_by_the_streams_tables(gj, kind, w, h, q, rst, il, sampling, forced):
+    """[ref: src/gpujpeg_reader.c:1168-1215] with segment info the reference's reader takes the segment positions from the
+    tables; here that replaces the marker scan on the device whenever K3 decodes one thread per segment"""
+    img = o.gen_image(kind, w, h)
+    with o.segment_info():
+        jpeg = o.encode(img, q, rst, il, threads=4, sampling=sampling)
+    want = o.decode(jpeg, threads=4)
+    d = gj.Decoder()
+    try:
+        if forced:
+            d.set_option("dec_opt_huffman", forced)
+        assert np.array_equal(d.decode(jpeg), want)
+        assert d.used_segment_info() == (il == 1 or forced is not None)
+        plain = o.encode(img, q, rst, il, threads=4, sampling=sampling)
+        assert np.array_equal(d.decode(plain), want) and not d.used_segment_info()
+        assert np.array_equal(d.decode(jpeg), want)
+    finally:
+        d.close()
+
+
+@pytest.mark.gpu
+def test_tables_are_advisory(gj):
+    """a table that does not describe the scan (wrong count, a position that is not behind a restart marker, out of range,
+    not ascending) sends the frame down the marker-scan path: same picture"""
+    img = o.gen_image("photo", 320, 208)
+    with o.segment_info():
+        jpeg = o.encode(img, 75, 2, 1, threads=4, sampling=(2, 2))
+    want = o.decode(jpeg, threads=4)
+    b = bytes(jpeg)
+    i = b.find(b"\xff\xed")
+    n = (b[i + 2] << 8) | b[i + 3]
+    table = i + 5            # first position (scan index byte in front of it)
+    d = gj.Decoder()
+    try:
+        assert np.array_equal(d.decode(jpeg), want) and d.used_segment_info()
+        bad = bytearray(b)
+        bad[table + 4 + 3] ^= 1                                   # second segment's position off by one
+        assert np.array_equal(d.decode(np.frombuffer(bytes(bad), np.uint8)), want) and not d.used_segment_info()
+        bad = bytearray(b)
+        bad[table + 8:table + 12] = (0x7FFFFFFF).to_bytes(4, "big")   # out of range
+        assert np.array_equal(d.decode(np.frombuffer(bytes(bad), np.uint8)), want) and not d.used_segment_info()
+        bad = bytearray(b)
+        bad[table + 8:table + 12], bad[table + 12:table + 16] = b[table + 12:table + 16], b[table + 8:table + 12]   # not ascending
+        assert np.array_equal(d.decode(np.frombuffer(bytes(bad), np.uint8)), want) and not d.used_segment_info()
+        short = bytearray(b[:i + 2] + (n - 4).to_bytes(2, "big") + b[i + 4:i + 2 + n - 4] + b[i + 2 + n:])   # one entry too few
+        assert np.array_equal(d.decode(np.frombuffer(bytes(short), np.uint8)), want) and not d.used_segment_info()
+        assert np.array_equal(d.decode(jpeg), want) and d.used_segment_info()
+    finally:
+        d.close()
