@@ -62,6 +62,7 @@ struct gpujpeg_decoder {
     uint32_t* d_seg_tab; size_t d_seg_tab_size;     /* resynchronised streams only: per segment {raw start, clean start, clean end} */
     uint32_t* d_seg_off; uint32_t* h_seg_off; size_t seg_off_size;   /* streams with segment info: file offset of every segment (h: pinned) */
     int used_segment_info;                          /* the last frame's scans were split by the stream's own tables */
+    int ignore_segment_info;                        /* set while a frame whose tables proved wrong is decoded again */
     unsigned long long* d_cta; size_t d_cta_size;   /* K0 scratch */
     uint32_t* d_mk;                                 /* K0 results (layout in gpujpeg_decoder_decode) */
     uint32_t* d_k3_ctr;                             /* K3 work counters (8 words, zero between launches) */
@@ -431,7 +432,7 @@ static int split_by_segment_info(struct gpujpeg_decoder* d, const uint8_t* image
                                  size_t* pos, int* adobe)
 {
     const struct gj_geometry* g = &d->geo;
-    if ( !st->seginfo[0].pieces || g->seg_mcu <= 0 || st->restart_interval <= 0 ) return 0;
+    if ( !st->seginfo[0].pieces || g->seg_mcu <= 0 || st->restart_interval <= 0 || d->ignore_segment_info ) return 0;
     for ( int k = 0; k < GJ_MAX_COMP; k++ )
         if ( d->force_lanes[k] ) return 0;   /* the self-synchronising kernel was asked for */
     if ( (size_t)g->seg_count * 4 > d->seg_off_size ) {
@@ -455,24 +456,31 @@ static int split_by_segment_info(struct gpujpeg_decoder* d, const uint8_t* image
         const int first = g->lay.scan_seg_begin[k], segs = g->lay.scan_seg_begin[k + 1] - first;
         if ( si->bytes != ((size_t)segs + 1) * 4 ) return 0;
         /* the positions, piece by piece (a piece boundary falls on an entry boundary in the reference's writer; any other
-         * cut is read byte-wise all the same) */
+         * cut is read byte-wise all the same).  Checked here: count, order, range; that every segment really starts behind
+         * the restart marker with the right number is checked by K3 where it reads the bytes anyway (a host check costs a
+         * cache miss per segment: 0.15 ms for an 8K frame) -- a frame that fails there is decoded again by marker scan. */
         const size_t begin = t.scan[k].begin;
         uint32_t prev = 0;
         int piece = 0;
         uint32_t at = 0;
         for ( int i = 0; i <= segs; i++ ) {
             uint32_t v = 0;
-            for ( int b = 0; b < 4; b++ ) {
-                while ( piece < si->pieces && at >= si->piece_bytes[piece] ) {
-                    piece++;
-                    at = 0;
-                }
-                if ( piece >= si->pieces ) return 0;
-                v = v << 8 | si->piece[piece][at++];
+            if ( piece < si->pieces && at + 4 <= si->piece_bytes[piece] ) {
+                const uint8_t* q = si->piece[piece] + at;
+                v = (uint32_t)q[0] << 24 | (uint32_t)q[1] << 16 | (uint32_t)q[2] << 8 | q[3];
+                at += 4;
             }
-            if ( (i == 0 && v != 0) || v < prev || begin + v + 2 > image_size ) return 0;
-            /* a segment starts behind the previous segment's RSTn marker */
-            if ( i > 0 && i < segs && (v < prev + 2 || image[begin + v - 2] != 0xFF || image[begin + v - 1] != 0xD0 + ((i - 1) & 7)) ) return 0;
+            else {
+                for ( int b = 0; b < 4; b++ ) {
+                    while ( piece < si->pieces && at >= si->piece_bytes[piece] ) {
+                        piece++;
+                        at = 0;
+                    }
+                    if ( piece >= si->pieces ) return 0;
+                    v = v << 8 | si->piece[piece][at++];
+                }
+            }
+            if ( (i == 0 && v != 0) || (i > 0 && v < prev + 2) || begin + v + 2 > image_size ) return 0;
             if ( i < segs ) d->h_seg_off[first + i] = (uint32_t)(begin + v);
             prev = v;
         }
@@ -888,6 +896,14 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     if ( gj_cuda_memcpy_d2h_async(d->h_mk, d->d_mk, 16, d->stream) || gj_cuda_stream_sync(d->stream) ) {
         GJ_ERR("Decoder failed: %s\n", gj_cuda_last_error());
         return GPUJPEG_ERROR;
+    }
+    if ( d->h_mk[3] && by_table ) {
+        /* a position of the stream's segment-info table does not lie behind the restart marker it should: forget the tables */
+        GJ_VERBOSE(d->verbose, "Segment info of the stream does not match its restart markers; decoding by marker scan.\n");
+        d->ignore_segment_info = 1;
+        const int rc = gpujpeg_decoder_decode(d, image, image_size, output);
+        d->ignore_segment_info = 0;
+        return rc;
     }
     if ( d->h_mk[3] && !resync && pass == 0 ) {
         /* K3 met a restart marker with the wrong number: resynchronise [ref: src/gpujpeg_reader.c:1071-1105] and decode again */

@@ -925,8 +925,11 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file
             start = a.d_seg_tab[3 * (size_t)g];
             absent = start == 0xFFFFFFFFu;
         }
-        else if ( seg_off ) {
+        else if ( seg_off ) {   // the stream's own segment-info table: trusted only as far as the restart markers confirm it
             start = seg_off[g];
+            if ( s > 0 && (start < 2u || start >= (uint32_t)(file_end - file) || file[start - 2] != 0xFF ||
+                           file[start - 1] != (uint8_t)(0xD0 + ((s - 1) & 7))) )
+                atomicExch(a.d_error, 1u);
         }
         else if ( s == 0 ) {
             start = a.scan_begin[scan];

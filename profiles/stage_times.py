@@ -13,7 +13,7 @@ stream = torch.cuda.current_stream().cuda_stream
 enc = g.Encoder(stream=stream, pinned_output=True)
 SS = os.environ.get("GJ_SS", "4:4:4"); IL = int(os.environ.get("GJ_IL", "0"))
 if "GJ_RST" in os.environ: rst = int(os.environ["GJ_RST"])
-jpeg = enc.encode(d_raw, Q, rst, IL, subsampling=SS)
+jpeg = enc.encode(d_raw, Q, rst, IL, subsampling=SS, segment_info=int(os.environ.get("GJ_SEGINFO", "0")))
 h_jpeg = torch.from_numpy(jpeg).pin_memory()
 d_out = torch.empty((h, w, 3), dtype=torch.uint8, device=dev)
 def timeit(fn, n=20):
@@ -30,9 +30,10 @@ for lanes in (["0", "1", "2", "4", "8", "16", "32"] if len(sys.argv) < 3 else sy
     dec.decode(h_jpeg.numpy(), out=d_out)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(5): dec.decode(h_jpeg.numpy(), out=d_out)
+    for _ in range(20): dec.decode(h_jpeg.numpy(), out=d_out)
     torch.cuda.synchronize()
-    call = (time.perf_counter() - t0) / 5 * 1e3
+    call = (time.perf_counter() - t0) / 20 * 1e3
+    if dec.used_segment_info(): print("(scans split by the stream's segment-info tables: no K0)")
     print(SIZE, Q, "%s lanes=%s: K0 %.1f us  K3 %.1f us  K4 %.1f us  K0+K3+K4 %.1f us | decode call to device buffer %.3f ms (jpeg %d B)" % (
         kind, lanes, timeit(lambda: dec.run_resident(d_out, 4)), timeit(lambda: dec.run_resident(d_out, 1)),
         timeit(lambda: dec.run_resident(d_out, 2)), timeit(lambda: dec.run_resident(d_out, 7)), call, jpeg.size), flush=True)
