@@ -323,10 +323,16 @@ static int launch_k4(struct gpujpeg_decoder* d, const int comp_tq[3], uint8_t* d
                                      d->param.color_space_internal,
                                      g->width, g->height, g->comp, g->comp_count, g->max_hs, g->max_vs, d->stream);
     }
+    /* dec_opt_flipped on the fused path (see gpujpeg_decoder_decode): rows are written last to first */
+    int pitch = g->pitch;
+    if ( d->flipped ) {
+        d_out += (size_t)(g->height - 1) * (size_t)g->pitch;
+        pitch = -pitch;
+    }
     if ( g->lay.simple )
-        return gj_launch_idct_rgb444(d->d_coef, g->bcx, g->bcy, comp_tq, d_out, g->width, g->height, g->pitch, d->idct_flavour,
+        return gj_launch_idct_rgb444(d->d_coef, g->bcx, g->bcy, comp_tq, d_out, g->width, g->height, pitch, d->idct_flavour,
                                      coef_dequantized, &d->h_tab, d->stream);
-    return gj_launch_idct_rgb_ss(d->d_coef, g->comp, comp_tq, d_out, g->width, g->height, g->pitch, d->idct_flavour,
+    return gj_launch_idct_rgb_ss(d->d_coef, g->comp, comp_tq, d_out, g->width, g->height, pitch, d->idct_flavour,
                                  coef_dequantized, &d->h_tab, d->stream);
 }
 
@@ -570,9 +576,12 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     pi.height = st.height;
     int out_mode = choose_output(d, &st, &pi);
     if ( !out_mode ) return GPUJPEG_ERROR;
-    /* the flip acts on the component planes, in front of the postprocessor [ref: src/gpujpeg_postprocessor.cu:447]: only the
-     * pass that has planes can do it */
-    if ( d->flipped ) out_mode = GJ_OUT_GENERIC;
+    /* the flip acts on the component planes, padding included, in front of the postprocessor
+     * [ref: src/gpujpeg_postprocessor.cu:447]: in general only the pass that has planes can do it.  Without vertical padding
+     * flipping the planes and then replicating chrominance rows is flipping the finished image, and the fused kernel does
+     * that by writing the rows last to first (launch_k4). */
+    if ( d->flipped && !(out_mode == GJ_OUT_RGB && st.height % (8 * (st.comp_count == 3 ? (st.comp_hv[0] & 15) : 1)) == 0) )
+        out_mode = GJ_OUT_GENERIC;
 
     if ( !d->initialised || d->param_image.width != pi.width || d->param_image.height != pi.height ||
          d->param_image.pixel_format != pi.pixel_format || d->param.comp_count != p.comp_count ||

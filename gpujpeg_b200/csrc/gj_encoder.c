@@ -311,10 +311,17 @@ static int launch_k1(struct gpujpeg_encoder* e, const uint8_t* d_raw)
         return gj_launch_fdct_samples(e->d_planes, &pl, e->d_coef, e->d_nzmask, padded, g->comp_count, g->lay.comp_tbl, &e->h_tab,
                                       e->stream);
     }
+    /* enc_opt_flipped on the fused path (see encoder_init_image): the kernels walk the rows through a pitch; start at the last
+     * row and step backwards */
+    int pitch = g->pitch;
+    if ( e->flipped ) {
+        d_raw += (size_t)(g->height - 1) * (size_t)g->pitch;
+        pitch = -pitch;
+    }
     if ( g->lay.simple )
-        return gj_launch_fdct_rgb444(d_raw, g->width, g->height, g->pitch, e->d_coef, e->d_nzmask, g->bcx, g->bcy, &e->h_tab,
+        return gj_launch_fdct_rgb444(d_raw, g->width, g->height, pitch, e->d_coef, e->d_nzmask, g->bcx, g->bcy, &e->h_tab,
                                      e->stream);
-    return gj_launch_fdct_rgb_ss(d_raw, g->width, g->height, g->pitch, e->d_coef, e->d_nzmask, g->comp, &e->h_tab, e->stream);
+    return gj_launch_fdct_rgb_ss(d_raw, g->width, g->height, pitch, e->d_coef, e->d_nzmask, g->comp, &e->h_tab, e->stream);
 }
 
 static void fill_huff_args(const struct gpujpeg_encoder* e, struct gj_huff_enc_args* ha)
@@ -349,8 +356,13 @@ static int encoder_init_image(struct gpujpeg_encoder* e, const struct gpujpeg_pa
 {
     gj_geometry_init(&e->geo, p, pi);
     e->input_mode = params_supported(p, pi);
-    /* the flip acts on the component planes [ref: src/gpujpeg_preprocessor.cu:474-485]: only the pass that has planes can do it */
-    if ( e->flipped && e->input_mode != GJ_IN_UNSUPPORTED ) e->input_mode = GJ_IN_GENERIC;
+    /* the flip acts on the component planes, padding included [ref: src/gpujpeg_preprocessor.cu:474-485]: in general only the
+     * pass that has planes can do it.  When no component is subsampled vertically and the height has no padding, flipping
+     * the planes is flipping the image rows, and the fused kernel does that by reading the rows backwards (launch_k1).
+     * (With vertical subsampling the two differ: the reference keeps every second row of the UNFLIPPED image.) */
+    if ( e->flipped && e->input_mode != GJ_IN_UNSUPPORTED &&
+         !(e->input_mode == GJ_IN_RGB && e->geo.max_vs == 1 && pi->height % 8 == 0) )
+        e->input_mode = GJ_IN_GENERIC;
     e->flip_mode = e->flipped != 0;
     if ( e->input_mode != GJ_IN_RGB && gj_raw_layout_init(&e->raw, pi) ) return -1;
     if ( e->input_mode == GJ_IN_GENERIC && grow((void**)&e->d_planes, &e->d_planes_size, e->geo.coef_count) ) return -1;

@@ -528,6 +528,9 @@ def test_rgba_input_and_output(gj, enc, il, sub):
 FLIP_REMAP = [  # fmt, colour space, JPEG subsampling, w, h, flipped, remap
     (o.FMT_444_P012, o.CS_RGB, "4:4:4", 322, 201, True, None),     # height not a multiple of 8: the flip acts on padded planes
     (o.FMT_444_P012, o.CS_RGB, "4:2:0", 320, 200, True, None),
+    (o.FMT_444_P012, o.CS_RGB, "4:4:4", 320, 208, True, None),     # no vertical padding: the fused kernels walk the rows backwards
+    (o.FMT_444_P012, o.CS_RGB, "4:2:2", 322, 208, True, None),
+    (o.FMT_444_P012, o.CS_RGB, "4:2:0", 320, 208, True, None),     # encoder: planes (every second row of the unflipped image); decoder: fused
     (o.FMT_444_P012, o.CS_RGB, "4:4:4", 160, 96, False, "210"),    # BGR input
     (o.FMT_444_P012, o.CS_RGB, "4:2:2", 322, 200, True, "2Z0"),
     (o.FMT_4444_P0123, o.CS_RGB, "4:4:4", 128, 64, False, "1230"), # ARGB -> RGBA

@@ -220,7 +220,7 @@ def test_reference_gpu_rgba(tmp_path):
 
 
 @pytest.mark.skipif(not os.path.exists(SO), reason="oracle/_ref/libgpujpeg_refgpu.so not built")
-@pytest.mark.parametrize("fmt,cs,w,h,flipped,remap", [(1, 1, 322, 201, True, None), (1, 1, 160, 96, False, "210"), (1, 1, 322, 200, True, "2Z0"),
+@pytest.mark.parametrize("fmt,cs,w,h,flipped,remap", [(1, 1, 322, 201, True, None), (1, 1, 320, 208, True, None), (1, 1, 160, 96, False, "210"), (1, 1, 322, 200, True, "2Z0"),
                                                       (6, 1, 128, 64, False, "1230"), (5, 3, 320, 200, True, None)])
 def test_reference_gpu_flip_and_channel_remap(tmp_path, fmt, cs, w, h, flipped, remap):
     """enc/dec_opt_flipped and enc/dec_opt_channel_remap: reference GPU library == oracle == product"""
