@@ -45,4 +45,30 @@ for fmt, cs, sub in [(o.FMT_U8, o.CS_JPEG, None), (o.FMT_420_P0P1P2, o.CS_JPEG, 
     assert np.array_equal(out, o.decode_any(want, fmt, cs) if fmt else o.decode_ycc(want, fmt, w, h))
     d.close()
     print("ok fmt", fmt, cs, sub, flush=True)
+# segment info written and used (one thread per segment: no marker scan), flipped frame on the fused kernels, forced lanes on an
+# interleaved scan, a broken restart sequence (resynchronised second pass)
+img = o.gen_image("photo", 320, 208)
+with o.segment_info():
+    want = o.encode(img, 75, 2, 1, sampling=(2, 2))
+assert np.array_equal(enc.encode(img, 75, 2, 1, subsampling="4:2:0", segment_info=1), want)
+d = g.Decoder()
+assert np.array_equal(d.decode(want), o.decode(want)) and d.used_segment_info()
+d.set_option("dec_opt_huffman_lanes", "8")
+assert np.array_equal(d.decode(want), o.decode(want)) and not d.used_segment_info()
+d.set_option("dec_opt_flipped", "1")
+d.set_option("dec_opt_huffman_lanes", "0")
+with o.flip_remap(True, None):
+    assert np.array_equal(d.decode(want), o.decode_any(want, o.FMT_444_P012, o.CS_RGB).reshape(208, 320, 3))
+d.close()
+e2 = g.Encoder()
+e2.set_option("enc_opt_flipped", "1")
+with o.flip_remap(True, None):
+    assert np.array_equal(e2.encode(img, 75, 4, 0), o.encode_any(np.ascontiguousarray(img).reshape(-1), 320, 208, o.FMT_444_P012, o.CS_RGB, 75, 4, 0, (1, 1)))
+e2.close()
+jpeg = bytearray(o.encode(o.gen_image("photo", 256, 192), 80, 4, 0))
+marks = [i for i in range(bytes(jpeg).find(b"\xff\xda"), len(jpeg) - 1) if jpeg[i] == 0xFF and 0xD0 <= jpeg[i + 1] <= 0xD7]
+jpeg[marks[5] + 1] = 0xD0 + ((jpeg[marks[5] + 1] - 0xD0 + 3) & 7)
+bad = np.frombuffer(bytes(jpeg), np.uint8)
+assert np.array_equal(dec.decode(bad), o.decode(bad))
+print("ok segment info / flip / resync", flush=True)
 print("all sanitizer cases ok")
