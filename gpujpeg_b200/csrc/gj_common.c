@@ -598,10 +598,45 @@ int gpujpeg_image_get_properties(const char* filename, struct gpujpeg_image_para
 
 int gpujpeg_image_destroy(uint8_t* image) { return gj_cuda_free_host(image); }
 
-void gpujpeg_image_range_info(const char* filename, int width, int height, enum gpujpeg_pixel_format sampling_factor)
+/* smallest and largest sample of every component of a raw image file, printed to stdout; packed 4:4:4 and UYVY only, as
+ * in the reference [ref: src/gpujpeg_common.c:1383-1442] */
+void gpujpeg_image_range_info(const char* filename, int width, int height, enum gpujpeg_pixel_format pixel_format)
 {
-    (void)filename; (void)width; (void)height; (void)sampling_factor;
-    GJ_WARN("gpujpeg_image_range_info is not implemented in this build\n");
+    uint8_t* image = NULL;
+    size_t size = 0;
+    if ( gpujpeg_image_load_from_file(filename, &image, &size) != 0 ) {
+        GJ_ERR("Failed to load image [%s]!\n", filename);
+        return;
+    }
+    int lo[3] = {256, 256, 256}, hi[3] = {0, 0, 0};
+    const size_t pixels = (size_t)(width > 0 ? width : 0) * (size_t)(height > 0 ? height : 0);
+    if ( pixel_format == GPUJPEG_444_U8_P012 && size >= pixels * 3 ) {
+        for ( size_t i = 0; i < pixels * 3; i++ ) {
+            const int c = (int)(i % 3), v = image[i];
+            if ( v < lo[c] ) lo[c] = v;
+            if ( v > hi[c] ) hi[c] = v;
+        }
+    }
+    else if ( pixel_format == GPUJPEG_422_U8_P1020 && size >= pixels * 2 ) {
+        /* U Y V Y: the odd bytes are luminance, the even ones alternate between the chrominance components; the reference
+         * files the byte of an even pixel under component 3 and that of an odd pixel under component 2 */
+        for ( size_t i = 0; i < pixels; i++ ) {
+            const int y = image[2 * i + 1], ch = image[2 * i], c = (i & 1) ? 1 : 2;
+            if ( y < lo[0] ) lo[0] = y;
+            if ( y > hi[0] ) hi[0] = y;
+            if ( ch < lo[c] ) lo[c] = ch;
+            if ( ch > hi[c] ) hi[c] = ch;
+        }
+    }
+    else {
+        GJ_ERR("gpujpeg_image_range_info handles 444-u8-p012 and 422-u8-p1020 files of at least width x height pixels only.\n");
+        gpujpeg_image_destroy(image);
+        return;
+    }
+    printf("Image Samples Range:\n");
+    for ( int c = 0; c < 3; c++ )
+        printf("Component %d: %d - %d\n", c + 1, lo[c], hi[c]);
+    gpujpeg_image_destroy(image);
 }
 
 /* "currently defunct" in the reference as well [ref: libgpujpeg/gpujpeg_common.h:455-470] */

@@ -261,3 +261,26 @@ def test_broken_restart_sequences_are_resynchronised_like_the_reference(gj, huff
         assert np.array_equal(d.decode(ok), o.decode(ok))
     finally:
         d.close()
+
+
+def test_image_range_info_prints_the_sample_ranges(gj, tmp_path, capfd):
+    """gpujpeg_image_range_info [ref: src/gpujpeg_common.c:1383-1442]: smallest and largest sample per component of a raw
+    file, packed 4:4:4 and UYVY (whose even pixels' chrominance byte is filed under component 3, odd pixels' under 2)"""
+    import ctypes as C
+    lib = gj.api.lib
+    lib.gpujpeg_image_range_info.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int]
+    lib.gpujpeg_image_range_info.restype = None
+    rgb = np.zeros((4, 6, 3), np.uint8)
+    rgb[..., 0], rgb[..., 1], rgb[..., 2] = 10, 20, 30
+    rgb[1, 2], rgb[3, 5] = (7, 99, 30), (200, 20, 1)
+    path = tmp_path / "a.rgb"
+    rgb.tofile(path)
+    lib.gpujpeg_image_range_info(str(path).encode(), 6, 4, 1)      # GPUJPEG_444_U8_P012
+    out = capfd.readouterr().out
+    assert "Component 1: 7 - 200" in out and "Component 2: 20 - 99" in out and "Component 3: 1 - 30" in out
+    uyvy = np.array([[50, 16, 60, 235, 40, 100, 90, 101]], np.uint8)   # U0 Y0 V0 Y1 | U1 Y2 V1 Y3
+    path = tmp_path / "b.uyvy"
+    uyvy.tofile(path)
+    lib.gpujpeg_image_range_info(str(path).encode(), 4, 1, 3)      # GPUJPEG_422_U8_P1020
+    out = capfd.readouterr().out
+    assert "Component 1: 16 - 235" in out and "Component 2: 60 - 90" in out and "Component 3: 40 - 50" in out
