@@ -513,15 +513,36 @@ static int tst_load(const char* filename, uint8_t** image, size_t* image_size)
     return 0;
 }
 
-/* returns a CUDA-pinned buffer, to be released with gpujpeg_image_destroy [ref: src/gpujpeg_common.c:1216-1256] */
+static void* pinned_alloc(size_t size)
+{
+    void* p = NULL;
+    if ( gj_cuda_malloc_host(&p, size ? size : 1) ) {
+        GJ_ERR("Could not alloc host pointer: %s\n", gj_cuda_last_error());
+        return NULL;
+    }
+    return p;
+}
+
+/* returns a CUDA-pinned buffer, to be released with gpujpeg_image_destroy [ref: src/gpujpeg_common.c:1216-1256].
+ * Netpbm and Y4M files are parsed (gj_imageio.c), .tst names are generated, everything else is read as it is. */
 int gpujpeg_image_load_from_file(const char* filename, uint8_t** image, size_t* image_size)
 {
     const enum gpujpeg_image_file_format format = gpujpeg_image_get_file_format(filename);
-    if ( format == GPUJPEG_IMAGE_FILE_TST ) return tst_load(filename, image, image_size);
-    if ( format != GPUJPEG_IMAGE_FILE_JPEG && !(GPUJPEG_IMAGE_FORMAT_IS_RAW(format) && format <= GPUJPEG_IMAGE_FILE_RGBA) &&
-         !(format >= GPUJPEG_IMAGE_FILE_YUV && format <= GPUJPEG_IMAGE_FILE_I420) ) {
-        GJ_ERR("Image file format of %s is not supported by this build (raw dumps, .jpg and .tst only)\n", filename);
-        return -1;
+    switch ( format ) {
+        case GPUJPEG_IMAGE_FILE_TST: return tst_load(filename, image, image_size);
+        case GPUJPEG_IMAGE_FILE_PGM:
+        case GPUJPEG_IMAGE_FILE_PPM:
+        case GPUJPEG_IMAGE_FILE_PNM:
+        case GPUJPEG_IMAGE_FILE_PAM:
+        case GPUJPEG_IMAGE_FILE_Y4M: return gj_imgfile_load(filename, image, image_size, pinned_alloc) ? 1 : 0;
+        case GPUJPEG_IMAGE_FILE_BMP:
+        case GPUJPEG_IMAGE_FILE_GIF:
+        case GPUJPEG_IMAGE_FILE_PNG:
+        case GPUJPEG_IMAGE_FILE_TGA:
+            GJ_ERR("Image file format of %s is not supported by this build (raw dumps, .jpg, .tst, PNM / PAM and Y4M only)\n",
+                   filename);
+            return -1;
+        default: break;
     }
     FILE* f = fopen(filename, "rb");
     if ( !f ) {
@@ -550,21 +571,41 @@ int gpujpeg_image_load_from_file(const char* filename, uint8_t** image, size_t* 
     return 0;
 }
 
+/* "name.XXX": the extension that can hold the image is filled in (the caller's string is written to, as in the reference)
+ * [ref: src/gpujpeg_common.c:1258-1275]; PNM / PAM / Y4M get their headers, other names a plain dump */
 int gpujpeg_image_save_to_file(const char* filename, const uint8_t* image, size_t image_size,
                                const struct gpujpeg_image_parameters* param_image)
 {
+    char* dot = strrchr(filename, '.');
+    if ( dot && strcmp(dot, ".XXX") == 0 && param_image ) {
+        const char* ext = param_image->pixel_format != GPUJPEG_U8 && param_image->color_space != GPUJPEG_RGB ? "y4m"
+                          : param_image->pixel_format == GPUJPEG_4444_U8_P0123                              ? "pam"
+                                                                                                            : "pnm";
+        memcpy(dot + 1, ext, 3);
+    }
     const enum gpujpeg_image_file_format format = gpujpeg_image_get_file_format(filename);
+    if ( param_image ) {
+        switch ( format ) {
+            case GPUJPEG_IMAGE_FILE_PAM: return gj_imgfile_save_pam(filename, param_image, image, 0);
+            case GPUJPEG_IMAGE_FILE_PGM:
+            case GPUJPEG_IMAGE_FILE_PPM:
+            case GPUJPEG_IMAGE_FILE_PNM: return gj_imgfile_save_pam(filename, param_image, image, 1);
+            case GPUJPEG_IMAGE_FILE_Y4M: return gj_imgfile_save_y4m(filename, param_image, image);
+            case GPUJPEG_IMAGE_FILE_BMP:
+            case GPUJPEG_IMAGE_FILE_GIF:
+            case GPUJPEG_IMAGE_FILE_PNG:
+            case GPUJPEG_IMAGE_FILE_TGA:
+                GJ_ERR("Image file format of %s is not supported by this build (raw dumps, .jpg, PNM / PAM and Y4M only)\n",
+                       filename);
+                return -1;
+            default: break;
+        }
+    }
     FILE* f = fopen(filename, "wb");
     if ( !f ) {
         GJ_ERR("Failed open %s for writing: %s\n", filename, strerror(errno));
         return -1;
     }
-    if ( (format == GPUJPEG_IMAGE_FILE_PPM || format == GPUJPEG_IMAGE_FILE_PNM) && param_image &&
-         param_image->pixel_format == GPUJPEG_444_U8_P012 )
-        fprintf(f, "P6\n%d %d\n255\n", param_image->width, param_image->height);
-    else if ( (format == GPUJPEG_IMAGE_FILE_PGM || format == GPUJPEG_IMAGE_FILE_PNM) && param_image &&
-              param_image->pixel_format == GPUJPEG_U8 )
-        fprintf(f, "P5\n%d %d\n255\n", param_image->width, param_image->height);
     if ( fwrite(image, 1, image_size, f) != image_size ) {
         GJ_ERR("Failed to write image data [%zd bytes] to file %s!\n", image_size, filename);
         fclose(f);
@@ -574,26 +615,68 @@ int gpujpeg_image_save_to_file(const char* filename, const uint8_t* image, size_
     return 0;
 }
 
+/* What a file name (and, for formats with a header, the file) says about the image.  Return values are the reference's:
+ * negative = error; raw formats return 1, PAM / PNM names of files still to be written return 1 as well
+ * [ref: src/gpujpeg_common.c:1311-1371, src/utils/image_delegate.c:149-205, 253-298] */
 int gpujpeg_image_get_properties(const char* filename, struct gpujpeg_image_parameters* param_image, int file_exists)
 {
-    (void)file_exists;
     const enum gpujpeg_image_file_format format = gpujpeg_image_get_file_format(filename);
     int pattern, arg;
     switch ( format ) {
         case GPUJPEG_IMAGE_FILE_TST: return tst_parse(filename, param_image, &pattern, &arg);
-        case GPUJPEG_IMAGE_FILE_RGB:
-            param_image->color_space = GPUJPEG_RGB;
-            param_image->pixel_format = GPUJPEG_444_U8_P012;
-            return 0;
-        case GPUJPEG_IMAGE_FILE_RGBA:
-            param_image->color_space = GPUJPEG_RGB;
-            param_image->pixel_format = GPUJPEG_4444_U8_P0123;
-            return 0;
-        case GPUJPEG_IMAGE_FILE_GRAY:
-            param_image->pixel_format = GPUJPEG_U8;
-            return 0;
-        default: return -1;
+        case GPUJPEG_IMAGE_FILE_PGM:
+        case GPUJPEG_IMAGE_FILE_PPM:
+        case GPUJPEG_IMAGE_FILE_PNM:
+        case GPUJPEG_IMAGE_FILE_PAM:
+            if ( !file_exists ) {
+                param_image->pixel_format = format == GPUJPEG_IMAGE_FILE_PGM   ? GPUJPEG_U8
+                                            : format == GPUJPEG_IMAGE_FILE_PPM ? GPUJPEG_444_U8_P012
+                                            : format == GPUJPEG_IMAGE_FILE_PNM ? GPUJPEG_PIXFMT_NO_ALPHA
+                                                                               : GPUJPEG_PIXFMT_AUTODETECT;
+                param_image->color_space = format == GPUJPEG_IMAGE_FILE_PGM ? GPUJPEG_YCBCR_JPEG : GPUJPEG_CS_DEFAULT;
+                return 1;
+            }
+            /* fall through */
+        case GPUJPEG_IMAGE_FILE_Y4M: {
+            if ( !file_exists ) {
+                param_image->color_space = GPUJPEG_YCBCR_BT601_256LVLS;
+                param_image->pixel_format = GPUJPEG_PIXFMT_STD;
+                return 0;
+            }
+            struct gj_imgfile f;
+            if ( gj_imgfile_probe(filename, &f) ) return GPUJPEG_ERROR;
+            return gj_imgfile_params(filename, &f, param_image);
+        }
+        case GPUJPEG_IMAGE_FILE_BMP:
+        case GPUJPEG_IMAGE_FILE_GIF:
+        case GPUJPEG_IMAGE_FILE_PNG:
+        case GPUJPEG_IMAGE_FILE_TGA:
+            GJ_ERR("Image file format of %s is not supported by this build\n", filename);
+            return -1;
+        case GPUJPEG_IMAGE_FILE_UNKNOWN: GJ_ERR("GPUJPEG_IMAGE_FILE_UNKNOWN should not be passed!\n"); return -1;
+        case GPUJPEG_IMAGE_FILE_JPEG: GJ_ERR("GPUJPEG_IMAGE_FILE_JPEG should not be passed!\n"); return -1;
+        default: break;
     }
+    switch ( format ) {   /* raw dumps: the extension names colour space and pixel format */
+        case GPUJPEG_IMAGE_FILE_RGB:
+        case GPUJPEG_IMAGE_FILE_RGBA: param_image->color_space = GPUJPEG_RGB; break;
+        case GPUJPEG_IMAGE_FILE_GRAY:
+        case GPUJPEG_IMAGE_FILE_YUV:
+        case GPUJPEG_IMAGE_FILE_YUVA:
+        case GPUJPEG_IMAGE_FILE_UYVY:
+        case GPUJPEG_IMAGE_FILE_I420: param_image->color_space = GPUJPEG_YCBCR_JPEG; break;
+        default: break;
+    }
+    switch ( format ) {
+        case GPUJPEG_IMAGE_FILE_RAW: param_image->pixel_format = GPUJPEG_PIXFMT_STD; break;
+        case GPUJPEG_IMAGE_FILE_GRAY: param_image->pixel_format = GPUJPEG_U8; break;
+        case GPUJPEG_IMAGE_FILE_RGBA:
+        case GPUJPEG_IMAGE_FILE_YUVA: param_image->pixel_format = GPUJPEG_4444_U8_P0123; break;
+        case GPUJPEG_IMAGE_FILE_UYVY: param_image->pixel_format = GPUJPEG_422_U8_P1020; break;
+        case GPUJPEG_IMAGE_FILE_I420: param_image->pixel_format = GPUJPEG_420_U8_P0P1P2; break;
+        default: param_image->pixel_format = GPUJPEG_444_U8_P012; break;   /* .rgb, .yuv */
+    }
+    return 1;
 }
 
 int gpujpeg_image_destroy(uint8_t* image) { return gj_cuda_free_host(image); }

@@ -233,6 +233,21 @@ int gj_reader_parse(const uint8_t* data, size_t size, struct gj_stream* s, int v
 /* split scan data at RSTn markers: fills seg_off/seg_len (file offsets of stuffed entropy bytes) */
 int gj_reader_split(const uint8_t* data, struct gj_stream* s, uint32_t* seg_off, uint32_t* seg_len, int max_segments);
 
+/* ---- image files (gj_imageio.c)  [ref: src/utils/image_delegate.c, src/utils/pam.c, src/utils/y4m.c] ---- */
+enum { GJ_IMGFILE_PNM = 1, GJ_IMGFILE_PAM, GJ_IMGFILE_Y4M };
+struct gj_imgfile {
+    int kind;
+    int width, height;
+    int channels, maxval;              /* Netpbm */
+    int subsampling, bitdepth, limited; /* Y4M: 400 / 420 / 422 / 444 / 4444 */
+    size_t data_offset, data_bytes;    /* where the samples are in the file */
+};
+int gj_imgfile_probe(const char* filename, struct gj_imgfile* f);
+int gj_imgfile_params(const char* filename, const struct gj_imgfile* f, struct gpujpeg_image_parameters* pi);
+int gj_imgfile_load(const char* filename, uint8_t** image, size_t* image_size, void* (*alloc)(size_t));
+int gj_imgfile_save_pam(const char* filename, const struct gpujpeg_image_parameters* pi, const uint8_t* data, int pnm);
+int gj_imgfile_save_y4m(const char* filename, const struct gpujpeg_image_parameters* pi, const uint8_t* data);
+
 /* ---- device side: the C-ABI stage launchers (implemented in *.cu) ---- */
 typedef struct CUstream_st* gj_stream_t;
 

@@ -4,8 +4,8 @@
  *
  * Built by oracle/Makefile into oracle/_ref/libgpujpeg_refcpu.so together with the reference's
  *   gpujpeg_huffman_cpu_encoder.c, gpujpeg_huffman_cpu_decoder.c, gpujpeg_table.c,
- *   gpujpeg_dct_cpu.c, gpujpeg_writer.c
- * The handful of CUDA-runtime / exif symbols those files reference are satisfied by the host
+ *   gpujpeg_dct_cpu.c, gpujpeg_writer.c, gpujpeg_exif.c, utils/pam.c, utils/y4m.c
+ * The handful of CUDA-runtime symbols those files reference are satisfied by the host
  * stubs below (the library must run on machines without a GPU; no libcudart is linked).
  *
  * What is exercised here is exactly SURVEY.md section 8a rows a3, a4, a8, a9, a12, a14.
@@ -22,6 +22,7 @@
 #include "src/gpujpeg_marker.h"
 #include "src/gpujpeg_table.h"
 #include "src/gpujpeg_writer.h"
+#include "src/gpujpeg_exif.h"
 
 /* ---- host stand-ins for the CUDA runtime calls made by the reference's CPU-side files ---- */
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t count, enum cudaMemcpyKind kind)
@@ -35,16 +36,12 @@ const char* cudaGetErrorString(cudaError_t e) { (void)e; return "host stub"; }
 cudaError_t cudaMallocHost(void** p, size_t size) { *p = malloc(size); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 /* symbols referenced by gpujpeg_writer.c / gpujpeg_dct_cpu.c that are never reached here */
-struct gpujpeg_exif_tags;
-void gpujpeg_writer_write_exif(struct gpujpeg_writer* w, const struct gpujpeg_parameters* p,
-                               const struct gpujpeg_image_parameters* pi, const struct gpujpeg_image_metadata* m,
-                               const struct gpujpeg_exif_tags* t)
-{
-    (void)w; (void)p; (void)pi; (void)m; (void)t;
-    abort();
-}
-void gpujpeg_exif_tags_destroy(struct gpujpeg_exif_tags* t) { (void)t; }
 int gpujpeg_coder_allocate_cpu_huffman_buf(struct gpujpeg_coder* c) { (void)c; abort(); }
+/* defined in the reference's gpujpeg_common.c (CUDA-bound, not compiled here); used by the messages of gpujpeg_exif.c */
+const char* gj_fg_red = "";
+const char* gj_fg_yellow = "";
+const char* gj_term_reset = "";
+const char* gpujpeg_color_space_get_name(enum gpujpeg_color_space cs) { (void)cs; return "(colour space)"; }
 
 /* ---- geometry restated without CUDA allocations [ref: src/gpujpeg_common.c:676-865] ---- */
 struct geom {
@@ -140,6 +137,28 @@ static int g_internal_rgb = 0;   /* components of an RGB-internal JPEG are all o
 static int g_internal_cs = 0;    /* other internal colour space (enum gpujpeg_color_space), 0 = YCbCr JPEG */
 static int g_header_type = 0;    /* forced header flavour (enum gpujpeg_header_type), 0 = by colour space */
 void ref_set_header_type(int t) { g_header_type = t; }
+/* orientation metadata and custom Exif tags handed to the reference writer [ref: src/gpujpeg_encoder.c:700-779] */
+static struct gpujpeg_image_metadata g_metadata;
+static struct gpujpeg_exif_tags* g_exif_tags = NULL;
+void ref_set_orientation(int set, int rotation, int flip)
+{
+    g_metadata.vals[GPUJPEG_METADATA_ORIENTATION].set = set;
+    g_metadata.vals[GPUJPEG_METADATA_ORIENTATION].orient.rotation = rotation;
+    g_metadata.vals[GPUJPEG_METADATA_ORIENTATION].orient.flip = flip;
+}
+int ref_add_exif_tag(const char* cfg) { return gpujpeg_exif_add_tag(&g_exif_tags, cfg) ? 0 : -1; }
+void ref_clear_exif_tags(void) { g_exif_tags = NULL; /* (the reference's destroy routine walks its lists wrongly; leak) */ }
+/* the reference's Exif APP1 parser on a buffer that starts at the segment's length field; returns what it found:
+ * bit 0 = orientation set, bits 8.. = rotation, bit 4 = flip */
+int ref_exif_parse(uint8_t* seg, size_t size)
+{
+    struct gpujpeg_image_metadata m;
+    memset(&m, 0, sizeof m);
+    uint8_t* p = seg;
+    gpujpeg_exif_parse(&p, seg + size, 0, &m);
+    return (m.vals[GPUJPEG_METADATA_ORIENTATION].set ? 1 : 0) | (m.vals[GPUJPEG_METADATA_ORIENTATION].orient.flip ? 16 : 0) |
+           (m.vals[GPUJPEG_METADATA_ORIENTATION].orient.rotation << 8);
+}
 
 size_t ref_encode_from_coef_ss(int16_t* coef, int w, int h, int comps, int quality, int rst, int interleaved, int lhs,
                                int lvs, uint8_t* out, size_t out_cap)
@@ -185,6 +204,8 @@ size_t ref_encode_from_coef_ss(int16_t* coef, int w, int h, int comps, int quali
     wr.buffer = out;
     wr.buffer_current = out;
     wr.buffer_allocated_size = out_cap;
+    wr.metadata = g_metadata;
+    wr.exif_tags = g_exif_tags;
     enc->writer = &wr;
     gpujpeg_writer_write_header(enc);
     size_t n = 0;

@@ -1,6 +1,7 @@
 """Builds and loads the two CPU shims under tests/cpu_shims (test infrastructure):
    kernel_math.so : the kernels' per-thread arithmetic (gj_device.cuh) compiled for the host
-   host_shim.so   : internal host functions of the product (tables, writer, reader)"""
+   host_shim.so   : internal host functions of the product (tables, writer, reader)
+   io_shim.so     : the product's public image-file helpers (gj_common.c + gj_imageio.c) over host stand-ins for CUDA"""
 import ctypes as C
 import os
 import subprocess
@@ -28,10 +29,16 @@ def _build():
     srcs = [os.path.join(SH, "host_shim.c"), os.path.join(CSRC, "gj_tables.c"), os.path.join(CSRC, "gj_codestream.c")]
     if _stale(hs, srcs + [os.path.join(CSRC, "gj_internal.h")]):
         subprocess.check_call(["/usr/bin/gcc", "-O2", "-std=gnu11", "-shared", "-fPIC", "-o", hs] + srcs)
-    return km, hs
+    io = os.path.join(SH, "io_shim.so")
+    srcs = [os.path.join(SH, "cuda_stub.c")] + [os.path.join(CSRC, f) for f in ("gj_common.c", "gj_imageio.c", "gj_tables.c",
+                                                                                "gj_codestream.c")]
+    if _stale(io, srcs + [os.path.join(CSRC, "gj_internal.h")]):
+        subprocess.check_call(["/usr/bin/gcc", "-O2", "-std=gnu11", "-shared", "-fPIC", "-o", io] + srcs)
+    return km, hs, io
 
 
-_km, _hs = _build()
+_km, _hs, _io = _build()
+io = C.CDLL(_io)
 km = C.CDLL(_km)
 km.km_check_rgb_to_ycbcr_exhaustive.restype = C.c_long
 km.km_check_ycbcr_to_rgb_exhaustive.restype = C.c_long
