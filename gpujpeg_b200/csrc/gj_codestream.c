@@ -234,15 +234,19 @@ static int comp_id(const struct gpujpeg_parameters* param, int c)
 
 /* Everything before the first SOS.  The header flavour follows the internal colour space unless the caller forces one
  * (enc_hdr option): SPIFF names the colour space (BT.601 / BT.709 need it), Adobe APP14 marks RGB, JFIF is the default for
- * YCbCr JPEG.  Exif and orientation metadata are outside the hot path.  [ref: src/gpujpeg_writer.c:451-518] */
+ * YCbCr JPEG, Exif on request (gj_exif.c).  An orientation goes into the SPIFF directory or the Exif header.
+ * [ref: src/gpujpeg_writer.c:451-518] */
 size_t gj_write_header(uint8_t* out, const struct gpujpeg_parameters* param,
                        const struct gpujpeg_image_parameters* pi, const uint8_t raw_q[2][64],
-                       const struct gj_huff_spec spec[2][2], enum gpujpeg_header_type header_type)
+                       const struct gj_huff_spec spec[2][2], enum gpujpeg_header_type header_type,
+                       const struct gj_header_extras* extras)
 {
     uint8_t* p = out;
     p = wmark(p, 0xD8);
-    if ( header_type == GPUJPEG_HEADER_DEFAULT )
-        header_type = (param->color_space_internal == GPUJPEG_YCBCR_BT601 || param->color_space_internal == GPUJPEG_YCBCR_BT709)
+    const int oriented = extras && extras->metadata.vals[GPUJPEG_METADATA_ORIENTATION].set;
+    if ( header_type == GPUJPEG_HEADER_DEFAULT )   /* four components and an orientation need SPIFF to be described */
+        header_type = (param->comp_count == 4 || oriented || param->color_space_internal == GPUJPEG_YCBCR_BT601 ||
+                       param->color_space_internal == GPUJPEG_YCBCR_BT709)
                           ? GPUJPEG_HEADER_SPIFF
                           : param->color_space_internal == GPUJPEG_RGB ? GPUJPEG_HEADER_ADOBE : GPUJPEG_HEADER_JFIF;
     if ( header_type == GPUJPEG_HEADER_SPIFF ) {
@@ -268,10 +272,21 @@ size_t gj_write_header(uint8_t* out, const struct gpujpeg_parameters* param,
         p = w8(p, 0);                                                          /* resolution units: ratio */
         p = w16(p, 0); p = w16(p, 1);
         p = w16(p, 0); p = w16(p, 1);
+        if ( oriented ) {   /* directory entry 4: quarter turns clockwise, mirrored [ref: src/gpujpeg_writer.c:226-238] */
+            p = wmark(p, 0xE8);
+            p = w16(p, 10);
+            p = w16(p, 0); p = w16(p, 4);
+            p = w8(p, extras->metadata.vals[GPUJPEG_METADATA_ORIENTATION].orient.rotation);
+            p = w8(p, extras->metadata.vals[GPUJPEG_METADATA_ORIENTATION].orient.flip);
+            p = w16(p, 0);
+        }
         p = wmark(p, 0xE8);
         p = w16(p, 8);
         p = w16(p, 0); p = w16(p, 1);                                          /* end of directory */
         p = wmark(p, 0xD8);
+    }
+    else if ( header_type == GPUJPEG_HEADER_EXIF ) {
+        p += gj_exif_write(p, param, pi, extras ? &extras->metadata : NULL, extras ? extras->exif_tags : NULL);
     }
     else if ( header_type == GPUJPEG_HEADER_ADOBE ) {
         /* Adobe APP14, transform 0 -- also when forced onto a YCbCr stream, as the reference writes it
@@ -474,9 +489,38 @@ int gj_reader_walk(const uint8_t* d, size_t size, size_t* pos, struct gj_stream*
             case 0xE0:
                 if ( n >= 5 && memcmp(b, "JFIF", 5) == 0 ) s->header_type = GPUJPEG_HEADER_JFIF;
                 break;
+            case 0xE1:   /* Exif: the orientation [ref: src/gpujpeg_reader.c:311-333] */
+                if ( n >= 5 && memcmp(b, "Exif", 5) == 0 ) {
+                    s->header_type = GPUJPEG_HEADER_EXIF;
+                    s->exif_seen = 1;
+                    gj_exif_parse(b, (size_t)n, d + size, s->verbose, &s->metadata);
+                }
+                else GJ_WARN("Skipping unsupported APP1 marker \"%.*s\"!\n", (int)strnlen((const char*)b, (size_t)(n < 49 ? n : 49)), (const char*)b);
+                break;
             case 0xE8:   /* SPIFF header: colour space code [ref: src/gpujpeg_reader.c:393-443, 504-543] */
+                if ( s->in_spiff_directory ) {   /* directory entries up to "end of directory" [ref: src/gpujpeg_reader.c:446-483] */
+                    if ( len < 8 ) {
+                        GJ_ERR("APP8 SPIFF directory too short (%d bytes)\n", len);
+                        return -1;
+                    }
+                    const uint32_t tag = (uint32_t)b[0] << 24 | (uint32_t)b[1] << 16 | (uint32_t)b[2] << 8 | b[3];
+                    if ( tag == 1 && len == 8 ) {
+                        s->in_spiff_directory = 0;
+                        if ( d[i + 8] != 0xFF || d[i + 9] != 0xD8 ) {   /* (the entry's length covers the SOI) */
+                            GJ_VERBOSE(s->verbose, "SPIFF entry 0x1 should be followed directly with SOI.\n");
+                            return -1;
+                        }
+                    }
+                    else if ( tag == 4 && n >= 6 ) {
+                        s->metadata.vals[GPUJPEG_METADATA_ORIENTATION].orient.rotation = b[4] & 3u;
+                        s->metadata.vals[GPUJPEG_METADATA_ORIENTATION].orient.flip = b[5] != 0;
+                        s->metadata.vals[GPUJPEG_METADATA_ORIENTATION].set = 1;
+                    }
+                    break;
+                }
                 if ( len == 32 && memcmp(b, "SPIFF", 6) == 0 && s->header_type != GPUJPEG_HEADER_SPIFF ) {
                     s->header_type = GPUJPEG_HEADER_SPIFF;
+                    s->in_spiff_directory = 1;
                     switch ( b[18] ) {
                         case 1: s->spiff_color_space = GPUJPEG_YCBCR_BT709; break;
                         case 3: case 8: s->spiff_color_space = GPUJPEG_YCBCR_BT601_256LVLS; break;
@@ -645,6 +689,7 @@ void gj_reader_begin(struct gj_stream* s, int ff_cs_itu601_is_709)
 enum gpujpeg_color_space gj_stream_color_space(const struct gj_stream* s, int adobe_transform)
 {
     if ( s->spiff_color_space != GPUJPEG_NONE && s->comp_count != 1 ) return (enum gpujpeg_color_space)s->spiff_color_space;
+    if ( s->exif_seen ) return GPUJPEG_YCBCR_BT601_256LVLS;   /* [ref: src/gpujpeg_reader.c:327] */
     if ( s->com_color_space != GPUJPEG_NONE && s->comp_count == 3 ) return (enum gpujpeg_color_space)s->com_color_space;
     if ( s->comp_count == 3 &&
          (adobe_transform == 0 || (s->comp_id[0] == 'R' && s->comp_id[1] == 'G' && s->comp_id[2] == 'B')) )

@@ -519,6 +519,7 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     /* ---- host reader, part 1: marker segments up to the first SOS (never touches entropy-coded data) ---- */
     struct gj_stream st;
     gj_reader_begin(&st, d->ff_cs_itu601_is_709);
+    st.verbose = d->verbose;
     if ( image_size < 4 || image[0] != 0xFF || image[1] != 0xD8 ) {
         GJ_ERR("JPEG data should begin with SOI marker!\n");
         return GPUJPEG_ERROR;
@@ -699,6 +700,7 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
     }
     }   /* K0 path */
     if ( gj_reader_finish(&st, adobe, d->verbose) ) return GPUJPEG_ERROR;
+    d->metadata = st.metadata;   /* handed out with the output [ref: src/gpujpeg_reader.c:1626-1636, src/gpujpeg_decoder.c:466] */
     if ( st.color_space != early_cs ) {
         GJ_ERR("The stream's colour space (%s) is announced after its first scan header; not supported.\n",
                gpujpeg_color_space_get_name(st.color_space));
@@ -985,6 +987,7 @@ int gpujpeg_decoder_get_image_info2(uint8_t* image, size_t image_size, struct gp
         info->param.sampling_factor[c].vertical = (uint8_t)(st.comp_hv[c] & 15);
     }
     info->header_type = st.header_type;
+    info->metadata = st.metadata;
     info->comment = st.comment;
     info->segment_count = 0;
     if ( flags & GPUJPEG_COUNT_SEG_COUNT_REQ ) {

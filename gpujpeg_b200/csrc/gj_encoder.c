@@ -68,7 +68,9 @@ struct gpujpeg_encoder {
 
     /* host output */
     uint8_t* out; size_t out_size; int out_is_pinned;
-    uint8_t header[1024]; size_t header_size;
+    uint8_t* header; size_t header_cap; size_t header_size;   /* file header, composed on the host */
+    struct gj_header_extras extras;            /* enc_metadata (orientation), enc_exif_tag (user tags, owned) */
+    int extras_dirty;                          /* an option changed what the header carries */
 
     /* timers [ref: src/gpujpeg_common_internal.h:414-422] */
     struct gj_timer t_to, t_from, t_pre, t_huff, t_gpu;
@@ -153,6 +155,8 @@ int gpujpeg_encoder_destroy(struct gpujpeg_encoder* e)
     gj_cuda_free(e->d_info);
     gj_cuda_free(e->d_sos);
     free(e->h_pre);
+    free(e->header);
+    gj_exif_tags_destroy((struct gj_exif_tags*)e->extras.exif_tags);
     gj_cuda_free(e->d_seg_pos);
     if ( e->h_seg_pos ) gj_cuda_free_host(e->h_seg_pos);
     gj_cuda_free_host(e->h_info);
@@ -570,10 +574,27 @@ int gpujpeg_encoder_encode(struct gpujpeg_encoder* e, const struct gpujpeg_param
     e->param.perf_stats = a.perf_stats;
     const struct gj_geometry* g = &e->geo;
 
-    if ( tables_dirty || geometry_dirty || e->header_written != e->header_type ) {
+    /* an Exif header carries the time of day: composed for every frame, as the reference does for all headers */
+    if ( tables_dirty || geometry_dirty || e->header_written != e->header_type || e->extras_dirty ||
+         e->header_type == GPUJPEG_HEADER_EXIF ) {
         e->header_written = e->header_type;
+        e->extras_dirty = 0;
+        const size_t need = GJ_HEADER_BASE_CAP + gj_exif_tags_bytes(e->extras.exif_tags);
+        if ( need > e->header_cap ) {
+            free(e->header);
+            e->header = (uint8_t*)malloc(need);
+            e->header_cap = e->header ? need : 0;
+            if ( !e->header ) {
+                GJ_ERR("Encoder header allocation failed (%zu bytes).\n", need);
+                return GPUJPEG_ERROR;
+            }
+        }
         /* host codestream writer: file header + SOS headers, composed once per parameter change */
-        e->header_size = gj_write_header(e->header, &e->param, &e->param_image, e->raw_q, e->spec, e->header_type);
+        e->header_size = gj_write_header(e->header, &e->param, &e->param_image, e->raw_q, e->spec, e->header_type, &e->extras);
+        if ( e->header_size + 64 > g->stream_cap ) {
+            GJ_ERR("The header (%zu bytes) does not fit the stream buffer of a %dx%d image.\n", e->header_size, g->width, g->height);
+            return GPUJPEG_ERROR;
+        }
         /* what precedes every scan's data: [APP13 segment-info headers, positions filled in after the frame is coded] SOS */
         e->with_segment_info = e->param.segment_info && e->param.restart_interval > 0;
         size_t pre_total = 0;
@@ -799,11 +820,39 @@ int gpujpeg_encoder_get_stats(struct gpujpeg_encoder* encoder, struct gpujpeg_du
 /* [ref: src/gpujpeg_encoder.c:728-733] */
 void gpujpeg_encoder_set_jpeg_header(struct gpujpeg_encoder* encoder, enum gpujpeg_header_type header_type)
 {
-    if ( header_type == GPUJPEG_HEADER_EXIF ) {
-        GJ_WARN("The Exif header is not implemented in this build; request ignored.\n");
-        return;
-    }
     encoder->header_type = header_type;
+}
+
+/* enc_metadata=orientation=<deg>[-]: quarter turns clockwise, '-' = mirrored afterwards [ref: src/gpujpeg_encoder.c:700-734] */
+static int add_metadata(struct gpujpeg_image_metadata* metadata, const char* config)
+{
+    if ( strstr(config, "help") != NULL ) {
+        printf(GPUJPEG_ENC_OPT_METADATA " usage:\n"
+               "\t" GPUJPEG_ENC_OPT_METADATA "=orientation=<deg>[-]\n"
+               "\t\t<deg> - clockwise rotation - 0, 90, 180 or 270 degrees\n"
+               "\t\t'-'   - mirror the image horizontally after rotation applied\n");
+        return GPUJPEG_ERROR;
+    }
+    static const char key[] = "orientation=";
+    if ( strncmp(config, key, sizeof key - 1) != 0 ) {
+        printf("Wrong metadata item: %s\n", config);
+        return GPUJPEG_ERROR;
+    }
+    char* end = NULL;
+    const long deg = strtol(config + sizeof key - 1, &end, 10);
+    int flip = 0;
+    if ( *end == '-' ) {
+        flip = 1;
+        end++;
+    }
+    if ( *end != '\0' || deg < 0 || deg > 270 || deg % 90 != 0 ) {
+        printf("Wrong orientation value: %s\n", config);
+        return GPUJPEG_ERROR;
+    }
+    metadata->vals[GPUJPEG_METADATA_ORIENTATION].set = 1;
+    metadata->vals[GPUJPEG_METADATA_ORIENTATION].orient.rotation = (unsigned)(deg / 90);
+    metadata->vals[GPUJPEG_METADATA_ORIENTATION].orient.flip = (unsigned)flip;
+    return GPUJPEG_NOERR;
 }
 
 /* [ref: src/gpujpeg_encoder.c:736-800] */
@@ -829,10 +878,6 @@ int gpujpeg_encoder_set_option(struct gpujpeg_encoder* encoder, const char* opt,
             GJ_ERR("Unknown encoder header type: %s\n", val);
             return GPUJPEG_ERROR;
         }
-        if ( t == GPUJPEG_HEADER_EXIF ) {
-            GJ_ERR("The Exif header is not implemented in this build.\n");
-            return GPUJPEG_ERROR;
-        }
         encoder->header_type = t;
         return GPUJPEG_NOERR;
     }
@@ -848,9 +893,14 @@ int gpujpeg_encoder_set_option(struct gpujpeg_encoder* encoder, const char* opt,
         encoder->channel_remap = m;
         return GPUJPEG_NOERR;
     }
-    if ( strcmp(opt, GPUJPEG_ENC_OPT_EXIF_TAG) == 0 || strcmp(opt, GPUJPEG_ENC_OPT_METADATA) == 0 ) {
-        GJ_ERR("Encoder option %s is not implemented in this build.\n", opt);
-        return GPUJPEG_ERROR;
+    if ( strcmp(opt, GPUJPEG_ENC_OPT_EXIF_TAG) == 0 ) {   /* a user tag asks for the Exif header [ref: src/gpujpeg_encoder.c:773-776] */
+        encoder->header_type = GPUJPEG_HEADER_EXIF;
+        encoder->extras_dirty = 1;
+        return gj_exif_add_tag((struct gj_exif_tags**)&encoder->extras.exif_tags, val) == 0 ? GPUJPEG_NOERR : GPUJPEG_ERROR;
+    }
+    if ( strcmp(opt, GPUJPEG_ENC_OPT_METADATA) == 0 ) {   /* [ref: src/gpujpeg_encoder.c:777-779] */
+        encoder->extras_dirty = 1;
+        return add_metadata(&encoder->extras.metadata, val);
     }
     GJ_ERR("Invalid encoder option: %s!\n", opt);
     return GPUJPEG_ERROR;
@@ -860,8 +910,10 @@ void gpujpeg_encoder_print_options(void)
 {
     printf("\t" GPUJPEG_ENC_OPT_OUT "=[" GPUJPEG_ENC_OUT_VAL_PAGEABLE "|" GPUJPEG_ENC_OUT_VAL_PINNED
            "] - output buffer in pageable or pinned host memory\n");
-    printf("\t" GPUJPEG_ENC_OPT_HDR "=[" GPUJPEG_ENC_HDR_VAL_JFIF "|" GPUJPEG_ENC_HDR_VAL_ADOBE "|" GPUJPEG_ENC_HDR_VAL_SPIFF
+    printf("\t" GPUJPEG_ENC_OPT_HDR "=[" GPUJPEG_ENC_HDR_VAL_JFIF "|" GPUJPEG_ENC_HDR_VAL_ADOBE "|" GPUJPEG_ENC_HDR_VAL_EXIF "|" GPUJPEG_ENC_HDR_VAL_SPIFF
            "] - output JPEG header (default: by internal colour space)\n");
+    printf("\t" GPUJPEG_ENC_OPT_EXIF_TAG "=<key>=<value>|help - custom EXIF tag (use help for syntax)\n");
+    printf("\t" GPUJPEG_ENC_OPT_METADATA "=<key>=<value>|help - set image metadata\n");
     printf("\t" GPUJPEG_ENC_OPT_FLIPPED_BOOL "=[" GPUJPEG_VAL_FALSE "|" GPUJPEG_VAL_TRUE
            "] - whether is the input image should be vertically flipped (prior encode)\n");
     printf("\t" GPUJPEG_ENC_OPT_CHANNEL_REMAP "=XYZ[W] - input channel mapping, eg. '210F' for GBRX,\n"

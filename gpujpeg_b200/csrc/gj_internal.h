@@ -175,9 +175,25 @@ int gj_geometry_init(struct gj_geometry* g, const struct gpujpeg_parameters* par
                      const struct gpujpeg_image_parameters* param_image);
 
 /* ---- codestream writer (gj_writer.c)  [ref: src/gpujpeg_writer.c] ---- */
+/* what a header may carry besides the coding parameters: orientation (SPIFF directory entry / Exif tag) and user Exif tags */
+struct gj_exif_tags;
+struct gj_header_extras {
+    struct gpujpeg_image_metadata metadata;
+    const struct gj_exif_tags* exif_tags;
+};
+#define GJ_HEADER_BASE_CAP 1024   /* bytes a header needs at most without user Exif tags */
 size_t gj_write_header(uint8_t* out, const struct gpujpeg_parameters* param,
                        const struct gpujpeg_image_parameters* param_image, const uint8_t raw_q[2][64],
-                       const struct gj_huff_spec spec[2][2], enum gpujpeg_header_type header_type);
+                       const struct gj_huff_spec spec[2][2], enum gpujpeg_header_type header_type,
+                       const struct gj_header_extras* extras /* may be NULL */);
+/* ---- Exif (gj_exif.c)  [ref: src/gpujpeg_exif.c] ---- */
+int gj_exif_add_tag(struct gj_exif_tags** tags, const char* cfg);   /* enc_exif_tag option value; 0 on success */
+void gj_exif_tags_destroy(struct gj_exif_tags* tags);
+size_t gj_exif_tags_bytes(const struct gj_exif_tags* tags);          /* what the user tags add to the header, at most */
+size_t gj_exif_write(uint8_t* out, const struct gpujpeg_parameters* param, const struct gpujpeg_image_parameters* pi,
+                     const struct gpujpeg_image_metadata* metadata, const struct gj_exif_tags* tags);
+void gj_exif_parse(const uint8_t* seg, size_t len, const uint8_t* file_end, int verbose, struct gpujpeg_image_metadata* metadata);
+unsigned gj_exif_orientation_code(const struct gpujpeg_orientation* o);
 size_t gj_write_sos(uint8_t* out, const struct gpujpeg_parameters* param, int scan_index);
 /* APP13 "segment info" headers of a scan (the positions left zero) [ref: src/gpujpeg_writer.c:553-599]; out == NULL: size only */
 #define GJ_SEGINFO_CHUNK (65536 - 100)   /* position bytes per header [ref: src/gpujpeg_common_internal.h:91] */
@@ -216,6 +232,10 @@ struct gj_stream {
     struct gj_seginfo seginfo_pending;        /* headers met since the last SOS */
     enum gpujpeg_color_space color_space;
     int spiff_color_space;   /* colour space named by a SPIFF header, GPUJPEG_NONE (0) if there is none */
+    int in_spiff_directory;  /* between the SPIFF header and its end-of-directory entry */
+    int exif_seen;           /* an Exif APP1 header: the components are YCbCr JPEG whatever their ids say */
+    int verbose;             /* in: log level of the reader's messages */
+    struct gpujpeg_image_metadata metadata;   /* orientation from a SPIFF directory entry or an Exif header */
     int com_color_space;     /* colour space named by FFmpeg's COM "CS=ITU601", GPUJPEG_NONE (0) if there is none */
     int ff_cs_itu601_is_709; /* in: read that comment as BT.709 [ref: libgpujpeg/gpujpeg_decoder.h:95] */
     enum gpujpeg_header_type header_type;

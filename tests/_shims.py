@@ -26,12 +26,13 @@ def _build():
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-o", km,
                                os.path.join(SH, "kernel_math.cpp")])
     hs = os.path.join(SH, "host_shim.so")
-    srcs = [os.path.join(SH, "host_shim.c"), os.path.join(CSRC, "gj_tables.c"), os.path.join(CSRC, "gj_codestream.c")]
+    srcs = [os.path.join(SH, "host_shim.c"), os.path.join(CSRC, "gj_tables.c"), os.path.join(CSRC, "gj_codestream.c"),
+            os.path.join(CSRC, "gj_exif.c"), os.path.join(SH, "names_stub.c")]
     if _stale(hs, srcs + [os.path.join(CSRC, "gj_internal.h")]):
         subprocess.check_call(["/usr/bin/gcc", "-O2", "-std=gnu11", "-shared", "-fPIC", "-o", hs] + srcs)
     io = os.path.join(SH, "io_shim.so")
     srcs = [os.path.join(SH, "cuda_stub.c")] + [os.path.join(CSRC, f) for f in ("gj_common.c", "gj_imageio.c", "gj_tables.c",
-                                                                                "gj_codestream.c")]
+                                                                                "gj_codestream.c", "gj_exif.c")]
     if _stale(io, srcs + [os.path.join(CSRC, "gj_internal.h")]):
         subprocess.check_call(["/usr/bin/gcc", "-O2", "-std=gnu11", "-shared", "-fPIC", "-o", io] + srcs)
     return km, hs, io

@@ -6,6 +6,19 @@
 
 static int g_header_type = 0;   /* GPUJPEG_HEADER_DEFAULT; shim_set_header_type forces a flavour (enc_hdr option) */
 void shim_set_header_type(int t) { g_header_type = t; }
+static struct gj_header_extras g_extras;   /* orientation and user Exif tags of the headers composed below */
+void shim_set_orientation(int set, int rotation, int flip)
+{
+    g_extras.metadata.vals[GPUJPEG_METADATA_ORIENTATION].set = set != 0;
+    g_extras.metadata.vals[GPUJPEG_METADATA_ORIENTATION].orient.rotation = (unsigned)rotation & 3u;
+    g_extras.metadata.vals[GPUJPEG_METADATA_ORIENTATION].orient.flip = flip != 0;
+}
+int shim_add_exif_tag(const char* cfg) { return gj_exif_add_tag((struct gj_exif_tags**)&g_extras.exif_tags, cfg); }
+void shim_clear_exif_tags(void)
+{
+    gj_exif_tags_destroy((struct gj_exif_tags*)g_extras.exif_tags);
+    g_extras.exif_tags = NULL;
+}
 
 int shim_header(int width, int height, int quality, int rst, int interleaved, unsigned char* out)
 {
@@ -31,7 +44,7 @@ int shim_header(int width, int height, int quality, int rst, int interleaved, un
         for ( int k = 0; k < 2; k++ )
             gj_huff_spec_default(t, k, &spec[t][k]);
     }
-    size_t n = gj_write_header(out, &p, &pi, raw, spec, (enum gpujpeg_header_type)g_header_type);
+    size_t n = gj_write_header(out, &p, &pi, raw, spec, (enum gpujpeg_header_type)g_header_type, &g_extras);
     n += gj_write_sos(out + n, &p, 0);
     return (int)n;
 }
@@ -116,6 +129,19 @@ int shim_parse(const unsigned char* data, size_t size, int* info /*[8]*/, unsign
     info[6] = (int)s.header_size;
     info[7] = (int)s.color_space;
     return gj_reader_split(data, &s, seg_off, seg_len, max_seg);
+}
+
+/* header flavour and orientation metadata the reader finds: out = {header type, orientation set, rotation, flip, colour space} */
+int shim_parse_meta(const unsigned char* data, size_t size, int* out /*[5]*/)
+{
+    struct gj_stream s;
+    if ( gj_reader_parse(data, size, &s, 0) ) return -1;
+    out[0] = (int)s.header_type;
+    out[1] = (int)s.metadata.vals[GPUJPEG_METADATA_ORIENTATION].set;
+    out[2] = (int)s.metadata.vals[GPUJPEG_METADATA_ORIENTATION].orient.rotation;
+    out[3] = (int)s.metadata.vals[GPUJPEG_METADATA_ORIENTATION].orient.flip;
+    out[4] = (int)s.color_space;
+    return 0;
 }
 
 int shim_geometry(int width, int height, int rst, int interleaved, long* out /*[8]*/)
@@ -218,7 +244,7 @@ int shim_header2(int width, int height, int quality, int rst, int interleaved, i
         for ( int k = 0; k < 2; k++ )
             gj_huff_spec_default(t, k, &spec[t][k]);
     }
-    size_t n = gj_write_header(out, &p, &pi, raw, spec, (enum gpujpeg_header_type)g_header_type);
+    size_t n = gj_write_header(out, &p, &pi, raw, spec, (enum gpujpeg_header_type)g_header_type, &g_extras);
     n += gj_write_sos(out + n, &p, 0);
     return (int)n;
 }
