@@ -163,7 +163,8 @@ def image_parameters(width, height, width_padding=0, pixel_format=None, color_sp
 
 # enum gpujpeg_pixel_format / gpujpeg_color_space values used by the helpers below
 (GPUJPEG_U8, GPUJPEG_444_U8_P012, GPUJPEG_444_U8_P0P1P2, GPUJPEG_422_U8_P1020, GPUJPEG_422_U8_P0P1P2,
- GPUJPEG_420_U8_P0P1P2) = range(6)
+ GPUJPEG_420_U8_P0P1P2, GPUJPEG_4444_U8_P0123) = range(7)
+GPUJPEG_PIXFMT_AUTODETECT, GPUJPEG_PIXFMT_NO_ALPHA = -2, -3
 GPUJPEG_PIXFMT_NATIVE, GPUJPEG_PIXFMT_STD = -5, -4
 GPUJPEG_NONE, GPUJPEG_RGB, GPUJPEG_YCBCR_BT601, GPUJPEG_YCBCR_JPEG, GPUJPEG_YCBCR_BT709 = range(5)
 GPUJPEG_CS_DEFAULT = -1
@@ -221,7 +222,7 @@ class Encoder:
         return np.ctypeslib.as_array((C.c_uint8 * size).from_address(addr)).copy()
 
     def encode_samples(self, raw, width, height, pixel_format, quality=75, restart_interval=RESTART_AUTO, interleaved=0,
-                       color_space=GPUJPEG_YCBCR_JPEG, subsampling=None):
+                       color_space=GPUJPEG_YCBCR_JPEG, subsampling=None, alpha=False, color_space_internal=None):
         """raw: flat uint8 buffer in `pixel_format` / `color_space`.  With the JPEG colour space and subsampling=None the
         samples go into the JPEG as they are (the JPEG takes the format's sampling); other colour spaces are
         transformed, and `subsampling` ("4:2:0", ...) selects a JPEG sampling other than the format's.  Returns the
@@ -229,6 +230,11 @@ class Encoder:
         p = default_parameters(quality, restart_interval, interleaved, subsampling or "4:4:4")
         if subsampling == "4:4:4":
             lib.gpujpeg_parameters_chroma_subsampling(C.byref(p), 0x11111100)
+        if alpha:   # comp_count = 4: the alpha samples of a 4444-u8-p0123 image become a fourth component (first one's sampling)
+            lh, lv = SUBSAMPLING[subsampling or "4:4:4"]
+            lib.gpujpeg_parameters_chroma_subsampling(C.byref(p), lh << 28 | lv << 24 | 0x111100 | lh << 4 | lv)
+        if color_space_internal is not None:
+            p.color_space_internal = color_space_internal
         # subsampling None: comp_count stays 0 and the sampling is derived from the pixel format
         addr, size = self.encode_raw(raw, p, image_parameters(width, height, 0, pixel_format, color_space))
         return np.ctypeslib.as_array((C.c_uint8 * size).from_address(addr)).copy()

@@ -691,7 +691,7 @@ enum gpujpeg_color_space gj_stream_color_space(const struct gj_stream* s, int ad
     if ( s->spiff_color_space != GPUJPEG_NONE && s->comp_count != 1 ) return (enum gpujpeg_color_space)s->spiff_color_space;
     if ( s->exif_seen ) return GPUJPEG_YCBCR_BT601_256LVLS;   /* [ref: src/gpujpeg_reader.c:327] */
     if ( s->com_color_space != GPUJPEG_NONE && s->comp_count == 3 ) return (enum gpujpeg_color_space)s->com_color_space;
-    if ( s->comp_count == 3 &&
+    if ( s->comp_count >= 3 &&
          (adobe_transform == 0 || (s->comp_id[0] == 'R' && s->comp_id[1] == 'G' && s->comp_id[2] == 'B')) )
         return GPUJPEG_RGB;
     return GPUJPEG_YCBCR_BT601_256LVLS;

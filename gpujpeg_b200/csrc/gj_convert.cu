@@ -31,9 +31,10 @@ struct ConvertParams {
     int uyvy;               /* 422-u8-p1020: U is stored by even pixels, V by odd pixels */
     int alpha_off;          /* 4444-u8-p0123: offset of the alpha byte inside a pixel, 0 = none */
     /* component planes of the JPEG: sample (x, y) of component c at poff + y * ppitch + x; a pixel contributes to /
-     * reads from plane c at (x / pdh, y / pdv) */
-    unsigned long long poff[3];
-    int ppitch[3], pdh[3], pdv[3];
+     * reads from plane c at (x / pdh, y / pdv).  A fourth component is the alpha of a 4444-u8-p0123 image: it passes by
+     * the colour transform [ref: src/gpujpeg_preprocessor.cu:131-138, src/gpujpeg_postprocessor.cu:122-131] */
+    unsigned long long poff[GJ_MAX_COMP];
+    int ppitch[GJ_MAX_COMP], pdh[GJ_MAX_COMP], pdv[GJ_MAX_COMP];
     int jpeg_comps;
     int width, height;
     int cs;                 /* colour space of the raw image (enum gpujpeg_color_space) */
@@ -82,9 +83,13 @@ k_convert_in(const uint8_t* __restrict__ raw, uint8_t* __restrict__ planes, cons
     for ( int k = 0; k < p.raw_comps; k++ )
         c[k] = raw[p.off[k] + (size_t)(y / p.rdv[k]) * p.pitch[k] + (size_t)(x / p.rdh[k]) * p.xs[k]];
     if ( p.raw_comps == 3 ) cs_transform(p.cs, p.cs_internal, c);
-    for ( int k = 0; k < p.jpeg_comps; k++ )
+    const int colour_comps = p.jpeg_comps < 3 ? p.jpeg_comps : 3;
+    for ( int k = 0; k < colour_comps; k++ )
         if ( x % p.pdh[k] == 0 && y % p.pdv[k] == 0 )
             planes[p.poff[k] + (size_t)(y / p.pdv[k]) * p.ppitch[k] + x / p.pdh[k]] = (uint8_t)c[k];
+    if ( p.jpeg_comps == 4 && x % p.pdh[3] == 0 && y % p.pdv[3] == 0 )
+        planes[p.poff[3] + (size_t)(y / p.pdv[3]) * p.ppitch[3] + x / p.pdh[3]] =
+            raw[p.off[0] + (size_t)y * p.pitch[0] + (size_t)x * p.xs[0] + p.alpha_off];
 }
 
 __global__ void __launch_bounds__(256)
@@ -93,11 +98,14 @@ k_convert_out(const uint8_t* __restrict__ planes, uint8_t* __restrict__ raw, con
     const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
     if ( x >= p.width ) return;
     int c[3] = {0, 128, 128};
-    for ( int k = 0; k < p.jpeg_comps; k++ )
+    const int colour_comps = p.jpeg_comps < 3 ? p.jpeg_comps : 3;
+    for ( int k = 0; k < colour_comps; k++ )
         c[k] = planes[p.poff[k] + (size_t)(y / p.pdv[k]) * p.ppitch[k] + x / p.pdh[k]];
-    if ( p.jpeg_comps == 3 ) cs_transform(p.cs_internal, p.cs, c);
+    if ( p.jpeg_comps >= 3 ) cs_transform(p.cs_internal, p.cs, c);
     raw[p.off[0] + (size_t)y * p.pitch[0] + (size_t)x * p.xs[0]] = (uint8_t)c[0];
-    if ( p.alpha_off ) raw[p.off[0] + (size_t)y * p.pitch[0] + (size_t)x * p.xs[0] + p.alpha_off] = 0xFF;
+    if ( p.alpha_off )   /* the stream's fourth component, opaque without one */
+        raw[p.off[0] + (size_t)y * p.pitch[0] + (size_t)x * p.xs[0] + p.alpha_off] =
+            p.jpeg_comps == 4 ? planes[p.poff[3] + (size_t)(y / p.pdv[3]) * p.ppitch[3] + x / p.pdh[3]] : (uint8_t)0xFF;
     if ( p.raw_comps == 1 ) return;
     if ( p.uyvy ) {
         const int k = (x & 1) ? 2 : 1;
@@ -155,7 +163,8 @@ int fill_params(ConvertParams* p, const struct gj_raw_layout* raw, enum gpujpeg_
     memset(p, 0, sizeof *p);
     if ( color_space_internal < GPUJPEG_RGB || color_space_internal > GPUJPEG_YCBCR_BT709 ) return -1;
     p->cs_internal = color_space_internal;
-    if ( comp_count < 1 || comp_count > 3 || (raw->comp_count != 1 && raw->comp_count != 3) ) return -1;
+    if ( comp_count < 1 || comp_count > GJ_MAX_COMP || (raw->comp_count != 1 && raw->comp_count != 3) ) return -1;
+    if ( comp_count == 4 && raw->comp_count != 3 ) return -1;
     if ( color_space < GPUJPEG_NONE || color_space > GPUJPEG_YCBCR_BT709 ) return -1;
     p->raw_comps = raw->comp_count;
     p->uyvy = fmt == GPUJPEG_422_U8_P1020;
@@ -167,6 +176,8 @@ int fill_params(ConvertParams* p, const struct gj_raw_layout* raw, enum gpujpeg_
         p->xs[k] = raw->comp[r].xs;
         p->rdh[k] = raw->sampling[0].horizontal / (raw->sampling[r].horizontal ? raw->sampling[r].horizontal : 1);
         p->rdv[k] = raw->sampling[0].vertical / (raw->sampling[r].vertical ? raw->sampling[r].vertical : 1);
+    }
+    for ( int k = 0; k < GJ_MAX_COMP; k++ ) {
         const int j = k < comp_count ? k : 0;
         p->poff[k] = (unsigned long long)comp[j].blk_off * 64;
         p->ppitch[k] = comp[j].bcx * 8;
@@ -189,6 +200,7 @@ extern "C" int gj_launch_convert_in(const uint8_t* d_raw, const struct gj_raw_la
 {
     ConvertParams p;
     if ( fill_params(&p, raw, fmt, color_space, color_space_internal, width, height, comp, comp_count, max_hs, max_vs) ) return -1;
+    if ( comp_count == 4 && !raw->alpha_off ) return -1;   /* a fourth component needs a pixel format that has alpha samples */
     /* samples outside the image are 0 [ref: src/gpujpeg_common.c:941-944] */
     if ( cudaMemsetAsync(d_planes, 0, planes_size, stream) != cudaSuccess ) return -1;
     k_convert_in<<<dim3((width + 255) / 256, height), 256, 0, stream>>>(d_raw, d_planes, p);

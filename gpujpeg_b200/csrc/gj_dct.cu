@@ -47,7 +47,7 @@ struct FdctParams {
     float fwd_zz[2][64];
 };
 struct IdctParams {
-    uint16_t q_zz[3][64];
+    uint16_t q_zz[GJ_MAX_COMP][64];   /* the fused kernels use the first three */
 };
 
 /* clamp four ints to [0,255] and pack them, p0 in the lowest byte: two I2IP instructions */
@@ -707,8 +707,8 @@ k_idct_rgb_ss(const int16_t* __restrict__ coef, const __grid_constant__ SsGrid g
  * block row, so for planar data a warp reads 256 contiguous bytes per image row.  Samples outside the component
  * are 0 on the way in [ref: src/gpujpeg_common.c:941-944] and not written on the way out. */
 struct SampleGrid {
-    unsigned long long off[3], pitch[3];
-    int xs[3], cw[3], ch[3], bcx[3], blk_off[4], table[3];
+    unsigned long long off[GJ_MAX_COMP], pitch[GJ_MAX_COMP];
+    int xs[GJ_MAX_COMP], cw[GJ_MAX_COMP], ch[GJ_MAX_COMP], bcx[GJ_MAX_COMP], blk_off[GJ_MAX_COMP + 1], table[GJ_MAX_COMP];
 };
 constexpr int SG_THREADS = 128;
 
@@ -718,7 +718,7 @@ k_fdct_samples(const uint8_t* __restrict__ raw, const __grid_constant__ SampleGr
 {
     const int bi = blockIdx.x * SG_THREADS + threadIdx.x;
     if ( bi >= total_blocks ) return;
-    const int comp = (bi >= g.blk_off[1]) + (bi >= g.blk_off[2]);
+    const int comp = (bi >= g.blk_off[1]) + (bi >= g.blk_off[2]) + (bi >= g.blk_off[3]);
     const int local = bi - g.blk_off[comp];
     const int by = local / g.bcx[comp], bx = local - by * g.bcx[comp];
     const int vw = min(8, g.cw[comp] - bx * 8), vh = min(8, g.ch[comp] - by * 8);   // may be <= 0 (MCU padding blocks)
@@ -750,7 +750,7 @@ k_idct_samples(const int16_t* __restrict__ coef, const __grid_constant__ SampleG
 {
     const int bi = blockIdx.x * SG_THREADS + threadIdx.x;
     if ( bi >= total_blocks ) return;
-    const int comp = (bi >= g.blk_off[1]) + (bi >= g.blk_off[2]);
+    const int comp = (bi >= g.blk_off[1]) + (bi >= g.blk_off[2]) + (bi >= g.blk_off[3]);
     const int local = bi - g.blk_off[comp];
     const int by = local / g.bcx[comp], bx = local - by * g.bcx[comp];
     const int vw = min(8, g.cw[comp] - bx * 8), vh = min(8, g.ch[comp] - by * 8);
@@ -967,10 +967,10 @@ extern "C" int gj_launch_idct_rgb_ss(const int16_t* d_coef, const struct gj_comp
 static int sample_grid(SampleGrid* sg, const struct gj_raw_layout* raw, const struct gj_comp_geo* comp, int comp_count,
                        const uint8_t* comp_tbl)
 {
-    if ( comp_count < 1 || comp_count > 3 || raw->comp_count != comp_count ) return -1;
+    if ( comp_count < 1 || comp_count > GJ_MAX_COMP || raw->comp_count != comp_count ) return -1;
     memset(sg, 0, sizeof *sg);
     int total = 0;
-    for ( int c = 0; c < 3; c++ ) {
+    for ( int c = 0; c < GJ_MAX_COMP; c++ ) {
         const int k = c < comp_count ? c : comp_count - 1;
         sg->off[c] = raw->comp[k].off;
         sg->pitch[c] = raw->comp[k].pitch;
@@ -978,13 +978,13 @@ static int sample_grid(SampleGrid* sg, const struct gj_raw_layout* raw, const st
         sg->cw[c] = comp[k].width;
         sg->ch[c] = comp[k].height;
         sg->bcx[c] = comp[k].bcx;
-        sg->table[c] = comp_tbl ? comp_tbl[k] : (c == 0 ? 0 : 1);
+        sg->table[c] = comp_tbl ? comp_tbl[k] : ((c == 0 || c == 3) ? 0 : 1);
         if ( c < comp_count ) {
             sg->blk_off[c] = comp[c].blk_off;
             total = comp[c].blk_off + comp[c].nblk;
         }
     }
-    for ( int c = comp_count; c < 4; c++ )
+    for ( int c = comp_count; c <= GJ_MAX_COMP; c++ )
         sg->blk_off[c] = 0x7FFFFFFF;   // never reached: the component search stops at the last real component
     return total;
 }
@@ -1007,7 +1007,7 @@ extern "C" int gj_launch_idct_samples(const int16_t* d_coef, const struct gj_com
                                       const struct gj_dev_dec_tables* h_tables, gj_stream_t stream)
 {
     IdctParams prm;
-    for ( int c = 0; c < 3; c++ )
+    for ( int c = 0; c < GJ_MAX_COMP; c++ )
         memcpy(prm.q_zz[c], h_tables->qinv_zz[comp_tq[c < comp_count ? c : 0]], sizeof prm.q_zz[c]);
     SampleGrid sg;
     const int total = sample_grid(&sg, raw, comp, comp_count, nullptr);

@@ -78,7 +78,7 @@ struct gpujpeg_decoder {
 
     struct gj_huff_dec_args last_args;  /* launch arguments of the last frame (resident re-runs) */
     size_t last_ecs_begin; uint32_t last_list_cap;
-    int last_tq[3];
+    int last_tq[GJ_MAX_COMP];
     int last_valid;
 };
 
@@ -216,11 +216,12 @@ int gpujpeg_decoder_init(struct gpujpeg_decoder* d, const struct gpujpeg_paramet
     }
     struct gpujpeg_parameters p = *param;
     struct gpujpeg_image_parameters pi = *param_image;
-    if ( p.comp_count != 3 && p.comp_count != 1 ) {
-        GJ_ERR("This build decodes 1- and 3-component images only.\n");
+    if ( p.comp_count != 3 && p.comp_count != 1 && p.comp_count != 4 ) {
+        GJ_ERR("This build decodes 1-, 3- and 4-component images only.\n");
         return -1;
     }
-    if ( (int)pi.pixel_format < 0 ) pi.pixel_format = p.comp_count == 1 ? GPUJPEG_U8 : GPUJPEG_444_U8_P012;
+    if ( (int)pi.pixel_format < 0 )
+        pi.pixel_format = p.comp_count == 1 ? GPUJPEG_U8 : p.comp_count == 4 ? GPUJPEG_4444_U8_P0123 : GPUJPEG_444_U8_P012;
     gj_geometry_init(&d->geo, &p, &pi);
     const struct gj_geometry* g = &d->geo;
     if ( grow_dev((void**)&d->d_coef, &d->d_coef_size, g->coef_count * 2) ||
@@ -271,19 +272,22 @@ static int choose_output(const struct gpujpeg_decoder* d, const struct gj_stream
     if ( cs == GPUJPEG_NONE ) cs = st->color_space;
     if ( special ) {
         const int planar_by_sampling = pf == GPUJPEG_PIXFMT_STD && cs != GPUJPEG_RGB;
-        if ( pf == GPUJPEG_PIXFMT_NATIVE || planar_by_sampling ) {
+        if ( pf == GPUJPEG_PIXFMT_NATIVE && st->comp_count == 4 ) pf = GPUJPEG_4444_U8_P0123;   /* [ref: src/gpujpeg_reader.c:1510-1512] */
+        else if ( pf == GPUJPEG_PIXFMT_NATIVE || planar_by_sampling ) {
             const int il = pf == GPUJPEG_PIXFMT_NATIVE && st->scan[0].ncomp > 1;
             if ( lh == 2 && lv == 2 ) pf = GPUJPEG_420_U8_P0P1P2;
             else if ( lh == 2 && lv == 1 ) pf = il ? GPUJPEG_422_U8_P1020 : GPUJPEG_422_U8_P0P1P2;
             else pf = il ? GPUJPEG_444_U8_P012 : GPUJPEG_444_U8_P0P1P2;
         }
         else {
-            pf = GPUJPEG_444_U8_P012;
+            /* a fourth component comes out as alpha unless the caller asked for "no alpha" [ref: src/gpujpeg_reader.c:1576-1581] */
+            pf = st->comp_count == 4 && pf != GPUJPEG_PIXFMT_NO_ALPHA ? GPUJPEG_4444_U8_P0123 : GPUJPEG_444_U8_P012;
         }
     }
     pi->pixel_format = pf;
     pi->color_space = cs;
-    if ( cs == GPUJPEG_RGB && pf == GPUJPEG_444_U8_P012 && st->color_space == GPUJPEG_YCBCR_BT601_256LVLS ) return GJ_OUT_RGB;
+    if ( st->comp_count == 3 && cs == GPUJPEG_RGB && pf == GPUJPEG_444_U8_P012 && st->color_space == GPUJPEG_YCBCR_BT601_256LVLS )
+        return GJ_OUT_RGB;
     if ( cs != GPUJPEG_RGB && cs != GPUJPEG_YCBCR_BT601 && cs != GPUJPEG_YCBCR_BT601_256LVLS && cs != GPUJPEG_YCBCR_BT709 ) {
         GJ_ERR("Colour space %s is not produced by this build.\n", gpujpeg_color_space_get_name(cs));
         return 0;
@@ -294,7 +298,8 @@ static int choose_output(const struct gpujpeg_decoder* d, const struct gj_stream
                pi->height);
         return 0;
     }
-    if ( cs != st->color_space || rl.sampling[0].horizontal != lh || rl.sampling[0].vertical != lv || rl.alpha_off ) {
+    if ( st->comp_count == 4 || cs != st->color_space || rl.sampling[0].horizontal != lh || rl.sampling[0].vertical != lv ||
+         rl.alpha_off ) {
         if ( (pi->width & 1) && rl.sampling[0].horizontal == 2 && pf != GPUJPEG_420_U8_P0P1P2 ) {
             GJ_ERR("Odd widths are only produced without colour / sampling conversion for this pixel format.\n");
             return 0;
@@ -305,7 +310,7 @@ static int choose_output(const struct gpujpeg_decoder* d, const struct gj_stream
 }
 
 /* K4 for the coder's geometry: the 4:4:4 kernel or the chroma-subsampling template instance */
-static int launch_k4(struct gpujpeg_decoder* d, const int comp_tq[3], uint8_t* d_out, int coef_dequantized)
+static int launch_k4(struct gpujpeg_decoder* d, const int comp_tq[GJ_MAX_COMP], uint8_t* d_out, int coef_dequantized)
 {
     const struct gj_geometry* g = &d->geo;
     if ( d->out_mode == GJ_OUT_SAMPLES )
@@ -534,22 +539,23 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
         GJ_ERR("Decoder failed when decoding image data (no scan found)!\n");
         return GPUJPEG_ERROR;
     }
-    if ( st.comp_count != 3 && st.comp_count != 1 ) {
-        GJ_ERR("This build decodes 1- and 3-component JPEGs only (stream has %d).\n", st.comp_count);
+    if ( st.comp_count != 3 && st.comp_count != 1 && st.comp_count != 4 ) {
+        GJ_ERR("This build decodes 1-, 3- and 4-component JPEGs only (stream has %d).\n", st.comp_count);
         return GPUJPEG_ERROR;
     }
     if ( st.comp_count == 1 ) st.comp_hv[0] = 0x11;   /* a single component is never subsampled (T.81 A.2.2) */
     /* luminance 1x1, 2x1, 1x2 or 2x2 with 1x1 chrominance (4:4:4, 4:2:2, 4:4:0, 4:2:0) */
-    if ( st.comp_count == 3 ) {
+    if ( st.comp_count >= 3 ) {   /* (a fourth component -- alpha -- with the first component's sampling) */
         const int lh = st.comp_hv[0] >> 4, lv = st.comp_hv[0] & 15;
-        if ( lh < 1 || lh > 2 || lv < 1 || lv > 2 || st.comp_hv[1] != 0x11 || st.comp_hv[2] != 0x11 ) {
+        if ( lh < 1 || lh > 2 || lv < 1 || lv > 2 || st.comp_hv[1] != 0x11 || st.comp_hv[2] != 0x11 ||
+             (st.comp_count == 4 && st.comp_hv[3] != st.comp_hv[0]) ) {
             GJ_ERR("This build decodes 4:4:4, 4:2:2, 4:2:0 and 4:4:0 only (sampling factors %dx%d %dx%d %dx%d).\n", lh, lv,
                    st.comp_hv[1] >> 4, st.comp_hv[1] & 15, st.comp_hv[2] >> 4, st.comp_hv[2] & 15);
             return GPUJPEG_ERROR;
         }
     }
     st.interleaved = st.scan[0].ncomp > 1;
-    if ( st.interleaved && st.scan[0].ncomp != 3 ) {
+    if ( st.interleaved && st.scan[0].ncomp != st.comp_count ) {
         GJ_ERR("Unsupported scan structure (%d components in first scan).\n", st.scan[0].ncomp);
         return GPUJPEG_ERROR;
     }
@@ -581,7 +587,7 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
      * [ref: src/gpujpeg_postprocessor.cu:447]: in general only the pass that has planes can do it.  Without vertical padding
      * flipping the planes and then replicating chrominance rows is flipping the finished image, and the fused kernel does
      * that by writing the rows last to first (launch_k4). */
-    if ( d->flipped && !(out_mode == GJ_OUT_RGB && st.height % (8 * (st.comp_count == 3 ? (st.comp_hv[0] & 15) : 1)) == 0) )
+    if ( d->flipped && !(out_mode == GJ_OUT_RGB && st.height % (8 * (st.comp_count >= 3 ? (st.comp_hv[0] & 15) : 1)) == 0) )
         out_mode = GJ_OUT_GENERIC;
 
     if ( !d->initialised || d->param_image.width != pi.width || d->param_image.height != pi.height ||
@@ -971,7 +977,7 @@ int gpujpeg_decoder_get_image_info2(uint8_t* image, size_t image_size, struct gp
     info->param_image.height = st.height;
     info->param_image.color_space = st.color_space;
     /* the stream's native pixel format [ref: src/gpujpeg_reader.c:1507-1547, 1750] */
-    info->param_image.pixel_format = st.comp_count == 1 ? GPUJPEG_U8 : GPUJPEG_444_U8_P012;
+    info->param_image.pixel_format = st.comp_count == 1 ? GPUJPEG_U8 : st.comp_count == 4 ? GPUJPEG_4444_U8_P0123 : GPUJPEG_444_U8_P012;
     if ( st.comp_count == 3 && st.comp_hv[1] == 0x11 && st.comp_hv[2] == 0x11 ) {
         const int il = st.interleaved;
         if ( st.comp_hv[0] == 0x22 ) info->param_image.pixel_format = GPUJPEG_420_U8_P0P1P2;

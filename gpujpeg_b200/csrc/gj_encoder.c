@@ -230,7 +230,7 @@ static int params_supported(const struct gpujpeg_parameters* p, const struct gpu
     /* YCbCr JPEG (JFIF header), RGB (Adobe APP14 header, every component coded with the luminance tables), or the
      * limited-range YCbCr spaces BT.601 / BT.709 (SPIFF header) [ref: src/gpujpeg_writer.c:456-475] */
     if ( p->color_space_internal != GPUJPEG_YCBCR_BT601_256LVLS &&
-         !(p->comp_count == 3 && (p->color_space_internal == GPUJPEG_RGB || p->color_space_internal == GPUJPEG_YCBCR_BT601 ||
+         !(p->comp_count >= 3 && (p->color_space_internal == GPUJPEG_RGB || p->color_space_internal == GPUJPEG_YCBCR_BT601 ||
                                   p->color_space_internal == GPUJPEG_YCBCR_BT709)) ) {
         GJ_ERR("Internal color space %s is not taken by this build.\n", gpujpeg_color_space_get_name(p->color_space_internal));
         return GJ_IN_UNSUPPORTED;
@@ -240,8 +240,8 @@ static int params_supported(const struct gpujpeg_parameters* p, const struct gpu
         GJ_ERR("BT.601 input into a BT.709-internal JPEG is not taken by this build.\n");
         return GJ_IN_UNSUPPORTED;
     }
-    if ( p->comp_count != 3 && p->comp_count != 1 ) {
-        GJ_ERR("This build encodes 1- and 3-component images only (comp_count = %d).\n", p->comp_count);
+    if ( p->comp_count != 3 && p->comp_count != 1 && p->comp_count != 4 ) {
+        GJ_ERR("This build encodes 1-, 3- and 4-component images only (comp_count = %d).\n", p->comp_count);
         return GJ_IN_UNSUPPORTED;
     }
     if ( pi->pixel_format == GPUJPEG_444_U8_P012 && pi->color_space == GPUJPEG_RGB && p->comp_count == 3 &&
@@ -263,20 +263,25 @@ static int params_supported(const struct gpujpeg_parameters* p, const struct gpu
                gpujpeg_pixel_format_get_name(pi->pixel_format), pi->width, pi->height, pi->width_padding);
         return GJ_IN_UNSUPPORTED;
     }
-    if ( rl.comp_count != p->comp_count ) {
+    /* comp_count = 4: the alpha samples of a 4444-u8-p0123 image are coded as a fourth component (with the luminance tables
+     * and the first component's sampling); with comp_count = 3 they are ignored [ref: src/gpujpeg_common.c:692-694,
+     * src/gpujpeg_preprocessor.cu:131-138] */
+    const int four = p->comp_count == 4;
+    if ( four ? !(rl.comp_count == 3 && rl.alpha_off) : rl.comp_count != p->comp_count ) {
         GJ_ERR("Pixel format %s has %d components, the JPEG parameters ask for %d.\n",
-               gpujpeg_pixel_format_get_name(pi->pixel_format), rl.comp_count, p->comp_count);
+               gpujpeg_pixel_format_get_name(pi->pixel_format), rl.comp_count + (rl.alpha_off ? 1 : 0), p->comp_count);
         return GJ_IN_UNSUPPORTED;
     }
-    int needs_pass = p->comp_count == 3 && pi->color_space != p->color_space_internal && pi->color_space != GPUJPEG_NONE;
-    for ( int c = 0; c < p->comp_count; c++ )
+    int needs_pass = four || (p->comp_count == 3 && pi->color_space != p->color_space_internal && pi->color_space != GPUJPEG_NONE);
+    for ( int c = 0; c < p->comp_count && c < 3; c++ )
         if ( p->sampling_factor[c].horizontal != rl.sampling[c].horizontal ||
              p->sampling_factor[c].vertical != rl.sampling[c].vertical )
             needs_pass = 1;
     if ( needs_pass ) {
         const int lh = p->sampling_factor[0].horizontal, lv = p->sampling_factor[0].vertical;
-        if ( p->comp_count != 3 || lh < 1 || lh > 2 || lv < 1 || lv > 2 || p->sampling_factor[1].horizontal != 1 ||
-             p->sampling_factor[1].vertical != 1 || p->sampling_factor[2].horizontal != 1 || p->sampling_factor[2].vertical != 1 ) {
+        if ( p->comp_count < 3 || lh < 1 || lh > 2 || lv < 1 || lv > 2 || p->sampling_factor[1].horizontal != 1 ||
+             p->sampling_factor[1].vertical != 1 || p->sampling_factor[2].horizontal != 1 || p->sampling_factor[2].vertical != 1 ||
+             (four && (p->sampling_factor[3].horizontal != lh || p->sampling_factor[3].vertical != lv)) ) {
             GJ_ERR("This build encodes 4:4:4, 4:2:2, 4:2:0 and 4:4:0 only (got %s).\n",
                    gpujpeg_subsampling_get_name(p->comp_count, p->sampling_factor));
             return GJ_IN_UNSUPPORTED;

@@ -650,23 +650,31 @@ static int g_rgb_internal = 0;
  * [ref: src/gpujpeg_writer.c:171-245, 462-466, 513-515] */
 static int g_spiff_cs = 0;
 
+/* table class of component c: luminance for the first and for a fourth (alpha) component, and for every component of an
+ * RGB-internal JPEG [ref: src/gpujpeg_common.c:692-694] */
+static int comp_class(int c) { return (c == 0 || c == 3 || g_rgb_internal) ? 0 : 1; }
+/* component ids of SOF0 / SOS [ref: src/gpujpeg_writer.c:305-313] */
+static int comp_ident(int c) { return g_rgb_internal ? "RGBA"[c] : c + 1; }
+
 size_t orc_write_header(uint8_t* out, int w, int h, int quality, int rst, int comp_count)
 {
     uint8_t raw[2][64];
     orc_quant_tables(quality, raw, NULL, NULL);
     uint8_t* p = out;
     p = putm(p, 0xD8);
-    if ( g_spiff_cs ) {
+    /* four components are described by a SPIFF header whatever the colour space [ref: src/gpujpeg_writer.c:458-460] */
+    const int spiff_cs = g_spiff_cs ? g_spiff_cs : comp_count == 4 ? (g_rgb_internal ? 10 : 3) : 0;
+    if ( spiff_cs ) {
         p = putm(p, 0xE8);
         p = put16(p, 32);
         memcpy(p, "SPIFF", 6);
         p += 6;
         p = put16(p, 0x100);
-        p = put8(p, 0);
+        p = put8(p, spiff_cs == 3 ? 1 : 0);   /* profile [ref: src/gpujpeg_writer.c:203] */
         p = put8(p, comp_count);
         p = put16(p, 0); p = put16(p, h);
         p = put16(p, 0); p = put16(p, w);
-        p = put8(p, g_spiff_cs);
+        p = put8(p, spiff_cs);
         p = put8(p, 8); p = put8(p, 5); p = put8(p, 0);
         p = put16(p, 0); p = put16(p, 1);
         p = put16(p, 0); p = put16(p, 1);
@@ -707,9 +715,9 @@ size_t orc_write_header(uint8_t* out, int w, int h, int quality, int rst, int co
     p = put16(p, w);
     p = put8(p, comp_count);
     for ( int c = 0; c < comp_count; c++ ) {
-        p = put8(p, g_rgb_internal ? "RGB"[c] : c + 1);
+        p = put8(p, comp_ident(c));
         p = put8(p, 0x11);
-        p = put8(p, (c == 0 || g_rgb_internal) ? 0 : 1);
+        p = put8(p, comp_class(c));
     }
     for ( int t = 0; t < ntypes; t++ ) {
         for ( int k = 0; k < 2; k++ ) {
@@ -805,15 +813,15 @@ static uint8_t* write_sos(uint8_t* p, int interleaved, int comp_count, int scan_
         p = put16(p, 6 + 2 * comp_count);
         p = put8(p, comp_count);
         for ( int c = 0; c < comp_count; c++ ) {
-            p = put8(p, g_rgb_internal ? "RGB"[c] : c + 1);
-            p = put8(p, (c == 0 || g_rgb_internal) ? 0x00 : 0x11);
+            p = put8(p, comp_ident(c));
+            p = put8(p, comp_class(c) ? 0x11 : 0x00);
         }
     }
     else {
         p = put16(p, 8);
         p = put8(p, 1);
-        p = put8(p, g_rgb_internal ? "RGB"[scan_comp] : scan_comp + 1);
-        p = put8(p, (scan_comp == 0 || g_rgb_internal) ? 0x00 : 0x11);
+        p = put8(p, comp_ident(scan_comp));
+        p = put8(p, comp_class(scan_comp) ? 0x11 : 0x00);
     }
     p = put8(p, 0);
     p = put8(p, 0x3F);
@@ -1020,7 +1028,7 @@ static size_t encode_from_planes(const uint8_t* planes, const struct ogeo g[4], 
     float fwd[2][64];
     orc_quant_tables(quality, raw, fwd, NULL);
     for ( int c = 0; c < comps; c++ )
-        orc_fdct_quant_plane(planes + g[c].off, g[c].dw, g[c].dh, fwd[(c == 0 || g_rgb_internal) ? 0 : 1], coef + g[c].off);
+        orc_fdct_quant_plane(planes + g[c].off, g[c].dw, g[c].dh, fwd[comp_class(c)], coef + g[c].off);
 
     /* header: as orc_write_header, with the sampling factors patched into SOF0 */
     size_t hl = orc_write_header(out, w, h, quality, rst, comps);
@@ -1066,14 +1074,14 @@ static size_t encode_from_planes(const uint8_t* planes, const struct ogeo g[4], 
         uint8_t* o = tmp + (size_t)si * slot;
         if ( !interleaved ) {
             seg_len[si] = orc_huff_encode_segment(coef + g[scan].off + (size_t)first * 64, cnt,
-                                                  (scan == 0 || g_rgb_internal) ? 0 : 1, o);
+                                                  comp_class(scan), o);
         }
         else {
             struct bitw bw = {o, 0, 0};
-            int pred[3] = {0, 0, 0};
+            int pred[4] = {0, 0, 0, 0};
             for ( int m = first; m < first + cnt; m++ )
                 for ( int c = 0; c < comps; c++ ) {
-                    const int cls = (c == 0 || g_rgb_internal) ? 0 : 1;
+                    const int cls = comp_class(c);
                     for ( int y = 0; y < g[c].vs; y++ )
                         for ( int x = 0; x < g[c].hs; x++ )
                             encode_block(&bw, mcu_block(coef, &g[c], mcu_x, m, x, y), &pred[c], &g_enc[cls][0], &g_enc[cls][1]);
@@ -1293,6 +1301,8 @@ static void cs_transform(int from, int to, int c[3])
  *                  the postprocessor [ref: src/gpujpeg_postprocessor.cu:447] */
 static int g_flipped = 0;
 static unsigned g_remap = 0;   /* (channel count << 24) | nibbles, 0 = none */
+static int g_four_components = 0;   /* param.comp_count = 4: an RGBA image keeps its alpha as a fourth component */
+void orc_set_four_components(int on) { g_four_components = on; }
 void orc_set_flip_remap(int flipped, unsigned remap)
 {
     g_flipped = flipped;
@@ -1357,8 +1367,10 @@ size_t orc_encode_any2(const uint8_t* raw, int w, int h, int fmt, int cs, int in
 #else
     (void)threads;
 #endif
-    const int comps = 3;
-    const int hs[4] = {lhs, 1, 1, 0}, vs[4] = {lvs, 1, 1, 0};
+    /* comp_count = 4 with the four-sample pixel format: the alpha samples become a fourth component with the sampling of the
+     * first, untouched by the colour transform [ref: src/gpujpeg_preprocessor.cu:131-138, 185-194] */
+    const int comps = (g_four_components && fmt == 6) ? 4 : 3;
+    const int hs[4] = {lhs, 1, 1, comps == 4 ? lhs : 0}, vs[4] = {lvs, 1, 1, comps == 4 ? lvs : 0};
     struct ogeo g[4];
     int max_hs, max_vs;
     size_t total = ogeo_init(g, comps, hs, vs, w, h, interleaved, &max_hs, &max_vs);
@@ -1372,7 +1384,7 @@ size_t orc_encode_any2(const uint8_t* raw, int w, int h, int fmt, int cs, int in
             if ( fmt == 6 ) c[3] = raw[rc[0].off + (size_t)y * rc[0].pitch + (size_t)x * 4 + 3];
             remap_channels(c, fmt == 6 ? 4 : fmt == 0 ? 1 : 3);
             cs_transform(cs, internal, c);
-            for ( int k = 0; k < 3; k++ ) {
+            for ( int k = 0; k < comps; k++ ) {
                 int dh = max_hs / g[k].hs, dv = max_vs / g[k].vs;
                 if ( x % dh || y % dv ) continue;
                 planes[g[k].off + (size_t)(y / dv) * g[k].dw + x / dh] = (uint8_t)c[k];
@@ -1867,9 +1879,9 @@ int orc_decode_any(const uint8_t* jpeg, size_t size, int idct_flavour, int threa
     (void)threads;
 #endif
     /* colour space of the components: Adobe transform 0 or ids 'R','G','B' mean RGB [ref: src/gpujpeg_reader.c:264-640] */
-    int stream_cs = (P.comps == 3 && (P.adobe_transform == 0 || (P.comp_id[0] == 'R' && P.comp_id[1] == 'G' && P.comp_id[2] == 'B')))
+    int stream_cs = (P.comps >= 3 && (P.adobe_transform == 0 || (P.comp_id[0] == 'R' && P.comp_id[1] == 'G' && P.comp_id[2] == 'B')))
                         ? CS_RGB : CS_601_256;
-    if ( P.comps == 3 && P.spiff_cs )
+    if ( P.comps >= 3 && P.spiff_cs )
         stream_cs = P.spiff_cs == 1 ? CS_709 : P.spiff_cs == 4 ? CS_601 : P.spiff_cs == 10 ? CS_RGB : CS_601_256;
     struct ogeo g[4];
     int max_hs, max_vs;
@@ -1885,14 +1897,14 @@ int orc_decode_any(const uint8_t* jpeg, size_t size, int idct_flavour, int threa
                     int dh = max_hs / g[k].hs, dv = max_vs / g[k].vs;
                     c[k] = planes[g[k].off + (size_t)(y / dv) * g[k].dw + x / dh];
                 }
-                if ( P.comps == 3 ) cs_transform(stream_cs, cs, c);
+                if ( P.comps >= 3 ) cs_transform(stream_cs, cs, c);   /* (a fourth component passes through) */
                 remap_channels(c, fmt == 6 ? 4 : fcomps == 1 ? 1 : 3);
                 if ( fcomps == 1 ) {
                     raw[rc[0].off + (size_t)y * rc[0].pitch + x] = (uint8_t)c[0];
                     continue;
                 }
                 raw[rc[0].off + (size_t)y * rc[0].pitch + (size_t)x * rc[0].xs] = (uint8_t)c[0];
-                if ( fmt == 6 ) raw[rc[0].off + (size_t)y * rc[0].pitch + (size_t)x * 4 + 3] = (uint8_t)c[3];   /* alpha: 0xFF unless remapped */
+                if ( fmt == 6 ) raw[rc[0].off + (size_t)y * rc[0].pitch + (size_t)x * 4 + 3] = (uint8_t)c[3];   /* alpha: the fourth component, 0xFF without one (unless remapped) */
                 const int dh = fhs[0], dv = fvs[0];   /* chroma of the format: every dh-th pixel of every dv-th row */
                 if ( fmt == 3 ) {
                     /* U from even pixels, V from odd pixels [ref: src/gpujpeg_preprocessor_common.cuh:179-189] */
@@ -1909,6 +1921,28 @@ int orc_decode_any(const uint8_t* jpeg, size_t size, int idct_flavour, int threa
     omp_set_num_threads(saved_threads);
 #endif
     return planes ? 0 : -1;
+}
+
+/* Quantised coefficients of a stream of any component count (1, 3 or 4) and sampling: component after component, blocks
+ * in raster order, natural order inside a block -- the layout the reference keeps them in.  Returns the number of
+ * coefficients, 0 on error; coef == NULL: the count only. */
+size_t orc_decode_coefficients(const uint8_t* jpeg, size_t size, int16_t* coef)
+{
+    struct parsed P;
+    if ( parse_stream(jpeg, size, &P) != 0 ) return 0;
+    struct ogeo g[4];
+    int max_hs, max_vs;
+    if ( !coef ) {
+        int hs[4] = {0, 0, 0, 0}, vs[4] = {0, 0, 0, 0};
+        for ( int c = 0; c < P.comps; c++ ) {
+            hs[c] = P.comps == 1 ? 1 : P.comp_hv[c] >> 4;
+            vs[c] = P.comps == 1 ? 1 : P.comp_hv[c] & 15;
+            if ( hs[c] < 1 || vs[c] < 1 ) return 0;
+        }
+        return ogeo_init(g, P.comps, hs, vs, P.w, P.h, P.comps > 1 && P.nscan == 1, &max_hs, &max_vs);
+    }
+    if ( !decode_to_planes(&P, jpeg, 0, g, &max_hs, &max_vs, coef, 0) ) return 0;
+    return (size_t)g[P.comps - 1].off + (size_t)g[P.comps - 1].nblk * 64;
 }
 
 /* [ref: src/gpujpeg_decoder.c:234-469 with the CPU Huffman path :275-295 and gpujpeg_idct_cpu] */

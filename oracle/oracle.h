@@ -94,6 +94,12 @@ int orc_decode_any(const uint8_t* jpeg, size_t size, int idct_flavour, int threa
  * header, component ids 'R','G','B', luminance tables for every component); orc_decode_any detects it from the stream */
 size_t orc_encode_any2(const uint8_t* raw, int w, int h, int fmt, int cs, int internal, int quality, int rst, int interleaved,
                        int lhs, int lvs, int threads, uint8_t* out);
+/* comp_count = 4 of the reference's parameters: a 4444-u8-p0123 image given to orc_encode_any* keeps its alpha samples as a
+ * fourth component (luminance tables, the first component's sampling, SPIFF header) [ref: src/gpujpeg_common.c:692-694,
+ * src/gpujpeg_writer.c:458-460]; orc_decode_any hands a fourth component out as alpha */
+void orc_set_four_components(int on);
+/* quantised coefficients of a stream with 1, 3 or 4 components: returns their number (coef == NULL: count only), 0 on error */
+size_t orc_decode_coefficients(const uint8_t* jpeg, size_t size, int16_t* coef);
 /* Decode a baseline JPEG produced by this codec family (3 comp, any of the above samplings, or 1 comp) to RGB/gray u8.
  * Returns 0 on success; fills w,h,comps.  rgb may be NULL to probe. coef_out optional. */
 int orc_decode_rgb(const uint8_t* jpeg, size_t size, int idct_flavour, int threads, uint8_t* rgb,

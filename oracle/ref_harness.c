@@ -53,13 +53,13 @@ struct geom {
 static int geom_init(struct geom* g, int w, int h, int comps, int rst, int interleaved, int lhs, int lvs, int16_t* coef)
 {
     memset(g, 0, sizeof *g);
-    const int max_h = lhs, max_v = lvs;   /* luminance carries the maximum, chrominance is 1x1 */
+    const int max_h = lhs, max_v = lvs;   /* luminance (and a fourth, alpha, component) carries the maximum, chrominance is 1x1 */
     size_t off = 0;
     for ( int c = 0; c < comps; c++ ) {
         struct gpujpeg_component* k = &g->comp[c];
-        const int sh = c == 0 ? lhs : 1, sv = c == 0 ? lvs : 1;
+        const int sh = (c == 0 || c == 3) ? lhs : 1, sv = (c == 0 || c == 3) ? lvs : 1;
         const int div_h = max_h / sh, div_v = max_v / sv;
-        k->type = c == 0 ? GPUJPEG_COMPONENT_LUMINANCE : GPUJPEG_COMPONENT_CHROMINANCE;
+        k->type = (c == 0 || c == 3) ? GPUJPEG_COMPONENT_LUMINANCE : GPUJPEG_COMPONENT_CHROMINANCE;   /* [ref: src/gpujpeg_common.c:692-694] */
         k->sampling_factor.horizontal = sh;
         k->sampling_factor.vertical = sv;
         k->width = ((w + div_h - 1) / div_h * div_h) * sh / max_h;
@@ -174,8 +174,8 @@ size_t ref_encode_from_coef_ss(int16_t* coef, int w, int h, int comps, int quali
     enc->coder.param.interleaved = interleaved;
     enc->coder.param.comp_count = comps;
     for ( int c = 0; c < comps; c++ ) {
-        enc->coder.param.sampling_factor[c].horizontal = c == 0 ? lhs : 1;
-        enc->coder.param.sampling_factor[c].vertical = c == 0 ? lvs : 1;
+        enc->coder.param.sampling_factor[c].horizontal = (c == 0 || c == 3) ? lhs : 1;
+        enc->coder.param.sampling_factor[c].vertical = (c == 0 || c == 3) ? lvs : 1;
     }
     enc->coder.param.color_space_internal = g_internal_rgb ? GPUJPEG_RGB : g_internal_cs ? (enum gpujpeg_color_space)g_internal_cs
                                                                                          : GPUJPEG_YCBCR_BT601_256LVLS;
@@ -224,6 +224,16 @@ size_t ref_encode_from_coef_rgb(int16_t* coef, int w, int h, int quality, int rs
 {
     g_internal_rgb = 1;
     size_t n = ref_encode_from_coef_ss(coef, w, h, 3, quality, rst, interleaved, lhs, lvs, out, out_cap);
+    g_internal_rgb = 0;
+    return n;
+}
+
+/* RGB-internal with any component count (4: 'R','G','B','A' under a SPIFF header) */
+size_t ref_encode_from_coef_rgb_n(int16_t* coef, int w, int h, int comps, int quality, int rst, int interleaved, uint8_t* out,
+                                  size_t out_cap)
+{
+    g_internal_rgb = 1;
+    size_t n = ref_encode_from_coef_ss(coef, w, h, comps, quality, rst, interleaved, 1, 1, out, out_cap);
     g_internal_rgb = 0;
     return n;
 }

@@ -215,12 +215,17 @@ class huffman_override:
 CS_NONE, CS_RGB, CS_601, CS_JPEG, CS_709 = range(5)
 
 
-def encode_any(raw, w, h, fmt, cs, quality=75, rst=8, interleaved=0, sampling=(1, 1), threads=1, internal=3):
+def encode_any(raw, w, h, fmt, cs, quality=75, rst=8, interleaved=0, sampling=(1, 1), threads=1, internal=3, alpha=False):
     """generic path of the reference: pixel format x colour space x JPEG sampling, per-pixel colour transform;
-    internal = colour space of the JPEG's components (3 = YCbCr JPEG / JFIF, 1 = RGB / Adobe APP14)"""
-    out = np.empty(4096 + w * h * 6 + 4096, np.uint8)
-    n = lib.orc_encode_any2(np.ascontiguousarray(raw).reshape(-1), w, h, fmt, cs, internal, quality, rst, interleaved,
-                            sampling[0], sampling[1], threads, out)
+    internal = colour space of the JPEG's components (3 = YCbCr JPEG / JFIF, 1 = RGB / Adobe APP14); alpha: comp_count = 4,
+    the alpha samples of a 4444-u8-p0123 image become a fourth component"""
+    out = np.empty(4096 + w * h * 8 + 4096, np.uint8)
+    lib.orc_set_four_components(1 if alpha else 0)
+    try:
+        n = lib.orc_encode_any2(np.ascontiguousarray(raw).reshape(-1), w, h, fmt, cs, internal, quality, rst, interleaved,
+                                sampling[0], sampling[1], threads, out)
+    finally:
+        lib.orc_set_four_components(0)
     assert n > 0
     return out[:n].copy()
 
@@ -231,6 +236,18 @@ def decode_any(jpeg, fmt, cs, flavour=IDCT_INT, threads=1):
     raw = np.zeros(lib.orc_raw_size(fmt, info.width, info.height, 0), np.uint8)
     assert lib.orc_decode_any(jpeg, jpeg.size, flavour, threads, fmt, cs, raw) == 0
     return raw
+
+
+def coefficients(jpeg):
+    """quantised coefficients of a stream with 1, 3 or 4 components: flat, component after component, natural order"""
+    jpeg = np.ascontiguousarray(jpeg, np.uint8)
+    lib.orc_decode_coefficients.restype = C.c_size_t
+    lib.orc_decode_coefficients.argtypes = [_u8p, C.c_size_t, C.c_void_p]
+    n = lib.orc_decode_coefficients(jpeg, jpeg.size, None)
+    assert n > 0
+    coef = np.zeros(n, np.int16)
+    assert lib.orc_decode_coefficients(jpeg, jpeg.size, coef.ctypes.data) == n
+    return coef
 
 
 def stream_sampling(jpeg):

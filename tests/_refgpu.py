@@ -142,7 +142,8 @@ def run(lib, a):
     Arguments of the form opt:<key>=<value> are passed to gpujpeg_{en,de}coder_set_option of the coder the command creates."""
     opts = [x[4:] for x in a if x.startswith("opt:")]
     pars = dict(x[4:].split("=") for x in a if x.startswith("par:"))   # par:<field>=<int>: struct gpujpeg_parameters fields
-    a = [x for x in a if not x.startswith(("opt:", "par:"))]
+    subs = [int(x[4:], 0) for x in a if x.startswith("sub:")]           # sub:<packed>: gpujpeg_parameters_chroma_subsampling
+    a = [x for x in a if not x.startswith(("opt:", "par:", "sub:"))]
     mode = a[0]
     if mode == "encode":
         kind, w, h, q, rst, il, path = a[1], *map(int, a[2:7]), a[7]
@@ -165,6 +166,11 @@ def run(lib, a):
         pi.pixel_format, pi.color_space = fmt, cs   # comp_count stays 0: sampling follows the pixel format
         if len(a) > 10:
             p.color_space_internal = int(a[10])   # e.g. 1 = GPUJPEG_RGB: RGB-internal JPEG (Adobe APP14)
+        for packed in subs:   # e.g. 0x11111111: four components (an RGBA image keeps its alpha)
+            lib.gpujpeg_parameters_chroma_subsampling.argtypes = [C.POINTER(Param), C.c_uint32]
+            lib.gpujpeg_parameters_chroma_subsampling(C.byref(p), packed)
+        for k, v in pars.items():
+            setattr(p, k, int(v))
         encode(lib, enc, raw, p, pi).tofile(path)
         lib.gpujpeg_encoder_destroy(enc)
     elif mode == "decode_fmt":
@@ -178,8 +184,32 @@ def run(lib, a):
         np.ctypeslib.as_array((C.c_uint8 * out.data_size).from_address(out.data)).tofile(a[4])
         reply = {"pixel_format": out.param_image.pixel_format, "color_space": out.param_image.color_space,
                  "size": out.data_size}
+        if out.metadata:   # struct gpujpeg_image_metadata: {rotation:2, flip:1} bit-field word, then the "set" bit
+            m = (C.c_uint32 * 2).from_address(out.metadata)
+            reply["orientation"] = [int(m[1] & 1), int(m[0] & 3), int((m[0] >> 2) & 1)]
         lib.gpujpeg_decoder_destroy(dec)
         return reply
+    elif mode == "file_props":   # gpujpeg_image_get_properties of the reference: [rc, width, height, colour space, pixel format]
+        pi = ImgParam()
+        pi.pixel_format = -1
+        lib.gpujpeg_image_get_properties.argtypes = [C.c_char_p, C.POINTER(ImgParam), C.c_int]
+        rc = lib.gpujpeg_image_get_properties(a[1].encode(), C.byref(pi), int(a[2]))
+        return [rc, pi.width, pi.height, pi.color_space, pi.pixel_format]
+    elif mode == "file_load":    # gpujpeg_image_load_from_file of the reference -> raw dump
+        lib.gpujpeg_image_load_from_file.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        ptr, size = C.c_void_p(), C.c_size_t(0)
+        rc = lib.gpujpeg_image_load_from_file(a[1].encode(), C.byref(ptr), C.byref(size))
+        if rc == 0:
+            np.ctypeslib.as_array((C.c_uint8 * size.value).from_address(ptr.value)).tofile(a[2])
+        return [rc, size.value]
+    elif mode == "file_save":    # gpujpeg_image_save_to_file of the reference: raw dump -> <out> as <fmt> <cs> <w> <h>
+        raw = np.fromfile(a[1], np.uint8)
+        pi = ImgParam()
+        lib.gpujpeg_image_set_default_parameters(C.byref(pi))
+        pi.pixel_format, pi.color_space, pi.width, pi.height = int(a[3]), int(a[4]), int(a[5]), int(a[6])
+        lib.gpujpeg_image_save_to_file.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(ImgParam)]
+        name = C.create_string_buffer(a[2].encode())
+        return [lib.gpujpeg_image_save_to_file(name, raw.ctypes.data, raw.size, C.byref(pi)), name.value.decode()]
     elif mode == "decode":
         data = np.fromfile(a[1], np.uint8)
         dec = lib.gpujpeg_decoder_create(None)

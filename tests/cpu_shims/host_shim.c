@@ -6,6 +6,7 @@
 
 static int g_header_type = 0;   /* GPUJPEG_HEADER_DEFAULT; shim_set_header_type forces a flavour (enc_hdr option) */
 void shim_set_header_type(int t) { g_header_type = t; }
+void shim_set_alpha_sampling(int on) { (void)on; }   /* (kept for the tests' symmetry: the fourth component always follows the first) */
 static struct gj_header_extras g_extras;   /* orientation and user Exif tags of the headers composed below */
 void shim_set_orientation(int set, int rotation, int flip)
 {
@@ -230,9 +231,9 @@ int shim_header2(int width, int height, int quality, int rst, int interleaved, i
     p.restart_interval = rst;
     p.interleaved = interleaved;
     p.comp_count = comps;
-    for ( int c = 0; c < comps; c++ ) {
-        p.sampling_factor[c].horizontal = (uint8_t)(c == 0 ? lhs : 1);
-        p.sampling_factor[c].vertical = (uint8_t)(c == 0 ? lvs : 1);
+    for ( int c = 0; c < comps; c++ ) {   /* a fourth component (alpha) takes the first one's sampling */
+        p.sampling_factor[c].horizontal = (uint8_t)((c == 0 || c == 3) ? lhs : 1);
+        p.sampling_factor[c].vertical = (uint8_t)((c == 0 || c == 3) ? lvs : 1);
     }
     p.color_space_internal = (enum gpujpeg_color_space)internal;
     pi.width = width;
