@@ -101,10 +101,10 @@ def test_exif_and_orientation_through_the_coders():
     img = o.gen_image("photo", w, h)
     plain = o.encode(img, 80, 6)
     d = g.Decoder()
-    for opts, hdr, want in (([("enc_opt_hdr", "Exif")], 8, (1, 0, 0)),
+    for opts, hdr, want in (([("enc_hdr", "Exif")], 8, (1, 0, 0)),
                             ([("enc_exif_tag", "0x10F:ASCII=maker"), ("enc_metadata", "orientation=270-")], 8, (1, 3, 1)),
                             ([("enc_metadata", "orientation=90")], 2, (1, 1, 0)),
-                            ([("enc_metadata", "orientation=180-"), ("enc_opt_hdr", "JFIF")], 1, (0, 0, 0))):
+                            ([("enc_metadata", "orientation=180-"), ("enc_hdr", "JFIF")], 1, (0, 0, 0))):
         e = g.Encoder()
         for k, v in opts:
             e.set_option(k, v)
@@ -127,9 +127,9 @@ def test_exif_and_orientation_through_the_coders():
 
 
 @have_ref
-@pytest.mark.parametrize("opts", [["enc_opt_hdr=Exif", "enc_exif_tag=DateTime=2024:02:29 12:34:56"],
+@pytest.mark.parametrize("opts", [["enc_hdr=Exif", "enc_exif_tag=DateTime=2024:02:29 12:34:56"],
                                   ["enc_exif_tag=DateTime=2024:02:29 12:34:56", "enc_metadata=orientation=90-", "enc_exif_tag=0x9286:UNDEFINED=hello"],
-                                  ["enc_metadata=orientation=180"], ["enc_metadata=orientation=270-", "enc_opt_hdr=SPIFF"]])
+                                  ["enc_metadata=orientation=180"], ["enc_metadata=orientation=270-", "enc_hdr=SPIFF"]])
 def test_exif_and_orientation_against_reference_gpu(tmp_path, opts):
     """whole files of the reference GPU library with the same options: identical bytes (a user DateTime fixes the clock);
     the reference decoder reads the product's orientation back"""
