@@ -140,6 +140,16 @@ extern "C" int gj_cuda_stream_create(gj_stream_t* s)
     return 0;
 }
 extern "C" void gj_cuda_stream_destroy(gj_stream_t s) { cudaStreamDestroy(s); }
+extern "C" int gj_cuda_event_create(void** ev)
+{
+    cudaEvent_t e;
+    if ( cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess ) return -1;
+    *ev = e;
+    return 0;
+}
+extern "C" void gj_cuda_event_destroy(void* ev) { if ( ev ) cudaEventDestroy((cudaEvent_t)ev); }
+extern "C" int gj_cuda_event_record(void* ev, gj_stream_t s) { return cudaEventRecord((cudaEvent_t)ev, s) == cudaSuccess ? 0 : -1; }
+extern "C" int gj_cuda_stream_wait_event(gj_stream_t s, void* ev) { return cudaStreamWaitEvent(s, (cudaEvent_t)ev, 0) == cudaSuccess ? 0 : -1; }
 extern "C" int gj_cuda_enable_peer(int peer)
 {
     const cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);

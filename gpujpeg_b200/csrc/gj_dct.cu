@@ -813,14 +813,14 @@ int pick_vec(const void* p, size_t pitch)
 
 }  // namespace
 
-extern "C" int gj_launch_fdct_rgb444(const uint8_t* d_raw, int width, int height, int pitch, int16_t* d_coef,
-                                     uint64_t* d_nzmask, int bcx, int bcy, const struct gj_dev_enc_tables* h_tables,
-                                     gj_stream_t stream)
+/* `bcy` block rows starting at the pointers given; `nblk` = blocks of a whole component plane (the distance between the
+ * components' coefficients), so that a frame can be transformed stripe by stripe */
+static int launch_fdct_rgb444(const uint8_t* d_raw, int width, int height, int pitch, int16_t* d_coef, uint64_t* d_nzmask,
+                              int bcx, int bcy, int nblk, const struct gj_dev_enc_tables* h_tables, gj_stream_t stream)
 {
     FdctParams prm;
     memcpy(prm.fwd_zz, h_tables->fwd_zz, sizeof prm.fwd_zz);
     const dim3 grid((bcx + TB - 1) / TB, bcy);
-    const int nblk = bcx * bcy;
     /* > 48 KB of dynamic shared memory needs an opt-in, once per device */
     static int attr_done[64];   // set once per device; two host threads racing write the same value
     int dev = 0;
@@ -860,15 +860,31 @@ extern "C" int gj_launch_fdct_rgb444(const uint8_t* d_raw, int width, int height
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-extern "C" int gj_launch_idct_rgb444(const int16_t* d_coef, int bcx, int bcy, const int comp_tq[3], uint8_t* d_raw,
-                                     int width, int height, int pitch, int idct_flavour, int coef_dequantized,
-                                     const struct gj_dev_dec_tables* h_tables, gj_stream_t stream)
+extern "C" int gj_launch_fdct_rgb444(const uint8_t* d_raw, int width, int height, int pitch, int16_t* d_coef,
+                                     uint64_t* d_nzmask, int bcx, int bcy, const struct gj_dev_enc_tables* h_tables,
+                                     gj_stream_t stream)
+{
+    return launch_fdct_rgb444(d_raw, width, height, pitch, d_coef, d_nzmask, bcx, bcy, bcx * bcy, h_tables, stream);
+}
+/* block rows [by0, by1) of the frame only (the encoder's stripe pipeline: rows are transformed while later rows still arrive) */
+extern "C" int gj_launch_fdct_rgb444_rows(const uint8_t* d_raw, int width, int height, int pitch, int16_t* d_coef,
+                                          uint64_t* d_nzmask, int bcx, int bcy, int by0, int by1,
+                                          const struct gj_dev_enc_tables* h_tables, gj_stream_t stream)
+{
+    if ( by0 < 0 || by1 > bcy || by0 >= by1 ) return -1;
+    const int rows = (by1 * 8 < height ? by1 * 8 : height) - by0 * 8;
+    return launch_fdct_rgb444(d_raw + (ptrdiff_t)by0 * 8 * pitch, width, rows, pitch, d_coef + (size_t)by0 * bcx * 64,
+                              d_nzmask + (size_t)by0 * bcx, bcx, by1 - by0, bcx * bcy, h_tables, stream);
+}
+
+static int launch_idct_rgb444(const int16_t* d_coef, int bcx, int bcy, int nblk, const int comp_tq[3], uint8_t* d_raw, int width,
+                              int height, int pitch, int idct_flavour, int coef_dequantized,
+                              const struct gj_dev_dec_tables* h_tables, gj_stream_t stream)
 {
     IdctParams prm;
     for ( int c = 0; c < 3; c++ )
         memcpy(prm.q_zz[c], h_tables->qinv_zz[comp_tq[c]], sizeof prm.q_zz[c]);
     const dim3 grid((bcx + TB - 1) / TB, bcy);
-    const int nblk = bcx * bcy;
     const int vec = pick_vec(d_raw, (size_t)pitch);
     if ( idct_flavour != 0 && coef_dequantized ) return -1;   // the float flavour needs raw coefficients
 #define GJ_K4(V, F, D) k_idct_rgb444<V, F, D><<<grid, NT, 0, stream>>>(d_coef, bcx, nblk, d_raw, width, height, (size_t)pitch, prm)
@@ -883,6 +899,23 @@ extern "C" int gj_launch_idct_rgb444(const int16_t* d_coef, int bcx, int bcy, co
     }
 #undef GJ_K4
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+extern "C" int gj_launch_idct_rgb444(const int16_t* d_coef, int bcx, int bcy, const int comp_tq[3], uint8_t* d_raw,
+                                     int width, int height, int pitch, int idct_flavour, int coef_dequantized,
+                                     const struct gj_dev_dec_tables* h_tables, gj_stream_t stream)
+{
+    return launch_idct_rgb444(d_coef, bcx, bcy, bcx * bcy, comp_tq, d_raw, width, height, pitch, idct_flavour, coef_dequantized,
+                              h_tables, stream);
+}
+/* block rows [by0, by1) only (the decoder's stripe pipeline: finished rows leave for the host while later rows are transformed) */
+extern "C" int gj_launch_idct_rgb444_rows(const int16_t* d_coef, int bcx, int bcy, int by0, int by1, const int comp_tq[3],
+                                          uint8_t* d_raw, int width, int height, int pitch, int idct_flavour,
+                                          int coef_dequantized, const struct gj_dev_dec_tables* h_tables, gj_stream_t stream)
+{
+    if ( by0 < 0 || by1 > bcy || by0 >= by1 ) return -1;
+    const int rows = (by1 * 8 < height ? by1 * 8 : height) - by0 * 8;
+    return launch_idct_rgb444(d_coef + (size_t)by0 * bcx * 64, bcx, by1 - by0, bcx * bcy, comp_tq, d_raw + (ptrdiff_t)by0 * 8 * pitch,
+                              width, rows, pitch, idct_flavour, coef_dequantized, h_tables, stream);
 }
 
 /* ---- subsampled variants: luminance hs x vs in {2x1, 2x2, 1x2}, chrominance 1x1 ---- */

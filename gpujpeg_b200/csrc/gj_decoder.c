@@ -28,8 +28,17 @@
 #define GJ_MK_OTHER_CAP 256 /* markers other than RSTn the device reports back (SOS, EOI, ...) */
 #define GJ_MK_WORDS (8 + 4 * GJ_MK_OTHER_CAP)   /* K0 result block: 8 counters/flags + {rank, position, code, clean position} per marker */
 
+#define GJ_STRIPES 8
+#define GJ_STRIPE_MIN_BYTES ((size_t)8 << 20)
+
 struct gpujpeg_decoder {
     gj_stream_t stream;
+    /* stripe pipeline of host output (4:4:4 RGB frames of GJ_STRIPE_MIN_BYTES or more): K4 runs on GJ_STRIPES pieces of the frame,
+     * every finished piece leaves for the host on a copy stream while the next one is transformed */
+    gj_stream_t copy_stream;
+    void* ev_stripe[GJ_STRIPES]; void* ev_done;
+    int stripes;                  /* GPUJPEG_B200_STRIPES (1 = off), default GJ_STRIPES */
+    size_t stripe_min_bytes;      /* GPUJPEG_B200_STRIPE_MIN_BYTES (tests), default GJ_STRIPE_MIN_BYTES */
     int device;
     int verbose, perf_stats;
     struct gpujpeg_parameters param;
@@ -172,6 +181,10 @@ int gpujpeg_decoder_destroy(struct gpujpeg_decoder* d)
     gj_cuda_free(d->d_planes);
     gj_cuda_free(d->d_raw);
     gj_cuda_free_host(d->h_raw);
+    if ( d->copy_stream ) gj_cuda_stream_destroy(d->copy_stream);
+    gj_cuda_event_destroy(d->ev_done);
+    for ( int i = 0; i < GJ_STRIPES; i++ )
+        gj_cuda_event_destroy(d->ev_stripe[i]);
     gj_timer_destroy(&d->t_to);
     gj_timer_destroy(&d->t_from);
     gj_timer_destroy(&d->t_huff);
@@ -339,6 +352,54 @@ static int launch_k4(struct gpujpeg_decoder* d, const int comp_tq[GJ_MAX_COMP], 
                                      coef_dequantized, &d->h_tab, d->stream);
     return gj_launch_idct_rgb_ss(d->d_coef, g->comp, comp_tq, d_out, g->width, g->height, pitch, d->idct_flavour,
                                  coef_dequantized, &d->h_tab, d->stream);
+}
+
+/* The stripe pipeline applies to what the fused 4:4:4 kernel writes as it goes: no flip, no channel remap. */
+static int stripes_usable(struct gpujpeg_decoder* d)
+{
+    const struct gj_geometry* g = &d->geo;
+    if ( d->out_mode != GJ_OUT_RGB || !g->lay.simple || d->flipped || d->channel_remap ) return 0;
+    if ( d->stripes == 0 ) {
+        const char* v = getenv("GPUJPEG_B200_STRIPES");
+        const char* m = getenv("GPUJPEG_B200_STRIPE_MIN_BYTES");
+        d->stripe_min_bytes = m ? (size_t)strtoull(m, NULL, 0) : GJ_STRIPE_MIN_BYTES;
+        d->stripes = v ? atoi(v) : GJ_STRIPES;
+        if ( d->stripes < 1 ) d->stripes = 1;
+        if ( d->stripes > GJ_STRIPES ) d->stripes = GJ_STRIPES;
+    }
+    if ( d->stripes < 2 || g->bcy < 2 * d->stripes || g->raw_size < d->stripe_min_bytes ) return 0;
+    if ( !d->copy_stream ) {
+        if ( gj_cuda_stream_create(&d->copy_stream) || gj_cuda_event_create(&d->ev_done) ) {
+            d->stripes = 1;
+            return 0;
+        }
+        for ( int i = 0; i < GJ_STRIPES; i++ )
+            if ( gj_cuda_event_create(&d->ev_stripe[i]) ) {
+                d->stripes = 1;
+                return 0;
+            }
+    }
+    return 1;
+}
+
+/* K4 stripe by stripe on the coder's stream, D2H of every finished stripe on the copy stream; the coder's stream then waits
+ * for the last copy, so that its next synchronisation covers the whole picture */
+static int decode_striped(struct gpujpeg_decoder* d, const int comp_tq[GJ_MAX_COMP], uint8_t* d_out, uint8_t* h_dst, int coef_dequantized)
+{
+    const struct gj_geometry* g = &d->geo;
+    for ( int i = 0; i < d->stripes; i++ ) {
+        const int by0 = (int)((long long)g->bcy * i / d->stripes), by1 = (int)((long long)g->bcy * (i + 1) / d->stripes);
+        const size_t row0 = (size_t)by0 * 8, row1 = (size_t)by1 * 8 < (size_t)g->height ? (size_t)by1 * 8 : (size_t)g->height;
+        const size_t off = row0 * (size_t)g->pitch;
+        const size_t bytes = (i + 1 == d->stripes ? g->raw_size : row1 * (size_t)g->pitch) - off;
+        if ( gj_launch_idct_rgb444_rows(d->d_coef, g->bcx, g->bcy, by0, by1, comp_tq, d_out, g->width, g->height, g->pitch,
+                                        d->idct_flavour, coef_dequantized, &d->h_tab, d->stream) ||
+             gj_cuda_event_record(d->ev_stripe[i], d->stream) || gj_cuda_stream_wait_event(d->copy_stream, d->ev_stripe[i]) ||
+             gj_cuda_memcpy_d2h_async(h_dst + off, d_out + off, bytes, d->copy_stream) )
+            return -1;
+    }
+    if ( gj_cuda_event_record(d->ev_done, d->copy_stream) || gj_cuda_stream_wait_event(d->stream, d->ev_done) ) return -1;
+    return 0;
 }
 
 /* A stream whose restart markers do not count RST0..RST7 cyclically (or whose count does not fit the geometry): the
@@ -870,7 +931,26 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
         GJ_ERR("OpenGL texture output is not supported in this build.\n");
         return GPUJPEG_ERROR;
     }
-    if ( launch_k4(d, st.comp_tq, d_out, ha.dequantize) ) {
+    const int to_host = output->type == GPUJPEG_DECODER_OUTPUT_INTERNAL_BUFFER || output->type == GPUJPEG_DECODER_OUTPUT_CUSTOM_BUFFER;
+    uint8_t* h_dst = output->data;
+    if ( to_host ) {
+        if ( output->type == GPUJPEG_DECODER_OUTPUT_INTERNAL_BUFFER ) {
+            if ( grow_host((void**)&d->h_raw, &d->h_raw_size, g->raw_size) ) return GPUJPEG_ERROR;
+            h_dst = d->h_raw;
+        }
+        else if ( !h_dst ) {
+            return GPUJPEG_ERROR;
+        }
+    }
+    int copied = 0;
+    if ( to_host && !stats && stripes_usable(d) ) {
+        if ( decode_striped(d, st.comp_tq, d_out, h_dst, ha.dequantize) ) {
+            GJ_ERR("Inverse DCT / copy of raw data failed: %s\n", gj_cuda_last_error());
+            return GPUJPEG_ERROR;
+        }
+        copied = 1;
+    }
+    else if ( launch_k4(d, st.comp_tq, d_out, ha.dequantize) ) {
         GJ_ERR("Inverse DCT launch failed: %s\n", gj_cuda_last_error());
         return GPUJPEG_ERROR;
     }
@@ -890,21 +970,15 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
 
     output->data_size = g->raw_size;
     output->param_image = pi;
-    if ( output->type == GPUJPEG_DECODER_OUTPUT_INTERNAL_BUFFER || output->type == GPUJPEG_DECODER_OUTPUT_CUSTOM_BUFFER ) {
-        uint8_t* h_dst = output->data;
-        if ( output->type == GPUJPEG_DECODER_OUTPUT_INTERNAL_BUFFER ) {
-            if ( grow_host((void**)&d->h_raw, &d->h_raw_size, g->raw_size) ) return GPUJPEG_ERROR;
-            h_dst = d->h_raw;
+    if ( to_host ) {
+        if ( !copied ) {
+            if ( stats && d->timers_ok ) gj_timer_start(&d->t_from, d->stream);
+            if ( gj_cuda_memcpy_d2h_async(h_dst, d_out, g->raw_size, d->stream) ) {
+                GJ_ERR("Decoder copy of raw data failed: %s\n", gj_cuda_last_error());
+                return GPUJPEG_ERROR;
+            }
+            if ( stats && d->timers_ok ) gj_timer_stop(&d->t_from, d->stream);
         }
-        else if ( !h_dst ) {
-            return GPUJPEG_ERROR;
-        }
-        if ( stats && d->timers_ok ) gj_timer_start(&d->t_from, d->stream);
-        if ( gj_cuda_memcpy_d2h_async(h_dst, d_out, g->raw_size, d->stream) ) {
-            GJ_ERR("Decoder copy of raw data failed: %s\n", gj_cuda_last_error());
-            return GPUJPEG_ERROR;
-        }
-        if ( stats && d->timers_ok ) gj_timer_stop(&d->t_from, d->stream);
         output->data = h_dst;
     }
     else {

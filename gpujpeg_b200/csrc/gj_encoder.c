@@ -23,6 +23,9 @@
 
 #include "gj_internal.h"
 
+#define GJ_STRIPES 8
+#define GJ_STRIPE_MIN_BYTES ((size_t)8 << 20)
+
 struct gpujpeg_encoder {
     gj_stream_t stream;
     int device;
@@ -69,6 +72,12 @@ struct gpujpeg_encoder {
     /* host output */
     uint8_t* out; size_t out_size; int out_is_pinned;
     uint8_t* header; size_t header_cap; size_t header_size;   /* file header, composed on the host */
+    /* stripe pipeline of host images (4:4:4 RGB frames of GJ_STRIPE_MIN_BYTES or more): the image arrives in GJ_STRIPES pieces
+     * on a copy stream, K1 runs on every piece as soon as it is there -- the transform hides behind the PCIe transfer */
+    gj_stream_t copy_stream;
+    void* ev_begin; void* ev_stripe[GJ_STRIPES];
+    int stripes;                               /* GPUJPEG_B200_STRIPES (1 = off), default GJ_STRIPES */
+    size_t stripe_min_bytes;                   /* GPUJPEG_B200_STRIPE_MIN_BYTES (tests), default GJ_STRIPE_MIN_BYTES */
     struct gj_header_extras extras;            /* enc_metadata (orientation), enc_exif_tag (user tags, owned) */
     int extras_dirty;                          /* an option changed what the header carries */
 
@@ -156,6 +165,10 @@ int gpujpeg_encoder_destroy(struct gpujpeg_encoder* e)
     gj_cuda_free(e->d_sos);
     free(e->h_pre);
     free(e->header);
+    if ( e->copy_stream ) gj_cuda_stream_destroy(e->copy_stream);
+    gj_cuda_event_destroy(e->ev_begin);
+    for ( int i = 0; i < GJ_STRIPES; i++ )
+        gj_cuda_event_destroy(e->ev_stripe[i]);
     gj_exif_tags_destroy((struct gj_exif_tags*)e->extras.exif_tags);
     gj_cuda_free(e->d_seg_pos);
     if ( e->h_seg_pos ) gj_cuda_free_host(e->h_seg_pos);
@@ -331,6 +344,54 @@ static int launch_k1(struct gpujpeg_encoder* e, const uint8_t* d_raw)
         return gj_launch_fdct_rgb444(d_raw, g->width, g->height, pitch, e->d_coef, e->d_nzmask, g->bcx, g->bcy, &e->h_tab,
                                      e->stream);
     return gj_launch_fdct_rgb_ss(d_raw, g->width, g->height, pitch, e->d_coef, e->d_nzmask, g->comp, &e->h_tab, e->stream);
+}
+
+/* The stripe pipeline applies to what the fused 4:4:4 kernel takes as it comes: no flip, no channel remap. */
+static int stripes_usable(struct gpujpeg_encoder* e)
+{
+    const struct gj_geometry* g = &e->geo;
+    if ( e->input_mode != GJ_IN_RGB || !g->lay.simple || e->flipped || e->channel_remap ) return 0;
+    if ( e->stripes == 0 ) {
+        const char* v = getenv("GPUJPEG_B200_STRIPES");
+        const char* m = getenv("GPUJPEG_B200_STRIPE_MIN_BYTES");
+        e->stripe_min_bytes = m ? (size_t)strtoull(m, NULL, 0) : GJ_STRIPE_MIN_BYTES;
+        e->stripes = v ? atoi(v) : GJ_STRIPES;
+        if ( e->stripes < 1 ) e->stripes = 1;
+        if ( e->stripes > GJ_STRIPES ) e->stripes = GJ_STRIPES;
+    }
+    if ( e->stripes < 2 || g->bcy < 2 * e->stripes || g->raw_size < e->stripe_min_bytes ) return 0;
+    if ( !e->copy_stream ) {
+        if ( gj_cuda_stream_create(&e->copy_stream) || gj_cuda_event_create(&e->ev_begin) ) {
+            e->stripes = 1;
+            return 0;
+        }
+        for ( int i = 0; i < GJ_STRIPES; i++ )
+            if ( gj_cuda_event_create(&e->ev_stripe[i]) ) {
+                e->stripes = 1;
+                return 0;
+            }
+    }
+    return 1;
+}
+
+/* H2D of the host image in stripes of whole block rows on the copy stream; K1 of a stripe on the coder's stream as soon as the
+ * stripe has arrived.  The copy stream starts behind everything the coder's stream holds (the previous frame's K1 reads d_raw). */
+static int encode_striped(struct gpujpeg_encoder* e, const uint8_t* h_image)
+{
+    const struct gj_geometry* g = &e->geo;
+    if ( gj_cuda_event_record(e->ev_begin, e->stream) || gj_cuda_stream_wait_event(e->copy_stream, e->ev_begin) ) return -1;
+    for ( int i = 0; i < e->stripes; i++ ) {
+        const int by0 = (int)((long long)g->bcy * i / e->stripes), by1 = (int)((long long)g->bcy * (i + 1) / e->stripes);
+        const size_t row0 = (size_t)by0 * 8, row1 = (size_t)by1 * 8 < (size_t)g->height ? (size_t)by1 * 8 : (size_t)g->height;
+        const size_t off = row0 * (size_t)g->pitch;
+        const size_t bytes = (i + 1 == e->stripes ? g->raw_size : row1 * (size_t)g->pitch) - off;
+        if ( gj_cuda_memcpy_h2d_async(e->d_raw + off, h_image + off, bytes, e->copy_stream) ||
+             gj_cuda_event_record(e->ev_stripe[i], e->copy_stream) || gj_cuda_stream_wait_event(e->stream, e->ev_stripe[i]) ||
+             gj_launch_fdct_rgb444_rows(e->d_raw, g->width, g->height, g->pitch, e->d_coef, e->d_nzmask, g->bcx, g->bcy, by0, by1,
+                                        &e->h_tab, e->stream) )
+            return -1;
+    }
+    return 0;
 }
 
 static void fill_huff_args(const struct gpujpeg_encoder* e, struct gj_huff_enc_args* ha)
@@ -653,6 +714,7 @@ int gpujpeg_encoder_encode(struct gpujpeg_encoder* e, const struct gpujpeg_param
 
     /* input [ref: src/gpujpeg_encoder.c:402-476] */
     const uint8_t* d_raw;
+    int k1_done = 0;
     if ( input->type == GPUJPEG_ENCODER_INPUT_IMAGE ) {
         /* the reference's unit test passes a device pointer as a host image and expects it to work
          * [ref: test/unit/run_tests.c:40-79]; cudaMemcpyDefault semantics give the same result */
@@ -660,15 +722,24 @@ int gpujpeg_encoder_encode(struct gpujpeg_encoder* e, const struct gpujpeg_param
             GJ_ERR("Encoder raw data allocation failed: %s\n", gj_cuda_last_error());
             return GPUJPEG_ERROR;
         }
-        if ( stats && e->timers_ok ) gj_timer_start(&e->t_to, e->stream);
-        int rc = gj_cuda_pointer_is_device(input->image)
-                     ? gj_cuda_memcpy_d2d_async(e->d_raw, input->image, g->raw_size, e->stream)
-                     : gj_cuda_memcpy_h2d_async(e->d_raw, input->image, g->raw_size, e->stream);
-        if ( rc ) {
-            GJ_ERR("Encoder raw data copy failed: %s\n", gj_cuda_last_error());
-            return GPUJPEG_ERROR;
+        const int on_device = gj_cuda_pointer_is_device(input->image);
+        if ( !on_device && !stats && stripes_usable(e) ) {
+            if ( encode_striped(e, input->image) ) {
+                GJ_ERR("Encoder raw data copy / forward DCT failed: %s\n", gj_cuda_last_error());
+                return GPUJPEG_ERROR;
+            }
+            k1_done = 1;
         }
-        if ( stats && e->timers_ok ) gj_timer_stop(&e->t_to, e->stream);
+        else {
+            if ( stats && e->timers_ok ) gj_timer_start(&e->t_to, e->stream);
+            int rc = on_device ? gj_cuda_memcpy_d2d_async(e->d_raw, input->image, g->raw_size, e->stream)
+                               : gj_cuda_memcpy_h2d_async(e->d_raw, input->image, g->raw_size, e->stream);
+            if ( rc ) {
+                GJ_ERR("Encoder raw data copy failed: %s\n", gj_cuda_last_error());
+                return GPUJPEG_ERROR;
+            }
+            if ( stats && e->timers_ok ) gj_timer_stop(&e->t_to, e->stream);
+        }
         d_raw = e->d_raw;
     }
     else if ( input->type == GPUJPEG_ENCODER_INPUT_GPU_IMAGE ) {
@@ -700,7 +771,7 @@ int gpujpeg_encoder_encode(struct gpujpeg_encoder* e, const struct gpujpeg_param
         gj_timer_start(&e->t_gpu, e->stream);
         gj_timer_start(&e->t_pre, e->stream);
     }
-    if ( launch_k1(e, d_raw) ) {
+    if ( !k1_done && launch_k1(e, d_raw) ) {
         GJ_ERR("Forward DCT launch failed: %s\n", gj_cuda_last_error());
         return GPUJPEG_ERROR;
     }

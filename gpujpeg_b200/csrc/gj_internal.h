@@ -287,6 +287,13 @@ struct gj_dev_dec_tables {
 int gj_launch_fdct_rgb444(const uint8_t* d_raw, int width, int height, int pitch, int16_t* d_coef, uint64_t* d_nzmask,
                           int bcx, int bcy, const struct gj_dev_enc_tables* d_tables, gj_stream_t stream);
 
+/* block rows [by0, by1) of the frame only: the stripe pipelines of the host-buffer calls (gj_encoder.c, gj_decoder.c) */
+int gj_launch_fdct_rgb444_rows(const uint8_t* d_raw, int width, int height, int pitch, int16_t* d_coef, uint64_t* d_nzmask,
+                               int bcx, int bcy, int by0, int by1, const struct gj_dev_enc_tables* d_tables, gj_stream_t stream);
+int gj_launch_idct_rgb444_rows(const int16_t* d_coef, int bcx, int bcy, int by0, int by1, const int comp_tq[3], uint8_t* d_raw,
+                               int width, int height, int pitch, int idct_flavour, int coef_dequantized,
+                               const struct gj_dev_dec_tables* d_tables, gj_stream_t stream);
+
 /* K2: Huffman-encode every restart segment and assemble the finished scan data
  * [replaces ref: src/gpujpeg_huffman_gpu_encoder.cu:1071-1167 + host loop src/gpujpeg_encoder.c:567-626]
  * d_stream receives [header gap][SOS][scan 0]...[EOI]; d_info[0] = total bytes, d_info[1] = error flag */
@@ -422,7 +429,11 @@ int gj_cuda_memcpy_d2h_async(void* dst, const void* src, size_t size, gj_stream_
 int gj_cuda_memcpy_d2d_async(void* dst, const void* src, size_t size, gj_stream_t s);
 int gj_cuda_memset_async(void* dst, int v, size_t size, gj_stream_t s);
 int gj_cuda_stream_sync(gj_stream_t s);
-int gj_cuda_stream_create(gj_stream_t* s);
+int gj_cuda_stream_create(gj_stream_t* s);   /* non-blocking: runs next to the legacy default stream */
+int gj_cuda_event_create(void** ev);          /* timing disabled */
+void gj_cuda_event_destroy(void* ev);
+int gj_cuda_event_record(void* ev, gj_stream_t s);
+int gj_cuda_stream_wait_event(gj_stream_t s, void* ev);
 void gj_cuda_stream_destroy(gj_stream_t s);
 int gj_cuda_enable_peer(int peer);
 int gj_cuda_memcpy_peer_async(void* dst, int dst_dev, const void* src, int src_dev, size_t size, gj_stream_t s);

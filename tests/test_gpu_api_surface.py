@@ -192,3 +192,29 @@ def test_image_files_through_the_public_api(tmp_path, name, fmt, cs):
         mine = api.ImageParameters(0, 0, 0, -1, 0)
         rc = lib.gpujpeg_image_get_properties(probe.encode(), C.byref(mine), 0)
         assert [rc, mine.color_space, mine.pixel_format] == [want[0], want[3], want[4]], probe
+
+
+@pytest.mark.parametrize("w,h,stripes", [(1920, 1080, 8), (1119, 561, 5), (640, 136, 8), (3840, 2160, 0)])
+def test_stripe_pipeline_of_host_buffers(monkeypatch, w, h, stripes):
+    """host images of 8 MB or more are copied and transformed stripe by stripe (K1 behind the upload, the download behind K4):
+    the same bytes and pixels as ever -- pinned and pageable buffers, frame heights that do not divide into the stripes, and
+    small frames with the threshold lowered"""
+    import torch
+    import gpujpeg_b200 as g
+    if stripes:
+        monkeypatch.setenv("GPUJPEG_B200_STRIPES", str(stripes))
+        monkeypatch.setenv("GPUJPEG_B200_STRIPE_MIN_BYTES", "1")
+    img = o.gen_image("photo", w, h)
+    want = o.encode(img, 80, 12, threads=4)
+    pix = o.decode(want, threads=4)
+    e, d = g.Encoder(), g.Decoder()
+    pinned = torch.from_numpy(img).pin_memory()
+    for src in (img, pinned, img):
+        assert np.array_equal(e.encode(src, 80, 12), want)
+    out = torch.empty((h, w, 3), dtype=torch.uint8).pin_memory()
+    d.decode(want, out=out.numpy())
+    assert np.array_equal(out.numpy(), pix)
+    assert np.array_equal(d.decode(want), pix)
+    assert np.array_equal(d.decode(want, out=np.zeros((h, w, 3), np.uint8)), pix)
+    e.close()
+    d.close()
