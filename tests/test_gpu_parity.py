@@ -358,14 +358,16 @@ def test_row_padding(enc):
 
 def test_unsupported_parameters_fail_loudly(gj, enc):
     p = gj.api.default_parameters()
-    pi = gj.api.image_parameters(64, 64)
-    pi.pixel_format = 6                      # GPUJPEG_4444_U8_P0123 ...
-    p.comp_count = 4                         # ... as a 4-component JPEG: alpha planes are outside this build
+    pi = gj.api.image_parameters(64, 64)     # 444-u8-p012 ...
+    p.comp_count = 4                         # ... cannot feed a 4-component JPEG: there are no alpha samples
     for c in range(4):
         p.sampling_factor[c].horizontal = p.sampling_factor[c].vertical = 1
-    img = np.zeros((64, 64, 4), np.uint8)
     with pytest.raises(gj.GpuJpegError):
-        enc.encode_raw(img, p, pi)
+        enc.encode_raw(np.zeros((64, 64, 3), np.uint8), p, pi)
+    pi.pixel_format = 6                      # GPUJPEG_4444_U8_P0123 has them, but the alpha component follows the first one's sampling
+    p.sampling_factor[0].horizontal = 2
+    with pytest.raises(gj.GpuJpegError):
+        enc.encode_raw(np.zeros((64, 64, 4), np.uint8), p, pi)
     p = gj.api.default_parameters()
     p.color_space_internal = gj.api.GPUJPEG_YCBCR_BT709   # this pair is converted with the wrong matrix by the reference
     with pytest.raises(gj.GpuJpegError):
