@@ -71,4 +71,27 @@ jpeg[marks[5] + 1] = 0xD0 + ((jpeg[marks[5] + 1] - 0xD0 + 3) & 7)
 bad = np.frombuffer(bytes(jpeg), np.uint8)
 assert np.array_equal(dec.decode(bad), o.decode(bad))
 print("ok segment info / flip / resync", flush=True)
+# 4-component JPEG (alpha as fourth component through the generic pass, four scans / one interleaved scan of four components)
+from test_alpha_component import rgba  # noqa: E402
+for il, sub, samp in ((0, "4:4:4", (1, 1)), (1, "4:2:0", (2, 2))):
+    w, h = 130, 70
+    im4 = rgba(w, h)
+    want = o.encode_any(im4, w, h, o.FMT_4444_P0123, o.CS_RGB, 80, 3, il, samp, alpha=True)
+    got = enc.encode_samples(im4.reshape(-1), w, h, 6, 80, 3, il, color_space=1, subsampling=sub, alpha=True)
+    assert np.array_equal(got, want)
+    d = g.Decoder()
+    out, _ = d.decode_samples(want)
+    assert np.array_equal(out, o.decode_any(want, o.FMT_4444_P0123, o.CS_RGB))
+    d.close()
+print("ok 4-component", flush=True)
+# stripe pipeline of the host-buffer calls (threshold lowered so that a small frame takes it)
+os.environ["GPUJPEG_B200_STRIPES"] = "5"
+os.environ["GPUJPEG_B200_STRIPE_MIN_BYTES"] = "1"
+e3, d3 = g.Encoder(), g.Decoder()
+img = o.gen_image("photo", 333, 203)
+want = o.encode(img, 80, 5)
+assert np.array_equal(e3.encode(img, 80, 5), want) and np.array_equal(d3.decode(want), o.decode(want))
+e3.close()
+d3.close()
+print("ok stripes", flush=True)
 print("all sanitizer cases ok")
