@@ -919,29 +919,51 @@ extern "C" int gj_launch_idct_rgb444_rows(const int16_t* d_coef, int bcx, int bc
 }
 
 /* ---- subsampled variants: luminance hs x vs in {2x1, 2x2, 1x2}, chrominance 1x1 ---- */
-extern "C" int gj_launch_fdct_rgb_ss(const uint8_t* d_raw, int width, int height, int pitch, int16_t* d_coef,
-                                     uint64_t* d_nzmask, const struct gj_comp_geo comp[3],
-                                     const struct gj_dev_enc_tables* h_tables, gj_stream_t stream)
+/* The block grids of the three components restricted to the MCU rows [my0, my1) (an MCU row = 8 * vs image rows): the kernels
+ * index every plane from its first block of the range, so a frame can be transformed stripe by stripe.  Returns the image
+ * rows the range holds. */
+static int ss_grid_rows(SsGrid* sg, const struct gj_comp_geo comp[3], int my0, int my1, int height)
+{
+    const int vs = comp[0].vs;
+    for ( int c = 0; c < 3; c++ ) {
+        const int per = c == 0 ? vs : 1;   /* block rows of the component per MCU row */
+        const int lo = my0 * per, hi = my1 * per < comp[c].bcy ? my1 * per : comp[c].bcy;
+        sg->bcx[c] = comp[c].bcx;
+        sg->bcy[c] = hi > lo ? hi - lo : 0;
+        sg->blk_off[c] = comp[c].blk_off + lo * comp[c].bcx;
+    }
+    const int y0 = my0 * 8 * vs, y1 = my1 * 8 * vs < height ? my1 * 8 * vs : height;
+    return y1 > y0 ? y1 - y0 : 0;
+}
+
+extern "C" int gj_launch_fdct_rgb_ss_rows(const uint8_t* d_raw, int width, int height, int pitch, int16_t* d_coef,
+                                          uint64_t* d_nzmask, const struct gj_comp_geo comp[3], int my0, int my1,
+                                          const struct gj_dev_enc_tables* h_tables, gj_stream_t stream)
 {
     FdctParams prm;
     memcpy(prm.fwd_zz, h_tables->fwd_zz, sizeof prm.fwd_zz);
-    SsGrid sg;
-    for ( int c = 0; c < 3; c++ ) {
-        sg.bcx[c] = comp[c].bcx;
-        sg.bcy[c] = comp[c].bcy;
-        sg.blk_off[c] = comp[c].blk_off;
-    }
     const int hs = comp[0].hs, vs = comp[0].vs;
     if ( comp[1].hs != 1 || comp[1].vs != 1 || comp[2].hs != 1 || comp[2].vs != 1 ) return -1;
-    const dim3 grid((comp[0].bcx + TB - 1) / TB, (comp[0].bcy + vs - 1) / vs);
+    const int mcu_rows = (comp[0].bcy + vs - 1) / vs;
+    if ( my0 < 0 || my1 > mcu_rows || my0 >= my1 ) return -1;
+    SsGrid sg;
+    height = ss_grid_rows(&sg, comp, my0, my1, height);
+    d_raw += (ptrdiff_t)my0 * 8 * vs * pitch;
+    const dim3 grid((comp[0].bcx + TB - 1) / TB, my1 - my0);
     const int vec = pick_vec(d_raw, (size_t)pitch);
+    static int attr_done[64][4];   // the shared-memory opt-in of a template instance, once per device
+    int dev = 0;
+    if ( cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 ) return -1;
 #define GJ_K1SS(H, V)                                                                                                        \
     do {                                                                                                                     \
         constexpr int nt = TB * V + 2 * TB / H;                                                                              \
         constexpr int sm = nt * BLK_F * 4;                                                                                   \
-        if ( cudaFuncSetAttribute(k_fdct_rgb_ss<H, V, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm) != cudaSuccess || \
-             cudaFuncSetAttribute(k_fdct_rgb_ss<H, V, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm) != cudaSuccess )  \
-            return -1;                                                                                                       \
+        if ( !__atomic_load_n(&attr_done[dev][H * 2 + V - 3], __ATOMIC_ACQUIRE) ) {                                          \
+            if ( cudaFuncSetAttribute(k_fdct_rgb_ss<H, V, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm) != cudaSuccess || \
+                 cudaFuncSetAttribute(k_fdct_rgb_ss<H, V, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm) != cudaSuccess )  \
+                return -1;                                                                                                   \
+            __atomic_store_n(&attr_done[dev][H * 2 + V - 3], 1, __ATOMIC_RELEASE);                                           \
+        }                                                                                                                    \
         if ( vec == 4 )                                                                                                      \
             k_fdct_rgb_ss<H, V, 4><<<grid, nt, sm, stream>>>(d_raw, width, height, (size_t)pitch, d_coef, d_nzmask, sg, prm); \
         else                                                                                                                 \
@@ -954,24 +976,31 @@ extern "C" int gj_launch_fdct_rgb_ss(const uint8_t* d_raw, int width, int height
 #undef GJ_K1SS
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
+extern "C" int gj_launch_fdct_rgb_ss(const uint8_t* d_raw, int width, int height, int pitch, int16_t* d_coef,
+                                     uint64_t* d_nzmask, const struct gj_comp_geo comp[3],
+                                     const struct gj_dev_enc_tables* h_tables, gj_stream_t stream)
+{
+    const int vs = comp[0].vs > 0 ? comp[0].vs : 1;
+    return gj_launch_fdct_rgb_ss_rows(d_raw, width, height, pitch, d_coef, d_nzmask, comp, 0, (comp[0].bcy + vs - 1) / vs, h_tables,
+                                      stream);
+}
 
-extern "C" int gj_launch_idct_rgb_ss(const int16_t* d_coef, const struct gj_comp_geo comp[3], const int comp_tq[3],
-                                     uint8_t* d_raw, int width, int height, int pitch, int idct_flavour,
-                                     int coef_dequantized, const struct gj_dev_dec_tables* h_tables, gj_stream_t stream)
+extern "C" int gj_launch_idct_rgb_ss_rows(const int16_t* d_coef, const struct gj_comp_geo comp[3], int my0, int my1,
+                                          const int comp_tq[3], uint8_t* d_raw, int width, int height, int pitch, int idct_flavour,
+                                          int coef_dequantized, const struct gj_dev_dec_tables* h_tables, gj_stream_t stream)
 {
     IdctParams prm;
     for ( int c = 0; c < 3; c++ )
         memcpy(prm.q_zz[c], h_tables->qinv_zz[comp_tq[c]], sizeof prm.q_zz[c]);
-    SsGrid sg;
-    for ( int c = 0; c < 3; c++ ) {
-        sg.bcx[c] = comp[c].bcx;
-        sg.bcy[c] = comp[c].bcy;
-        sg.blk_off[c] = comp[c].blk_off;
-    }
     const int hs = comp[0].hs, vs = comp[0].vs;
     if ( comp[1].hs != 1 || comp[1].vs != 1 || comp[2].hs != 1 || comp[2].vs != 1 ) return -1;
     if ( idct_flavour != 0 && coef_dequantized ) return -1;
-    const dim3 grid((comp[0].bcx + TB - 1) / TB, (comp[0].bcy + vs - 1) / vs);
+    const int mcu_rows = (comp[0].bcy + vs - 1) / vs;
+    if ( my0 < 0 || my1 > mcu_rows || my0 >= my1 ) return -1;
+    SsGrid sg;
+    height = ss_grid_rows(&sg, comp, my0, my1, height);
+    d_raw += (ptrdiff_t)my0 * 8 * vs * pitch;
+    const dim3 grid((comp[0].bcx + TB - 1) / TB, my1 - my0);
     const int vec = pick_vec(d_raw, (size_t)pitch);
 #define GJ_K4SS2(H, V, VE, F, D) \
     k_idct_rgb_ss<H, V, VE, F, D><<<grid, TB * V + 2 * TB / H, 0, stream>>>(d_coef, sg, d_raw, width, height, (size_t)pitch, prm)
@@ -994,6 +1023,14 @@ extern "C" int gj_launch_idct_rgb_ss(const int16_t* d_coef, const struct gj_comp
 #undef GJ_K4SS
 #undef GJ_K4SS2
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+extern "C" int gj_launch_idct_rgb_ss(const int16_t* d_coef, const struct gj_comp_geo comp[3], const int comp_tq[3],
+                                     uint8_t* d_raw, int width, int height, int pitch, int idct_flavour,
+                                     int coef_dequantized, const struct gj_dev_dec_tables* h_tables, gj_stream_t stream)
+{
+    const int vs = comp[0].vs > 0 ? comp[0].vs : 1;
+    return gj_launch_idct_rgb_ss_rows(d_coef, comp, 0, (comp[0].bcy + vs - 1) / vs, comp_tq, d_raw, width, height, pitch,
+                                      idct_flavour, coef_dequantized, h_tables, stream);
 }
 
 /* ---- no colour transform: grey, planar and packed YCbCr formats ---- */

@@ -33,7 +33,7 @@
 
 struct gpujpeg_decoder {
     gj_stream_t stream;
-    /* stripe pipeline of host output (4:4:4 RGB frames of GJ_STRIPE_MIN_BYTES or more): K4 runs on GJ_STRIPES pieces of the frame,
+    /* stripe pipeline of host output (RGB frames of GJ_STRIPE_MIN_BYTES or more from the fused kernels): K4 runs on GJ_STRIPES pieces of the frame,
      * every finished piece leaves for the host on a copy stream while the next one is transformed */
     gj_stream_t copy_stream;
     void* ev_stripe[GJ_STRIPES]; void* ev_done;
@@ -354,11 +354,11 @@ static int launch_k4(struct gpujpeg_decoder* d, const int comp_tq[GJ_MAX_COMP], 
                                  coef_dequantized, &d->h_tab, d->stream);
 }
 
-/* The stripe pipeline applies to what the fused 4:4:4 kernel writes as it goes: no flip, no channel remap. */
+/* The stripe pipeline applies to what the fused RGB kernels write as they go: no flip, no channel remap. */
 static int stripes_usable(struct gpujpeg_decoder* d)
 {
     const struct gj_geometry* g = &d->geo;
-    if ( d->out_mode != GJ_OUT_RGB || !g->lay.simple || d->flipped || d->channel_remap ) return 0;
+    if ( d->out_mode != GJ_OUT_RGB || d->flipped || d->channel_remap ) return 0;
     if ( d->stripes == 0 ) {
         const char* v = getenv("GPUJPEG_B200_STRIPES");
         const char* m = getenv("GPUJPEG_B200_STRIPE_MIN_BYTES");
@@ -367,7 +367,7 @@ static int stripes_usable(struct gpujpeg_decoder* d)
         if ( d->stripes < 1 ) d->stripes = 1;
         if ( d->stripes > GJ_STRIPES ) d->stripes = GJ_STRIPES;
     }
-    if ( d->stripes < 2 || g->bcy < 2 * d->stripes || g->raw_size < d->stripe_min_bytes ) return 0;
+    if ( d->stripes < 2 || g->bcy / g->max_vs < 2 * d->stripes || g->raw_size < d->stripe_min_bytes ) return 0;
     if ( !d->copy_stream ) {
         if ( gj_cuda_stream_create(&d->copy_stream) || gj_cuda_event_create(&d->ev_done) ) {
             d->stripes = 1;
@@ -387,13 +387,18 @@ static int stripes_usable(struct gpujpeg_decoder* d)
 static int decode_striped(struct gpujpeg_decoder* d, const int comp_tq[GJ_MAX_COMP], uint8_t* d_out, uint8_t* h_dst, int coef_dequantized)
 {
     const struct gj_geometry* g = &d->geo;
+    const int mcu_h = 8 * g->max_vs;                                  /* image rows per MCU row (4:4:4: one block row) */
+    const int mcu_rows = (g->bcy + g->max_vs - 1) / g->max_vs;
     for ( int i = 0; i < d->stripes; i++ ) {
-        const int by0 = (int)((long long)g->bcy * i / d->stripes), by1 = (int)((long long)g->bcy * (i + 1) / d->stripes);
-        const size_t row0 = (size_t)by0 * 8, row1 = (size_t)by1 * 8 < (size_t)g->height ? (size_t)by1 * 8 : (size_t)g->height;
+        const int my0 = (int)((long long)mcu_rows * i / d->stripes), my1 = (int)((long long)mcu_rows * (i + 1) / d->stripes);
+        const size_t row0 = (size_t)my0 * mcu_h, row1 = (size_t)my1 * mcu_h < (size_t)g->height ? (size_t)my1 * mcu_h : (size_t)g->height;
         const size_t off = row0 * (size_t)g->pitch;
         const size_t bytes = (i + 1 == d->stripes ? g->raw_size : row1 * (size_t)g->pitch) - off;
-        if ( gj_launch_idct_rgb444_rows(d->d_coef, g->bcx, g->bcy, by0, by1, comp_tq, d_out, g->width, g->height, g->pitch,
-                                        d->idct_flavour, coef_dequantized, &d->h_tab, d->stream) ||
+        const int rc = g->lay.simple ? gj_launch_idct_rgb444_rows(d->d_coef, g->bcx, g->bcy, my0, my1, comp_tq, d_out, g->width, g->height,
+                                                                  g->pitch, d->idct_flavour, coef_dequantized, &d->h_tab, d->stream)
+                                     : gj_launch_idct_rgb_ss_rows(d->d_coef, g->comp, my0, my1, comp_tq, d_out, g->width, g->height, g->pitch,
+                                                                  d->idct_flavour, coef_dequantized, &d->h_tab, d->stream);
+        if ( rc ||
              gj_cuda_event_record(d->ev_stripe[i], d->stream) || gj_cuda_stream_wait_event(d->copy_stream, d->ev_stripe[i]) ||
              gj_cuda_memcpy_d2h_async(h_dst + off, d_out + off, bytes, d->copy_stream) )
             return -1;

@@ -72,7 +72,7 @@ struct gpujpeg_encoder {
     /* host output */
     uint8_t* out; size_t out_size; int out_is_pinned;
     uint8_t* header; size_t header_cap; size_t header_size;   /* file header, composed on the host */
-    /* stripe pipeline of host images (4:4:4 RGB frames of GJ_STRIPE_MIN_BYTES or more): the image arrives in GJ_STRIPES pieces
+    /* stripe pipeline of host images (RGB frames of GJ_STRIPE_MIN_BYTES or more on the fused kernels): the image arrives in GJ_STRIPES pieces
      * on a copy stream, K1 runs on every piece as soon as it is there -- the transform hides behind the PCIe transfer */
     gj_stream_t copy_stream;
     void* ev_begin; void* ev_stripe[GJ_STRIPES];
@@ -346,11 +346,11 @@ static int launch_k1(struct gpujpeg_encoder* e, const uint8_t* d_raw)
     return gj_launch_fdct_rgb_ss(d_raw, g->width, g->height, pitch, e->d_coef, e->d_nzmask, g->comp, &e->h_tab, e->stream);
 }
 
-/* The stripe pipeline applies to what the fused 4:4:4 kernel takes as it comes: no flip, no channel remap. */
+/* The stripe pipeline applies to what the fused RGB kernels take as it comes: no flip, no channel remap. */
 static int stripes_usable(struct gpujpeg_encoder* e)
 {
     const struct gj_geometry* g = &e->geo;
-    if ( e->input_mode != GJ_IN_RGB || !g->lay.simple || e->flipped || e->channel_remap ) return 0;
+    if ( e->input_mode != GJ_IN_RGB || e->flipped || e->channel_remap ) return 0;
     if ( e->stripes == 0 ) {
         const char* v = getenv("GPUJPEG_B200_STRIPES");
         const char* m = getenv("GPUJPEG_B200_STRIPE_MIN_BYTES");
@@ -359,7 +359,7 @@ static int stripes_usable(struct gpujpeg_encoder* e)
         if ( e->stripes < 1 ) e->stripes = 1;
         if ( e->stripes > GJ_STRIPES ) e->stripes = GJ_STRIPES;
     }
-    if ( e->stripes < 2 || g->bcy < 2 * e->stripes || g->raw_size < e->stripe_min_bytes ) return 0;
+    if ( e->stripes < 2 || g->bcy / g->max_vs < 2 * e->stripes || g->raw_size < e->stripe_min_bytes ) return 0;
     if ( !e->copy_stream ) {
         if ( gj_cuda_stream_create(&e->copy_stream) || gj_cuda_event_create(&e->ev_begin) ) {
             e->stripes = 1;
@@ -380,16 +380,21 @@ static int encode_striped(struct gpujpeg_encoder* e, const uint8_t* h_image)
 {
     const struct gj_geometry* g = &e->geo;
     if ( gj_cuda_event_record(e->ev_begin, e->stream) || gj_cuda_stream_wait_event(e->copy_stream, e->ev_begin) ) return -1;
+    const int mcu_h = 8 * g->max_vs;                                  /* image rows per MCU row (4:4:4: one block row) */
+    const int mcu_rows = (g->bcy + g->max_vs - 1) / g->max_vs;
     for ( int i = 0; i < e->stripes; i++ ) {
-        const int by0 = (int)((long long)g->bcy * i / e->stripes), by1 = (int)((long long)g->bcy * (i + 1) / e->stripes);
-        const size_t row0 = (size_t)by0 * 8, row1 = (size_t)by1 * 8 < (size_t)g->height ? (size_t)by1 * 8 : (size_t)g->height;
+        const int my0 = (int)((long long)mcu_rows * i / e->stripes), my1 = (int)((long long)mcu_rows * (i + 1) / e->stripes);
+        const size_t row0 = (size_t)my0 * mcu_h, row1 = (size_t)my1 * mcu_h < (size_t)g->height ? (size_t)my1 * mcu_h : (size_t)g->height;
         const size_t off = row0 * (size_t)g->pitch;
         const size_t bytes = (i + 1 == e->stripes ? g->raw_size : row1 * (size_t)g->pitch) - off;
         if ( gj_cuda_memcpy_h2d_async(e->d_raw + off, h_image + off, bytes, e->copy_stream) ||
-             gj_cuda_event_record(e->ev_stripe[i], e->copy_stream) || gj_cuda_stream_wait_event(e->stream, e->ev_stripe[i]) ||
-             gj_launch_fdct_rgb444_rows(e->d_raw, g->width, g->height, g->pitch, e->d_coef, e->d_nzmask, g->bcx, g->bcy, by0, by1,
-                                        &e->h_tab, e->stream) )
+             gj_cuda_event_record(e->ev_stripe[i], e->copy_stream) || gj_cuda_stream_wait_event(e->stream, e->ev_stripe[i]) )
             return -1;
+        const int rc = g->lay.simple ? gj_launch_fdct_rgb444_rows(e->d_raw, g->width, g->height, g->pitch, e->d_coef, e->d_nzmask, g->bcx,
+                                                                  g->bcy, my0, my1, &e->h_tab, e->stream)
+                                     : gj_launch_fdct_rgb_ss_rows(e->d_raw, g->width, g->height, g->pitch, e->d_coef, e->d_nzmask, g->comp,
+                                                                  my0, my1, &e->h_tab, e->stream);
+        if ( rc ) return -1;
     }
     return 0;
 }

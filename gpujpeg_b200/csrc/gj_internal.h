@@ -294,6 +294,14 @@ int gj_launch_idct_rgb444_rows(const int16_t* d_coef, int bcx, int bcy, int by0,
                                int width, int height, int pitch, int idct_flavour, int coef_dequantized,
                                const struct gj_dev_dec_tables* d_tables, gj_stream_t stream);
 
+/* the same for the chroma-subsampled kernels: MCU rows [my0, my1), an MCU row = 8 * comp[0].vs image rows */
+int gj_launch_fdct_rgb_ss_rows(const uint8_t* d_raw, int width, int height, int pitch, int16_t* d_coef, uint64_t* d_nzmask,
+                               const struct gj_comp_geo comp[3], int my0, int my1, const struct gj_dev_enc_tables* h_tables,
+                               gj_stream_t stream);
+int gj_launch_idct_rgb_ss_rows(const int16_t* d_coef, const struct gj_comp_geo comp[3], int my0, int my1, const int comp_tq[3],
+                               uint8_t* d_raw, int width, int height, int pitch, int idct_flavour, int coef_dequantized,
+                               const struct gj_dev_dec_tables* h_tables, gj_stream_t stream);
+
 /* K2: Huffman-encode every restart segment and assemble the finished scan data
  * [replaces ref: src/gpujpeg_huffman_gpu_encoder.cu:1071-1167 + host loop src/gpujpeg_encoder.c:567-626]
  * d_stream receives [header gap][SOS][scan 0]...[EOI]; d_info[0] = total bytes, d_info[1] = error flag */

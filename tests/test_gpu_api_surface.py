@@ -194,23 +194,25 @@ def test_image_files_through_the_public_api(tmp_path, name, fmt, cs):
         assert [rc, mine.color_space, mine.pixel_format] == [want[0], want[3], want[4]], probe
 
 
-@pytest.mark.parametrize("w,h,stripes", [(1920, 1080, 8), (1119, 561, 5), (640, 136, 8), (3840, 2160, 0)])
-def test_stripe_pipeline_of_host_buffers(monkeypatch, w, h, stripes):
+@pytest.mark.parametrize("w,h,stripes,ss,il", [(1920, 1080, 8, "4:4:4", 0), (1119, 561, 5, "4:4:4", 0), (640, 136, 8, "4:4:4", 0),
+                                               (3840, 2160, 0, "4:4:4", 0), (1119, 561, 7, "4:2:0", 1), (1118, 562, 8, "4:2:0", 0),
+                                               (642, 361, 6, "4:2:2", 1), (640, 300, 4, "4:4:0", 0), (3840, 2160, 0, "4:2:0", 1)])
+def test_stripe_pipeline_of_host_buffers(monkeypatch, w, h, stripes, ss, il):
     """host images of 8 MB or more are copied and transformed stripe by stripe (K1 behind the upload, the download behind K4):
-    the same bytes and pixels as ever -- pinned and pageable buffers, frame heights that do not divide into the stripes, and
-    small frames with the threshold lowered"""
+    the same bytes and pixels as ever -- pinned and pageable buffers, frame heights that do not divide into the stripes,
+    chroma subsampling (stripes of whole MCU rows), and small frames with the threshold lowered"""
     import torch
     import gpujpeg_b200 as g
     if stripes:
         monkeypatch.setenv("GPUJPEG_B200_STRIPES", str(stripes))
         monkeypatch.setenv("GPUJPEG_B200_STRIPE_MIN_BYTES", "1")
     img = o.gen_image("photo", w, h)
-    want = o.encode(img, 80, 12, threads=4)
+    want = o.encode(img, 80, 12, il, threads=4, sampling=g.api.SUBSAMPLING[ss])
     pix = o.decode(want, threads=4)
     e, d = g.Encoder(), g.Decoder()
     pinned = torch.from_numpy(img).pin_memory()
     for src in (img, pinned, img):
-        assert np.array_equal(e.encode(src, 80, 12), want)
+        assert np.array_equal(e.encode(src, 80, 12, il, subsampling=ss), want)
     out = torch.empty((h, w, 3), dtype=torch.uint8).pin_memory()
     d.decode(want, out=out.numpy())
     assert np.array_equal(out.numpy(), pix)
