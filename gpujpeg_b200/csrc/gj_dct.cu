@@ -29,6 +29,7 @@
 
 #include "gj_device.cuh"
 #include "gj_internal.h"
+#include "gj_launch.cuh"
 
 namespace {
 
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(NT)
 k_fdct_rgb444(const uint8_t* __restrict__ raw, int width, int height, size_t pitch, int16_t* __restrict__ coef,
               uint64_t* __restrict__ nzmask, int bcx, int nblk, const __grid_constant__ FdctParams prm)
 {
+    gj_pdl_wait();
     extern __shared__ __align__(16) uint8_t smem[];
     float* s_pl = reinterpret_cast<float*>(smem);
 
@@ -485,6 +487,7 @@ __global__ void __launch_bounds__(NT)
 k_idct_rgb444(const int16_t* __restrict__ coef, int bcx, int nblk, uint8_t* __restrict__ raw, int width, int height,
               size_t pitch, const __grid_constant__ IdctParams prm)
 {
+    gj_pdl_wait();
     __shared__ __align__(16) uint8_t s_pl[3 * K4_PLANE];
 
     const int bx0 = blockIdx.x * TB;
@@ -854,9 +857,9 @@ static int launch_fdct_rgb444(const uint8_t* d_raw, int width, int height, int p
         k_fdct_rgb444_bulk<<<ctas, NT, K1T_SMEM, stream>>>(d_raw, width, height, (size_t)pitch, d_coef, d_nzmask, bcx, bcy, nblk, prm);
     }
     else if ( pick_vec(d_raw, (size_t)pitch) == 4 )
-        k_fdct_rgb444<4><<<grid, NT, K1_SMEM, stream>>>(d_raw, width, height, (size_t)pitch, d_coef, d_nzmask, bcx, nblk, prm);
+        gj_launch_pdl(k_fdct_rgb444<4>, grid, dim3(NT), K1_SMEM, stream, d_raw, width, height, (size_t)pitch, d_coef, d_nzmask, bcx, nblk, prm);
     else
-        k_fdct_rgb444<1><<<grid, NT, K1_SMEM, stream>>>(d_raw, width, height, (size_t)pitch, d_coef, d_nzmask, bcx, nblk, prm);
+        gj_launch_pdl(k_fdct_rgb444<1>, grid, dim3(NT), K1_SMEM, stream, d_raw, width, height, (size_t)pitch, d_coef, d_nzmask, bcx, nblk, prm);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -887,7 +890,7 @@ static int launch_idct_rgb444(const int16_t* d_coef, int bcx, int bcy, int nblk,
     const dim3 grid((bcx + TB - 1) / TB, bcy);
     const int vec = pick_vec(d_raw, (size_t)pitch);
     if ( idct_flavour != 0 && coef_dequantized ) return -1;   // the float flavour needs raw coefficients
-#define GJ_K4(V, F, D) k_idct_rgb444<V, F, D><<<grid, NT, 0, stream>>>(d_coef, bcx, nblk, d_raw, width, height, (size_t)pitch, prm)
+#define GJ_K4(V, F, D) gj_launch_pdl(k_idct_rgb444<V, F, D>, grid, dim3(NT), 0, stream, d_coef, bcx, nblk, d_raw, width, height, (size_t)pitch, prm)
     if ( idct_flavour == 0 && coef_dequantized ) {
         if ( vec == 4 ) GJ_K4(4, 0, false); else GJ_K4(1, 0, false);
     }

@@ -26,6 +26,7 @@
 #include "gj_internal.h"
 
 #define GJ_MK_OTHER_CAP 256 /* markers other than RSTn the device reports back (SOS, EOI, ...) */
+#define GJ_CTA_BYTES0 (64 * 1024)   /* first size of the tile-status area behind the result block: files up to 32 MB */
 #define GJ_MK_WORDS (8 + 4 * GJ_MK_OTHER_CAP)   /* K0 result block: 8 counters/flags + {rank, position, code, clean position} per marker */
 
 #define GJ_STRIPES 8
@@ -72,7 +73,7 @@ struct gpujpeg_decoder {
     uint32_t* d_seg_off; uint32_t* h_seg_off; size_t seg_off_size;   /* streams with segment info: file offset of every segment (h: pinned) */
     int used_segment_info;                          /* the last frame's scans were split by the stream's own tables */
     int ignore_segment_info;                        /* set while a frame whose tables proved wrong is decoded again */
-    unsigned long long* d_cta; size_t d_cta_size;   /* K0 scratch */
+    unsigned long long* d_cta; size_t d_cta_size;   /* K0 scratch: tile status words, kept right behind d_mk (one allocation, one memset) */
     uint32_t* d_mk;                                 /* K0 results (layout in gpujpeg_decoder_decode) */
     uint32_t* d_k3_ctr;                             /* K3 work counters (8 words, zero between launches) */
     uint32_t* h_mk;                                 /* pinned mirror */
@@ -142,7 +143,7 @@ struct gpujpeg_decoder* gpujpeg_decoder_create_with_params(const struct gpujpeg_
     d->req_pixel_format = GPUJPEG_PIXFMT_AUTODETECT;
     d->req_color_space = GPUJPEG_CS_DEFAULT;
     if ( d->device < 0 || gj_cuda_malloc((void**)&d->d_tab, sizeof *d->d_tab) ||
-         gj_cuda_malloc((void**)&d->d_mk, GJ_MK_WORDS * 4) || gj_cuda_malloc((void**)&d->d_k3_ctr, 32) ||
+         gj_cuda_malloc((void**)&d->d_mk, GJ_MK_WORDS * 4 + GJ_CTA_BYTES0) || gj_cuda_malloc((void**)&d->d_k3_ctr, 32) ||
          gj_cuda_memset_async(d->d_k3_ctr, 0, 32, d->stream) || gj_cuda_stream_sync(d->stream) ||
          gj_cuda_malloc_host((void**)&d->h_mk, GJ_MK_WORDS * 4) ) {
         GJ_ERR("Decoder allocation failed: %s\n", gj_cuda_last_error());
@@ -173,7 +174,6 @@ int gpujpeg_decoder_destroy(struct gpujpeg_decoder* d)
     gj_cuda_free(d->d_seg_tab);
     gj_cuda_free(d->d_seg_off);
     if ( d->h_seg_off ) gj_cuda_free_host(d->h_seg_off);
-    gj_cuda_free(d->d_cta);
     gj_cuda_free(d->d_mk);
     gj_cuda_free(d->d_k3_ctr);
     gj_cuda_free_host(d->h_mk);
@@ -212,6 +212,25 @@ static int grow_host(void** p, size_t* have, size_t want)
     *have = 0;
     if ( gj_cuda_malloc_host(p, want) ) return -1;
     *have = want;
+    return 0;
+}
+
+/* K0's result block and its tile-status words as one allocation (nothing in it outlives a frame) */
+static int grow_mk_cta(struct gpujpeg_decoder* d, size_t cta_bytes)
+{
+    if ( d->d_cta && cta_bytes <= d->d_cta_size ) return 0;
+    if ( !d->d_cta && cta_bytes <= GJ_CTA_BYTES0 ) {
+        d->d_cta = (unsigned long long*)(d->d_mk + GJ_MK_WORDS);
+        d->d_cta_size = GJ_CTA_BYTES0;
+        return 0;
+    }
+    const size_t want = cta_bytes + cta_bytes / 4;
+    uint32_t* fresh = NULL;
+    if ( gj_cuda_stream_sync(d->stream) || gj_cuda_malloc((void**)&fresh, GJ_MK_WORDS * 4 + want) ) return -1;
+    gj_cuda_free(d->d_mk);
+    d->d_mk = fresh;
+    d->d_cta = (unsigned long long*)(fresh + GJ_MK_WORDS);
+    d->d_cta_size = want;
     return 0;
 }
 
@@ -679,7 +698,7 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
          grow_dev((void**)&d->d_list_code, &d->d_list_code_size, (size_t)list_cap) ||
          grow_dev((void**)&d->d_list_cpos, &d->d_list_cpos_size, (size_t)list_cap * 4) ||
          grow_dev((void**)&d->d_clean, &d->d_clean_size, image_size - ecs_begin + 64) ||
-         grow_dev((void**)&d->d_cta, &d->d_cta_size, n_cta * 8) ) {
+         grow_mk_cta(d, n_cta * 8) ) {
         GJ_ERR("Decoder device allocation failed: %s\n", gj_cuda_last_error());
         return GPUJPEG_ERROR;
     }

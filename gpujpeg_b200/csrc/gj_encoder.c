@@ -66,7 +66,9 @@ struct gpujpeg_encoder {
     int pre_len[GJ_MAX_COMP], pre_off[GJ_MAX_COMP];
     int with_segment_info;                     /* param.segment_info && restart_interval > 0 [ref: src/gpujpeg_writer.c:553] */
     uint64_t* d_seg_pos; uint64_t* h_seg_pos; size_t seg_pos_size;   /* segment info: stream offset of every segment (pinned copy) */
-    uint64_t* d_info;
+    uint64_t* d_info;                          /* two blocks of 4 words: K2's tail clears the one the next launch uses */
+    uint64_t* d_info_cur;                      /* the block the last K2 launch reported into */
+    int info_parity, info_clean;
     uint64_t* h_info;                          /* pinned */
 
     /* host output */
@@ -399,6 +401,20 @@ static int encode_striped(struct gpujpeg_encoder* e, const uint8_t* h_image)
     return 0;
 }
 
+static void fill_huff_args(const struct gpujpeg_encoder* e, struct gj_huff_enc_args* ha);
+/* K2 on the frame K1 left in place.  The 32-byte result block alternates between two halves of d_info: the tail kernel of
+ * one launch clears the half the next launch accumulates into, so no memset stands between K1 and K2. */
+static int launch_k2(struct gpujpeg_encoder* e)
+{
+    struct gj_huff_enc_args ha;
+    fill_huff_args(e, &ha);
+    const int rc = gj_launch_huffman_encode(&ha, e->stream);
+    e->d_info_cur = ha.d_info;
+    e->info_parity ^= 1;
+    e->info_clean = rc == 0;   /* after a failed launch nothing is known about either half: the next launch clears its own */
+    return rc;
+}
+
 static void fill_huff_args(const struct gpujpeg_encoder* e, struct gj_huff_enc_args* ha)
 {
     const struct gj_geometry* g = &e->geo;
@@ -421,7 +437,9 @@ static void fill_huff_args(const struct gpujpeg_encoder* e, struct gj_huff_enc_a
         ha->pre_off[s] = e->pre_off[s];
     }
     ha->d_seg_pos = e->with_segment_info ? e->d_seg_pos : NULL;
-    ha->d_info = e->d_info;
+    ha->d_info = e->d_info + 4 * e->info_parity;
+    ha->d_info_next = e->d_info + 4 * (e->info_parity ^ 1);
+    ha->info_is_zero = e->info_clean;
     ha->d_tables = e->d_tab;
 }
 
@@ -784,9 +802,7 @@ int gpujpeg_encoder_encode(struct gpujpeg_encoder* e, const struct gpujpeg_param
         gj_timer_stop(&e->t_pre, e->stream);
         gj_timer_start(&e->t_huff, e->stream);
     }
-    struct gj_huff_enc_args ha;
-    fill_huff_args(e, &ha);
-    if ( gj_launch_huffman_encode(&ha, e->stream) ) {
+    if ( launch_k2(e) ) {
         GJ_ERR("Huffman encoder launch failed: %s\n", gj_cuda_last_error());
         return GPUJPEG_ERROR;
     }
@@ -796,7 +812,7 @@ int gpujpeg_encoder_encode(struct gpujpeg_encoder* e, const struct gpujpeg_param
         gj_timer_start(&e->t_from, e->stream);
     }
     /* the only two synchronisation points of a frame: size, then payload */
-    if ( gj_cuda_memcpy_d2h_async(e->h_info, e->d_info, 32, e->stream) || gj_cuda_stream_sync(e->stream) ) {
+    if ( gj_cuda_memcpy_d2h_async(e->h_info, e->d_info_cur, 32, e->stream) || gj_cuda_stream_sync(e->stream) ) {
         GJ_ERR("Encoder failed: %s\n", gj_cuda_last_error());
         return GPUJPEG_ERROR;
     }
@@ -812,8 +828,7 @@ int gpujpeg_encoder_encode(struct gpujpeg_encoder* e, const struct gpujpeg_param
             GJ_ERR("Encoder device allocation failed (%zu bytes): %s\n", (size_t)g->seg_count * e->slot_stride, gj_cuda_last_error());
             return GPUJPEG_ERROR;
         }
-        fill_huff_args(e, &ha);
-        if ( gj_launch_huffman_encode(&ha, e->stream) || gj_cuda_memcpy_d2h_async(e->h_info, e->d_info, 32, e->stream) ||
+        if ( launch_k2(e) || gj_cuda_memcpy_d2h_async(e->h_info, e->d_info_cur, 32, e->stream) ||
              gj_cuda_stream_sync(e->stream) ) {
             GJ_ERR("Encoder failed: %s\n", gj_cuda_last_error());
             return GPUJPEG_ERROR;
@@ -1012,11 +1027,7 @@ GPUJPEG_API int gpujpegx_encoder_run_resident(struct gpujpeg_encoder* e, const u
     if ( !d_raw ) d_raw = e->d_raw;
     if ( !d_raw ) return -1;
     if ( (stage_mask & 1) && launch_k1(e, d_raw) ) return -1;
-    if ( stage_mask & 2 ) {
-        struct gj_huff_enc_args ha;
-        fill_huff_args(e, &ha);
-        if ( gj_launch_huffman_encode(&ha, e->stream) ) return -1;
-    }
+    if ( (stage_mask & 2) && launch_k2(e) ) return -1;
     return 0;
 }
 

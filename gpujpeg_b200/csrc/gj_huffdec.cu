@@ -43,6 +43,7 @@
 
 #include "gj_device.cuh"
 #include "gj_internal.h"
+#include "gj_launch.cuh"
 
 namespace {
 
@@ -762,6 +763,7 @@ template <bool DEQ>
 __global__ void __launch_bounds__(SD_THREADS)
 k_huff_decode_sync(const __grid_constant__ SdParams P)
 {
+    gj_pdl_wait();
     extern __shared__ __align__(16) uint8_t sm[];
     const gj_scan_layout& L = P.lay;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1004,8 +1006,8 @@ extern "C" int gj_launch_huffman_decode_sync(const struct gj_huff_dec_args* a, g
     }
     if ( cta == 0 ) return 0;
     if ( a->dequantize )
-        k_huff_decode_sync<true><<<cta, nw * 32, smem, stream>>>(P);
+        gj_launch_pdl(k_huff_decode_sync<true>, dim3(cta), dim3(nw * 32), smem, stream, P);
     else
-        k_huff_decode_sync<false><<<cta, nw * 32, smem, stream>>>(P);
+        gj_launch_pdl(k_huff_decode_sync<false>, dim3(cta), dim3(nw * 32), smem, stream, P);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

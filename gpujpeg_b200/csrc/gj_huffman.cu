@@ -31,6 +31,7 @@
 
 #include "gj_device.cuh"
 #include "gj_internal.h"
+#include "gj_launch.cuh"
 
 namespace {
 
@@ -373,6 +374,7 @@ k_huff_encode_packed(const int16_t* __restrict__ coef, const uint64_t* __restric
                      const gj_dev_enc_tables* __restrict__ tables, uint64_t* __restrict__ info,
                      unsigned long long* __restrict__ place_status, int n_status)
 {
+    gj_pdl_wait();
     if ( threadIdx.x == 0 && (int)blockIdx.x < n_status ) place_status[blockIdx.x] = 0ull;   // for k_huff_place, the next launch
     const uint32_t slot_cap = (uint32_t)slot_stride;
     extern __shared__ __align__(16) uint32_t he_smem[];
@@ -621,8 +623,9 @@ k_huff_place(const uint8_t* __restrict__ tmp, size_t slot_stride, const uint32_t
              const __grid_constant__ ScanSegs segs, const uint8_t* __restrict__ sos, const __grid_constant__ ScanPrefix pre,
              uint32_t header_size, uint64_t stream_cap, uint8_t* __restrict__ stream,
              volatile unsigned long long* status /* zeroed by the encoder kernel */, uint64_t* __restrict__ seg_pos /* or NULL */,
-             uint64_t* __restrict__ info)
+             uint64_t* __restrict__ info, uint64_t* __restrict__ info_next /* zeroed for the next launch, or NULL */)
 {
+    gj_pdl_wait();
     __shared__ uint32_t s_excl[CP_SEGS];
     __shared__ unsigned long long s_part[8];
     __shared__ uint32_t s_own;
@@ -687,6 +690,7 @@ k_huff_place(const uint8_t* __restrict__ tmp, size_t slot_stride, const uint32_t
         const uint64_t total = (uint64_t)header_size + base + s_own + 2;   // + EOI
         info[0] = total;
         info[1] = (info[1] & 2ull) | (total > stream_cap ? 1ull : 0ull);   // bit 1: a segment slot overflowed (set by the encoder)
+        if ( info_next ) info_next[0] = info_next[1] = info_next[2] = info_next[3] = 0ull;
     }
     if ( info[1] & 2ull ) return;   // slots too small: their contents are truncated, the host encodes again
     /* what precedes the data of a scan that starts in this tile ([APP13 segment-info headers] SOS header; with segment
@@ -1039,7 +1043,9 @@ __global__ void k_coef_to_natural(const int16_t* __restrict__ in, int16_t* __res
 extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_stream_t stream)
 {
     const int seg_count = a->lay.scan_seg_begin[GJ_MAX_COMP];
-    if ( cudaMemsetAsync(a->d_info, 0, 32, stream) != cudaSuccess ) return -1;
+    /* the info block is zero when this launch starts: cleared here, or -- d_info_next given -- by the k_huff_place of the
+     * previous launch (the encoder alternates between two blocks: one memset less in front of every frame) */
+    if ( !a->info_is_zero && cudaMemsetAsync(a->d_info, 0, 32, stream) != cudaSuccess ) return -1;
     ScanSegs segs;
     for ( int k = 0; k <= GJ_MAX_COMP; k++ )
         segs.begin[k] = a->lay.scan_seg_begin[k];
@@ -1063,9 +1069,9 @@ extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_str
         }
         /* one thread per block of the CTA's segments: 288 blocks -> 9 warps, all busy in phase A */
         const int hp_threads = max(HE_WARPS * 32, (HE_WARPS * a->seg_mcu * a->lay.bpm + 31) / 32 * 32);
-        k_huff_encode_packed<<<(seg_count + HE_WARPS - 1) / HE_WARPS, hp_threads, HP_SMEM, stream>>>(
-            a->d_coef, a->d_nzmask, a->lay, a->seg_mcu, seg_count, a->d_tmp, a->slot_stride, a->d_seg_bytes, a->d_spill,
-            a->d_tables, a->d_info, place_status, n_status);
+        gj_launch_pdl(k_huff_encode_packed, dim3((seg_count + HE_WARPS - 1) / HE_WARPS), dim3(hp_threads), HP_SMEM, stream,
+                      a->d_coef, a->d_nzmask, a->lay, a->seg_mcu, seg_count, a->d_tmp, a->slot_stride, a->d_seg_bytes, a->d_spill,
+                      a->d_tables, a->d_info, place_status, n_status);
     }
     else {
         k_huff_encode<<<(seg_count + HE_WARPS - 1) / HE_WARPS, HE_WARPS * 32, HE_SMEM, stream>>>(
@@ -1077,8 +1083,9 @@ extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_str
         pre.len[k] = a->pre_len[k];
         pre.off[k] = a->pre_off[k];
     }
-    k_huff_place<<<n_status, 256, 0, stream>>>(a->d_tmp, a->slot_stride, a->d_seg_bytes, seg_count, segs, a->d_sos, pre, a->header_size,
-                                               (uint64_t)a->stream_cap, a->d_stream, place_status, a->d_seg_pos, a->d_info);
+    gj_launch_pdl(k_huff_place, dim3(n_status), dim3(256), 0, stream, (const uint8_t*)a->d_tmp, a->slot_stride, (const uint32_t*)a->d_seg_bytes,
+                  seg_count, segs, a->d_sos, pre, a->header_size, (uint64_t)a->stream_cap, a->d_stream,
+                  (volatile unsigned long long*)place_status, a->d_seg_pos, a->d_info, a->d_info_next);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -324,6 +324,8 @@ struct gj_huff_enc_args {
     int pre_len[GJ_MAX_COMP], pre_off[GJ_MAX_COMP];
     uint64_t* d_seg_pos;    /* [seg_count] or NULL: receives the stream offset of every segment's first byte (segment info) */
     uint64_t* d_info;       /* [4]: total, error, reserved */
+    uint64_t* d_info_next;  /* [4] or NULL: cleared by this launch for the next one */
+    int info_is_zero;       /* d_info has been cleared by the previous launch */
     const struct gj_dev_enc_tables* d_tables;
 };
 int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_stream_t stream);

@@ -29,6 +29,7 @@
 #include <stdint.h>
 
 #include "gj_internal.h"
+#include "gj_launch.cuh"
 
 namespace {
 
@@ -101,6 +102,7 @@ k_marker_scan_write(const uint8_t* __restrict__ file, size_t begin, size_t end, 
                     uint8_t* __restrict__ clean, uint32_t* __restrict__ result /*[0]=markers, [1]=other count, [2]=overflow, [5]=clean bytes*/,
                     uint32_t* __restrict__ other /*{rank,pos,code,cpos}*/, uint32_t other_cap)
 {
+    gj_pdl_wait();
     __shared__ uint32_t s_warp[MK_THREADS / 32];
     __shared__ __align__(16) uint8_t s_bytes[MK_TILE + 8];
     __shared__ uint32_t s_total;
@@ -259,10 +261,18 @@ extern "C" int gj_launch_marker_scan(const uint8_t* d_file, size_t begin, size_t
     const size_t base = begin & ~static_cast<size_t>(15);
     const int n_cta = (int)((end - base + MK_TILE - 1) / MK_TILE);
     if ( end - base >= ((size_t)1 << 31) ) return -1;   // the tile status holds 31-bit counts
-    if ( cudaMemsetAsync(d_result, 0, 8 * sizeof(uint32_t), stream) != cudaSuccess ||
-         cudaMemsetAsync(d_cta, 0, (size_t)n_cta * sizeof(unsigned long long), stream) != cudaSuccess )
+    /* counters and tile status start from zero: one memset when the caller keeps the status words right behind the result
+     * block (counters + list of other markers), as the decoder does */
+    const uint8_t* const result_end = reinterpret_cast<const uint8_t*>(d_other + 4 * (size_t)other_cap);
+    if ( d_other == d_result + 8 && reinterpret_cast<const uint8_t*>(d_cta) == result_end ) {
+        if ( cudaMemsetAsync(d_result, 0, (size_t)(result_end - reinterpret_cast<const uint8_t*>(d_result)) + (size_t)n_cta * sizeof(unsigned long long),
+                             stream) != cudaSuccess )
+            return -1;
+    }
+    else if ( cudaMemsetAsync(d_result, 0, 8 * sizeof(uint32_t), stream) != cudaSuccess ||
+              cudaMemsetAsync(d_cta, 0, (size_t)n_cta * sizeof(unsigned long long), stream) != cudaSuccess )
         return -1;
-    k_marker_scan_write<<<n_cta, MK_THREADS, 0, stream>>>(d_file, begin, end, base, d_cta, d_list_pos, d_list_code, d_list_cpos, list_cap,
-                                                          d_clean, d_result, d_other, other_cap);
+    gj_launch_pdl(k_marker_scan_write, dim3(n_cta), dim3(MK_THREADS), 0, stream, d_file, begin, end, base, (volatile unsigned long long*)d_cta,
+                  d_list_pos, d_list_code, d_list_cpos, list_cap, d_clean, d_result, d_other, other_cap);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
