@@ -102,7 +102,6 @@ __global__ void __launch_bounds__(NT)
 k_fdct_rgb444(const uint8_t* __restrict__ raw, int width, int height, size_t pitch, int16_t* __restrict__ coef,
               uint64_t* __restrict__ nzmask, int bcx, int nblk, const __grid_constant__ FdctParams prm)
 {
-    gj_pdl_trigger();
     gj_pdl_wait();
     extern __shared__ __align__(16) uint8_t smem[];
     float* s_pl = reinterpret_cast<float*>(smem);
@@ -488,7 +487,6 @@ __global__ void __launch_bounds__(NT)
 k_idct_rgb444(const int16_t* __restrict__ coef, int bcx, int nblk, uint8_t* __restrict__ raw, int width, int height,
               size_t pitch, const __grid_constant__ IdctParams prm)
 {
-    gj_pdl_trigger();
     gj_pdl_wait();
     __shared__ __align__(16) uint8_t s_pl[3 * K4_PLANE];
 

@@ -763,7 +763,7 @@ template <bool DEQ>
 __global__ void __launch_bounds__(SD_THREADS)
 k_huff_decode_sync(const __grid_constant__ SdParams P)
 {
-    gj_pdl_trigger();
+    gj_pdl_wait();
     extern __shared__ __align__(16) uint8_t sm[];
     const gj_scan_layout& L = P.lay;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -836,7 +836,6 @@ k_huff_decode_sync(const __grid_constant__ SdParams P)
     for ( int i = threadIdx.x; i < ncomp * 64; i += blockDim.x )
         s_q[i] = P.tables->qinv_zz[P.scan_tq[scan][i >> 6]][i & 63];
     __syncthreads();
-    if ( round == 0 ) gj_pdl_wait();   // the tables are constants of the coder; the stream and the counters belong to the frame
 
     const int mode = P.staged[scan] ? M_STAGED : M_SPLIT;
     if ( L.interleaved ) {

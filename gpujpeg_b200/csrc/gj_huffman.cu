@@ -374,7 +374,8 @@ k_huff_encode_packed(const int16_t* __restrict__ coef, const uint64_t* __restric
                      const gj_dev_enc_tables* __restrict__ tables, uint64_t* __restrict__ info,
                      unsigned long long* __restrict__ place_status, int n_status)
 {
-    gj_pdl_trigger();
+    gj_pdl_wait();
+    if ( threadIdx.x == 0 && (int)blockIdx.x < n_status ) place_status[blockIdx.x] = 0ull;   // for k_huff_place, the next launch
     const uint32_t slot_cap = (uint32_t)slot_stride;
     extern __shared__ __align__(16) uint32_t he_smem[];
     uint32_t (*s_ac)[256] = reinterpret_cast<uint32_t (*)[256]>(he_smem);
@@ -388,8 +389,6 @@ k_huff_encode_packed(const int16_t* __restrict__ coef, const uint64_t* __restric
         s_ac[i >> 8][i & 255] = tables->lut[i >> 8].ac[i & 255];
     if ( threadIdx.x < 32 ) s_dc[threadIdx.x >> 4][threadIdx.x & 15] = tables->lut[threadIdx.x >> 4].dc[threadIdx.x & 15];
     __syncthreads();
-    gj_pdl_wait();   // the tables above are constants of the coder; everything below belongs to the frame
-    if ( threadIdx.x == 0 && (int)blockIdx.x < n_status ) place_status[blockIdx.x] = 0ull;   // for k_huff_place, the next launch
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g0 = blockIdx.x * HE_WARPS;
@@ -626,7 +625,6 @@ k_huff_place(const uint8_t* __restrict__ tmp, size_t slot_stride, const uint32_t
              volatile unsigned long long* status /* zeroed by the encoder kernel */, uint64_t* __restrict__ seg_pos /* or NULL */,
              uint64_t* __restrict__ info, uint64_t* __restrict__ info_next /* zeroed for the next launch, or NULL */)
 {
-    gj_pdl_trigger();
     gj_pdl_wait();
     __shared__ uint32_t s_excl[CP_SEGS];
     __shared__ unsigned long long s_part[8];

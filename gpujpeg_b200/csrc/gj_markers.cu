@@ -102,7 +102,6 @@ k_marker_scan_write(const uint8_t* __restrict__ file, size_t begin, size_t end, 
                     uint8_t* __restrict__ clean, uint32_t* __restrict__ result /*[0]=markers, [1]=other count, [2]=overflow, [5]=clean bytes*/,
                     uint32_t* __restrict__ other /*{rank,pos,code,cpos}*/, uint32_t other_cap)
 {
-    gj_pdl_trigger();
     gj_pdl_wait();
     __shared__ uint32_t s_warp[MK_THREADS / 32];
     __shared__ __align__(16) uint8_t s_bytes[MK_TILE + 8];
