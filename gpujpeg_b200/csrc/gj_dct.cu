@@ -347,6 +347,7 @@ __global__ void __launch_bounds__(TB * VS + 2 * TB / HS)
 k_fdct_rgb_ss(const uint8_t* __restrict__ raw, int width, int height, size_t pitch, int16_t* __restrict__ coef,
               uint64_t* __restrict__ nzmask, const __grid_constant__ SsGrid grid, const __grid_constant__ FdctParams prm)
 {
+    gj_pdl_wait();
     constexpr int NTS = TB * VS + 2 * TB / HS;      // threads = blocks per strip
     constexpr int CB = TB / HS;                      // chrominance blocks per component per strip
     constexpr int ITERS = (GROUPS + NTS - 1) / NTS;
@@ -588,6 +589,7 @@ __global__ void __launch_bounds__(TB * VS + 2 * TB / HS)
 k_idct_rgb_ss(const int16_t* __restrict__ coef, const __grid_constant__ SsGrid grid, uint8_t* __restrict__ raw, int width,
               int height, size_t pitch, const __grid_constant__ IdctParams prm)
 {
+    gj_pdl_wait();
     constexpr int NTS = TB * VS + 2 * TB / HS;
     constexpr int CB = TB / HS;
     constexpr int CW = STRIP_PX / HS;                 // chrominance samples per strip row
@@ -968,9 +970,9 @@ extern "C" int gj_launch_fdct_rgb_ss_rows(const uint8_t* d_raw, int width, int h
             __atomic_store_n(&attr_done[dev][H * 2 + V - 3], 1, __ATOMIC_RELEASE);                                           \
         }                                                                                                                    \
         if ( vec == 4 )                                                                                                      \
-            k_fdct_rgb_ss<H, V, 4><<<grid, nt, sm, stream>>>(d_raw, width, height, (size_t)pitch, d_coef, d_nzmask, sg, prm); \
+            gj_launch_pdl(k_fdct_rgb_ss<H, V, 4>, grid, dim3(nt), sm, stream, d_raw, width, height, (size_t)pitch, d_coef, d_nzmask, sg, prm); \
         else                                                                                                                 \
-            k_fdct_rgb_ss<H, V, 1><<<grid, nt, sm, stream>>>(d_raw, width, height, (size_t)pitch, d_coef, d_nzmask, sg, prm); \
+            gj_launch_pdl(k_fdct_rgb_ss<H, V, 1>, grid, dim3(nt), sm, stream, d_raw, width, height, (size_t)pitch, d_coef, d_nzmask, sg, prm); \
     } while ( 0 )
     if ( hs == 2 && vs == 2 ) GJ_K1SS(2, 2);
     else if ( hs == 2 && vs == 1 ) GJ_K1SS(2, 1);
@@ -1006,7 +1008,7 @@ extern "C" int gj_launch_idct_rgb_ss_rows(const int16_t* d_coef, const struct gj
     const dim3 grid((comp[0].bcx + TB - 1) / TB, my1 - my0);
     const int vec = pick_vec(d_raw, (size_t)pitch);
 #define GJ_K4SS2(H, V, VE, F, D) \
-    k_idct_rgb_ss<H, V, VE, F, D><<<grid, TB * V + 2 * TB / H, 0, stream>>>(d_coef, sg, d_raw, width, height, (size_t)pitch, prm)
+    gj_launch_pdl(k_idct_rgb_ss<H, V, VE, F, D>, grid, dim3(TB * V + 2 * TB / H), 0, stream, d_coef, sg, d_raw, width, height, (size_t)pitch, prm)
 #define GJ_K4SS(H, V)                                                                  \
     do {                                                                               \
         if ( idct_flavour == 0 && coef_dequantized ) {                                 \

@@ -150,6 +150,7 @@ k_huff_encode(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzm
               uint32_t* __restrict__ seg_bytes, uint32_t* __restrict__ spill_all, const gj_dev_enc_tables* __restrict__ tables,
               uint64_t* __restrict__ info, unsigned long long* __restrict__ place_status, int n_status)
 {
+    gj_pdl_wait();
     if ( threadIdx.x == 0 && (int)blockIdx.x < n_status ) place_status[blockIdx.x] = 0ull;   // for k_huff_place, the next launch
     const uint32_t slot_cap = (uint32_t)slot_stride;
     extern __shared__ __align__(16) uint32_t he_smem[];
@@ -870,6 +871,7 @@ k_huff_decode(const uint8_t* __restrict__ file, const uint8_t* __restrict__ file
               int seg_count, int seg_mcu, const __grid_constant__ gj_huff_dec_args a, const __grid_constant__ SegOwners own,
               int16_t* __restrict__ coef, const gj_dev_dec_tables* __restrict__ tables)
 {
+    gj_pdl_wait();
     __shared__ DecTabs s_tab;
     __shared__ uint16_t s_q[4][64];
     __shared__ __align__(16) uint32_t s_blk[HD_THREADS * 32];   // one private 8x8 block (128 B) per owner lane
@@ -1074,9 +1076,9 @@ extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_str
                       a->d_tables, a->d_info, place_status, n_status);
     }
     else {
-        k_huff_encode<<<(seg_count + HE_WARPS - 1) / HE_WARPS, HE_WARPS * 32, HE_SMEM, stream>>>(
-            a->d_coef, a->d_nzmask, a->lay, a->seg_mcu, seg_count, a->d_tmp, a->slot_stride, a->d_seg_bytes, a->d_spill,
-            a->d_tables, a->d_info, place_status, n_status);
+        gj_launch_pdl(k_huff_encode, dim3((seg_count + HE_WARPS - 1) / HE_WARPS), dim3(HE_WARPS * 32), HE_SMEM, stream,
+                      a->d_coef, a->d_nzmask, a->lay, a->seg_mcu, seg_count, a->d_tmp, a->slot_stride, a->d_seg_bytes, a->d_spill,
+                      a->d_tables, a->d_info, place_status, n_status);
     }
     ScanPrefix pre;
     for ( int k = 0; k < GJ_MAX_COMP; k++ ) {
@@ -1116,11 +1118,11 @@ extern "C" int gj_launch_huffman_decode(const struct gj_huff_dec_args* a, gj_str
     const int warps = own.warps0 + (a->seg_count - own.segs0 + own.spw1 - 1) / own.spw1;
     const dim3 grid((warps + HD_THREADS / 32 - 1) / (HD_THREADS / 32));
     if ( a->dequantize )
-        k_huff_decode<true><<<grid, HD_THREADS, 0, stream>>>(a->d_file, a->d_file + a->file_size, a->d_seg_off, a->seg_count,
-                                                             a->seg_mcu, *a, own, a->d_coef, a->d_tables);
+        gj_launch_pdl(k_huff_decode<true>, dim3(grid), dim3(HD_THREADS), 0, stream, a->d_file, a->d_file + a->file_size, a->d_seg_off,
+                      a->seg_count, a->seg_mcu, *a, own, a->d_coef, a->d_tables);
     else
-        k_huff_decode<false><<<grid, HD_THREADS, 0, stream>>>(a->d_file, a->d_file + a->file_size, a->d_seg_off, a->seg_count,
-                                                              a->seg_mcu, *a, own, a->d_coef, a->d_tables);
+        gj_launch_pdl(k_huff_decode<false>, dim3(grid), dim3(HD_THREADS), 0, stream, a->d_file, a->d_file + a->file_size, a->d_seg_off,
+                      a->seg_count, a->seg_mcu, *a, own, a->d_coef, a->d_tables);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
