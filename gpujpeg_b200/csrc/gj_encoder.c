@@ -79,6 +79,7 @@ struct gpujpeg_encoder {
     gj_stream_t copy_stream;
     void* ev_begin; void* ev_stripe[GJ_STRIPES];
     int stripes;                               /* GPUJPEG_B200_STRIPES (1 = off), default GJ_STRIPES */
+    int k2_parts;                              /* GPUJPEG_B200_STRIPES_K2 (0 = K2 behind the last stripe only); -1 = not read yet */
     size_t stripe_min_bytes;                   /* GPUJPEG_B200_STRIPE_MIN_BYTES (tests), default GJ_STRIPE_MIN_BYTES */
     struct gj_header_extras extras;            /* enc_metadata (orientation), enc_exif_tag (user tags, owned) */
     int extras_dirty;                          /* an option changed what the header carries */
@@ -138,6 +139,7 @@ struct gpujpeg_encoder* gpujpeg_encoder_create(cudaStream_t stream)
     e->device = gj_cuda_get_device();
     e->quality = -1;
     e->header_type = GPUJPEG_HEADER_DEFAULT;
+    e->k2_parts = -1;
     if ( e->device < 0 ) {
         GJ_ERR("Cannot get CUDA device: %s\n", gj_cuda_last_error());
         free(e);
@@ -348,6 +350,8 @@ static int launch_k1(struct gpujpeg_encoder* e, const uint8_t* d_raw)
     return gj_launch_fdct_rgb_ss(d_raw, g->width, g->height, pitch, e->d_coef, e->d_nzmask, g->comp, &e->h_tab, e->stream);
 }
 
+static void fill_huff_args(const struct gpujpeg_encoder* e, struct gj_huff_enc_args* ha);
+
 /* The stripe pipeline applies to what the fused RGB kernels take as it comes: no flip, no channel remap. */
 static int stripes_usable(struct gpujpeg_encoder* e)
 {
@@ -378,10 +382,20 @@ static int stripes_usable(struct gpujpeg_encoder* e)
 
 /* H2D of the host image in stripes of whole block rows on the copy stream; K1 of a stripe on the coder's stream as soon as the
  * stripe has arrived.  The copy stream starts behind everything the coder's stream holds (the previous frame's K1 reads d_raw). */
-static int encode_striped(struct gpujpeg_encoder* e, const uint8_t* h_image)
+static int encode_striped(struct gpujpeg_encoder* e, const uint8_t* h_image, int* k2_done)
 {
     const struct gj_geometry* g = &e->geo;
     if ( gj_cuda_event_record(e->ev_begin, e->stream) || gj_cuda_stream_wait_event(e->copy_stream, e->ev_begin) ) return -1;
+    /* K2 as well, stripe by stripe, where a stripe's restart segments can be told from its rows (4:4:4: MCU = block position) and
+     * are short enough for the packed kernel: the segments that lie completely inside the rows transformed so far */
+    struct gj_huff_enc_args ha;
+    fill_huff_args(e, &ha);
+    if ( e->k2_parts < 0 ) {
+        const char* v = getenv("GPUJPEG_B200_STRIPES_K2");
+        e->k2_parts = !(v && v[0] == '0');
+    }
+    const int parts = e->k2_parts && gj_huffman_encode_parts_eligible(&ha);
+    int segs_done[GJ_MAX_COMP] = {0, 0, 0, 0};
     const int mcu_h = 8 * g->max_vs;                                  /* image rows per MCU row (4:4:4: one block row) */
     const int mcu_rows = (g->bcy + g->max_vs - 1) / g->max_vs;
     for ( int i = 0; i < e->stripes; i++ ) {
@@ -397,11 +411,33 @@ static int encode_striped(struct gpujpeg_encoder* e, const uint8_t* h_image)
                                      : gj_launch_fdct_rgb_ss_rows(e->d_raw, g->width, g->height, g->pitch, e->d_coef, e->d_nzmask, g->comp,
                                                                   my0, my1, &e->h_tab, e->stream);
         if ( rc ) return -1;
+        if ( parts ) {
+            int lo[GJ_MAX_COMP] = {0, 0, 0, 0}, n[GJ_MAX_COMP] = {0, 0, 0, 0};
+            for ( int k = 0; k < g->scan_count; k++ ) {
+                const int segs = g->lay.scan_seg_begin[k + 1] - g->lay.scan_seg_begin[k];
+                long long hi = i + 1 == e->stripes ? segs : (long long)my1 * g->bcx / g->seg_mcu;   /* whole segments in rows [0, my1) */
+                if ( hi > segs ) hi = segs;
+                lo[k] = segs_done[k];
+                n[k] = (int)hi - segs_done[k];
+                segs_done[k] = (int)hi;
+            }
+            if ( gj_launch_huffman_encode_part(&ha, i == 0, lo, n, e->stream) ) {
+                e->info_clean = 0;
+                return -1;
+            }
+        }
+    }
+    if ( parts ) {
+        const int rc = gj_launch_huffman_place(&ha, e->stream);
+        e->d_info_cur = ha.d_info;
+        e->info_parity ^= 1;
+        e->info_clean = rc == 0;
+        if ( rc ) return -1;
+        *k2_done = 1;
     }
     return 0;
 }
 
-static void fill_huff_args(const struct gpujpeg_encoder* e, struct gj_huff_enc_args* ha);
 /* K2 on the frame K1 left in place.  The 32-byte result block alternates between two halves of d_info: the tail kernel of
  * one launch clears the half the next launch accumulates into, so no memset stands between K1 and K2. */
 static int launch_k2(struct gpujpeg_encoder* e)
@@ -737,7 +773,7 @@ int gpujpeg_encoder_encode(struct gpujpeg_encoder* e, const struct gpujpeg_param
 
     /* input [ref: src/gpujpeg_encoder.c:402-476] */
     const uint8_t* d_raw;
-    int k1_done = 0;
+    int k1_done = 0, k2_done = 0;   /* the stripe pipeline has launched them already */
     if ( input->type == GPUJPEG_ENCODER_INPUT_IMAGE ) {
         /* the reference's unit test passes a device pointer as a host image and expects it to work
          * [ref: test/unit/run_tests.c:40-79]; cudaMemcpyDefault semantics give the same result */
@@ -747,7 +783,7 @@ int gpujpeg_encoder_encode(struct gpujpeg_encoder* e, const struct gpujpeg_param
         }
         const int on_device = gj_cuda_pointer_is_device(input->image);
         if ( !on_device && !stats && stripes_usable(e) ) {
-            if ( encode_striped(e, input->image) ) {
+            if ( encode_striped(e, input->image, &k2_done) ) {
                 GJ_ERR("Encoder raw data copy / forward DCT failed: %s\n", gj_cuda_last_error());
                 return GPUJPEG_ERROR;
             }
@@ -802,7 +838,7 @@ int gpujpeg_encoder_encode(struct gpujpeg_encoder* e, const struct gpujpeg_param
         gj_timer_stop(&e->t_pre, e->stream);
         gj_timer_start(&e->t_huff, e->stream);
     }
-    if ( launch_k2(e) ) {
+    if ( !k2_done && launch_k2(e) ) {
         GJ_ERR("Huffman encoder launch failed: %s\n", gj_cuda_last_error());
         return GPUJPEG_ERROR;
     }

@@ -368,15 +368,34 @@ constexpr int HP_THREADS_MAX = HE_WARPS * HP_MAXBLK;   // one thread per block o
 static_assert(HE_WARPS * HE_WORDS >= HP_THREADS_MAX * HE_HEAD, "heads must fit into the stream buffers");
 constexpr int HP_SMEM = (2 * 256 + 2 * 16 + HE_WARPS * HE_WORDS + HE_WARPS * HP_MAXBLK * HE_PRIV + HE_WARPS * HP_MAXBLK) * 4;
 
+/* The segments one launch encodes: up to GJ_MAX_COMP runs of consecutive global segment numbers (one run per scan when a
+ * frame is encoded stripe by stripe while it arrives; one run of everything otherwise).  Launch-local number j -> segment. */
+struct SegPick {
+    int n[GJ_MAX_COMP], lo[GJ_MAX_COMP];
+    int total;
+    int zero_status;   // this launch clears k_huff_place's tile status (the first launch of a frame)
+};
+__device__ __forceinline__ int pick_segment(const SegPick& P, int j)
+{
+#pragma unroll
+    for ( int k = 0; k < GJ_MAX_COMP; k++ ) {
+        if ( j < P.n[k] ) return P.lo[k] + j;
+        j -= P.n[k];
+    }
+    return P.lo[0];   // not reached: callers test j < P.total
+}
+
 __global__ void __launch_bounds__(HP_THREADS_MAX)
 k_huff_encode_packed(const int16_t* __restrict__ coef, const uint64_t* __restrict__ nzmask,
-                     const __grid_constant__ gj_scan_layout lay, int seg_mcu, int seg_count, uint8_t* __restrict__ tmp,
-                     size_t slot_stride, uint32_t* __restrict__ seg_bytes, uint32_t* __restrict__ spill_all,
-                     const gj_dev_enc_tables* __restrict__ tables, uint64_t* __restrict__ info,
+                     const __grid_constant__ gj_scan_layout lay, int seg_mcu, const __grid_constant__ SegPick pick,
+                     uint8_t* __restrict__ tmp, size_t slot_stride, uint32_t* __restrict__ seg_bytes,
+                     uint32_t* __restrict__ spill_all, const gj_dev_enc_tables* __restrict__ tables, uint64_t* __restrict__ info,
                      unsigned long long* __restrict__ place_status, int n_status)
 {
     gj_pdl_wait();
-    if ( threadIdx.x == 0 && (int)blockIdx.x < n_status ) place_status[blockIdx.x] = 0ull;   // for k_huff_place, the next launch
+    if ( pick.zero_status )   // for k_huff_place, which runs behind the last launch of the frame
+        for ( int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_status; i += gridDim.x * blockDim.x )
+            place_status[i] = 0ull;
     const uint32_t slot_cap = (uint32_t)slot_stride;
     extern __shared__ __align__(16) uint32_t he_smem[];
     uint32_t (*s_ac)[256] = reinterpret_cast<uint32_t (*)[256]>(he_smem);
@@ -401,8 +420,8 @@ k_huff_encode_packed(const int16_t* __restrict__ coef, const uint64_t* __restric
         const int16_t* head16 = reinterpret_cast<const int16_t*>(head);
         for ( int lb = threadIdx.x; lb < HE_WARPS * segblk; lb += blockDim.x ) {
             const int sl = lb / segblk, j = lb - sl * segblk;
-            const int g = g0 + sl;
-            if ( g >= seg_count ) break;
+            if ( g0 + sl >= pick.total ) break;
+            const int g = pick_segment(pick, g0 + sl);
             const int scan = scan_of_segment(lay, g), s = g - lay.scan_seg_begin[scan];
             const int first_mcu = s * seg_mcu;
             const int nblocks = min(seg_mcu, lay.scan_mcus[scan] - first_mcu) * lay.bpm;
@@ -480,8 +499,8 @@ k_huff_encode_packed(const int16_t* __restrict__ coef, const uint64_t* __restric
     __syncthreads();
 
     /* ---- phase B: one warp per segment ---- */
-    const int g = g0 + warp;
-    if ( warp >= HE_WARPS || g >= seg_count ) return;
+    if ( warp >= HE_WARPS || g0 + warp >= pick.total ) return;
+    const int g = pick_segment(pick, g0 + warp);
     const int scan = scan_of_segment(lay, g), s = g - lay.scan_seg_begin[scan];
     const int nblocks = min(seg_mcu, lay.scan_mcus[scan] - s * seg_mcu) * lay.bpm;
     uint32_t* buf = s_buf + warp * HE_WORDS;
@@ -1042,44 +1061,60 @@ __global__ void k_coef_to_natural(const int16_t* __restrict__ in, int16_t* __res
 
 }  // namespace
 
-extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_stream_t stream)
+/* tile status of k_huff_place's look-back: one word per CP_SEGS segments, in the (otherwise unused) offset array */
+static unsigned long long* place_status_of(const struct gj_huff_enc_args* a) { return reinterpret_cast<unsigned long long*>(a->d_seg_off); }
+
+extern "C" int gj_huffman_encode_parts_eligible(const struct gj_huff_enc_args* a)
+{
+    return a->lay.simple && a->seg_mcu * a->lay.bpm <= HP_MAXBLK;
+}
+
+/* K2 on some of the frame's segments: scan k's segments [lo[k], lo[k] + n[k]) (numbers inside the scan).  `first`: the first
+ * such launch of a frame (clears what the frame accumulates into).  gj_launch_huffman_place finishes the frame.  Short
+ * segments only (gj_huffman_encode_parts_eligible). */
+extern "C" int gj_launch_huffman_encode_part(const struct gj_huff_enc_args* a, int first, const int lo[GJ_MAX_COMP],
+                                             const int n[GJ_MAX_COMP], gj_stream_t stream)
 {
     const int seg_count = a->lay.scan_seg_begin[GJ_MAX_COMP];
-    /* the info block is zero when this launch starts: cleared here, or -- d_info_next given -- by the k_huff_place of the
-     * previous launch (the encoder alternates between two blocks: one memset less in front of every frame) */
-    if ( !a->info_is_zero && cudaMemsetAsync(a->d_info, 0, 32, stream) != cudaSuccess ) return -1;
+    if ( a->seg_mcu * a->lay.bpm > HP_MAXBLK ) return -1;
+    /* the info block is zero when the frame starts: cleared here, or -- d_info_next given -- by the k_huff_place of the
+     * previous frame (the encoder alternates between two blocks: one memset less in front of every frame) */
+    if ( first && !a->info_is_zero && cudaMemsetAsync(a->d_info, 0, 32, stream) != cudaSuccess ) return -1;
+    SegPick pick;
+    pick.total = 0;
+    pick.zero_status = first;
+    for ( int k = 0; k < GJ_MAX_COMP; k++ ) {
+        const bool real = k < a->lay.scan_count;
+        pick.n[k] = real ? n[k] : 0;
+        pick.lo[k] = real ? a->lay.scan_seg_begin[k] + lo[k] : 0;
+        if ( pick.n[k] < 0 || (real && (lo[k] < 0 || pick.lo[k] + pick.n[k] > a->lay.scan_seg_begin[k + 1])) ) return -1;
+        pick.total += pick.n[k];
+    }
+    if ( pick.total == 0 && !first ) return 0;
+    const int n_status = (seg_count + CP_SEGS - 1) / CP_SEGS;
+    static int attr_done_p[64];
+    int dev = 0;
+    if ( cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 ) return -1;
+    if ( !__atomic_load_n(&attr_done_p[dev], __ATOMIC_ACQUIRE) ) {
+        if ( cudaFuncSetAttribute(k_huff_encode_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, HP_SMEM) != cudaSuccess ) return -1;
+        __atomic_store_n(&attr_done_p[dev], 1, __ATOMIC_RELEASE);
+    }
+    /* one thread per block of the CTA's segments: 288 blocks -> 9 warps, all busy in phase A */
+    const int hp_threads = max(HE_WARPS * 32, (HE_WARPS * a->seg_mcu * a->lay.bpm + 31) / 32 * 32);
+    const int ctas = pick.total ? (pick.total + HE_WARPS - 1) / HE_WARPS : 1;   // (an empty first part still clears the status)
+    gj_launch_pdl(k_huff_encode_packed, dim3(ctas), dim3(hp_threads), HP_SMEM, stream, a->d_coef, a->d_nzmask, a->lay, a->seg_mcu, pick,
+                  a->d_tmp, a->slot_stride, a->d_seg_bytes, a->d_spill, a->d_tables, a->d_info, place_status_of(a), n_status);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+/* the tail of K2: every segment to its final offset in the stream */
+extern "C" int gj_launch_huffman_place(const struct gj_huff_enc_args* a, gj_stream_t stream)
+{
+    const int seg_count = a->lay.scan_seg_begin[GJ_MAX_COMP];
+    const int n_status = (seg_count + CP_SEGS - 1) / CP_SEGS;
     ScanSegs segs;
     for ( int k = 0; k <= GJ_MAX_COMP; k++ )
         segs.begin[k] = a->lay.scan_seg_begin[k];
-    /* tile status of k_huff_place's look-back: one word per 32 segments, in the (otherwise unused) offset array; zeroed by
-     * the encoder kernel, whose grid (one CTA per 8 segments) is larger */
-    const int n_status = (seg_count + CP_SEGS - 1) / CP_SEGS;
-    unsigned long long* const place_status = reinterpret_cast<unsigned long long*>(a->d_seg_off);
-    static bool attr_done[64] = {false};
-    int dev = 0;
-    if ( cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 ) return -1;
-    if ( !attr_done[dev] ) {
-        if ( cudaFuncSetAttribute(k_huff_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, HE_SMEM) != cudaSuccess ) return -1;
-        attr_done[dev] = true;
-    }
-    if ( a->seg_mcu * a->lay.bpm <= HP_MAXBLK ) {
-        static bool attr_done_p[64] = {false};
-        if ( !attr_done_p[dev] ) {
-            if ( cudaFuncSetAttribute(k_huff_encode_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, HP_SMEM) != cudaSuccess )
-                return -1;
-            attr_done_p[dev] = true;
-        }
-        /* one thread per block of the CTA's segments: 288 blocks -> 9 warps, all busy in phase A */
-        const int hp_threads = max(HE_WARPS * 32, (HE_WARPS * a->seg_mcu * a->lay.bpm + 31) / 32 * 32);
-        gj_launch_pdl(k_huff_encode_packed, dim3((seg_count + HE_WARPS - 1) / HE_WARPS), dim3(hp_threads), HP_SMEM, stream,
-                      a->d_coef, a->d_nzmask, a->lay, a->seg_mcu, seg_count, a->d_tmp, a->slot_stride, a->d_seg_bytes, a->d_spill,
-                      a->d_tables, a->d_info, place_status, n_status);
-    }
-    else {
-        gj_launch_pdl(k_huff_encode, dim3((seg_count + HE_WARPS - 1) / HE_WARPS), dim3(HE_WARPS * 32), HE_SMEM, stream,
-                      a->d_coef, a->d_nzmask, a->lay, a->seg_mcu, seg_count, a->d_tmp, a->slot_stride, a->d_seg_bytes, a->d_spill,
-                      a->d_tables, a->d_info, place_status, n_status);
-    }
     ScanPrefix pre;
     for ( int k = 0; k < GJ_MAX_COMP; k++ ) {
         pre.len[k] = a->pre_len[k];
@@ -1087,8 +1122,35 @@ extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_str
     }
     gj_launch_pdl(k_huff_place, dim3(n_status), dim3(256), 0, stream, (const uint8_t*)a->d_tmp, a->slot_stride, (const uint32_t*)a->d_seg_bytes,
                   seg_count, segs, a->d_sos, pre, a->header_size, (uint64_t)a->stream_cap, a->d_stream,
-                  (volatile unsigned long long*)place_status, a->d_seg_pos, a->d_info, a->d_info_next);
+                  (volatile unsigned long long*)place_status_of(a), a->d_seg_pos, a->d_info, a->d_info_next);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_stream_t stream)
+{
+    const int seg_count = a->lay.scan_seg_begin[GJ_MAX_COMP];
+    if ( a->seg_mcu * a->lay.bpm <= HP_MAXBLK ) {
+        int lo[GJ_MAX_COMP] = {0, 0, 0, 0}, n[GJ_MAX_COMP] = {0, 0, 0, 0};
+        for ( int k = 0; k < a->lay.scan_count && k < GJ_MAX_COMP; k++ )
+            n[k] = a->lay.scan_seg_begin[k + 1] - a->lay.scan_seg_begin[k];
+        if ( gj_launch_huffman_encode_part(a, 1, lo, n, stream) ) return -1;
+    }
+    else {
+        if ( !a->info_is_zero && cudaMemsetAsync(a->d_info, 0, 32, stream) != cudaSuccess ) return -1;
+        const int n_status = (seg_count + CP_SEGS - 1) / CP_SEGS;
+        static int attr_done[64];
+        int dev = 0;
+        if ( cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 ) return -1;
+        if ( !__atomic_load_n(&attr_done[dev], __ATOMIC_ACQUIRE) ) {
+            if ( cudaFuncSetAttribute(k_huff_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, HE_SMEM) != cudaSuccess ) return -1;
+            __atomic_store_n(&attr_done[dev], 1, __ATOMIC_RELEASE);
+        }
+        gj_launch_pdl(k_huff_encode, dim3((seg_count + HE_WARPS - 1) / HE_WARPS), dim3(HE_WARPS * 32), HE_SMEM, stream,
+                      a->d_coef, a->d_nzmask, a->lay, a->seg_mcu, seg_count, a->d_tmp, a->slot_stride, a->d_seg_bytes, a->d_spill,
+                      a->d_tables, a->d_info, place_status_of(a), n_status);
+        if ( cudaGetLastError() != cudaSuccess ) return -1;
+    }
+    return gj_launch_huffman_place(a, stream);
 }
 
 extern "C" int gj_huffman_decode_sync_eligible(const struct gj_huff_dec_args* a);

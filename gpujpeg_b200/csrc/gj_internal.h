@@ -329,6 +329,12 @@ struct gj_huff_enc_args {
     const struct gj_dev_enc_tables* d_tables;
 };
 int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_stream_t stream);
+/* the same in pieces (the encoder's stripe pipeline): K2 on scan k's segments [lo[k], lo[k] + n[k]) -- `first` marks the first
+ * piece of a frame --, then the tail kernel once; only for frames gj_huffman_encode_parts_eligible() accepts */
+int gj_huffman_encode_parts_eligible(const struct gj_huff_enc_args* a);
+int gj_launch_huffman_encode_part(const struct gj_huff_enc_args* a, int first, const int lo[GJ_MAX_COMP], const int n[GJ_MAX_COMP],
+                                  gj_stream_t stream);
+int gj_launch_huffman_place(const struct gj_huff_enc_args* a, gj_stream_t stream);
 
 /* K3: Huffman-decode every restart segment into zig-zag coefficients
  * [replaces ref: src/gpujpeg_huffman_gpu_decoder.cu:663-746] */

@@ -195,7 +195,7 @@ def test_image_files_through_the_public_api(tmp_path, name, fmt, cs):
 
 
 @pytest.mark.parametrize("w,h,stripes,ss,il", [(1920, 1080, 8, "4:4:4", 0), (1119, 561, 5, "4:4:4", 0), (640, 136, 8, "4:4:4", 0),
-                                               (3840, 2160, 0, "4:4:4", 0), (1119, 561, 7, "4:2:0", 1), (1118, 562, 8, "4:2:0", 0),
+                                               (3840, 2160, 0, "4:4:4", 0), (1119, 561, 7, "4:4:4", 1), (1280, 720, 8, "4:4:4", 1), (1119, 561, 7, "4:2:0", 1), (1118, 562, 8, "4:2:0", 0),
                                                (642, 361, 6, "4:2:2", 1), (640, 300, 4, "4:4:0", 0), (3840, 2160, 0, "4:2:0", 1)])
 def test_stripe_pipeline_of_host_buffers(monkeypatch, w, h, stripes, ss, il):
     """host images of 8 MB or more are copied and transformed stripe by stripe (K1 behind the upload, the download behind K4):
