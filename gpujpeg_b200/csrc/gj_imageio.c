@@ -209,8 +209,10 @@ int gj_imgfile_probe(const char* filename, struct gj_imgfile* f)
         c.p += 9;
         rc = parse_y4m(&c, f);
         if ( rc == 0 ) {
-            f->data_bytes = y4m_payload(f);
-            if ( f->data_bytes == 0 ) rc = -1;
+            if ( f->width > 0 && f->height > 0 && f->width <= 65535 && f->height <= 65535 ) {
+                f->data_bytes = y4m_payload(f);
+                if ( f->data_bytes == 0 ) rc = -1;
+            }
         }
         else fprintf(stderr, "File '%s' doesn't seem to be valid Y4M.\n", filename);
     }
@@ -228,6 +230,15 @@ int gj_imgfile_probe(const char* filename, struct gj_imgfile* f)
         fprintf(stderr, "File '%s' doesn't seem to be valid PAM, PNM or Y4M.\n", filename);
     }
     if ( rc ) return -1;
+    /* nothing a JPEG could hold is larger (and the byte counts below stay far from overflowing) */
+    if ( f->width > 65535 || f->height > 65535 || f->channels > 4 ) {
+        fprintf(stderr, "Image %s is too large (%dx%d, %d channels)!\n", filename, f->width, f->height, f->channels);
+        return -1;
+    }
+    if ( f->kind == GJ_IMGFILE_Y4M && (f->width <= 0 || f->height <= 0) ) {
+        fprintf(stderr, "Unspecified/incorrect size %dx%d!\n", f->width, f->height);
+        return -1;
+    }
     if ( f->kind != GJ_IMGFILE_Y4M ) {   /* [ref: src/utils/pam.c:193-205] */
         if ( f->width <= 0 || f->height <= 0 ) {
             fprintf(stderr, "Unspecified/incorrect size %dx%d!\n", f->width, f->height);

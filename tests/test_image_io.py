@@ -157,6 +157,8 @@ def test_netpbm_headers_with_comments(tmp_path):
     (b"P7\nWIDTH 2\nHEIGHT 2\nMAXVAL 255\nENDHDR\n" + bytes(12), "PAM without DEPTH"),
     (b"P6\n2 2\n255\n" + bytes(5), "samples missing"),
     (b"GIF89a", "not Netpbm"),
+    (b"P7\nWIDTH 2147483647\nHEIGHT 2147483647\nDEPTH 2147483647\nMAXVAL 255\nENDHDR\n" + bytes(64), "sizes whose product wraps"),
+    (b"P6\n70000 2\n255\n" + bytes(64), "wider than a JPEG can be"),
 ])
 def test_netpbm_refused(tmp_path, content, why):
     p = tmp_path / "bad.pnm"
@@ -166,7 +168,7 @@ def test_netpbm_refused(tmp_path, content, why):
     if why != "samples missing":
         rc, _ = _props(p)
         assert rc < 0, why
-    if o.ref is not None and why not in ("16-bit samples", "bitmap"):   # (pam.c reads those; the delegates then refuse everything but 255 levels)
+    if o.ref is not None and why not in ("16-bit samples", "bitmap", "sizes whose product wraps", "wider than a JPEG can be"):   # (pam.c reads those; the delegates then refuse everything but 255 levels)
         m, ptr = PamMeta(), C.c_void_p()
         assert not o.ref.pam_read(str(p).encode(), C.byref(m), C.byref(ptr), _malloc), why
 
@@ -221,7 +223,8 @@ def test_y4m_foreign_headers(tmp_path):
     assert rc == 0 and back.size == n420
     for head, why in ((b"YUV4MPEG2 W6 H4 C420p10\nFRAME\n", "10 bits"), (b"YUV4MPEG2 W6 H4 C444alpha\nFRAME\n", "alpha"),
                       (b"YUV4MPEG2 W6 H4\nFRAME\n", "no chroma tag: the reference does not assume 4:2:0"),
-                      (b"YUV4MPEG2 W6 H4 C420\nFRAME \n", "FRAME with parameters"), (b"YUV4MPEG W6 H4 C420\nFRAME\n", "magic")):
+                      (b"YUV4MPEG2 W6 H4 C420\nFRAME \n", "FRAME with parameters"), (b"YUV4MPEG W6 H4 C420\nFRAME\n", "magic"),
+                      (b"YUV4MPEG2 W2147483647 H2147483647 C444\nFRAME\n", "sizes whose product wraps"), (b"YUV4MPEG2 W0 H4 C444\nFRAME\n", "no width")):
         q = tmp_path / "bad.y4m"
         q.write_bytes(head + bytes(200))
         assert _props(q)[0] < 0, why
