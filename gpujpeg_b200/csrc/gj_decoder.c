@@ -40,6 +40,7 @@ struct gpujpeg_decoder {
     void* ev_stripe[GJ_STRIPES]; void* ev_done;
     int stripes;                  /* GPUJPEG_B200_STRIPES (1 = off), default GJ_STRIPES */
     size_t stripe_min_bytes;      /* GPUJPEG_B200_STRIPE_MIN_BYTES (tests), default GJ_STRIPE_MIN_BYTES */
+    int k3_parts;                 /* GPUJPEG_B200_STRIPES_K3 (0 = K3 on the whole frame first); -1 = not read yet */
     int device;
     int verbose, perf_stats;
     struct gpujpeg_parameters param;
@@ -141,6 +142,7 @@ struct gpujpeg_decoder* gpujpeg_decoder_create_with_params(const struct gpujpeg_
     d->device = gj_cuda_get_device();
     d->sm_count = gj_cuda_sm_count();
     d->req_pixel_format = GPUJPEG_PIXFMT_AUTODETECT;
+    d->k3_parts = -1;
     d->req_color_space = GPUJPEG_CS_DEFAULT;
     if ( d->device < 0 || gj_cuda_malloc((void**)&d->d_tab, sizeof *d->d_tab) ||
          gj_cuda_malloc((void**)&d->d_mk, GJ_MK_WORDS * 4 + GJ_CTA_BYTES0) || gj_cuda_malloc((void**)&d->d_k3_ctr, 32) ||
@@ -403,9 +405,13 @@ static int stripes_usable(struct gpujpeg_decoder* d)
 
 /* K4 stripe by stripe on the coder's stream, D2H of every finished stripe on the copy stream; the coder's stream then waits
  * for the last copy, so that its next synchronisation covers the whole picture */
-static int decode_striped(struct gpujpeg_decoder* d, const int comp_tq[GJ_MAX_COMP], uint8_t* d_out, uint8_t* h_dst, int coef_dequantized)
+static int decode_striped(struct gpujpeg_decoder* d, const int comp_tq[GJ_MAX_COMP], uint8_t* d_out, uint8_t* h_dst, int coef_dequantized,
+                          const struct gj_huff_dec_args* k3 /* NULL: K3 has run on the whole frame */)
 {
     const struct gj_geometry* g = &d->geo;
+    struct gj_huff_dec_args part;
+    int segs_done[GJ_MAX_COMP] = {0, 0, 0, 0};
+    if ( k3 ) part = *k3;
     const int mcu_h = 8 * g->max_vs;                                  /* image rows per MCU row (4:4:4: one block row) */
     const int mcu_rows = (g->bcy + g->max_vs - 1) / g->max_vs;
     for ( int i = 0; i < d->stripes; i++ ) {
@@ -413,6 +419,25 @@ static int decode_striped(struct gpujpeg_decoder* d, const int comp_tq[GJ_MAX_CO
         const size_t row0 = (size_t)my0 * mcu_h, row1 = (size_t)my1 * mcu_h < (size_t)g->height ? (size_t)my1 * mcu_h : (size_t)g->height;
         const size_t off = row0 * (size_t)g->pitch;
         const size_t bytes = (i + 1 == d->stripes ? g->raw_size : row1 * (size_t)g->pitch) - off;
+        if ( k3 ) {
+            /* the segments that hold the blocks of the rows [0, my1), handed over at multiples of 32 segments (whole units of
+             * every lane count); 4:4:4, one scan per component: block position = MCU number in every scan */
+            int any = 0;
+            for ( int k = 0; k < g->scan_count; k++ ) {
+                const int segs = g->lay.scan_seg_begin[k + 1] - g->lay.scan_seg_begin[k];
+                long long hi = i + 1 == d->stripes ? segs : (((long long)my1 * g->bcx + g->seg_mcu - 1) / g->seg_mcu + 31) / 32 * 32;
+                if ( hi > segs ) hi = segs;
+                part.part_seg_lo[k] = segs_done[k];
+                part.part_seg_hi[k] = (int)hi;
+                if ( (int)hi > segs_done[k] ) any = 1;
+                segs_done[k] = (int)hi;
+            }
+            if ( any ) {
+                for ( int k = 0; k < g->scan_count; k++ )   /* (part_seg_hi == 0 means "the whole scan": an empty range at 0 is [0, 0) of nothing) */
+                    if ( part.part_seg_hi[k] == 0 ) part.part_seg_lo[k] = 0;
+                if ( gj_launch_huffman_decode(&part, d->stream) ) return -1;
+            }
+        }
         const int rc = g->lay.simple ? gj_launch_idct_rgb444_rows(d->d_coef, g->bcx, g->bcy, my0, my1, comp_tq, d_out, g->width, g->height,
                                                                   g->pitch, d->idct_flavour, coef_dequantized, &d->h_tab, d->stream)
                                      : gj_launch_idct_rgb_ss_rows(d->d_coef, g->comp, my0, my1, comp_tq, d_out, g->width, g->height, g->pitch,
@@ -936,7 +961,16 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
         if ( resync_segments(d, &st, first_rank, end_rank, scan_cbegin, &ha) ) return GPUJPEG_ERROR;
         d->last_args = ha;
     }
-    if ( gj_launch_huffman_decode(&ha, d->stream) ) {
+    /* host output of a large frame leaves stripe by stripe (decode_striped): K4 per stripe and, where the Huffman decoder can
+     * work on a part of the frame, K3 per stripe as well -- the segments the stripe's rows need, just before its K4 */
+    const int to_host = output->type == GPUJPEG_DECODER_OUTPUT_INTERNAL_BUFFER || output->type == GPUJPEG_DECODER_OUTPUT_CUSTOM_BUFFER;
+    const int striped = to_host && !stats && stripes_usable(d);
+    if ( d->k3_parts < 0 ) {
+        const char* v = getenv("GPUJPEG_B200_STRIPES_K3");
+        d->k3_parts = !(v && v[0] == '0');
+    }
+    const int k3_striped = striped && d->k3_parts && !resync && gj_huffman_decode_parts_eligible(&ha);
+    if ( !k3_striped && gj_launch_huffman_decode(&ha, d->stream) ) {
         GJ_ERR("Huffman decoder launch failed: %s\n", gj_cuda_last_error());
         return GPUJPEG_ERROR;
     }
@@ -955,7 +989,6 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
         GJ_ERR("OpenGL texture output is not supported in this build.\n");
         return GPUJPEG_ERROR;
     }
-    const int to_host = output->type == GPUJPEG_DECODER_OUTPUT_INTERNAL_BUFFER || output->type == GPUJPEG_DECODER_OUTPUT_CUSTOM_BUFFER;
     uint8_t* h_dst = output->data;
     if ( to_host ) {
         if ( output->type == GPUJPEG_DECODER_OUTPUT_INTERNAL_BUFFER ) {
@@ -967,8 +1000,8 @@ int gpujpeg_decoder_decode(struct gpujpeg_decoder* d, uint8_t* image, size_t ima
         }
     }
     int copied = 0;
-    if ( to_host && !stats && stripes_usable(d) ) {
-        if ( decode_striped(d, st.comp_tq, d_out, h_dst, ha.dequantize) ) {
+    if ( striped ) {
+        if ( decode_striped(d, st.comp_tq, d_out, h_dst, ha.dequantize, k3_striped ? &ha : NULL) ) {
             GJ_ERR("Inverse DCT / copy of raw data failed: %s\n", gj_cuda_last_error());
             return GPUJPEG_ERROR;
         }

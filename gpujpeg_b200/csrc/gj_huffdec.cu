@@ -72,6 +72,8 @@ struct SdParams {
     const uint32_t* seg_tab;             // resynchronised streams: {file offset, clean start, clean end} per segment, or NULL
     uint32_t first_rank[GJ_MAX_COMP], scan_cbegin[GJ_MAX_COMP];
     int cta_begin[GJ_MAX_COMP + 1];      // first CTA of every scan
+    int unit_lo[GJ_MAX_COMP], unit_hi[GJ_MAX_COMP];   // the units of scan s this launch works on: [unit_lo, unit_hi) (a frame can be
+                                                       // decoded in several launches, rows first needed first)
     int dynamic;                         // more units than resident warps: warps fetch further units from unit_ctr
     uint32_t* unit_ctr;                  // [scan] next unit to hand out, [4] CTAs that are done; all zero between launches
     uint8_t lanes_log2[GJ_MAX_COMP];     // lanes per segment in scan s
@@ -524,14 +526,15 @@ __device__ __forceinline__ void run_units(const SdParams& P, const int scan, con
     const int slot = lane >> lanes_log2, gl = lane & (lanes - 1);
     const int segblk = P.seg_mcu * L.bpm;
     const int scan_segs = L.scan_seg_begin[scan + 1] - L.scan_seg_begin[scan];
-    const int scan_units = (scan_segs + spu - 1) / spu;
+    const int scan_units = P.unit_hi[scan];            // one past the last unit of this launch
+    const int unit_lo = P.unit_lo[scan];
     /* units are handed out by a counter per scan: the CTAs stay (tables and staging are set up once) and a warp that
      * got a cheap unit simply takes the next one */
     uint32_t* const ctr = P.unit_ctr + scan;
     const int scan_warps = (P.cta_begin[scan + 1] - P.cta_begin[scan]) * nwarps;
-    int unit = ((int)blockIdx.x - P.cta_begin[scan]) * nwarps + warp;   // the first one: no counter needed
+    int unit = unit_lo + ((int)blockIdx.x - P.cta_begin[scan]) * nwarps + warp;   // the first one: no counter needed
     if ( !at_home ) {   // a guest in this scan: every unit comes from the counter
-        if ( lane == 0 ) unit = scan_warps + (int)atomicAdd(ctr, 1u);
+        if ( lane == 0 ) unit = unit_lo + scan_warps + (int)atomicAdd(ctr, 1u);
         unit = __shfl_sync(FULL, unit, 0);
     }
     uint32_t* const tgt = s_tgt + slot * segblk;       // IL only
@@ -543,7 +546,7 @@ __device__ __forceinline__ void run_units(const SdParams& P, const int scan, con
         /* the next one: requested now, needed when this unit is done.  (Not when every unit has a warp of its own:
          * thousands of additions to one address take their time even if nobody waits for the result.) */
         int next_unit = scan_units;
-        if ( P.dynamic && lane == 0 ) next_unit = scan_warps + (int)atomicAdd(ctr, 1u);
+        if ( P.dynamic && lane == 0 ) next_unit = unit_lo + scan_warps + (int)atomicAdd(ctr, 1u);
         const int s = unit * spu + slot;
         const bool valid = s < scan_segs;
 
@@ -809,8 +812,7 @@ k_huff_decode_sync(const __grid_constant__ SdParams P)
         if ( !P.dynamic ) break;
         __syncthreads();   // nobody reads the previous scan's tables any more
         if ( threadIdx.x == 0 ) {
-            const int spu = 32 >> P.lanes_log2[scan];
-            const int units = (L.scan_seg_begin[scan + 1] - L.scan_seg_begin[scan] + spu - 1) / spu;
+            const int units = P.unit_hi[scan] - P.unit_lo[scan];
             const int handed = (P.cta_begin[scan + 1] - P.cta_begin[scan]) * (int)(blockDim.x >> 5) + (int)*(volatile uint32_t*)(P.unit_ctr + scan);
             s_go = handed < units;
         }
@@ -896,6 +898,7 @@ extern "C" int gj_launch_huffman_decode_sync(const struct gj_huff_dec_args* a, g
         P.scan_cbegin[s] = a->scan_cbegin[s];
         P.lanes_log2[s] = 5;
         P.staged[s] = 0;
+        P.unit_lo[s] = P.unit_hi[s] = 0;
         for ( int k = 0; k < GJ_MAX_COMP; k++ ) {
             P.scan_td[s][k] = (int8_t)a->scan_td[s][k];
             P.scan_ta[s][k] = (int8_t)a->scan_ta[s][k];
@@ -908,7 +911,13 @@ extern "C" int gj_launch_huffman_decode_sync(const struct gj_huff_dec_args* a, g
         const int spu = 32 >> l2;
         P.staged[s] = spu <= 2 && a->scan_dense[s];   // dense scans stage in shared memory, sparse ones write through
         const int segs = a->lay.scan_seg_begin[s + 1] - a->lay.scan_seg_begin[s];
-        units[s] = (segs + spu - 1) / spu;
+        const int scan_units = (segs + spu - 1) / spu;
+        /* a part of the frame (the decoder's stripe pipeline): whole units that cover the segments [part_seg_lo, part_seg_hi) */
+        P.unit_lo[s] = a->part_seg_hi[s] ? a->part_seg_lo[s] / spu : 0;
+        P.unit_hi[s] = a->part_seg_hi[s] ? (a->part_seg_hi[s] + spu - 1) / spu : scan_units;
+        if ( P.unit_hi[s] > scan_units ) P.unit_hi[s] = scan_units;
+        if ( P.unit_lo[s] > P.unit_hi[s] ) P.unit_lo[s] = P.unit_hi[s];
+        units[s] = P.unit_hi[s] - P.unit_lo[s];
         total_units += units[s];
         /* staging area for a unit's clean bytes: twice the scan's average, so that nearly every unit fits */
         const size_t want = 2 * ((size_t)a->scan_bytes[s] / (size_t)(segs > 0 ? segs : 1) + 16) * (size_t)spu + 64;

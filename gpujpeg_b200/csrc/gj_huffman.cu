@@ -1156,6 +1156,13 @@ extern "C" int gj_launch_huffman_encode(const struct gj_huff_enc_args* a, gj_str
 extern "C" int gj_huffman_decode_sync_eligible(const struct gj_huff_dec_args* a);
 extern "C" int gj_launch_huffman_decode_sync(const struct gj_huff_dec_args* a, gj_stream_t stream);
 
+/* can the frame be decoded in several launches (part_seg_lo / part_seg_hi of the arguments)?  The self-synchronising kernel on
+ * 4:4:4 frames with one scan per component, positions from the marker list */
+extern "C" int gj_huffman_decode_parts_eligible(const struct gj_huff_dec_args* a)
+{
+    return !a->force_thread_per_segment && gj_huffman_decode_sync_eligible(a) && !a->d_seg_tab && a->lay.simple && !a->lay.interleaved;
+}
+
 extern "C" int gj_launch_huffman_decode(const struct gj_huff_dec_args* a, gj_stream_t stream)
 {
     /* restart segments of at most 40 blocks (every RESTART_AUTO setting): several lanes per segment, self-synchronising

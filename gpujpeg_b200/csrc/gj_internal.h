@@ -365,6 +365,10 @@ struct gj_huff_dec_args {
     uint32_t scan_bytes[GJ_MAX_COMP];  /* entropy-coded bytes of scan s (as in the file) */
     uint8_t scan_dense[GJ_MAX_COMP];   /* >= 16 bytes of entropy-coded data per block: worth staging blocks in shared memory */
     int force_thread_per_segment;   /* dec_opt_huffman=thread_per_segment: always the one-thread-per-segment kernel */
+    /* the decoder's stripe pipeline (self-synchronising kernel only): this launch decodes scan s's segments
+     * [part_seg_lo[s], part_seg_hi[s]) -- rounded outwards to whole units, so launches must hand over at multiples of 32
+     * segments --, part_seg_hi[s] == 0: all of the scan */
+    int part_seg_lo[GJ_MAX_COMP], part_seg_hi[GJ_MAX_COMP];
     int dequantize;             /* 1: store coefficient*quantiser wrapped to int16 (integer IDCT flavour) */
     struct gj_scan_layout lay;  /* scans, segments and the block order inside them */
     int seg_count, seg_mcu;
@@ -375,6 +379,7 @@ struct gj_huff_dec_args {
     const struct gj_dev_dec_tables* d_tables;
 };
 int gj_launch_huffman_decode(const struct gj_huff_dec_args* a, gj_stream_t stream);
+int gj_huffman_decode_parts_eligible(const struct gj_huff_dec_args* a);   /* part_seg_lo / part_seg_hi may be used */
 
 /* K0: marker list of the entropy-coded part of the file, built on the device (gj_markers.cu)
  * [replaces ref: src/gpujpeg_reader.c:1038-1155] */
