@@ -645,7 +645,8 @@ def main():
                     "workers": used_workers,
                     "how": "gpujpeg_encoder_encode + gpujpeg_decoder_decode with pinned host buffers, strictly serial calls on "
                            "one coder pair (the reference's `gpujpegtool -n` method); pipelined_* = the same calls from %d "
-                           "host threads, one coder pair and one CUDA stream each" % workers,
+                           "host threads, one coder pair and one CUDA stream each.  Inside a call the library moves the frame in "
+                           "8 stripes and runs its kernels stripe by stripe behind the copy (DESIGN.md section 5)" % workers,
                     "serial_value": round(world * npix / (e2e_sync_ms * 1e-3) / 1e6, 1), "serial_ms_per_step": round(e2e_sync_ms, 3),
                     "pipelined_value": round(world * npix / (e2e_pipe_ms * 1e-3) / 1e6, 1) if e2e_pipe_ms else None,
                     "pipelined_ms_per_step": round(e2e_pipe_ms, 3) if e2e_pipe_ms else None, "pipelined_workers": workers},
