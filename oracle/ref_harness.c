@@ -291,8 +291,8 @@ int ref_huff_decode_ss(const uint8_t* data, size_t data_size, int w, int h, int 
         }
     }
     for ( int c = 0; c < comps; c++ ) {
-        dec->comp_table_huffman_map[c][GPUJPEG_HUFFMAN_DC] = c == 0 ? 0 : 1;
-        dec->comp_table_huffman_map[c][GPUJPEG_HUFFMAN_AC] = c == 0 ? 0 : 1;
+        dec->comp_table_huffman_map[c][GPUJPEG_HUFFMAN_DC] = (c == 0 || c == 3) ? 0 : 1;   /* what the reader takes from the SOS selectors; a fourth component codes like luminance */
+        dec->comp_table_huffman_map[c][GPUJPEG_HUFFMAN_AC] = (c == 0 || c == 3) ? 0 : 1;
     }
     int rc = gpujpeg_huffman_cpu_decoder_decode(dec);
     free(g.seg);

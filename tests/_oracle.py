@@ -95,11 +95,12 @@ SAMPLINGS = {"444": (1, 1), "422": (2, 1), "420": (2, 2), "440": (1, 2)}
 
 def plane_geometry(w, h, sampling=(1, 1), interleaved=0, comps=3):
     """Per-component (data_width, data_height) as the reference lays the planes out
-    [ref: src/gpujpeg_common.c:671-736]: luminance carries the sampling factors, chrominance is 1x1."""
+    [ref: src/gpujpeg_common.c:671-736]: luminance (and a fourth, alpha, component) carries the sampling factors,
+    chrominance is 1x1."""
     mh, mv = sampling
     out = []
     for c in range(comps):
-        hs, vs = (mh, mv) if c == 0 else (1, 1)
+        hs, vs = (mh, mv) if c in (0, 3) else (1, 1)
         dh_, dv_ = mh // hs, mv // vs
         cw = (w + dh_ - 1) // dh_ * dh_ * hs // mh
         ch = (h + dv_ - 1) // dv_ * dv_ * vs // mv

@@ -44,6 +44,10 @@ def test_four_component_stream_bytes(w, h, q, rst, il, sampling, internal):
     else:
         n = o.ref.ref_encode_from_coef_ss(coef, w, h, 4, q, rst, il, sampling[0], sampling[1], out, out.size)
     assert n > 0 and np.array_equal(out[:n], jpeg), "oracle bytes != reference header writer + CPU Huffman encoder"
+    if internal != o.CS_RGB:   # and back: the reference's CPU Huffman decoder recovers the coefficients of all four components
+        from _refcpu import ref_decode_coef
+        ref_coef = ref_decode_coef(jpeg, w, h, rst, il, comps=4, sampling=sampling)
+        assert np.array_equal(ref_coef.reshape(-1), coef), "reference CPU Huffman decoder != oracle coefficients"
     back = o.decode_any(jpeg, o.FMT_4444_P0123, o.CS_RGB).reshape(h, w, 4).astype(int)
     assert np.abs(back[:, :, :3] - img[:, :, :3]).mean() < 14 and np.abs(back[:, :, 3] - img[:, :, 3]).mean() < 8
     # without alpha on the way out: the colour samples are the same
